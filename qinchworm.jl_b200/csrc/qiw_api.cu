@@ -1,0 +1,814 @@
+// qiw_api.cu — C-ABI entry points of libqinchworm_cuda.so (include/qinchworm.h) and the runtime
+// behind them: device-resident model tables, compiled entries, launch planning, NCCL.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/qinchworm.h"
+#include "qiw_device.cuh"
+#include "qiw_host.hpp"
+
+namespace qiw {
+cudaError_t launch_scalar_step(int maxl, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_reduce(const DevEntryDyn* dyn, const int* entry_ids, const double2* partials,
+                          const int* rows_per_item, int S, double2* out, int n_entries, cudaStream_t st);
+cudaError_t launch_sobol_points(int D, const uint32_t* m, const uint32_t* x0, unsigned long long start,
+                                unsigned long long count, uint32_t* out, cudaStream_t st);
+cudaError_t launch_dfma_peak(double* out, int blocks, int iters, cudaStream_t st);
+}  // namespace qiw
+
+using namespace qiw;
+
+// ---- NCCL through dlopen (no link-time dependency: the library must load on a CPU-only box) ----
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct Nccl {
+    void* h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string err;
+    bool load() {
+        if (h) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+        if (!h) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+        GetUniqueId = (int (*)(ncclUniqueId*))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+        CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+        AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+        GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { err = "libnccl lacks required symbols"; return false; }
+        return true;
+    }
+};
+Nccl g_nccl;
+constexpr int kNcclDouble = 8;  // ncclFloat64
+constexpr int kNcclSum = 0;
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(n, (size_t)16);
+        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    cudaError_t upload(const T* src, size_t n, cudaStream_t st) {
+        cudaError_t e = reserve(n);
+        if (e != cudaSuccess || n == 0) return e;
+        return cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct EntryDev {
+    EntryProgram prog;
+    bool valid = false;
+    DevBuf<uint64_t> words;
+    DevBuf<uint32_t> tree_off;
+    DevBuf<double2> coefs;
+    DevBuf<int4> dslots;
+    DevBuf<uint32_t> sobol;   // m[D][32] + x0[D] of the current call
+    std::vector<uint32_t> default_sobol;
+};
+
+struct Plan {   // launch plan of one qiw_eval call shape, cached
+    std::vector<int> ids;
+    uint64_t count = 0;
+    bool explicit_mode = false;
+    struct Group { int maxl; int item0, n_items; int grid_x; size_t smem; int max_slots; };
+    std::vector<Group> groups;
+    std::vector<WorkItem> items;
+    std::vector<uint32_t> chunk_tree0;
+    std::vector<int> entry_chunk_base;     // indexed by entry id
+    std::vector<int> rows_per_item;        // per call entry
+    std::vector<int> item0, n_items;       // per call entry
+    size_t partial_rows = 0;
+    uint64_t max_sb = 1;
+    int pitch = 1;
+    DevBuf<uint32_t> d_sobol;
+    std::vector<size_t> sobol_off;         // per call entry, offset into d_sobol
+    std::vector<uint32_t> h_sobol;
+    bool default_sobol_resident = false;
+    DevBuf<WorkItem> d_items;
+    DevBuf<uint32_t> d_chunk_tree0;
+    DevBuf<int> d_entry_chunk_base, d_rows_per_item, d_ids;
+};
+}  // namespace
+
+struct qiw_context {
+    int device = 0;
+    bool no_device = false;   // QIW_DEVICE_NONE: planning only
+    int warps = 8;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    HostModel model;
+    bool have_model = false;
+    int n_tau = 0;
+    double beta = 0;
+    std::vector<cplx> hostP;
+    DevBuf<double2> dP;
+    DevBuf<double> dE;
+    struct Table { int kind = 0, n = 0; double beta = 0; DevBuf<double2> y, M; };
+    std::vector<Table> tables;
+    DevBuf<DevDelta> dDeltas;
+    bool deltas_dirty = true;
+    std::vector<std::unique_ptr<EntryDev>> entries;
+    DevBuf<DevEntry> dEntries;
+    bool entries_dirty = true;
+    DevBuf<DevEntryDyn> dDyn;
+    std::vector<DevEntryDyn> hDyn;
+    DevBuf<double2> dPartials, dOut, dPerSample;
+    DevBuf<double> dTimes;
+    double2* hOut = nullptr;  // pinned
+    size_t hOutCap = 0;
+    std::unique_ptr<Plan> plan;
+    double last_ms = 0;
+    int64_t launches = 0;
+    // NCCL
+    ncclComm_t comm = nullptr;
+    int n_ranks = 1, rank = 0;
+};
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                   \
+            return QIW_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+static int fail(qiw_context* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+extern "C" {
+
+const char* qiw_version(void) { return "0.1.0"; }
+
+int qiw_create(const qiw_options* opts, qiw_context** out) {
+    if (!out) return QIW_ERR_BAD_ARG;
+    *out = nullptr;
+    if (opts && opts->device == QIW_DEVICE_NONE) {
+        qiw_context* c = new qiw_context();
+        c->no_device = true;
+        c->device = QIW_DEVICE_NONE;
+        *out = c;
+        return QIW_OK;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        // no CPU fallback by design
+        fprintf(stderr, "libqinchworm_cuda: no CUDA device available (%s); this library has no CPU path\n",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return QIW_ERR_CUDA;
+    }
+    qiw_context* ctx = new qiw_context();
+    int dev = -1;
+    if (opts) { dev = opts->device; if (opts->warps_per_block > 0) ctx->warps = std::min(8, opts->warps_per_block); }
+    if (dev < 0) cudaGetDevice(&dev);
+    ctx->device = dev;
+    if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return QIW_ERR_CUDA;
+    }
+    *out = ctx;
+    return QIW_OK;
+}
+
+int qiw_destroy(qiw_context* ctx) {
+    if (!ctx) return QIW_OK;
+    if (ctx->no_device) { delete ctx; return QIW_OK; }
+    cudaSetDevice(ctx->device);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->dP.release(); ctx->dE.release(); ctx->dDeltas.release(); ctx->dEntries.release(); ctx->dDyn.release();
+    ctx->dPartials.release(); ctx->dOut.release(); ctx->dPerSample.release(); ctx->dTimes.release();
+    for (auto& t : ctx->tables) { t.y.release(); t.M.release(); }
+    for (auto& e : ctx->entries)
+        if (e) { e->words.release(); e->tree_off.release(); e->coefs.release(); e->dslots.release(); e->sobol.release(); }
+    if (ctx->plan) {
+        ctx->plan->d_items.release(); ctx->plan->d_chunk_tree0.release(); ctx->plan->d_entry_chunk_base.release();
+        ctx->plan->d_rows_per_item.release(); ctx->plan->d_ids.release(); ctx->plan->d_sobol.release();
+    }
+    if (ctx->hOut) cudaFreeHost(ctx->hOut);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return QIW_OK;
+}
+
+const char* qiw_last_error(const qiw_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int qiw_set_model(qiw_context* ctx, int32_t S, const int32_t* dims, const double* energies, int32_t n_ops,
+                  const int32_t* op_target, const int64_t* op_mat_off, const double* op_pool, int32_t n_pairs,
+                  const int32_t* pair_op_i, const int32_t* pair_op_f, const int32_t* pair_table, int32_t n_corr,
+                  const int32_t* corr_A, const int32_t* corr_B) {
+    if (!ctx || S <= 0 || !dims || !energies || n_ops < 0 || n_pairs < 0) return fail(ctx, QIW_ERR_BAD_ARG, "qiw_set_model: bad argument");
+    HostModel& m = ctx->model;
+    m = HostModel();
+    m.S = S;
+    m.dim.assign(dims, dims + S);
+    m.boff.resize(S); m.eoff.resize(S);
+    int off = 0, eoff = 0;
+    m.scalar = true; m.maxdim = 0;
+    for (int s = 0; s < S; ++s) {
+        if (dims[s] <= 0) return fail(ctx, QIW_ERR_BAD_ARG, "qiw_set_model: non-positive sector dimension");
+        m.boff[s] = off; off += dims[s] * dims[s];
+        m.eoff[s] = eoff; eoff += dims[s];
+        if (dims[s] != 1) m.scalar = false;
+        m.maxdim = std::max(m.maxdim, (int)dims[s]);
+    }
+    m.bsize = off;
+    m.energies.assign(energies, energies + eoff);
+    m.n_ops = n_ops;
+    m.op_target.assign(op_target, op_target + (size_t)n_ops * S);
+    m.op_off.assign(op_mat_off, op_mat_off + (size_t)n_ops * S);
+    size_t pool_n = 0;
+    for (int o = 0; o < n_ops; ++o)
+        for (int s = 0; s < S; ++s) {
+            int t = m.op_target[(size_t)o * S + s];
+            if (t >= S) return fail(ctx, QIW_ERR_BAD_ARG, "qiw_set_model: operator target out of range");
+            if (t >= 0) pool_n = std::max(pool_n, (size_t)m.op_off[(size_t)o * S + s] + (size_t)dims[t] * dims[s]);
+        }
+    m.pool.resize(pool_n);
+    for (size_t k = 0; k < pool_n; ++k) m.pool[k] = cplx(op_pool[2 * k], op_pool[2 * k + 1]);
+    m.pair_op_i.assign(pair_op_i, pair_op_i + n_pairs);
+    m.pair_op_f.assign(pair_op_f, pair_op_f + n_pairs);
+    m.pair_table.assign(pair_table, pair_table + n_pairs);
+    for (int p = 0; p < n_pairs; ++p)
+        if (pair_op_i[p] < 0 || pair_op_i[p] >= n_ops || pair_op_f[p] < 0 || pair_op_f[p] >= n_ops || pair_table[p] < 0 ||
+            pair_table[p] >= kMaxTables)
+            return fail(ctx, QIW_ERR_BAD_ARG, "qiw_set_model: bad interaction pair");
+    m.attachable.assign(S, {});
+    for (int s = 0; s < S; ++s)  // findall(op -> haskey(op[1], s), pair_operator_mat), src/expansion.jl:180-183
+        for (int p = 0; p < n_pairs; ++p)
+            if (m.target(pair_op_i[p], s) >= 0) m.attachable[s].push_back(p);
+    m.corr_A.assign(corr_A, corr_A + n_corr);
+    m.corr_B.assign(corr_B, corr_B + n_corr);
+    ctx->have_model = true;
+    if (!ctx->no_device) {
+        cudaSetDevice(ctx->device);
+        CK(ctx->dE.upload(m.energies.data(), m.energies.size(), ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    for (auto& e : ctx->entries) if (e) e->valid = false;   // programs depend on the model
+    ctx->entries_dirty = true;
+    ctx->plan.reset();
+    return QIW_OK;
+}
+
+int qiw_set_grid(qiw_context* ctx, int32_t n_tau, double beta) {
+    if (!ctx || !ctx->have_model || n_tau < 2 || !(beta > 0)) return fail(ctx, QIW_ERR_BAD_ARG, "qiw_set_grid: bad argument (model first)");
+    if (ctx->no_device) { ctx->n_tau = n_tau; ctx->beta = beta; return QIW_OK; }
+    cudaSetDevice(ctx->device);
+    ctx->n_tau = n_tau; ctx->beta = beta;
+    ctx->hostP.assign((size_t)n_tau * ctx->model.bsize, cplx(0));
+    CK(ctx->dP.reserve((size_t)n_tau * ctx->model.bsize));
+    CK(cudaMemsetAsync(ctx->dP.p, 0, (size_t)n_tau * ctx->model.bsize * sizeof(double2), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return QIW_OK;
+}
+
+int qiw_set_delta(qiw_context* ctx, int32_t id, int32_t kind, int32_t n, double beta, const double* values) {
+    if (!ctx || id < 0 || id >= kMaxTables || n < 2 || !values || (kind != 0 && kind != 1))
+        return fail(ctx, QIW_ERR_BAD_ARG, "qiw_set_delta: bad argument");
+    if (ctx->no_device) return fail(ctx, QIW_ERR_CUDA, "planning-only context has no device tables");
+    cudaSetDevice(ctx->device);
+    if ((int)ctx->tables.size() <= id) ctx->tables.resize(id + 1);
+    auto& t = ctx->tables[id];
+    t.kind = kind; t.n = n; t.beta = beta;
+    std::vector<cplx> y(n), M(n);
+    for (int k = 0; k < n; ++k) y[k] = cplx(values[2 * k], values[2 * k + 1]);
+    natural_spline_second_derivatives(n, beta / (n - 1), y.data(), M.data());
+    CK(t.y.upload((const double2*)y.data(), n, ctx->stream));
+    CK(t.M.upload((const double2*)M.data(), n, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->deltas_dirty = true;
+    return QIW_OK;
+}
+
+int qiw_set_P(qiw_context* ctx, int32_t first, int32_t count, const double* rows) {
+    if (!ctx || ctx->n_tau == 0 || first < 0 || count < 0 || first + count > ctx->n_tau || !rows)
+        return fail(ctx, QIW_ERR_BAD_ARG, "qiw_set_P: bad argument (grid first)");
+    if (ctx->no_device) return fail(ctx, QIW_ERR_CUDA, "planning-only context has no device tables");
+    cudaSetDevice(ctx->device);
+    const size_t bs = ctx->model.bsize;
+    CK(cudaMemcpyAsync(ctx->dP.p + (size_t)first * bs, rows, (size_t)count * bs * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return QIW_OK;
+}
+
+int qiw_get_P(qiw_context* ctx, int32_t first, int32_t count, double* rows) {
+    if (!ctx || ctx->n_tau == 0 || first < 0 || count < 0 || first + count > ctx->n_tau || !rows)
+        return fail(ctx, QIW_ERR_BAD_ARG, "qiw_get_P: bad argument");
+    if (ctx->no_device) return fail(ctx, QIW_ERR_CUDA, "planning-only context has no device tables");
+    cudaSetDevice(ctx->device);
+    const size_t bs = ctx->model.bsize;
+    CK(cudaMemcpyAsync(rows, ctx->dP.p + (size_t)first * bs, (size_t)count * bs * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return QIW_OK;
+}
+
+int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t order, int32_t n_pts_after,
+                       int32_t corr_idx, int32_t n_top, const int32_t* pairs, const int32_t* parity) {
+    if (!ctx || !ctx->have_model || entry_id < 0 || entry_id > 4095 || n_top < 0 || (n_top > 0 && (!parity || (order > 0 && !pairs))))
+        return fail(ctx, QIW_ERR_BAD_ARG, "qiw_set_topologies: bad argument (model first)");
+    if (!ctx->no_device) cudaSetDevice(ctx->device);
+    if ((int)ctx->entries.size() <= entry_id) ctx->entries.resize(entry_id + 1);
+    if (!ctx->entries[entry_id]) ctx->entries[entry_id].reset(new EntryDev());
+    EntryDev& ed = *ctx->entries[entry_id];
+    ed.valid = false;
+    std::string err;
+    int rc = compile_entry(ctx->model, mode, order, n_pts_after, corr_idx, n_top, pairs, parity, ed.prog, err);
+    if (rc) return fail(ctx, rc, "qiw_set_topologies: " + err);
+    const EntryProgram& pr = ed.prog;
+    if (ctx->no_device) { ed.valid = true; return QIW_OK; }
+    CK(ed.words.upload(pr.words.data(), pr.words.size(), ctx->stream));
+    CK(ed.tree_off.upload(pr.tree_off.data(), pr.tree_off.size(), ctx->stream));
+    std::vector<double2> cf(std::max<size_t>(pr.coefs.size(), 1));
+    for (size_t k = 0; k < pr.coefs.size(); ++k) cf[k] = make_double2(pr.coefs[k].real(), pr.coefs[k].imag());
+    CK(ed.coefs.upload(cf.data(), cf.size(), ctx->stream));
+    std::vector<int4> ds(std::max<size_t>(pr.dslots.size(), 1));
+    for (size_t k = 0; k < pr.dslots.size(); ++k) ds[k] = make_int4(pr.dslots[k].pos_tail, pr.dslots[k].pos_head, pr.dslots[k].table, 0);
+    CK(ed.dslots.upload(ds.data(), ds.size(), ctx->stream));
+    ed.default_sobol.assign((size_t)pr.D * 33 + 1, 0u);
+    if (pr.D > 0 && sobol_direction_numbers(pr.D, ed.default_sobol.data())) return fail(ctx, QIW_ERR_BAD_ARG, "Sobol dimension too large");
+    CK(ed.sobol.reserve((size_t)pr.D * 33 + 1));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ed.valid = true;
+    ctx->entries_dirty = true;
+    ctx->plan.reset();
+    return QIW_OK;
+}
+
+int qiw_entry_stats(qiw_context* ctx, int32_t id, int64_t* n_top, int64_t* n_leaves, int64_t* n_edges, double* flops) {
+    if (!ctx || id < 0 || id >= (int)ctx->entries.size() || !ctx->entries[id] || !ctx->entries[id]->valid)
+        return fail(ctx, QIW_ERR_BAD_ARG, "qiw_entry_stats: unknown entry");
+    const EntryProgram& p = ctx->entries[id]->prog;
+    if (n_top) *n_top = p.n_top;
+    if (n_leaves) *n_leaves = p.n_leaves;
+    if (n_edges) *n_edges = p.n_edges;
+    if (flops) *flops = p.flops_per_sample;
+    return QIW_OK;
+}
+
+int qiw_entry_program(qiw_context* ctx, int32_t id, int64_t* n_words, uint64_t* words, int64_t* n_trees,
+                      uint32_t* tree_off, int64_t* n_coefs, double* coefs, int64_t* n_dslots, int32_t* dslots,
+                      int32_t* pos_src, int32_t* info) {
+    if (!ctx || id < 0 || id >= (int)ctx->entries.size() || !ctx->entries[id] || !ctx->entries[id]->valid)
+        return fail(ctx, QIW_ERR_BAD_ARG, "qiw_entry_program: unknown entry");
+    const EntryProgram& p = ctx->entries[id]->prog;
+    if (n_words) *n_words = (int64_t)p.words.size();
+    if (n_trees) *n_trees = (int64_t)p.tree_off.size() - 1;
+    if (n_coefs) *n_coefs = (int64_t)p.coefs.size();
+    if (n_dslots) *n_dslots = (int64_t)p.dslots.size();
+    if (words) memcpy(words, p.words.data(), p.words.size() * sizeof(uint64_t));
+    if (tree_off) memcpy(tree_off, p.tree_off.data(), p.tree_off.size() * sizeof(uint32_t));
+    if (coefs) for (size_t k = 0; k < p.coefs.size(); ++k) { coefs[2 * k] = p.coefs[k].real(); coefs[2 * k + 1] = p.coefs[k].imag(); }
+    if (dslots) for (size_t k = 0; k < p.dslots.size(); ++k) { dslots[3 * k] = p.dslots[k].pos_tail; dslots[3 * k + 1] = p.dslots[k].pos_head; dslots[3 * k + 2] = p.dslots[k].table; }
+    if (pos_src) for (int k = 0; k <= kMaxNodes; ++k) pos_src[k] = p.pos_src[k];
+    if (info) { info[0] = p.n_nodes; info[1] = p.nP; info[2] = ctx->model.S; info[3] = p.scalar ? 1 : 0; }
+    return QIW_OK;
+}
+
+}  // extern "C"
+
+// ---- launch planning ---------------------------------------------------------------------------
+
+static int maxl_class(int n_nodes) { return n_nodes <= 7 ? 7 : n_nodes <= 11 ? 11 : n_nodes <= 15 ? 15 : 19; }
+
+static int sync_static_tables(qiw_context* ctx) {
+    if (ctx->deltas_dirty) {
+        std::vector<DevDelta> dd(std::max<size_t>(ctx->tables.size(), 1));
+        for (size_t t = 0; t < ctx->tables.size(); ++t) {
+            auto& tb = ctx->tables[t];
+            dd[t].y = tb.y.p; dd[t].M = tb.M.p; dd[t].kind = tb.kind; dd[t].n = tb.n;
+            dd[t].h = tb.n > 1 ? tb.beta / (tb.n - 1) : 1.0;
+        }
+        CK(ctx->dDeltas.upload(dd.data(), dd.size(), ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->deltas_dirty = false;
+    }
+    if (ctx->entries_dirty) {
+        std::vector<DevEntry> de(std::max<size_t>(ctx->entries.size(), 1));
+        memset(de.data(), 0, de.size() * sizeof(DevEntry));
+        for (size_t i = 0; i < ctx->entries.size(); ++i) {
+            if (!ctx->entries[i] || !ctx->entries[i]->valid) continue;
+            EntryDev& ed = *ctx->entries[i];
+            const EntryProgram& p = ed.prog;
+            DevEntry& d = de[i];
+            d.mode = p.mode; d.order = p.order; d.n_nodes = p.n_nodes; d.D = p.D;
+            d.d_after = (p.mode == 0) ? p.D : p.n_pts_after;
+            d.d_before = p.D - d.d_after;
+            d.nP = p.nP; d.nD = (int)p.dslots.size();
+            d.n_trees = (int)p.tree_off.size() - 1;
+            d.exact = (p.order == 0);
+            for (int k = 0; k <= kDevMaxNodes; ++k) d.pos_src[k] = p.pos_src[k];
+            d.words = ed.words.p; d.tree_off = ed.tree_off.p; d.coefs = ed.coefs.p; d.dslots = ed.dslots.p;
+        }
+        CK(ctx->dEntries.upload(de.data(), de.size(), ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->entries_dirty = false;
+        ctx->hDyn.assign(std::max<size_t>(ctx->entries.size(), 1), DevEntryDyn());
+        CK(ctx->dDyn.reserve(ctx->hDyn.size()));
+    }
+    return QIW_OK;
+}
+
+// Splits every entry's trees into chunks of similar cost and groups chunks into CTA jobs.
+static int build_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_t count, bool explicit_mode) {
+    std::unique_ptr<Plan> pl(new Plan());
+    pl->ids.assign(ids, ids + n_entries);
+    pl->count = count; pl->explicit_mode = explicit_mode;
+    const int W = ctx->warps;
+    const int S = ctx->model.S;
+    int ndev_sm = 148;
+    cudaDeviceGetAttribute(&ndev_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+    // total cost in (edges x sample blocks) to size the chunks
+    double total = 0;
+    for (int i = 0; i < n_entries; ++i) {
+        const EntryProgram& p = ctx->entries[ids[i]]->prog;
+        const uint64_t c = p.order == 0 ? 1 : count;
+        total += (double)p.n_edges * (double)((c + 31) / 32);
+    }
+    const double target_tasks = (double)ndev_sm * 32.0;
+    const double cost_per_task = std::max(192.0, total / target_tasks);
+    pl->entry_chunk_base.assign(ctx->entries.size(), 0);
+    pl->rows_per_item.resize(n_entries); pl->item0.resize(n_entries); pl->n_items.resize(n_entries);
+    std::map<int, std::vector<int>> by_class;
+    for (int i = 0; i < n_entries; ++i) by_class[maxl_class(ctx->entries[ids[i]]->prog.n_nodes)].push_back(i);
+    for (auto& kv : by_class) {
+        Plan::Group g;
+        g.maxl = kv.first; g.item0 = (int)pl->items.size(); g.max_slots = 1;
+        uint64_t max_sb = 1;
+        for (int i : kv.second) {
+            const EntryProgram& p = ctx->entries[ids[i]]->prog;
+            const int n_trees = (int)p.tree_off.size() - 1;
+            const uint64_t c = p.order == 0 ? 1 : count;
+            const uint64_t n_sb = (c + 31) / 32;
+            max_sb = std::max(max_sb, n_sb);
+            int n_chunks = 1;
+            if (!explicit_mode && n_trees > 0) {
+                double per_sb_tasks = std::ceil((double)p.n_edges / cost_per_task);
+                n_chunks = (int)std::min<double>(n_trees, std::max<double>(std::min(W, n_trees), per_sb_tasks));
+                if (n_chunks > W) n_chunks = ((n_chunks + W - 1) / W) * W;   // full CTAs
+                n_chunks = std::min(n_chunks, n_trees);
+            }
+            // boundaries by cumulative tree cost
+            pl->entry_chunk_base[ids[i]] = (int)pl->chunk_tree0.size();
+            double tot = 0;
+            for (int t = 0; t < n_trees; ++t) tot += p.tree_cost[t];
+            double acc = 0;
+            int c_done = 0;
+            pl->chunk_tree0.push_back(0);
+            for (int t = 0; t < n_trees; ++t) {
+                acc += p.tree_cost[t];
+                while (c_done + 1 < n_chunks && acc >= tot * (double)(c_done + 1) / n_chunks && t + 1 <= n_trees - (n_chunks - c_done - 1)) {
+                    pl->chunk_tree0.push_back((uint32_t)(t + 1));
+                    ++c_done;
+                }
+            }
+            while (c_done + 1 < n_chunks) { pl->chunk_tree0.push_back((uint32_t)n_trees); ++c_done; }
+            pl->chunk_tree0.push_back((uint32_t)n_trees);
+            pl->item0[i] = (int)pl->items.size();
+            for (int c0 = 0; c0 < n_chunks; c0 += W) {
+                WorkItem it;
+                it.entry = ids[i]; it.chunk0 = c0; it.n_chunks = std::min(W, n_chunks - c0);
+                it.partial0 = (int)pl->items.size();
+                pl->items.push_back(it);
+            }
+            pl->n_items[i] = (int)pl->items.size() - pl->item0[i];
+            g.max_slots = std::max(g.max_slots, p.nP + (int)p.dslots.size());
+        }
+        g.n_items = (int)pl->items.size() - g.item0;
+        g.grid_x = 1;
+        g.max_slots = std::max(g.max_slots, (S * W + 31) / 32 + 1);
+        g.smem = (size_t)g.max_slots * 32 * sizeof(double2) + (size_t)S * W * 32 * sizeof(double2) +
+                 (size_t)(kDevMaxNodes + 1) * 32 * sizeof(double) + (size_t)kDevMaxDim * 32 * sizeof(double) + 32 * sizeof(int);
+        if (g.smem > 227 * 1024) return fail(ctx, QIW_ERR_UNSUPPORTED, "per-sample tables exceed shared memory (too many sectors for the scalar kernel)");
+        pl->max_sb = std::max(pl->max_sb, max_sb);
+        pl->groups.push_back(g);
+    }
+    // grid.x (common to all groups = row pitch of the partials buffer): enough sample-block
+    // columns to fill the machine a few times over; the kernel strides over the remaining blocks
+    {
+        const uint64_t want_ctas = (uint64_t)ndev_sm * 8;
+        uint64_t gx = std::max<uint64_t>(1, want_ctas / std::max<size_t>(1, pl->items.size()));
+        pl->pitch = (int)std::min<uint64_t>(pl->max_sb, std::min<uint64_t>(gx, 65535));
+    }
+    pl->partial_rows = pl->items.size() * (size_t)pl->pitch;
+    for (int i = 0; i < n_entries; ++i) pl->rows_per_item[i] = pl->pitch;
+    CK(pl->d_items.upload(pl->items.data(), pl->items.size(), ctx->stream));
+    CK(pl->d_chunk_tree0.upload(pl->chunk_tree0.data(), pl->chunk_tree0.size(), ctx->stream));
+    CK(pl->d_entry_chunk_base.upload(pl->entry_chunk_base.data(), pl->entry_chunk_base.size(), ctx->stream));
+    CK(pl->d_rows_per_item.upload(pl->rows_per_item.data(), pl->rows_per_item.size(), ctx->stream));
+    CK(pl->d_ids.upload(pl->ids.data(), pl->ids.size(), ctx->stream));
+    CK(ctx->dPartials.reserve(pl->partial_rows * S));
+    CK(ctx->dOut.reserve((size_t)n_entries * ctx->model.bsize));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->plan = std::move(pl);
+    return QIW_OK;
+}
+
+static double simplex_volume(int d, double edge) {  // src/qmc_integrate.jl:46
+    double v = 1.0;
+    for (int i = 1; i <= d; ++i) v *= edge / i;
+    return v;
+}
+
+// Common body of qiw_eval / qiw_eval_range / qiw_eval_at_times (scalar models).
+static int eval_scalar(qiw_context* ctx, double t_i, double t_w, double t_f, int n_entries, const int32_t* ids,
+                       const uint32_t* sobol_m, const uint32_t* sobol_x0, uint64_t start, uint64_t count,
+                       uint64_t N_total, bool allreduce, double* out, const double* explicit_times, int n_explicit) {
+    const HostModel& m = ctx->model;
+    const int S = m.S;
+    const bool explicit_mode = explicit_times != nullptr;
+    int rc = sync_static_tables(ctx);
+    if (rc) return rc;
+    bool same = ctx->plan && ctx->plan->count == count && ctx->plan->explicit_mode == explicit_mode &&
+                (int)ctx->plan->ids.size() == n_entries && std::equal(ids, ids + n_entries, ctx->plan->ids.begin());
+    if (!same) { rc = build_plan(ctx, n_entries, ids, count, explicit_mode); if (rc) return rc; }
+    Plan& pl = *ctx->plan;
+    // per-call dynamic data: Sobol parameters of every entry, staged into one buffer
+    const bool default_sobol = (sobol_m == nullptr && sobol_x0 == nullptr);
+    if (pl.sobol_off.empty()) {
+        size_t tot = 0;
+        for (int i = 0; i < n_entries; ++i) { pl.sobol_off.push_back(tot); tot += (size_t)ctx->entries[ids[i]]->prog.D * 33 + 1; }
+        pl.h_sobol.assign(tot, 0u);
+        CK(pl.d_sobol.reserve(tot));
+    }
+    if (!(default_sobol && pl.default_sobol_resident)) {
+        size_t moff = 0, xoff = 0;
+        for (int i = 0; i < n_entries; ++i) {
+            EntryDev& ed = *ctx->entries[ids[i]];
+            const int D = ed.prog.D;
+            uint32_t* sb = pl.h_sobol.data() + pl.sobol_off[i];
+            memcpy(sb, sobol_m ? sobol_m + moff : ed.default_sobol.data(), (size_t)D * 32 * sizeof(uint32_t));
+            if (sobol_x0) memcpy(sb + (size_t)D * 32, sobol_x0 + xoff, (size_t)D * sizeof(uint32_t));
+            else memset(sb + (size_t)D * 32, 0, (size_t)D * sizeof(uint32_t));
+            moff += (size_t)D * 32; xoff += D;
+        }
+        CK(cudaMemcpyAsync(pl.d_sobol.p, pl.h_sobol.data(), pl.h_sobol.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        pl.default_sobol_resident = default_sobol;
+    }
+    for (int i = 0; i < n_entries; ++i) {
+        EntryDev& ed = *ctx->entries[ids[i]];
+        const EntryProgram& p = ed.prog;
+        const int D = p.D;
+        DevEntryDyn& dy = ctx->hDyn[ids[i]];
+        dy.sobol = pl.d_sobol.p + pl.sobol_off[i];
+        dy.out_index = i;
+        dy.item0 = pl.item0[i]; dy.n_items = pl.n_items[i];
+        if (p.order == 0) {
+            dy.start = 0; dy.count = 1;
+            // exact entries are identical on every rank: only rank 0 contributes to the sum
+            const double w = (allreduce && ctx->rank != 0) ? 0.0 : 1.0;
+            dy.scale = make_double2(w, 0.0);
+        } else {
+            dy.start = start; dy.count = count;
+            const int d_after = (p.mode == 0) ? D : p.n_pts_after, d_before = D - d_after;
+            double jac = (p.mode == 0) ? simplex_volume(D, t_f - t_i)
+                                        : simplex_volume(d_before, t_w - t_i) * simplex_volume(d_after, t_f - t_w);
+            // (-i)^D with D even: (-1)^order  (src/qmc_integrate.jl:565-569,610)
+            const double dir = (p.order & 1) ? -1.0 : 1.0;
+            dy.scale = make_double2(explicit_mode ? 1.0 : dir * jac / (double)N_total, 0.0);
+        }
+    }
+    CK(cudaMemcpyAsync(ctx->dDyn.p, ctx->hDyn.data(), ctx->hDyn.size() * sizeof(DevEntryDyn), cudaMemcpyHostToDevice, ctx->stream));
+    StepParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.entries = ctx->dEntries.p; sp.dyn = ctx->dDyn.p; sp.items = pl.d_items.p;
+    sp.chunk_tree0 = pl.d_chunk_tree0.p; sp.entry_chunk_base = pl.d_entry_chunk_base.p;
+    sp.P = ctx->dP.p; sp.E = ctx->dE.p; sp.deltas = ctx->dDeltas.p;
+    sp.S = S; sp.bsize = m.bsize; sp.n_tau = ctx->n_tau; sp.h = ctx->beta / (ctx->n_tau - 1);
+    sp.t_i = t_i; sp.t_w = t_w; sp.t_f = t_f; sp.times_dev = nullptr;
+    sp.partials = ctx->dPartials.p;
+    if (explicit_mode) {
+        const int D = ctx->entries[ids[0]]->prog.D;
+        CK(ctx->dTimes.upload(explicit_times, (size_t)n_explicit * std::max(D, 1), ctx->stream));
+        CK(ctx->dPerSample.reserve((size_t)n_explicit * S));
+        CK(cudaMemsetAsync(ctx->dPerSample.p, 0, (size_t)n_explicit * S * sizeof(double2), ctx->stream));
+        sp.explicit_times = ctx->dTimes.p; sp.per_sample_out = ctx->dPerSample.p;
+    }
+    const int pitch = pl.pitch;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (auto& g : pl.groups) {
+        StepParams gp = sp;
+        gp.items = pl.d_items.p + g.item0;
+        gp.max_slots = g.max_slots;
+        // partial rows are addressed as (item.partial0 * gridDim.x + blockIdx.x): make the pitch
+        // explicit by launching every group with the common pitch in x
+        dim3 grid((unsigned)pitch, (unsigned)g.n_items);
+        CK(launch_scalar_step(g.maxl, gp, grid, ctx->warps * 32, g.smem, ctx->stream));
+        ctx->launches++;
+    }
+    if (!explicit_mode) {
+        CK(launch_reduce(ctx->dDyn.p, pl.d_ids.p, ctx->dPartials.p, pl.d_rows_per_item.p, S, ctx->dOut.p, n_entries, ctx->stream));
+        ctx->launches++;
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    const size_t n_out = explicit_mode ? (size_t)n_explicit * S : (size_t)n_entries * m.bsize;
+    double2* src = explicit_mode ? ctx->dPerSample.p : ctx->dOut.p;
+    if (allreduce && ctx->comm && !explicit_mode) {
+        int nrc = g_nccl.AllReduce(src, src, n_out * 2, kNcclDouble, kNcclSum, ctx->comm, ctx->stream);
+        if (nrc) return fail(ctx, QIW_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "error"));
+    }
+    if (ctx->hOutCap < n_out) {
+        if (ctx->hOut) cudaFreeHost(ctx->hOut);
+        CK(cudaMallocHost((void**)&ctx->hOut, n_out * sizeof(double2)));
+        ctx->hOutCap = n_out;
+    }
+    CK(cudaMemcpyAsync(ctx->hOut, src, n_out * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_ms = ms;
+    memcpy(out, ctx->hOut, n_out * sizeof(double2));
+    return QIW_OK;
+}
+
+static int check_entries(qiw_context* ctx, int n_entries, const int32_t* ids, const char* who) {
+    if (!ctx) return QIW_ERR_BAD_ARG;
+    if (ctx->no_device) return fail(ctx, QIW_ERR_CUDA, std::string(who) + ": planning-only context (QIW_DEVICE_NONE) cannot compute; there is no CPU path");
+    if (!ctx->have_model || ctx->n_tau == 0) return fail(ctx, QIW_ERR_BAD_ARG, std::string(who) + ": model and grid must be set first");
+    if (n_entries <= 0 || !ids) return fail(ctx, QIW_ERR_BAD_ARG, std::string(who) + ": no entries");
+    for (int i = 0; i < n_entries; ++i) {
+        if (ids[i] < 0 || ids[i] >= (int)ctx->entries.size() || !ctx->entries[ids[i]] || !ctx->entries[ids[i]]->valid)
+            return fail(ctx, QIW_ERR_BAD_ARG, std::string(who) + ": unknown entry id");
+        for (int j = 0; j < i; ++j) if (ids[j] == ids[i]) return fail(ctx, QIW_ERR_BAD_ARG, std::string(who) + ": duplicate entry id");
+    }
+    if (!ctx->model.scalar) return fail(ctx, QIW_ERR_UNSUPPORTED, std::string(who) + ": sector blocks larger than 1x1 are not supported by this build yet");
+    return QIW_OK;
+}
+
+extern "C" {
+
+int qiw_eval_range(qiw_context* ctx, double t_i, double t_w, double t_f, int32_t n_entries, const int32_t* ids,
+                   const uint32_t* sobol_m, const uint32_t* sobol_x0, uint64_t start, uint64_t count,
+                   uint64_t N_total, double* out) {
+    int rc = check_entries(ctx, n_entries, ids, "qiw_eval_range");
+    if (rc) return rc;
+    if (!out || N_total == 0 || start + count > N_total || N_total > 0xFFFFFFFFull) return fail(ctx, QIW_ERR_BAD_ARG, "qiw_eval_range: bad sample range");
+    cudaSetDevice(ctx->device);
+    return eval_scalar(ctx, t_i, t_w, t_f, n_entries, ids, sobol_m, sobol_x0, start, count, N_total, false, out, nullptr, 0);
+}
+
+int qiw_eval(qiw_context* ctx, double t_i, double t_w, double t_f, int32_t n_entries, const int32_t* ids,
+             const uint32_t* sobol_m, const uint32_t* sobol_x0, uint64_t N_total, double* out) {
+    int rc = check_entries(ctx, n_entries, ids, "qiw_eval");
+    if (rc) return rc;
+    if (!out || N_total == 0 || N_total > 0xFFFFFFFFull) return fail(ctx, QIW_ERR_BAD_ARG, "qiw_eval: bad N_total");
+    cudaSetDevice(ctx->device);
+    uint64_t start = 0, count = N_total;
+    rank_sub_range(N_total, ctx->n_ranks, ctx->rank, &start, &count);
+    return eval_scalar(ctx, t_i, t_w, t_f, n_entries, ids, sobol_m, sobol_x0, start, count, N_total, true, out, nullptr, 0);
+}
+
+int qiw_eval_at_times(qiw_context* ctx, int32_t entry_id, double t_i, double t_w, double t_f, int32_t n_samples,
+                      const double* times, double* out) {
+    int rc = check_entries(ctx, 1, &entry_id, "qiw_eval_at_times");
+    if (rc) return rc;
+    if (n_samples <= 0 || !times || !out) return fail(ctx, QIW_ERR_BAD_ARG, "qiw_eval_at_times: bad argument");
+    cudaSetDevice(ctx->device);
+    return eval_scalar(ctx, t_i, t_w, t_f, 1, &entry_id, nullptr, nullptr, 0, (uint64_t)n_samples, (uint64_t)n_samples, false,
+                       out, times, n_samples);
+}
+
+int qiw_last_device_ms(qiw_context* ctx, double* ms) { if (!ctx || !ms) return QIW_ERR_BAD_ARG; *ms = ctx->last_ms; return QIW_OK; }
+int qiw_launch_count(qiw_context* ctx, int64_t* n) { if (!ctx || !n) return QIW_ERR_BAD_ARG; *n = ctx->launches; return QIW_OK; }
+
+int qiw_inchworm_run(qiw_context* ctx, int32_t, const int32_t*, int32_t, const int32_t*, const uint32_t*, const uint32_t*,
+                     uint64_t, double*) {
+    return fail(ctx, QIW_ERR_UNSUPPORTED, "qiw_inchworm_run: not implemented in this build");
+}
+
+// ---- Sobol / topologies / partitioning -----------------------------------------------------------
+
+int qiw_sobol_direction_numbers(int32_t D, uint32_t* m) { return (m && sobol_direction_numbers(D, m) == 0) ? QIW_OK : QIW_ERR_BAD_ARG; }
+
+int qiw_sobol_scramble(int32_t D, uint32_t* m, uint32_t* x0, const uint8_t* shift_bits, const uint8_t* ltm_bits) {
+    if (D < 0 || !m || !x0 || !shift_bits || !ltm_bits) return QIW_ERR_BAD_ARG;
+    return sobol_scramble(D, m, x0, shift_bits, ltm_bits) == 0 ? QIW_OK : QIW_ERR_BAD_ARG;
+}
+
+int qiw_sobol_points(qiw_context* ctx, int32_t D, const uint32_t* m, const uint32_t* x0, uint64_t start, uint64_t count,
+                     uint32_t* out) {
+    if (!ctx || D <= 0 || !m || !out || start + count > 0x100000000ull) return fail(ctx, QIW_ERR_BAD_ARG, "qiw_sobol_points: bad argument");
+    if (ctx->no_device) return fail(ctx, QIW_ERR_CUDA, "planning-only context cannot compute");
+    cudaSetDevice(ctx->device);
+    DevBuf<uint32_t> dm, dx, dout;
+    std::vector<uint32_t> zeros(D, 0u);
+    CK(dm.upload(m, (size_t)D * 32, ctx->stream));
+    CK(dx.upload(x0 ? x0 : zeros.data(), D, ctx->stream));
+    CK(dout.reserve(count * D));
+    if (count) {
+        CK(launch_sobol_points(D, dm.p, dx.p, start, count, dout.p, ctx->stream));
+        ctx->launches++;
+        CK(cudaMemcpyAsync(out, dout.p, count * D * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    dm.release(); dx.release(); dout.release();
+    return QIW_OK;
+}
+
+int qiw_topologies(int32_t order, int32_t k, int32_t with_external_arc, int64_t* n_top, int32_t* pairs, int32_t* parity) {
+    if (!n_top) return QIW_ERR_BAD_ARG;
+    int64_t n = enumerate_topologies(order, k, with_external_arc != 0, pairs, parity);
+    if (n < 0) return QIW_ERR_BAD_ARG;
+    *n_top = n;
+    return QIW_OK;
+}
+
+int qiw_rank_sub_range(uint64_t N, int32_t n_ranks, int32_t rank, uint64_t* start, uint64_t* count) {
+    if (n_ranks <= 0 || rank < 0 || rank >= n_ranks || !start || !count) return QIW_ERR_BAD_ARG;
+    rank_sub_range(N, n_ranks, rank, start, count);
+    return QIW_OK;
+}
+
+// ---- NCCL ------------------------------------------------------------------------------------------
+
+int qiw_comm_unique_id(uint8_t id[QIW_UNIQUE_ID_BYTES]) {
+    if (!id || !g_nccl.load()) return QIW_ERR_NCCL;
+    ncclUniqueId u;
+    if (g_nccl.GetUniqueId(&u)) return QIW_ERR_NCCL;
+    memcpy(id, u.internal, QIW_UNIQUE_ID_BYTES);
+    return QIW_OK;
+}
+
+int qiw_comm_init(qiw_context* ctx, int32_t n_ranks, int32_t rank, const uint8_t id[QIW_UNIQUE_ID_BYTES]) {
+    if (!ctx || n_ranks <= 0 || rank < 0 || rank >= n_ranks || !id) return fail(ctx, QIW_ERR_BAD_ARG, "qiw_comm_init: bad argument");
+    if (ctx->no_device) return fail(ctx, QIW_ERR_CUDA, "planning-only context cannot communicate");
+    if (!g_nccl.load()) return fail(ctx, QIW_ERR_NCCL, g_nccl.err);
+    cudaSetDevice(ctx->device);
+    ncclUniqueId u;
+    memcpy(u.internal, id, QIW_UNIQUE_ID_BYTES);
+    int rc = g_nccl.CommInitRank(&ctx->comm, n_ranks, u, rank);
+    if (rc) return fail(ctx, QIW_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    ctx->n_ranks = n_ranks; ctx->rank = rank;
+    ctx->plan.reset();
+    return QIW_OK;
+}
+
+int qiw_comm_destroy(qiw_context* ctx) {
+    if (!ctx) return QIW_ERR_BAD_ARG;
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    ctx->comm = nullptr; ctx->n_ranks = 1; ctx->rank = 0;
+    ctx->plan.reset();
+    return QIW_OK;
+}
+
+// ---- measurement --------------------------------------------------------------------------------------
+
+int qiw_measure_fp64_peak(qiw_context* ctx, double* tflops) {
+    if (!ctx || !tflops) return QIW_ERR_BAD_ARG;
+    if (ctx->no_device) return fail(ctx, QIW_ERR_CUDA, "planning-only context cannot compute");
+    cudaSetDevice(ctx->device);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int blocks = sms * 8, iters = 1 << 14;
+    DevBuf<double> buf;
+    CK(buf.reserve((size_t)blocks * 256));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        CK(launch_dfma_peak(buf.p, blocks, iters, ctx->stream));
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->launches++;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        const double fl = (double)blocks * 256.0 * iters * 8.0 * 2.0;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    buf.release();
+    *tflops = best;
+    return QIW_OK;
+}
+
+}  // extern "C"

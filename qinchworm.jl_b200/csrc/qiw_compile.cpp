@@ -1,0 +1,231 @@
+// qiw_compile.cpp — turns one TopologiesInputData + the model into a traversal program.
+//
+// The reference rebuilds a TopologyEvaluator at every step (src/inchworm.jl:165 ->
+// src/topology_eval.jl:249-330) and, for every sample and topology, walks the configuration tree
+// recursively with run-time pruning by sector selection rules (_traverse_configuration_tree!,
+// :454-556).  Which branches survive depends only on (model, topology, initial sector) — not on the
+// sample — so here the walk is done ONCE on the host: dead branches are dropped and the surviving
+// tree is emitted as a flat pre-order word stream that every sample (= one GPU lane) replays in
+// lock step.  Node order inside a tree is the reference's own DFS order.
+#include <algorithm>
+#include <map>
+
+#include "qiw_host.hpp"
+
+namespace qiw {
+
+namespace {
+
+enum Kind { K_FREE = 0, K_IDENT = 1, K_INCH = 2, K_OPER = 3, K_HEAD = 4, K_TAIL = 5 };
+
+struct Builder {
+    const HostModel& m;
+    EntryProgram& e;
+    int n_nodes;
+    int kind[kMaxNodes + 2];
+    int arc_of[kMaxNodes + 2];      // arc index of a head/tail position
+    int head_pos_of_arc[kMaxOrder + 1];
+    int selected[kMaxOrder + 1];    // pair chosen at the head of each arc
+    int s_init = 0;
+    cplx top_sign;
+    bool offdiag = false;
+    std::map<std::pair<double, double>, int> coef_index;
+    std::map<std::tuple<int, int, int>, int> dslot_index;
+    // statistics of the reference algorithm for the current chain
+    int64_t leaves = 0, edges = 0;
+    double flops = 0;
+
+    Builder(const HostModel& m_, EntryProgram& e_) : m(m_), e(e_), n_nodes(e_.n_nodes) {}
+
+    int coef_id(cplx c) {
+        // canonicalise signed zeros so that +0 / -0 do not create distinct entries
+        double re = c.real() == 0.0 ? 0.0 : c.real(), im = c.imag() == 0.0 ? 0.0 : c.imag();
+        auto key = std::make_pair(re, im);
+        auto it = coef_index.find(key);
+        if (it != coef_index.end()) return it->second;
+        int id = (int)e.coefs.size();
+        e.coefs.push_back(cplx(re, im));
+        coef_index[key] = id;
+        return id;
+    }
+
+    int dslot_id(int pos_tail, int pos_head, int table) {
+        auto key = std::make_tuple(pos_tail, pos_head, table);
+        auto it = dslot_index.find(key);
+        if (it != dslot_index.end()) return it->second;
+        int id = (int)e.dslots.size();
+        e.dslots.push_back(DeltaSlot{pos_tail, pos_head, table});
+        dslot_index[key] = id;
+        return id;
+    }
+
+    // Emits the sibling nodes of position `pos` (one per live alternative: a head position has one
+    // alternative per attachable pair, every other position has one), entered in sector `s` with
+    // the product `coef` of operator matrix elements collected so far (scalar models only).
+    // `first` = no matrix has been pushed yet (the reference's LazyMatrixProduct copies its first
+    // factor instead of multiplying, src/utility.jl:304-308).
+    // Returns the number of leaves below and, through n_emitted, the number of nodes emitted at
+    // this level; dead branches emit nothing.
+    int64_t node(int pos, int s, cplx coef, bool first, uint32_t& n_emitted) {
+        int ops[256], pair_of[256], nops = 0;
+        const int k = kind[pos];
+        if (k == K_IDENT || k == K_INCH) { ops[nops] = -1; pair_of[nops++] = -1; }
+        else if (k == K_OPER) { ops[nops] = e.fixed_op[pos]; pair_of[nops++] = -1; }
+        else if (k == K_HEAD) {  // :475-493
+            for (int p : m.attachable[s]) { ops[nops] = m.pair_op_i[p]; pair_of[nops++] = p; }
+        } else {  // tail: the pair was chosen at the head (:497)
+            const int p = selected[arc_of[pos]];
+            ops[nops] = m.pair_op_f[p]; pair_of[nops++] = p;
+        }
+        int64_t total = 0;
+        n_emitted = 0;
+        for (int alt = 0; alt < nops; ++alt) {
+            const int op = ops[alt];
+            int s_next = s;
+            cplx c2 = coef;
+            if (op >= 0) {
+                s_next = m.target(op, s);
+                if (s_next < 0) continue;  // pruned: no block leaves the current sector (:501,524)
+                if (e.scalar) c2 *= m.block(op, s)[0];
+            }
+            if (k == K_HEAD) selected[arc_of[pos]] = pair_of[alt];
+            const uint32_t slotA = e.scalar ? (uint32_t)((pos - 2) * m.S + s) : (uint32_t)s;
+            const size_t my = e.words.size();
+            const int64_t my_edges = edges;
+            const double my_flops = flops;
+            const size_t my_dslots = e.dslots.size();
+            uint32_t slotB = 0;
+            if (k == K_TAIL)
+                slotB = (uint32_t)(e.nP + dslot_id(pos, head_pos_of_arc[arc_of[pos]], m.pair_table[pair_of[alt]]));
+            e.words.push_back(0);  // placeholder, patched below
+            // cost of this edge in the reference algorithm: (d_next x d_s) times (d_s x d_init)
+            edges += 1;
+            if (!first) flops += 8.0 * m.dim[s_next] * m.dim[s] * m.dim[s_init];
+            int64_t below = 0;
+            uint32_t nchild = 0;
+            if (pos == n_nodes) {
+                if (s_next != s_init) offdiag = true;  // the @assert at :462
+                else { below = 1; flops += 8.0 * m.dim[s_init] * m.dim[s_init]; }
+            } else {
+                below = node(pos + 1, s_next, c2, false, nchild);
+            }
+            if (below == 0) {  // dead branch: roll back everything it emitted
+                e.words.resize(my);
+                edges = my_edges;
+                flops = my_flops;
+                while (e.dslots.size() > my_dslots) {
+                    const DeltaSlot& d = e.dslots.back();
+                    dslot_index.erase(std::make_tuple(d.pos_tail, d.pos_head, d.table));
+                    e.dslots.pop_back();
+                }
+                continue;
+            }
+            uint32_t aux = 0;
+            if (pos == n_nodes) aux = (uint32_t)coef_id(e.scalar ? c2 * top_sign : top_sign);
+            e.words[my] = make_word(slotA, slotB, nchild, aux, e.scalar ? 0u : (uint32_t)(op + 1));
+            total += below;
+            ++n_emitted;
+        }
+        return total;
+    }
+};
+
+}  // namespace
+
+int compile_entry(const HostModel& m, int mode, int order, int n_pts_after, int corr_idx, int n_top,
+                  const int32_t* pairs, const int32_t* parity, EntryProgram& e, std::string& err) {
+    if (order < 0 || order > kMaxOrder) { err = "order out of range"; return 1; }
+    if (mode < 0 || mode > 2) { err = "bad mode"; return 1; }
+    if (mode == 2 && (corr_idx < 0 || corr_idx >= (int)m.corr_A.size())) { err = "bad corr_idx"; return 1; }
+    e = EntryProgram();
+    e.mode = mode; e.order = order; e.n_pts_after = n_pts_after; e.corr_idx = corr_idx;
+    e.scalar = m.scalar;
+    e.D = 2 * order;
+    const int n = order;
+    const int d_after = (mode == 0) ? 2 * n : n_pts_after;
+    const int d_before = 2 * n - d_after;
+    if (order > 0 && mode != 0 && (d_after < 1 || d_after > 2 * n)) { err = "bad n_pts_after"; return 1; }
+    e.n_nodes = (mode == 0) ? 2 * n + 2 : 2 * n + 3;  // src/topology_eval.jl:254
+    e.nP = (e.n_nodes - 1) * m.S;
+    int kind[kMaxNodes + 2];
+    for (int p = 0; p <= kMaxNodes; ++p) { e.pos_src[p] = 0; e.fixed_op[p] = -1; kind[p] = K_FREE; }
+    // fixed nodes: src/inchworm.jl:150,163 (bold) :260,274 (bare) :817-819,835,849 (correlator)
+    if (mode == 0) {
+        kind[1] = K_IDENT; e.pos_src[1] = SRC_TI;
+        kind[2 * n + 2] = K_IDENT; e.pos_src[2 * n + 2] = SRC_TF;
+    } else {
+        const int pw = (order == 0) ? 2 : d_before + 2;
+        kind[1] = (mode == 1) ? K_IDENT : K_OPER; e.pos_src[1] = SRC_TI;
+        kind[pw] = (mode == 1) ? K_INCH : K_OPER; e.pos_src[pw] = SRC_TW;
+        kind[2 * n + 3] = K_IDENT; e.pos_src[2 * n + 3] = SRC_TF;
+        if (mode == 2) { e.fixed_op[1] = m.corr_B[corr_idx]; e.fixed_op[pw] = m.corr_A[corr_idx]; }
+    }
+    // free positions, highest first, receive the sample's times in the order the transform
+    // produces them; topology vertex v is the v-th of them (src/topology_eval.jl:269-275)
+    int vertex_pos[2 * kMaxOrder + 1];
+    {
+        int v = 0;
+        for (int pos = e.n_nodes; pos >= 1; --pos)
+            if (kind[pos] == K_FREE) { e.pos_src[pos] = v; vertex_pos[++v] = pos; }
+        if (v != 2 * n) { err = "internal: free position count"; return 1; }
+    }
+
+    Builder b(m, e);
+    e.n_top = n_top;
+    e.tree_off.clear(); e.tree_cost.clear();
+    // Trees are grouped by initial sector (outer) so that an executor flushes its accumulator
+    // rarely; inside a sector group the reference's topology order is kept.
+    for (int s_i = 0; s_i < m.S; ++s_i) {
+        for (int t = 0; t < n_top; ++t) {
+            for (int pos = 1; pos <= e.n_nodes; ++pos) { b.kind[pos] = kind[pos]; b.arc_of[pos] = -1; }
+            for (int a = 0; a < n; ++a) {
+                const int va = pairs[((size_t)t * n + a) * 2], vb = pairs[((size_t)t * n + a) * 2 + 1];
+                if (va < 1 || vb < 1 || va > 2 * n || vb > 2 * n || va >= vb) { err = "bad topology pair"; return 1; }
+                const int pos_tail = vertex_pos[va], pos_head = vertex_pos[vb];  // :398-403
+                b.kind[pos_tail] = K_TAIL; b.arc_of[pos_tail] = a;
+                b.kind[pos_head] = K_HEAD; b.arc_of[pos_head] = a;
+                b.head_pos_of_arc[a] = pos_head;
+            }
+            // result += -i * parity * (-1)^order * top_result  (src/topology_eval.jl:431)
+            b.top_sign = cplx(0, -1) * (double)parity[t] * ((n & 1) ? -1.0 : 1.0);
+            b.s_init = s_i;
+            const size_t root = e.words.size();
+            const int64_t edges0 = b.edges;
+            e.words.push_back(0);
+            // position 1 is always a fixed node: identity (no factor) or operator B (bare matrix)
+            cplx coef(1.0, 0.0);
+            int s_next = s_i;
+            uint32_t rootop = 0;
+            bool first = true;
+            if (kind[1] == K_OPER) {
+                const int op = e.fixed_op[1];
+                s_next = m.target(op, s_i);
+                if (s_next < 0) { e.words.resize(root); continue; }
+                if (e.scalar) coef *= m.block(op, s_i)[0];
+                rootop = (uint32_t)(op + 1);
+                b.edges += 1;  // pushed as the (free) first factor
+                first = false;
+            }
+            uint32_t nchild = 0;
+            const double flops0 = b.flops;
+            const int64_t below = b.node(2, s_next, coef, first, nchild);
+            if (below == 0) { e.words.resize(root); b.edges = edges0; b.flops = flops0; continue; }
+            e.words[root] = make_word((uint32_t)s_next, 0, nchild, (uint32_t)s_i, rootop);
+            b.leaves += below;
+            e.tree_off.push_back((uint32_t)root);
+            e.tree_cost.push_back((uint32_t)(b.edges - edges0));
+        }
+    }
+    if (b.offdiag) {
+        err = "a block off-diagonal contribution to a pseudo-particle propagator detected "
+              "(src/topology_eval.jl:462): pass more symmetry breakers to the ED";
+        return 4;
+    }
+    e.tree_off.push_back((uint32_t)e.words.size());
+    e.words.push_back(0);  // pad: executors prefetch one word ahead
+    e.n_leaves = b.leaves; e.n_edges = b.edges; e.flops_per_sample = b.flops;
+    if (e.nP + (int)e.dslots.size() > 4095 || e.coefs.size() > 65535) { err = "program table overflow"; return 5; }
+    return 0;
+}
+
+}  // namespace qiw

@@ -1,0 +1,78 @@
+// qiw_device.cuh — device-side structures and kernels' declarations of libqinchworm_cuda.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace qiw {
+
+constexpr int kDevMaxNodes = 19;
+constexpr int kDevMaxDim = 24;      // Sobol dimensions handled per entry (2 * order <= 16)
+constexpr int kMaxTables = 64;
+
+// One scalar propagator table resident in HBM.
+struct DevDelta {
+    const double2* y;   // grid values
+    const double2* M;   // spline second derivatives (kind == 1)
+    int kind, n;
+    double h;           // beta / (n - 1)
+};
+
+// Static (per compiled entry) description read by every CTA working on the entry.
+struct DevEntry {
+    int mode, order, n_nodes, D;
+    int d_after, d_before;
+    int nP, nD;                 // table slots: propagators, pair interactions
+    int n_trees;
+    int exact;                  // order 0: one deterministic evaluation
+    int pos_src[kDevMaxNodes + 1];
+    const uint64_t* words;
+    const uint32_t* tree_off;   // [n_trees + 1]
+    const double2* coefs;
+    const int4* dslots;         // (pos_tail, pos_head, table, 0)
+};
+
+// Per call, per entry.
+struct DevEntryDyn {
+    const uint32_t* sobol;      // m[D][32] followed by x0[D]
+    double2 scale;              // (-i)^d * J / N_total  (1 for exact entries)
+    unsigned long long start;   // first Sobol index evaluated by this rank
+    unsigned long long count;   // number of Sobol points evaluated by this rank (1 if exact)
+    int out_index;              // row of the output
+    int item0, n_items;         // this entry's CTA jobs (consecutive rows of the partials buffer)
+    int pad;
+};
+
+// One CTA job: a group of up to `warps` consecutive chunks of one entry.
+struct WorkItem {
+    int entry;        // index into the DevEntry / DevEntryDyn arrays of the call
+    int chunk0;       // first chunk of the group
+    int n_chunks;     // chunks in the group (<= warps per CTA)
+    int partial0;     // first row of this item in the partials buffer
+};
+
+struct StepParams {
+    const DevEntry* entries;
+    const DevEntryDyn* dyn;
+    const WorkItem* items;
+    const uint32_t* chunk_tree0;   // [total chunks + 1] per-entry chunk -> first tree (concatenated)
+    const int* entry_chunk_base;   // [n entries] offset of the entry's chunks in chunk_tree0
+    // model
+    const double2* P;              // [n_tau][bsize]
+    const double* E;               // [S] (scalar models) energies + lambda
+    const DevDelta* deltas;
+    int S, bsize, n_tau;
+    double h;                      // beta / (n_tau - 1)
+    // times; when `times_dev` is non-null the triple is read from device memory (run-level API)
+    double t_i, t_w, t_f;
+    const double* times_dev;
+    int max_slots;                 // shared-memory table rows reserved per CTA
+    // explicit-times mode (qiw_eval_at_times): times[count][D], per-sample output, no reduction
+    const double* explicit_times;
+    double2* per_sample_out;       // [count][S]
+    // output
+    double2* partials;             // [n partial rows][gridDim.x][S]
+};
+
+}  // namespace qiw

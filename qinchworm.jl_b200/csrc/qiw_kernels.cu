@@ -1,0 +1,389 @@
+// qiw_kernels.cu — hand-written CUDA kernels (sm_100a) of the qMC diagram-evaluation hot path.
+//
+// Mapping: one LANE owns one scrambled-Sobol sample; a CTA owns 32 samples of one
+// entry (one TopologiesInputData) and a group of up to `warps` chunks of that entry's configuration
+// trees.  All warps of the CTA first build the per-sample tables in shared memory —
+//   Sobol point by Gray-code random access      (src/scrambled_sobol.jl:158-197)
+//   cube -> ordered-time simplex                (src/qmc_integrate.jl:225-235,425-449)
+//   i*P_s(t_pos, t_pos-1) for every interval/sector, i*Delta for every used arc/table
+//                                               (src/topology_eval.jl:357-374,397-416)
+// laid out [slot][lane] so that the 16-byte loads of the walk are bank-conflict free — and then
+// every warp replays its chunk of the pre-compiled, pruned configuration trees in lock step
+// (src/topology_eval.jl:454-556): the program word is warp-uniform, the data are per lane, partial
+// products of the chain live in registers (one complex per tree level).
+#include <cstdio>
+
+#include "qiw_device.cuh"
+
+namespace qiw {
+
+// ---- small complex helpers -------------------------------------------------------------------
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {  // a*b + c
+    return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 cscale(double a, double2 b) { return make_double2(a * b.x, a * b.y); }
+__device__ __forceinline__ double2 times_i(double2 a) { return make_double2(-a.y, a.x); }
+
+// ---- interpolation ---------------------------------------------------------------------------
+
+// Keldysh.jl's generic grid interpolation of a translation-invariant imaginary-time function
+// stored as D[k] = G(k h): bilinear on the cell (a, b) of the (t_f, t_i) grid, linear on the
+// triangle when both times share a cell (rule: DESIGN.md §2; call sites
+// src/topology_eval.jl:368,414).
+__device__ __forceinline__ double2 grid_interp(const double2* __restrict__ D, int stride, int n, double h,
+                                               double t_f, double t_i) {
+    const double qf = t_f / h, qi = t_i / h;
+    int a = (int)floor(qf), b = (int)floor(qi);
+    a = min(max(a, 0), n - 2);
+    b = min(max(b, 0), n - 2);
+    const double w1 = qf - (double)a, w2 = qi - (double)b;
+    if (a == b) {
+        const double2 d0 = __ldg(D), d1 = __ldg(D + stride);
+        const double w = w1 - w2;
+        return make_double2(d0.x + w * (d1.x - d0.x), d0.y + w * (d1.y - d0.y));
+    }
+    const int k = a - b;
+    const double2 dk = __ldg(D + (size_t)k * stride), dp = __ldg(D + (size_t)(k + 1) * stride),
+                  dm = __ldg(D + (size_t)(k - 1) * stride);
+    const double c00 = (1.0 - w1) * (1.0 - w2), c10 = w1 * (1.0 - w2), c01 = (1.0 - w1) * w2, c11 = w1 * w2;
+    return make_double2(c00 * dk.x + c10 * dp.x + c01 * dm.x + c11 * dk.x,
+                        c00 * dk.y + c10 * dp.y + c01 * dm.y + c11 * dk.y);
+}
+
+// Natural cubic spline in dt = t_f - t_i (src/spline_gf.jl:208-219).
+__device__ __forceinline__ double2 spline_eval(const DevDelta& t, double dt) {
+    const double h = t.h;
+    int j = (int)floor(dt / h);
+    j = min(max(j, 0), t.n - 2);
+    const double xa = dt - (double)j * h, xb = (double)(j + 1) * h - dt;
+    const double2 y0 = __ldg(t.y + j), y1 = __ldg(t.y + j + 1), m0 = __ldg(t.M + j), m1 = __ldg(t.M + j + 1);
+    const double ca = xa * xa * xa / (6.0 * h), cb = xb * xb * xb / (6.0 * h);
+    return make_double2(m0.x * cb + m1.x * ca + (y0.x / h - m0.x * h / 6.0) * xb + (y1.x / h - m1.x * h / 6.0) * xa,
+                        m0.y * cb + m1.y * ca + (y0.y / h - m0.y * h / 6.0) * xb + (y1.y / h - m1.y * h / 6.0) * xa);
+}
+
+__device__ __forceinline__ double2 delta_eval(const DevDelta& t, double t_f, double t_i) {
+    if (t.kind == 1) return spline_eval(t, t_f - t_i);
+    return grid_interp(t.y, 1, t.n, t.h, t_f, t_i);
+}
+
+// ---- Sobol -----------------------------------------------------------------------------------
+
+// Point k (0-based) of a digital sequence: x0 xor the direction numbers selected by gray(k);
+// identical to k calls of next! (src/scrambled_sobol.jl:158-173).
+__device__ __forceinline__ uint32_t sobol_coord(const uint32_t* __restrict__ m, uint32_t x0, uint32_t k) {
+    uint32_t g = k ^ (k >> 1), x = x0;
+    int b = 0;
+    while (g) {
+        if (g & 1u) x ^= __ldg(m + b);
+        g >>= 1;
+        ++b;
+    }
+    return x;
+}
+
+__global__ void sobol_points_kernel(int D, const uint32_t* __restrict__ m, const uint32_t* __restrict__ x0,
+                                    unsigned long long start, unsigned long long count, uint32_t* __restrict__ out) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >= count * (unsigned long long)D) return;
+    const unsigned long long k = i / D;
+    const int d = (int)(i % D);
+    out[i] = sobol_coord(m + d * 32, x0[d], (uint32_t)(start + k));
+}
+
+// ---- tree walk -------------------------------------------------------------------------------
+
+struct Walk {
+    const uint64_t* __restrict__ prog;
+    const double2* __restrict__ coefs;
+    const double2* T;     // shared-memory table, already offset by the lane
+    uint32_t pc;
+    uint64_t next;        // prefetched word prog[pc]
+    double2 acc;
+};
+
+__device__ __forceinline__ uint32_t w_slotA(uint64_t w) { return (uint32_t)w & 0xFFFu; }
+__device__ __forceinline__ uint32_t w_slotB(uint64_t w) { return ((uint32_t)w >> 12) & 0xFFFu; }
+__device__ __forceinline__ uint32_t w_nchild(uint64_t w) { return ((uint32_t)w >> 24) & 0xFFu; }
+__device__ __forceinline__ uint32_t w_aux(uint64_t w) { return (uint32_t)(w >> 32) & 0xFFFFu; }
+
+// One node at tree level L (= backbone position L): multiply the parent's partial product by the
+// node's factors, then either accumulate (last position) or descend into the children, which
+// follow in the word stream.  Recursion is over a compile-time level so that every partial
+// product has its own registers.
+template <int L, int MAXL>
+struct Level {
+    static __device__ __forceinline__ void run(Walk& w, const double2 vp) {
+        const uint64_t word = w.next;
+        w.next = __ldg(w.prog + (++w.pc));
+        double2 v = cmul(vp, w.T[w_slotA(word) * 32]);
+        const uint32_t sb = w_slotB(word);
+        if (sb) v = cmul(v, w.T[sb * 32]);
+        const uint32_t nc = w_nchild(word);
+        if (nc == 0) {
+            w.acc = cfma(__ldg(w.coefs + w_aux(word)), v, w.acc);
+            return;
+        }
+        if constexpr (L < MAXL) {
+            for (uint32_t c = 0; c < nc; ++c) Level<L + 1, MAXL>::run(w, v);
+        }
+    }
+};
+
+// ---- the step kernel (scalar models: every sector block is 1x1) ------------------------------
+
+// Register budget: deep trees (orders 5-8) need one live complex per level plus loop state, so
+// they run at one CTA per SM; shallower trees leave room for two.
+template <int MAXL>
+__global__ void __launch_bounds__(256, (MAXL <= 11) ? 2 : 1) scalar_step_kernel(const StepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const WorkItem it = p.items[blockIdx.y];
+    const DevEntry& e = p.entries[it.entry];
+    const DevEntryDyn& dy = p.dyn[it.entry];
+    const int S = p.S, D = e.D, n_nodes = e.n_nodes, nP = e.nP, n_slots = e.nP + e.nD;
+    const int d_after = e.d_after;
+
+    // shared memory carve-up (sizes fixed per launch from the largest entry, see host)
+    double2* T = reinterpret_cast<double2*>(smem_raw);                       // [max_slots][32]
+    double2* sacc = T + (size_t)p.max_slots * 32;                         // [S][blockDim.x]
+    double* times = reinterpret_cast<double*>(sacc + (size_t)S * blockDim.x); // [kDevMaxNodes+1][32]
+    double* pw = times + (kDevMaxNodes + 1) * 32;                            // [kDevMaxDim][32]
+    int* okflag = reinterpret_cast<int*>(pw + kDevMaxDim * 32);              // [32]
+
+    for (int s = 0; s < S; ++s) sacc[s * blockDim.x + threadIdx.x] = make_double2(0.0, 0.0);
+
+    double t_i = p.t_i, t_w = p.t_w, t_f = p.t_f;
+    if (p.times_dev) { t_i = p.times_dev[0]; t_w = p.times_dev[1]; t_f = p.times_dev[2]; }
+    const double lo_after = (e.mode == 0) ? t_i : t_w, len_after = t_f - lo_after;
+    const double len_before = t_w - t_i;
+
+    const uint32_t* __restrict__ sm = dy.sobol;
+    const unsigned long long count = dy.count;
+    const int n_sb = (int)((count + 31ull) >> 5);
+
+    // this warp's chunk of trees
+    int tree0 = 0, tree1 = 0;
+    if (warp < it.n_chunks) {
+        const uint32_t* ct = p.chunk_tree0 + p.entry_chunk_base[it.entry] + it.chunk0 + warp;
+        tree0 = (int)ct[0];
+        tree1 = (int)ct[1];
+    }
+
+    for (int sb = blockIdx.x; sb < n_sb; sb += gridDim.x) {
+        const unsigned long long local = (unsigned long long)sb * 32ull + lane;
+        const bool active = local < count;
+        const uint32_t k = (uint32_t)(dy.start + local);
+
+        // -- 1. Sobol coordinates and the independent roots x_j^(1/(remaining dims)) ----------
+        if (p.explicit_times == nullptr) {
+            for (int j = warp; j < D; j += nw) {
+                const uint32_t xi = sobol_coord(sm + j * 32, __ldg(sm + D * 32 + j), k);
+                const double x = (double)xi * 2.3283064365386963e-10;  // ldexp(x, -32), exact
+                const int den = (j < d_after) ? (d_after - j) : (D - j);
+                pw[j * 32 + lane] = pow(x, 1.0 / (double)den);
+            }
+        }
+        __syncthreads();
+
+        // -- 2. ordered times of every backbone position ----------------------------------------
+        if (warp == 0) {
+            bool ok = true;
+            double u = 1.0;
+            for (int pos = n_nodes; pos >= 1; --pos) {   // free positions, highest first = u[0], u[1], ...
+                const int src = e.pos_src[pos];
+                double t;
+                if (src == -1) t = t_i;
+                else if (src == -2) t = t_w;
+                else if (src == -3) t = t_f;
+                else if (p.explicit_times) {
+                    t = active ? p.explicit_times[local * D + src] : 0.0;
+                } else {
+                    if (src == 0 || src == d_after) u = pw[src * 32 + lane];
+                    else u = __dmul_rn(u, pw[src * 32 + lane]);
+                    if (src < d_after) t = __dadd_rn(__dmul_rn(u, len_after), lo_after);
+                    else t = __dadd_rn(__dmul_rn(u, len_before), t_i);
+                    ok = ok && (t >= 0.0);   // all(refs .>= 0) (src/qmc_integrate.jl:608)
+                }
+                times[pos * 32 + lane] = t;
+            }
+            okflag[lane] = (ok && active) ? 1 : 0;
+        }
+        __syncthreads();
+
+        // -- 3. per-sample tables --------------------------------------------------------------
+        for (int q = warp; q < n_slots; q += nw) {
+            double2 val;
+            if (q < nP) {
+                const int iv = q / S, s = q - iv * S;      // interval between positions iv+1, iv+2
+                const double ta = times[(iv + 1) * 32 + lane];
+                double tb = times[(iv + 2) * 32 + lane];
+                if (tb < ta) tb = ta;                       // src/topology_eval.jl:362-364
+                if (e.mode == 0) {                          // bare: i * (-i) exp(-dt (E + lambda))
+                    val = make_double2(exp(-(tb - ta) * __ldg(p.E + s)), 0.0);
+                } else {
+                    val = times_i(grid_interp(p.P + s, p.bsize, p.n_tau, p.h, tb, ta));
+                }
+            } else {
+                const int4 ds = __ldg(e.dslots + (q - nP));
+                const double th = times[ds.y * 32 + lane];
+                double tt = times[ds.x * 32 + lane];
+                if (tt < th) tt = th;                       // :407-410
+                val = times_i(delta_eval(p.deltas[ds.z], tt, th));
+            }
+            T[q * 32 + lane] = val;
+        }
+        __syncthreads();
+
+        // -- 4. replay this warp's trees -------------------------------------------------------
+        if (tree0 < tree1) {
+            Walk w;
+            w.prog = e.words;
+            w.coefs = e.coefs;
+            w.T = T + lane;
+            w.acc = make_double2(0.0, 0.0);
+            const bool ok = okflag[lane] != 0;
+            int cur_s = -1;
+            w.pc = __ldg(e.tree_off + tree0);
+            w.next = __ldg(w.prog + w.pc);
+            for (int t = tree0; t < tree1; ++t) {
+                const uint64_t root = w.next;
+                w.next = __ldg(w.prog + (++w.pc));
+                const int s_i = (int)w_aux(root);
+                if (s_i != cur_s) {
+                    if (cur_s >= 0 && ok) {
+                        if (p.per_sample_out) {
+                            double2* o = p.per_sample_out + local * S + cur_s;
+                            *o = cadd(*o, w.acc);
+                        } else {
+                            double2* a = sacc + cur_s * blockDim.x + threadIdx.x;
+                            *a = cadd(*a, w.acc);
+                        }
+                    }
+                    w.acc = make_double2(0.0, 0.0);
+                    cur_s = s_i;
+                }
+                const uint32_t nc = w_nchild(root);
+                const double2 one = make_double2(1.0, 0.0);
+                for (uint32_t c = 0; c < nc; ++c) Level<2, MAXL>::run(w, one);
+            }
+            if (cur_s >= 0 && ok) {
+                if (p.per_sample_out) {
+                    double2* o = p.per_sample_out + local * S + cur_s;
+                    *o = cadd(*o, w.acc);
+                } else {
+                    double2* a = sacc + cur_s * blockDim.x + threadIdx.x;
+                    *a = cadd(*a, w.acc);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    if (p.per_sample_out) return;
+
+    // -- 5. CTA reduction: lanes by shuffle, warps through shared memory, fixed order ---------
+    double2* red = T;  // reuse: [S][nw]
+    for (int s = 0; s < S; ++s) {
+        double2 v = sacc[s * blockDim.x + threadIdx.x];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            v.x += __shfl_down_sync(0xFFFFFFFFu, v.x, off);
+            v.y += __shfl_down_sync(0xFFFFFFFFu, v.y, off);
+        }
+        if (lane == 0) red[s * nw + warp] = v;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < S) {
+        double2 v = make_double2(0.0, 0.0);
+        for (int w2 = 0; w2 < nw; ++w2) v = cadd(v, red[threadIdx.x * nw + w2]);
+        p.partials[((size_t)it.partial0 * gridDim.x + blockIdx.x) * S + threadIdx.x] = v;
+    }
+}
+
+}  // namespace qiw
+
+namespace qiw {
+
+// ---- deterministic reduction of the per-CTA partial sums -------------------------------------
+// One CTA per entry of the call; rows of an entry are consecutive.  out = scale * sum(rows).
+__global__ void __launch_bounds__(128) reduce_partials_kernel(const DevEntryDyn* __restrict__ dyn,
+                                                              const int* __restrict__ entry_ids,
+                                                              const double2* __restrict__ partials,
+                                                              const int* __restrict__ rows_per_item, int S,
+                                                              double2* __restrict__ out) {
+    __shared__ double2 buf[128];
+    const DevEntryDyn& dy = dyn[entry_ids[blockIdx.x]];
+    const int R = rows_per_item[blockIdx.x];
+    const size_t row0 = (size_t)dy.item0 * R, nrows = (size_t)dy.n_items * R;
+    for (int s = 0; s < S; ++s) {
+        double2 v = make_double2(0.0, 0.0);
+        for (size_t r = threadIdx.x; r < nrows; r += blockDim.x) v = cadd(v, partials[(row0 + r) * S + s]);
+        buf[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 64; off > 0; off >>= 1) {
+            if ((int)threadIdx.x < off) buf[threadIdx.x] = cadd(buf[threadIdx.x], buf[threadIdx.x + off]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[(size_t)dy.out_index * S + s] = cmul(dy.scale, buf[0]);
+        __syncthreads();
+    }
+}
+
+// ---- FP64 FMA peak probe ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0,
+           a6 = a0 + 6.0, a7 = a0 + 7.0;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ---- host-callable launchers -----------------------------------------------------------------
+
+template <int MAXL>
+static cudaError_t launch_scalar(const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(scalar_step_kernel<MAXL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    scalar_step_kernel<MAXL><<<grid, threads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scalar_step(int maxl, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    if (maxl <= 7) return launch_scalar<7>(p, grid, threads, smem, st);
+    if (maxl <= 11) return launch_scalar<11>(p, grid, threads, smem, st);
+    if (maxl <= 15) return launch_scalar<15>(p, grid, threads, smem, st);
+    return launch_scalar<19>(p, grid, threads, smem, st);
+}
+
+cudaError_t launch_reduce(const DevEntryDyn* dyn, const int* entry_ids, const double2* partials,
+                          const int* rows_per_item, int S, double2* out, int n_entries, cudaStream_t st) {
+    reduce_partials_kernel<<<n_entries, 128, 0, st>>>(dyn, entry_ids, partials, rows_per_item, S, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sobol_points(int D, const uint32_t* m, const uint32_t* x0, unsigned long long start,
+                                unsigned long long count, uint32_t* out, cudaStream_t st) {
+    const unsigned long long n = count * (unsigned long long)D;
+    sobol_points_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D, m, x0, start, count, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dfma_peak(double* out, int blocks, int iters, cudaStream_t st) {
+    dfma_peak_kernel<<<blocks, 256, 0, st>>>(out, iters);
+    return cudaGetLastError();
+}
+
+}  // namespace qiw

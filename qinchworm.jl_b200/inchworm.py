@@ -1,0 +1,221 @@
+"""qMC inchworm drivers — host mirror of src/inchworm.jl on top of libqinchworm_cuda.so.
+
+Same call shapes as the reference:
+    inchworm_step_bare(expansion, grid, k_i, k_f, top_data)          src/inchworm.jl:228
+    inchworm_step(expansion, grid, k_i, k_w, k_f, top_data)          src/inchworm.jl:123
+    inchworm(expansion, grid, orders, orders_bare, N_samples, ...)   src/inchworm.jl:332
+    correlator_2p(expansion, grid, orders, N_samples, ...)           src/inchworm.jl:918,1075
+Grid points are passed as 0-based indices into `grid.tau`.  All sampling, interpolation and
+diagram evaluation happens on the GPU inside `Context.eval`; what stays here is what stays in
+Julia: topology tables, the sequential loop over time steps, set_ppgf!/normalize!, the
+randomisation loop (one library call per scrambled sequence)."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import lib, ppgf
+from .lib import MODE_BARE, MODE_BOLD, MODE_CORR
+
+__all__ = ["RandomizationParams", "TopologiesInputData", "Solver", "inchworm_step", "inchworm_step_bare",
+           "inchworm", "correlator_2p", "get_topologies_at_order"]
+
+
+def get_topologies_at_order(order, k=None, with_external_arc=False):
+    """src/diagrammatics.jl:322-337 (enumerated inside the library, same order and parity)."""
+    return lib.topologies(order, k, with_external_arc)
+
+
+@dataclass
+class RandomizationParams:
+    """src/randomization.jl:46-57.  rng: numpy Generator used to draw scrambling bits, or None to
+    disable scrambling (the default, as in the reference)."""
+    rng: object = None
+    N_seqs: int = 1
+    target_std: float = 0.0
+
+
+@dataclass
+class TopologiesInputData:
+    """src/inchworm.jl:60-98."""
+    order: int
+    n_pts_after: int
+    topologies: tuple            # (pairs[n, order, 2], parity[n])
+    N_samples: int
+    rand_params: RandomizationParams = field(default_factory=RandomizationParams)
+    entry_id: int = -1           # handle of the compiled entry inside the library
+
+
+def _scrambled_sequence(D, rng):
+    """ScrambledSobolSeq(D, scramble_rng=rng) (src/scrambled_sobol.jl:66-143): the random bits are
+    drawn here, in the order the reference draws them (shift first, then the matrices)."""
+    m = lib.sobol_direction_numbers(D)
+    if rng is None or D == 0:
+        return m, np.zeros(D, dtype=np.uint32)
+    shift_bits = rng.integers(0, 2, size=(D, 32), dtype=np.uint8)
+    ltm_bits = rng.integers(0, 2, size=(D, 32, 32), dtype=np.uint8)
+    return lib.sobol_scramble(m, shift_bits, ltm_bits)
+
+
+class Solver:
+    """Binds one `Expansion` to one library context (one GPU) and keeps compiled entries."""
+
+    def __init__(self, expansion, ctx=None, device=-1):
+        self.expansion = expansion
+        self.ctx = ctx if ctx is not None else lib.Context(device=device)
+        self.payload = self.ctx.set_expansion(expansion)
+        self._next_entry = 0
+        self._n_corr_uploaded = len(expansion.corr_operators_mat)
+
+    def refresh_model(self):
+        """Re-upload after add_corr_operators (invalidates compiled entries, as in the ABI)."""
+        self.payload = self.ctx.set_expansion(self.expansion)
+        self._next_entry = 0
+        self._n_corr_uploaded = len(self.expansion.corr_operators_mat)
+
+    def upload_P(self, first=0, count=None):
+        count = self.expansion.grid.n_tau - first if count is None else count
+        self.ctx.set_P(first, self.expansion.P[first:first + count])
+
+    def make_entry(self, mode, order, n_pts_after, N_samples, rand_params=None, corr_idx=0):
+        if mode == MODE_BARE:
+            tops = get_topologies_at_order(order)
+        else:
+            tops = get_topologies_at_order(order, n_pts_after if order > 0 else 0, mode == MODE_CORR) \
+                if order > 0 else get_topologies_at_order(0, 0, mode == MODE_CORR)
+        if len(tops[1]) == 0:
+            return None
+        td = TopologiesInputData(order, n_pts_after, tops, N_samples, rand_params or RandomizationParams())
+        td.entry_id = self._next_entry
+        self._next_entry += 1
+        self.ctx.set_topologies(td.entry_id, mode, order, n_pts_after, tops[0], tops[1], corr_idx=corr_idx)
+        return td
+
+    def eval_entries(self, t_i, t_w, t_f, top_data):
+        """mean/std over randomised sequences of the per-entry qMC integrals
+        (mean_std_from_randomization, src/randomization.jl:86-100).  Returns (mean, std) arrays
+        [n_entries, bsize]; std is NaN for a single sequence, as in the reference."""
+        if not top_data:
+            z = np.zeros((0, self.ctx.bsize), dtype=complex)
+            return z, z
+        ids = [td.entry_id for td in top_data]
+        N = top_data[0].N_samples
+        rp = top_data[0].rand_params
+        assert all(td.N_samples == N for td in top_data)
+        samples = []
+        for s in range(rp.N_seqs):
+            sobol = None
+            if rp.rng is not None:
+                sobol = [_scrambled_sequence(2 * td.order, rp.rng) for td in top_data]
+            samples.append(self.ctx.eval(t_i, t_w, t_f, ids, N, sobol=sobol))
+            if s > 0 and np.max(np.abs(np.std(samples, axis=0, ddof=1))) <= rp.target_std:
+                break
+        mean = np.mean(samples, axis=0)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            std = np.std(samples, axis=0, ddof=1) if len(samples) > 1 else np.full_like(mean, np.nan)
+        for j, td in enumerate(top_data):
+            if td.order == 0:
+                std[j] = 0.0  # exact evaluation (src/inchworm.jl:155)
+        return mean, std
+
+
+def _order_sums(top_data, mean, std, bsize):
+    orders = sorted({td.order for td in top_data})
+    contribs = {o: np.zeros(bsize, dtype=complex) for o in orders}
+    contribs_std = {o: np.zeros(bsize, dtype=complex) for o in orders}
+    for j, td in enumerate(top_data):
+        contribs[td.order] = contribs[td.order] + mean[j]
+        contribs_std[td.order] = contribs_std[td.order] + std[j]
+    total = sum(contribs.values()) if contribs else np.zeros(bsize, dtype=complex)
+    return total, contribs, contribs_std
+
+
+def inchworm_step_bare(solver: Solver, grid, k_i, k_f, top_data):
+    """One initial step with bare propagators (src/inchworm.jl:228-304).  Returns
+    (value, order_contribs, order_contribs_std) as packed block vectors."""
+    mean, std = solver.eval_entries(grid.tau[k_i], grid.tau[k_i], grid.tau[k_f], top_data)
+    return _order_sums(top_data, mean, std, solver.ctx.bsize)
+
+
+def inchworm_step(solver: Solver, grid, k_i, k_w, k_f, top_data):
+    """One regular inchworm step with bold propagators (src/inchworm.jl:123-204)."""
+    mean, std = solver.eval_entries(grid.tau[k_i], grid.tau[k_w], grid.tau[k_f], top_data)
+    return _order_sums(top_data, mean, std, solver.ctx.bsize)
+
+
+def inchworm(expansion, grid, orders, orders_bare, N_samples, n_pts_after_max=None,
+             rand_params=None, solver=None):
+    """inchworm!(expansion, grid, orders, orders_bare, N_samples; ...) (src/inchworm.jl:332-498).
+    Results are written into `expansion.P`; returns (P_orders, P_orders_std): dicts
+    order -> [n_tau, bsize] arrays of order-resolved contributions."""
+    assert N_samples == 0 or (N_samples & (N_samples - 1)) == 0, "N_samples must be a power of 2"
+    rand_params = rand_params or RandomizationParams()
+    assert rand_params.N_seqs > 0
+    solver = solver or Solver(expansion)
+    n_tau = grid.n_tau
+    orders, orders_bare = list(orders), list(orders_bare)
+    P_orders = {o: np.zeros((n_tau, solver.ctx.bsize), dtype=complex) for o in set(orders) | set(orders_bare)}
+    P_orders_std = {o: np.zeros((n_tau, solver.ctx.bsize), dtype=complex) for o in P_orders}
+    # first step: bare diagrams (:373-416)
+    top_data = [solver.make_entry(MODE_BARE, o, 2 * o, N_samples, rand_params) for o in orders_bare]
+    solver.upload_P()
+    value, contribs, contribs_std = inchworm_step_bare(solver, grid, 0, 1, top_data)
+    ppgf.set_ppgf(expansion, 1, value)
+    for o in contribs:
+        P_orders[o][1] = contribs[o]
+        P_orders_std[o][1] = contribs_std[o]
+    # the rest of inching (:420-493)
+    top_data = []
+    for o in orders:
+        rng = [0] if o == 0 else range(1, min(2 * o - 1, n_pts_after_max or 10 ** 9) + 1)
+        for k in rng:
+            td = solver.make_entry(MODE_BOLD, o, k, N_samples, rand_params)
+            if td is not None:
+                top_data.append(td)
+    solver.upload_P()
+    for n in range(1, n_tau - 1):
+        value, contribs, contribs_std = inchworm_step(solver, grid, 0, n, n + 1, top_data)
+        ppgf.set_ppgf(expansion, n + 1, value)
+        ppgf.normalize_at(expansion, n + 1)  # suppress exponential growth (:488)
+        solver.upload_P()
+        for o in contribs:
+            P_orders[o][n + 1] = contribs[o]
+            P_orders_std[o][n + 1] = contribs_std[o]
+    return P_orders, P_orders_std
+
+
+def correlator_2p(expansion, grid, orders, N_samples, rand_params=None, solver=None, return_std=False):
+    """correlator_2p(expansion, grid, orders, N_samples) (src/inchworm.jl:918-1086): one array
+    [n_tau] per registered pair in expansion.corr_operators."""
+    assert N_samples == 0 or (N_samples & (N_samples - 1)) == 0
+    rand_params = rand_params or RandomizationParams()
+    solver = solver or Solver(expansion)
+    if solver._n_corr_uploaded != len(expansion.corr_operators_mat):
+        solver.refresh_model()
+    solver.upload_P()
+    n_tau = grid.n_tau
+    diag = ppgf._diag_indices(expansion)
+    Z = ppgf.partition_function(expansion)
+    out, out_std = [], []
+    for c in range(len(expansion.corr_operators)):
+        top_data = []
+        for o in orders:
+            for k in ([0] if o == 0 else range(1, 2 * o)):
+                td = solver.make_entry(MODE_CORR, o, k, N_samples, rand_params, corr_idx=c)
+                if td is not None:
+                    top_data.append(td)
+        g = np.zeros(n_tau, dtype=complex)
+        g_std = np.zeros(n_tau, dtype=complex)
+        for k in range(n_tau):
+            tds = top_data
+            if k == 0:  # only order 0 contributes at tau_A = tau_B (:1013-1024)
+                tds = top_data[:1] if top_data and top_data[0].order == 0 else []
+                if not tds:
+                    continue
+            mean, std = solver.eval_entries(grid.tau[0], grid.tau[k], grid.tau[-1], tds)
+            g[k] = mean[:, diag].sum() / Z      # tr(...) / partition_function (:869,889)
+            g_std[k] = std[:, diag].sum() / Z
+        out.append(g)
+        out_std.append(g_std)
+    return (out, out_std) if return_std else out

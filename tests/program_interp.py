@@ -1,0 +1,72 @@
+"""Test-only Python interpreter of the traversal programs that libqinchworm_cuda.so compiles
+(qiw_entry_program).  It replays the word stream exactly as the CUDA kernel does, with the
+per-sample tables computed in numpy, so that the host-side compiler (csrc/qiw_compile.cpp) can be
+checked against the oracle on a GPU-less box.  Not part of the product."""
+import numpy as np
+
+
+def grid_interp(D, h, t_f, t_i):
+    n = len(D)
+    a = min(max(int(np.floor(t_f / h)), 0), n - 2)
+    b = min(max(int(np.floor(t_i / h)), 0), n - 2)
+    w1, w2 = t_f / h - a, t_i / h - b
+    if a == b:
+        return D[0] + (w1 - w2) * (D[1] - D[0])
+    k = a - b
+    return (1 - w1) * (1 - w2) * D[k] + w1 * (1 - w2) * D[k + 1] + (1 - w1) * w2 * D[k - 1] + w1 * w2 * D[k]
+
+
+def natural_spline(y, h):
+    from scipy.interpolate import CubicSpline
+    x = np.arange(len(y)) * h
+    return CubicSpline(x, y, bc_type="natural")
+
+
+def run_program(prog, expansion, payload, mode, t_i, t_w, t_f, times):
+    """Per-sample evaluator value (packed, scalar models): sum over trees of leaf coef * chain."""
+    S, nP, n_nodes = prog["S"], prog["nP"], prog["n_nodes"]
+    beta, n_tau = payload["beta"], payload["n_tau"]
+    h = beta / (n_tau - 1)
+    # times per position
+    t = np.zeros(n_nodes + 1)
+    for pos in range(1, n_nodes + 1):
+        src = prog["pos_src"][pos]
+        t[pos] = {-1: t_i, -2: t_w, -3: t_f}.get(int(src), None) if src < 0 else times[src]
+    T = np.zeros(nP + len(prog["dslots"]), dtype=complex)
+    for q in range(nP):
+        iv, s = divmod(q, S)
+        ta, tb = t[iv + 1], max(t[iv + 2], t[iv + 1])
+        if mode == 0:
+            T[q] = np.exp(-(tb - ta) * payload["energies"][s])
+        else:
+            T[q] = 1j * grid_interp(expansion.P[:, s], h, tb, ta)
+    for j, (pt, ph, tab) in enumerate(prog["dslots"]):
+        kind, data = payload["tables"][tab]
+        th, tt = t[ph], max(t[pt], t[ph])
+        if kind == 1:
+            T[nP + j] = 1j * natural_spline(data, beta / (len(data) - 1))(tt - th)
+        else:
+            T[nP + j] = 1j * grid_interp(data, beta / (len(data) - 1), tt, th)
+    words = prog["words"]
+    out = np.zeros(S, dtype=complex)
+    pc = [0]
+
+    def node(vp):
+        w = int(words[pc[0]]); pc[0] += 1
+        v = vp * T[w & 0xFFF]
+        sb = (w >> 12) & 0xFFF
+        if sb:
+            v = v * T[sb]
+        nc = (w >> 24) & 0xFF
+        if nc == 0:
+            return prog["coefs"][(w >> 32) & 0xFFFF] * v
+        return sum(node(v) for _ in range(nc))
+
+    for k in range(len(prog["tree_off"]) - 1):
+        pc[0] = int(prog["tree_off"][k])
+        root = int(words[pc[0]]); pc[0] += 1
+        s_i = (root >> 32) & 0xFFFF
+        for _ in range((root >> 24) & 0xFF):
+            out[s_i] += node(1.0 + 0j)
+        assert pc[0] == int(prog["tree_off"][k + 1]) or k == len(prog["tree_off"]) - 2
+    return out

@@ -1,0 +1,132 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs, and against the reference's golden vectors.  Tolerance: FP64 relative 1e-10
+(BASELINE.json north_star); Sobol points bit-exact."""
+import numpy as np
+import pytest
+
+import models
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def relerr(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+
+
+def test_sobol_points_bit_exact(gpu_ctx, qlib, oracle_lib):
+    for D in (1, 5, 12):
+        m = qlib.sobol_direction_numbers(D)
+        x0 = np.zeros(D, dtype=np.uint32)
+        ref, _ = oracle_lib.sobol_points(m, x0, 0, 4096)
+        got = gpu_ctx.sobol_points(m, x0, 0, 4096)
+        assert np.array_equal(got, ref)
+        ref, _ = oracle_lib.sobol_points(m, x0, 1000, 77)       # skip!(seq, 1000, exact=true)
+        assert np.array_equal(gpu_ctx.sobol_points(m, x0, 1000, 77), ref)
+    # scrambled sequence with the reference's MockRNG bits (test/scrambled_sobol.jl:97-105)
+    G = load_golden("sobol_tables.json")
+
+    def mock_bits(shape):
+        v = np.array([bin(i).count("1") % 2 for i in range(int(np.prod(shape)))], dtype=np.uint8)
+        return v.reshape(shape, order="F")
+    for D, key in ((1, "scrambled_D1"), (5, "scrambled_D5")):
+        m, x0 = qlib.sobol_scramble(qlib.sobol_direction_numbers(D), mock_bits((D, 32)), mock_bits((D, 32, 32)))
+        pts = gpu_ctx.sobol_points(m, x0, 0, 8).astype(np.float64) * 2.0 ** -32
+        assert np.abs(pts - np.array(G[key])).max() < 1e-10
+
+
+def test_topology_eval_golden(gpu_ctx, qlib):
+    """test/topology_eval.jl:137-151 through qiw_eval_at_times."""
+    G = load_golden("topology_eval_h5.json")
+    ex, grid, f = models.single_level(n_tau=30, spline=False, rev="transpose")
+    gpu_ctx.set_expansion(ex)
+    pairs, parity = qlib.topologies(3, 1)
+    assert len(parity) == 4
+    gpu_ctx.set_topologies(0, qlib.MODE_BOLD, 3, 1, pairs, parity)
+    tau = grid.tau
+    tw, tf = tau[6], tau[7]
+    times = np.zeros((100, 6))
+    times[:, 0] = tw + (tf - tw) * G["/x1_list"]
+    times[:, 1:] = tw * G["/xs_list"]
+    got = gpu_ctx.eval_at_times(0, 0.0, tw, tf, times)
+    ref = G["/values"].T[:, ::-1]   # golden sector 1 = occupied = our sector 1
+    assert relerr(got, ref) < RTOL
+
+
+@pytest.mark.parametrize("name", ["single_level", "anderson"])
+def test_step_vs_oracle(gpu_ctx, qlib, oracle_lib, name):
+    """One bold step, one bare step and one correlator point against the oracle."""
+    if name == "single_level":
+        ex, grid, f = models.single_level(n_tau=20, spline=True)
+        from qinchworm_b200.expansion import add_corr_operators
+        add_corr_operators(ex, (f.c("0"), f.c_dag("0")))
+        orders, N = range(0, 4), 2 ** 8
+    else:
+        ex, grid, f = models.anderson(n_tau=50, corr=True)
+        orders, N = range(0, 4), 2 ** 9
+    rng = np.random.default_rng(7)
+    ex.P = ex.P * (1.0 + 0.05 * rng.random(ex.P.shape))   # away from the atomic limit
+    pl = gpu_ctx.set_expansion(ex)
+    o = oracle_lib.Oracle(pl, ex.P)
+    tau = grid.tau
+    eid = 0
+    for mode, (ki, kw, kf), corr in ((qlib.MODE_BOLD, (0, 11, 12), 0), (qlib.MODE_BARE, (0, 0, 1), 0),
+                                     (qlib.MODE_CORR, (0, 9, len(tau) - 1), 0),
+                                     (qlib.MODE_CORR, (0, 5, len(tau) - 1), len(ex.corr_operators) - 1)):
+        ids = []
+        for order in orders:
+            ks = [None] if mode == qlib.MODE_BARE else ([0] if order == 0 else range(1, 2 * order))
+            for k in ks:
+                pr, pa = qlib.topologies(order, None if mode == qlib.MODE_BARE else k, mode == qlib.MODE_CORR)
+                if len(pa) == 0:
+                    continue
+                kk = 2 * order if mode == qlib.MODE_BARE else k
+                gpu_ctx.set_topologies(eid, mode, order, kk, pr, pa, corr_idx=corr)
+                o.set_topologies(eid, mode, order, kk, pr, pa)
+                ids.append(eid)
+                eid += 1
+        got = gpu_ctx.eval(tau[ki], tau[kw], tau[kf], ids, N)
+        ref = o.eval(tau[ki], tau[kw], tau[kf], ids, N, corr_idx=corr)
+        assert relerr(got, ref) < RTOL, (mode, corr, relerr(got, ref))
+        # ragged sample range + scrambled sequence, no all-reduce
+        sob = []
+        for e in ids:
+            D = 2 * gpu_ctx.entry_order[e]
+            m = qlib.sobol_direction_numbers(D)
+            if D:
+                m, x0 = qlib.sobol_scramble(m, rng.integers(0, 2, (D, 32)), rng.integers(0, 2, (D, 32, 32)))
+            else:
+                x0 = np.zeros(0, dtype=np.uint32)
+            sob.append((m, x0))
+        got = gpu_ctx.eval_range(tau[ki], tau[kw], tau[kf], ids, N, 37, 101, sobol=sob)
+        ref = o.eval(tau[ki], tau[kw], tau[kf], ids, N, start=37, count=101, corr_idx=corr, sobol=sob)
+        assert relerr(got, ref) < RTOL, ("range", mode, corr, relerr(got, ref))
+
+
+def test_inchworm_golden(gpu_ctx, qlib):
+    """test/inchworm.jl:179-212: full inchworm! + correlator_2p against test/inchworm.h5."""
+    from qinchworm_b200.expansion import add_corr_operators
+    from qinchworm_b200.inchworm import Solver, correlator_2p, inchworm
+    G = load_golden("inchworm_h5.json")
+    ex, grid, f = models.single_level(n_tau=20, spline=True)
+    solver = Solver(ex, ctx=gpu_ctx)
+    inchworm(ex, grid, range(0, 4), range(0, 3), 2 ** 8, solver=solver)
+    assert relerr(ex.P[:, 1], G["/inchworm/P/1"].ravel()) < RTOL
+    assert relerr(ex.P[:, 0], G["/inchworm/P/2"].ravel()) < RTOL
+    add_corr_operators(ex, (f.c("0"), f.c_dag("0")))
+    g = -correlator_2p(ex, grid, range(0, 4), 2 ** 8, solver=solver)[0]
+    assert relerr(g, G["/inchworm/g"].ravel()) < RTOL
+
+
+def test_hubbard_dimer_physics(gpu_ctx, qlib):
+    """test/dimers.jl:124-196: density matrix of the Hubbard dimer vs exact ED (< 1e-4)."""
+    from qinchworm_b200 import ppgf
+    from qinchworm_b200.inchworm import Solver, inchworm
+    ex, grid, f = models.hubbard_dimer_impurity(n_tau=32)
+    inchworm(ex, grid, range(0, 3), range(0, 3), 8 * 2 ** 5, solver=Solver(ex, ctx=gpu_ctx))
+    ppgf.normalize(ex)
+    rho = ex.ed.to_fock_basis(ppgf.density_matrix(ex))
+    ref = models.hubbard_dimer_exact_rho()
+    assert np.abs(rho - ref).max() < 1e-4
