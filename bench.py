@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py — qMC diagram evaluations/sec and inchworm! wall time on the README Anderson configuration.
+
+Workload (BASELINE.json configs[0], the configuration the metric is quoted on): single-orbital
+Anderson model on a Bethe bath, beta=10, U=1, eps=0.1, V=0.5, n_tau=200, orders 0:4, orders_bare 0:4,
+N_samples = 2^10 per GPU (weak scaling: N_samples = 2^10 * n_gpus, each GPU takes a disjoint Sobol
+index range, one ncclAllReduce per inchworm step).  One "step" = one complete inchworm! run
+(bare step + 198 bold steps) = 5.69e7 diagram evaluations per 2^10 samples.
+
+    value : diagram evaluations/s of the device-resident run (qiw_inchworm_run; tables resident in
+            HBM, CUDA events on the library's stream around the whole run), max over ranks
+    e2e   : the same metric through the reference-shaped host API inchworm(expansion, grid, orders,
+            orders_bare, N_samples): one qiw_eval per step with HOST buffers — the P table goes
+            host->device and the per-entry results device->host inside the timed region
+    roofline     : dominant kernel (step kernel, tree depth <= 11 = orders 3-4) against the FP64 FMA
+                   peak measured in the same process by a DFMA-saturating kernel
+    cpu_baseline : the CPU oracle port (faithful restatement of the reference algorithm), all host
+                   cores, on a bounded sample of the same workload
+
+`--impl reference` times the CPU port alone (the Julia reference cannot run here: no Julia).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ORDERS = range(0, 5)
+N_TAU = 200
+N_PER_GPU = 2 ** 10
+METRIC = "qmc_diagram_evals_per_sec"
+UNIT = "diagram_evals/s"
+
+
+def workload_config(n_gpus, N):
+    return {"workload": "C1 README single-orbital Anderson, Bethe bath (beta=10,U=1,eps=0.1,V=0.5), n_tau=200, "
+                        "orders 0:4, orders_bare 0:4; one step = one full inchworm! run",
+            "N_samples": N, "n_tau": N_TAU, "orders": "0:4", "orders_bare": "0:4", "samples_per_gpu": N_PER_GPU,
+            "parallelism": "sobol-index-shard x%d, 1 ncclAllReduce/step" % n_gpus,
+            "l2": "working set (tables+programs < 1 MB) is cache-resident by construction; 256 MiB L2 flush "
+                  "write between timed runs"}
+
+
+def diagram_evals(N, n_tau=N_TAU, bold_steps=None):
+    """N*[sum bare (2n-1)!!] + (n_tau-2)*N*280 (+ the order-0 single evaluations)."""
+    bare = 1 + N * (1 + 3 + 15 + 105)
+    steps = (n_tau - 2) if bold_steps is None else bold_steps
+    return bare + steps * (1 + N * 280)
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, device_index):
+        super().__init__(daemon=True)
+        self.dev, self.samples, self.reasons, self.stop_flag, self.max_mhz = device_index, [], set(), False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_port_run(threads, bold_steps, N):
+    """Bounded sample of the workload on the CPU oracle port: bare step + first `bold_steps` bold steps."""
+    import models
+    from oracle import oracle as orc
+    ex, grid, f = models.anderson(n_tau=N_TAU)
+    pl = ex.flatten()
+    t0 = time.perf_counter()
+    res = orc.inchworm(pl, ex.P, ORDERS, ORDERS, N, threads=threads, max_bold_steps=bold_steps)
+    dt = time.perf_counter() - t0
+    return res["evals"] / dt, dt, res["evals"]
+
+
+def run_reference(args):
+    """Reference arm: the reference's own (CPU) implementation of the path.  The Julia package cannot
+    run here (no Julia toolchain in the image), so the oracle port stands in, on all host cores."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    bold_steps = 6
+    N = N_PER_GPU
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt, ev = cpu_port_run(cores, bold_steps, N)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+    sample = "bare step + first %d of %d bold steps at N_samples=%d, %d host threads (split_count rule)" % (
+        bold_steps, N_TAU - 2, N, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus, N),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle port (C++ restatement of the reference algorithm); the Julia+MPI reference itself cannot run: no Julia in the image"}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import models
+    from qinchworm_b200 import lib, mpi
+    from qinchworm_b200.inchworm import Solver, inchworm
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    args.warmup = max(args.warmup, 3)
+    N = N_PER_GPU * world
+
+    # ---- set-up (untimed): model, tables, compiled entries resident on the device ----
+    ex, grid, f = models.anderson(n_tau=N_TAU)
+    P_atomic = ex.P.copy()
+    ctx = lib.Context(device=local)
+    solver = Solver(ex, ctx=ctx)
+    if world > 1:
+        mpi.init_comm(ctx)
+    from qinchworm_b200.inchworm import MODE_BARE, _bold_entries
+    bare = [solver.make_entry(MODE_BARE, o, 2 * o, N) for o in ORDERS]
+    bold = _bold_entries(solver, ORDERS, N, None, None)
+    bare_ids, bold_ids = [t.entry_id for t in bare], [t.entry_id for t in bold]
+    stats = {t.entry_id: ctx.entry_stats(t.entry_id) for t in bare + bold}
+    flops_bold_sample = sum(stats[i]["flops_per_sample"] for i in bold_ids)
+    flops_deep_sample = sum(stats[t.entry_id]["flops_per_sample"] for t in bold if t.order >= 3)
+    evals_per_run = diagram_evals(N)
+    fp64_peak = ctx.measure_fp64_peak()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def device_run():
+        ctx.set_P(0, P_atomic)
+        ctx.inchworm_run(bare_ids, bold_ids, N, want_contribs=False)
+        return ctx.last_device_ms()
+
+    # ---- value: device-resident run, K steps ----
+    for _ in range(args.warmup):
+        device_run()
+    l0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)          # L2 flush between timed runs (not inside the event bracket)
+        torch.cuda.synchronize()
+        dev_ms.append(device_run())
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    launches = ctx.launch_count() - l0
+    ms_per_step = max_over_ranks(float(np.mean(dev_ms)))
+    wall_ms = max_over_ranks(wall_ms)
+    value = evals_per_run / (ms_per_step * 1e-3)
+    P_dev = ctx.get_P()
+
+    # ---- e2e: host-driven inchworm() through the step-level C ABI with host buffers ----
+    def host_run():
+        ex.P[:] = P_atomic
+        t = time.perf_counter()
+        inchworm(ex, grid, ORDERS, ORDERS, N, solver=solver)
+        return (time.perf_counter() - t) * 1e3
+    host_run()
+    barrier()
+    e2e_ms = float(np.mean([host_run() for _ in range(max(2, min(args.steps, 3)))]))
+    barrier()
+    e2e_ms = max_over_ranks(e2e_ms)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    e2e_value = evals_per_run / (e2e_ms * 1e-3)
+    parity = float(np.abs(ex.P - P_dev).max() / np.abs(P_dev).max())
+    bs = ctx.bsize
+    h2d = (N_TAU - 1) * N_TAU * bs * 16                          # qiw_set_P after every step
+    d2h = len(bare_ids) * bs * 16 + (N_TAU - 2) * len(bold_ids) * bs * 16
+
+    # ---- roofline of the dominant kernel: one profiled run (event pair around every launch) ----
+    ctx.profile_enable(True)
+    ctx.profile_read(reset=True)
+    device_run()
+    prof = ctx.profile_read(reset=True)
+    ctx.profile_enable(False)
+    dom = prof.get("step_depth11", {"ms": float("nan"), "launches": 1})
+    n_count = mpi.split_count(N, world)[rank]
+    dom_ms = dom["ms"] / max(dom["launches"], 1)
+    dom_flops = flops_deep_sample * n_count                       # algorithmic chain FLOPs of one launch
+    achieved = dom_flops / (dom_ms * 1e-3) / 1e12
+    total_prof = sum(v["ms"] for v in prof.values())
+    roofline = {"bound": "fp64_fma", "kernel": "scalar_step_kernel<11> (bold orders 3-4)", "achieved": achieved,
+                "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                "peak_source": "measured in this process by qiw_measure_fp64_peak (DFMA-saturating kernel); "
+                               "MEASURED_PEAKS.json has no FP64 entry",
+                "flops_per_launch": dom_flops, "ms_per_launch": dom_ms, "traffic": None,
+                "kernel_share_of_step": dom["ms"] / total_prof if total_prof else None,
+                "profile_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
+                "profile_launches": {k: v["launches"] for k, v in prof.items()},
+                "whole_run_frac": (flops_bold_sample * n_count * (N_TAU - 2)) / (ms_per_step * 1e-3) / 1e12 / fp64_peak}
+
+    # ---- CPU baseline: oracle port on a bounded sample, rank 0 at N=1 only ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        steps_cpu = 4
+        v, dt, ev = cpu_port_run(cores, steps_cpu, N_PER_GPU)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
+               "sample": "bare step + first %d of %d bold steps at N_samples=%d (%.3g diagram evals), %d threads"
+                         % (steps_cpu, N_TAU - 2, N_PER_GPU, ev, cores)}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(world, N),
+            "inchworm_wall_ms": {"device_resident_events": ms_per_step, "device_resident_host_clock": wall_ms,
+                                 "host_driven_e2e": e2e_ms},
+            "diagram_evals_per_step": evals_per_run,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "qinchworm_b200.inchworm.inchworm(expansion, grid, orders, orders_bare, N_samples)",
+                    "max_rel_diff_vs_device_resident": parity},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary()}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

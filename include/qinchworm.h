@@ -186,6 +186,15 @@ int qiw_last_device_ms(qiw_context* ctx, double* ms);
 /* Number of kernel launches issued by this context so far. */
 int qiw_launch_count(qiw_context* ctx, int64_t* n);
 
+/* Per-kernel device timing (CUDA events on the launching stream around every launch).  Classes:
+ * 0..3 step kernel for tree depth <= 7 / 11 / 15 / 19 positions, 4 reduction, 5 per-step state update,
+ * 6 NCCL all-reduce.  Profiling serialises nothing but adds two event records per launch; keep it
+ * off for timed runs.  qiw_profile_read synchronises, returns accumulated ms and launch counts per
+ * class (arrays of QIW_PROFILE_CLASSES) and optionally resets them. */
+#define QIW_PROFILE_CLASSES 8
+int qiw_profile_enable(qiw_context* ctx, int32_t on);
+int qiw_profile_read(qiw_context* ctx, double* ms, int64_t* launches, int32_t reset);
+
 /* ---- whole inchworm run on the device (replaces the loop of inchworm!, src/inchworm.jl:474-493) -- */
 
 /* Runs the bare step (entries bare_ids at grid[0] -> grid[1]) followed by the bold steps

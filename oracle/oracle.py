@@ -243,7 +243,7 @@ def _diag_idx(dims):
 
 
 def inchworm(payload, P0_table, orders, orders_bare, N_samples, n_pts_after_max=None, threads=1,
-             n_ranks=1):
+             n_ranks=1, max_bold_steps=None):
     """inchworm!(expansion, grid, orders, orders_bare, N_samples) on the oracle.
 
     Returns dict(P=[n_tau,bsize] final (per-step normalised) table, P_orders={order: [n_tau,bsize]},
@@ -295,6 +295,8 @@ def inchworm(payload, P0_table, orders, orders_bare, N_samples, n_pts_after_max=
             bold_ids.append(eid); bold_orders.append(order); eid += 1
             n_top_bold += (N_samples if order > 0 else 1) * len(parity)
     for n in range(1, n_tau - 1):  # Julia n = 2 : n_tau-1  ->  tau_w = tau[n], tau_f = tau[n+1]
+        if max_bold_steps is not None and n > max_bold_steps:
+            break  # bounded sample for CPU-baseline timing
         res = run(bold_ids, tau[0], tau[n], tau[n + 1])
         for j, order in enumerate(bold_orders):
             P_orders[order][n + 1] += res[j]

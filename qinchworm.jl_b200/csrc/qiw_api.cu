@@ -18,8 +18,10 @@
 
 namespace qiw {
 cudaError_t launch_scalar_step(int maxl, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st);
-cudaError_t launch_reduce(const DevEntryDyn* dyn, const int* entry_ids, const double2* partials,
-                          const int* rows_per_item, int S, double2* out, int n_entries, cudaStream_t st);
+cudaError_t launch_reduce(const DevEntryDyn* dyn, const DevEntry* entries, const double2* partials, int pitch, int S,
+                          double t_i, double t_w, double t_f, double2* out, int n_entries, cudaStream_t st);
+cudaError_t launch_finish_step(double2* P, int n_tau, int bsize, const int* diag, int n_diag, double h, int k_f,
+                               const double2* contribs, int n_contrib, int do_normalize, double2* hist, cudaStream_t st);
 cudaError_t launch_sobol_points(int D, const uint32_t* m, const uint32_t* x0, unsigned long long start,
                                 unsigned long long count, uint32_t* out, cudaStream_t st);
 cudaError_t launch_dfma_peak(double* out, int blocks, int iters, cudaStream_t st);
@@ -96,13 +98,16 @@ struct Plan {   // launch plan of one qiw_eval call shape, cached
     std::vector<int> ids;
     uint64_t count = 0;
     bool explicit_mode = false;
-    struct Group { int maxl; int item0, n_items; int grid_x; size_t smem; int max_slots; };
+    struct Group { int maxl; int item0, n_items; size_t smem; int max_slots; };
     std::vector<Group> groups;
     std::vector<WorkItem> items;
     std::vector<uint32_t> chunk_tree0;
-    std::vector<int> entry_chunk_base;     // indexed by entry id
-    std::vector<int> rows_per_item;        // per call entry
+    std::vector<int> entry_chunk_base;     // per call entry
     std::vector<int> item0, n_items;       // per call entry
+    std::vector<DevEntryDyn> h_dyn;        // per call entry
+    DevBuf<DevEntryDyn> d_dyn;
+    DevBuf<double2> d_partials, d_out;
+    bool dyn_resident = false;
     size_t partial_rows = 0;
     uint64_t max_sb = 1;
     int pitch = 1;
@@ -112,7 +117,7 @@ struct Plan {   // launch plan of one qiw_eval call shape, cached
     bool default_sobol_resident = false;
     DevBuf<WorkItem> d_items;
     DevBuf<uint32_t> d_chunk_tree0;
-    DevBuf<int> d_entry_chunk_base, d_rows_per_item, d_ids;
+    DevBuf<int> d_entry_chunk_base;
 };
 }  // namespace
 
@@ -137,15 +142,20 @@ struct qiw_context {
     std::vector<std::unique_ptr<EntryDev>> entries;
     DevBuf<DevEntry> dEntries;
     bool entries_dirty = true;
-    DevBuf<DevEntryDyn> dDyn;
-    std::vector<DevEntryDyn> hDyn;
-    DevBuf<double2> dPartials, dOut, dPerSample;
+    DevBuf<double2> dPerSample, dHist;
     DevBuf<double> dTimes;
+    DevBuf<int> dDiag;
     double2* hOut = nullptr;  // pinned
     size_t hOutCap = 0;
-    std::unique_ptr<Plan> plan;
+    std::vector<std::unique_ptr<Plan>> plans;
     double last_ms = 0;
     int64_t launches = 0;
+    // optional per-kernel profiling
+    bool profiling = false;
+    struct ProfEv { int cls; cudaEvent_t a, b; };
+    std::vector<ProfEv> prof_events;
+    double prof_ms[QIW_PROFILE_CLASSES] = {0};
+    int64_t prof_n[QIW_PROFILE_CLASSES] = {0};
     // NCCL
     ncclComm_t comm = nullptr;
     int n_ranks = 1, rank = 0;
@@ -159,6 +169,26 @@ struct qiw_context {
             return QIW_ERR_CUDA;                                                              \
         }                                                                                     \
     } while (0)
+
+struct ProfScope {   // records an event pair around one launch when profiling is on
+    qiw_context* ctx; int cls; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(qiw_context* c, int k) : ctx(c), cls(k) {
+        if (!ctx->profiling) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->prof_events.push_back({cls, a, b});
+    }
+};
+
+static void release_plan(Plan& pl);
+static void drop_plans(qiw_context* ctx) {
+    for (auto& pl : ctx->plans) release_plan(*pl);
+    ctx->plans.clear();
+}
 
 static int fail(qiw_context* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -207,15 +237,13 @@ int qiw_destroy(qiw_context* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     cudaStreamSynchronize(ctx->stream);
-    ctx->dP.release(); ctx->dE.release(); ctx->dDeltas.release(); ctx->dEntries.release(); ctx->dDyn.release();
-    ctx->dPartials.release(); ctx->dOut.release(); ctx->dPerSample.release(); ctx->dTimes.release();
+    ctx->dP.release(); ctx->dE.release(); ctx->dDeltas.release(); ctx->dEntries.release();
+    ctx->dPerSample.release(); ctx->dTimes.release(); ctx->dHist.release(); ctx->dDiag.release();
     for (auto& t : ctx->tables) { t.y.release(); t.M.release(); }
     for (auto& e : ctx->entries)
         if (e) { e->words.release(); e->tree_off.release(); e->coefs.release(); e->dslots.release(); e->sobol.release(); }
-    if (ctx->plan) {
-        ctx->plan->d_items.release(); ctx->plan->d_chunk_tree0.release(); ctx->plan->d_entry_chunk_base.release();
-        ctx->plan->d_rows_per_item.release(); ctx->plan->d_ids.release(); ctx->plan->d_sobol.release();
-    }
+    for (auto& pl : ctx->plans) release_plan(*pl);
+    ctx->plans.clear();
     if (ctx->hOut) cudaFreeHost(ctx->hOut);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -279,7 +307,7 @@ int qiw_set_model(qiw_context* ctx, int32_t S, const int32_t* dims, const double
     }
     for (auto& e : ctx->entries) if (e) e->valid = false;   // programs depend on the model
     ctx->entries_dirty = true;
-    ctx->plan.reset();
+    drop_plans(ctx);
     return QIW_OK;
 }
 
@@ -363,7 +391,7 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
     CK(cudaStreamSynchronize(ctx->stream));
     ed.valid = true;
     ctx->entries_dirty = true;
-    ctx->plan.reset();
+    drop_plans(ctx);
     return QIW_OK;
 }
 
@@ -435,14 +463,24 @@ static int sync_static_tables(qiw_context* ctx) {
         CK(ctx->dEntries.upload(de.data(), de.size(), ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->entries_dirty = false;
-        ctx->hDyn.assign(std::max<size_t>(ctx->entries.size(), 1), DevEntryDyn());
-        CK(ctx->dDyn.reserve(ctx->hDyn.size()));
     }
     return QIW_OK;
 }
 
+static void release_plan(Plan& pl) {
+    pl.d_items.release(); pl.d_chunk_tree0.release(); pl.d_entry_chunk_base.release(); pl.d_sobol.release();
+    pl.d_dyn.release(); pl.d_partials.release(); pl.d_out.release();
+}
+
 // Splits every entry's trees into chunks of similar cost and groups chunks into CTA jobs.
-static int build_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_t count, bool explicit_mode) {
+// Plans are cached per (entry list, sample count, mode).
+static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_t count, bool explicit_mode, Plan** out) {
+    for (auto& up : ctx->plans) {
+        Plan& c = *up;
+        if (c.count == count && c.explicit_mode == explicit_mode && (int)c.ids.size() == n_entries &&
+            std::equal(ids, ids + n_entries, c.ids.begin())) { *out = &c; return QIW_OK; }
+    }
+    if (ctx->plans.size() >= 6) { release_plan(*ctx->plans.front()); ctx->plans.erase(ctx->plans.begin()); }
     std::unique_ptr<Plan> pl(new Plan());
     pl->ids.assign(ids, ids + n_entries);
     pl->count = count; pl->explicit_mode = explicit_mode;
@@ -459,20 +497,18 @@ static int build_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint6
     }
     const double target_tasks = (double)ndev_sm * 32.0;
     const double cost_per_task = std::max(192.0, total / target_tasks);
-    pl->entry_chunk_base.assign(ctx->entries.size(), 0);
-    pl->rows_per_item.resize(n_entries); pl->item0.resize(n_entries); pl->n_items.resize(n_entries);
+    pl->entry_chunk_base.assign(n_entries, 0);
+    pl->item0.resize(n_entries); pl->n_items.resize(n_entries);
     std::map<int, std::vector<int>> by_class;
     for (int i = 0; i < n_entries; ++i) by_class[maxl_class(ctx->entries[ids[i]]->prog.n_nodes)].push_back(i);
     for (auto& kv : by_class) {
         Plan::Group g;
         g.maxl = kv.first; g.item0 = (int)pl->items.size(); g.max_slots = 1;
-        uint64_t max_sb = 1;
         for (int i : kv.second) {
             const EntryProgram& p = ctx->entries[ids[i]]->prog;
             const int n_trees = (int)p.tree_off.size() - 1;
             const uint64_t c = p.order == 0 ? 1 : count;
-            const uint64_t n_sb = (c + 31) / 32;
-            max_sb = std::max(max_sb, n_sb);
+            pl->max_sb = std::max<uint64_t>(pl->max_sb, (c + 31) / 32);
             int n_chunks = 1;
             if (!explicit_mode && n_trees > 0) {
                 double per_sb_tasks = std::ceil((double)p.n_edges / cost_per_task);
@@ -480,8 +516,8 @@ static int build_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint6
                 if (n_chunks > W) n_chunks = ((n_chunks + W - 1) / W) * W;   // full CTAs
                 n_chunks = std::min(n_chunks, n_trees);
             }
-            // boundaries by cumulative tree cost
-            pl->entry_chunk_base[ids[i]] = (int)pl->chunk_tree0.size();
+            // chunk boundaries by cumulative tree cost
+            pl->entry_chunk_base[i] = (int)pl->chunk_tree0.size();
             double tot = 0;
             for (int t = 0; t < n_trees; ++t) tot += p.tree_cost[t];
             double acc = 0;
@@ -489,7 +525,7 @@ static int build_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint6
             pl->chunk_tree0.push_back(0);
             for (int t = 0; t < n_trees; ++t) {
                 acc += p.tree_cost[t];
-                while (c_done + 1 < n_chunks && acc >= tot * (double)(c_done + 1) / n_chunks && t + 1 <= n_trees - (n_chunks - c_done - 1)) {
+                while (c_done + 1 < n_chunks && acc >= tot * (double)(c_done + 1) / n_chunks) {
                     pl->chunk_tree0.push_back((uint32_t)(t + 1));
                     ++c_done;
                 }
@@ -499,7 +535,7 @@ static int build_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint6
             pl->item0[i] = (int)pl->items.size();
             for (int c0 = 0; c0 < n_chunks; c0 += W) {
                 WorkItem it;
-                it.entry = ids[i]; it.chunk0 = c0; it.n_chunks = std::min(W, n_chunks - c0);
+                it.entry = ids[i]; it.slot = i; it.chunk0 = c0; it.n_chunks = std::min(W, n_chunks - c0);
                 it.partial0 = (int)pl->items.size();
                 pl->items.push_back(it);
             }
@@ -507,12 +543,10 @@ static int build_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint6
             g.max_slots = std::max(g.max_slots, p.nP + (int)p.dslots.size());
         }
         g.n_items = (int)pl->items.size() - g.item0;
-        g.grid_x = 1;
         g.max_slots = std::max(g.max_slots, (S * W + 31) / 32 + 1);
         g.smem = (size_t)g.max_slots * 32 * sizeof(double2) + (size_t)S * W * 32 * sizeof(double2) +
                  (size_t)(kDevMaxNodes + 1) * 32 * sizeof(double) + (size_t)kDevMaxDim * 32 * sizeof(double) + 32 * sizeof(int);
         if (g.smem > 227 * 1024) return fail(ctx, QIW_ERR_UNSUPPORTED, "per-sample tables exceed shared memory (too many sectors for the scalar kernel)");
-        pl->max_sb = std::max(pl->max_sb, max_sb);
         pl->groups.push_back(g);
     }
     // grid.x (common to all groups = row pitch of the partials buffer): enough sample-block
@@ -523,23 +557,121 @@ static int build_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint6
         pl->pitch = (int)std::min<uint64_t>(pl->max_sb, std::min<uint64_t>(gx, 65535));
     }
     pl->partial_rows = pl->items.size() * (size_t)pl->pitch;
-    for (int i = 0; i < n_entries; ++i) pl->rows_per_item[i] = pl->pitch;
+    // static part of the per-entry call data
+    pl->h_dyn.assign(n_entries, DevEntryDyn());
+    size_t tot = 0;
+    for (int i = 0; i < n_entries; ++i) { pl->sobol_off.push_back(tot); tot += (size_t)ctx->entries[ids[i]]->prog.D * 33 + 1; }
+    pl->h_sobol.assign(tot, 0u);
+    CK(pl->d_sobol.reserve(tot));
+    CK(pl->d_dyn.reserve(n_entries));
+    for (int i = 0; i < n_entries; ++i) {
+        DevEntryDyn& dy = pl->h_dyn[i];
+        dy.sobol = pl->d_sobol.p + pl->sobol_off[i];
+        dy.entry = ids[i]; dy.out_index = i; dy.item0 = pl->item0[i]; dy.n_items = pl->n_items[i];
+    }
     CK(pl->d_items.upload(pl->items.data(), pl->items.size(), ctx->stream));
     CK(pl->d_chunk_tree0.upload(pl->chunk_tree0.data(), pl->chunk_tree0.size(), ctx->stream));
     CK(pl->d_entry_chunk_base.upload(pl->entry_chunk_base.data(), pl->entry_chunk_base.size(), ctx->stream));
-    CK(pl->d_rows_per_item.upload(pl->rows_per_item.data(), pl->rows_per_item.size(), ctx->stream));
-    CK(pl->d_ids.upload(pl->ids.data(), pl->ids.size(), ctx->stream));
-    CK(ctx->dPartials.reserve(pl->partial_rows * S));
-    CK(ctx->dOut.reserve((size_t)n_entries * ctx->model.bsize));
+    CK(pl->d_partials.reserve(pl->partial_rows * S));
+    CK(pl->d_out.reserve((size_t)n_entries * ctx->model.bsize));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->plan = std::move(pl);
+    ctx->plans.push_back(std::move(pl));
+    *out = ctx->plans.back().get();
     return QIW_OK;
 }
 
-static double simplex_volume(int d, double edge) {  // src/qmc_integrate.jl:46
-    double v = 1.0;
-    for (int i = 1; i <= d; ++i) v *= edge / i;
-    return v;
+// Per-call data of a plan: Sobol parameters, sample range, weights.
+static int stage_call(qiw_context* ctx, Plan& pl, const uint32_t* sobol_m, const uint32_t* sobol_x0, uint64_t start,
+                      uint64_t count, uint64_t N_total, bool allreduce) {
+    const int n_entries = (int)pl.ids.size();
+    const bool default_sobol = (sobol_m == nullptr && sobol_x0 == nullptr);
+    if (!(default_sobol && pl.default_sobol_resident)) {
+        size_t moff = 0, xoff = 0;
+        for (int i = 0; i < n_entries; ++i) {
+            EntryDev& ed = *ctx->entries[pl.ids[i]];
+            const int D = ed.prog.D;
+            uint32_t* sb = pl.h_sobol.data() + pl.sobol_off[i];
+            memcpy(sb, sobol_m ? sobol_m + moff : ed.default_sobol.data(), (size_t)D * 32 * sizeof(uint32_t));
+            if (sobol_x0) memcpy(sb + (size_t)D * 32, sobol_x0 + xoff, (size_t)D * sizeof(uint32_t));
+            else memset(sb + (size_t)D * 32, 0, (size_t)D * sizeof(uint32_t));
+            moff += (size_t)D * 32; xoff += D;
+        }
+        CK(cudaMemcpyAsync(pl.d_sobol.p, pl.h_sobol.data(), pl.h_sobol.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        pl.default_sobol_resident = default_sobol;
+    }
+    bool changed = !pl.dyn_resident;
+    for (int i = 0; i < n_entries; ++i) {
+        const EntryProgram& p = ctx->entries[pl.ids[i]]->prog;
+        DevEntryDyn& dy = pl.h_dyn[i];
+        unsigned long long s2, c2;
+        double w;
+        if (p.order == 0) {
+            // exact entries are identical on every rank: only rank 0 contributes to the sum
+            s2 = 0; c2 = 1; w = (allreduce && ctx->rank != 0) ? 0.0 : 1.0;
+        } else {
+            s2 = start; c2 = count; w = pl.explicit_mode ? 1.0 : 1.0 / (double)N_total;
+        }
+        if (dy.start != s2 || dy.count != c2 || dy.weight != w) changed = true;
+        dy.start = s2; dy.count = c2; dy.weight = w;
+    }
+    if (changed) {
+        CK(cudaMemcpyAsync(pl.d_dyn.p, pl.h_dyn.data(), pl.h_dyn.size() * sizeof(DevEntryDyn), cudaMemcpyHostToDevice, ctx->stream));
+        pl.dyn_resident = true;
+    }
+    return QIW_OK;
+}
+
+// Enqueue the kernels of one evaluation of a plan at fixed times: step kernels (one per tree-depth
+// class) + the deterministic reduction.  Nothing is synchronised here.
+static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, double t_f) {
+    const HostModel& m = ctx->model;
+    StepParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.entries = ctx->dEntries.p; sp.dyn = pl.d_dyn.p;
+    sp.chunk_tree0 = pl.d_chunk_tree0.p; sp.entry_chunk_base = pl.d_entry_chunk_base.p;
+    sp.P = ctx->dP.p; sp.E = ctx->dE.p; sp.deltas = ctx->dDeltas.p;
+    sp.S = m.S; sp.bsize = m.bsize; sp.n_tau = ctx->n_tau; sp.h = ctx->beta / (ctx->n_tau - 1);
+    sp.t_i = t_i; sp.t_w = t_w; sp.t_f = t_f;
+    sp.partials = pl.d_partials.p;
+    if (pl.explicit_mode) { sp.explicit_times = ctx->dTimes.p; sp.per_sample_out = ctx->dPerSample.p; }
+    for (auto& g : pl.groups) {
+        StepParams gp = sp;
+        gp.items = pl.d_items.p + g.item0;
+        gp.max_slots = g.max_slots;
+        dim3 grid((unsigned)pl.pitch, (unsigned)g.n_items);
+        {
+            ProfScope ps(ctx, g.maxl <= 7 ? 0 : g.maxl <= 11 ? 1 : g.maxl <= 15 ? 2 : 3);
+            CK(launch_scalar_step(g.maxl, gp, grid, ctx->warps * 32, g.smem, ctx->stream));
+        }
+        ctx->launches++;
+    }
+    if (!pl.explicit_mode) {
+        {
+            ProfScope ps(ctx, 4);
+            CK(launch_reduce(pl.d_dyn.p, ctx->dEntries.p, pl.d_partials.p, pl.pitch, m.S, t_i, t_w, t_f, pl.d_out.p,
+                             (int)pl.ids.size(), ctx->stream));
+        }
+        ctx->launches++;
+    }
+    return QIW_OK;
+}
+
+static int nccl_allreduce(qiw_context* ctx, double2* buf, size_t n_complex) {
+    if (!ctx->comm) return QIW_OK;
+    ProfScope ps(ctx, 6);
+    int nrc = g_nccl.AllReduce(buf, buf, n_complex * 2, kNcclDouble, kNcclSum, ctx->comm, ctx->stream);
+    if (nrc) return fail(ctx, QIW_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "error"));
+    return QIW_OK;
+}
+
+static int ensure_host_out(qiw_context* ctx, size_t n) {
+    if (ctx->hOutCap < n) {
+        if (ctx->hOut) cudaFreeHost(ctx->hOut);
+        ctx->hOut = nullptr; ctx->hOutCap = 0;
+        CK(cudaMallocHost((void**)&ctx->hOut, n * sizeof(double2)));
+        ctx->hOutCap = n;
+    }
+    return QIW_OK;
 }
 
 // Common body of qiw_eval / qiw_eval_range / qiw_eval_at_times (scalar models).
@@ -551,99 +683,27 @@ static int eval_scalar(qiw_context* ctx, double t_i, double t_w, double t_f, int
     const bool explicit_mode = explicit_times != nullptr;
     int rc = sync_static_tables(ctx);
     if (rc) return rc;
-    bool same = ctx->plan && ctx->plan->count == count && ctx->plan->explicit_mode == explicit_mode &&
-                (int)ctx->plan->ids.size() == n_entries && std::equal(ids, ids + n_entries, ctx->plan->ids.begin());
-    if (!same) { rc = build_plan(ctx, n_entries, ids, count, explicit_mode); if (rc) return rc; }
-    Plan& pl = *ctx->plan;
-    // per-call dynamic data: Sobol parameters of every entry, staged into one buffer
-    const bool default_sobol = (sobol_m == nullptr && sobol_x0 == nullptr);
-    if (pl.sobol_off.empty()) {
-        size_t tot = 0;
-        for (int i = 0; i < n_entries; ++i) { pl.sobol_off.push_back(tot); tot += (size_t)ctx->entries[ids[i]]->prog.D * 33 + 1; }
-        pl.h_sobol.assign(tot, 0u);
-        CK(pl.d_sobol.reserve(tot));
-    }
-    if (!(default_sobol && pl.default_sobol_resident)) {
-        size_t moff = 0, xoff = 0;
-        for (int i = 0; i < n_entries; ++i) {
-            EntryDev& ed = *ctx->entries[ids[i]];
-            const int D = ed.prog.D;
-            uint32_t* sb = pl.h_sobol.data() + pl.sobol_off[i];
-            memcpy(sb, sobol_m ? sobol_m + moff : ed.default_sobol.data(), (size_t)D * 32 * sizeof(uint32_t));
-            if (sobol_x0) memcpy(sb + (size_t)D * 32, sobol_x0 + xoff, (size_t)D * sizeof(uint32_t));
-            else memset(sb + (size_t)D * 32, 0, (size_t)D * sizeof(uint32_t));
-            moff += (size_t)D * 32; xoff += D;
-        }
-        CK(cudaMemcpyAsync(pl.d_sobol.p, pl.h_sobol.data(), pl.h_sobol.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-        pl.default_sobol_resident = default_sobol;
-    }
-    for (int i = 0; i < n_entries; ++i) {
-        EntryDev& ed = *ctx->entries[ids[i]];
-        const EntryProgram& p = ed.prog;
-        const int D = p.D;
-        DevEntryDyn& dy = ctx->hDyn[ids[i]];
-        dy.sobol = pl.d_sobol.p + pl.sobol_off[i];
-        dy.out_index = i;
-        dy.item0 = pl.item0[i]; dy.n_items = pl.n_items[i];
-        if (p.order == 0) {
-            dy.start = 0; dy.count = 1;
-            // exact entries are identical on every rank: only rank 0 contributes to the sum
-            const double w = (allreduce && ctx->rank != 0) ? 0.0 : 1.0;
-            dy.scale = make_double2(w, 0.0);
-        } else {
-            dy.start = start; dy.count = count;
-            const int d_after = (p.mode == 0) ? D : p.n_pts_after, d_before = D - d_after;
-            double jac = (p.mode == 0) ? simplex_volume(D, t_f - t_i)
-                                        : simplex_volume(d_before, t_w - t_i) * simplex_volume(d_after, t_f - t_w);
-            // (-i)^D with D even: (-1)^order  (src/qmc_integrate.jl:565-569,610)
-            const double dir = (p.order & 1) ? -1.0 : 1.0;
-            dy.scale = make_double2(explicit_mode ? 1.0 : dir * jac / (double)N_total, 0.0);
-        }
-    }
-    CK(cudaMemcpyAsync(ctx->dDyn.p, ctx->hDyn.data(), ctx->hDyn.size() * sizeof(DevEntryDyn), cudaMemcpyHostToDevice, ctx->stream));
-    StepParams sp;
-    memset(&sp, 0, sizeof(sp));
-    sp.entries = ctx->dEntries.p; sp.dyn = ctx->dDyn.p; sp.items = pl.d_items.p;
-    sp.chunk_tree0 = pl.d_chunk_tree0.p; sp.entry_chunk_base = pl.d_entry_chunk_base.p;
-    sp.P = ctx->dP.p; sp.E = ctx->dE.p; sp.deltas = ctx->dDeltas.p;
-    sp.S = S; sp.bsize = m.bsize; sp.n_tau = ctx->n_tau; sp.h = ctx->beta / (ctx->n_tau - 1);
-    sp.t_i = t_i; sp.t_w = t_w; sp.t_f = t_f; sp.times_dev = nullptr;
-    sp.partials = ctx->dPartials.p;
+    Plan* plp = nullptr;
+    rc = get_plan(ctx, n_entries, ids, count, explicit_mode, &plp);
+    if (rc) return rc;
+    Plan& pl = *plp;
+    rc = stage_call(ctx, pl, sobol_m, sobol_x0, start, count, N_total, allreduce);
+    if (rc) return rc;
     if (explicit_mode) {
         const int D = ctx->entries[ids[0]]->prog.D;
         CK(ctx->dTimes.upload(explicit_times, (size_t)n_explicit * std::max(D, 1), ctx->stream));
         CK(ctx->dPerSample.reserve((size_t)n_explicit * S));
         CK(cudaMemsetAsync(ctx->dPerSample.p, 0, (size_t)n_explicit * S * sizeof(double2), ctx->stream));
-        sp.explicit_times = ctx->dTimes.p; sp.per_sample_out = ctx->dPerSample.p;
     }
-    const int pitch = pl.pitch;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    for (auto& g : pl.groups) {
-        StepParams gp = sp;
-        gp.items = pl.d_items.p + g.item0;
-        gp.max_slots = g.max_slots;
-        // partial rows are addressed as (item.partial0 * gridDim.x + blockIdx.x): make the pitch
-        // explicit by launching every group with the common pitch in x
-        dim3 grid((unsigned)pitch, (unsigned)g.n_items);
-        CK(launch_scalar_step(g.maxl, gp, grid, ctx->warps * 32, g.smem, ctx->stream));
-        ctx->launches++;
-    }
-    if (!explicit_mode) {
-        CK(launch_reduce(ctx->dDyn.p, pl.d_ids.p, ctx->dPartials.p, pl.d_rows_per_item.p, S, ctx->dOut.p, n_entries, ctx->stream));
-        ctx->launches++;
-    }
+    rc = enqueue_step(ctx, pl, t_i, t_w, t_f);
+    if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     const size_t n_out = explicit_mode ? (size_t)n_explicit * S : (size_t)n_entries * m.bsize;
-    double2* src = explicit_mode ? ctx->dPerSample.p : ctx->dOut.p;
-    if (allreduce && ctx->comm && !explicit_mode) {
-        int nrc = g_nccl.AllReduce(src, src, n_out * 2, kNcclDouble, kNcclSum, ctx->comm, ctx->stream);
-        if (nrc) return fail(ctx, QIW_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "error"));
-    }
-    if (ctx->hOutCap < n_out) {
-        if (ctx->hOut) cudaFreeHost(ctx->hOut);
-        CK(cudaMallocHost((void**)&ctx->hOut, n_out * sizeof(double2)));
-        ctx->hOutCap = n_out;
-    }
+    double2* src = explicit_mode ? ctx->dPerSample.p : pl.d_out.p;
+    if (allreduce && !explicit_mode) { rc = nccl_allreduce(ctx, src, n_out); if (rc) return rc; }
+    rc = ensure_host_out(ctx, n_out);
+    if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->hOut, src, n_out * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
@@ -703,9 +763,82 @@ int qiw_eval_at_times(qiw_context* ctx, int32_t entry_id, double t_i, double t_w
 int qiw_last_device_ms(qiw_context* ctx, double* ms) { if (!ctx || !ms) return QIW_ERR_BAD_ARG; *ms = ctx->last_ms; return QIW_OK; }
 int qiw_launch_count(qiw_context* ctx, int64_t* n) { if (!ctx || !n) return QIW_ERR_BAD_ARG; *n = ctx->launches; return QIW_OK; }
 
-int qiw_inchworm_run(qiw_context* ctx, int32_t, const int32_t*, int32_t, const int32_t*, const uint32_t*, const uint32_t*,
-                     uint64_t, double*) {
-    return fail(ctx, QIW_ERR_UNSUPPORTED, "qiw_inchworm_run: not implemented in this build");
+// inchworm!'s loop (src/inchworm.jl:400-493) with the per-step state update on the device.
+int qiw_inchworm_run(qiw_context* ctx, int32_t n_bare, const int32_t* bare_ids, int32_t n_bold, const int32_t* bold_ids,
+                     const uint32_t* sobol_m, const uint32_t* sobol_x0, uint64_t N_total, double* order_contribs) {
+    int rc = check_entries(ctx, n_bare, bare_ids, "qiw_inchworm_run");
+    if (rc) return rc;
+    if (n_bold > 0) { rc = check_entries(ctx, n_bold, bold_ids, "qiw_inchworm_run"); if (rc) return rc; }
+    if (N_total == 0 || N_total > 0xFFFFFFFFull) return fail(ctx, QIW_ERR_BAD_ARG, "qiw_inchworm_run: bad N_total");
+    for (int i = 0; i < n_bare; ++i) if (ctx->entries[bare_ids[i]]->prog.mode != QIW_MODE_BARE) return fail(ctx, QIW_ERR_BAD_ARG, "qiw_inchworm_run: bare_ids must hold QIW_MODE_BARE entries");
+    for (int i = 0; i < n_bold; ++i) if (ctx->entries[bold_ids[i]]->prog.mode != QIW_MODE_BOLD) return fail(ctx, QIW_ERR_BAD_ARG, "qiw_inchworm_run: bold_ids must hold QIW_MODE_BOLD entries");
+    cudaSetDevice(ctx->device);
+    const HostModel& m = ctx->model;
+    const int n_tau = ctx->n_tau, bs = m.bsize;
+    const double h = ctx->beta / (n_tau - 1);
+    rc = sync_static_tables(ctx);
+    if (rc) return rc;
+    uint64_t start = 0, count = N_total;
+    rank_sub_range(N_total, ctx->n_ranks, ctx->rank, &start, &count);
+    Plan *pb = nullptr, *pd = nullptr;
+    rc = get_plan(ctx, n_bare, bare_ids, count, false, &pb);
+    if (rc) return rc;
+    if (n_bold > 0) {
+        rc = get_plan(ctx, n_bold, bold_ids, count, false, &pd);
+        if (rc) return rc;
+        rc = get_plan(ctx, n_bare, bare_ids, count, false, &pb);   // re-fetch: building pd may have evicted it
+        if (rc) return rc;
+    }
+    size_t moff = 0, xoff = 0;
+    for (int i = 0; i < n_bare; ++i) { moff += (size_t)ctx->entries[bare_ids[i]]->prog.D * 32; xoff += ctx->entries[bare_ids[i]]->prog.D; }
+    rc = stage_call(ctx, *pb, sobol_m, sobol_x0, start, count, N_total, true);
+    if (rc) return rc;
+    if (n_bold > 0) {
+        rc = stage_call(ctx, *pd, sobol_m ? sobol_m + moff : nullptr, sobol_x0 ? sobol_x0 + xoff : nullptr, start, count, N_total, true);
+        if (rc) return rc;
+    }
+    const int n_hist = n_bare + n_bold;
+    if (order_contribs) {
+        CK(ctx->dHist.reserve((size_t)n_tau * n_hist * bs));
+        CK(cudaMemsetAsync(ctx->dHist.p, 0, (size_t)n_tau * n_hist * bs * sizeof(double2), ctx->stream));
+    }
+    // diagonal element indices of the packed block vector
+    std::vector<int> diag;
+    for (int s = 0; s < m.S; ++s) for (int i = 0; i < m.dim[s]; ++i) diag.push_back(m.boff[s] + i + m.dim[s] * i);
+    CK(ctx->dDiag.upload(diag.data(), diag.size(), ctx->stream));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    // bare step: grid[0] -> grid[1], no normalisation (src/inchworm.jl:400-416)
+    rc = enqueue_step(ctx, *pb, 0.0, 0.0, h);
+    if (rc) return rc;
+    rc = nccl_allreduce(ctx, pb->d_out.p, (size_t)n_bare * bs);
+    if (rc) return rc;
+    {
+        ProfScope ps(ctx, 5);
+        CK(launch_finish_step(ctx->dP.p, n_tau, bs, ctx->dDiag.p, (int)diag.size(), h, 1, pb->d_out.p, n_bare, 0,
+                              order_contribs ? ctx->dHist.p + (size_t)1 * n_hist * bs : nullptr, ctx->stream));
+    }
+    ctx->launches++;
+    // bold steps n = 2 .. n_tau-1 (1-based): tau_w = grid[n], tau_f = grid[n+1] (:474-493)
+    for (int n = 1; n_bold > 0 && n < n_tau - 1; ++n) {
+        rc = enqueue_step(ctx, *pd, 0.0, n * h, (n + 1) * h);
+        if (rc) return rc;
+        rc = nccl_allreduce(ctx, pd->d_out.p, (size_t)n_bold * bs);
+        if (rc) return rc;
+        {
+            ProfScope ps(ctx, 5);
+            CK(launch_finish_step(ctx->dP.p, n_tau, bs, ctx->dDiag.p, (int)diag.size(), h, n + 1, pd->d_out.p, n_bold, 1,
+                                  order_contribs ? ctx->dHist.p + ((size_t)(n + 1) * n_hist + n_bare) * bs : nullptr, ctx->stream));
+        }
+        ctx->launches++;
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (order_contribs)
+        CK(cudaMemcpyAsync(order_contribs, ctx->dHist.p, (size_t)n_tau * n_hist * bs * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_ms = ms;
+    return QIW_OK;
 }
 
 // ---- Sobol / topologies / partitioning -----------------------------------------------------------
@@ -771,7 +904,7 @@ int qiw_comm_init(qiw_context* ctx, int32_t n_ranks, int32_t rank, const uint8_t
     int rc = g_nccl.CommInitRank(&ctx->comm, n_ranks, u, rank);
     if (rc) return fail(ctx, QIW_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
     ctx->n_ranks = n_ranks; ctx->rank = rank;
-    ctx->plan.reset();
+    drop_plans(ctx);
     return QIW_OK;
 }
 
@@ -779,7 +912,33 @@ int qiw_comm_destroy(qiw_context* ctx) {
     if (!ctx) return QIW_ERR_BAD_ARG;
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     ctx->comm = nullptr; ctx->n_ranks = 1; ctx->rank = 0;
-    ctx->plan.reset();
+    drop_plans(ctx);
+    return QIW_OK;
+}
+
+int qiw_profile_enable(qiw_context* ctx, int32_t on) {
+    if (!ctx) return QIW_ERR_BAD_ARG;
+    ctx->profiling = (on != 0) && !ctx->no_device;
+    return QIW_OK;
+}
+
+int qiw_profile_read(qiw_context* ctx, double* ms, int64_t* launches, int32_t reset) {
+    if (!ctx) return QIW_ERR_BAD_ARG;
+    if (!ctx->no_device) {
+        cudaSetDevice(ctx->device);
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (auto& pe : ctx->prof_events) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, pe.a, pe.b) == cudaSuccess) { ctx->prof_ms[pe.cls] += t; ctx->prof_n[pe.cls] += 1; }
+            cudaEventDestroy(pe.a); cudaEventDestroy(pe.b);
+        }
+        ctx->prof_events.clear();
+    }
+    for (int k = 0; k < QIW_PROFILE_CLASSES; ++k) {
+        if (ms) ms[k] = ctx->prof_ms[k];
+        if (launches) launches[k] = ctx->prof_n[k];
+        if (reset) { ctx->prof_ms[k] = 0; ctx->prof_n[k] = 0; }
+    }
     return QIW_OK;
 }
 

@@ -36,17 +36,18 @@ struct DevEntry {
 // Per call, per entry.
 struct DevEntryDyn {
     const uint32_t* sobol;      // m[D][32] followed by x0[D]
-    double2 scale;              // (-i)^d * J / N_total  (1 for exact entries)
+    double weight;              // 1/N_total (sampled entries); 1 or 0 (exact entries, by rank)
     unsigned long long start;   // first Sobol index evaluated by this rank
     unsigned long long count;   // number of Sobol points evaluated by this rank (1 if exact)
+    int entry;                  // id of the compiled entry
     int out_index;              // row of the output
     int item0, n_items;         // this entry's CTA jobs (consecutive rows of the partials buffer)
-    int pad;
 };
 
 // One CTA job: a group of up to `warps` consecutive chunks of one entry.
 struct WorkItem {
-    int entry;        // index into the DevEntry / DevEntryDyn arrays of the call
+    int entry;        // id of the compiled entry (index into the DevEntry table)
+    int slot;         // index of the entry within the call (DevEntryDyn, chunk tables)
     int chunk0;       // first chunk of the group
     int n_chunks;     // chunks in the group (<= warps per CTA)
     int partial0;     // first row of this item in the partials buffer
@@ -57,7 +58,7 @@ struct StepParams {
     const DevEntryDyn* dyn;
     const WorkItem* items;
     const uint32_t* chunk_tree0;   // [total chunks + 1] per-entry chunk -> first tree (concatenated)
-    const int* entry_chunk_base;   // [n entries] offset of the entry's chunks in chunk_tree0
+    const int* entry_chunk_base;   // [call entries] offset of the entry's chunks in chunk_tree0
     // model
     const double2* P;              // [n_tau][bsize]
     const double* E;               // [S] (scalar models) energies + lambda

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256, (MAXL <= 11) ? 2 : 1) scalar_step_kernel(
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const WorkItem it = p.items[blockIdx.y];
     const DevEntry& e = p.entries[it.entry];
-    const DevEntryDyn& dy = p.dyn[it.entry];
+    const DevEntryDyn& dy = p.dyn[it.slot];
     const int S = p.S, D = e.D, n_nodes = e.n_nodes, nP = e.nP, n_slots = e.nP + e.nD;
     const int d_after = e.d_after;
 
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256, (MAXL <= 11) ? 2 : 1) scalar_step_kernel(
     // this warp's chunk of trees
     int tree0 = 0, tree1 = 0;
     if (warp < it.n_chunks) {
-        const uint32_t* ct = p.chunk_tree0 + p.entry_chunk_base[it.entry] + it.chunk0 + warp;
+        const uint32_t* ct = p.chunk_tree0 + p.entry_chunk_base[it.slot] + it.chunk0 + warp;
         tree0 = (int)ct[0];
         tree1 = (int)ct[1];
     }
@@ -311,16 +311,31 @@ __global__ void __launch_bounds__(256, (MAXL <= 11) ? 2 : 1) scalar_step_kernel(
 namespace qiw {
 
 // ---- deterministic reduction of the per-CTA partial sums -------------------------------------
-// One CTA per entry of the call; rows of an entry are consecutive.  out = scale * sum(rows).
+// One CTA per entry of the call; rows of an entry are consecutive.
+// out = weight * (-i)^d * Jacobian * sum(rows): the factors of contour_integral / qmc_integral
+// (src/qmc_integrate.jl:497-507,565-569,597-612) and of the simplex maps (:46,458-463).
+__device__ __forceinline__ double simplex_volume(int d, double edge) {
+    double v = 1.0;
+    for (int i = 1; i <= d; ++i) v *= edge / (double)i;
+    return v;
+}
+
 __global__ void __launch_bounds__(128) reduce_partials_kernel(const DevEntryDyn* __restrict__ dyn,
-                                                              const int* __restrict__ entry_ids,
-                                                              const double2* __restrict__ partials,
-                                                              const int* __restrict__ rows_per_item, int S,
+                                                              const DevEntry* __restrict__ entries,
+                                                              const double2* __restrict__ partials, int pitch, int S,
+                                                              double t_i, double t_w, double t_f,
                                                               double2* __restrict__ out) {
     __shared__ double2 buf[128];
-    const DevEntryDyn& dy = dyn[entry_ids[blockIdx.x]];
-    const int R = rows_per_item[blockIdx.x];
-    const size_t row0 = (size_t)dy.item0 * R, nrows = (size_t)dy.n_items * R;
+    const DevEntryDyn& dy = dyn[blockIdx.x];
+    const DevEntry& e = entries[dy.entry];
+    double scale = dy.weight;
+    if (!e.exact) {
+        const double jac = (e.mode == 0) ? simplex_volume(e.D, t_f - t_i)
+                                         : simplex_volume(e.d_before, t_w - t_i) * simplex_volume(e.d_after, t_f - t_w);
+        const double dir = (e.order & 1) ? -1.0 : 1.0;   // (-i)^(2 order)
+        scale = dir * jac * dy.weight;
+    }
+    const size_t row0 = (size_t)dy.item0 * pitch, nrows = (size_t)dy.n_items * pitch;
     for (int s = 0; s < S; ++s) {
         double2 v = make_double2(0.0, 0.0);
         for (size_t r = threadIdx.x; r < nrows; r += blockDim.x) v = cadd(v, partials[(row0 + r) * S + s]);
@@ -330,8 +345,42 @@ __global__ void __launch_bounds__(128) reduce_partials_kernel(const DevEntryDyn*
             if ((int)threadIdx.x < off) buf[threadIdx.x] = cadd(buf[threadIdx.x], buf[threadIdx.x + off]);
             __syncthreads();
         }
-        if (threadIdx.x == 0) out[(size_t)dy.out_index * S + s] = cmul(dy.scale, buf[0]);
+        if (threadIdx.x == 0) out[(size_t)dy.out_index * S + s] = cscale(scale, buf[0]);
         __syncthreads();
+    }
+}
+
+// ---- per-step state update on the device ---------------------------------------------------------
+// set_ppgf!(P, tau_i, tau_f, result) followed by normalize!(P, tau_f) (src/ppgf.jl:495-504,646-668):
+// P(tau_f) <- sum of the entries' contributions; lambda = log(max_s max diag(-Im P_s(tau_f))) / tau_f;
+// every stored grid value is multiplied by exp(-lambda tau_k).  One CTA; the table is tiny.
+__global__ void __launch_bounds__(256) finish_step_kernel(double2* __restrict__ P, int n_tau, int bsize,
+                                                          const int* __restrict__ diag, int n_diag, double h, int k_f,
+                                                          const double2* __restrict__ contribs, int n_contrib,
+                                                          int do_normalize, double2* __restrict__ hist) {
+    __shared__ double lambda_s;
+    for (int e = threadIdx.x; e < bsize; e += blockDim.x) {
+        double2 v = make_double2(0.0, 0.0);
+        for (int j = 0; j < n_contrib; ++j) {
+            const double2 c = contribs[(size_t)j * bsize + e];
+            v = cadd(v, c);
+            if (hist) hist[(size_t)j * bsize + e] = c;
+        }
+        P[(size_t)k_f * bsize + e] = v;
+    }
+    __syncthreads();
+    if (!do_normalize) return;
+    if (threadIdx.x == 0) {
+        double pmax = -1.0e300;
+        for (int i = 0; i < n_diag; ++i) pmax = fmax(pmax, -P[(size_t)k_f * bsize + diag[i]].y);
+        lambda_s = log(pmax) / ((double)k_f * h);
+    }
+    __syncthreads();
+    const double lambda = lambda_s;
+    for (int idx = threadIdx.x; idx < n_tau * bsize; idx += blockDim.x) {
+        const int k = idx / bsize;
+        const double f = exp(-((double)k * h) * lambda);
+        P[idx] = cscale(f, P[idx]);
     }
 }
 
@@ -368,9 +417,15 @@ cudaError_t launch_scalar_step(int maxl, const StepParams& p, dim3 grid, int thr
     return launch_scalar<19>(p, grid, threads, smem, st);
 }
 
-cudaError_t launch_reduce(const DevEntryDyn* dyn, const int* entry_ids, const double2* partials,
-                          const int* rows_per_item, int S, double2* out, int n_entries, cudaStream_t st) {
-    reduce_partials_kernel<<<n_entries, 128, 0, st>>>(dyn, entry_ids, partials, rows_per_item, S, out);
+cudaError_t launch_reduce(const DevEntryDyn* dyn, const DevEntry* entries, const double2* partials, int pitch, int S,
+                          double t_i, double t_w, double t_f, double2* out, int n_entries, cudaStream_t st) {
+    reduce_partials_kernel<<<n_entries, 128, 0, st>>>(dyn, entries, partials, pitch, S, t_i, t_w, t_f, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finish_step(double2* P, int n_tau, int bsize, const int* diag, int n_diag, double h, int k_f,
+                               const double2* contribs, int n_contrib, int do_normalize, double2* hist, cudaStream_t st) {
+    finish_step_kernel<<<1, 256, 0, st>>>(P, n_tau, bsize, diag, n_diag, h, k_f, contribs, n_contrib, do_normalize, hist);
     return cudaGetLastError();
 }
 

@@ -144,11 +144,26 @@ def inchworm_step(solver: Solver, grid, k_i, k_w, k_f, top_data):
     return _order_sums(top_data, mean, std, solver.ctx.bsize)
 
 
+def _bold_entries(solver, orders, N_samples, rand_params, n_pts_after_max):
+    top_data = []
+    for o in orders:
+        rng = [0] if o == 0 else range(1, min(2 * o - 1, n_pts_after_max or 10 ** 9) + 1)
+        for k in rng:
+            td = solver.make_entry(MODE_BOLD, o, k, N_samples, rand_params)
+            if td is not None:
+                top_data.append(td)
+    return top_data
+
+
 def inchworm(expansion, grid, orders, orders_bare, N_samples, n_pts_after_max=None,
-             rand_params=None, solver=None):
+             rand_params=None, solver=None, device_resident=False):
     """inchworm!(expansion, grid, orders, orders_bare, N_samples; ...) (src/inchworm.jl:332-498).
     Results are written into `expansion.P`; returns (P_orders, P_orders_std): dicts
-    order -> [n_tau, bsize] arrays of order-resolved contributions."""
+    order -> [n_tau, bsize] arrays of order-resolved contributions.
+
+    device_resident=True runs the whole loop inside the library (qiw_inchworm_run): set_ppgf! and
+    normalize! happen on the GPU between steps, with no host round trip.  It requires the default
+    RandomizationParams (one unscrambled or one fixed scrambled sequence reused at every step)."""
     assert N_samples == 0 or (N_samples & (N_samples - 1)) == 0, "N_samples must be a power of 2"
     rand_params = rand_params or RandomizationParams()
     assert rand_params.N_seqs > 0
@@ -157,6 +172,18 @@ def inchworm(expansion, grid, orders, orders_bare, N_samples, n_pts_after_max=No
     orders, orders_bare = list(orders), list(orders_bare)
     P_orders = {o: np.zeros((n_tau, solver.ctx.bsize), dtype=complex) for o in set(orders) | set(orders_bare)}
     P_orders_std = {o: np.zeros((n_tau, solver.ctx.bsize), dtype=complex) for o in P_orders}
+    if device_resident:
+        assert rand_params.rng is None and rand_params.N_seqs == 1, "device-resident loop: default RandomizationParams only"
+        bare = [solver.make_entry(MODE_BARE, o, 2 * o, N_samples, rand_params) for o in orders_bare]
+        bold = _bold_entries(solver, orders, N_samples, rand_params, n_pts_after_max)
+        solver.upload_P()
+        hist = solver.ctx.inchworm_run([td.entry_id for td in bare], [td.entry_id for td in bold], N_samples)
+        expansion.P[:] = solver.ctx.get_P()
+        for j, td in enumerate(bare + bold):
+            P_orders[td.order] += hist[:, j, :]
+        for o in P_orders_std:
+            P_orders_std[o][:] = np.nan   # std of a single sequence (src/randomization.jl:99)
+        return P_orders, P_orders_std
     # first step: bare diagrams (:373-416)
     top_data = [solver.make_entry(MODE_BARE, o, 2 * o, N_samples, rand_params) for o in orders_bare]
     solver.upload_P()
@@ -166,13 +193,7 @@ def inchworm(expansion, grid, orders, orders_bare, N_samples, n_pts_after_max=No
         P_orders[o][1] = contribs[o]
         P_orders_std[o][1] = contribs_std[o]
     # the rest of inching (:420-493)
-    top_data = []
-    for o in orders:
-        rng = [0] if o == 0 else range(1, min(2 * o - 1, n_pts_after_max or 10 ** 9) + 1)
-        for k in rng:
-            td = solver.make_entry(MODE_BOLD, o, k, N_samples, rand_params)
-            if td is not None:
-                top_data.append(td)
+    top_data = _bold_entries(solver, orders, N_samples, rand_params, n_pts_after_max)
     solver.upload_P()
     for n in range(1, n_tau - 1):
         value, contribs, contribs_std = inchworm_step(solver, grid, 0, n, n + 1, top_data)

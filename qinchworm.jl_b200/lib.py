@@ -68,6 +68,8 @@ _SIGNATURES = {
                                     f64p, f64p]),
     "qiw_last_device_ms": (C.c_int, [C.c_void_p, f64p]),
     "qiw_launch_count": (C.c_int, [C.c_void_p, i64p]),
+    "qiw_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
+    "qiw_profile_read": (C.c_int, [C.c_void_p, f64p, i64p, C.c_int32]),
     "qiw_inchworm_run": (C.c_int, [C.c_void_p, C.c_int32, i32p, C.c_int32, i32p, u32p, u32p, C.c_uint64, f64p]),
     "qiw_sobol_direction_numbers": (C.c_int, [C.c_int32, u32p]),
     "qiw_sobol_scramble": (C.c_int, [C.c_int32, u32p, u32p, u8p, u8p]),
@@ -309,6 +311,30 @@ class Context:
         self._ck(self.L.qiw_eval_at_times(self.h, entry_id, t_i, t_w, t_f, times.shape[0], _ptr(times, f64p),
                                           _ptr(out.view(np.float64), f64p)))
         return out
+
+    def inchworm_run(self, bare_ids, bold_ids, N_total, sobol=None, want_contribs=True):
+        """qiw_inchworm_run: the whole inchworm! loop on the device.  Returns the per-entry
+        contributions [n_tau, n_bare + n_bold, bsize] (or None); read P with get_P()."""
+        b = np.ascontiguousarray(bare_ids, dtype=np.int32)
+        d = np.ascontiguousarray(bold_ids, dtype=np.int32)
+        _m, _x, pm, px = self._sobol_args(None, sobol)
+        hist = np.zeros((self.n_tau, len(b) + len(d), self.bsize), dtype=np.complex128) if want_contribs else None
+        self._ck(self.L.qiw_inchworm_run(self.h, len(b), _ptr(b, i32p), len(d), _ptr(d, i32p) if len(d) else None,
+                                         pm, px, N_total,
+                                         _ptr(hist.view(np.float64), f64p) if want_contribs else None))
+        return hist
+
+    PROFILE_CLASSES = ("step_depth7", "step_depth11", "step_depth15", "step_depth19", "reduce", "finish_step",
+                       "nccl_allreduce", "other")
+
+    def profile_enable(self, on=True):
+        self._ck(self.L.qiw_profile_enable(self.h, int(on)))
+
+    def profile_read(self, reset=True):
+        ms = np.zeros(8, dtype=np.float64)
+        n = np.zeros(8, dtype=np.int64)
+        self._ck(self.L.qiw_profile_read(self.h, _ptr(ms, f64p), _ptr(n, i64p), int(reset)))
+        return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(self.PROFILE_CLASSES) if n[i]}
 
     def last_device_ms(self):
         v = C.c_double(0)

@@ -130,3 +130,41 @@ def test_hubbard_dimer_physics(gpu_ctx, qlib):
     rho = ex.ed.to_fock_basis(ppgf.density_matrix(ex))
     ref = models.hubbard_dimer_exact_rho()
     assert np.abs(rho - ref).max() < 1e-4
+
+
+def test_inchworm_device_resident(gpu_ctx, qlib):
+    """qiw_inchworm_run (set_ppgf!/normalize! on the device) against test/inchworm.h5 and against
+    the host-driven loop, including the order-resolved contributions."""
+    from qinchworm_b200.inchworm import Solver, inchworm
+    G = load_golden("inchworm_h5.json")
+    ex, grid, f = models.single_level(n_tau=20, spline=True)
+    Po, _ = inchworm(ex, grid, range(0, 4), range(0, 3), 2 ** 8, solver=Solver(ex, ctx=gpu_ctx), device_resident=True)
+    assert relerr(ex.P[:, 1], G["/inchworm/P/1"].ravel()) < RTOL
+    assert relerr(ex.P[:, 0], G["/inchworm/P/2"].ravel()) < RTOL
+    ex2, grid2, _ = models.single_level(n_tau=20, spline=True)
+    Po2, _ = inchworm(ex2, grid2, range(0, 4), range(0, 3), 2 ** 8, solver=Solver(ex2, ctx=gpu_ctx))
+    assert relerr(ex.P, ex2.P) < RTOL
+    for o in Po:
+        assert relerr(Po[o], Po2[o]) < RTOL
+
+
+def test_readme_anderson_run(gpu_ctx, qlib, oracle_lib):
+    """README.md:34-158 configuration at reduced n_tau (the oracle finishes in seconds): P(tau), Z and
+    rho_imp of the device-resident run vs the oracle, tolerance 1e-10; PH-symmetric variant gives
+    rho = 1/4 (test/bethe.jl:104-126)."""
+    from qinchworm_b200 import ppgf
+    from qinchworm_b200.inchworm import Solver, inchworm
+    ex, grid, f = models.anderson(n_tau=24)
+    ref = oracle_lib.inchworm(ex.flatten(), ex.P, range(0, 5), range(0, 5), 2 ** 7)["P"]
+    inchworm(ex, grid, range(0, 5), range(0, 5), 2 ** 7, solver=Solver(ex, ctx=gpu_ctx), device_resident=True)
+    assert relerr(ex.P, ref) < RTOL
+    Z = ppgf.partition_function(ex)
+    Zref = (1j * ref[-1]).sum()
+    assert abs(Z - Zref) < RTOL * abs(Zref)
+    # particle-hole symmetric point: eps = -U/2
+    ex, grid, f = models.anderson(n_tau=24, eps=-0.5, U=1.0)
+    inchworm(ex, grid, range(0, 3), range(0, 3), 2 ** 8, solver=Solver(ex, ctx=gpu_ctx), device_resident=True)
+    ppgf.normalize(ex)
+    rho = np.array([d[0, 0].real for d in ppgf.density_matrix(ex)])
+    assert np.abs(rho[1] - rho[2]) < 1e-12 and abs(rho.sum() - 1) < 1e-12
+    assert np.abs(rho[0] - rho[3]) < 2e-3

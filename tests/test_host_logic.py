@@ -1,0 +1,183 @@
+"""CPU-side checks of the product's host logic: the C-ABI library loads and exports every symbol
+include/qinchworm.h declares, the integer work (Sobol tables, scrambling, topology enumeration,
+sample partitioning) is bit-exact against the oracle, and the host-side topology compiler
+produces programs that replay to the oracle's values.  No GPU compute is called."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import models
+from program_interp import run_program
+
+
+def test_library_exports_every_declared_symbol(qlib):
+    hdr = open(qlib.HEADER_PATH).read()
+    declared = set(re.findall(r"\b(qiw_[A-Za-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    L = ctypes.CDLL(qlib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), "symbol %s declared in qinchworm.h but not exported" % name
+    assert declared == set(qlib.exported_symbols())
+    assert qlib.load().qiw_version().decode() == "0.1.0"
+
+
+def test_no_cpu_fallback(qlib):
+    """Without a device the compute path must fail loudly; the planning-only context must refuse
+    every compute entry point."""
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(qlib.QiwError):
+            qlib.Context()
+    ex, grid, f = models.single_level(n_tau=10, spline=False)
+    ctx = qlib.Context(device=qlib.DEVICE_NONE)
+    ctx.set_expansion(ex)
+    pr, pa = qlib.topologies(1, 1)
+    ctx.set_topologies(0, qlib.MODE_BOLD, 1, 1, pr, pa)
+    with pytest.raises(qlib.QiwError) as ei:
+        ctx.bsize = 2
+        ctx.eval(0.0, 1.0, 2.0, [0], 16)
+    assert ei.value.code == 2
+    with pytest.raises(qlib.QiwError):
+        ctx.sobol_points(qlib.sobol_direction_numbers(2), None, 0, 4)
+
+
+def test_sobol_host_bit_exact(qlib, oracle_lib):
+    for D in (0, 1, 2, 5, 12, 16, 40):
+        assert np.array_equal(qlib.sobol_direction_numbers(D), oracle_lib.sobol_direction_numbers(D))
+    with pytest.raises(ValueError):
+        qlib.sobol_direction_numbers(65)
+    rng = np.random.default_rng(5)
+    for D in (1, 4, 12):
+        m = qlib.sobol_direction_numbers(D)
+        sb, lb = rng.integers(0, 2, (D, 32)), rng.integers(0, 2, (D, 32, 32))
+        a, b = qlib.sobol_scramble(m, sb, lb), oracle_lib.sobol_scramble(m, sb, lb)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_topologies_bit_exact(qlib, oracle_lib):
+    for n in range(0, 6):
+        for k in [None] + list(range(0, 2 * n)):
+            for ext in (False, True):
+                a, b = qlib.topologies(n, k, ext), oracle_lib.topologies(n, k, ext)
+                assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (n, k, ext)
+    assert len(qlib.topologies(6, 1)[1]) == 2830 + 0 or True
+    assert [len(qlib.topologies(n, 1)[1]) for n in range(1, 7)] == [1, 1, 4, 27, 248, 2830]
+
+
+def test_partitioning(qlib, oracle_lib):
+    from qinchworm_b200 import mpi
+    assert mpi.split_count(10, 3) == [4, 3, 3]
+    assert list(mpi.range_from_chunks_and_idx([4, 3, 3], 2)) == [5, 6, 7]
+    for N in (0, 1, 7, 10, 1024, 2 ** 20 + 3):
+        for R in (1, 2, 3, 8):
+            tot = 0
+            for r in range(R):
+                s, c = qlib.rank_sub_range(N, R, r)
+                assert (s, c) == oracle_lib.rank_sub_range(N, R, r)
+                rr = mpi.rank_sub_range(N, r, R)
+                assert (rr.start - 1, len(rr)) == (s, c)
+                assert s == tot
+                tot += c
+            assert tot == N
+
+
+@pytest.mark.parametrize("model", ["anderson", "single_level", "dimer"])
+def test_compiled_programs_replay_to_oracle(qlib, oracle_lib, model):
+    """qiw_set_topologies (host compiler) vs the oracle's recursive evaluator, all three modes."""
+    from qinchworm_b200.expansion import add_corr_operators
+    rng = np.random.default_rng(11)
+    if model == "anderson":
+        ex, grid, f = models.anderson(n_tau=30, corr=True)
+        max_order = 3
+    elif model == "single_level":
+        ex, grid, f = models.single_level(n_tau=16, spline=True)
+        add_corr_operators(ex, (f.c("0"), f.c_dag("0")))
+        max_order = 4
+    else:
+        ex, grid, f = models.hubbard_dimer_impurity(n_tau=16)
+        add_corr_operators(ex, (f.c(1), f.c_dag(1)))
+        max_order = 3
+    ex.P = ex.P * (1 + 0.1 * rng.random(ex.P.shape))
+    pl = ex.flatten()
+    ctx = qlib.Context(device=qlib.DEVICE_NONE)
+    ctx.set_expansion(ex)
+    o = oracle_lib.Oracle(pl, ex.P)
+    tau = grid.tau
+    eid = 0
+    for mode in (qlib.MODE_BOLD, qlib.MODE_BARE, qlib.MODE_CORR):
+        for corr in range(len(ex.corr_operators) if mode == qlib.MODE_CORR else 1):
+            for order in range(0, max_order + 1):
+                ks = [None] if mode == qlib.MODE_BARE else ([0] if order == 0 else range(1, 2 * order))
+                for k in ks:
+                    pr, pa = qlib.topologies(order, None if mode == qlib.MODE_BARE else k, mode == qlib.MODE_CORR)
+                    if len(pa) == 0 or (order == max_order and k not in (None, 1, 2 * order - 1)):
+                        continue
+                    kk = 2 * order if mode == qlib.MODE_BARE else k
+                    ctx.set_topologies(eid, mode, order, kk, pr, pa, corr_idx=corr)
+                    o.set_topologies(eid, mode, order, kk, pr, pa)
+                    st, prog = ctx.entry_stats(eid), ctx.entry_program(eid)
+                    if mode == qlib.MODE_BARE:
+                        t_i, t_w, t_f = 0.0, tau[0], tau[1]
+                    elif mode == qlib.MODE_BOLD:
+                        t_i, t_w, t_f = 0.0, tau[7], tau[8]
+                    else:
+                        t_i, t_w, t_f = 0.0, tau[9], tau[-1]
+                    times = np.zeros((2, 2 * order))
+                    for i in range(2):
+                        if mode == qlib.MODE_BARE:
+                            times[i] = np.sort(rng.uniform(t_i, t_f, 2 * order))[::-1]
+                        else:
+                            times[i, :kk] = np.sort(rng.uniform(t_w, t_f, kk))[::-1]
+                            times[i, kk:] = np.sort(rng.uniform(t_i, t_w, 2 * order - kk))[::-1]
+                    ref = o.eval_at_times(eid, t_i, t_w, t_f, times, corr_idx=corr)
+                    fl, lv = o.last_counts()
+                    got = np.array([run_program(prog, ex, pl, mode, t_i, t_w, t_f, times[i]) for i in range(2)])
+                    assert np.abs(got - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1e-300)  # interpreter uses SciPy splines
+                    assert st["n_leaves"] == lv and st["flops_per_sample"] == fl and st["n_top"] == len(pa)
+                    eid += 1
+    assert eid > 10
+
+
+def test_offdiagonal_block_is_an_error(qlib):
+    """Under-resolved sectors must be reported like the reference's @assert
+    (src/topology_eval.jl:462), at compile time."""
+    from qinchworm_b200.ed import EDCore, FockSpace
+    from qinchworm_b200.expansion import Expansion, InteractionPair
+    from qinchworm_b200.gf import ImaginaryTimeGrid, delta_dos_gf, ph_conj
+    f = FockSpace([["a"], ["b"]])
+    H = 0.3 * f.n_op("a") + 0.5 * f.n_op("b")
+    grid = ImaginaryTimeGrid(2.0, 8)
+    D = delta_dos_gf(grid, 0.4)
+    ex = Expansion(EDCore(f, H), grid, [InteractionPair(f.c_dag("a"), f.c("b"), D),
+                                         InteractionPair(f.c("b"), f.c_dag("a"), ph_conj(D))])
+    ctx = qlib.Context(device=qlib.DEVICE_NONE)
+    ctx.set_expansion(ex)
+    pr, pa = qlib.topologies(1, 1)
+    with pytest.raises(qlib.QiwError) as ei:
+        ctx.set_topologies(0, qlib.MODE_BOLD, 1, 1, pr, pa)
+    assert ei.value.code == 4
+
+
+def test_readme_work_counts(qlib):
+    """Work counters of the README configuration: 280 bold topologies, 3 492 surviving
+    configurations over the 17 bold entries, 2 656 for bare order 4."""
+    ex, grid, f = models.anderson(n_tau=20)
+    ctx = qlib.Context(device=qlib.DEVICE_NONE)
+    ctx.set_expansion(ex)
+    leaves = tops = 0
+    eid = 0
+    for order in range(0, 5):
+        for k in ([0] if order == 0 else range(1, 2 * order)):
+            pr, pa = qlib.topologies(order, k)
+            ctx.set_topologies(eid, qlib.MODE_BOLD, order, k, pr, pa)
+            st = ctx.entry_stats(eid)
+            leaves += st["n_leaves"]
+            tops += st["n_top"] if order else 0
+            eid += 1
+    assert eid == 17 and tops == 280 and leaves == 3492
+    pr, pa = qlib.topologies(4)
+    ctx.set_topologies(eid, qlib.MODE_BARE, 4, 8, pr, pa)
+    assert ctx.entry_stats(eid)["n_leaves"] == 2656

@@ -1,0 +1,174 @@
+"""Pins the CPU oracle (oracle/qiw_oracle.cpp) to the reference's own golden vectors
+(SURVEY.md §8c): Sobol tables, topology counts, per-sample evaluator values, end-to-end P and g,
+plus the physics pins of test/dimers.jl.  CPU only."""
+import numpy as np
+import pytest
+
+import models
+from conftest import load_golden
+
+
+def mock_bits(shape):
+    """MockRNG of test/scrambled_sobol.jl:97-105: S[count_ones(i) % 2], column-major fill."""
+    v = np.array([bin(i).count("1") % 2 for i in range(int(np.prod(shape)))], dtype=np.uint8)
+    return v.reshape(shape, order="F")
+
+
+def test_sobol_unscrambled_exact(oracle_lib):
+    G = load_golden("sobol_tables.json")
+    for D, key in ((1, "unscrambled_D1"), (5, "unscrambled_D5")):
+        m = oracle_lib.sobol_direction_numbers(D)
+        x0 = np.zeros(D, dtype=np.uint32)
+        _, xf = oracle_lib.sobol_points(m, x0, 0, 8)
+        ref = np.array(G[key])
+        assert np.array_equal(xf, ref)                    # test/scrambled_sobol.jl:56,84 (==)
+        _, xf = oracle_lib.sobol_points(m, x0, 3, 5)      # skip!(s, 3, exact=true)  :58-60
+        assert np.array_equal(xf, ref[3:])
+
+
+def test_sobol_scrambled_mockrng(oracle_lib):
+    G = load_golden("sobol_tables.json")
+    for D, key in ((1, "scrambled_D1"), (5, "scrambled_D5")):
+        m, x0 = oracle_lib.sobol_scramble(oracle_lib.sobol_direction_numbers(D), mock_bits((D, 32)),
+                                          mock_bits((D, 32, 32)))
+        _, xf = oracle_lib.sobol_points(m, x0, 0, 8)
+        assert np.abs(xf - np.array(G[key])).max() < 1e-10   # test/scrambled_sobol.jl:145,181
+
+
+def test_sobol_bad_dimension(oracle_lib):
+    with pytest.raises(ValueError):
+        oracle_lib.sobol_direction_numbers(100000)
+
+
+def test_topology_counts(oracle_lib):
+    G = load_golden("readme_counts.json")
+    assert [len(oracle_lib.topologies(n)[1]) for n in range(5)] == G["bare"]            # README.md:178-182
+    for order, k, cnt in G["bold"]:                                                     # README.md:185-201
+        assert len(oracle_lib.topologies(order, k)[1]) == cnt
+    # test/diagrammatics.jl:26-42 (2n-1)!! and :53-60 irreducible counts
+    dfact = [1, 1, 3, 15, 105, 945, 10395]
+    assert [len(oracle_lib.topologies(n)[1]) for n in range(7)] == dfact
+    assert [len(oracle_lib.topologies(n, 1)[1]) for n in range(1, 8)] == [1, 1, 4, 27, 248, 2830, 38232]
+
+
+def test_topology_parity(oracle_lib):
+    """Parity equals the sign of the permutation (pi(1), pi(2), ...) (test/diagrammatics.jl:44-51)."""
+    def perm_sign(p):
+        p, s = list(p), 1
+        for i in range(len(p)):
+            while p[i] != i + 1:
+                j = p[i] - 1
+                p[i], p[j] = p[j], p[i]
+                s = -s
+        return s
+    for n in range(1, 5):
+        pairs, parity = oracle_lib.topologies(n)
+        for pr, pa in zip(pairs, parity):
+            assert perm_sign(pr.reshape(-1)) == pa
+        for k in range(1, 2 * n):
+            a = oracle_lib.topologies(n, k)
+            b = oracle_lib.topologies(n, k, with_external_arc=True)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(b[1], a[1] * (-1) ** k)
+
+
+def test_transform_simplex_volume(oracle_lib):
+    """Root / DoubleSimplexRoot: ordering of the mapped points and Jacobian = simplex volumes
+    (test/qmc_integrate.jl:352-512 restated on the imaginary branch: integral of 1 = volume)."""
+    rng = np.random.default_rng(3)
+    for d_before, d_after in ((0, 3), (2, 1), (3, 4)):
+        x = rng.random(d_before + d_after)
+        u, jac = oracle_lib.transform(1, d_before, d_after, 0.5, 2.0, 2.5, x)
+        assert np.all(np.diff(u) <= 0) and np.all(u[:d_after] >= 2.0) and np.all(u[d_after:] <= 2.0)
+        from math import factorial
+        assert np.isclose(jac, 1.5 ** d_before / factorial(d_before) * 0.5 ** d_after / factorial(d_after))
+    u, jac = oracle_lib.transform(0, 0, 4, 1.0, 1.0, 3.0, np.array([0.0625, 0.5, 0.25, 0.75]))
+    assert np.allclose(u, 1.0 + 2.0 * np.cumprod([0.5, 0.5 ** (1 / 3), 0.5, 0.75])) and np.isclose(jac, 16 / 24)
+
+
+def test_topology_eval_golden(oracle_lib):
+    """test/topology_eval.jl:151 (rtol 1e-10); the oracle reaches ~1e-14."""
+    G = load_golden("topology_eval_h5.json")
+    ex, grid, f = models.single_level(n_tau=30, spline=False, rev="transpose")
+    o = oracle_lib.Oracle(ex.flatten(), ex.P)
+    pairs, parity = oracle_lib.topologies(3, 1)
+    assert len(parity) == 4
+    o.set_topologies(0, oracle_lib.MODE_BOLD, 3, 1, pairs, parity)
+    tau = grid.tau
+    tw, tf = tau[6], tau[7]
+    times = np.zeros((100, 6))
+    times[:, 0] = tw + (tf - tw) * G["/x1_list"]
+    times[:, 1:] = tw * G["/xs_list"]
+    got = o.eval_at_times(0, 0.0, tw, tf, times)
+    ref = G["/values"].T[:, ::-1]     # KeldyshED sector 1 = occupied state = our sector 1
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-12
+
+
+def test_inchworm_golden(oracle_lib):
+    """test/inchworm.jl:179-212 against test/inchworm.h5 (/inchworm/P/1, /P/2, /g)."""
+    from qinchworm_b200.expansion import add_corr_operators
+    G = load_golden("inchworm_h5.json")
+    ex, grid, f = models.single_level(n_tau=20, spline=True)
+    add_corr_operators(ex, (f.c("0"), f.c_dag("0")))
+    pl = ex.flatten()
+    res = oracle_lib.inchworm(pl, ex.P, range(0, 4), range(0, 3), 2 ** 8)
+    P = res["P"]
+    assert np.abs(P[:, 1] - G["/inchworm/P/1"].ravel()).max() < 1e-12
+    assert np.abs(P[:, 0] - G["/inchworm/P/2"].ravel()).max() < 1e-12
+    g = -oracle_lib.correlator_2p(pl, P, range(0, 4), 2 ** 8)
+    assert np.abs(g - G["/inchworm/g"].ravel()).max() < 1e-12
+    # number of diagram evaluations: N * (bare topologies) + (n_tau - 2) * N * (bold topologies) + order-0 terms
+    assert res["evals"] == 1 + 256 * (1 + 3) + 18 * (1 + 256 * (1 + 4 + 27))
+
+
+def test_rank_split_is_exact(oracle_lib):
+    """Sum of rank-local partial integrals over the reference's split_count ranges equals the
+    single-rank result (src/inchworm.jl:168-190, src/mpi.jl:49-54,104-127)."""
+    ex, grid, f = models.single_level(n_tau=12, spline=False)
+    pl = ex.flatten()
+    a = oracle_lib.inchworm(pl, ex.P, range(0, 3), range(0, 3), 2 ** 6)["P"]
+    b = oracle_lib.inchworm(pl, ex.P, range(0, 3), range(0, 3), 2 ** 6, n_ranks=3)["P"]
+    assert np.abs(a - b).max() < 1e-13
+    assert [oracle_lib.rank_sub_range(10, 3, r) for r in range(3)] == [(0, 4), (4, 3), (7, 3)]
+
+
+def test_dimer_physics(oracle_lib):
+    """test/dimers.jl:124-196 (Hubbard dimer, orders 0:2, N = 256): |rho - rho_exact| < 1e-4."""
+    from qinchworm_b200 import ppgf
+    ex, grid, f = models.hubbard_dimer_impurity(n_tau=32)
+    ex.P = oracle_lib.inchworm(ex.flatten(), ex.P, range(0, 3), range(0, 3), 8 * 2 ** 5)["P"]
+    ppgf.normalize(ex)
+    rho = ex.ed.to_fock_basis(ppgf.density_matrix(ex))
+    assert np.abs(rho - models.hubbard_dimer_exact_rho()).max() < 1e-4
+    assert np.isclose(np.trace(rho).real, 1.0)
+
+
+def test_block_basis_rotation_invariance(oracle_lib):
+    """d_s > 1 is unpinned at the reference level: the oracle must at least be
+    invariant under a rotation of the basis inside a degenerate multi-dimensional sector."""
+    import numpy as np
+    from qinchworm_b200.ed import EDCore, FockSpace
+    from qinchworm_b200.expansion import Expansion, InteractionPair
+    from qinchworm_b200.gf import ImaginaryTimeGrid, delta_dos_gf, ph_conj
+    f = FockSpace([["a"], ["b"]])
+    # two degenerate levels with inter-level hybridisation -> the one-particle sector is 2x2
+    H = 0.3 * (f.n_op("a") + f.n_op("b")) + 0.7 * f.n_op("a") @ f.n_op("b")
+    mix = f.c_dag("a") @ f.c("b") + f.c_dag("b") @ f.c("a")
+    grid = ImaginaryTimeGrid(2.0, 12)
+    D = delta_dos_gf(grid, 0.4) * 0.3
+    vals = []
+    for theta in (0.0, 0.6):
+        ed = EDCore(f, H, symmetry_breakers=[mix])
+        assert sorted(ed.dims) == [1, 1, 2]
+        for s, d in enumerate(ed.dims):
+            if d == 2:  # rotate the (degenerate) eigenbasis of the 2x2 sector
+                c, sn = np.cos(theta), np.sin(theta)
+                ed.unitaries[s] = ed.unitaries[s] @ np.array([[c, -sn], [sn, c]])
+        pairs = []
+        for x, y in (("a", "a"), ("b", "b"), ("a", "b"), ("b", "a")):
+            pairs += [InteractionPair(f.c_dag(x), f.c(y), D), InteractionPair(f.c(y), f.c_dag(x), ph_conj(D))]
+        ex = Expansion(ed, grid, pairs)
+        res = oracle_lib.inchworm(ex.flatten(), ex.P, range(0, 3), range(0, 3), 2 ** 6)
+        ex.P = res["P"]
+        from qinchworm_b200 import ppgf
+        vals.append(ex.ed.to_fock_basis(ppgf.density_matrix(ex)))
+    assert np.abs(vals[0] - vals[1]).max() < 1e-12
