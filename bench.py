@@ -231,13 +231,13 @@ def main():
     device_run()
     prof = ctx.profile_read(reset=True)
     ctx.profile_enable(False)
-    dom = prof.get("step_depth11", {"ms": float("nan"), "launches": 1})
+    dom = prof.get("step_order_le4", {"ms": float("nan"), "launches": 1})
     n_count = mpi.split_count(N, world)[rank]
     dom_ms = dom["ms"] / max(dom["launches"], 1)
-    dom_flops = flops_deep_sample * n_count                       # algorithmic chain FLOPs of one launch
+    dom_flops = flops_bold_sample * n_count                       # algorithmic chain FLOPs of one launch
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12
     total_prof = sum(v["ms"] for v in prof.values())
-    roofline = {"bound": "fp64_fma", "kernel": "scalar_step_kernel<11> (bold orders 3-4)", "achieved": achieved,
+    roofline = {"bound": "fp64_fma", "kernel": "scalar_step_kernel<14> (all bold entries, orders 0-4)", "achieved": achieved,
                 "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 "peak_source": "measured in this process by qiw_measure_fp64_peak (DFMA-saturating kernel); "
                                "MEASURED_PEAKS.json has no FP64 entry",

@@ -187,7 +187,7 @@ int qiw_last_device_ms(qiw_context* ctx, double* ms);
 int qiw_launch_count(qiw_context* ctx, int64_t* n);
 
 /* Per-kernel device timing (CUDA events on the launching stream around every launch).  Classes:
- * 0..3 step kernel for tree depth <= 7 / 11 / 15 / 19 positions, 4 reduction, 5 per-step state update,
+ * 0..3 step kernel for expansion orders <= 2 / 4 / 6 / 8, 4 reduction, 5 per-step state update,
  * 6 NCCL all-reduce.  Profiling serialises nothing but adds two event records per launch; keep it
  * off for timed runs.  qiw_profile_read synchronises, returns accumulated ms and launch counts per
  * class (arrays of QIW_PROFILE_CLASSES) and optionally resets them. */

@@ -86,8 +86,7 @@ struct DevBuf {
 struct EntryDev {
     EntryProgram prog;
     bool valid = false;
-    DevBuf<uint64_t> words;
-    DevBuf<uint32_t> tree_off;
+    DevBuf<uint32_t> records;
     DevBuf<double2> coefs;
     DevBuf<int4> dslots;
     DevBuf<uint32_t> sobol;   // m[D][32] + x0[D] of the current call
@@ -101,8 +100,6 @@ struct Plan {   // launch plan of one qiw_eval call shape, cached
     struct Group { int maxl; int item0, n_items; size_t smem; int max_slots; };
     std::vector<Group> groups;
     std::vector<WorkItem> items;
-    std::vector<uint32_t> chunk_tree0;
-    std::vector<int> entry_chunk_base;     // per call entry
     std::vector<int> item0, n_items;       // per call entry
     std::vector<DevEntryDyn> h_dyn;        // per call entry
     DevBuf<DevEntryDyn> d_dyn;
@@ -116,8 +113,6 @@ struct Plan {   // launch plan of one qiw_eval call shape, cached
     std::vector<uint32_t> h_sobol;
     bool default_sobol_resident = false;
     DevBuf<WorkItem> d_items;
-    DevBuf<uint32_t> d_chunk_tree0;
-    DevBuf<int> d_entry_chunk_base;
 };
 }  // namespace
 
@@ -241,7 +236,7 @@ int qiw_destroy(qiw_context* ctx) {
     ctx->dPerSample.release(); ctx->dTimes.release(); ctx->dHist.release(); ctx->dDiag.release();
     for (auto& t : ctx->tables) { t.y.release(); t.M.release(); }
     for (auto& e : ctx->entries)
-        if (e) { e->words.release(); e->tree_off.release(); e->coefs.release(); e->dslots.release(); e->sobol.release(); }
+        if (e) { e->records.release(); e->coefs.release(); e->dslots.release(); e->sobol.release(); }
     for (auto& pl : ctx->plans) release_plan(*pl);
     ctx->plans.clear();
     if (ctx->hOut) cudaFreeHost(ctx->hOut);
@@ -377,8 +372,11 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
     if (rc) return fail(ctx, rc, "qiw_set_topologies: " + err);
     const EntryProgram& pr = ed.prog;
     if (ctx->no_device) { ed.valid = true; return QIW_OK; }
-    CK(ed.words.upload(pr.words.data(), pr.words.size(), ctx->stream));
-    CK(ed.tree_off.upload(pr.tree_off.data(), pr.tree_off.size(), ctx->stream));
+    {   // leaf records, padded so that a stray vector load past the end stays in bounds
+        std::vector<uint32_t> rec(pr.records);
+        rec.resize(rec.size() + 32, 0u);
+        CK(ed.records.upload(rec.data(), rec.size(), ctx->stream));
+    }
     std::vector<double2> cf(std::max<size_t>(pr.coefs.size(), 1));
     for (size_t k = 0; k < pr.coefs.size(); ++k) cf[k] = make_double2(pr.coefs[k].real(), pr.coefs[k].imag());
     CK(ed.coefs.upload(cf.data(), cf.size(), ctx->stream));
@@ -429,7 +427,6 @@ int qiw_entry_program(qiw_context* ctx, int32_t id, int64_t* n_words, uint64_t* 
 
 // ---- launch planning ---------------------------------------------------------------------------
 
-static int maxl_class(int n_nodes) { return n_nodes <= 7 ? 7 : n_nodes <= 11 ? 11 : n_nodes <= 15 ? 15 : 19; }
 
 static int sync_static_tables(qiw_context* ctx) {
     if (ctx->deltas_dirty) {
@@ -438,6 +435,7 @@ static int sync_static_tables(qiw_context* ctx) {
             auto& tb = ctx->tables[t];
             dd[t].y = tb.y.p; dd[t].M = tb.M.p; dd[t].kind = tb.kind; dd[t].n = tb.n;
             dd[t].h = tb.n > 1 ? tb.beta / (tb.n - 1) : 1.0;
+            dd[t].inv_h = 1.0 / dd[t].h;
         }
         CK(ctx->dDeltas.upload(dd.data(), dd.size(), ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -455,10 +453,10 @@ static int sync_static_tables(qiw_context* ctx) {
             d.d_after = (p.mode == 0) ? p.D : p.n_pts_after;
             d.d_before = p.D - d.d_after;
             d.nP = p.nP; d.nD = (int)p.dslots.size();
-            d.n_trees = (int)p.tree_off.size() - 1;
+            d.L = p.L; d.n_leaves = (int)p.n_leaves;
             d.exact = (p.order == 0);
             for (int k = 0; k <= kDevMaxNodes; ++k) d.pos_src[k] = p.pos_src[k];
-            d.words = ed.words.p; d.tree_off = ed.tree_off.p; d.coefs = ed.coefs.p; d.dslots = ed.dslots.p;
+            d.records = ed.records.p; d.coefs = ed.coefs.p; d.dslots = ed.dslots.p;
         }
         CK(ctx->dEntries.upload(de.data(), de.size(), ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -468,7 +466,7 @@ static int sync_static_tables(qiw_context* ctx) {
 }
 
 static void release_plan(Plan& pl) {
-    pl.d_items.release(); pl.d_chunk_tree0.release(); pl.d_entry_chunk_base.release(); pl.d_sobol.release();
+    pl.d_items.release(); pl.d_sobol.release();
     pl.d_dyn.release(); pl.d_partials.release(); pl.d_out.release();
 }
 
@@ -488,54 +486,53 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
     const int S = ctx->model.S;
     int ndev_sm = 148;
     cudaDeviceGetAttribute(&ndev_sm, cudaDevAttrMultiProcessorCount, ctx->device);
-    // total cost in (edges x sample blocks) to size the chunks
-    double total = 0;
+    // Chunking.  A CTA owns (entry, 32 samples) and builds that sample block's tables once, so the
+    // fewer CTAs share an entry the less set-up work is repeated: by default an entry's
+    // configurations are split into exactly W chunks (one per warp, one CTA job).  Only entries
+    // whose chunks would exceed `chunk_cap` configurations are split further (their set-up cost is
+    // then amortised anyway), and when the call is too small to fill the machine the cap is
+    // lowered to expose more CTAs.
+    double max_leaves = 1;
+    uint64_t n_sb_all = 1;
     for (int i = 0; i < n_entries; ++i) {
         const EntryProgram& p = ctx->entries[ids[i]]->prog;
         const uint64_t c = p.order == 0 ? 1 : count;
-        total += (double)p.n_edges * (double)((c + 31) / 32);
+        max_leaves = std::max(max_leaves, (double)p.n_leaves);
+        n_sb_all = std::max<uint64_t>(n_sb_all, (c + 31) / 32);
     }
-    const double target_tasks = (double)ndev_sm * 32.0;
-    const double cost_per_task = std::max(192.0, total / target_tasks);
-    pl->entry_chunk_base.assign(n_entries, 0);
+    double chunk_cap = 512.0;
+    {
+        // CTAs available if every entry is one job; lower the cap until ~2 CTAs per SM exist
+        const double ctas = (double)n_entries * (double)n_sb_all;
+        const double want = 2.0 * ndev_sm;
+        if (ctas < want) chunk_cap = std::max(16.0, max_leaves / W / std::ceil(want / ctas));
+    }
     pl->item0.resize(n_entries); pl->n_items.resize(n_entries);
-    std::map<int, std::vector<int>> by_class;
-    for (int i = 0; i < n_entries; ++i) by_class[maxl_class(ctx->entries[ids[i]]->prog.n_nodes)].push_back(i);
-    for (auto& kv : by_class) {
+    // heavy entries first: their CTAs are the critical path of the launch
+    std::vector<int> order_idx(n_entries);
+    for (int i = 0; i < n_entries; ++i) order_idx[i] = i;
+    std::stable_sort(order_idx.begin(), order_idx.end(), [&](int a2, int b2) {
+        const EntryProgram &pa = ctx->entries[ids[a2]]->prog, &pb2 = ctx->entries[ids[b2]]->prog;
+        return (double)pa.n_leaves * pa.L > (double)pb2.n_leaves * pb2.L; });
+    {
         Plan::Group g;
-        g.maxl = kv.first; g.item0 = (int)pl->items.size(); g.max_slots = 1;
-        for (int i : kv.second) {
+        g.maxl = 1; g.item0 = 0; g.max_slots = 1;
+        for (int i : order_idx) {
             const EntryProgram& p = ctx->entries[ids[i]]->prog;
-            const int n_trees = (int)p.tree_off.size() - 1;
+            g.maxl = std::max(g.maxl, p.L);
             const uint64_t c = p.order == 0 ? 1 : count;
             pl->max_sb = std::max<uint64_t>(pl->max_sb, (c + 31) / 32);
             int n_chunks = 1;
-            if (!explicit_mode && n_trees > 0) {
-                double per_sb_tasks = std::ceil((double)p.n_edges / cost_per_task);
-                n_chunks = (int)std::min<double>(n_trees, std::max<double>(std::min(W, n_trees), per_sb_tasks));
-                if (n_chunks > W) n_chunks = ((n_chunks + W - 1) / W) * W;   // full CTAs
-                n_chunks = std::min(n_chunks, n_trees);
+            const int64_t nl = p.n_leaves;
+            if (!explicit_mode && nl > 0) {
+                const int groups = (int)std::max(1.0, std::ceil((double)nl / (W * chunk_cap)));
+                n_chunks = (int)std::min<int64_t>(nl, (int64_t)W * groups);
             }
-            // chunk boundaries by cumulative tree cost
-            pl->entry_chunk_base[i] = (int)pl->chunk_tree0.size();
-            double tot = 0;
-            for (int t = 0; t < n_trees; ++t) tot += p.tree_cost[t];
-            double acc = 0;
-            int c_done = 0;
-            pl->chunk_tree0.push_back(0);
-            for (int t = 0; t < n_trees; ++t) {
-                acc += p.tree_cost[t];
-                while (c_done + 1 < n_chunks && acc >= tot * (double)(c_done + 1) / n_chunks) {
-                    pl->chunk_tree0.push_back((uint32_t)(t + 1));
-                    ++c_done;
-                }
-            }
-            while (c_done + 1 < n_chunks) { pl->chunk_tree0.push_back((uint32_t)n_trees); ++c_done; }
-            pl->chunk_tree0.push_back((uint32_t)n_trees);
             pl->item0[i] = (int)pl->items.size();
             for (int c0 = 0; c0 < n_chunks; c0 += W) {
                 WorkItem it;
                 it.entry = ids[i]; it.slot = i; it.chunk0 = c0; it.n_chunks = std::min(W, n_chunks - c0);
+                it.n_chunks_total = n_chunks;
                 it.partial0 = (int)pl->items.size();
                 pl->items.push_back(it);
             }
@@ -570,8 +567,6 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         dy.entry = ids[i]; dy.out_index = i; dy.item0 = pl->item0[i]; dy.n_items = pl->n_items[i];
     }
     CK(pl->d_items.upload(pl->items.data(), pl->items.size(), ctx->stream));
-    CK(pl->d_chunk_tree0.upload(pl->chunk_tree0.data(), pl->chunk_tree0.size(), ctx->stream));
-    CK(pl->d_entry_chunk_base.upload(pl->entry_chunk_base.data(), pl->entry_chunk_base.size(), ctx->stream));
     CK(pl->d_partials.reserve(pl->partial_rows * S));
     CK(pl->d_out.reserve((size_t)n_entries * ctx->model.bsize));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -628,9 +623,8 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
     StepParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.entries = ctx->dEntries.p; sp.dyn = pl.d_dyn.p;
-    sp.chunk_tree0 = pl.d_chunk_tree0.p; sp.entry_chunk_base = pl.d_entry_chunk_base.p;
     sp.P = ctx->dP.p; sp.E = ctx->dE.p; sp.deltas = ctx->dDeltas.p;
-    sp.S = m.S; sp.bsize = m.bsize; sp.n_tau = ctx->n_tau; sp.h = ctx->beta / (ctx->n_tau - 1);
+    sp.S = m.S; sp.bsize = m.bsize; sp.n_tau = ctx->n_tau; sp.h = ctx->beta / (ctx->n_tau - 1); sp.inv_h = 1.0 / sp.h;
     sp.t_i = t_i; sp.t_w = t_w; sp.t_f = t_f;
     sp.partials = pl.d_partials.p;
     if (pl.explicit_mode) { sp.explicit_times = ctx->dTimes.p; sp.per_sample_out = ctx->dPerSample.p; }
@@ -640,7 +634,7 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         gp.max_slots = g.max_slots;
         dim3 grid((unsigned)pl.pitch, (unsigned)g.n_items);
         {
-            ProfScope ps(ctx, g.maxl <= 7 ? 0 : g.maxl <= 11 ? 1 : g.maxl <= 15 ? 2 : 3);
+            ProfScope ps(ctx, g.maxl <= 8 ? 0 : g.maxl <= 14 ? 1 : g.maxl <= 20 ? 2 : 3);
             CK(launch_scalar_step(g.maxl, gp, grid, ctx->warps * 32, g.smem, ctx->stream));
         }
         ctx->launches++;

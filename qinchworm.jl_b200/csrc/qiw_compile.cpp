@@ -34,6 +34,7 @@ struct Builder {
     // statistics of the reference algorithm for the current chain
     int64_t leaves = 0, edges = 0;
     double flops = 0;
+    std::vector<uint32_t> path;   // table slots of the factors collected along the current branch
 
     Builder(const HostModel& m_, EntryProgram& e_) : m(m_), e(e_), n_nodes(e_.n_nodes) {}
 
@@ -103,12 +104,25 @@ struct Builder {
             if (!first) flops += 8.0 * m.dim[s_next] * m.dim[s] * m.dim[s_init];
             int64_t below = 0;
             uint32_t nchild = 0;
+            const size_t path_mark = path.size();
+            path.push_back(slotA);
+            if (slotB) path.push_back(slotB);
             if (pos == n_nodes) {
                 if (s_next != s_init) offdiag = true;  // the @assert at :462
-                else { below = 1; flops += 8.0 * m.dim[s_init] * m.dim[s_init]; }
+                else {
+                    below = 1;
+                    flops += 8.0 * m.dim[s_init] * m.dim[s_init];
+                    if (e.scalar) {   // leaf record
+                        const uint32_t cid = (uint32_t)coef_id(c2 * top_sign);
+                        e.records.push_back(cid | ((uint32_t)s_init << 16));
+                        for (uint32_t sl : path) e.records.push_back(sl * 512u);
+                        for (int k = (int)path.size() + 1; k < e.RL; ++k) e.records.push_back(0u);
+                    }
+                }
             } else {
                 below = node(pos + 1, s_next, c2, false, nchild);
             }
+            path.resize(path_mark);
             if (below == 0) {  // dead branch: roll back everything it emitted
                 e.words.resize(my);
                 edges = my_edges;
@@ -147,6 +161,8 @@ int compile_entry(const HostModel& m, int mode, int order, int n_pts_after, int 
     if (order > 0 && mode != 0 && (d_after < 1 || d_after > 2 * n)) { err = "bad n_pts_after"; return 1; }
     e.n_nodes = (mode == 0) ? 2 * n + 2 : 2 * n + 3;  // src/topology_eval.jl:254
     e.nP = (e.n_nodes - 1) * m.S;
+    e.L = e.n_nodes - 1 + order;
+    e.RL = ((e.L + 1 + 3) / 4) * 4;
     int kind[kMaxNodes + 2];
     for (int p = 0; p <= kMaxNodes; ++p) { e.pos_src[p] = 0; e.fixed_op[p] = -1; kind[p] = K_FREE; }
     // fixed nodes: src/inchworm.jl:150,163 (bold) :260,274 (bare) :817-819,835,849 (correlator)
@@ -208,6 +224,7 @@ int compile_entry(const HostModel& m, int mode, int order, int n_pts_after, int 
             }
             uint32_t nchild = 0;
             const double flops0 = b.flops;
+            b.path.clear();
             const int64_t below = b.node(2, s_next, coef, first, nchild);
             if (below == 0) { e.words.resize(root); b.edges = edges0; b.flops = flops0; continue; }
             e.words[root] = make_word((uint32_t)s_next, 0, nchild, (uint32_t)s_i, rootop);
@@ -222,7 +239,8 @@ int compile_entry(const HostModel& m, int mode, int order, int n_pts_after, int 
         return 4;
     }
     e.tree_off.push_back((uint32_t)e.words.size());
-    e.words.push_back(0);  // pad: executors prefetch one word ahead
+    e.words.push_back(0);  // pad: executors prefetch two words ahead
+    e.words.push_back(0);
     e.n_leaves = b.leaves; e.n_edges = b.edges; e.flops_per_sample = b.flops;
     if (e.nP + (int)e.dslots.size() > 4095 || e.coefs.size() > 65535) { err = "program table overflow"; return 5; }
     return 0;

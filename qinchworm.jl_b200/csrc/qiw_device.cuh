@@ -17,6 +17,7 @@ struct DevDelta {
     const double2* M;   // spline second derivatives (kind == 1)
     int kind, n;
     double h;           // beta / (n - 1)
+    double inv_h;
 };
 
 // Static (per compiled entry) description read by every CTA working on the entry.
@@ -24,11 +25,10 @@ struct DevEntry {
     int mode, order, n_nodes, D;
     int d_after, d_before;
     int nP, nD;                 // table slots: propagators, pair interactions
-    int n_trees;
     int exact;                  // order 0: one deterministic evaluation
     int pos_src[kDevMaxNodes + 1];
-    const uint64_t* words;
-    const uint32_t* tree_off;   // [n_trees + 1]
+    int L, n_leaves;            // record length (factors per configuration), number of records
+    const uint32_t* records;    // [n_leaves][RL]
     const double2* coefs;
     const int4* dslots;         // (pos_tail, pos_head, table, 0)
 };
@@ -50,6 +50,7 @@ struct WorkItem {
     int slot;         // index of the entry within the call (DevEntryDyn, chunk tables)
     int chunk0;       // first chunk of the group
     int n_chunks;     // chunks in the group (<= warps per CTA)
+    int n_chunks_total;  // chunks the entry's configurations are split into
     int partial0;     // first row of this item in the partials buffer
 };
 
@@ -57,14 +58,12 @@ struct StepParams {
     const DevEntry* entries;
     const DevEntryDyn* dyn;
     const WorkItem* items;
-    const uint32_t* chunk_tree0;   // [total chunks + 1] per-entry chunk -> first tree (concatenated)
-    const int* entry_chunk_base;   // [call entries] offset of the entry's chunks in chunk_tree0
     // model
     const double2* P;              // [n_tau][bsize]
     const double* E;               // [S] (scalar models) energies + lambda
     const DevDelta* deltas;
     int S, bsize, n_tau;
-    double h;                      // beta / (n_tau - 1)
+    double h, inv_h;               // beta / (n_tau - 1) and its reciprocal
     // times; when `times_dev` is non-null the triple is read from device memory (run-level API)
     double t_i, t_w, t_f;
     const double* times_dev;

@@ -61,6 +61,12 @@ struct EntryProgram {
     std::vector<cplx> coefs;               // distinct leaf coefficients
     std::vector<DeltaSlot> dslots;         // pair-interaction factors referenced by the program
     int nP = 0;                            // number of propagator slots ((n_nodes-1) * S)
+    // Leaf records (scalar models): one fixed-length record per surviving configuration, in the
+    // tree's leaf order.  rec[0] = coefficient index | initial sector << 16; rec[1..L] = byte offset
+    // (slot * 512) of every factor of the configuration's weight in the per-sample table; padded
+    // with zeros to RL words (RL % 4 == 0).  L = (n_nodes - 1) propagators + `order` interactions.
+    std::vector<uint32_t> records;
+    int L = 0, RL = 0;
     // statistics
     int64_t n_top = 0, n_leaves = 0, n_edges = 0;
     double flops_per_sample = 0;

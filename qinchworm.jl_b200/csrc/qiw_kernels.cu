@@ -35,9 +35,11 @@ __device__ __forceinline__ double2 times_i(double2 a) { return make_double2(-a.y
 // stored as D[k] = G(k h): bilinear on the cell (a, b) of the (t_f, t_i) grid, linear on the
 // triangle when both times share a cell (rule: DESIGN.md §2; call sites
 // src/topology_eval.jl:368,414).
-__device__ __forceinline__ double2 grid_interp(const double2* __restrict__ D, int stride, int n, double h,
+__device__ __forceinline__ double2 grid_interp(const double2* __restrict__ D, int stride, int n, double inv_h,
                                                double t_f, double t_i) {
-    const double qf = t_f / h, qi = t_i / h;
+    // t * (1/h) instead of t / h: may pick the neighbouring cell when t sits on a grid point to the
+    // last bit, where the interpolant is continuous, so the value changes by O(ulp) only
+    const double qf = t_f * inv_h, qi = t_i * inv_h;
     int a = (int)floor(qf), b = (int)floor(qi);
     a = min(max(a, 0), n - 2);
     b = min(max(b, 0), n - 2);
@@ -58,18 +60,19 @@ __device__ __forceinline__ double2 grid_interp(const double2* __restrict__ D, in
 // Natural cubic spline in dt = t_f - t_i (src/spline_gf.jl:208-219).
 __device__ __forceinline__ double2 spline_eval(const DevDelta& t, double dt) {
     const double h = t.h;
-    int j = (int)floor(dt / h);
+    int j = (int)floor(dt * t.inv_h);
     j = min(max(j, 0), t.n - 2);
     const double xa = dt - (double)j * h, xb = (double)(j + 1) * h - dt;
     const double2 y0 = __ldg(t.y + j), y1 = __ldg(t.y + j + 1), m0 = __ldg(t.M + j), m1 = __ldg(t.M + j + 1);
-    const double ca = xa * xa * xa / (6.0 * h), cb = xb * xb * xb / (6.0 * h);
-    return make_double2(m0.x * cb + m1.x * ca + (y0.x / h - m0.x * h / 6.0) * xb + (y1.x / h - m1.x * h / 6.0) * xa,
-                        m0.y * cb + m1.y * ca + (y0.y / h - m0.y * h / 6.0) * xb + (y1.y / h - m1.y * h / 6.0) * xa);
+    const double i6h = t.inv_h * (1.0 / 6.0), h6 = h * (1.0 / 6.0), ih = t.inv_h;
+    const double ca = xa * xa * xa * i6h, cb = xb * xb * xb * i6h;
+    return make_double2(m0.x * cb + m1.x * ca + (y0.x * ih - m0.x * h6) * xb + (y1.x * ih - m1.x * h6) * xa,
+                        m0.y * cb + m1.y * ca + (y0.y * ih - m0.y * h6) * xb + (y1.y * ih - m1.y * h6) * xa);
 }
 
 __device__ __forceinline__ double2 delta_eval(const DevDelta& t, double t_f, double t_i) {
     if (t.kind == 1) return spline_eval(t, t_f - t_i);
-    return grid_interp(t.y, 1, t.n, t.h, t_f, t_i);
+    return grid_interp(t.y, 1, t.n, t.inv_h, t_f, t_i);
 }
 
 // ---- Sobol -----------------------------------------------------------------------------------
@@ -96,51 +99,70 @@ __global__ void sobol_points_kernel(int D, const uint32_t* __restrict__ m, const
     out[i] = sobol_coord(m + d * 32, x0[d], (uint32_t)(start + k));
 }
 
-// ---- tree walk -------------------------------------------------------------------------------
-
-struct Walk {
-    const uint64_t* __restrict__ prog;
-    const double2* __restrict__ coefs;
-    const double2* T;     // shared-memory table, already offset by the lane
-    uint32_t pc;
-    uint64_t next;        // prefetched word prog[pc]
-    double2 acc;
-};
-
-__device__ __forceinline__ uint32_t w_slotA(uint64_t w) { return (uint32_t)w & 0xFFFu; }
-__device__ __forceinline__ uint32_t w_slotB(uint64_t w) { return ((uint32_t)w >> 12) & 0xFFFu; }
-__device__ __forceinline__ uint32_t w_nchild(uint64_t w) { return ((uint32_t)w >> 24) & 0xFFu; }
-__device__ __forceinline__ uint32_t w_aux(uint64_t w) { return (uint32_t)(w >> 32) & 0xFFFFu; }
-
-// One node at tree level L (= backbone position L): multiply the parent's partial product by the
-// node's factors, then either accumulate (last position) or descend into the children, which
-// follow in the word stream.  Recursion is over a compile-time level so that every partial
-// product has its own registers.
-template <int L, int MAXL>
-struct Level {
-    static __device__ __forceinline__ void run(Walk& w, const double2 vp) {
-        const uint64_t word = w.next;
-        w.next = __ldg(w.prog + (++w.pc));
-        double2 v = cmul(vp, w.T[w_slotA(word) * 32]);
-        const uint32_t sb = w_slotB(word);
-        if (sb) v = cmul(v, w.T[sb * 32]);
-        const uint32_t nc = w_nchild(word);
-        if (nc == 0) {
-            w.acc = cfma(__ldg(w.coefs + w_aux(word)), v, w.acc);
-            return;
+// ---- configuration walk ------------------------------------------------------------------------
+// Every surviving configuration of the entry is a fixed-length record of table offsets
+// (qiw_host.hpp: EntryProgram::records).  The record is warp-uniform, the table is per lane: the walk
+// is a branch-free product of L factors gathered from shared memory — exactly the weight
+//   prod_arcs[i Delta_p(t_tail, t_head)] * prod_pos[O_pos * i P_s(t_pos, t_pos-1)]
+// of src/topology_eval.jl:454-556 with the operator matrix elements and the topology sign
+// (-i * parity * (-1)^order, :431) folded into the record's coefficient.  For 1x1 blocks the
+// reference's cached partial products (src/utility.jl:234-323) save almost nothing (the tree
+// branches at the earliest positions), while a flat record needs no control flow at all.
+template <int L>
+__device__ __forceinline__ void leaf_walk(const uint32_t* __restrict__ rec, int leaf0, int leaf1,
+                                          const unsigned char* Tl, const double2* __restrict__ coefs,
+                                          double2* sacc_t, int sacc_stride, bool ok, double2* sample_out) {
+    constexpr int RL = ((L + 1 + 3) / 4) * 4;
+    const uint4* r = reinterpret_cast<const uint4*>(rec + (size_t)leaf0 * RL);
+    double2 acc = make_double2(0.0, 0.0);
+    int cur_s = -1;
+    for (int leaf = leaf0; leaf < leaf1; ++leaf) {
+        uint32_t w[RL];
+#pragma unroll
+        for (int q = 0; q < RL / 4; ++q) {
+            const uint4 x = __ldg(r + q);
+            w[4 * q] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w;
         }
-        if constexpr (L < MAXL) {
-            for (uint32_t c = 0; c < nc; ++c) Level<L + 1, MAXL>::run(w, v);
+        r += RL / 4;
+        const int s_i = (int)(w[0] >> 16);
+        if (s_i != cur_s) {   // records are grouped by initial sector: rare
+            if (cur_s >= 0 && ok) {
+                double2* a = sample_out ? sample_out + cur_s : sacc_t + cur_s * sacc_stride;
+                *a = cadd(*a, acc);
+            }
+            acc = make_double2(0.0, 0.0);
+            cur_s = s_i;
         }
+        const double2 coef = __ldg(coefs + (w[0] & 0xFFFFu));
+        double2 v = *reinterpret_cast<const double2*>(Tl + w[1]);
+#pragma unroll
+        for (int f = 2; f <= L; ++f) v = cmul(v, *reinterpret_cast<const double2*>(Tl + w[f]));
+        acc = cfma(coef, v, acc);
     }
-};
+    if (cur_s >= 0 && ok) {
+        double2* a = sample_out ? sample_out + cur_s : sacc_t + cur_s * sacc_stride;
+        *a = cadd(*a, acc);
+    }
+}
+
+// Record lengths that occur: 3n+2 (bold / correlator, order n) and 3n+1 (bare).
+template <int LMAX>
+__device__ __forceinline__ void leaf_dispatch(int L, const uint32_t* rec, int leaf0, int leaf1, const unsigned char* Tl,
+                                              const double2* coefs, double2* sacc_t, int stride, bool ok, double2* so) {
+#define QIW_CASE(N) case N: if constexpr (N <= LMAX) leaf_walk<N>(rec, leaf0, leaf1, Tl, coefs, sacc_t, stride, ok, so); break;
+    switch (L) {
+        QIW_CASE(1) QIW_CASE(2) QIW_CASE(4) QIW_CASE(5) QIW_CASE(7) QIW_CASE(8) QIW_CASE(10) QIW_CASE(11)
+        QIW_CASE(13) QIW_CASE(14) QIW_CASE(16) QIW_CASE(17) QIW_CASE(19) QIW_CASE(20) QIW_CASE(22) QIW_CASE(23)
+        QIW_CASE(25) QIW_CASE(26)
+        default: break;
+    }
+#undef QIW_CASE
+}
 
 // ---- the step kernel (scalar models: every sector block is 1x1) ------------------------------
 
-// Register budget: deep trees (orders 5-8) need one live complex per level plus loop state, so
-// they run at one CTA per SM; shallower trees leave room for two.
-template <int MAXL>
-__global__ void __launch_bounds__(256, (MAXL <= 11) ? 2 : 1) scalar_step_kernel(const StepParams p) {
+template <int LMAX>
+__global__ void __launch_bounds__(256, (LMAX <= 14) ? 3 : 2) scalar_step_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const WorkItem it = p.items[blockIdx.y];
@@ -151,7 +173,7 @@ __global__ void __launch_bounds__(256, (MAXL <= 11) ? 2 : 1) scalar_step_kernel(
 
     // shared memory carve-up (sizes fixed per launch from the largest entry, see host)
     double2* T = reinterpret_cast<double2*>(smem_raw);                       // [max_slots][32]
-    double2* sacc = T + (size_t)p.max_slots * 32;                         // [S][blockDim.x]
+    double2* sacc = T + (size_t)p.max_slots * 32;                            // [S][blockDim.x]
     double* times = reinterpret_cast<double*>(sacc + (size_t)S * blockDim.x); // [kDevMaxNodes+1][32]
     double* pw = times + (kDevMaxNodes + 1) * 32;                            // [kDevMaxDim][32]
     int* okflag = reinterpret_cast<int*>(pw + kDevMaxDim * 32);              // [32]
@@ -167,12 +189,12 @@ __global__ void __launch_bounds__(256, (MAXL <= 11) ? 2 : 1) scalar_step_kernel(
     const unsigned long long count = dy.count;
     const int n_sb = (int)((count + 31ull) >> 5);
 
-    // this warp's chunk of trees
-    int tree0 = 0, tree1 = 0;
+    // this warp's share of the entry's configurations: chunk c of n_chunks_total
+    int leaf0 = 0, leaf1 = 0;
     if (warp < it.n_chunks) {
-        const uint32_t* ct = p.chunk_tree0 + p.entry_chunk_base[it.slot] + it.chunk0 + warp;
-        tree0 = (int)ct[0];
-        tree1 = (int)ct[1];
+        const long long c = it.chunk0 + warp, nct = it.n_chunks_total, nl = e.n_leaves;
+        leaf0 = (int)(c * nl / nct);
+        leaf1 = (int)((c + 1) * nl / nct);
     }
 
     for (int sb = blockIdx.x; sb < n_sb; sb += gridDim.x) {
@@ -186,7 +208,7 @@ __global__ void __launch_bounds__(256, (MAXL <= 11) ? 2 : 1) scalar_step_kernel(
                 const uint32_t xi = sobol_coord(sm + j * 32, __ldg(sm + D * 32 + j), k);
                 const double x = (double)xi * 2.3283064365386963e-10;  // ldexp(x, -32), exact
                 const int den = (j < d_after) ? (d_after - j) : (D - j);
-                pw[j * 32 + lane] = pow(x, 1.0 / (double)den);
+                pw[j * 32 + lane] = (den == 1) ? x : pow(x, 1.0 / (double)den);
             }
         }
         __syncthreads();
@@ -227,7 +249,7 @@ __global__ void __launch_bounds__(256, (MAXL <= 11) ? 2 : 1) scalar_step_kernel(
                 if (e.mode == 0) {                          // bare: i * (-i) exp(-dt (E + lambda))
                     val = make_double2(exp(-(tb - ta) * __ldg(p.E + s)), 0.0);
                 } else {
-                    val = times_i(grid_interp(p.P + s, p.bsize, p.n_tau, p.h, tb, ta));
+                    val = times_i(grid_interp(p.P + s, p.bsize, p.n_tau, p.inv_h, tb, ta));
                 }
             } else {
                 const int4 ds = __ldg(e.dslots + (q - nP));
@@ -240,47 +262,12 @@ __global__ void __launch_bounds__(256, (MAXL <= 11) ? 2 : 1) scalar_step_kernel(
         }
         __syncthreads();
 
-        // -- 4. replay this warp's trees -------------------------------------------------------
-        if (tree0 < tree1) {
-            Walk w;
-            w.prog = e.words;
-            w.coefs = e.coefs;
-            w.T = T + lane;
-            w.acc = make_double2(0.0, 0.0);
+        // -- 4. this warp's configurations -----------------------------------------------------
+        if (leaf0 < leaf1) {
             const bool ok = okflag[lane] != 0;
-            int cur_s = -1;
-            w.pc = __ldg(e.tree_off + tree0);
-            w.next = __ldg(w.prog + w.pc);
-            for (int t = tree0; t < tree1; ++t) {
-                const uint64_t root = w.next;
-                w.next = __ldg(w.prog + (++w.pc));
-                const int s_i = (int)w_aux(root);
-                if (s_i != cur_s) {
-                    if (cur_s >= 0 && ok) {
-                        if (p.per_sample_out) {
-                            double2* o = p.per_sample_out + local * S + cur_s;
-                            *o = cadd(*o, w.acc);
-                        } else {
-                            double2* a = sacc + cur_s * blockDim.x + threadIdx.x;
-                            *a = cadd(*a, w.acc);
-                        }
-                    }
-                    w.acc = make_double2(0.0, 0.0);
-                    cur_s = s_i;
-                }
-                const uint32_t nc = w_nchild(root);
-                const double2 one = make_double2(1.0, 0.0);
-                for (uint32_t c = 0; c < nc; ++c) Level<2, MAXL>::run(w, one);
-            }
-            if (cur_s >= 0 && ok) {
-                if (p.per_sample_out) {
-                    double2* o = p.per_sample_out + local * S + cur_s;
-                    *o = cadd(*o, w.acc);
-                } else {
-                    double2* a = sacc + cur_s * blockDim.x + threadIdx.x;
-                    *a = cadd(*a, w.acc);
-                }
-            }
+            double2* so = p.per_sample_out ? p.per_sample_out + local * S : nullptr;
+            leaf_dispatch<LMAX>(e.L, e.records, leaf0, leaf1, reinterpret_cast<const unsigned char*>(T + lane), e.coefs,
+                                sacc + threadIdx.x, (int)blockDim.x, ok, so);
         }
         __syncthreads();
     }
@@ -398,23 +385,24 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) 
 
 // ---- host-callable launchers -----------------------------------------------------------------
 
-template <int MAXL>
+template <int LMAX>
 static cudaError_t launch_scalar(const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(scalar_step_kernel<MAXL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(scalar_step_kernel<LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    scalar_step_kernel<MAXL><<<grid, threads, smem, st>>>(p);
+    scalar_step_kernel<LMAX><<<grid, threads, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_scalar_step(int maxl, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    if (maxl <= 7) return launch_scalar<7>(p, grid, threads, smem, st);
-    if (maxl <= 11) return launch_scalar<11>(p, grid, threads, smem, st);
-    if (maxl <= 15) return launch_scalar<15>(p, grid, threads, smem, st);
-    return launch_scalar<19>(p, grid, threads, smem, st);
+// `lmax` = longest record of the launch; classes: orders <= 2, <= 4, <= 6, <= 8.
+cudaError_t launch_scalar_step(int lmax, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    if (lmax <= 8) return launch_scalar<8>(p, grid, threads, smem, st);
+    if (lmax <= 14) return launch_scalar<14>(p, grid, threads, smem, st);
+    if (lmax <= 20) return launch_scalar<20>(p, grid, threads, smem, st);
+    return launch_scalar<26>(p, grid, threads, smem, st);
 }
 
 cudaError_t launch_reduce(const DevEntryDyn* dyn, const DevEntry* entries, const double2* partials, int pitch, int S,

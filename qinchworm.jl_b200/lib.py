@@ -324,7 +324,7 @@ class Context:
                                          _ptr(hist.view(np.float64), f64p) if want_contribs else None))
         return hist
 
-    PROFILE_CLASSES = ("step_depth7", "step_depth11", "step_depth15", "step_depth19", "reduce", "finish_step",
+    PROFILE_CLASSES = ("step_order_le2", "step_order_le4", "step_order_le6", "step_order_le8", "reduce", "finish_step",
                        "nccl_allreduce", "other")
 
     def profile_enable(self, on=True):
