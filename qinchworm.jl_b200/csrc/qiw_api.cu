@@ -97,7 +97,7 @@ struct Plan {   // launch plan of one qiw_eval call shape, cached
     std::vector<int> ids;
     uint64_t count = 0;
     bool explicit_mode = false;
-    struct Group { int maxl; int item0, n_items; size_t smem; int max_slots; };
+    struct Group { int maxl; int item0, n_items; size_t smem; int max_slots; int max_dslots; };
     std::vector<Group> groups;
     std::vector<WorkItem> items;
     std::vector<int> item0, n_items;       // per call entry
@@ -105,6 +105,9 @@ struct Plan {   // launch plan of one qiw_eval call shape, cached
     DevBuf<DevEntryDyn> d_dyn;
     DevBuf<double2> d_partials, d_out;
     bool dyn_resident = false;
+    DevBuf<double> d_ucache;               // simplex roots cached across calls with the same sequence
+    std::vector<size_t> ucache_off;
+    bool ucache_enabled = false, ucache_valid = false;
     size_t partial_rows = 0;
     uint64_t max_sb = 1;
     int pitch = 1;
@@ -133,6 +136,7 @@ struct qiw_context {
     struct Table { int kind = 0, n = 0; double beta = 0; DevBuf<double2> y, M; };
     std::vector<Table> tables;
     DevBuf<DevDelta> dDeltas;
+    std::vector<DevDelta> hDeltas;
     bool deltas_dirty = true;
     std::vector<std::unique_ptr<EntryDev>> entries;
     DevBuf<DevEntry> dEntries;
@@ -140,6 +144,7 @@ struct qiw_context {
     DevBuf<double2> dPerSample, dHist;
     DevBuf<double> dTimes;
     DevBuf<int> dDiag;
+    DevBuf<unsigned long long> dTrace;
     double2* hOut = nullptr;  // pinned
     size_t hOutCap = 0;
     std::vector<std::unique_ptr<Plan>> plans;
@@ -233,7 +238,7 @@ int qiw_destroy(qiw_context* ctx) {
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     cudaStreamSynchronize(ctx->stream);
     ctx->dP.release(); ctx->dE.release(); ctx->dDeltas.release(); ctx->dEntries.release();
-    ctx->dPerSample.release(); ctx->dTimes.release(); ctx->dHist.release(); ctx->dDiag.release();
+    ctx->dPerSample.release(); ctx->dTimes.release(); ctx->dHist.release(); ctx->dDiag.release(); ctx->dTrace.release();
     for (auto& t : ctx->tables) { t.y.release(); t.M.release(); }
     for (auto& e : ctx->entries)
         if (e) { e->records.release(); e->coefs.release(); e->dslots.release(); e->sobol.release(); }
@@ -372,9 +377,24 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
     if (rc) return fail(ctx, rc, "qiw_set_topologies: " + err);
     const EntryProgram& pr = ed.prog;
     if (ctx->no_device) { ed.valid = true; return QIW_OK; }
-    {   // leaf records, padded so that a stray vector load past the end stays in bounds
-        std::vector<uint32_t> rec(pr.records);
-        rec.resize(rec.size() + 32, 0u);
+    {   // configuration records, transposed into groups of 32 so that lane l of a warp reads record
+        // 32 g + l with coalesced loads; the last group is padded with null records (zero coefficient)
+        const int L = pr.L, RL = pr.RL;
+        const int64_t nl = pr.n_leaves, ng = (nl + 31) / 32;
+        std::vector<uint32_t> rec((size_t)std::max<int64_t>(ng, 1) * (L + 1) * 32, 0u);
+        for (int64_t g = 0; g < ng; ++g)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int64_t leaf = g * 32 + lane;
+                uint32_t* dst = rec.data() + (size_t)g * (L + 1) * 32 + lane;
+                if (leaf < nl) {
+                    const uint32_t* src = pr.records.data() + (size_t)leaf * RL;
+                    dst[0] = src[0];
+                    for (int q = 1; q <= L; ++q) dst[(size_t)q * 32] = src[q] * 16u;
+                } else {
+                    const uint32_t s_last = nl ? (pr.records[(size_t)(nl - 1) * RL] >> 16) : 0u;
+                    dst[0] = (uint32_t)pr.coefs.size() | (s_last << 16);   // index of the appended zero coefficient
+                }
+            }
         CK(ed.records.upload(rec.data(), rec.size(), ctx->stream));
     }
     std::vector<double2> cf(std::max<size_t>(pr.coefs.size(), 1));
@@ -438,6 +458,7 @@ static int sync_static_tables(qiw_context* ctx) {
             dd[t].inv_h = 1.0 / dd[t].h;
         }
         CK(ctx->dDeltas.upload(dd.data(), dd.size(), ctx->stream));
+        ctx->hDeltas = dd;
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->deltas_dirty = false;
     }
@@ -453,7 +474,7 @@ static int sync_static_tables(qiw_context* ctx) {
             d.d_after = (p.mode == 0) ? p.D : p.n_pts_after;
             d.d_before = p.D - d.d_after;
             d.nP = p.nP; d.nD = (int)p.dslots.size();
-            d.L = p.L; d.n_leaves = (int)p.n_leaves;
+            d.L = p.L; d.n_leaves = (int)p.n_leaves; d.n_groups = (int)((p.n_leaves + 31) / 32); d.n_coefs = (int)p.coefs.size();
             d.exact = (p.order == 0);
             for (int k = 0; k <= kDevMaxNodes; ++k) d.pos_src[k] = p.pos_src[k];
             d.records = ed.records.p; d.coefs = ed.coefs.p; d.dslots = ed.dslots.p;
@@ -466,7 +487,7 @@ static int sync_static_tables(qiw_context* ctx) {
 }
 
 static void release_plan(Plan& pl) {
-    pl.d_items.release(); pl.d_sobol.release();
+    pl.d_items.release(); pl.d_sobol.release(); pl.d_ucache.release();
     pl.d_dyn.release(); pl.d_partials.release(); pl.d_out.release();
 }
 
@@ -492,20 +513,22 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
     // whose chunks would exceed `chunk_cap` configurations are split further (their set-up cost is
     // then amortised anyway), and when the call is too small to fill the machine the cap is
     // lowered to expose more CTAs.
-    double max_leaves = 1;
+    double max_groups = 1;
     uint64_t n_sb_all = 1;
+    int max_coefs = 1;
     for (int i = 0; i < n_entries; ++i) {
         const EntryProgram& p = ctx->entries[ids[i]]->prog;
         const uint64_t c = p.order == 0 ? 1 : count;
-        max_leaves = std::max(max_leaves, (double)p.n_leaves);
+        max_groups = std::max(max_groups, (double)((p.n_leaves + 31) / 32));
         n_sb_all = std::max<uint64_t>(n_sb_all, (c + 31) / 32);
+        max_coefs = std::max(max_coefs, (int)p.coefs.size());
     }
-    double chunk_cap = 512.0;
+    double chunk_cap = 16.0;   // groups of 32 configurations per warp and sample block
     {
-        // CTAs available if every entry is one job; lower the cap until ~2 CTAs per SM exist
+        // CTAs available if every entry is one job; lower the cap until ~3 CTAs per SM exist
         const double ctas = (double)n_entries * (double)n_sb_all;
-        const double want = 2.0 * ndev_sm;
-        if (ctas < want) chunk_cap = std::max(16.0, max_leaves / W / std::ceil(want / ctas));
+        const double want = 3.0 * ndev_sm;
+        if (ctas < want) chunk_cap = std::max(1.0, std::floor(max_groups / W / std::ceil(want / ctas)));
     }
     pl->item0.resize(n_entries); pl->n_items.resize(n_entries);
     // heavy entries first: their CTAs are the critical path of the launch
@@ -516,17 +539,17 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         return (double)pa.n_leaves * pa.L > (double)pb2.n_leaves * pb2.L; });
     {
         Plan::Group g;
-        g.maxl = 1; g.item0 = 0; g.max_slots = 1;
+        g.maxl = 1; g.item0 = 0; g.max_slots = 1; g.max_dslots = 1;
         for (int i : order_idx) {
             const EntryProgram& p = ctx->entries[ids[i]]->prog;
             g.maxl = std::max(g.maxl, p.L);
             const uint64_t c = p.order == 0 ? 1 : count;
             pl->max_sb = std::max<uint64_t>(pl->max_sb, (c + 31) / 32);
+            const int64_t ng = (p.n_leaves + 31) / 32;
             int n_chunks = 1;
-            const int64_t nl = p.n_leaves;
-            if (!explicit_mode && nl > 0) {
-                const int groups = (int)std::max(1.0, std::ceil((double)nl / (W * chunk_cap)));
-                n_chunks = (int)std::min<int64_t>(nl, (int64_t)W * groups);
+            if (!explicit_mode && ng > 0) {
+                const int jobs = (int)std::max(1.0, std::ceil((double)ng / (W * chunk_cap)));
+                n_chunks = (int)std::min<int64_t>(ng, (int64_t)W * jobs);
             }
             pl->item0[i] = (int)pl->items.size();
             for (int c0 = 0; c0 < n_chunks; c0 += W) {
@@ -537,12 +560,13 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
                 pl->items.push_back(it);
             }
             pl->n_items[i] = (int)pl->items.size() - pl->item0[i];
-            g.max_slots = std::max(g.max_slots, p.nP + (int)p.dslots.size());
+            g.max_slots = std::max(g.max_slots, (p.nP + (int)p.dslots.size()) | 1);
+            g.max_dslots = std::max(g.max_dslots, (int)p.dslots.size());
         }
         g.n_items = (int)pl->items.size() - g.item0;
-        g.max_slots = std::max(g.max_slots, (S * W + 31) / 32 + 1);
-        g.smem = (size_t)g.max_slots * 32 * sizeof(double2) + (size_t)S * W * 32 * sizeof(double2) +
-                 (size_t)(kDevMaxNodes + 1) * 32 * sizeof(double) + (size_t)kDevMaxDim * 32 * sizeof(double) + 32 * sizeof(int);
+        g.smem = (size_t)g.max_slots * 32 * sizeof(double2) + (size_t)S * W * sizeof(double2) +
+                 (size_t)(kDevMaxNodes + 1) * 32 * sizeof(double) + (size_t)kDevMaxDim * 32 * sizeof(double) + 32 * sizeof(int) +
+                 (size_t)(max_coefs + 1) * sizeof(double2) + (size_t)g.max_dslots * sizeof(int4);
         if (g.smem > 227 * 1024) return fail(ctx, QIW_ERR_UNSUPPORTED, "per-sample tables exceed shared memory (too many sectors for the scalar kernel)");
         pl->groups.push_back(g);
     }
@@ -561,6 +585,12 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
     pl->h_sobol.assign(tot, 0u);
     CK(pl->d_sobol.reserve(tot));
     CK(pl->d_dyn.reserve(n_entries));
+    {   // cache of the unit-simplex roots: 8 bytes per (entry dimension, sample); skipped when large
+        size_t ud = 0;
+        for (int i = 0; i < n_entries; ++i) { pl->ucache_off.push_back(ud); ud += (size_t)ctx->entries[ids[i]]->prog.D * count; }
+        pl->ucache_enabled = !explicit_mode && ud > 0 && ud * sizeof(double) <= ((size_t)2 << 30);
+        if (pl->ucache_enabled) CK(pl->d_ucache.reserve(ud));
+    }
     for (int i = 0; i < n_entries; ++i) {
         DevEntryDyn& dy = pl->h_dyn[i];
         dy.sobol = pl->d_sobol.p + pl->sobol_off[i];
@@ -593,6 +623,7 @@ static int stage_call(qiw_context* ctx, Plan& pl, const uint32_t* sobol_m, const
         }
         CK(cudaMemcpyAsync(pl.d_sobol.p, pl.h_sobol.data(), pl.h_sobol.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         pl.default_sobol_resident = default_sobol;
+        pl.ucache_valid = false;   // new sequence parameters: the cached roots are stale
     }
     bool changed = !pl.dyn_resident;
     for (int i = 0; i < n_entries; ++i) {
@@ -606,8 +637,11 @@ static int stage_call(qiw_context* ctx, Plan& pl, const uint32_t* sobol_m, const
         } else {
             s2 = start; c2 = count; w = pl.explicit_mode ? 1.0 : 1.0 / (double)N_total;
         }
-        if (dy.start != s2 || dy.count != c2 || dy.weight != w) changed = true;
-        dy.start = s2; dy.count = c2; dy.weight = w;
+        if (dy.start != s2 || dy.count != c2) pl.ucache_valid = false;
+        double* uc = (pl.ucache_enabled && p.order > 0) ? pl.d_ucache.p + pl.ucache_off[i] : nullptr;
+        const int uv = (uc && pl.ucache_valid) ? 1 : 0;
+        if (dy.start != s2 || dy.count != c2 || dy.weight != w || dy.ucache != uc || dy.ucache_valid != uv) changed = true;
+        dy.start = s2; dy.count = c2; dy.weight = w; dy.ucache = uc; dy.ucache_valid = uv;
     }
     if (changed) {
         CK(cudaMemcpyAsync(pl.d_dyn.p, pl.h_dyn.data(), pl.h_dyn.size() * sizeof(DevEntryDyn), cudaMemcpyHostToDevice, ctx->stream));
@@ -624,20 +658,42 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
     memset(&sp, 0, sizeof(sp));
     sp.entries = ctx->dEntries.p; sp.dyn = pl.d_dyn.p;
     sp.P = ctx->dP.p; sp.E = ctx->dE.p; sp.deltas = ctx->dDeltas.p;
+    for (int t = 0; t < kInlineTables && t < (int)ctx->hDeltas.size(); ++t) sp.deltas_inline[t] = ctx->hDeltas[t];
     sp.S = m.S; sp.bsize = m.bsize; sp.n_tau = ctx->n_tau; sp.h = ctx->beta / (ctx->n_tau - 1); sp.inv_h = 1.0 / sp.h;
     sp.t_i = t_i; sp.t_w = t_w; sp.t_f = t_f;
     sp.partials = pl.d_partials.p;
     if (pl.explicit_mode) { sp.explicit_times = ctx->dTimes.p; sp.per_sample_out = ctx->dPerSample.p; }
+    const char* trace_path = getenv("QIW_TRACE");   // diagnostics: per-CTA timeline of the last step kernel
+    size_t trace_words = 0;
+    if (trace_path) {
+        trace_words = (size_t)pl.pitch * pl.items.size() * 8;
+        CK(ctx->dTrace.reserve(trace_words));
+        CK(cudaMemsetAsync(ctx->dTrace.p, 0, trace_words * sizeof(unsigned long long), ctx->stream));
+        sp.trace = ctx->dTrace.p;
+    }
     for (auto& g : pl.groups) {
         StepParams gp = sp;
         gp.items = pl.d_items.p + g.item0;
         gp.max_slots = g.max_slots;
+        gp.max_dslots = g.max_dslots;
         dim3 grid((unsigned)pl.pitch, (unsigned)g.n_items);
         {
             ProfScope ps(ctx, g.maxl <= 8 ? 0 : g.maxl <= 14 ? 1 : g.maxl <= 20 ? 2 : 3);
             CK(launch_scalar_step(g.maxl, gp, grid, ctx->warps * 32, g.smem, ctx->stream));
         }
         ctx->launches++;
+    }
+    if (trace_path) {
+        std::vector<unsigned long long> tr(trace_words);
+        CK(cudaMemcpyAsync(tr.data(), ctx->dTrace.p, trace_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (FILE* f = fopen(trace_path, "w")) {
+            fprintf(f, "cta,start_clk,tables_clk,walk_clk,end_clk,smid,entry,groups_warp0,start_ns\n");
+            for (size_t c = 0; c < trace_words / 8; ++c)
+                fprintf(f, "%zu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu\n", c, tr[c * 8], tr[c * 8 + 1], tr[c * 8 + 2], tr[c * 8 + 3],
+                        tr[c * 8 + 4], tr[c * 8 + 5], tr[c * 8 + 6], tr[c * 8 + 7]);
+            fclose(f);
+        }
     }
     if (!pl.explicit_mode) {
         {
@@ -647,6 +703,15 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         }
         ctx->launches++;
     }
+    return QIW_OK;
+}
+
+// After the first evaluation of a plan the simplex roots of its sequence are in the cache.
+static int mark_ucache_valid(qiw_context* ctx, Plan& pl) {
+    if (!pl.ucache_enabled || pl.ucache_valid) return QIW_OK;
+    pl.ucache_valid = true;
+    for (auto& dy : pl.h_dyn) dy.ucache_valid = dy.ucache ? 1 : 0;
+    CK(cudaMemcpyAsync(pl.d_dyn.p, pl.h_dyn.data(), pl.h_dyn.size() * sizeof(DevEntryDyn), cudaMemcpyHostToDevice, ctx->stream));
     return QIW_OK;
 }
 
@@ -693,6 +758,8 @@ static int eval_scalar(qiw_context* ctx, double t_i, double t_w, double t_f, int
     rc = enqueue_step(ctx, pl, t_i, t_w, t_f);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    rc = mark_ucache_valid(ctx, pl);
+    if (rc) return rc;
     const size_t n_out = explicit_mode ? (size_t)n_explicit * S : (size_t)n_entries * m.bsize;
     double2* src = explicit_mode ? ctx->dPerSample.p : pl.d_out.p;
     if (allreduce && !explicit_mode) { rc = nccl_allreduce(ctx, src, n_out); if (rc) return rc; }
@@ -815,6 +882,8 @@ int qiw_inchworm_run(qiw_context* ctx, int32_t n_bare, const int32_t* bare_ids, 
     // bold steps n = 2 .. n_tau-1 (1-based): tau_w = grid[n], tau_f = grid[n+1] (:474-493)
     for (int n = 1; n_bold > 0 && n < n_tau - 1; ++n) {
         rc = enqueue_step(ctx, *pd, 0.0, n * h, (n + 1) * h);
+        if (rc) return rc;
+        rc = mark_ucache_valid(ctx, *pd);
         if (rc) return rc;
         rc = nccl_allreduce(ctx, pd->d_out.p, (size_t)n_bold * bs);
         if (rc) return rc;

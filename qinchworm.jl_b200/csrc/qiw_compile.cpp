@@ -115,7 +115,7 @@ struct Builder {
                     if (e.scalar) {   // leaf record
                         const uint32_t cid = (uint32_t)coef_id(c2 * top_sign);
                         e.records.push_back(cid | ((uint32_t)s_init << 16));
-                        for (uint32_t sl : path) e.records.push_back(sl * 512u);
+                        for (uint32_t sl : path) e.records.push_back(sl);
                         for (int k = (int)path.size() + 1; k < e.RL; ++k) e.records.push_back(0u);
                     }
                 }

@@ -10,6 +10,7 @@ namespace qiw {
 constexpr int kDevMaxNodes = 19;
 constexpr int kDevMaxDim = 24;      // Sobol dimensions handled per entry (2 * order <= 16)
 constexpr int kMaxTables = 64;
+constexpr int kInlineTables = 8;     // propagator tables described directly in the kernel parameters
 
 // One scalar propagator table resident in HBM.
 struct DevDelta {
@@ -27,8 +28,10 @@ struct DevEntry {
     int nP, nD;                 // table slots: propagators, pair interactions
     int exact;                  // order 0: one deterministic evaluation
     int pos_src[kDevMaxNodes + 1];
-    int L, n_leaves;            // record length (factors per configuration), number of records
-    const uint32_t* records;    // [n_leaves][RL]
+    int n_coefs;
+    int L, n_leaves, n_groups;  // record length (factors per configuration), records, groups of 32
+    const uint32_t* records;    // transposed: [n_groups][L + 1][32 lanes]; word 0 = coef | s_i << 16,
+                                // words 1..L = byte offset (slot * 16) inside a sample's table row
     const double2* coefs;
     const int4* dslots;         // (pos_tail, pos_head, table, 0)
 };
@@ -36,6 +39,8 @@ struct DevEntry {
 // Per call, per entry.
 struct DevEntryDyn {
     const uint32_t* sobol;      // m[D][32] followed by x0[D]
+    double* ucache;             // cached simplex roots [D][count] of this entry, or null
+    int ucache_valid, pad_;
     double weight;              // 1/N_total (sampled entries); 1 or 0 (exact entries, by rank)
     unsigned long long start;   // first Sobol index evaluated by this rank
     unsigned long long count;   // number of Sobol points evaluated by this rank (1 if exact)
@@ -62,6 +67,8 @@ struct StepParams {
     const double2* P;              // [n_tau][bsize]
     const double* E;               // [S] (scalar models) energies + lambda
     const DevDelta* deltas;
+    DevDelta deltas_inline[kInlineTables];
+    int max_dslots;
     int S, bsize, n_tau;
     double h, inv_h;               // beta / (n_tau - 1) and its reciprocal
     // times; when `times_dev` is non-null the triple is read from device memory (run-level API)
@@ -73,6 +80,7 @@ struct StepParams {
     double2* per_sample_out;       // [count][S]
     // output
     double2* partials;             // [n partial rows][gridDim.x][S]
+    unsigned long long* trace;     // diagnostics: 8 words per CTA, or null
 };
 
 }  // namespace qiw

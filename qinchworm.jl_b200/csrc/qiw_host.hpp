@@ -62,8 +62,8 @@ struct EntryProgram {
     std::vector<DeltaSlot> dslots;         // pair-interaction factors referenced by the program
     int nP = 0;                            // number of propagator slots ((n_nodes-1) * S)
     // Leaf records (scalar models): one fixed-length record per surviving configuration, in the
-    // tree's leaf order.  rec[0] = coefficient index | initial sector << 16; rec[1..L] = byte offset
-    // (slot * 512) of every factor of the configuration's weight in the per-sample table; padded
+    // tree's leaf order.  rec[0] = coefficient index | initial sector << 16; rec[1..L] = table slot
+    // of every factor of the configuration's weight in the per-sample table; padded
     // with zeros to RL words (RL % 4 == 0).  L = (n_nodes - 1) propagators + `order` interactions.
     std::vector<uint32_t> records;
     int L = 0, RL = 0;

@@ -99,57 +99,96 @@ __global__ void sobol_points_kernel(int D, const uint32_t* __restrict__ m, const
     out[i] = sobol_coord(m + d * 32, x0[d], (uint32_t)(start + k));
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // ---- configuration walk ------------------------------------------------------------------------
-// Every surviving configuration of the entry is a fixed-length record of table offsets
-// (qiw_host.hpp: EntryProgram::records).  The record is warp-uniform, the table is per lane: the walk
-// is a branch-free product of L factors gathered from shared memory — exactly the weight
+// Every surviving configuration of an entry is a fixed-length record of table offsets
+// (qiw_host.hpp: EntryProgram::records): the weight
 //   prod_arcs[i Delta_p(t_tail, t_head)] * prod_pos[O_pos * i P_s(t_pos, t_pos-1)]
 // of src/topology_eval.jl:454-556 with the operator matrix elements and the topology sign
 // (-i * parity * (-1)^order, :431) folded into the record's coefficient.  For 1x1 blocks the
 // reference's cached partial products (src/utility.jl:234-323) save almost nothing (the tree
 // branches at the earliest positions), while a flat record needs no control flow at all.
-template <int L>
-__device__ __forceinline__ void leaf_walk(const uint32_t* __restrict__ rec, int leaf0, int leaf1,
-                                          const unsigned char* Tl, const double2* __restrict__ coefs,
-                                          double2* sacc_t, int sacc_stride, bool ok, double2* sample_out) {
-    constexpr int RL = ((L + 1 + 3) / 4) * 4;
-    const uint4* r = reinterpret_cast<const uint4*>(rec + (size_t)leaf0 * RL);
-    double2 acc = make_double2(0.0, 0.0);
-    int cur_s = -1;
-    for (int leaf = leaf0; leaf < leaf1; ++leaf) {
-        uint32_t w[RL];
+//
+// Mapping: one LANE owns one configuration (its record lives in registers for the whole sample
+// block), and loops over the 32 samples of the CTA, whose tables sit in shared memory as
+// T[sample][slot].  Per factor that is ONE instruction (LDS with a uniform row base + the lane's
+// constant offset) feeding four FP64 instructions; lanes that need the same factor (all lanes do,
+// up to the sector index) read the same address, which shared memory serves as a broadcast.
+template <int L, bool PER_SAMPLE>
+__device__ __forceinline__ void config_walk(const uint32_t* __restrict__ rec_t, int g0, int g1,
+                                            const unsigned char* T, int row_bytes, const double2* coefs_s,
+                                            double2* red, int nw, int warp, int lane, int S,
+                                            double2* sample_out, unsigned long long local0, unsigned long long count) {
+    constexpr int H = (L + 1) / 2;   // the product is evaluated as two independent half chains
+    for (int g = g0; g < g1; ++g) {
+        uint32_t w[L + 1];
+        const uint32_t* rp = rec_t + (size_t)g * (L + 1) * 32 + lane;
 #pragma unroll
-        for (int q = 0; q < RL / 4; ++q) {
-            const uint4 x = __ldg(r + q);
-            w[4 * q] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w;
-        }
-        r += RL / 4;
+        for (int q = 0; q <= L; ++q) w[q] = __ldg(rp + q * 32);
         const int s_i = (int)(w[0] >> 16);
-        if (s_i != cur_s) {   // records are grouped by initial sector: rare
-            if (cur_s >= 0 && ok) {
-                double2* a = sample_out ? sample_out + cur_s : sacc_t + cur_s * sacc_stride;
-                *a = cadd(*a, acc);
-            }
-            acc = make_double2(0.0, 0.0);
-            cur_s = s_i;
-        }
-        const double2 coef = __ldg(coefs + (w[0] & 0xFFFFu));
-        double2 v = *reinterpret_cast<const double2*>(Tl + w[1]);
+        const double2 coef = coefs_s[w[0] & 0xFFFFu];
+        const int smin = (int)__reduce_min_sync(0xFFFFFFFFu, (unsigned)s_i);
+        const int smax = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)s_i);
+        double2 acc = make_double2(0.0, 0.0);
+#pragma unroll 2
+        for (int smp = 0; smp < 32; ++smp) {
+            const unsigned char* row = T + smp * row_bytes;
+            double2 va = *reinterpret_cast<const double2*>(row + w[1]);
 #pragma unroll
-        for (int f = 2; f <= L; ++f) v = cmul(v, *reinterpret_cast<const double2*>(Tl + w[f]));
-        acc = cfma(coef, v, acc);
-    }
-    if (cur_s >= 0 && ok) {
-        double2* a = sample_out ? sample_out + cur_s : sacc_t + cur_s * sacc_stride;
-        *a = cadd(*a, acc);
+            for (int f = 2; f <= H; ++f) va = cmul(va, *reinterpret_cast<const double2*>(row + w[f]));
+            if constexpr (L > H) {
+                double2 vb = *reinterpret_cast<const double2*>(row + w[H + 1]);
+#pragma unroll
+                for (int f = H + 2; f <= L; ++f) vb = cmul(vb, *reinterpret_cast<const double2*>(row + w[f]));
+                va = cmul(va, vb);
+            }
+            if constexpr (PER_SAMPLE) {
+                // qiw_eval_at_times: the evaluator's value for every sample separately
+                const double2 c = cmul(coef, va);
+                for (int s = smin; s <= smax; ++s) {
+                    double2 r = (s_i == s) ? c : make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        r.x += __shfl_down_sync(0xFFFFFFFFu, r.x, off);
+                        r.y += __shfl_down_sync(0xFFFFFFFFu, r.y, off);
+                    }
+                    if (lane == 0 && local0 + smp < count) {
+                        double2* o = sample_out + (local0 + smp) * S + s;
+                        *o = cadd(*o, r);
+                    }
+                }
+            } else {
+                acc = cadd(acc, va);
+            }
+        }
+        if constexpr (!PER_SAMPLE) {
+            // sum over the lanes' configurations, separately for every initial sector present
+            const double2 c = cmul(coef, acc);
+            for (int s = smin; s <= smax; ++s) {
+                double2 r = (s_i == s) ? c : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    r.x += __shfl_down_sync(0xFFFFFFFFu, r.x, off);
+                    r.y += __shfl_down_sync(0xFFFFFFFFu, r.y, off);
+                }
+                if (lane == 0) red[s * nw + warp] = cadd(red[s * nw + warp], r);
+            }
+        }
     }
 }
 
 // Record lengths that occur: 3n+2 (bold / correlator, order n) and 3n+1 (bare).
-template <int LMAX>
-__device__ __forceinline__ void leaf_dispatch(int L, const uint32_t* rec, int leaf0, int leaf1, const unsigned char* Tl,
-                                              const double2* coefs, double2* sacc_t, int stride, bool ok, double2* so) {
-#define QIW_CASE(N) case N: if constexpr (N <= LMAX) leaf_walk<N>(rec, leaf0, leaf1, Tl, coefs, sacc_t, stride, ok, so); break;
+template <int LMAX, bool PER_SAMPLE>
+__device__ __forceinline__ void walk_dispatch(int L, const uint32_t* rec_t, int g0, int g1, const unsigned char* T,
+                                              int row_bytes, const double2* coefs_s, double2* red, int nw, int warp,
+                                              int lane, int S, double2* so, unsigned long long local0,
+                                              unsigned long long count) {
+#define QIW_CASE(N) case N: if constexpr (N <= LMAX) config_walk<N, PER_SAMPLE>(rec_t, g0, g1, T, row_bytes, coefs_s, red, nw, warp, lane, S, so, local0, count); break;
     switch (L) {
         QIW_CASE(1) QIW_CASE(2) QIW_CASE(4) QIW_CASE(5) QIW_CASE(7) QIW_CASE(8) QIW_CASE(10) QIW_CASE(11)
         QIW_CASE(13) QIW_CASE(14) QIW_CASE(16) QIW_CASE(17) QIW_CASE(19) QIW_CASE(20) QIW_CASE(22) QIW_CASE(23)
@@ -161,7 +200,7 @@ __device__ __forceinline__ void leaf_dispatch(int L, const uint32_t* rec, int le
 
 // ---- the step kernel (scalar models: every sector block is 1x1) ------------------------------
 
-template <int LMAX>
+template <int LMAX, bool PER_SAMPLE>
 __global__ void __launch_bounds__(256, (LMAX <= 14) ? 3 : 2) scalar_step_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -170,15 +209,22 @@ __global__ void __launch_bounds__(256, (LMAX <= 14) ? 3 : 2) scalar_step_kernel(
     const DevEntryDyn& dy = p.dyn[it.slot];
     const int S = p.S, D = e.D, n_nodes = e.n_nodes, nP = e.nP, n_slots = e.nP + e.nD;
     const int d_after = e.d_after;
+    // shared memory carve-up (sizes fixed per launch from the largest entry, see host):
+    // T[32 samples][row] with an odd row pitch (in 16-byte units) so that the lanes' stores during
+    // the fill hit different banks
+    const int row_bytes = (n_slots | 1) * 16;
+    unsigned char* T = smem_raw;                                                 // [32][max_row_bytes]
+    double2* red = reinterpret_cast<double2*>(smem_raw + (size_t)p.max_slots * 32 * 16);   // [S][nw]
+    double* times = reinterpret_cast<double*>(red + (size_t)S * nw);             // [kDevMaxNodes+1][32]
+    double* pw = times + (kDevMaxNodes + 1) * 32;                                // [kDevMaxDim][32]
+    int* okflag = reinterpret_cast<int*>(pw + kDevMaxDim * 32);                  // [32]
+    int4* dslots_s = reinterpret_cast<int4*>(okflag + 32);                       // [max_dslots]
+    double2* coefs_s = reinterpret_cast<double2*>(dslots_s + p.max_dslots);      // [n_coefs + 1]
+    for (int c = threadIdx.x; c < e.nD; c += blockDim.x) dslots_s[c] = e.dslots[c];
 
-    // shared memory carve-up (sizes fixed per launch from the largest entry, see host)
-    double2* T = reinterpret_cast<double2*>(smem_raw);                       // [max_slots][32]
-    double2* sacc = T + (size_t)p.max_slots * 32;                            // [S][blockDim.x]
-    double* times = reinterpret_cast<double*>(sacc + (size_t)S * blockDim.x); // [kDevMaxNodes+1][32]
-    double* pw = times + (kDevMaxNodes + 1) * 32;                            // [kDevMaxDim][32]
-    int* okflag = reinterpret_cast<int*>(pw + kDevMaxDim * 32);              // [32]
-
-    for (int s = 0; s < S; ++s) sacc[s * blockDim.x + threadIdx.x] = make_double2(0.0, 0.0);
+    for (int c = threadIdx.x; c < S * nw; c += blockDim.x) red[c] = make_double2(0.0, 0.0);
+    for (int c = threadIdx.x; c <= e.n_coefs; c += blockDim.x)
+        coefs_s[c] = (c < e.n_coefs) ? e.coefs[c] : make_double2(0.0, 0.0);   // last: padding records
 
     double t_i = p.t_i, t_w = p.t_w, t_f = p.t_f;
     if (p.times_dev) { t_i = p.times_dev[0]; t_w = p.times_dev[1]; t_f = p.times_dev[2]; }
@@ -189,26 +235,50 @@ __global__ void __launch_bounds__(256, (LMAX <= 14) ? 3 : 2) scalar_step_kernel(
     const unsigned long long count = dy.count;
     const int n_sb = (int)((count + 31ull) >> 5);
 
-    // this warp's share of the entry's configurations: chunk c of n_chunks_total
-    int leaf0 = 0, leaf1 = 0;
+    // this warp's share of the entry's configuration groups (32 configurations per group)
+    int g0 = 0, g1 = 0;
     if (warp < it.n_chunks) {
-        const long long c = it.chunk0 + warp, nct = it.n_chunks_total, nl = e.n_leaves;
-        leaf0 = (int)(c * nl / nct);
-        leaf1 = (int)((c + 1) * nl / nct);
+        const long long c = it.chunk0 + warp, nct = it.n_chunks_total, ng = e.n_groups;
+        g0 = (int)(c * ng / nct);
+        g1 = (int)((c + 1) * ng / nct);
+    }
+
+    // optional per-CTA timeline (diagnostics; compiled in only with -DQIW_TRACE_BUILD because
+    // reading %globaltimer costs microseconds): start / tables ready / walk done / end
+#ifdef QIW_TRACE_BUILD
+    unsigned long long* trace = p.trace ? p.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+#else
+    constexpr unsigned long long* trace = nullptr;
+#endif
+    if (trace && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        trace[7] = globaltimer_ns();   // one wall-clock stamp; phase durations use the SM cycle counter
+        trace[0] = clock64(); trace[4] = smid; trace[5] = it.entry; trace[6] = (unsigned long long)(g1 - g0);
     }
 
     for (int sb = blockIdx.x; sb < n_sb; sb += gridDim.x) {
-        const unsigned long long local = (unsigned long long)sb * 32ull + lane;
+        const unsigned long long local0 = (unsigned long long)sb * 32ull, local = local0 + lane;
         const bool active = local < count;
         const uint32_t k = (uint32_t)(dy.start + local);
 
         // -- 1. Sobol coordinates and the independent roots x_j^(1/(remaining dims)) ----------
+        //       The roots depend only on (entry, Sobol sequence, sample), not on the time step: when the
+        //       host provides a cache they are computed once per run and re-read afterwards.
         if (p.explicit_times == nullptr) {
+            double* uc = dy.ucache;
             for (int j = warp; j < D; j += nw) {
-                const uint32_t xi = sobol_coord(sm + j * 32, __ldg(sm + D * 32 + j), k);
-                const double x = (double)xi * 2.3283064365386963e-10;  // ldexp(x, -32), exact
-                const int den = (j < d_after) ? (d_after - j) : (D - j);
-                pw[j * 32 + lane] = (den == 1) ? x : pow(x, 1.0 / (double)den);
+                double r;
+                if (uc && dy.ucache_valid) {
+                    r = active ? uc[(size_t)j * count + local] : 0.0;
+                } else {
+                    const uint32_t xi = sobol_coord(sm + j * 32, __ldg(sm + D * 32 + j), k);
+                    const double x = (double)xi * 2.3283064365386963e-10;  // ldexp(x, -32), exact
+                    const int den = (j < d_after) ? (d_after - j) : (D - j);
+                    r = (den == 1) ? x : pow(x, 1.0 / (double)den);
+                    if (uc && active && it.chunk0 == 0) uc[(size_t)j * count + local] = r;
+                }
+                pw[j * 32 + lane] = r;
             }
         }
         __syncthreads();
@@ -238,59 +308,56 @@ __global__ void __launch_bounds__(256, (LMAX <= 14) ? 3 : 2) scalar_step_kernel(
         }
         __syncthreads();
 
-        // -- 3. per-sample tables --------------------------------------------------------------
-        for (int q = warp; q < n_slots; q += nw) {
-            double2 val;
-            if (q < nP) {
-                const int iv = q / S, s = q - iv * S;      // interval between positions iv+1, iv+2
-                const double ta = times[(iv + 1) * 32 + lane];
-                double tb = times[(iv + 2) * 32 + lane];
-                if (tb < ta) tb = ta;                       // src/topology_eval.jl:362-364
-                if (e.mode == 0) {                          // bare: i * (-i) exp(-dt (E + lambda))
-                    val = make_double2(exp(-(tb - ta) * __ldg(p.E + s)), 0.0);
+        // -- 3. per-sample tables: thread (warp, lane) fills slots warp, warp+nw, ... of sample `lane`.
+        //       Discarded samples (src/qmc_integrate.jl:503,608) and lanes past the range get zero rows.
+        {
+            const bool ok = okflag[lane] != 0;
+            unsigned char* myrow = T + lane * row_bytes;
+#pragma unroll 2
+            for (int q = warp; q < n_slots; q += nw) {
+                double2 val;
+                if (q < nP) {
+                    const int iv = q / S, s = q - iv * S;      // interval between positions iv+1, iv+2
+                    const double ta = times[(iv + 1) * 32 + lane];
+                    double tb = times[(iv + 2) * 32 + lane];
+                    if (tb < ta) tb = ta;                       // src/topology_eval.jl:362-364
+                    if (e.mode == 0) {                          // bare: i * (-i) exp(-dt (E + lambda))
+                        val = make_double2(exp(-(tb - ta) * __ldg(p.E + s)), 0.0);
+                    } else {
+                        val = times_i(grid_interp(p.P + s, p.bsize, p.n_tau, p.inv_h, tb, ta));
+                    }
                 } else {
-                    val = times_i(grid_interp(p.P + s, p.bsize, p.n_tau, p.inv_h, tb, ta));
+                    const int4 ds = dslots_s[q - nP];
+                    const double th = times[ds.y * 32 + lane];
+                    double tt = times[ds.x * 32 + lane];
+                    if (tt < th) tt = th;                       // :407-410
+                    val = times_i(delta_eval(ds.z < kInlineTables ? p.deltas_inline[ds.z] : p.deltas[ds.z], tt, th));
                 }
-            } else {
-                const int4 ds = __ldg(e.dslots + (q - nP));
-                const double th = times[ds.y * 32 + lane];
-                double tt = times[ds.x * 32 + lane];
-                if (tt < th) tt = th;                       // :407-410
-                val = times_i(delta_eval(p.deltas[ds.z], tt, th));
+                if (!ok) val = make_double2(0.0, 0.0);
+                *reinterpret_cast<double2*>(myrow + q * 16) = val;
             }
-            T[q * 32 + lane] = val;
         }
         __syncthreads();
+        if (trace && threadIdx.x == 0) trace[1] = clock64();
 
         // -- 4. this warp's configurations -----------------------------------------------------
-        if (leaf0 < leaf1) {
-            const bool ok = okflag[lane] != 0;
-            double2* so = p.per_sample_out ? p.per_sample_out + local * S : nullptr;
-            leaf_dispatch<LMAX>(e.L, e.records, leaf0, leaf1, reinterpret_cast<const unsigned char*>(T + lane), e.coefs,
-                                sacc + threadIdx.x, (int)blockDim.x, ok, so);
+        if (g0 < g1) {
+            walk_dispatch<LMAX, PER_SAMPLE>(e.L, e.records, g0, g1, T, row_bytes, coefs_s, red, nw, warp, lane, S,
+                                            p.per_sample_out, local0, count);
         }
         __syncthreads();
+        if (trace && threadIdx.x == 0) trace[2] = clock64();
     }
 
-    if (p.per_sample_out) return;
+    if constexpr (PER_SAMPLE) return;
 
-    // -- 5. CTA reduction: lanes by shuffle, warps through shared memory, fixed order ---------
-    double2* red = T;  // reuse: [S][nw]
-    for (int s = 0; s < S; ++s) {
-        double2 v = sacc[s * blockDim.x + threadIdx.x];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            v.x += __shfl_down_sync(0xFFFFFFFFu, v.x, off);
-            v.y += __shfl_down_sync(0xFFFFFFFFu, v.y, off);
-        }
-        if (lane == 0) red[s * nw + warp] = v;
-    }
-    __syncthreads();
+    // -- 5. CTA result: warps summed in fixed order -----------------------------------------------
     if ((int)threadIdx.x < S) {
         double2 v = make_double2(0.0, 0.0);
         for (int w2 = 0; w2 < nw; ++w2) v = cadd(v, red[threadIdx.x * nw + w2]);
         p.partials[((size_t)it.partial0 * gridDim.x + blockIdx.x) * S + threadIdx.x] = v;
     }
+    if (trace && threadIdx.x == 0) trace[3] = clock64();
 }
 
 }  // namespace qiw
@@ -385,16 +452,23 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) 
 
 // ---- host-callable launchers -----------------------------------------------------------------
 
-template <int LMAX>
-static cudaError_t launch_scalar(const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+template <int LMAX, bool PER_SAMPLE>
+static cudaError_t launch_scalar_t(const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(scalar_step_kernel<LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(scalar_step_kernel<LMAX, PER_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    scalar_step_kernel<LMAX><<<grid, threads, smem, st>>>(p);
+    scalar_step_kernel<LMAX, PER_SAMPLE><<<grid, threads, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+template <int LMAX>
+static cudaError_t launch_scalar(const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    // the per-sample variant (qiw_eval_at_times) is only instantiated for the deepest class
+    if (p.per_sample_out) return launch_scalar_t<26, true>(p, grid, threads, smem, st);
+    return launch_scalar_t<LMAX, false>(p, grid, threads, smem, st);
 }
 
 // `lmax` = longest record of the launch; classes: orders <= 2, <= 4, <= 6, <= 8.

@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libqinchworm_cuda.so")
+LIB_PATH = os.environ.get("QIW_LIB", os.path.join(HERE, "libqinchworm_cuda.so"))
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "qinchworm.h")
 
 MODE_BARE, MODE_BOLD, MODE_CORR = 0, 1, 2
