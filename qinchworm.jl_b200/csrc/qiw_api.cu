@@ -25,6 +25,7 @@ cudaError_t launch_finish_step(double2* P, int n_tau, int bsize, const int* diag
 cudaError_t launch_sobol_points(int D, const uint32_t* m, const uint32_t* x0, unsigned long long start,
                                 unsigned long long count, uint32_t* out, cudaStream_t st);
 cudaError_t launch_dfma_peak(double* out, int blocks, int iters, cudaStream_t st);
+cudaError_t launch_block_step(const StepParams& p, const BlockParams& bp, dim3 grid, int threads, size_t smem, cudaStream_t st);
 }  // namespace qiw
 
 using namespace qiw;
@@ -87,6 +88,8 @@ struct EntryDev {
     EntryProgram prog;
     bool valid = false;
     DevBuf<uint32_t> records;
+    DevBuf<uint64_t> words;      // block models: tree word stream
+    DevBuf<uint32_t> tree_off;
     DevBuf<double2> coefs;
     DevBuf<int4> dslots;
     DevBuf<uint32_t> sobol;   // m[D][32] + x0[D] of the current call
@@ -111,6 +114,8 @@ struct Plan {   // launch plan of one qiw_eval call shape, cached
     size_t partial_rows = 0;
     uint64_t max_sb = 1;
     int pitch = 1;
+    int block_threads = 0;                 // block models: threads per CTA
+    size_t scratch_per_thread = 0;
     DevBuf<uint32_t> d_sobol;
     std::vector<size_t> sobol_off;         // per call entry, offset into d_sobol
     std::vector<uint32_t> h_sobol;
@@ -144,6 +149,13 @@ struct qiw_context {
     DevBuf<double2> dPerSample, dHist;
     DevBuf<double> dTimes;
     DevBuf<int> dDiag;
+    // block models
+    DevBuf<int> dDim, dBoff, dEoff, dOpTarget;
+    DevBuf<long long> dOpOff;
+    DevBuf<double2> dPool, dScratch;
+    DevBuf<const uint64_t*> dWordsPtr;
+    DevBuf<const uint32_t*> dTreeOffPtr;
+    DevBuf<int> dNTrees;
     DevBuf<unsigned long long> dTrace;
     double2* hOut = nullptr;  // pinned
     size_t hOutCap = 0;
@@ -239,9 +251,11 @@ int qiw_destroy(qiw_context* ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->dP.release(); ctx->dE.release(); ctx->dDeltas.release(); ctx->dEntries.release();
     ctx->dPerSample.release(); ctx->dTimes.release(); ctx->dHist.release(); ctx->dDiag.release(); ctx->dTrace.release();
+    ctx->dDim.release(); ctx->dBoff.release(); ctx->dEoff.release(); ctx->dOpTarget.release(); ctx->dOpOff.release();
+    ctx->dPool.release(); ctx->dScratch.release(); ctx->dWordsPtr.release(); ctx->dTreeOffPtr.release(); ctx->dNTrees.release();
     for (auto& t : ctx->tables) { t.y.release(); t.M.release(); }
     for (auto& e : ctx->entries)
-        if (e) { e->records.release(); e->coefs.release(); e->dslots.release(); e->sobol.release(); }
+        if (e) { e->records.release(); e->words.release(); e->tree_off.release(); e->coefs.release(); e->dslots.release(); e->sobol.release(); }
     for (auto& pl : ctx->plans) release_plan(*pl);
     ctx->plans.clear();
     if (ctx->hOut) cudaFreeHost(ctx->hOut);
@@ -303,8 +317,16 @@ int qiw_set_model(qiw_context* ctx, int32_t S, const int32_t* dims, const double
     if (!ctx->no_device) {
         cudaSetDevice(ctx->device);
         CK(ctx->dE.upload(m.energies.data(), m.energies.size(), ctx->stream));
+        CK(ctx->dDim.upload(m.dim.data(), m.dim.size(), ctx->stream));
+        CK(ctx->dBoff.upload(m.boff.data(), m.boff.size(), ctx->stream));
+        CK(ctx->dEoff.upload(m.eoff.data(), m.eoff.size(), ctx->stream));
+        CK(ctx->dOpTarget.upload(m.op_target.data(), m.op_target.size(), ctx->stream));
+        std::vector<long long> off64(m.op_off.begin(), m.op_off.end());
+        CK(ctx->dOpOff.upload(off64.data(), off64.size(), ctx->stream));
+        CK(ctx->dPool.upload((const double2*)m.pool.data(), m.pool.size(), ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    if (m.maxdim > 4) return fail(ctx, QIW_ERR_UNSUPPORTED, "qiw_set_model: sector blocks larger than 4x4 are not supported");
     for (auto& e : ctx->entries) if (e) e->valid = false;   // programs depend on the model
     ctx->entries_dirty = true;
     drop_plans(ctx);
@@ -377,7 +399,7 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
     if (rc) return fail(ctx, rc, "qiw_set_topologies: " + err);
     const EntryProgram& pr = ed.prog;
     if (ctx->no_device) { ed.valid = true; return QIW_OK; }
-    {   // configuration records, transposed into groups of 32 so that lane l of a warp reads record
+    if (ctx->model.scalar) {   // configuration records, transposed into groups of 32 so that lane l of a warp reads record
         // 32 g + l with coalesced loads; the last group is padded with null records (zero coefficient)
         const int L = pr.L, RL = pr.RL;
         const int64_t nl = pr.n_leaves, ng = (nl + 31) / 32;
@@ -396,6 +418,10 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
                 }
             }
         CK(ed.records.upload(rec.data(), rec.size(), ctx->stream));
+    }
+    if (!ctx->model.scalar) {
+        CK(ed.words.upload(pr.words.data(), pr.words.size(), ctx->stream));
+        CK(ed.tree_off.upload(pr.tree_off.data(), pr.tree_off.size(), ctx->stream));
     }
     std::vector<double2> cf(std::max<size_t>(pr.coefs.size(), 1));
     for (size_t k = 0; k < pr.coefs.size(); ++k) cf[k] = make_double2(pr.coefs[k].real(), pr.coefs[k].imag());
@@ -480,6 +506,19 @@ static int sync_static_tables(qiw_context* ctx) {
             d.records = ed.records.p; d.coefs = ed.coefs.p; d.dslots = ed.dslots.p;
         }
         CK(ctx->dEntries.upload(de.data(), de.size(), ctx->stream));
+        if (!ctx->model.scalar) {
+            std::vector<const uint64_t*> wp(de.size(), nullptr);
+            std::vector<const uint32_t*> tp(de.size(), nullptr);
+            std::vector<int> nt(de.size(), 0);
+            for (size_t i = 0; i < ctx->entries.size(); ++i) {
+                if (!ctx->entries[i] || !ctx->entries[i]->valid) continue;
+                wp[i] = ctx->entries[i]->words.p; tp[i] = ctx->entries[i]->tree_off.p;
+                nt[i] = (int)ctx->entries[i]->prog.tree_off.size() - 1;
+            }
+            CK(ctx->dWordsPtr.upload(wp.data(), wp.size(), ctx->stream));
+            CK(ctx->dTreeOffPtr.upload(tp.data(), tp.size(), ctx->stream));
+            CK(ctx->dNTrees.upload(nt.data(), nt.size(), ctx->stream));
+        }
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->entries_dirty = false;
     }
@@ -507,6 +546,40 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
     const int S = ctx->model.S;
     int ndev_sm = 148;
     cudaDeviceGetAttribute(&ndev_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+    if (!ctx->model.scalar) {
+        // Block models: one thread per (sample, chunk of trees); 64 samples per CTA.
+        const int TPB = 64;
+        uint64_t n_sb_max = 1;
+        for (int i = 0; i < n_entries; ++i) {
+            const EntryProgram& p = ctx->entries[ids[i]]->prog;
+            n_sb_max = std::max<uint64_t>(n_sb_max, ((p.order == 0 ? 1 : count) + TPB - 1) / TPB);
+        }
+        const int split = explicit_mode ? 1 : (int)std::max<double>(1.0, std::ceil(4.0 * ndev_sm / ((double)n_entries * (double)n_sb_max)));
+        pl->item0.resize(n_entries); pl->n_items.resize(n_entries);
+        Plan::Group g;
+        g.maxl = 0; g.item0 = 0; g.max_slots = 1; g.max_dslots = 1;
+        size_t spt = 1;
+        for (int i = 0; i < n_entries; ++i) {
+            const EntryProgram& p = ctx->entries[ids[i]]->prog;
+            const int n_trees = (int)p.tree_off.size() - 1;
+            const int n_chunks = std::max(1, std::min(n_trees, split));
+            pl->item0[i] = (int)pl->items.size();
+            for (int c0 = 0; c0 < n_chunks; ++c0) {
+                WorkItem it;
+                it.entry = ids[i]; it.slot = i; it.chunk0 = c0; it.n_chunks = 1; it.n_chunks_total = n_chunks;
+                it.partial0 = (int)pl->items.size();
+                pl->items.push_back(it);
+            }
+            pl->n_items[i] = n_chunks;
+            spt = std::max(spt, (size_t)(p.n_nodes - 1) * ctx->model.bsize + p.dslots.size() + ctx->model.bsize);
+        }
+        g.n_items = (int)pl->items.size();
+        g.smem = (size_t)(TPB / 32) * ctx->model.bsize * sizeof(double2);
+        pl->groups.push_back(g);
+        pl->max_sb = n_sb_max;
+        pl->block_threads = TPB;
+        pl->scratch_per_thread = spt;
+    } else {
     // Chunking.  A CTA owns (entry, 32 samples) and builds that sample block's tables once, so the
     // fewer CTAs share an entry the less set-up work is repeated: by default an entry's
     // configurations are split into exactly W chunks (one per warp, one CTA job).  Only entries
@@ -570,6 +643,7 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         if (g.smem > 227 * 1024) return fail(ctx, QIW_ERR_UNSUPPORTED, "per-sample tables exceed shared memory (too many sectors for the scalar kernel)");
         pl->groups.push_back(g);
     }
+    }
     // grid.x (common to all groups = row pitch of the partials buffer): enough sample-block
     // columns to fill the machine a few times over; the kernel strides over the remaining blocks
     {
@@ -597,7 +671,8 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         dy.entry = ids[i]; dy.out_index = i; dy.item0 = pl->item0[i]; dy.n_items = pl->n_items[i];
     }
     CK(pl->d_items.upload(pl->items.data(), pl->items.size(), ctx->stream));
-    CK(pl->d_partials.reserve(pl->partial_rows * S));
+    CK(pl->d_partials.reserve(pl->partial_rows * ctx->model.bsize));
+    if (pl->block_threads) CK(ctx->dScratch.reserve((size_t)pl->pitch * pl->items.size() * pl->block_threads * pl->scratch_per_thread));
     CK(pl->d_out.reserve((size_t)n_entries * ctx->model.bsize));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->plans.push_back(std::move(pl));
@@ -671,6 +746,22 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         CK(cudaMemsetAsync(ctx->dTrace.p, 0, trace_words * sizeof(unsigned long long), ctx->stream));
         sp.trace = ctx->dTrace.p;
     }
+    if (!m.scalar) {
+        BlockParams bp;
+        bp.m.dim = ctx->dDim.p; bp.m.boff = ctx->dBoff.p; bp.m.eoff = ctx->dEoff.p; bp.m.op_target = ctx->dOpTarget.p;
+        bp.m.op_off = ctx->dOpOff.p; bp.m.pool = ctx->dPool.p; bp.m.S = m.S; bp.m.bsize = m.bsize; bp.m.maxdim = m.maxdim;
+        bp.m.n_ops = m.n_ops;
+        bp.words = ctx->dWordsPtr.p; bp.tree_off = ctx->dTreeOffPtr.p; bp.n_trees = ctx->dNTrees.p;
+        bp.scratch = ctx->dScratch.p; bp.scratch_per_thread = pl.scratch_per_thread;
+        StepParams gp = sp;
+        gp.items = pl.d_items.p;
+        dim3 grid((unsigned)pl.pitch, (unsigned)pl.items.size());
+        {
+            ProfScope ps(ctx, 7);
+            CK(launch_block_step(gp, bp, grid, pl.block_threads, pl.groups[0].smem, ctx->stream));
+        }
+        ctx->launches++;
+    } else
     for (auto& g : pl.groups) {
         StepParams gp = sp;
         gp.items = pl.d_items.p + g.item0;
@@ -698,7 +789,7 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
     if (!pl.explicit_mode) {
         {
             ProfScope ps(ctx, 4);
-            CK(launch_reduce(pl.d_dyn.p, ctx->dEntries.p, pl.d_partials.p, pl.pitch, m.S, t_i, t_w, t_f, pl.d_out.p,
+            CK(launch_reduce(pl.d_dyn.p, ctx->dEntries.p, pl.d_partials.p, pl.pitch, m.bsize, t_i, t_w, t_f, pl.d_out.p,
                              (int)pl.ids.size(), ctx->stream));
         }
         ctx->launches++;
@@ -738,7 +829,6 @@ static int eval_scalar(qiw_context* ctx, double t_i, double t_w, double t_f, int
                        const uint32_t* sobol_m, const uint32_t* sobol_x0, uint64_t start, uint64_t count,
                        uint64_t N_total, bool allreduce, double* out, const double* explicit_times, int n_explicit) {
     const HostModel& m = ctx->model;
-    const int S = m.S;
     const bool explicit_mode = explicit_times != nullptr;
     int rc = sync_static_tables(ctx);
     if (rc) return rc;
@@ -751,8 +841,8 @@ static int eval_scalar(qiw_context* ctx, double t_i, double t_w, double t_f, int
     if (explicit_mode) {
         const int D = ctx->entries[ids[0]]->prog.D;
         CK(ctx->dTimes.upload(explicit_times, (size_t)n_explicit * std::max(D, 1), ctx->stream));
-        CK(ctx->dPerSample.reserve((size_t)n_explicit * S));
-        CK(cudaMemsetAsync(ctx->dPerSample.p, 0, (size_t)n_explicit * S * sizeof(double2), ctx->stream));
+        CK(ctx->dPerSample.reserve((size_t)n_explicit * m.bsize));
+        CK(cudaMemsetAsync(ctx->dPerSample.p, 0, (size_t)n_explicit * m.bsize * sizeof(double2), ctx->stream));
     }
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     rc = enqueue_step(ctx, pl, t_i, t_w, t_f);
@@ -760,7 +850,7 @@ static int eval_scalar(qiw_context* ctx, double t_i, double t_w, double t_f, int
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     rc = mark_ucache_valid(ctx, pl);
     if (rc) return rc;
-    const size_t n_out = explicit_mode ? (size_t)n_explicit * S : (size_t)n_entries * m.bsize;
+    const size_t n_out = explicit_mode ? (size_t)n_explicit * m.bsize : (size_t)n_entries * m.bsize;
     double2* src = explicit_mode ? ctx->dPerSample.p : pl.d_out.p;
     if (allreduce && !explicit_mode) { rc = nccl_allreduce(ctx, src, n_out); if (rc) return rc; }
     rc = ensure_host_out(ctx, n_out);
@@ -784,7 +874,6 @@ static int check_entries(qiw_context* ctx, int n_entries, const int32_t* ids, co
             return fail(ctx, QIW_ERR_BAD_ARG, std::string(who) + ": unknown entry id");
         for (int j = 0; j < i; ++j) if (ids[j] == ids[i]) return fail(ctx, QIW_ERR_BAD_ARG, std::string(who) + ": duplicate entry id");
     }
-    if (!ctx->model.scalar) return fail(ctx, QIW_ERR_UNSUPPORTED, std::string(who) + ": sector blocks larger than 1x1 are not supported by this build yet");
     return QIW_OK;
 }
 

@@ -84,3 +84,27 @@ struct StepParams {
 };
 
 }  // namespace qiw
+
+namespace qiw {
+
+// Model tables for sector blocks larger than 1x1 (block kernel).
+struct DevModel {
+    const int* dim;          // [S]
+    const int* boff;         // [S] offsets into the packed block vector
+    const int* eoff;         // [S] offsets into E
+    const int* op_target;    // [n_ops][S]
+    const long long* op_off; // [n_ops][S] into pool
+    const double2* pool;     // operator blocks, column-major
+    int S, bsize, maxdim, n_ops;
+};
+
+struct BlockParams {
+    DevModel m;
+    const uint64_t* const* words;      // per compiled entry id: tree word stream
+    const uint32_t* const* tree_off;   // per compiled entry id: [n_trees + 1]
+    const int* n_trees;                // per compiled entry id
+    double2* scratch;                  // per thread: propagator blocks, interaction factors
+    size_t scratch_per_thread;         // in double2
+};
+
+}  // namespace qiw

@@ -504,3 +504,197 @@ cudaError_t launch_dfma_peak(double* out, int blocks, int iters, cudaStream_t st
 }
 
 }  // namespace qiw
+
+namespace qiw {
+
+// ---- the step kernel for sector blocks larger than 1x1 --------------------------------------------
+// One THREAD owns one (sample, chunk of configuration trees) and replays the pruned tree of
+// src/topology_eval.jl:454-556 with the reference's own prefix sharing: the running product
+// A_pos ... A_1 (src/utility.jl:234-323) is kept on a per-thread stack, one (d x d_init) matrix per tree
+// level.  Node matrix = operator block times i P_s(t_pos, t_pos-1) (:376-388).  Blocks are at most
+// kMaxBlockDim x kMaxBlockDim.  This path favours generality over speed: all BASELINE headline
+// configurations have 1x1 blocks and use the scalar kernel.
+constexpr int kMaxBlockDim = 4;
+
+__device__ __forceinline__ double2 zero2() { return make_double2(0.0, 0.0); }
+// tree word fields (qiw_host.hpp make_word)
+__device__ __forceinline__ uint32_t w_slotA(uint64_t w) { return (uint32_t)w & 0xFFFu; }
+__device__ __forceinline__ uint32_t w_slotB(uint64_t w) { return ((uint32_t)w >> 12) & 0xFFFu; }
+__device__ __forceinline__ uint32_t w_nchild(uint64_t w) { return ((uint32_t)w >> 24) & 0xFFu; }
+__device__ __forceinline__ uint32_t w_aux(uint64_t w) { return (uint32_t)(w >> 32) & 0xFFFFu; }
+
+__global__ void __launch_bounds__(64) block_step_kernel(const StepParams p, const BlockParams bp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const WorkItem it = p.items[blockIdx.y];
+    const DevEntry& e = p.entries[it.entry];
+    const DevEntryDyn& dy = p.dyn[it.slot];
+    const DevModel& m = bp.m;
+    const int S = m.S, bsize = m.bsize, D = e.D, n_nodes = e.n_nodes, d_after = e.d_after;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* red = reinterpret_cast<double2*>(smem_raw);   // [nw][bsize]
+
+    double t_i = p.t_i, t_w = p.t_w, t_f = p.t_f;
+    const double lo_after = (e.mode == 0) ? t_i : t_w, len_after = t_f - lo_after, len_before = t_w - t_i;
+    const unsigned long long count = dy.count;
+    const int n_sb = (int)((count + blockDim.x - 1) / blockDim.x);
+    const size_t tid_global = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    double2* iP = bp.scratch + tid_global * bp.scratch_per_thread;        // [n_nodes-1][bsize]
+    double2* dl = iP + (size_t)(n_nodes - 1) * bsize;                      // [nD]
+    double2* acc = dl + e.nD;                                              // [bsize]
+    const uint64_t* __restrict__ words = bp.words[it.entry];
+    const uint32_t* __restrict__ toff = bp.tree_off[it.entry];
+    const int n_trees = bp.n_trees[it.entry];
+    const long long c = it.chunk0, nct = it.n_chunks_total;
+    const int tree0 = (int)(c * n_trees / nct), tree1 = (int)((c + 1) * n_trees / nct);
+
+    for (int k = 0; k < bsize; ++k) acc[k] = zero2();
+
+    for (int sb = blockIdx.x; sb < n_sb; sb += gridDim.x) {
+        const unsigned long long local = (unsigned long long)sb * blockDim.x + threadIdx.x;
+        const bool active = local < count;
+        if (!active) continue;
+        // -- times of every backbone position (src/qmc_integrate.jl:225-235,425-449) ---------------
+        double times[kDevMaxNodes + 1];
+        bool ok = true;
+        {
+            double u = 1.0;
+            const uint32_t kk = (uint32_t)(dy.start + local);
+            for (int pos = n_nodes; pos >= 1; --pos) {
+                const int src = e.pos_src[pos];
+                double t;
+                if (src == -1) t = t_i;
+                else if (src == -2) t = t_w;
+                else if (src == -3) t = t_f;
+                else if (p.explicit_times) t = p.explicit_times[local * D + src];
+                else {
+                    const uint32_t xi = sobol_coord(dy.sobol + src * 32, __ldg(dy.sobol + D * 32 + src), kk);
+                    const double x = (double)xi * 2.3283064365386963e-10;
+                    const int den = (src < d_after) ? (d_after - src) : (D - src);
+                    const double r = (den == 1) ? x : pow(x, 1.0 / (double)den);
+                    u = (src == 0 || src == d_after) ? r : __dmul_rn(u, r);
+                    t = (src < d_after) ? __dadd_rn(__dmul_rn(u, len_after), lo_after) : __dadd_rn(__dmul_rn(u, len_before), t_i);
+                    ok = ok && (t >= 0.0);
+                }
+                times[pos] = t;
+            }
+        }
+        if (!ok) continue;   // discarded sample still counts in N (src/qmc_integrate.jl:503)
+        // -- i P_s(t_pos, t_pos-1) for every interval and sector (:357-374) ------------------------------
+        for (int iv = 0; iv < n_nodes - 1; ++iv) {
+            const double ta = times[iv + 1];
+            double tb = times[iv + 2];
+            if (tb < ta) tb = ta;
+            for (int s = 0; s < S; ++s) {
+                const int d = m.dim[s], bo = m.boff[s];
+                for (int el = 0; el < d * d; ++el) {
+                    double2 v;
+                    if (e.mode == 0) {
+                        const int r = el % d, cc = el / d;
+                        v = (r == cc) ? make_double2(exp(-(tb - ta) * __ldg(p.E + m.eoff[s] + r)), 0.0) : zero2();
+                    } else {
+                        v = times_i(grid_interp(p.P + bo + el, bsize, p.n_tau, p.inv_h, tb, ta));
+                    }
+                    iP[(size_t)iv * bsize + bo + el] = v;
+                }
+            }
+        }
+        for (int q = 0; q < e.nD; ++q) {   // i Delta for every used (arc, table)  (:397-416)
+            const int4 ds = __ldg(e.dslots + q);
+            const double th = times[ds.y];
+            double tt = times[ds.x];
+            if (tt < th) tt = th;
+            dl[q] = times_i(delta_eval(p.deltas[ds.z], tt, th));
+        }
+        // -- replay the trees --------------------------------------------------------------------------
+        double2 V[kDevMaxNodes + 1][kMaxBlockDim * kMaxBlockDim];   // V[level]: (dim_cur x d_init), column-major
+        int rem[kDevMaxNodes + 1];
+        for (int t = tree0; t < tree1; ++t) {
+            uint32_t pc = toff[t];
+            const uint64_t root = words[pc++];
+            const int s_init = (int)w_aux(root), d0 = m.dim[s_init];
+            const int rootop = (int)((root >> 48) & 0xFFF) - 1;
+            int depth = 1;
+            if (rootop >= 0) {   // operator node at position 1: bare matrix (:377,540)
+                const int s_next = (int)w_slotA(root), dr = m.dim[s_next];
+                const double2* O = m.pool + m.op_off[(size_t)rootop * S + s_init];
+                for (int k = 0; k < dr * d0; ++k) V[1][k] = O[k];
+            } else {
+                for (int k = 0; k < d0 * d0; ++k) V[1][k] = (k % d0 == k / d0) ? make_double2(1.0, 0.0) : zero2();
+            }
+            rem[1] = (int)w_nchild(root);
+            while (depth >= 1) {
+                if (rem[depth] == 0) { --depth; continue; }
+                --rem[depth];
+                const uint64_t w = words[pc++];
+                const int s = (int)w_slotA(w), ds_ = m.dim[s];
+                const int op = (int)((w >> 48) & 0xFFF) - 1;
+                const int iv = depth - 1;   // the node sits at position depth+1: interval depth-1
+                const double2* Pm = iP + (size_t)iv * bsize + m.boff[s];
+                const double2* Vp = V[depth];
+                double2 tmp[kMaxBlockDim * kMaxBlockDim];
+                for (int j = 0; j < d0; ++j)           // tmp = iP_s * V_parent   (d_s x d0)
+                    for (int i = 0; i < ds_; ++i) {
+                        double2 a = zero2();
+                        for (int k = 0; k < ds_; ++k) a = cfma(Pm[i + ds_ * k], Vp[k + ds_ * j], a);
+                        tmp[i + ds_ * j] = a;
+                    }
+                int dr = ds_;
+                double2* Vc = V[depth + 1];
+                if (op >= 0) {                          // V_child = O * tmp   (d_t x d0)
+                    const int tgt = m.op_target[(size_t)op * S + s];
+                    dr = m.dim[tgt];
+                    const double2* O = m.pool + m.op_off[(size_t)op * S + s];
+                    for (int j = 0; j < d0; ++j)
+                        for (int i = 0; i < dr; ++i) {
+                            double2 a = zero2();
+                            for (int k = 0; k < ds_; ++k) a = cfma(O[i + dr * k], tmp[k + ds_ * j], a);
+                            Vc[i + dr * j] = a;
+                        }
+                } else {
+                    for (int k = 0; k < ds_ * d0; ++k) Vc[k] = tmp[k];
+                }
+                const uint32_t sbq = w_slotB(w);
+                if (sbq) {                              // interaction weight at the arc's tail (:506-507)
+                    const double2 dv = dl[sbq - e.nP];
+                    for (int k = 0; k < dr * d0; ++k) Vc[k] = cmul(Vc[k], dv);
+                }
+                const int nc = (int)w_nchild(w);
+                if (nc == 0) {                          // leaf: top_result[s_init] += weight * product (:465)
+                    const double2 coef = __ldg(e.coefs + w_aux(w));
+                    double2* a = acc + m.boff[s_init];
+                    for (int k = 0; k < d0 * d0; ++k) a[k] = cfma(coef, Vc[k], a[k]);
+                } else {
+                    ++depth;
+                    rem[depth] = nc;
+                }
+            }
+        }
+        if (p.per_sample_out) {
+            for (int k = 0; k < bsize; ++k) { p.per_sample_out[local * bsize + k] = acc[k]; acc[k] = zero2(); }
+        }
+    }
+    if (p.per_sample_out) return;
+    // -- CTA reduction ------------------------------------------------------------------------------------
+    for (int k = 0; k < bsize; ++k) {
+        double2 v = acc[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            v.x += __shfl_down_sync(0xFFFFFFFFu, v.x, off);
+            v.y += __shfl_down_sync(0xFFFFFFFFu, v.y, off);
+        }
+        if (lane == 0) red[warp * bsize + k] = v;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < bsize; k += blockDim.x) {
+        double2 v = zero2();
+        for (int w2 = 0; w2 < nw; ++w2) v = cadd(v, red[w2 * bsize + k]);
+        p.partials[((size_t)it.partial0 * gridDim.x + blockIdx.x) * bsize + k] = v;
+    }
+}
+
+cudaError_t launch_block_step(const StepParams& p, const BlockParams& bp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    block_step_kernel<<<grid, threads, smem, st>>>(p, bp);
+    return cudaGetLastError();
+}
+
+}  // namespace qiw

@@ -92,3 +92,52 @@ def bold_entries(make, orders, n_pts_after_max=None):
         for k in ([0] if o == 0 else range(1, min(2 * o - 1, n_pts_after_max or 10 ** 9) + 1)):
             out.append((o, k))
     return out
+
+
+def two_level_mixed(n_tau=12, beta=2.0, theta=0.0):
+    """Two degenerate levels with inter-level hybridisation: the one-particle sector is a 2x2 block
+    (rotated by `theta` inside the degenerate eigenspace).  Exercises d_s > 1."""
+    f = FockSpace([["a"], ["b"]])
+    H = 0.3 * (f.n_op("a") + f.n_op("b")) + 0.7 * f.n_op("a") @ f.n_op("b")
+    mix = f.c_dag("a") @ f.c("b") + f.c_dag("b") @ f.c("a")
+    ed = EDCore(f, H, symmetry_breakers=[mix])
+    for s, d in enumerate(ed.dims):
+        if d == 2:
+            c, sn = np.cos(theta), np.sin(theta)
+            ed.unitaries[s] = ed.unitaries[s] @ np.array([[c, -sn], [sn, c]])
+    grid = ImaginaryTimeGrid(beta, n_tau)
+    D = delta_dos_gf(grid, 0.4) * 0.3
+    pairs = []
+    for x, y in (("a", "a"), ("b", "b"), ("a", "b"), ("b", "a")):
+        pairs += [InteractionPair(f.c_dag(x), f.c(y), D), InteractionPair(f.c(y), f.c_dag(x), ph_conj(D))]
+    ex = Expansion(ed, grid, pairs)
+    add_corr_operators(ex, (f.c("a"), f.c_dag("a")))
+    return ex, grid, f
+
+
+def two_band(n_tau=16, beta=8.0, U=2.0, J=0.2, e_k=2.3):
+    """bench/two_band_eg_model_discrete_bath: two-band e_g model, 16 Fock states, 9 sectors with
+    dimensions {1,1,1,1,2,2,2,2,4}, 16 interaction pairs, discrete bath."""
+    labels = [[s, o] for s in ("up", "dn") for o in (1, 2)]
+    f = FockSpace(labels)
+    mu = (3 * U - 5 * J) / 2 - 1.5
+    n, c, cd = f.n_op, f.c, f.c_dag
+    H = -mu * sum(n("up", o) + n("dn", o) for o in (1, 2)) + U * sum(n("up", o) @ n("dn", o) for o in (1, 2))
+    H = H + (U - 2 * J) * sum(n("up", o1) @ n("dn", o2) for o1 in (1, 2) for o2 in (1, 2) if o1 != o2)
+    H = H + (U - 3 * J) * sum(n(s, o1) @ n(s, o2) for s in ("up", "dn") for o1 in (1, 2) for o2 in (1, 2) if o2 < o1)
+    H = H - J * sum(cd("up", o1) @ cd("dn", o1) @ c("up", o2) @ c("dn", o2) for o1 in (1, 2) for o2 in (1, 2) if o1 != o2)
+    H = H - J * sum(cd("up", o1) @ cd("dn", o2) @ c("up", o2) @ c("dn", o1) for o1 in (1, 2) for o2 in (1, 2) if o1 != o2)
+    sb = [cd("up", 1) @ c("up", 2) + cd("up", 2) @ c("up", 1), cd("dn", 1) @ c("dn", 2) + cd("dn", 2) @ c("dn", 1)]
+    ed = EDCore(f, H, sb)
+    grid = ImaginaryTimeGrid(beta, n_tau)
+    Delta = delta_dos_gf(grid, [e_k, -e_k], [1.0, 1.0])
+    ips = []
+    for s in ("up", "dn"):
+        for o in (1, 2):
+            ips += [InteractionPair(cd(s, o), c(s, o), Delta), InteractionPair(c(s, o), cd(s, o), ph_conj(Delta))]
+    for s in ("up", "dn"):
+        ips += [InteractionPair(cd(s, 1), c(s, 2), Delta), InteractionPair(c(s, 2), cd(s, 1), ph_conj(Delta)),
+                InteractionPair(cd(s, 2), c(s, 1), Delta), InteractionPair(c(s, 1), cd(s, 2), ph_conj(Delta))]
+    ex = Expansion(ed, grid, ips)
+    add_corr_operators(ex, (c("up", 1), cd("up", 1)))
+    return ex, grid, f

@@ -168,3 +168,63 @@ def test_readme_anderson_run(gpu_ctx, qlib, oracle_lib):
     rho = np.array([d[0, 0].real for d in ppgf.density_matrix(ex)])
     assert np.abs(rho[1] - rho[2]) < 1e-12 and abs(rho.sum() - 1) < 1e-12
     assert np.abs(rho[0] - rho[3]) < 2e-3
+
+
+@pytest.mark.parametrize("name", ["two_level_mixed", "two_band"])
+def test_block_models_vs_oracle(gpu_ctx, qlib, oracle_lib, name):
+    """Sector blocks larger than 1x1 (unpinned at the reference level; the oracle is
+    self-validated by basis-rotation invariance): bold / bare / correlator entries against the oracle,
+    per-sample values through qiw_eval_at_times, and a full device-resident run."""
+    from qinchworm_b200.inchworm import Solver, inchworm
+    if name == "two_level_mixed":
+        ex, grid, f = models.two_level_mixed(n_tau=12, theta=0.6)
+        orders, N = range(0, 4), 2 ** 7
+    else:
+        ex, grid, f = models.two_band(n_tau=10)
+        assert sorted(ex.dims) == [1, 1, 1, 1, 2, 2, 2, 2, 4]
+        orders, N = range(0, 3), 2 ** 6
+    rng = np.random.default_rng(3)
+    ex.P = ex.P * (1.0 + 0.05 * rng.random(ex.P.shape))
+    pl = gpu_ctx.set_expansion(ex)
+    o = oracle_lib.Oracle(pl, ex.P)
+    tau = grid.tau
+    eid = 0
+    for mode, (ki, kw, kf) in ((qlib.MODE_BOLD, (0, 5, 6)), (qlib.MODE_BARE, (0, 0, 1)), (qlib.MODE_CORR, (0, 4, len(tau) - 1))):
+        ids = []
+        for order in orders:
+            ks = [None] if mode == qlib.MODE_BARE else ([0] if order == 0 else range(1, 2 * order))
+            for k in ks:
+                pr, pa = qlib.topologies(order, None if mode == qlib.MODE_BARE else k, mode == qlib.MODE_CORR)
+                if len(pa) == 0:
+                    continue
+                kk = 2 * order if mode == qlib.MODE_BARE else k
+                gpu_ctx.set_topologies(eid, mode, order, kk, pr, pa)
+                o.set_topologies(eid, mode, order, kk, pr, pa)
+                st = gpu_ctx.entry_stats(eid)
+                ids.append(eid)
+                eid += 1
+        got = gpu_ctx.eval(tau[ki], tau[kw], tau[kf], ids, N)
+        ref = o.eval(tau[ki], tau[kw], tau[kf], ids, N)
+        assert relerr(got, ref) < RTOL, (mode, relerr(got, ref))
+        got = gpu_ctx.eval_range(tau[ki], tau[kw], tau[kf], ids, N, 5, 33)
+        ref = o.eval(tau[ki], tau[kw], tau[kf], ids, N, start=5, count=33)
+        assert relerr(got, ref) < RTOL, ("range", mode, relerr(got, ref))
+    # per-sample evaluator values for one order-2 bold entry
+    pr, pa = qlib.topologies(2, 2)
+    gpu_ctx.set_topologies(eid, qlib.MODE_BOLD, 2, 2, pr, pa)
+    o.set_topologies(eid, qlib.MODE_BOLD, 2, 2, pr, pa)
+    times = np.zeros((7, 4))
+    for i in range(7):
+        times[i, :2] = np.sort(rng.uniform(tau[5], tau[6], 2))[::-1]
+        times[i, 2:] = np.sort(rng.uniform(0, tau[5], 2))[::-1]
+    got = gpu_ctx.eval_at_times(eid, 0.0, tau[5], tau[6], times)
+    ref = o.eval_at_times(eid, 0.0, tau[5], tau[6], times)
+    assert relerr(got, ref) < RTOL
+    fl, lv = o.last_counts()
+    st = gpu_ctx.entry_stats(eid)
+    assert st["n_leaves"] == lv and st["flops_per_sample"] == fl
+    # full run on the device vs the oracle's driver
+    ex2 = models.two_level_mixed(n_tau=12, theta=0.6)[0] if name == "two_level_mixed" else models.two_band(n_tau=10)[0]
+    refP = oracle_lib.inchworm(ex2.flatten(), ex2.P, range(0, 3), range(0, 3), 2 ** 5)["P"]
+    inchworm(ex2, ex2.grid, range(0, 3), range(0, 3), 2 ** 5, solver=Solver(ex2, ctx=gpu_ctx), device_resident=True)
+    assert relerr(ex2.P, refP) < RTOL
