@@ -231,13 +231,14 @@ def main():
     device_run()
     prof = ctx.profile_read(reset=True)
     ctx.profile_enable(False)
-    dom = prof.get("step_order_le4", {"ms": float("nan"), "launches": 1})
+    dom_name = "step_real" if "step_real" in prof else "step_complex"
+    dom = prof.get(dom_name, {"ms": float("nan"), "launches": 1})
     n_count = mpi.split_count(N, world)[rank]
     dom_ms = dom["ms"] / max(dom["launches"], 1)
     dom_flops = flops_bold_sample * n_count                       # algorithmic chain FLOPs of one launch
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12
     total_prof = sum(v["ms"] for v in prof.values())
-    roofline = {"bound": "fp64_fma", "kernel": "scalar_step_kernel<14> (all bold entries, orders 0-4)", "achieved": achieved,
+    roofline = {"bound": "fp64_fma", "kernel": "scalar_step_kernel<%s> (all bold entries, orders 0-4)" % ("real" if dom_name == "step_real" else "complex"), "achieved": achieved,
                 "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 "peak_source": "measured in this process by qiw_measure_fp64_peak (DFMA-saturating kernel); "
                                "MEASURED_PEAKS.json has no FP64 entry",

@@ -144,6 +144,13 @@ int qiw_entry_program(qiw_context* ctx, int32_t entry_id, int64_t* n_words, uint
                       int64_t* n_trees, uint32_t* tree_off, int64_t* n_coefs, double* coefs,
                       int64_t* n_dslots, int32_t* dslots, int32_t* pos_src, int32_t* info);
 
+/* Factorised configuration records of a compiled entry of a 1x1-block model — what the step kernel
+ * executes (layout: csrc/qiw_host.hpp EntryProgram::rec2).  Call with NULL arrays to get the sizes.
+ *   info[8]  : K (segments), L2 (= K + order operands per configuration), n_leaves, nSeg,
+ *              seg_stride, nP, nD, 0
+ *   rec2[n_leaves][L2 + 1], segdef[nSeg][seg_stride] */
+int qiw_entry_records(qiw_context* ctx, int32_t entry_id, int32_t* info, uint32_t* rec2, uint16_t* segdef);
+
 /* ---- the hot path ---------------------------------------------------------------------------- */
 
 /* Evaluate `n_entries` entries at the fixed times (t_i, t_w, t_f) with N_total Sobol points each.
@@ -187,8 +194,8 @@ int qiw_last_device_ms(qiw_context* ctx, double* ms);
 int qiw_launch_count(qiw_context* ctx, int64_t* n);
 
 /* Per-kernel device timing (CUDA events on the launching stream around every launch).  Classes:
- * 0..3 step kernel for expansion orders <= 2 / 4 / 6 / 8, 4 reduction, 5 per-step state update,
- * 6 NCCL all-reduce.  Profiling serialises nothing but adds two event records per launch; keep it
+ * 0 step kernel in complex arithmetic, 1 step kernel in real arithmetic (1x1-block models), 4 reduction,
+ * 5 per-step state update, 6 NCCL all-reduce, 7 step kernel for sector blocks larger than 1x1.  Profiling serialises nothing but adds two event records per launch; keep it
  * off for timed runs.  qiw_profile_read synchronises, returns accumulated ms and launch counts per
  * class (arrays of QIW_PROFILE_CLASSES) and optionally resets them. */
 #define QIW_PROFILE_CLASSES 8

@@ -17,7 +17,7 @@
 #include "qiw_host.hpp"
 
 namespace qiw {
-cudaError_t launch_scalar_step(int maxl, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_scalar_step(bool real_mode, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st);
 cudaError_t launch_reduce(const DevEntryDyn* dyn, const DevEntry* entries, const double2* partials, int pitch, int S,
                           double t_i, double t_w, double t_f, double2* out, int n_entries, cudaStream_t st);
 cudaError_t launch_finish_step(double2* P, int n_tau, int bsize, const int* diag, int n_diag, double h, int k_f,
@@ -88,6 +88,8 @@ struct EntryDev {
     EntryProgram prog;
     bool valid = false;
     DevBuf<uint32_t> records;
+    DevBuf<uint16_t> segdef;
+    bool imag_coefs = false;     // every folded coefficient is purely imaginary (real-mode precondition)
     DevBuf<uint64_t> words;      // block models: tree word stream
     DevBuf<uint32_t> tree_off;
     DevBuf<double2> coefs;
@@ -100,7 +102,10 @@ struct Plan {   // launch plan of one qiw_eval call shape, cached
     std::vector<int> ids;
     uint64_t count = 0;
     bool explicit_mode = false;
-    struct Group { int maxl; int item0, n_items; size_t smem; int max_slots; int max_dslots; };
+    struct Group {
+        int maxl; int item0, n_items; int max_slots; int max_dslots; int max_coefs; int max_segdef;
+        size_t smem[2]; int spb[2];   // [0] complex arithmetic, [1] real arithmetic
+    };
     std::vector<Group> groups;
     std::vector<WorkItem> items;
     std::vector<int> item0, n_items;       // per call entry
@@ -138,7 +143,9 @@ struct qiw_context {
     std::vector<cplx> hostP;
     DevBuf<double2> dP;
     DevBuf<double> dE;
-    struct Table { int kind = 0, n = 0; double beta = 0; DevBuf<double2> y, M; };
+    struct Table { int kind = 0, n = 0; double beta = 0; bool imag_only = false; DevBuf<double2> y, M; };
+    std::vector<uint8_t> p_row_complex;   // per grid point: the stored P row has a non-zero real part
+    int last_real_mode = 0;
     std::vector<Table> tables;
     DevBuf<DevDelta> dDeltas;
     std::vector<DevDelta> hDeltas;
@@ -255,7 +262,7 @@ int qiw_destroy(qiw_context* ctx) {
     ctx->dPool.release(); ctx->dScratch.release(); ctx->dWordsPtr.release(); ctx->dTreeOffPtr.release(); ctx->dNTrees.release();
     for (auto& t : ctx->tables) { t.y.release(); t.M.release(); }
     for (auto& e : ctx->entries)
-        if (e) { e->records.release(); e->words.release(); e->tree_off.release(); e->coefs.release(); e->dslots.release(); e->sobol.release(); }
+        if (e) { e->records.release(); e->segdef.release(); e->words.release(); e->tree_off.release(); e->coefs.release(); e->dslots.release(); e->sobol.release(); }
     for (auto& pl : ctx->plans) release_plan(*pl);
     ctx->plans.clear();
     if (ctx->hOut) cudaFreeHost(ctx->hOut);
@@ -339,6 +346,7 @@ int qiw_set_grid(qiw_context* ctx, int32_t n_tau, double beta) {
     cudaSetDevice(ctx->device);
     ctx->n_tau = n_tau; ctx->beta = beta;
     ctx->hostP.assign((size_t)n_tau * ctx->model.bsize, cplx(0));
+    ctx->p_row_complex.assign(n_tau, 0);
     CK(ctx->dP.reserve((size_t)n_tau * ctx->model.bsize));
     CK(cudaMemsetAsync(ctx->dP.p, 0, (size_t)n_tau * ctx->model.bsize * sizeof(double2), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -356,6 +364,8 @@ int qiw_set_delta(qiw_context* ctx, int32_t id, int32_t kind, int32_t n, double 
     std::vector<cplx> y(n), M(n);
     for (int k = 0; k < n; ++k) y[k] = cplx(values[2 * k], values[2 * k + 1]);
     natural_spline_second_derivatives(n, beta / (n - 1), y.data(), M.data());
+    t.imag_only = true;
+    for (int k = 0; k < n; ++k) if (y[k].real() != 0.0 || M[k].real() != 0.0) t.imag_only = false;
     CK(t.y.upload((const double2*)y.data(), n, ctx->stream));
     CK(t.M.upload((const double2*)M.data(), n, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -369,6 +379,11 @@ int qiw_set_P(qiw_context* ctx, int32_t first, int32_t count, const double* rows
     if (ctx->no_device) return fail(ctx, QIW_ERR_CUDA, "planning-only context has no device tables");
     cudaSetDevice(ctx->device);
     const size_t bs = ctx->model.bsize;
+    for (int k = 0; k < count; ++k) {
+        uint8_t c = 0;
+        for (size_t el = 0; el < bs; ++el) if (rows[2 * ((size_t)k * bs + el)] != 0.0) { c = 1; break; }
+        ctx->p_row_complex[first + k] = c;
+    }
     CK(cudaMemcpyAsync(ctx->dP.p + (size_t)first * bs, rows, (size_t)count * bs * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return QIW_OK;
@@ -401,7 +416,7 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
     if (ctx->no_device) { ed.valid = true; return QIW_OK; }
     if (ctx->model.scalar) {   // configuration records, transposed into groups of 32 so that lane l of a warp reads record
         // 32 g + l with coalesced loads; the last group is padded with null records (zero coefficient)
-        const int L = pr.L, RL = pr.RL;
+        const int L = pr.L2, RL = pr.L2 + 1;
         const int64_t nl = pr.n_leaves, ng = (nl + 31) / 32;
         std::vector<uint32_t> rec((size_t)std::max<int64_t>(ng, 1) * (L + 1) * 32, 0u);
         for (int64_t g = 0; g < ng; ++g)
@@ -409,22 +424,26 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
                 const int64_t leaf = g * 32 + lane;
                 uint32_t* dst = rec.data() + (size_t)g * (L + 1) * 32 + lane;
                 if (leaf < nl) {
-                    const uint32_t* src = pr.records.data() + (size_t)leaf * RL;
-                    dst[0] = src[0];
-                    for (int q = 1; q <= L; ++q) dst[(size_t)q * 32] = src[q] * 16u;
+                    const uint32_t* src = pr.rec2.data() + (size_t)leaf * RL;
+                    for (int q = 0; q <= L; ++q) dst[(size_t)q * 32] = src[q];
                 } else {
-                    const uint32_t s_last = nl ? (pr.records[(size_t)(nl - 1) * RL] >> 16) : 0u;
+                    const uint32_t s_last = nl ? (pr.rec2[(size_t)(nl - 1) * RL] >> 16) : 0u;
                     dst[0] = (uint32_t)pr.coefs.size() | (s_last << 16);   // index of the appended zero coefficient
                 }
             }
         CK(ed.records.upload(rec.data(), rec.size(), ctx->stream));
+        CK(ed.segdef.upload(pr.segdef.data(), pr.segdef.size(), ctx->stream));
     }
     if (!ctx->model.scalar) {
         CK(ed.words.upload(pr.words.data(), pr.words.size(), ctx->stream));
         CK(ed.tree_off.upload(pr.tree_off.data(), pr.tree_off.size(), ctx->stream));
     }
     std::vector<double2> cf(std::max<size_t>(pr.coefs.size(), 1));
-    for (size_t k = 0; k < pr.coefs.size(); ++k) cf[k] = make_double2(pr.coefs[k].real(), pr.coefs[k].imag());
+    ed.imag_coefs = true;
+    for (size_t k = 0; k < pr.coefs.size(); ++k) {
+        cf[k] = make_double2(pr.coefs[k].real(), pr.coefs[k].imag());
+        if (pr.coefs[k].real() != 0.0) ed.imag_coefs = false;
+    }
     CK(ed.coefs.upload(cf.data(), cf.size(), ctx->stream));
     std::vector<int4> ds(std::max<size_t>(pr.dslots.size(), 1));
     for (size_t k = 0; k < pr.dslots.size(); ++k) ds[k] = make_int4(pr.dslots[k].pos_tail, pr.dslots[k].pos_head, pr.dslots[k].table, 0);
@@ -469,6 +488,20 @@ int qiw_entry_program(qiw_context* ctx, int32_t id, int64_t* n_words, uint64_t* 
     return QIW_OK;
 }
 
+int qiw_entry_records(qiw_context* ctx, int32_t id, int32_t* info, uint32_t* rec2, uint16_t* segdef) {
+    if (!ctx || id < 0 || id >= (int)ctx->entries.size() || !ctx->entries[id] || !ctx->entries[id]->valid)
+        return fail(ctx, QIW_ERR_BAD_ARG, "qiw_entry_records: unknown entry");
+    const EntryProgram& p = ctx->entries[id]->prog;
+    if (!p.scalar) return fail(ctx, QIW_ERR_UNSUPPORTED, "qiw_entry_records: only 1x1-block models have configuration records");
+    if (info) {
+        info[0] = p.K; info[1] = p.L2; info[2] = (int32_t)p.n_leaves; info[3] = p.nSeg; info[4] = p.seg_stride;
+        info[5] = p.nP; info[6] = (int32_t)p.dslots.size(); info[7] = 0;
+    }
+    if (rec2) memcpy(rec2, p.rec2.data(), p.rec2.size() * sizeof(uint32_t));
+    if (segdef) memcpy(segdef, p.segdef.data(), (size_t)p.nSeg * p.seg_stride * sizeof(uint16_t));
+    return QIW_OK;
+}
+
 }  // extern "C"
 
 // ---- launch planning ---------------------------------------------------------------------------
@@ -500,7 +533,8 @@ static int sync_static_tables(qiw_context* ctx) {
             d.d_after = (p.mode == 0) ? p.D : p.n_pts_after;
             d.d_before = p.D - d.d_after;
             d.nP = p.nP; d.nD = (int)p.dslots.size();
-            d.L = p.L; d.n_leaves = (int)p.n_leaves; d.n_groups = (int)((p.n_leaves + 31) / 32); d.n_coefs = (int)p.coefs.size();
+            d.L2 = p.L2; d.n_leaves = (int)p.n_leaves; d.n_groups = (int)((p.n_leaves + 31) / 32); d.n_coefs = (int)p.coefs.size();
+            d.nSeg = p.nSeg; d.seg_stride = p.seg_stride; d.segdef = ed.segdef.p;
             d.exact = (p.order == 0);
             for (int k = 0; k <= kDevMaxNodes; ++k) d.pos_src[k] = p.pos_src[k];
             d.records = ed.records.p; d.coefs = ed.coefs.p; d.dslots = ed.dslots.p;
@@ -528,6 +562,18 @@ static int sync_static_tables(qiw_context* ctx) {
 static void release_plan(Plan& pl) {
     pl.d_items.release(); pl.d_sobol.release(); pl.d_ucache.release();
     pl.d_dyn.release(); pl.d_partials.release(); pl.d_out.release();
+}
+
+// Real arithmetic is exact when every operand is (real number) * i: the stored P rows and Delta tables
+// purely imaginary, the folded coefficients purely imaginary.  QIW_FORCE_COMPLEX=1
+// disables it (tests compare the two modes).
+static bool real_mode_possible(qiw_context* ctx, int n_entries, const int32_t* ids) {
+    if (!ctx->model.scalar) return false;
+    if (const char* env = getenv("QIW_FORCE_COMPLEX")) if (env[0] == '1') return false;
+    for (auto& t : ctx->tables) if (t.n > 0 && !t.imag_only) return false;
+    for (uint8_t c : ctx->p_row_complex) if (c) return false;
+    for (int i = 0; i < n_entries; ++i) if (!ctx->entries[ids[i]]->imag_coefs) return false;
+    return true;
 }
 
 // Splits every entry's trees into chunks of similar cost and groups chunks into CTA jobs.
@@ -574,7 +620,8 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
             spt = std::max(spt, (size_t)(p.n_nodes - 1) * ctx->model.bsize + p.dslots.size() + ctx->model.bsize);
         }
         g.n_items = (int)pl->items.size();
-        g.smem = (size_t)(TPB / 32) * ctx->model.bsize * sizeof(double2);
+        g.smem[0] = g.smem[1] = (size_t)(TPB / 32) * ctx->model.bsize * sizeof(double2);
+        g.spb[0] = g.spb[1] = TPB;
         pl->groups.push_back(g);
         pl->max_sb = n_sb_max;
         pl->block_threads = TPB;
@@ -588,13 +635,40 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
     // lowered to expose more CTAs.
     double max_groups = 1;
     uint64_t n_sb_all = 1;
-    int max_coefs = 1;
+    Plan::Group g;
+    g.maxl = 1; g.item0 = 0; g.max_slots = 1; g.max_dslots = 1; g.max_coefs = 1; g.max_segdef = 1;
+    for (int i = 0; i < n_entries; ++i) {
+        const EntryProgram& p = ctx->entries[ids[i]]->prog;
+        max_groups = std::max(max_groups, (double)((p.n_leaves + 31) / 32));
+        g.maxl = std::max(g.maxl, p.L2);
+        g.max_coefs = std::max(g.max_coefs, (int)p.coefs.size());
+        g.max_slots = std::max(g.max_slots, (p.nP + (int)p.dslots.size() + p.nSeg) | 1);
+        g.max_dslots = std::max(g.max_dslots, (int)p.dslots.size());
+        g.max_segdef = std::max(g.max_segdef, p.nSeg * p.seg_stride);
+    }
+    // samples per CTA pass and shared memory, for complex (16-byte operands) and real (8-byte) arithmetic:
+    // the largest power of two <= 32 whose tables leave room for two CTAs per SM, else whatever fits
+    for (int real = 0; real < 2; ++real) {
+        const size_t opsz = real ? sizeof(double) : sizeof(double2);
+        auto smem_of = [&](int spb) {
+            size_t b = (size_t)g.max_slots * spb * opsz;
+            b = (b + 15) & ~(size_t)15;
+            return b + (size_t)S * W * sizeof(double2) + (size_t)(kDevMaxNodes + 1) * 32 * sizeof(double) +
+                   (size_t)kDevMaxDim * 32 * sizeof(double) + 32 * sizeof(int) + (size_t)g.max_dslots * sizeof(int4) +
+                   (size_t)(g.max_coefs + 1) * opsz + (size_t)g.max_segdef * sizeof(uint16_t) + 16;
+        };
+        int spb = 32;
+        while (spb > 1 && smem_of(spb) > (size_t)110 * 1024) spb >>= 1;
+        if (spb < 16) { spb = 32; while (spb > 1 && smem_of(spb) > (size_t)227 * 1024) spb >>= 1; }
+        if (smem_of(spb) > (size_t)227 * 1024) return fail(ctx, QIW_ERR_UNSUPPORTED, "per-sample tables exceed shared memory (too many sectors for the scalar kernel)");
+        g.spb[real] = explicit_mode ? std::min(spb, 32) : spb;
+        g.smem[real] = smem_of(g.spb[real]);
+    }
+    const int spb_plan = g.spb[real_mode_possible(ctx, n_entries, ids) ? 1 : 0];
     for (int i = 0; i < n_entries; ++i) {
         const EntryProgram& p = ctx->entries[ids[i]]->prog;
         const uint64_t c = p.order == 0 ? 1 : count;
-        max_groups = std::max(max_groups, (double)((p.n_leaves + 31) / 32));
-        n_sb_all = std::max<uint64_t>(n_sb_all, (c + 31) / 32);
-        max_coefs = std::max(max_coefs, (int)p.coefs.size());
+        n_sb_all = std::max<uint64_t>(n_sb_all, (c + spb_plan - 1) / spb_plan);
     }
     double chunk_cap = 16.0;   // groups of 32 configurations per warp and sample block
     {
@@ -609,15 +683,13 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
     for (int i = 0; i < n_entries; ++i) order_idx[i] = i;
     std::stable_sort(order_idx.begin(), order_idx.end(), [&](int a2, int b2) {
         const EntryProgram &pa = ctx->entries[ids[a2]]->prog, &pb2 = ctx->entries[ids[b2]]->prog;
-        return (double)pa.n_leaves * pa.L > (double)pb2.n_leaves * pb2.L; });
+        return (double)pa.n_leaves * pa.L2 > (double)pb2.n_leaves * pb2.L2; });
     {
-        Plan::Group g;
-        g.maxl = 1; g.item0 = 0; g.max_slots = 1; g.max_dslots = 1;
+        const int spb_min = std::min(g.spb[0], g.spb[1]);
         for (int i : order_idx) {
             const EntryProgram& p = ctx->entries[ids[i]]->prog;
-            g.maxl = std::max(g.maxl, p.L);
             const uint64_t c = p.order == 0 ? 1 : count;
-            pl->max_sb = std::max<uint64_t>(pl->max_sb, (c + 31) / 32);
+            pl->max_sb = std::max<uint64_t>(pl->max_sb, (c + spb_min - 1) / spb_min);
             const int64_t ng = (p.n_leaves + 31) / 32;
             int n_chunks = 1;
             if (!explicit_mode && ng > 0) {
@@ -633,14 +705,8 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
                 pl->items.push_back(it);
             }
             pl->n_items[i] = (int)pl->items.size() - pl->item0[i];
-            g.max_slots = std::max(g.max_slots, (p.nP + (int)p.dslots.size()) | 1);
-            g.max_dslots = std::max(g.max_dslots, (int)p.dslots.size());
         }
         g.n_items = (int)pl->items.size() - g.item0;
-        g.smem = (size_t)g.max_slots * 32 * sizeof(double2) + (size_t)S * W * sizeof(double2) +
-                 (size_t)(kDevMaxNodes + 1) * 32 * sizeof(double) + (size_t)kDevMaxDim * 32 * sizeof(double) + 32 * sizeof(int) +
-                 (size_t)(max_coefs + 1) * sizeof(double2) + (size_t)g.max_dslots * sizeof(int4);
-        if (g.smem > 227 * 1024) return fail(ctx, QIW_ERR_UNSUPPORTED, "per-sample tables exceed shared memory (too many sectors for the scalar kernel)");
         pl->groups.push_back(g);
     }
     }
@@ -758,19 +824,24 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         dim3 grid((unsigned)pl.pitch, (unsigned)pl.items.size());
         {
             ProfScope ps(ctx, 7);
-            CK(launch_block_step(gp, bp, grid, pl.block_threads, pl.groups[0].smem, ctx->stream));
+            CK(launch_block_step(gp, bp, grid, pl.block_threads, pl.groups[0].smem[0], ctx->stream));
         }
         ctx->launches++;
     } else
     for (auto& g : pl.groups) {
         StepParams gp = sp;
         gp.items = pl.d_items.p + g.item0;
+        const int real = real_mode_possible(ctx, (int)pl.ids.size(), pl.ids.data()) ? 1 : 0;
+        ctx->last_real_mode = real;
         gp.max_slots = g.max_slots;
         gp.max_dslots = g.max_dslots;
+        gp.max_coefs = g.max_coefs;
+        gp.max_segdef = g.max_segdef;
+        gp.spb = g.spb[real];
         dim3 grid((unsigned)pl.pitch, (unsigned)g.n_items);
         {
-            ProfScope ps(ctx, g.maxl <= 8 ? 0 : g.maxl <= 14 ? 1 : g.maxl <= 20 ? 2 : 3);
-            CK(launch_scalar_step(g.maxl, gp, grid, ctx->warps * 32, g.smem, ctx->stream));
+            ProfScope ps(ctx, real ? 1 : 0);
+            CK(launch_scalar_step(real != 0, gp, grid, ctx->warps * 32, g.smem[real], ctx->stream));
         }
         ctx->launches++;
     }

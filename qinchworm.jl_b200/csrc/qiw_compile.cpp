@@ -8,7 +8,9 @@
 // tree is emitted as a flat pre-order word stream that every sample (= one GPU lane) replays in
 // lock step.  Node order inside a tree is the reference's own DFS order.
 #include <algorithm>
+#include <cstdlib>
 #include <map>
+#include <tuple>
 
 #include "qiw_host.hpp"
 
@@ -243,7 +245,76 @@ int compile_entry(const HostModel& m, int mode, int order, int n_pts_after, int 
     e.words.push_back(0);
     e.n_leaves = b.leaves; e.n_edges = b.edges; e.flops_per_sample = b.flops;
     if (e.nP + (int)e.dslots.size() > 4095 || e.coefs.size() > 65535) { err = "program table overflow"; return 5; }
+    if (e.scalar) {
+        int K = 0;
+        if (const char* env = getenv("QIW_SEGMENTS")) K = atoi(env);
+        factorise_records(e, m.S, K);
+        if (e.nP + (int)e.dslots.size() + e.nSeg > 65535) { err = "segment table overflow"; return 5; }
+    }
     return 0;
+}
+
+// Groups the propagator factors of every configuration into K segments of consecutive backbone
+// intervals and tabulates the distinct sector sub-sequences per segment.  For 1x1 blocks all factors
+// commute, so  weight = coef * prod_segments[prod_{iv in seg} iP(iv, s_iv)] * prod_arcs[i Delta]:
+// the segment products are shared by all configurations that run through the same sectors on that
+// stretch of the backbone (and they are many: the sector sequence is fixed by the operator sequence,
+// whereas configurations also differ by which vertices the arcs connect).
+void factorise_records(EntryProgram& e, int S, int K_req) {
+    const int nI = e.n_nodes - 1, n = e.order, nP = e.nP, nD = (int)e.dslots.size();
+    const int64_t nl = e.n_leaves;
+    // candidate segmentations: K equal parts; keep the cheapest in shared-memory operand loads
+    //   cost(K) = leaves * (K + n)  +  sum over segments (entries * segment length)
+    int bestK = 1;
+    double best_cost = 1e300;
+    std::vector<uint32_t> best_rec;
+    std::vector<uint16_t> best_def;
+    int best_nseg = 0, best_stride = 0;
+    const int Kmax = std::min(nI, 4);
+    for (int K = (K_req > 0 ? std::min(K_req, nI) : 1); K <= (K_req > 0 ? std::min(K_req, nI) : Kmax); ++K) {
+        std::vector<int> bound(K + 1);
+        for (int g = 0; g <= K; ++g) bound[g] = (int)((int64_t)g * nI / K);
+        int stride = 0;
+        for (int g = 0; g < K; ++g) stride = std::max(stride, bound[g + 1] - bound[g]);
+        std::vector<std::map<std::vector<uint16_t>, int>> index(K);
+        std::vector<uint16_t> def;
+        std::vector<uint32_t> rec((size_t)nl * (K + n + 1));
+        int nseg = 0;
+        double seg_cost = 0;
+        for (int64_t l = 0; l < nl; ++l) {
+            const uint32_t* src = e.records.data() + (size_t)l * e.RL;
+            uint32_t* dst = rec.data() + (size_t)l * (K + n + 1);
+            dst[0] = src[0];
+            // split the flat factor list into propagator slots (in interval order) and interaction slots
+            uint16_t ps[64];
+            int np = 0, nd = 0;
+            for (int q = 1; q <= e.L; ++q) {
+                if ((int)src[q] < nP) ps[np++] = (uint16_t)src[q];
+                else dst[1 + K + nd++] = src[q];
+            }
+            for (int g = 0; g < K; ++g) {
+                std::vector<uint16_t> key(ps + bound[g], ps + bound[g + 1]);
+                auto it = index[g].find(key);
+                int id;
+                if (it == index[g].end()) {
+                    id = nseg++;
+                    index[g][key] = id;
+                    for (int i = 0; i < stride; ++i) def.push_back(i < (int)key.size() ? key[i] : (uint16_t)0xFFFF);
+                    seg_cost += (double)key.size();
+                } else id = it->second;
+                dst[1 + g] = (uint32_t)(nP + nD + id);
+            }
+        }
+        // slots per sample row bound the CTA's shared memory: penalise tables beyond ~4 KB of doubles
+        const double row = nP + nD + nseg;
+        double cost = (double)nl * (K + n) + seg_cost + (row > 512 ? 1e6 * (row - 512) : 0.0);
+        if (cost < best_cost) {
+            best_cost = cost; bestK = K; best_rec.swap(rec); best_def.swap(def); best_nseg = nseg; best_stride = stride;
+        }
+    }
+    e.K = bestK; e.L2 = bestK + n; e.nSeg = best_nseg; e.seg_stride = std::max(best_stride, 1);
+    e.rec2.swap(best_rec); e.segdef.swap(best_def);
+    if (e.segdef.empty()) e.segdef.assign(1, 0xFFFF);
 }
 
 }  // namespace qiw

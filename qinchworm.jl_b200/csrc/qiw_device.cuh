@@ -8,7 +8,7 @@
 namespace qiw {
 
 constexpr int kDevMaxNodes = 19;
-constexpr int kDevMaxDim = 24;      // Sobol dimensions handled per entry (2 * order <= 16)
+constexpr int kDevMaxDim = 16;      // Sobol dimensions handled per entry (2 * order <= 16)
 constexpr int kMaxTables = 64;
 constexpr int kInlineTables = 8;     // propagator tables described directly in the kernel parameters
 
@@ -29,9 +29,11 @@ struct DevEntry {
     int exact;                  // order 0: one deterministic evaluation
     int pos_src[kDevMaxNodes + 1];
     int n_coefs;
-    int L, n_leaves, n_groups;  // record length (factors per configuration), records, groups of 32
-    const uint32_t* records;    // transposed: [n_groups][L + 1][32 lanes]; word 0 = coef | s_i << 16,
-                                // words 1..L = byte offset (slot * 16) inside a sample's table row
+    int L2, n_leaves, n_groups; // operands per configuration (K segments + order), records, groups of 32
+    int nSeg, seg_stride;       // segment-product table: entries, propagator slots per entry
+    const uint32_t* records;    // transposed: [n_groups][L2 + 1][32 lanes]; word 0 = coef | s_i << 16,
+                                // words 1..L2 = operand slot inside a sample's table row
+    const uint16_t* segdef;     // [nSeg][seg_stride] propagator slots of each segment product (0xFFFF = none)
     const double2* coefs;
     const int4* dslots;         // (pos_tail, pos_head, table, 0)
 };
@@ -74,7 +76,9 @@ struct StepParams {
     // times; when `times_dev` is non-null the triple is read from device memory (run-level API)
     double t_i, t_w, t_f;
     const double* times_dev;
-    int max_slots;                 // shared-memory table rows reserved per CTA
+    int max_slots;                 // operands per sample row reserved in shared memory
+    int max_coefs, max_segdef;     // shared-memory staging sizes (largest entry of the launch)
+    int spb;                       // samples per CTA pass (<= 32)
     // explicit-times mode (qiw_eval_at_times): times[count][D], per-sample output, no reduction
     const double* explicit_times;
     double2* per_sample_out;       // [count][S]

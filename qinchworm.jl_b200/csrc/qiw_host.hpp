@@ -67,6 +67,17 @@ struct EntryProgram {
     // with zeros to RL words (RL % 4 == 0).  L = (n_nodes - 1) propagators + `order` interactions.
     std::vector<uint32_t> records;
     int L = 0, RL = 0;
+    // Factorised records (scalar models; what the step kernel executes).  The (n_nodes - 1)
+    // propagator factors of a configuration are grouped into K contiguous segments of backbone
+    // intervals; every distinct sector sub-sequence of a segment becomes one entry of a per-sample
+    // table of segment products, so a configuration needs only K + order operands:
+    //   rec2[0] = coefficient index | initial sector << 16
+    //   rec2[1..K]       = slot of the segment product  (nP + nD + entry index)
+    //   rec2[K+1..K+order] = slot of the pair-interaction factor (nP + dslot index)
+    // segdef[nSeg][seg_stride]: propagator slots multiplied into each segment product (0xFFFF = unused).
+    std::vector<uint32_t> rec2;
+    std::vector<uint16_t> segdef;
+    int K = 0, L2 = 0, nSeg = 0, seg_stride = 0;
     // statistics
     int64_t n_top = 0, n_leaves = 0, n_edges = 0;
     double flops_per_sample = 0;
@@ -75,6 +86,8 @@ struct EntryProgram {
 // Compile one TopologiesInputData against the model.  Returns 0 or a qiw_status.
 int compile_entry(const HostModel& m, int mode, int order, int n_pts_after, int corr_idx, int n_top,
                   const int32_t* pairs, const int32_t* parity, EntryProgram& out, std::string& err);
+// Regroup the flat leaf records into factorised records with `K` segments (0 = choose).
+void factorise_records(EntryProgram& e, int S, int K);
 
 // Host Sobol / topology helpers (qiw_seq.cpp)
 int sobol_direction_numbers(int D, uint32_t* m);

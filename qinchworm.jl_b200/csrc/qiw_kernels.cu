@@ -105,51 +105,121 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
+// ---- arithmetic modes ----------------------------------------------------------------------------
+// On the imaginary-time branch every factor of a configuration's weight is i*P or i*Delta with P and
+// Delta purely imaginary, and the folded coefficient (operator matrix elements times -i * parity *
+// (-1)^order) is purely imaginary: the whole product is (real number) * i, exactly.  When the host has
+// verified that for the tables and coefficients in use (DESIGN.md §3 "real mode") the kernel runs in
+// real arithmetic — bit-identical results, one FP64 multiply and one 8-byte shared-memory operand per
+// factor instead of four and 16 bytes.  Anything else runs the same code in complex arithmetic.
+template <bool REAL> struct Num;
+template <> struct Num<true> {
+    typedef double T;
+    static __device__ __forceinline__ T zero() { return 0.0; }
+    static __device__ __forceinline__ T mul(T a, T b) { return a * b; }
+    static __device__ __forceinline__ T add(T a, T b) { return a + b; }
+    static __device__ __forceinline__ T from_real(double x) { return x; }
+    static __device__ __forceinline__ T times_i_of(double2 v) { return -v.y; }          // Re(i v), Im(i v) = v.x = 0
+    static __device__ __forceinline__ T coef_of(double2 c) { return c.y; }               // coef = i * c.y
+    static __device__ __forceinline__ double2 result(T coef, T acc) { return make_double2(0.0, coef * acc); }
+    static __device__ __forceinline__ T shfl_down(T v, int off) { return __shfl_down_sync(0xFFFFFFFFu, v, off); }
+};
+template <> struct Num<false> {
+    typedef double2 T;
+    static __device__ __forceinline__ T zero() { return make_double2(0.0, 0.0); }
+    static __device__ __forceinline__ T mul(T a, T b) { return cmul(a, b); }
+    static __device__ __forceinline__ T add(T a, T b) { return cadd(a, b); }
+    static __device__ __forceinline__ T from_real(double x) { return make_double2(x, 0.0); }
+    static __device__ __forceinline__ T times_i_of(double2 v) { return times_i(v); }
+    static __device__ __forceinline__ T coef_of(double2 c) { return c; }
+    static __device__ __forceinline__ double2 result(T coef, T acc) { return cmul(coef, acc); }
+    static __device__ __forceinline__ T shfl_down(T v, int off) {
+        return make_double2(__shfl_down_sync(0xFFFFFFFFu, v.x, off), __shfl_down_sync(0xFFFFFFFFu, v.y, off));
+    }
+};
+
+// i * D(t_f, t_i) for a table D[k] = G(k h) with element stride `stride`; the real-mode branch keeps the
+// exact operation order of grid_interp on the imaginary components (bit-identical results).
+template <bool REAL>
+__device__ __forceinline__ typename Num<REAL>::T grid_apply_i(const double2* __restrict__ D, int stride, int n, double inv_h,
+                                                              double t_f, double t_i) {
+    if constexpr (!REAL) {
+        return times_i(grid_interp(D, stride, n, inv_h, t_f, t_i));
+    } else {
+        const double qf = t_f * inv_h, qi = t_i * inv_h;
+        int a = (int)floor(qf), b = (int)floor(qi);
+        a = min(max(a, 0), n - 2);
+        b = min(max(b, 0), n - 2);
+        const double w1 = qf - (double)a, w2 = qi - (double)b;
+        if (a == b) {
+            const double d0 = __ldg(&D[0].y), d1 = __ldg(&D[stride].y);
+            const double w = w1 - w2;
+            return -(d0 + w * (d1 - d0));
+        }
+        const int k = a - b;
+        const double dk = __ldg(&D[(size_t)k * stride].y), dp = __ldg(&D[(size_t)(k + 1) * stride].y),
+                     dm = __ldg(&D[(size_t)(k - 1) * stride].y);
+        const double c00 = (1.0 - w1) * (1.0 - w2), c10 = w1 * (1.0 - w2), c01 = (1.0 - w1) * w2, c11 = w1 * w2;
+        return -(c00 * dk + c10 * dp + c01 * dm + c11 * dk);
+    }
+}
+
+template <bool REAL>
+__device__ __forceinline__ typename Num<REAL>::T delta_apply_i(const DevDelta& t, double t_f, double t_i) {
+    if constexpr (!REAL) {
+        return times_i(delta_eval(t, t_f, t_i));
+    } else {
+        if (t.kind == 1) {
+            const double dt = t_f - t_i, h = t.h;
+            int j = (int)floor(dt * t.inv_h);
+            j = min(max(j, 0), t.n - 2);
+            const double xa = dt - (double)j * h, xb = (double)(j + 1) * h - dt;
+            const double y0 = __ldg(&t.y[j].y), y1 = __ldg(&t.y[j + 1].y), m0 = __ldg(&t.M[j].y), m1 = __ldg(&t.M[j + 1].y);
+            const double i6h = t.inv_h * (1.0 / 6.0), h6 = h * (1.0 / 6.0), ih = t.inv_h;
+            const double ca = xa * xa * xa * i6h, cb = xb * xb * xb * i6h;
+            return -(m0 * cb + m1 * ca + (y0 * ih - m0 * h6) * xb + (y1 * ih - m1 * h6) * xa);
+        }
+        return grid_apply_i<true>(t.y, 1, t.n, t.inv_h, t_f, t_i);
+    }
+}
+
 // ---- configuration walk ------------------------------------------------------------------------
-// Every surviving configuration of an entry is a fixed-length record of table offsets
-// (qiw_host.hpp: EntryProgram::records): the weight
-//   prod_arcs[i Delta_p(t_tail, t_head)] * prod_pos[O_pos * i P_s(t_pos, t_pos-1)]
-// of src/topology_eval.jl:454-556 with the operator matrix elements and the topology sign
-// (-i * parity * (-1)^order, :431) folded into the record's coefficient.  For 1x1 blocks the
-// reference's cached partial products (src/utility.jl:234-323) save almost nothing (the tree
-// branches at the earliest positions), while a flat record needs no control flow at all.
+// Every surviving configuration of an entry is a fixed-length record (qiw_host.hpp: EntryProgram::rec2)
+// of K + order operand slots in the per-sample table: K segment products of propagators and one
+// pair-interaction factor per arc; the operator matrix elements and the topology sign
+// (-i * parity * (-1)^order, src/topology_eval.jl:431) are folded into the record's coefficient.
 //
 // Mapping: one LANE owns one configuration (its record lives in registers for the whole sample
-// block), and loops over the 32 samples of the CTA, whose tables sit in shared memory as
-// T[sample][slot].  Per factor that is ONE instruction (LDS with a uniform row base + the lane's
-// constant offset) feeding four FP64 instructions; lanes that need the same factor (all lanes do,
-// up to the sector index) read the same address, which shared memory serves as a broadcast.
-template <int L, bool PER_SAMPLE>
-__device__ __forceinline__ void config_walk(const uint32_t* __restrict__ rec_t, int g0, int g1,
-                                            const unsigned char* T, int row_bytes, const double2* coefs_s,
-                                            double2* red, int nw, int warp, int lane, int S,
-                                            double2* sample_out, unsigned long long local0, unsigned long long count) {
-    constexpr int H = (L + 1) / 2;   // the product is evaluated as two independent half chains
+// block) and loops over the samples of the CTA, whose tables sit in shared memory as T[sample][slot].
+// Per factor that is one LDS feeding one multiply (real mode) or four FP64 instructions (complex).
+template <int L, bool REAL, bool PER_SAMPLE>
+__device__ __forceinline__ void config_walk(const uint32_t* __restrict__ rec_t, int g0, int g1, const unsigned char* Tb,
+                                            int row_bytes, int spb, const typename Num<REAL>::T* coefs_s, double2* red,
+                                            int nw, int warp, int lane, int S, double2* sample_out,
+                                            unsigned long long local0, unsigned long long count) {
+    typedef typename Num<REAL>::T T;
+    typedef Num<REAL> N;
+    constexpr int SH = REAL ? 3 : 4;
     for (int g = g0; g < g1; ++g) {
         uint32_t w[L + 1];
         const uint32_t* rp = rec_t + (size_t)g * (L + 1) * 32 + lane;
 #pragma unroll
         for (int q = 0; q <= L; ++q) w[q] = __ldg(rp + q * 32);
+#pragma unroll
+        for (int q = 1; q <= L; ++q) w[q] <<= SH;
         const int s_i = (int)(w[0] >> 16);
-        const double2 coef = coefs_s[w[0] & 0xFFFFu];
+        const T coef = coefs_s[w[0] & 0xFFFFu];
         const int smin = (int)__reduce_min_sync(0xFFFFFFFFu, (unsigned)s_i);
         const int smax = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)s_i);
-        double2 acc = make_double2(0.0, 0.0);
-#pragma unroll 2
-        for (int smp = 0; smp < 32; ++smp) {
-            const unsigned char* row = T + smp * row_bytes;
-            double2 va = *reinterpret_cast<const double2*>(row + w[1]);
+        T acc0 = N::zero(), acc1 = N::zero();
+        if constexpr (PER_SAMPLE) {
+            for (int smp = 0; smp < spb; ++smp) {
+                const unsigned char* row = Tb + smp * row_bytes;
+                T va = *reinterpret_cast<const T*>(row + w[1]);
 #pragma unroll
-            for (int f = 2; f <= H; ++f) va = cmul(va, *reinterpret_cast<const double2*>(row + w[f]));
-            if constexpr (L > H) {
-                double2 vb = *reinterpret_cast<const double2*>(row + w[H + 1]);
-#pragma unroll
-                for (int f = H + 2; f <= L; ++f) vb = cmul(vb, *reinterpret_cast<const double2*>(row + w[f]));
-                va = cmul(va, vb);
-            }
-            if constexpr (PER_SAMPLE) {
+                for (int f = 2; f <= L; ++f) va = N::mul(va, *reinterpret_cast<const T*>(row + w[f]));
                 // qiw_eval_at_times: the evaluator's value for every sample separately
-                const double2 c = cmul(coef, va);
+                const double2 c = N::result(coef, va);
                 for (int s = smin; s <= smax; ++s) {
                     double2 r = (s_i == s) ? c : make_double2(0.0, 0.0);
 #pragma unroll
@@ -162,18 +232,38 @@ __device__ __forceinline__ void config_walk(const uint32_t* __restrict__ rec_t, 
                         *o = cadd(*o, r);
                     }
                 }
-            } else {
-                acc = cadd(acc, va);
             }
-        }
-        if constexpr (!PER_SAMPLE) {
+        } else {
+            // two samples in flight per iteration: independent multiply chains
+            int smp = 0;
+#pragma unroll 2
+            for (; smp + 1 < spb; smp += 2) {
+                const unsigned char* r0 = Tb + smp * row_bytes;
+                const unsigned char* r1 = r0 + row_bytes;
+                T va = *reinterpret_cast<const T*>(r0 + w[1]);
+                T vb = *reinterpret_cast<const T*>(r1 + w[1]);
+#pragma unroll
+                for (int f = 2; f <= L; ++f) {
+                    va = N::mul(va, *reinterpret_cast<const T*>(r0 + w[f]));
+                    vb = N::mul(vb, *reinterpret_cast<const T*>(r1 + w[f]));
+                }
+                acc0 = N::add(acc0, va);
+                acc1 = N::add(acc1, vb);
+            }
+            if (smp < spb) {
+                const unsigned char* r0 = Tb + smp * row_bytes;
+                T va = *reinterpret_cast<const T*>(r0 + w[1]);
+#pragma unroll
+                for (int f = 2; f <= L; ++f) va = N::mul(va, *reinterpret_cast<const T*>(r0 + w[f]));
+                acc0 = N::add(acc0, va);
+            }
             // sum over the lanes' configurations, separately for every initial sector present
-            const double2 c = cmul(coef, acc);
+            const double2 c = N::result(coef, N::add(acc0, acc1));
             for (int s = smin; s <= smax; ++s) {
                 double2 r = (s_i == s) ? c : make_double2(0.0, 0.0);
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
-                    r.x += __shfl_down_sync(0xFFFFFFFFu, r.x, off);
+                    if constexpr (!REAL) r.x += __shfl_down_sync(0xFFFFFFFFu, r.x, off);
                     r.y += __shfl_down_sync(0xFFFFFFFFu, r.y, off);
                 }
                 if (lane == 0) red[s * nw + warp] = cadd(red[s * nw + warp], r);
@@ -182,17 +272,16 @@ __device__ __forceinline__ void config_walk(const uint32_t* __restrict__ rec_t, 
     }
 }
 
-// Record lengths that occur: 3n+2 (bold / correlator, order n) and 3n+1 (bare).
-template <int LMAX, bool PER_SAMPLE>
-__device__ __forceinline__ void walk_dispatch(int L, const uint32_t* rec_t, int g0, int g1, const unsigned char* T,
-                                              int row_bytes, const double2* coefs_s, double2* red, int nw, int warp,
-                                              int lane, int S, double2* so, unsigned long long local0,
+// Record lengths: K + order operands, K <= 4 segments, order <= 8.
+template <bool REAL, bool PER_SAMPLE>
+__device__ __forceinline__ void walk_dispatch(int L, const uint32_t* rec_t, int g0, int g1, const unsigned char* Tb,
+                                              int row_bytes, int spb, const typename Num<REAL>::T* coefs_s, double2* red,
+                                              int nw, int warp, int lane, int S, double2* so, unsigned long long local0,
                                               unsigned long long count) {
-#define QIW_CASE(N) case N: if constexpr (N <= LMAX) config_walk<N, PER_SAMPLE>(rec_t, g0, g1, T, row_bytes, coefs_s, red, nw, warp, lane, S, so, local0, count); break;
+#define QIW_CASE(N_) case N_: config_walk<N_, REAL, PER_SAMPLE>(rec_t, g0, g1, Tb, row_bytes, spb, coefs_s, red, nw, warp, lane, S, so, local0, count); break;
     switch (L) {
-        QIW_CASE(1) QIW_CASE(2) QIW_CASE(4) QIW_CASE(5) QIW_CASE(7) QIW_CASE(8) QIW_CASE(10) QIW_CASE(11)
-        QIW_CASE(13) QIW_CASE(14) QIW_CASE(16) QIW_CASE(17) QIW_CASE(19) QIW_CASE(20) QIW_CASE(22) QIW_CASE(23)
-        QIW_CASE(25) QIW_CASE(26)
+        QIW_CASE(1) QIW_CASE(2) QIW_CASE(3) QIW_CASE(4) QIW_CASE(5) QIW_CASE(6) QIW_CASE(7) QIW_CASE(8)
+        QIW_CASE(9) QIW_CASE(10) QIW_CASE(11) QIW_CASE(12)
         default: break;
     }
 #undef QIW_CASE
@@ -200,31 +289,37 @@ __device__ __forceinline__ void walk_dispatch(int L, const uint32_t* rec_t, int 
 
 // ---- the step kernel (scalar models: every sector block is 1x1) ------------------------------
 
-template <int LMAX, bool PER_SAMPLE>
-__global__ void __launch_bounds__(256, (LMAX <= 14) ? 3 : 2) scalar_step_kernel(const StepParams p) {
+template <bool REAL, bool PER_SAMPLE>
+__global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p) {
+    typedef typename Num<REAL>::T T;
+    typedef Num<REAL> N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, nthr = blockDim.x;
     const WorkItem it = p.items[blockIdx.y];
     const DevEntry& e = p.entries[it.entry];
     const DevEntryDyn& dy = p.dyn[it.slot];
-    const int S = p.S, D = e.D, n_nodes = e.n_nodes, nP = e.nP, n_slots = e.nP + e.nD;
+    const int S = p.S, D = e.D, n_nodes = e.n_nodes, nP = e.nP, nD = e.nD, nSeg = e.nSeg;
+    const int n_slots = nP + nD + nSeg;
     const int d_after = e.d_after;
+    const int spb = p.spb;
     // shared memory carve-up (sizes fixed per launch from the largest entry, see host):
-    // T[32 samples][row] with an odd row pitch (in 16-byte units) so that the lanes' stores during
+    // T[spb samples][row] with an odd row pitch (in operand units) so that the lanes' stores during
     // the fill hit different banks
-    const int row_bytes = (n_slots | 1) * 16;
-    unsigned char* T = smem_raw;                                                 // [32][max_row_bytes]
-    double2* red = reinterpret_cast<double2*>(smem_raw + (size_t)p.max_slots * 32 * 16);   // [S][nw]
+    const int row_bytes = (n_slots | 1) * (int)sizeof(T);
+    unsigned char* Tb = smem_raw;                                                            // [spb][max_row]
+    double2* red = reinterpret_cast<double2*>(smem_raw + (size_t)p.max_slots * spb * sizeof(T));   // [S][nw]
     double* times = reinterpret_cast<double*>(red + (size_t)S * nw);             // [kDevMaxNodes+1][32]
     double* pw = times + (kDevMaxNodes + 1) * 32;                                // [kDevMaxDim][32]
     int* okflag = reinterpret_cast<int*>(pw + kDevMaxDim * 32);                  // [32]
     int4* dslots_s = reinterpret_cast<int4*>(okflag + 32);                       // [max_dslots]
-    double2* coefs_s = reinterpret_cast<double2*>(dslots_s + p.max_dslots);      // [n_coefs + 1]
-    for (int c = threadIdx.x; c < e.nD; c += blockDim.x) dslots_s[c] = e.dslots[c];
-
-    for (int c = threadIdx.x; c < S * nw; c += blockDim.x) red[c] = make_double2(0.0, 0.0);
-    for (int c = threadIdx.x; c <= e.n_coefs; c += blockDim.x)
-        coefs_s[c] = (c < e.n_coefs) ? e.coefs[c] : make_double2(0.0, 0.0);   // last: padding records
+    T* coefs_s = reinterpret_cast<T*>(dslots_s + p.max_dslots);                  // [max_coefs + 1]
+    uint16_t* segdef_s = reinterpret_cast<uint16_t*>(coefs_s + p.max_coefs + 1); // [max_segdef]
+    const int seg_stride = e.seg_stride;
+    for (int c = threadIdx.x; c < nD; c += nthr) dslots_s[c] = e.dslots[c];
+    for (int c = threadIdx.x; c < S * nw; c += nthr) red[c] = make_double2(0.0, 0.0);
+    for (int c = threadIdx.x; c <= e.n_coefs; c += nthr)
+        coefs_s[c] = (c < e.n_coefs) ? N::coef_of(e.coefs[c]) : N::zero();   // last: padding records
+    for (int c = threadIdx.x; c < nSeg * seg_stride; c += nthr) segdef_s[c] = e.segdef[c];
 
     double t_i = p.t_i, t_w = p.t_w, t_f = p.t_f;
     if (p.times_dev) { t_i = p.times_dev[0]; t_w = p.times_dev[1]; t_f = p.times_dev[2]; }
@@ -233,7 +328,7 @@ __global__ void __launch_bounds__(256, (LMAX <= 14) ? 3 : 2) scalar_step_kernel(
 
     const uint32_t* __restrict__ sm = dy.sobol;
     const unsigned long long count = dy.count;
-    const int n_sb = (int)((count + 31ull) >> 5);
+    const int n_sb = (int)((count + (unsigned long long)spb - 1ull) / (unsigned long long)spb);
 
     // this warp's share of the entry's configuration groups (32 configurations per group)
     int g0 = 0, g1 = 0;
@@ -258,91 +353,107 @@ __global__ void __launch_bounds__(256, (LMAX <= 14) ? 3 : 2) scalar_step_kernel(
     }
 
     for (int sb = blockIdx.x; sb < n_sb; sb += gridDim.x) {
-        const unsigned long long local0 = (unsigned long long)sb * 32ull, local = local0 + lane;
-        const bool active = local < count;
-        const uint32_t k = (uint32_t)(dy.start + local);
+        const unsigned long long local0 = (unsigned long long)sb * (unsigned long long)spb;
 
         // -- 1. Sobol coordinates and the independent roots x_j^(1/(remaining dims)) ----------
         //       The roots depend only on (entry, Sobol sequence, sample), not on the time step: when the
         //       host provides a cache they are computed once per run and re-read afterwards.
+        if ((int)threadIdx.x < spb) okflag[threadIdx.x] = (local0 + threadIdx.x < count) ? 1 : 0;
         if (p.explicit_times == nullptr) {
             double* uc = dy.ucache;
-            for (int j = warp; j < D; j += nw) {
+            for (int task = threadIdx.x; task < D * spb; task += nthr) {
+                const int j = task / spb, smp = task - j * spb;
+                const unsigned long long local = local0 + smp;
+                const bool active = local < count;
                 double r;
                 if (uc && dy.ucache_valid) {
                     r = active ? uc[(size_t)j * count + local] : 0.0;
                 } else {
-                    const uint32_t xi = sobol_coord(sm + j * 32, __ldg(sm + D * 32 + j), k);
+                    const uint32_t xi = sobol_coord(sm + j * 32, __ldg(sm + D * 32 + j), (uint32_t)(dy.start + local));
                     const double x = (double)xi * 2.3283064365386963e-10;  // ldexp(x, -32), exact
                     const int den = (j < d_after) ? (d_after - j) : (D - j);
                     r = (den == 1) ? x : pow(x, 1.0 / (double)den);
                     if (uc && active && it.chunk0 == 0) uc[(size_t)j * count + local] = r;
                 }
-                pw[j * 32 + lane] = r;
+                pw[j * 32 + smp] = r;
             }
         }
         __syncthreads();
 
-        // -- 2. ordered times of every backbone position ----------------------------------------
-        if (warp == 0) {
-            bool ok = true;
-            double u = 1.0;
-            for (int pos = n_nodes; pos >= 1; --pos) {   // free positions, highest first = u[0], u[1], ...
-                const int src = e.pos_src[pos];
-                double t;
-                if (src == -1) t = t_i;
-                else if (src == -2) t = t_w;
-                else if (src == -3) t = t_f;
-                else if (p.explicit_times) {
-                    t = active ? p.explicit_times[local * D + src] : 0.0;
-                } else {
-                    if (src == 0 || src == d_after) u = pw[src * 32 + lane];
-                    else u = __dmul_rn(u, pw[src * 32 + lane]);
-                    if (src < d_after) t = __dadd_rn(__dmul_rn(u, len_after), lo_after);
-                    else t = __dadd_rn(__dmul_rn(u, len_before), t_i);
-                    ok = ok && (t >= 0.0);   // all(refs .>= 0) (src/qmc_integrate.jl:608)
-                }
-                times[pos * 32 + lane] = t;
+        // -- 2. ordered times of every backbone position: thread = (position, sample).  The running
+        //       product u_j = ((r_0 r_1) r_2) ... r_j is re-evaluated from the start of its simplex so that
+        //       positions are independent (same operation order as the sequential map, bit-identical).
+        for (int task = threadIdx.x; task < n_nodes * spb; task += nthr) {
+            const int pos = 1 + task / spb, smp = task - (pos - 1) * spb;
+            const int src = e.pos_src[pos];
+            double t;
+            if (src == -1) t = t_i;
+            else if (src == -2) t = t_w;
+            else if (src == -3) t = t_f;
+            else if (p.explicit_times) {
+                t = (local0 + smp < count) ? p.explicit_times[(local0 + smp) * D + src] : 0.0;
+            } else {
+                const int j0 = (src < d_after) ? 0 : d_after;
+                double u = pw[j0 * 32 + smp];
+                for (int j = j0 + 1; j <= src; ++j) u = __dmul_rn(u, pw[j * 32 + smp]);
+                if (src < d_after) t = __dadd_rn(__dmul_rn(u, len_after), lo_after);
+                else t = __dadd_rn(__dmul_rn(u, len_before), t_i);
+                if (!(t >= 0.0)) okflag[smp] = 0;   // all(refs .>= 0) (src/qmc_integrate.jl:608)
             }
-            okflag[lane] = (ok && active) ? 1 : 0;
+            times[pos * 32 + smp] = t;
         }
         __syncthreads();
 
-        // -- 3. per-sample tables: thread (warp, lane) fills slots warp, warp+nw, ... of sample `lane`.
-        //       Discarded samples (src/qmc_integrate.jl:503,608) and lanes past the range get zero rows.
+        // -- 3. per-sample tables.  Propagators: thread = (backbone interval, sample) evaluates all
+        //       sectors; pair interactions: thread = (slot, sample).  Discarded samples
+        //       (src/qmc_integrate.jl:503,608) and samples past the range get zero rows.
         {
-            const bool ok = okflag[lane] != 0;
-            unsigned char* myrow = T + lane * row_bytes;
-#pragma unroll 2
-            for (int q = warp; q < n_slots; q += nw) {
-                double2 val;
-                if (q < nP) {
-                    const int iv = q / S, s = q - iv * S;      // interval between positions iv+1, iv+2
-                    const double ta = times[(iv + 1) * 32 + lane];
-                    double tb = times[(iv + 2) * 32 + lane];
+            const int nI = n_nodes - 1;
+            for (int task = threadIdx.x; task < (nI + nD) * spb; task += nthr) {
+                const int q = task / spb, smp = task - q * spb;
+                const bool ok = okflag[smp] != 0;
+                T* myrow = reinterpret_cast<T*>(Tb + smp * row_bytes);
+                if (q < nI) {
+                    const double ta = times[(q + 1) * 32 + smp];
+                    double tb = times[(q + 2) * 32 + smp];
                     if (tb < ta) tb = ta;                       // src/topology_eval.jl:362-364
-                    if (e.mode == 0) {                          // bare: i * (-i) exp(-dt (E + lambda))
-                        val = make_double2(exp(-(tb - ta) * __ldg(p.E + s)), 0.0);
-                    } else {
-                        val = times_i(grid_interp(p.P + s, p.bsize, p.n_tau, p.inv_h, tb, ta));
+                    for (int s = 0; s < S; ++s) {
+                        T val;
+                        if (e.mode == 0) val = N::from_real(exp(-(tb - ta) * __ldg(p.E + s)));   // i * (-i) exp(-dt (E + lambda))
+                        else val = grid_apply_i<REAL>(p.P + s, p.bsize, p.n_tau, p.inv_h, tb, ta);
+                        myrow[q * S + s] = ok ? val : N::zero();
                     }
                 } else {
-                    const int4 ds = dslots_s[q - nP];
-                    const double th = times[ds.y * 32 + lane];
-                    double tt = times[ds.x * 32 + lane];
+                    const int4 ds = dslots_s[q - nI];
+                    const double th = times[ds.y * 32 + smp];
+                    double tt = times[ds.x * 32 + smp];
                     if (tt < th) tt = th;                       // :407-410
-                    val = times_i(delta_eval(ds.z < kInlineTables ? p.deltas_inline[ds.z] : p.deltas[ds.z], tt, th));
+                    const T val = delta_apply_i<REAL>(ds.z < kInlineTables ? p.deltas_inline[ds.z] : p.deltas[ds.z], tt, th);
+                    myrow[nP + (q - nI)] = ok ? val : N::zero();
                 }
-                if (!ok) val = make_double2(0.0, 0.0);
-                *reinterpret_cast<double2*>(myrow + q * 16) = val;
             }
+        }
+        __syncthreads();
+
+        // -- 4. segment products: thread = (segment entry, sample) ----------------------------------
+        for (int task = threadIdx.x; task < nSeg * spb; task += nthr) {
+            const int j = task / spb, smp = task - j * spb;
+            const T* myrow = reinterpret_cast<const T*>(Tb + smp * row_bytes);
+            const uint16_t* sd = segdef_s + j * seg_stride;
+            T v = myrow[sd[0]];
+            for (int i = 1; i < seg_stride; ++i) {
+                const uint16_t q = sd[i];
+                if (q == 0xFFFFu) break;
+                v = N::mul(v, myrow[q]);
+            }
+            reinterpret_cast<T*>(Tb + smp * row_bytes)[nP + nD + j] = v;
         }
         __syncthreads();
         if (trace && threadIdx.x == 0) trace[1] = clock64();
 
-        // -- 4. this warp's configurations -----------------------------------------------------
+        // -- 5. this warp's configurations -----------------------------------------------------
         if (g0 < g1) {
-            walk_dispatch<LMAX, PER_SAMPLE>(e.L, e.records, g0, g1, T, row_bytes, coefs_s, red, nw, warp, lane, S,
+            walk_dispatch<REAL, PER_SAMPLE>(e.L2, e.records, g0, g1, Tb, row_bytes, spb, coefs_s, red, nw, warp, lane, S,
                                             p.per_sample_out, local0, count);
         }
         __syncthreads();
@@ -351,7 +462,7 @@ __global__ void __launch_bounds__(256, (LMAX <= 14) ? 3 : 2) scalar_step_kernel(
 
     if constexpr (PER_SAMPLE) return;
 
-    // -- 5. CTA result: warps summed in fixed order -----------------------------------------------
+    // -- 6. CTA result: warps summed in fixed order -----------------------------------------------
     if ((int)threadIdx.x < S) {
         double2 v = make_double2(0.0, 0.0);
         for (int w2 = 0; w2 < nw; ++w2) v = cadd(v, red[threadIdx.x * nw + w2]);
@@ -452,31 +563,24 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) 
 
 // ---- host-callable launchers -----------------------------------------------------------------
 
-template <int LMAX, bool PER_SAMPLE>
+template <bool REAL, bool PER_SAMPLE>
 static cudaError_t launch_scalar_t(const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(scalar_step_kernel<LMAX, PER_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(scalar_step_kernel<REAL, PER_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    scalar_step_kernel<LMAX, PER_SAMPLE><<<grid, threads, smem, st>>>(p);
+    scalar_step_kernel<REAL, PER_SAMPLE><<<grid, threads, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-template <int LMAX>
-static cudaError_t launch_scalar(const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    // the per-sample variant (qiw_eval_at_times) is only instantiated for the deepest class
-    if (p.per_sample_out) return launch_scalar_t<26, true>(p, grid, threads, smem, st);
-    return launch_scalar_t<LMAX, false>(p, grid, threads, smem, st);
-}
-
-// `lmax` = longest record of the launch; classes: orders <= 2, <= 4, <= 6, <= 8.
-cudaError_t launch_scalar_step(int lmax, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    if (lmax <= 8) return launch_scalar<8>(p, grid, threads, smem, st);
-    if (lmax <= 14) return launch_scalar<14>(p, grid, threads, smem, st);
-    if (lmax <= 20) return launch_scalar<20>(p, grid, threads, smem, st);
-    return launch_scalar<26>(p, grid, threads, smem, st);
+// `real_mode`: every table and coefficient in use has been verified purely imaginary by the host.
+cudaError_t launch_scalar_step(bool real_mode, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    if (p.per_sample_out) {
+        return real_mode ? launch_scalar_t<true, true>(p, grid, threads, smem, st) : launch_scalar_t<false, true>(p, grid, threads, smem, st);
+    }
+    return real_mode ? launch_scalar_t<true, false>(p, grid, threads, smem, st) : launch_scalar_t<false, false>(p, grid, threads, smem, st);
 }
 
 cudaError_t launch_reduce(const DevEntryDyn* dyn, const DevEntry* entries, const double2* partials, int pitch, int S,

@@ -60,6 +60,7 @@ _SIGNATURES = {
     "qiw_entry_stats": (C.c_int, [C.c_void_p, C.c_int32, i64p, i64p, i64p, f64p]),
     "qiw_entry_program": (C.c_int, [C.c_void_p, C.c_int32, i64p, C.POINTER(C.c_uint64), i64p, u32p, i64p, f64p,
                                     i64p, i32p, i32p, i32p]),
+    "qiw_entry_records": (C.c_int, [C.c_void_p, C.c_int32, i32p, u32p, C.POINTER(C.c_uint16)]),
     "qiw_eval": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int32, i32p, u32p, u32p,
                            C.c_uint64, f64p]),
     "qiw_eval_range": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int32, i32p, u32p, u32p,
@@ -280,6 +281,18 @@ class Context:
         return dict(words=words, tree_off=tree_off, coefs=coefs[:nc.value], dslots=dslots[:nd.value],
                     pos_src=pos_src, n_nodes=int(info[0]), nP=int(info[1]), S=int(info[2]), scalar=bool(info[3]))
 
+    def entry_records(self, entry_id):
+        """Factorised configuration records of a compiled entry (qiw_entry_records)."""
+        info = np.zeros(8, dtype=np.int32)
+        self._ck(self.L.qiw_entry_records(self.h, entry_id, _ptr(info, i32p), None, None))
+        K, L2, nl, nseg, stride, nP, nD = (int(x) for x in info[:7])
+        rec2 = np.zeros((max(nl, 1), L2 + 1), dtype=np.uint32)
+        segdef = np.zeros((max(nseg, 1), stride), dtype=np.uint16)
+        self._ck(self.L.qiw_entry_records(self.h, entry_id, _ptr(info, i32p), _ptr(rec2, u32p),
+                                          segdef.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return dict(K=K, L2=L2, n_leaves=nl, nSeg=nseg, seg_stride=stride, nP=nP, nD=nD, rec2=rec2[:nl],
+                    segdef=segdef[:nseg])
+
     # -- hot path
     def _sobol_args(self, ids, sobol):
         if sobol is None:
@@ -324,8 +337,8 @@ class Context:
                                          _ptr(hist.view(np.float64), f64p) if want_contribs else None))
         return hist
 
-    PROFILE_CLASSES = ("step_order_le2", "step_order_le4", "step_order_le6", "step_order_le8", "reduce", "finish_step",
-                       "nccl_allreduce", "other")
+    PROFILE_CLASSES = ("step_complex", "step_real", "unused2", "unused3", "reduce", "finish_step",
+                       "nccl_allreduce", "step_block")
 
     def profile_enable(self, on=True):
         self._ck(self.L.qiw_profile_enable(self.h, int(on)))

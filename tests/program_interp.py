@@ -22,8 +22,8 @@ def natural_spline(y, h):
     return CubicSpline(x, y, bc_type="natural")
 
 
-def run_program(prog, expansion, payload, mode, t_i, t_w, t_f, times):
-    """Per-sample evaluator value (packed, scalar models): sum over trees of leaf coef * chain."""
+def sample_table(prog, expansion, payload, mode, t_i, t_w, t_f, times):
+    """The per-sample operand table the step kernel builds: i P per (interval, sector), i Delta per slot."""
     S, nP, n_nodes = prog["S"], prog["nP"], prog["n_nodes"]
     beta, n_tau = payload["beta"], payload["n_tau"]
     h = beta / (n_tau - 1)
@@ -47,6 +47,33 @@ def run_program(prog, expansion, payload, mode, t_i, t_w, t_f, times):
             T[nP + j] = 1j * natural_spline(data, beta / (len(data) - 1))(tt - th)
         else:
             T[nP + j] = 1j * grid_interp(data, beta / (len(data) - 1), tt, th)
+    return T
+
+
+def run_records(rec, prog, expansion, payload, mode, t_i, t_w, t_f, times):
+    """Replays the factorised configuration records (qiw_entry_records) as the CUDA kernel does:
+    segment products first, then K + order operands per configuration."""
+    T = sample_table(prog, expansion, payload, mode, t_i, t_w, t_f, times)
+    seg = np.ones(rec["nSeg"], dtype=complex)
+    for j in range(rec["nSeg"]):
+        for q in rec["segdef"][j]:
+            if q != 0xFFFF:
+                seg[j] *= T[q]
+    T = np.concatenate([T, seg])
+    assert len(T) == rec["nP"] + rec["nD"] + rec["nSeg"]
+    out = np.zeros(prog["S"], dtype=complex)
+    for r in rec["rec2"]:
+        v = prog["coefs"][int(r[0]) & 0xFFFF]
+        for q in r[1:]:
+            v = v * T[int(q)]
+        out[int(r[0]) >> 16] += v
+    return out
+
+
+def run_program(prog, expansion, payload, mode, t_i, t_w, t_f, times):
+    """Per-sample evaluator value (packed, scalar models): sum over trees of leaf coef * chain."""
+    S = prog["S"]
+    T = sample_table(prog, expansion, payload, mode, t_i, t_w, t_f, times)
     words = prog["words"]
     out = np.zeros(S, dtype=complex)
     pc = [0]

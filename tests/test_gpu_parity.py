@@ -228,3 +228,43 @@ def test_block_models_vs_oracle(gpu_ctx, qlib, oracle_lib, name):
     refP = oracle_lib.inchworm(ex2.flatten(), ex2.P, range(0, 3), range(0, 3), 2 ** 5)["P"]
     inchworm(ex2, ex2.grid, range(0, 3), range(0, 3), 2 ** 5, solver=Solver(ex2, ctx=gpu_ctx), device_resident=True)
     assert relerr(ex2.P, refP) < RTOL
+
+
+def test_real_and_complex_arithmetic_agree(gpu_ctx, qlib, oracle_lib, monkeypatch):
+    """The real-arithmetic fast path (all operands purely imaginary-time) and the general complex path
+    of the step kernel give the same numbers; a complex hybridisation forces the complex path and still
+    matches the oracle."""
+    ex, grid, f = models.anderson(n_tau=40)
+    rng = np.random.default_rng(11)
+    ex.P = ex.P * (1.0 + 0.05 * rng.random(ex.P.shape))
+    pl = gpu_ctx.set_expansion(ex)
+    o = oracle_lib.Oracle(pl, ex.P)
+    ids = []
+    for order in range(0, 5):
+        for k in ([0] if order == 0 else range(1, 2 * order)):
+            pr, pa = qlib.topologies(order, k)
+            gpu_ctx.set_topologies(len(ids), qlib.MODE_BOLD, order, k, pr, pa)
+            o.set_topologies(len(ids), qlib.MODE_BOLD, order, k, pr, pa)
+            ids.append(len(ids))
+    tau = grid.tau
+    N = 2 ** 9
+    ref = o.eval(0.0, tau[20], tau[21], ids, N)
+    got_real = gpu_ctx.eval(0.0, tau[20], tau[21], ids, N)
+    monkeypatch.setenv("QIW_FORCE_COMPLEX", "1")
+    got_cplx = gpu_ctx.eval(0.0, tau[20], tau[21], ids, N)
+    monkeypatch.delenv("QIW_FORCE_COMPLEX")
+    assert relerr(got_real, ref) < RTOL and relerr(got_cplx, ref) < RTOL
+    assert relerr(got_real, got_cplx) < 1e-13
+    # a P table with a real part switches the library to complex arithmetic by itself
+    P2 = ex.P * (1.0 + 0.02j)
+    gpu_ctx.set_P(0, P2)
+    o2 = oracle_lib.Oracle(pl, P2)
+    eid = 0
+    for order in range(0, 5):
+        for k in ([0] if order == 0 else range(1, 2 * order)):
+            pr, pa = qlib.topologies(order, k)
+            o2.set_topologies(eid, qlib.MODE_BOLD, order, k, pr, pa)
+            eid += 1
+    got = gpu_ctx.eval(0.0, tau[20], tau[21], ids, N)
+    ref2 = o2.eval(0.0, tau[20], tau[21], ids, N)
+    assert relerr(got, ref2) < RTOL
