@@ -432,7 +432,17 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
                 }
             }
         CK(ed.records.upload(rec.data(), rec.size(), ctx->stream));
-        CK(ed.segdef.upload(pr.segdef.data(), pr.segdef.size(), ctx->stream));
+        {   // segment definitions transposed into groups of 32 entries; padding -> the constant-one slot
+            const int nsg = (pr.nSeg + 31) / 32, st = pr.seg_stride;
+            const uint16_t one = (uint16_t)(pr.nP + (int)pr.dslots.size() + pr.nSeg);
+            std::vector<uint16_t> sd((size_t)std::max(nsg, 1) * st * 32, one);
+            for (int j = 0; j < pr.nSeg; ++j)
+                for (int i = 0; i < st; ++i) {
+                    const uint16_t q = pr.segdef[(size_t)j * st + i];
+                    sd[((size_t)(j / 32) * st + i) * 32 + (j % 32)] = (q == 0xFFFFu) ? one : q;
+                }
+            CK(ed.segdef.upload(sd.data(), sd.size(), ctx->stream));
+        }
     }
     if (!ctx->model.scalar) {
         CK(ed.words.upload(pr.words.data(), pr.words.size(), ctx->stream));
@@ -642,7 +652,7 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         max_groups = std::max(max_groups, (double)((p.n_leaves + 31) / 32));
         g.maxl = std::max(g.maxl, p.L2);
         g.max_coefs = std::max(g.max_coefs, (int)p.coefs.size());
-        g.max_slots = std::max(g.max_slots, (p.nP + (int)p.dslots.size() + p.nSeg) | 1);
+        g.max_slots = std::max(g.max_slots, (p.nP + (int)p.dslots.size() + p.nSeg + 1) | 1);
         g.max_dslots = std::max(g.max_dslots, (int)p.dslots.size());
         g.max_segdef = std::max(g.max_segdef, p.nSeg * p.seg_stride);
     }
@@ -655,7 +665,7 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
             b = (b + 15) & ~(size_t)15;
             return b + (size_t)S * W * sizeof(double2) + (size_t)(kDevMaxNodes + 1) * 32 * sizeof(double) +
                    (size_t)kDevMaxDim * 32 * sizeof(double) + 32 * sizeof(int) + (size_t)g.max_dslots * sizeof(int4) +
-                   (size_t)(g.max_coefs + 1) * opsz + (size_t)g.max_segdef * sizeof(uint16_t) + 16;
+                   (size_t)(g.max_coefs + 1) * opsz + 16;
         };
         int spb = 32;
         while (spb > 1 && smem_of(spb) > (size_t)110 * 1024) spb >>= 1;
@@ -685,7 +695,7 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         const EntryProgram &pa = ctx->entries[ids[a2]]->prog, &pb2 = ctx->entries[ids[b2]]->prog;
         return (double)pa.n_leaves * pa.L2 > (double)pb2.n_leaves * pb2.L2; });
     {
-        const int spb_min = std::min(g.spb[0], g.spb[1]);
+        const int spb_min = spb_plan;
         for (int i : order_idx) {
             const EntryProgram& p = ctx->entries[ids[i]]->prog;
             const uint64_t c = p.order == 0 ? 1 : count;
@@ -838,6 +848,8 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         gp.max_coefs = g.max_coefs;
         gp.max_segdef = g.max_segdef;
         gp.spb = g.spb[real];
+        gp.spb_log2 = 0;
+        while ((1 << gp.spb_log2) < gp.spb) ++gp.spb_log2;
         dim3 grid((unsigned)pl.pitch, (unsigned)g.n_items);
         {
             ProfScope ps(ctx, real ? 1 : 0);

@@ -270,8 +270,10 @@ void factorise_records(EntryProgram& e, int S, int K_req) {
     std::vector<uint32_t> best_rec;
     std::vector<uint16_t> best_def;
     int best_nseg = 0, best_stride = 0;
-    const int Kmax = std::min(nI, 4);
-    for (int K = (K_req > 0 ? std::min(K_req, nI) : 1); K <= (K_req > 0 ? std::min(K_req, nI) : Kmax); ++K) {
+    const int Kmin = (nI + 8) / 9;   // the kernel handles segments of up to 9 intervals
+    const int Kmax = std::max(Kmin, std::min(nI, 4));
+    const int K_lo = K_req > 0 ? std::max(Kmin, std::min(K_req, nI)) : Kmin, K_hi = K_req > 0 ? K_lo : Kmax;
+    for (int K = K_lo; K <= K_hi; ++K) {
         std::vector<int> bound(K + 1);
         for (int g = 0; g <= K; ++g) bound[g] = (int)((int64_t)g * nI / K);
         int stride = 0;

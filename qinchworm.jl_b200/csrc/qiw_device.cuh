@@ -33,7 +33,8 @@ struct DevEntry {
     int nSeg, seg_stride;       // segment-product table: entries, propagator slots per entry
     const uint32_t* records;    // transposed: [n_groups][L2 + 1][32 lanes]; word 0 = coef | s_i << 16,
                                 // words 1..L2 = operand slot inside a sample's table row
-    const uint16_t* segdef;     // [nSeg][seg_stride] propagator slots of each segment product (0xFFFF = none)
+    const uint16_t* segdef;     // transposed [groups of 32 entries][seg_stride][32 lanes]: propagator slots of each
+                                // segment product; unused positions point at the row's constant-one slot
     const double2* coefs;
     const int4* dslots;         // (pos_tail, pos_head, table, 0)
 };
@@ -78,7 +79,7 @@ struct StepParams {
     const double* times_dev;
     int max_slots;                 // operands per sample row reserved in shared memory
     int max_coefs, max_segdef;     // shared-memory staging sizes (largest entry of the launch)
-    int spb;                       // samples per CTA pass (<= 32)
+    int spb, spb_log2;             // samples per CTA pass (power of two <= 32)
     // explicit-times mode (qiw_eval_at_times): times[count][D], per-sample output, no reduction
     const double* explicit_times;
     double2* per_sample_out;       // [count][S]

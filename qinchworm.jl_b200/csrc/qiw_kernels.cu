@@ -138,29 +138,42 @@ template <> struct Num<false> {
     }
 };
 
-// i * D(t_f, t_i) for a table D[k] = G(k h) with element stride `stride`; the real-mode branch keeps the
-// exact operation order of grid_interp on the imaginary components (bit-identical results).
+// Cell and weights of the Keldysh.jl grid rule for one (t_f, t_i) pair; shared by every sector / table
+// evaluated at that pair.  k = 0: both times in one cell (triangular rule).
+struct GridCell { int k; double c00, c10, c01, c11; };
+__device__ __forceinline__ GridCell grid_cell(int n, double inv_h, double t_f, double t_i) {
+    const double qf = t_f * inv_h, qi = t_i * inv_h;
+    int a = __double2int_rd(qf), b = __double2int_rd(qi);
+    a = min(max(a, 0), n - 2);
+    b = min(max(b, 0), n - 2);
+    const double w1 = qf - (double)a, w2 = qi - (double)b;
+    GridCell c;
+    c.k = a - b;
+    if (c.k == 0) { c.c00 = w1 - w2; c.c10 = c.c01 = c.c11 = 0.0; }
+    else { c.c00 = (1.0 - w1) * (1.0 - w2); c.c10 = w1 * (1.0 - w2); c.c01 = (1.0 - w1) * w2; c.c11 = w1 * w2; }
+    return c;
+}
+// i * D(t_f, t_i) for a table D[k] = G(k h) with element stride `stride` (same operation order as
+// grid_interp; the real mode works on the imaginary components only).
 template <bool REAL>
-__device__ __forceinline__ typename Num<REAL>::T grid_apply_i(const double2* __restrict__ D, int stride, int n, double inv_h,
-                                                              double t_f, double t_i) {
+__device__ __forceinline__ typename Num<REAL>::T cell_apply_i(const double2* __restrict__ D, int stride, const GridCell& c) {
     if constexpr (!REAL) {
-        return times_i(grid_interp(D, stride, n, inv_h, t_f, t_i));
-    } else {
-        const double qf = t_f * inv_h, qi = t_i * inv_h;
-        int a = (int)floor(qf), b = (int)floor(qi);
-        a = min(max(a, 0), n - 2);
-        b = min(max(b, 0), n - 2);
-        const double w1 = qf - (double)a, w2 = qi - (double)b;
-        if (a == b) {
-            const double d0 = __ldg(&D[0].y), d1 = __ldg(&D[stride].y);
-            const double w = w1 - w2;
-            return -(d0 + w * (d1 - d0));
+        if (c.k == 0) {
+            const double2 d0 = __ldg(D), d1 = __ldg(D + stride);
+            return make_double2(-(d0.y + c.c00 * (d1.y - d0.y)), d0.x + c.c00 * (d1.x - d0.x));
         }
-        const int k = a - b;
-        const double dk = __ldg(&D[(size_t)k * stride].y), dp = __ldg(&D[(size_t)(k + 1) * stride].y),
-                     dm = __ldg(&D[(size_t)(k - 1) * stride].y);
-        const double c00 = (1.0 - w1) * (1.0 - w2), c10 = w1 * (1.0 - w2), c01 = (1.0 - w1) * w2, c11 = w1 * w2;
-        return -(c00 * dk + c10 * dp + c01 * dm + c11 * dk);
+        const double2 dk = __ldg(D + (size_t)c.k * stride), dp = __ldg(D + (size_t)(c.k + 1) * stride),
+                      dm = __ldg(D + (size_t)(c.k - 1) * stride);
+        return make_double2(-(c.c00 * dk.y + c.c10 * dp.y + c.c01 * dm.y + c.c11 * dk.y),
+                            c.c00 * dk.x + c.c10 * dp.x + c.c01 * dm.x + c.c11 * dk.x);
+    } else {
+        if (c.k == 0) {
+            const double d0 = __ldg(&D[0].y), d1 = __ldg(&D[stride].y);
+            return -(d0 + c.c00 * (d1 - d0));
+        }
+        const double dk = __ldg(&D[(size_t)c.k * stride].y), dp = __ldg(&D[(size_t)(c.k + 1) * stride].y),
+                     dm = __ldg(&D[(size_t)(c.k - 1) * stride].y);
+        return -(c.c00 * dk + c.c10 * dp + c.c01 * dm + c.c11 * dk);
     }
 }
 
@@ -179,7 +192,39 @@ __device__ __forceinline__ typename Num<REAL>::T delta_apply_i(const DevDelta& t
             const double ca = xa * xa * xa * i6h, cb = xb * xb * xb * i6h;
             return -(m0 * cb + m1 * ca + (y0 * ih - m0 * h6) * xb + (y1 * ih - m1 * h6) * xa);
         }
-        return grid_apply_i<true>(t.y, 1, t.n, t.inv_h, t_f, t_i);
+        return cell_apply_i<true>(t.y, 1, grid_cell(t.n, t.inv_h, t_f, t_i));
+    }
+}
+
+// Segment products (EntryProgram::segdef): lane = table entry, loop over the samples of a range; the
+// entry's propagator slots live in registers.  Shorter segments are padded with the row's constant-one slot.
+template <int LEN, bool REAL>
+__device__ __forceinline__ void segment_products(const uint16_t* __restrict__ segdef_t, int n_seg, int out0,
+                                                 unsigned char* Tb, int row_bytes, int spb, int warp, int nw, int lane) {
+    typedef typename Num<REAL>::T T;
+    typedef Num<REAL> N;
+    constexpr int SH = REAL ? 3 : 4;
+    const int n_groups = (n_seg + 31) >> 5;
+    // tasks = (group of 32 entries) x (sample sub-range); split the samples so that every warp has work
+    int split = 1;
+    while (n_groups * split < nw && split < spb) split <<= 1;
+    const int per = spb / split;
+    for (int task = warp; task < n_groups * split; task += nw) {
+        const int g = task / split, part = task - g * split;
+        const int j = g * 32 + lane;
+        uint32_t q[LEN];
+        const uint16_t* sd = segdef_t + (size_t)g * LEN * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < LEN; ++i) q[i] = (uint32_t)sd[i * 32] << SH;
+        if (j >= n_seg) continue;
+        unsigned char* row = Tb + (size_t)part * per * row_bytes;
+#pragma unroll 2
+        for (int smp = 0; smp < per; ++smp, row += row_bytes) {
+            T v = *reinterpret_cast<const T*>(row + q[0]);
+#pragma unroll
+            for (int i = 1; i < LEN; ++i) v = N::mul(v, *reinterpret_cast<const T*>(row + q[i]));
+            reinterpret_cast<T*>(row)[out0 + j] = v;
+        }
     }
 }
 
@@ -234,23 +279,28 @@ __device__ __forceinline__ void config_walk(const uint32_t* __restrict__ rec_t, 
                 }
             }
         } else {
-            // two samples in flight per iteration: independent multiply chains
+            // four samples in flight per iteration: independent multiply chains
             int smp = 0;
-#pragma unroll 2
-            for (; smp + 1 < spb; smp += 2) {
+            for (; smp + 3 < spb; smp += 4) {
                 const unsigned char* r0 = Tb + smp * row_bytes;
                 const unsigned char* r1 = r0 + row_bytes;
+                const unsigned char* r2 = r1 + row_bytes;
+                const unsigned char* r3 = r2 + row_bytes;
                 T va = *reinterpret_cast<const T*>(r0 + w[1]);
                 T vb = *reinterpret_cast<const T*>(r1 + w[1]);
+                T vc = *reinterpret_cast<const T*>(r2 + w[1]);
+                T vd = *reinterpret_cast<const T*>(r3 + w[1]);
 #pragma unroll
                 for (int f = 2; f <= L; ++f) {
                     va = N::mul(va, *reinterpret_cast<const T*>(r0 + w[f]));
                     vb = N::mul(vb, *reinterpret_cast<const T*>(r1 + w[f]));
+                    vc = N::mul(vc, *reinterpret_cast<const T*>(r2 + w[f]));
+                    vd = N::mul(vd, *reinterpret_cast<const T*>(r3 + w[f]));
                 }
-                acc0 = N::add(acc0, va);
-                acc1 = N::add(acc1, vb);
+                acc0 = N::add(acc0, N::add(va, vc));
+                acc1 = N::add(acc1, N::add(vb, vd));
             }
-            if (smp < spb) {
+            for (; smp < spb; ++smp) {
                 const unsigned char* r0 = Tb + smp * row_bytes;
                 T va = *reinterpret_cast<const T*>(r0 + w[1]);
 #pragma unroll
@@ -299,9 +349,9 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
     const DevEntry& e = p.entries[it.entry];
     const DevEntryDyn& dy = p.dyn[it.slot];
     const int S = p.S, D = e.D, n_nodes = e.n_nodes, nP = e.nP, nD = e.nD, nSeg = e.nSeg;
-    const int n_slots = nP + nD + nSeg;
+    const int n_slots = nP + nD + nSeg + 1;   // + the constant-one slot that pads short segment products
     const int d_after = e.d_after;
-    const int spb = p.spb;
+    const int spb = p.spb, spb_sh = p.spb_log2, spb_mask = spb - 1;   // spb is a power of two
     // shared memory carve-up (sizes fixed per launch from the largest entry, see host):
     // T[spb samples][row] with an odd row pitch (in operand units) so that the lanes' stores during
     // the fill hit different banks
@@ -313,13 +363,11 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
     int* okflag = reinterpret_cast<int*>(pw + kDevMaxDim * 32);                  // [32]
     int4* dslots_s = reinterpret_cast<int4*>(okflag + 32);                       // [max_dslots]
     T* coefs_s = reinterpret_cast<T*>(dslots_s + p.max_dslots);                  // [max_coefs + 1]
-    uint16_t* segdef_s = reinterpret_cast<uint16_t*>(coefs_s + p.max_coefs + 1); // [max_segdef]
     const int seg_stride = e.seg_stride;
     for (int c = threadIdx.x; c < nD; c += nthr) dslots_s[c] = e.dslots[c];
     for (int c = threadIdx.x; c < S * nw; c += nthr) red[c] = make_double2(0.0, 0.0);
     for (int c = threadIdx.x; c <= e.n_coefs; c += nthr)
         coefs_s[c] = (c < e.n_coefs) ? N::coef_of(e.coefs[c]) : N::zero();   // last: padding records
-    for (int c = threadIdx.x; c < nSeg * seg_stride; c += nthr) segdef_s[c] = e.segdef[c];
 
     double t_i = p.t_i, t_w = p.t_w, t_f = p.t_f;
     if (p.times_dev) { t_i = p.times_dev[0]; t_w = p.times_dev[1]; t_f = p.times_dev[2]; }
@@ -362,7 +410,7 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
         if (p.explicit_times == nullptr) {
             double* uc = dy.ucache;
             for (int task = threadIdx.x; task < D * spb; task += nthr) {
-                const int j = task / spb, smp = task - j * spb;
+                const int j = task >> spb_sh, smp = task & spb_mask;
                 const unsigned long long local = local0 + smp;
                 const bool active = local < count;
                 double r;
@@ -384,7 +432,7 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
         //       product u_j = ((r_0 r_1) r_2) ... r_j is re-evaluated from the start of its simplex so that
         //       positions are independent (same operation order as the sequential map, bit-identical).
         for (int task = threadIdx.x; task < n_nodes * spb; task += nthr) {
-            const int pos = 1 + task / spb, smp = task - (pos - 1) * spb;
+            const int pos = 1 + (task >> spb_sh), smp = task & spb_mask;
             const int src = e.pos_src[pos];
             double t;
             if (src == -1) t = t_i;
@@ -410,18 +458,25 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
         {
             const int nI = n_nodes - 1;
             for (int task = threadIdx.x; task < (nI + nD) * spb; task += nthr) {
-                const int q = task / spb, smp = task - q * spb;
+                const int q = task >> spb_sh, smp = task & spb_mask;
                 const bool ok = okflag[smp] != 0;
                 T* myrow = reinterpret_cast<T*>(Tb + smp * row_bytes);
                 if (q < nI) {
                     const double ta = times[(q + 1) * 32 + smp];
                     double tb = times[(q + 2) * 32 + smp];
                     if (tb < ta) tb = ta;                       // src/topology_eval.jl:362-364
-                    for (int s = 0; s < S; ++s) {
-                        T val;
-                        if (e.mode == 0) val = N::from_real(exp(-(tb - ta) * __ldg(p.E + s)));   // i * (-i) exp(-dt (E + lambda))
-                        else val = grid_apply_i<REAL>(p.P + s, p.bsize, p.n_tau, p.inv_h, tb, ta);
-                        myrow[q * S + s] = ok ? val : N::zero();
+                    if (q == 0) myrow[n_slots - 1] = N::from_real(1.0);
+                    if (e.mode == 0) {
+                        for (int s = 0; s < S; ++s) {           // bare: i * (-i) exp(-dt (E + lambda))
+                            const T val = N::from_real(exp(-(tb - ta) * __ldg(p.E + s)));
+                            myrow[q * S + s] = ok ? val : N::zero();
+                        }
+                    } else {
+                        const GridCell cell = grid_cell(p.n_tau, p.inv_h, tb, ta);
+                        for (int s = 0; s < S; ++s) {
+                            const T val = cell_apply_i<REAL>(p.P + s, p.bsize, cell);
+                            myrow[q * S + s] = ok ? val : N::zero();
+                        }
                     }
                 } else {
                     const int4 ds = dslots_s[q - nI];
@@ -435,18 +490,12 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
         }
         __syncthreads();
 
-        // -- 4. segment products: thread = (segment entry, sample) ----------------------------------
-        for (int task = threadIdx.x; task < nSeg * spb; task += nthr) {
-            const int j = task / spb, smp = task - j * spb;
-            const T* myrow = reinterpret_cast<const T*>(Tb + smp * row_bytes);
-            const uint16_t* sd = segdef_s + j * seg_stride;
-            T v = myrow[sd[0]];
-            for (int i = 1; i < seg_stride; ++i) {
-                const uint16_t q = sd[i];
-                if (q == 0xFFFFu) break;
-                v = N::mul(v, myrow[q]);
-            }
-            reinterpret_cast<T*>(Tb + smp * row_bytes)[nP + nD + j] = v;
+        // -- 4. segment products -----------------------------------------------------------------------
+        switch (seg_stride) {
+#define QIW_SEG(N_) case N_: segment_products<N_, REAL>(e.segdef, nSeg, nP + nD, Tb, row_bytes, spb, warp, nw, lane); break;
+            QIW_SEG(1) QIW_SEG(2) QIW_SEG(3) QIW_SEG(4) QIW_SEG(5) QIW_SEG(6) QIW_SEG(7) QIW_SEG(8) QIW_SEG(9)
+#undef QIW_SEG
+            default: break;
         }
         __syncthreads();
         if (trace && threadIdx.x == 0) trace[1] = clock64();
