@@ -257,6 +257,18 @@ int qiw_comm_unique_id(uint8_t id[QIW_UNIQUE_ID_BYTES]);
 int qiw_comm_init(qiw_context* ctx, int32_t n_ranks, int32_t rank, const uint8_t id[QIW_UNIQUE_ID_BYTES]);
 int qiw_comm_destroy(qiw_context* ctx);
 
+#define QIW_PEER_HANDLE_BYTES 64
+/* Peer-memory all-reduce (preferred when the GPUs of the job see each other over NVLink/NVSwitch):
+ * the reduction of the per-GPU block sums is performed INSIDE the step kernel's tail — every rank
+ * stores its sums into all peers' mailboxes, raises a flag and adds up what the peers stored, in rank
+ * order — so an inchworm step stays a single kernel launch on every GPU.
+ * Every rank calls qiw_peer_handle (allocates its mailbox, returns the CUDA IPC handle), the host
+ * all-gathers the 64-byte handles (MPI.Allgather in Julia, torch.distributed here) and passes all of
+ * them, in rank order, to qiw_peer_init.  Payloads larger than 64 KiB per call and block models fall
+ * back to the NCCL communicator of qiw_comm_init (which must then exist). */
+int qiw_peer_handle(qiw_context* ctx, uint8_t handle[QIW_PEER_HANDLE_BYTES]);
+int qiw_peer_init(qiw_context* ctx, int32_t n_ranks, int32_t rank, const uint8_t* handles);
+
 /* ---- measurement helpers ---------------------------------------------------------------------------- */
 
 /* Runs a DFMA-saturating kernel and reports the measured FP64 FMA throughput (TFLOP/s, 2 flops

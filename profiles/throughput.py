@@ -15,7 +15,6 @@ print("measured FP64 FMA peak %.2f TFLOP/s" % peak)
 solver = Solver(ex, ctx=ctx)
 tau = grid.tau
 for N in Ns:
-    solver._next_entry = 0
     bold = _bold_entries(solver, range(0, max_order + 1), N, None, None)
     ids = [t.entry_id for t in bold]
     st = [ctx.entry_stats(i) for i in ids]

@@ -25,6 +25,9 @@ t0 = t[:, 8].min()
 print("CTAs", len(t), "start spread us", (t[:, 8].max() - t0) / 1e3)
 m = t[:, 2] > 0
 print("setup us: mean %.2f max %.2f" % (((t[m, 2] - t[m, 1]) / clk).mean(), ((t[m, 2] - t[m, 1]) / clk).max()))
+print("  of which roots %.2f times %.2f fill %.2f segments %.2f (means)" % (((t[m, 9] - t[m, 1]) / clk).mean(), ((t[m, 10] - t[m, 9]) / clk).mean(),
+      ((t[m, 11] - t[m, 10]) / clk).mean(), ((t[m, 2] - t[m, 11]) / clk).mean()))
+print("kernel span us (first CTA start .. last CTA end, globaltimer + cycles): %.2f" % ((t[m, 8] - t0) / 1e3 + (t[m, 4] - t[m, 1]) / clk).max())
 print("walk  us: mean %.2f max %.2f" % (((t[m, 3] - t[m, 2]) / clk).mean(), ((t[m, 3] - t[m, 2]) / clk).max()))
 print("tail  us: mean %.2f max %.2f" % (((t[m, 4] - t[m, 3]) / clk).mean(), ((t[m, 4] - t[m, 3]) / clk).max()))
 print("start offsets us: pctl", np.percentile((t[:, 8] - t0) / 1e3, [0, 25, 50, 75, 90, 100]))
@@ -32,8 +35,10 @@ for e in sorted(set(t[:, 6])):
     k = (t[:, 6] == e) & m
     if k.sum() == 0:
         continue
-    print("entry %d: n %d groups/warp0 %d setup %.2f walk %.2f tail %.2f total %.2f start %.1f" % (
-        e, k.sum(), t[k, 7].mean(), ((t[k, 2] - t[k, 1]) / clk).mean(), ((t[k, 3] - t[k, 2]) / clk).mean(),
+    print("entry %d: n %d groups/warp0 %d roots %.2f times %.2f fill %.2f seg %.2f | setup %.2f walk %.2f tail %.2f total %.2f start %.1f" % (
+        e, k.sum(), t[k, 7].mean(), ((t[k, 9] - t[k, 1]) / clk).mean(), ((t[k, 10] - t[k, 9]) / clk).mean(),
+        ((t[k, 11] - t[k, 10]) / clk).mean(), ((t[k, 2] - t[k, 11]) / clk).mean(),
+        ((t[k, 2] - t[k, 1]) / clk).mean(), ((t[k, 3] - t[k, 2]) / clk).mean(),
         ((t[k, 4] - t[k, 3]) / clk).mean(), ((t[k, 4] - t[k, 1]) / clk).mean(), ((t[k, 8] - t0) / 1e3).mean()))
 # per-SM busy time
 import collections

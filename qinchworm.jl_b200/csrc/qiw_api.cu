@@ -164,6 +164,7 @@ struct qiw_context {
     DevBuf<const uint32_t*> dTreeOffPtr;
     DevBuf<int> dNTrees;
     DevBuf<unsigned long long> dTrace;
+    DevBuf<unsigned int> dCounter;   // arrival counter of the step kernel's fused tail (self-resetting)
     double2* hOut = nullptr;  // pinned
     size_t hOutCap = 0;
     std::vector<std::unique_ptr<Plan>> plans;
@@ -178,6 +179,13 @@ struct qiw_context {
     // NCCL
     ncclComm_t comm = nullptr;
     int n_ranks = 1, rank = 0;
+    // peer-memory all-reduce
+    unsigned char* peerLocal = nullptr;            // this rank's mailbox
+    std::vector<unsigned char*> peerPtrs;          // every rank's mailbox as mapped here (own = peerLocal)
+    DevBuf<unsigned char*> dPeerPtrs;
+    DevBuf<int> dPeerStatus;
+    unsigned long long peer_seq = 0;
+    bool peer_ready = false;
 };
 
 #define CK(call)                                                                              \
@@ -256,8 +264,12 @@ int qiw_destroy(qiw_context* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     cudaStreamSynchronize(ctx->stream);
+    for (size_t q = 0; q < ctx->peerPtrs.size(); ++q)
+        if (ctx->peerPtrs[q] && ctx->peerPtrs[q] != ctx->peerLocal) cudaIpcCloseMemHandle(ctx->peerPtrs[q]);
+    if (ctx->peerLocal) cudaFree(ctx->peerLocal);
+    ctx->dPeerPtrs.release(); ctx->dPeerStatus.release();
     ctx->dP.release(); ctx->dE.release(); ctx->dDeltas.release(); ctx->dEntries.release();
-    ctx->dPerSample.release(); ctx->dTimes.release(); ctx->dHist.release(); ctx->dDiag.release(); ctx->dTrace.release();
+    ctx->dPerSample.release(); ctx->dTimes.release(); ctx->dHist.release(); ctx->dDiag.release(); ctx->dTrace.release(); ctx->dCounter.release();
     ctx->dDim.release(); ctx->dBoff.release(); ctx->dEoff.release(); ctx->dOpTarget.release(); ctx->dOpOff.release();
     ctx->dPool.release(); ctx->dScratch.release(); ctx->dWordsPtr.release(); ctx->dTreeOffPtr.release(); ctx->dNTrees.release();
     for (auto& t : ctx->tables) { t.y.release(); t.M.release(); }
@@ -664,14 +676,19 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
             size_t b = (size_t)g.max_slots * spb * opsz;
             b = (b + 15) & ~(size_t)15;
             return b + (size_t)S * W * sizeof(double2) + (size_t)(kDevMaxNodes + 1) * 32 * sizeof(double) +
-                   (size_t)kDevMaxDim * 32 * sizeof(double) + 32 * sizeof(int) + (size_t)g.max_dslots * sizeof(int4) +
+                   (size_t)kDevMaxDim * 32 * sizeof(double) + (size_t)(kDevMaxNodes + 1) * 32 * (sizeof(double) + sizeof(int)) +
+                   32 * sizeof(int) + (size_t)g.max_dslots * sizeof(int4) +
                    (size_t)(g.max_coefs + 1) * opsz + 16;
         };
         int spb = 32;
         while (spb > 1 && smem_of(spb) > (size_t)110 * 1024) spb >>= 1;
-        if (spb < 16) { spb = 32; while (spb > 1 && smem_of(spb) > (size_t)227 * 1024) spb >>= 1; }
-        if (smem_of(spb) > (size_t)227 * 1024) return fail(ctx, QIW_ERR_UNSUPPORTED, "per-sample tables exceed shared memory (too many sectors for the scalar kernel)");
-        g.spb[real] = explicit_mode ? std::min(spb, 32) : spb;
+        if (spb < 16) { spb = 32; while (spb > 1 && smem_of(spb) > (size_t)226 * 1024) spb >>= 1; }
+        if (smem_of(spb) > (size_t)226 * 1024) return fail(ctx, QIW_ERR_UNSUPPORTED, "per-sample tables exceed shared memory (too many sectors for the scalar kernel)");
+        if (const char* env = getenv("QIW_SPB")) {   // tuning override (power of two <= 32)
+            const int v = atoi(env);
+            if (v >= 1 && v <= 32 && (v & (v - 1)) == 0 && smem_of(v) <= (size_t)226 * 1024) spb = v;
+        }
+        g.spb[real] = spb;
         g.smem[real] = smem_of(g.spb[real]);
     }
     const int spb_plan = g.spb[real_mode_possible(ctx, n_entries, ids) ? 1 : 0];
@@ -801,9 +818,17 @@ static int stage_call(qiw_context* ctx, Plan& pl, const uint32_t* sobol_m, const
     return QIW_OK;
 }
 
-// Enqueue the kernels of one evaluation of a plan at fixed times: step kernels (one per tree-depth
-// class) + the deterministic reduction.  Nothing is synchronised here.
-static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, double t_f) {
+// What the step kernel's last CTA does after the reduction in the device-resident loop.
+struct FinishArgs { int k_f = -1; int normalize = 0; double2* hist = nullptr; const int* diag = nullptr; int n_diag = 0; };
+
+// Enqueue the kernels of one evaluation of a plan at fixed times: the step kernel (whose last CTA
+// also performs the deterministic reduction and, if `fin` asks for it, the P update) — or, for block
+// models, step kernel + reduction kernel.  Nothing is synchronised here.  Returns through
+// `finish_done` whether the P update was fused.
+static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, double t_f, const FinishArgs* fin = nullptr,
+                        bool* finish_done = nullptr, bool collective = false, bool* collective_done = nullptr) {
+    if (finish_done) *finish_done = false;
+    if (collective_done) *collective_done = false;
     const HostModel& m = ctx->model;
     StepParams sp;
     memset(&sp, 0, sizeof(sp));
@@ -813,11 +838,34 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
     sp.S = m.S; sp.bsize = m.bsize; sp.n_tau = ctx->n_tau; sp.h = ctx->beta / (ctx->n_tau - 1); sp.inv_h = 1.0 / sp.h;
     sp.t_i = t_i; sp.t_w = t_w; sp.t_f = t_f;
     sp.partials = pl.d_partials.p;
+    sp.finish_k_f = -1;
+    if (m.scalar && !pl.explicit_mode) {
+        if (!ctx->dCounter.p) {
+            CK(ctx->dCounter.reserve(1));
+            CK(cudaMemsetAsync(ctx->dCounter.p, 0, sizeof(unsigned int), ctx->stream));
+        }
+        sp.done_counter = ctx->dCounter.p;
+        sp.n_call_entries = (int)pl.ids.size();
+        sp.out = pl.d_out.p;
+        bool exchange_fused = false;
+        if (collective && ctx->peer_ready && ctx->n_ranks > 1 && pl.ids.size() * (size_t)m.bsize * sizeof(double2) <= kPeerSlotBytes) {
+            sp.peer_ranks = ctx->n_ranks; sp.peer_rank = ctx->rank; sp.peer_seq = ++ctx->peer_seq;
+            sp.peer_mail = ctx->dPeerPtrs.p; sp.peer_status = ctx->dPeerStatus.p;
+            exchange_fused = true;
+            if (collective_done) *collective_done = true;
+        }
+        // the P update can be fused only if the sums are already global when the tail reaches it
+        if (fin && fin->k_f >= 0 && (exchange_fused || ctx->n_ranks == 1 || !collective)) {
+            sp.finish_k_f = fin->k_f; sp.finish_normalize = fin->normalize; sp.finish_P = ctx->dP.p;
+            sp.finish_diag = fin->diag; sp.finish_n_diag = fin->n_diag; sp.finish_hist = fin->hist;
+            if (finish_done) *finish_done = true;
+        }
+    }
     if (pl.explicit_mode) { sp.explicit_times = ctx->dTimes.p; sp.per_sample_out = ctx->dPerSample.p; }
     const char* trace_path = getenv("QIW_TRACE");   // diagnostics: per-CTA timeline of the last step kernel
     size_t trace_words = 0;
     if (trace_path) {
-        trace_words = (size_t)pl.pitch * pl.items.size() * 8;
+        trace_words = (size_t)pl.pitch * pl.items.size() * 12;
         CK(ctx->dTrace.reserve(trace_words));
         CK(cudaMemsetAsync(ctx->dTrace.p, 0, trace_words * sizeof(unsigned long long), ctx->stream));
         sp.trace = ctx->dTrace.p;
@@ -862,14 +910,14 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         CK(cudaMemcpyAsync(tr.data(), ctx->dTrace.p, trace_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (FILE* f = fopen(trace_path, "w")) {
-            fprintf(f, "cta,start_clk,tables_clk,walk_clk,end_clk,smid,entry,groups_warp0,start_ns\n");
-            for (size_t c = 0; c < trace_words / 8; ++c)
-                fprintf(f, "%zu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu\n", c, tr[c * 8], tr[c * 8 + 1], tr[c * 8 + 2], tr[c * 8 + 3],
-                        tr[c * 8 + 4], tr[c * 8 + 5], tr[c * 8 + 6], tr[c * 8 + 7]);
+            fprintf(f, "cta,start_clk,tables_clk,walk_clk,end_clk,smid,entry,groups_warp0,start_ns,roots_clk,times_clk,fill_clk\n");
+            for (size_t c = 0; c < trace_words / 12; ++c)
+                fprintf(f, "%zu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu\n", c, tr[c * 12], tr[c * 12 + 1], tr[c * 12 + 2], tr[c * 12 + 3],
+                        tr[c * 12 + 4], tr[c * 12 + 5], tr[c * 12 + 6], tr[c * 12 + 7], tr[c * 12 + 8], tr[c * 12 + 9], tr[c * 12 + 10]);
             fclose(f);
         }
     }
-    if (!pl.explicit_mode) {
+    if (!pl.explicit_mode && !m.scalar) {
         {
             ProfScope ps(ctx, 4);
             CK(launch_reduce(pl.d_dyn.p, ctx->dEntries.p, pl.d_partials.p, pl.pitch, m.bsize, t_i, t_w, t_f, pl.d_out.p,
@@ -894,6 +942,18 @@ static int nccl_allreduce(qiw_context* ctx, double2* buf, size_t n_complex) {
     ProfScope ps(ctx, 6);
     int nrc = g_nccl.AllReduce(buf, buf, n_complex * 2, kNcclDouble, kNcclSum, ctx->comm, ctx->stream);
     if (nrc) return fail(ctx, QIW_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "error"));
+    return QIW_OK;
+}
+
+// After a synchronised call that used the peer exchange: did every peer answer?
+static int check_peer_status(qiw_context* ctx) {
+    if (!ctx->peer_ready || ctx->n_ranks <= 1) return QIW_OK;
+    int st = 0;
+    CK(cudaMemcpy(&st, ctx->dPeerStatus.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st) {
+        cudaMemset(ctx->dPeerStatus.p, 0, sizeof(int));
+        return fail(ctx, QIW_ERR_NCCL, "peer-memory all-reduce timed out: a rank of the job did not reach the collective");
+    }
     return QIW_OK;
 }
 
@@ -928,14 +988,15 @@ static int eval_scalar(qiw_context* ctx, double t_i, double t_w, double t_f, int
         CK(cudaMemsetAsync(ctx->dPerSample.p, 0, (size_t)n_explicit * m.bsize * sizeof(double2), ctx->stream));
     }
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    rc = enqueue_step(ctx, pl, t_i, t_w, t_f);
+    bool coll_done = false;
+    rc = enqueue_step(ctx, pl, t_i, t_w, t_f, nullptr, nullptr, allreduce && !explicit_mode, &coll_done);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     rc = mark_ucache_valid(ctx, pl);
     if (rc) return rc;
     const size_t n_out = explicit_mode ? (size_t)n_explicit * m.bsize : (size_t)n_entries * m.bsize;
     double2* src = explicit_mode ? ctx->dPerSample.p : pl.d_out.p;
-    if (allreduce && !explicit_mode) { rc = nccl_allreduce(ctx, src, n_out); if (rc) return rc; }
+    if (allreduce && !explicit_mode && !coll_done) { rc = nccl_allreduce(ctx, src, n_out); if (rc) return rc; }
     rc = ensure_host_out(ctx, n_out);
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->hOut, src, n_out * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
@@ -944,6 +1005,7 @@ static int eval_scalar(qiw_context* ctx, double t_i, double t_w, double t_f, int
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_ms = ms;
     memcpy(out, ctx->hOut, n_out * sizeof(double2));
+    if (coll_done) return check_peer_status(ctx);
     return QIW_OK;
 }
 
@@ -1041,30 +1103,35 @@ int qiw_inchworm_run(qiw_context* ctx, int32_t n_bare, const int32_t* bare_ids, 
     CK(ctx->dDiag.upload(diag.data(), diag.size(), ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     // bare step: grid[0] -> grid[1], no normalisation (src/inchworm.jl:400-416)
-    rc = enqueue_step(ctx, *pb, 0.0, 0.0, h);
+    FinishArgs fin;
+    bool coll_done = false;
+    fin.diag = ctx->dDiag.p; fin.n_diag = (int)diag.size();
+    bool fused = false;
+    fin.k_f = 1; fin.normalize = 0; fin.hist = order_contribs ? ctx->dHist.p + (size_t)1 * n_hist * bs : nullptr;
+    rc = enqueue_step(ctx, *pb, 0.0, 0.0, h, &fin, &fused, true, &coll_done);
     if (rc) return rc;
-    rc = nccl_allreduce(ctx, pb->d_out.p, (size_t)n_bare * bs);
-    if (rc) return rc;
-    {
+    if (!coll_done) { rc = nccl_allreduce(ctx, pb->d_out.p, (size_t)n_bare * bs); if (rc) return rc; }
+    if (!fused) {
         ProfScope ps(ctx, 5);
         CK(launch_finish_step(ctx->dP.p, n_tau, bs, ctx->dDiag.p, (int)diag.size(), h, 1, pb->d_out.p, n_bare, 0,
                               order_contribs ? ctx->dHist.p + (size_t)1 * n_hist * bs : nullptr, ctx->stream));
+        ctx->launches++;
     }
-    ctx->launches++;
     // bold steps n = 2 .. n_tau-1 (1-based): tau_w = grid[n], tau_f = grid[n+1] (:474-493)
     for (int n = 1; n_bold > 0 && n < n_tau - 1; ++n) {
-        rc = enqueue_step(ctx, *pd, 0.0, n * h, (n + 1) * h);
+        fin.k_f = n + 1; fin.normalize = 1;
+        fin.hist = order_contribs ? ctx->dHist.p + ((size_t)(n + 1) * n_hist + n_bare) * bs : nullptr;
+        rc = enqueue_step(ctx, *pd, 0.0, n * h, (n + 1) * h, &fin, &fused, true, &coll_done);
         if (rc) return rc;
         rc = mark_ucache_valid(ctx, *pd);
         if (rc) return rc;
-        rc = nccl_allreduce(ctx, pd->d_out.p, (size_t)n_bold * bs);
-        if (rc) return rc;
-        {
+        if (!coll_done) { rc = nccl_allreduce(ctx, pd->d_out.p, (size_t)n_bold * bs); if (rc) return rc; }
+        if (!fused) {
             ProfScope ps(ctx, 5);
             CK(launch_finish_step(ctx->dP.p, n_tau, bs, ctx->dDiag.p, (int)diag.size(), h, n + 1, pd->d_out.p, n_bold, 1,
                                   order_contribs ? ctx->dHist.p + ((size_t)(n + 1) * n_hist + n_bare) * bs : nullptr, ctx->stream));
+            ctx->launches++;
         }
-        ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     if (order_contribs)
@@ -1073,6 +1140,9 @@ int qiw_inchworm_run(qiw_context* ctx, int32_t n_bare, const int32_t* bare_ids, 
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_ms = ms;
+    // rows written in complex arithmetic may carry a real part: the next qiw_set_P re-examines them
+    if (!(m.scalar && ctx->last_real_mode)) for (int k = 1; k < n_tau; ++k) ctx->p_row_complex[k] = 1;
+    if (coll_done) return check_peer_status(ctx);
     return QIW_OK;
 }
 
@@ -1147,6 +1217,54 @@ int qiw_comm_destroy(qiw_context* ctx) {
     if (!ctx) return QIW_ERR_BAD_ARG;
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     ctx->comm = nullptr; ctx->n_ranks = 1; ctx->rank = 0;
+    drop_plans(ctx);
+    return QIW_OK;
+}
+
+int qiw_peer_handle(qiw_context* ctx, uint8_t handle[QIW_PEER_HANDLE_BYTES]) {
+    if (!ctx || !handle) return fail(ctx, QIW_ERR_BAD_ARG, "qiw_peer_handle: bad argument");
+    if (ctx->no_device) return fail(ctx, QIW_ERR_CUDA, "planning-only context cannot communicate");
+    static_assert(sizeof(cudaIpcMemHandle_t) == QIW_PEER_HANDLE_BYTES, "IPC handle size");
+    cudaSetDevice(ctx->device);
+    if (!ctx->peerLocal) {
+        CK(cudaMalloc((void**)&ctx->peerLocal, kPeerMailBytes));
+        CK(cudaMemset(ctx->peerLocal, 0, kPeerMailBytes));
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->peerLocal));
+    memcpy(handle, &h, QIW_PEER_HANDLE_BYTES);
+    return QIW_OK;
+}
+
+int qiw_peer_init(qiw_context* ctx, int32_t n_ranks, int32_t rank, const uint8_t* handles) {
+    if (!ctx || n_ranks <= 0 || n_ranks > kMaxPeers || rank < 0 || rank >= n_ranks || !handles)
+        return fail(ctx, QIW_ERR_BAD_ARG, "qiw_peer_init: bad argument (at most 16 ranks)");
+    if (ctx->no_device) return fail(ctx, QIW_ERR_CUDA, "planning-only context cannot communicate");
+    if (!ctx->peerLocal) return fail(ctx, QIW_ERR_BAD_ARG, "qiw_peer_init: call qiw_peer_handle first");
+    if (ctx->comm && (ctx->n_ranks != n_ranks || ctx->rank != rank)) return fail(ctx, QIW_ERR_BAD_ARG, "qiw_peer_init: rank layout differs from qiw_comm_init");
+    cudaSetDevice(ctx->device);
+    ctx->peerPtrs.assign(n_ranks, nullptr);
+    for (int q = 0; q < n_ranks; ++q) {
+        if (q == rank) { ctx->peerPtrs[q] = ctx->peerLocal; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)q * QIW_PEER_HANDLE_BYTES, QIW_PEER_HANDLE_BYTES);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            ctx->peerPtrs.clear();
+            return fail(ctx, QIW_ERR_CUDA, std::string("qiw_peer_init: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e) +
+                                           " (no peer access between the GPUs? the NCCL path of qiw_comm_init remains usable)");
+        }
+        ctx->peerPtrs[q] = (unsigned char*)ptr;
+    }
+    CK(ctx->dPeerPtrs.upload(ctx->peerPtrs.data(), ctx->peerPtrs.size(), ctx->stream));
+    CK(ctx->dPeerStatus.reserve(1));
+    CK(cudaMemsetAsync(ctx->dPeerStatus.p, 0, sizeof(int), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_ranks = n_ranks; ctx->rank = rank;
+    ctx->peer_seq = 0;
+    ctx->peer_ready = true;
     drop_plans(ctx);
     return QIW_OK;
 }

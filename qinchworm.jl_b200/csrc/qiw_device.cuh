@@ -85,8 +85,32 @@ struct StepParams {
     double2* per_sample_out;       // [count][S]
     // output
     double2* partials;             // [n partial rows][gridDim.x][S]
-    unsigned long long* trace;     // diagnostics: 8 words per CTA, or null
+    unsigned long long* trace;     // diagnostics: 12 words per CTA, or null
+    // fused tail: the last CTA to finish reduces the per-CTA partial sums of every entry of the call
+    // (deterministic order) and, in the device-resident loop, applies set_ppgf! + normalize!
+    unsigned int* done_counter;    // null = no fused tail (separate reduction kernel)
+    int n_call_entries;            // entries of this call (rows of `dyn`)
+    double2* out;                  // [n_call_entries][S] reduced results
+    int finish_k_f;                // >= 0: write P(tau_k_f) = sum of the entries' results ...
+    int finish_normalize;          // ... and rescale the table (src/ppgf.jl:646-668)
+    double2* finish_P;             // the P table to update (== P)
+    const int* finish_diag;
+    int finish_n_diag;
+    double2* finish_hist;          // optional per-entry contributions of this step
+    // peer-memory all-reduce inside the fused tail (one process per GPU, mailboxes mapped with CUDA IPC):
+    // every rank stores its reduced block sums into all peers' mailboxes over NVLink, raises a flag,
+    // waits for the peers' flags and sums the contributions in rank order (identical on all ranks)
+    int peer_ranks, peer_rank;     // peer_ranks <= 1: no exchange
+    unsigned long long peer_seq;   // sequence number of this collective (flags carry it; parity selects the buffer)
+    unsigned char* const* peer_mail;   // [peer_ranks] base address of every rank's mailbox (own included)
+    int* peer_status;              // set to 1 if a peer did not answer within the time-out
 };
+
+// Mailbox layout (per rank): flags[kMaxPeers][2] (uint64), then data[kMaxPeers][2][kPeerSlotBytes].
+constexpr int kMaxPeers = 16;
+constexpr size_t kPeerSlotBytes = 64 * 1024;
+constexpr size_t kPeerFlagBytes = (size_t)kMaxPeers * 2 * sizeof(unsigned long long);
+constexpr size_t kPeerMailBytes = kPeerFlagBytes + (size_t)kMaxPeers * 2 * kPeerSlotBytes;
 
 }  // namespace qiw
 

@@ -153,6 +153,14 @@ __device__ __forceinline__ GridCell grid_cell(int n, double inv_h, double t_f, d
     else { c.c00 = (1.0 - w1) * (1.0 - w2); c.c10 = w1 * (1.0 - w2); c.c01 = (1.0 - w1) * w2; c.c11 = w1 * w2; }
     return c;
 }
+// The same from per-time cell indices and fractional weights computed once per backbone position.
+__device__ __forceinline__ GridCell grid_cell_from(int a, double w1, int b, double w2) {
+    GridCell c;
+    c.k = a - b;
+    if (c.k == 0) { c.c00 = w1 - w2; c.c10 = c.c01 = c.c11 = 0.0; }
+    else { c.c00 = (1.0 - w1) * (1.0 - w2); c.c10 = w1 * (1.0 - w2); c.c01 = (1.0 - w1) * w2; c.c11 = w1 * w2; }
+    return c;
+}
 // i * D(t_f, t_i) for a table D[k] = G(k h) with element stride `stride` (same operation order as
 // grid_interp; the real mode works on the imaginary components only).
 template <bool REAL>
@@ -337,6 +345,105 @@ __device__ __forceinline__ void walk_dispatch(int L, const uint32_t* rec_t, int 
 #undef QIW_CASE
 }
 
+// ---- fused tail of the step kernel ---------------------------------------------------------------
+// out = weight * (-i)^d * Jacobian * sum(rows): the factors of contour_integral / qmc_integral
+// (src/qmc_integrate.jl:497-507,565-569,597-612) and of the simplex maps (:46,458-463).
+__device__ __forceinline__ double simplex_volume(int d, double edge) {
+    double v = 1.0;
+    for (int i = 1; i <= d; ++i) v *= edge / (double)i;
+    return v;
+}
+
+__device__ __forceinline__ double entry_scale(const DevEntry& e, const DevEntryDyn& dy, double t_i, double t_w, double t_f) {
+    if (e.exact) return dy.weight;
+    const double jac = (e.mode == 0) ? simplex_volume(e.D, t_f - t_i)
+                                     : simplex_volume(e.d_before, t_w - t_i) * simplex_volume(e.d_after, t_f - t_w);
+    const double dir = (e.order & 1) ? -1.0 : 1.0;   // (-i)^(2 order)
+    return dir * jac * dy.weight;
+}
+
+// Executed by the last CTA of a step launch: every (entry, sector) sum runs over the partial rows in
+// fixed order, so the result does not depend on which CTA happens to be last.  Optionally followed by
+// set_ppgf!(P, tau_f, result) and normalize!(P, tau_f) (src/ppgf.jl:495-504,646-668).
+__device__ void fused_tail(const StepParams& p, double t_i, double t_w, double t_f, int pitch) {
+    const int S = p.S, n_out = p.n_call_entries * S;
+    for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+        const int i = o / S, s = o - i * S;
+        const DevEntryDyn& dy = p.dyn[i];
+        const DevEntry& e = p.entries[dy.entry];
+        const double scale = entry_scale(e, dy, t_i, t_w, t_f);
+        const size_t row0 = (size_t)dy.item0 * pitch, nrows = (size_t)dy.n_items * pitch;
+        double2 v0 = make_double2(0.0, 0.0), v1 = v0;
+        size_t r = 0;
+        for (; r + 1 < nrows; r += 2) {
+            v0 = cadd(v0, __ldcg(p.partials + (row0 + r) * S + s));
+            v1 = cadd(v1, __ldcg(p.partials + (row0 + r + 1) * S + s));
+        }
+        if (r < nrows) v0 = cadd(v0, __ldcg(p.partials + (row0 + r) * S + s));
+        p.out[(size_t)dy.out_index * S + s] = cscale(scale, cadd(v0, v1));
+    }
+    if (p.peer_ranks > 1) {
+        // ---- all-reduce over peer memory (replaces all_reduce!, src/mpi.jl:104-127) ----
+        __syncthreads();
+        const int par = (int)(p.peer_seq & 1ull);
+        const size_t my_slot = kPeerFlagBytes + ((size_t)p.peer_rank * 2 + par) * kPeerSlotBytes;
+        for (int q = 0; q < p.peer_ranks; ++q) {
+            double2* dst = reinterpret_cast<double2*>(p.peer_mail[q] + my_slot);
+            for (int o = threadIdx.x; o < n_out; o += blockDim.x) dst[o] = p.out[o];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < p.peer_ranks) {
+            // raise my flag in peer `threadIdx.x`'s mailbox, then wait for that peer's flag in mine
+            unsigned long long* theirs = reinterpret_cast<unsigned long long*>(p.peer_mail[threadIdx.x]) + p.peer_rank * 2 + par;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(p.peer_seq) : "memory");
+            const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(p.peer_mail[p.peer_rank]) + threadIdx.x * 2 + par;
+            const unsigned long long t0 = globaltimer_ns();
+            unsigned long long seen;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+                if (seen != p.peer_seq && globaltimer_ns() - t0 > 10000000000ull) { *p.peer_status = 1; break; }   // 10 s
+            } while (seen != p.peer_seq);
+        }
+        __syncthreads();
+        const unsigned char* base = p.peer_mail[p.peer_rank] + kPeerFlagBytes;
+        for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+            double2 v = make_double2(0.0, 0.0);
+            for (int q = 0; q < p.peer_ranks; ++q)
+                v = cadd(v, __ldcv(reinterpret_cast<const double2*>(base + ((size_t)q * 2 + par) * kPeerSlotBytes) + o));
+            p.out[o] = v;
+        }
+    }
+    if (p.finish_k_f < 0) return;
+    __syncthreads();
+    __shared__ double lambda_s;
+    const int bsize = p.bsize, k_f = p.finish_k_f;
+    double2* P = p.finish_P;
+    for (int el = threadIdx.x; el < bsize; el += blockDim.x) {
+        double2 v = make_double2(0.0, 0.0);
+        for (int j = 0; j < p.n_call_entries; ++j) {
+            const double2 c = p.out[(size_t)j * bsize + el];
+            v = cadd(v, c);
+            if (p.finish_hist) p.finish_hist[(size_t)j * bsize + el] = c;
+        }
+        P[(size_t)k_f * bsize + el] = v;
+    }
+    __syncthreads();
+    if (!p.finish_normalize) return;
+    if (threadIdx.x == 0) {
+        double pmax = -1.0e300;
+        for (int i = 0; i < p.finish_n_diag; ++i) pmax = fmax(pmax, -P[(size_t)k_f * bsize + p.finish_diag[i]].y);
+        lambda_s = log(pmax) / ((double)k_f * p.h);
+    }
+    __syncthreads();
+    const double lambda = lambda_s;
+    for (int idx = threadIdx.x; idx < p.n_tau * bsize; idx += blockDim.x) {
+        const int k = idx / bsize;
+        const double f = exp(-((double)k * p.h) * lambda);
+        P[idx] = cscale(f, P[idx]);
+    }
+}
+
 // ---- the step kernel (scalar models: every sector block is 1x1) ------------------------------
 
 template <bool REAL, bool PER_SAMPLE>
@@ -360,7 +467,9 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
     double2* red = reinterpret_cast<double2*>(smem_raw + (size_t)p.max_slots * spb * sizeof(T));   // [S][nw]
     double* times = reinterpret_cast<double*>(red + (size_t)S * nw);             // [kDevMaxNodes+1][32]
     double* pw = times + (kDevMaxNodes + 1) * 32;                                // [kDevMaxDim][32]
-    int* okflag = reinterpret_cast<int*>(pw + kDevMaxDim * 32);                  // [32]
+    double* cellw = pw + kDevMaxDim * 32;                                        // [kDevMaxNodes+1][32] fractional cell weight
+    int* cella = reinterpret_cast<int*>(cellw + (kDevMaxNodes + 1) * 32);        // [kDevMaxNodes+1][32] grid cell of each time
+    int* okflag = cella + (kDevMaxNodes + 1) * 32;                               // [32]
     int4* dslots_s = reinterpret_cast<int4*>(okflag + 32);                       // [max_dslots]
     T* coefs_s = reinterpret_cast<T*>(dslots_s + p.max_dslots);                  // [max_coefs + 1]
     const int seg_stride = e.seg_stride;
@@ -389,7 +498,7 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
     // optional per-CTA timeline (diagnostics; compiled in only with -DQIW_TRACE_BUILD because
     // reading %globaltimer costs microseconds): start / tables ready / walk done / end
 #ifdef QIW_TRACE_BUILD
-    unsigned long long* trace = p.trace ? p.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+    unsigned long long* trace = p.trace ? p.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 12 : nullptr;
 #else
     constexpr unsigned long long* trace = nullptr;
 #endif
@@ -427,6 +536,7 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
             }
         }
         __syncthreads();
+        if (trace && threadIdx.x == 0) trace[8] = clock64();
 
         // -- 2. ordered times of every backbone position: thread = (position, sample).  The running
         //       product u_j = ((r_0 r_1) r_2) ... r_j is re-evaluated from the start of its simplex so that
@@ -449,8 +559,14 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
                 if (!(t >= 0.0)) okflag[smp] = 0;   // all(refs .>= 0) (src/qmc_integrate.jl:608)
             }
             times[pos * 32 + smp] = t;
+            // grid cell and weight of this time on the P grid (Keldysh.jl rule, shared by all slots)
+            const double q = t * p.inv_h;
+            const int a = min(max(__double2int_rd(q), 0), p.n_tau - 2);
+            cella[pos * 32 + smp] = a;
+            cellw[pos * 32 + smp] = q - (double)a;
         }
         __syncthreads();
+        if (trace && threadIdx.x == 0) trace[9] = clock64();
 
         // -- 3. per-sample tables.  Propagators: thread = (backbone interval, sample) evaluates all
         //       sectors; pair interactions: thread = (slot, sample).  Discarded samples
@@ -472,7 +588,9 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
                             myrow[q * S + s] = ok ? val : N::zero();
                         }
                     } else {
-                        const GridCell cell = grid_cell(p.n_tau, p.inv_h, tb, ta);
+                        const bool sw = times[(q + 2) * 32 + smp] < ta;   // clamped: both ends in the earlier time's cell
+                        const int ia = (q + 1) * 32 + smp, ib = sw ? ia : ia + 32;
+                        const GridCell cell = grid_cell_from(cella[ib], cellw[ib], cella[ia], cellw[ia]);
                         for (int s = 0; s < S; ++s) {
                             const T val = cell_apply_i<REAL>(p.P + s, p.bsize, cell);
                             myrow[q * S + s] = ok ? val : N::zero();
@@ -483,12 +601,20 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
                     const double th = times[ds.y * 32 + smp];
                     double tt = times[ds.x * 32 + smp];
                     if (tt < th) tt = th;                       // :407-410
-                    const T val = delta_apply_i<REAL>(ds.z < kInlineTables ? p.deltas_inline[ds.z] : p.deltas[ds.z], tt, th);
+                    const DevDelta& dt = ds.z < kInlineTables ? p.deltas_inline[ds.z] : p.deltas[ds.z];
+                    T val;
+                    if (dt.kind == 0 && dt.n == p.n_tau && dt.inv_h == p.inv_h) {   // table on the P grid: reuse the cells
+                        const int ih = ds.y * 32 + smp, it2 = (tt == th) ? ih : ds.x * 32 + smp;
+                        val = cell_apply_i<REAL>(dt.y, 1, grid_cell_from(cella[it2], cellw[it2], cella[ih], cellw[ih]));
+                    } else {
+                        val = delta_apply_i<REAL>(dt, tt, th);
+                    }
                     myrow[nP + (q - nI)] = ok ? val : N::zero();
                 }
             }
         }
         __syncthreads();
+        if (trace && threadIdx.x == 0) trace[10] = clock64();
 
         // -- 4. segment products -----------------------------------------------------------------------
         switch (seg_stride) {
@@ -518,6 +644,22 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
         p.partials[((size_t)it.partial0 * gridDim.x + blockIdx.x) * S + threadIdx.x] = v;
     }
     if (trace && threadIdx.x == 0) trace[3] = clock64();
+
+    // -- 7. fused tail: the last CTA to arrive reduces all partial sums (and updates P) ---------------
+    if (p.done_counter) {
+        __shared__ int is_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned ticket = atomicAdd(p.done_counter, 1u);
+            is_last = (ticket == gridDim.x * gridDim.y - 1u) ? 1 : 0;
+        }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        fused_tail(p, t_i, t_w, t_f, (int)gridDim.x);
+        if (threadIdx.x == 0) *p.done_counter = 0u;
+    }
 }
 
 }  // namespace qiw
@@ -528,12 +670,6 @@ namespace qiw {
 // One CTA per entry of the call; rows of an entry are consecutive.
 // out = weight * (-i)^d * Jacobian * sum(rows): the factors of contour_integral / qmc_integral
 // (src/qmc_integrate.jl:497-507,565-569,597-612) and of the simplex maps (:46,458-463).
-__device__ __forceinline__ double simplex_volume(int d, double edge) {
-    double v = 1.0;
-    for (int i = 1; i <= d; ++i) v *= edge / (double)i;
-    return v;
-}
-
 __global__ void __launch_bounds__(128) reduce_partials_kernel(const DevEntryDyn* __restrict__ dyn,
                                                               const DevEntry* __restrict__ entries,
                                                               const double2* __restrict__ partials, int pitch, int S,
@@ -542,13 +678,7 @@ __global__ void __launch_bounds__(128) reduce_partials_kernel(const DevEntryDyn*
     __shared__ double2 buf[128];
     const DevEntryDyn& dy = dyn[blockIdx.x];
     const DevEntry& e = entries[dy.entry];
-    double scale = dy.weight;
-    if (!e.exact) {
-        const double jac = (e.mode == 0) ? simplex_volume(e.D, t_f - t_i)
-                                         : simplex_volume(e.d_before, t_w - t_i) * simplex_volume(e.d_after, t_f - t_w);
-        const double dir = (e.order & 1) ? -1.0 : 1.0;   // (-i)^(2 order)
-        scale = dir * jac * dy.weight;
-    }
+    const double scale = entry_scale(e, dy, t_i, t_w, t_f);
     const size_t row0 = (size_t)dy.item0 * pitch, nrows = (size_t)dy.n_items * pitch;
     for (int s = 0; s < S; ++s) {
         double2 v = make_double2(0.0, 0.0);
@@ -616,7 +746,7 @@ template <bool REAL, bool PER_SAMPLE>
 static cudaError_t launch_scalar_t(const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(scalar_step_kernel<REAL, PER_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(scalar_step_kernel<REAL, PER_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }

@@ -66,12 +66,14 @@ class Solver:
         self.ctx = ctx if ctx is not None else lib.Context(device=device)
         self.payload = self.ctx.set_expansion(expansion)
         self._next_entry = 0
+        self._entries = {}       # (mode, order, n_pts_after, corr_idx) -> compiled entry, reused across calls
         self._n_corr_uploaded = len(expansion.corr_operators_mat)
 
     def refresh_model(self):
         """Re-upload after add_corr_operators (invalidates compiled entries, as in the ABI)."""
         self.payload = self.ctx.set_expansion(self.expansion)
         self._next_entry = 0
+        self._entries = {}
         self._n_corr_uploaded = len(self.expansion.corr_operators_mat)
 
     def upload_P(self, first=0, count=None):
@@ -79,17 +81,30 @@ class Solver:
         self.ctx.set_P(first, self.expansion.P[first:first + count])
 
     def make_entry(self, mode, order, n_pts_after, N_samples, rand_params=None, corr_idx=0):
+        """TopologiesInputData for one (order, n_pts_after): the topology list is generated and compiled
+        against the model once per Solver (the reference rebuilds both on every call,
+        src/inchworm.jl:380,431-447 and :165)."""
+        key = (mode, order, n_pts_after, corr_idx)
+        if key in self._entries:
+            eid, tops = self._entries[key]
+            if eid is None:
+                return None
+            td = TopologiesInputData(order, n_pts_after, tops, N_samples, rand_params or RandomizationParams())
+            td.entry_id = eid
+            return td
         if mode == MODE_BARE:
             tops = get_topologies_at_order(order)
         else:
             tops = get_topologies_at_order(order, n_pts_after if order > 0 else 0, mode == MODE_CORR) \
                 if order > 0 else get_topologies_at_order(0, 0, mode == MODE_CORR)
         if len(tops[1]) == 0:
+            self._entries[key] = (None, tops)
             return None
         td = TopologiesInputData(order, n_pts_after, tops, N_samples, rand_params or RandomizationParams())
         td.entry_id = self._next_entry
         self._next_entry += 1
         self.ctx.set_topologies(td.entry_id, mode, order, n_pts_after, tops[0], tops[1], corr_idx=corr_idx)
+        self._entries[key] = (td.entry_id, tops)
         return td
 
     def eval_entries(self, t_i, t_w, t_f, top_data):
@@ -156,18 +171,22 @@ def _bold_entries(solver, orders, N_samples, rand_params, n_pts_after_max):
 
 
 def inchworm(expansion, grid, orders, orders_bare, N_samples, n_pts_after_max=None,
-             rand_params=None, solver=None, device_resident=False):
+             rand_params=None, solver=None, device_resident=None):
     """inchworm!(expansion, grid, orders, orders_bare, N_samples; ...) (src/inchworm.jl:332-498).
     Results are written into `expansion.P`; returns (P_orders, P_orders_std): dicts
     order -> [n_tau, bsize] arrays of order-resolved contributions.
 
     device_resident=True runs the whole loop inside the library (qiw_inchworm_run): set_ppgf! and
     normalize! happen on the GPU between steps, with no host round trip.  It requires the default
-    RandomizationParams (one unscrambled or one fixed scrambled sequence reused at every step)."""
+    RandomizationParams (one unscrambled sequence reused at every step) and is chosen automatically
+    in that case (device_resident=None); device_resident=False forces the host-stepped loop, one
+    qiw_eval per step, which is what the Julia shim does."""
     assert N_samples == 0 or (N_samples & (N_samples - 1)) == 0, "N_samples must be a power of 2"
     rand_params = rand_params or RandomizationParams()
     assert rand_params.N_seqs > 0
     solver = solver or Solver(expansion)
+    if device_resident is None:
+        device_resident = rand_params.rng is None and rand_params.N_seqs == 1
     n_tau = grid.n_tau
     orders, orders_bare = list(orders), list(orders_bare)
     P_orders = {o: np.zeros((n_tau, solver.ctx.bsize), dtype=complex) for o in set(orders) | set(orders_bare)}

@@ -16,6 +16,7 @@ HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "qinchworm.h")
 MODE_BARE, MODE_BOLD, MODE_CORR = 0, 1, 2
 DEVICE_CURRENT, DEVICE_NONE = -1, -2
 UNIQUE_ID_BYTES = 128
+PEER_HANDLE_BYTES = 64
 
 
 class QiwError(RuntimeError):
@@ -80,6 +81,8 @@ _SIGNATURES = {
     "qiw_comm_unique_id": (C.c_int, [u8p]),
     "qiw_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, u8p]),
     "qiw_comm_destroy": (C.c_int, [C.c_void_p]),
+    "qiw_peer_handle": (C.c_int, [C.c_void_p, u8p]),
+    "qiw_peer_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, u8p]),
     "qiw_measure_fp64_peak": (C.c_int, [C.c_void_p, f64p]),
 }
 
@@ -370,6 +373,16 @@ class Context:
     def comm_init(self, n_ranks, rank, unique_id):
         uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
         self._ck(self.L.qiw_comm_init(self.h, n_ranks, rank, _ptr(uid, u8p)))
+
+    def peer_handle(self):
+        """Allocate this rank's mailbox and return its CUDA IPC handle (64 bytes)."""
+        buf = np.zeros(PEER_HANDLE_BYTES, dtype=np.uint8)
+        self._ck(self.L.qiw_peer_handle(self.h, _ptr(buf, u8p)))
+        return buf
+
+    def peer_init(self, n_ranks, rank, handles):
+        h = np.ascontiguousarray(handles, dtype=np.uint8).reshape(n_ranks * PEER_HANDLE_BYTES)
+        self._ck(self.L.qiw_peer_init(self.h, n_ranks, rank, _ptr(h, u8p)))
 
     def measure_fp64_peak(self):
         v = C.c_double(0)

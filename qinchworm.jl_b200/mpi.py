@@ -46,15 +46,34 @@ def ismaster():
     return world()[0] == 0
 
 
-def init_comm(ctx):
-    """Create the NCCL communicator of a lib.Context across the torch.distributed world."""
-    import torch
+def init_comm(ctx, peer=None):
+    """Join a lib.Context to the job: the NCCL communicator (fallback path) and, unless disabled
+    (peer=False or QIW_NO_PEER=1), the peer-memory mailboxes that let the step kernel perform the
+    all-reduce inside its own tail over NVLink.  Returns "peer", "nccl" or "single"."""
     import torch.distributed as dist
     from . import lib
     rank, size = world()
     if size == 1:
-        return
+        return "single"
     uid = lib.comm_unique_id() if rank == 0 else np.zeros(lib.UNIQUE_ID_BYTES, dtype=np.uint8)
     box = [uid.tobytes()]
     dist.broadcast_object_list(box, src=0)
     ctx.comm_init(size, rank, np.frombuffer(box[0], dtype=np.uint8))
+    if peer is None:
+        peer = os.environ.get("QIW_NO_PEER", "0") != "1"
+    if not peer:
+        return "nccl"
+    mine = ctx.peer_handle().tobytes()
+    allh = [None] * size
+    dist.all_gather_object(allh, mine)
+    ok = 1
+    try:
+        ctx.peer_init(size, rank, np.frombuffer(b"".join(allh), dtype=np.uint8))
+    except lib.QiwError:
+        ok = 0
+    flags = [None] * size
+    dist.all_gather_object(flags, ok)
+    if not all(flags):
+        raise RuntimeError("peer-memory mailboxes could not be mapped on every rank (no P2P access?); "
+                           "run with QIW_NO_PEER=1 to use the NCCL all-reduce")
+    return "peer"

@@ -112,7 +112,7 @@ def test_inchworm_golden(gpu_ctx, qlib):
     G = load_golden("inchworm_h5.json")
     ex, grid, f = models.single_level(n_tau=20, spline=True)
     solver = Solver(ex, ctx=gpu_ctx)
-    inchworm(ex, grid, range(0, 4), range(0, 3), 2 ** 8, solver=solver)
+    inchworm(ex, grid, range(0, 4), range(0, 3), 2 ** 8, solver=solver, device_resident=False)   # host-stepped loop
     assert relerr(ex.P[:, 1], G["/inchworm/P/1"].ravel()) < RTOL
     assert relerr(ex.P[:, 0], G["/inchworm/P/2"].ravel()) < RTOL
     add_corr_operators(ex, (f.c("0"), f.c_dag("0")))
@@ -142,7 +142,7 @@ def test_inchworm_device_resident(gpu_ctx, qlib):
     assert relerr(ex.P[:, 1], G["/inchworm/P/1"].ravel()) < RTOL
     assert relerr(ex.P[:, 0], G["/inchworm/P/2"].ravel()) < RTOL
     ex2, grid2, _ = models.single_level(n_tau=20, spline=True)
-    Po2, _ = inchworm(ex2, grid2, range(0, 4), range(0, 3), 2 ** 8, solver=Solver(ex2, ctx=gpu_ctx))
+    Po2, _ = inchworm(ex2, grid2, range(0, 4), range(0, 3), 2 ** 8, solver=Solver(ex2, ctx=gpu_ctx), device_resident=False)
     assert relerr(ex.P, ex2.P) < RTOL
     for o in Po:
         assert relerr(Po[o], Po2[o]) < RTOL
@@ -268,3 +268,19 @@ def test_real_and_complex_arithmetic_agree(gpu_ctx, qlib, oracle_lib, monkeypatc
     got = gpu_ctx.eval(0.0, tau[20], tau[21], ids, N)
     ref2 = o2.eval(0.0, tau[20], tau[21], ids, N)
     assert relerr(got, ref2) < RTOL
+
+
+def test_multi_gpu_allreduce(qlib):
+    """One rank per GPU (torchrun, 2 ranks): sharded Sobol ranges + the all-reduce (peer-memory exchange
+    inside the step kernel, and the NCCL fallback) against the single-process oracle.  Needs 2 GPUs."""
+    import subprocess
+    import sys
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(here, "multigpu_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "multigpu_check OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
