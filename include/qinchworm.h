@@ -174,6 +174,15 @@ int qiw_eval(qiw_context* ctx, double t_i, double t_w, double t_f, int32_t n_ent
              const int32_t* entry_ids, const uint32_t* sobol_m, const uint32_t* sobol_x0,
              uint64_t N_total, double* out);
 
+/* Batched form of qiw_eval: the same entries at `n_times` independent time triples
+ * times[n_times][3] = (t_i, t_w, t_f) in ONE launch; out[n_times][n_entries] packed block vectors.
+ * Replaces the loop over grid points of the correlator_2p driver (src/inchworm.jl:1035-1046), whose
+ * (operator pair, tau) evaluations are independent because P is final.  The same Sobol sequence is
+ * used for every triple (RandomizationParams() default). */
+int qiw_eval_batch(qiw_context* ctx, int32_t n_times, const double* times, int32_t n_entries,
+                   const int32_t* entry_ids, const uint32_t* sobol_m, const uint32_t* sobol_x0,
+                   uint64_t N_total, double* out);
+
 /* Same, but evaluates only Sobol indices [start, start+count) and does NOT all-reduce: the
  * rank-local partial sum (already divided by N_total).  Used by hosts that own the collective. */
 int qiw_eval_range(qiw_context* ctx, double t_i, double t_w, double t_f, int32_t n_entries,

@@ -164,7 +164,9 @@ struct qiw_context {
     DevBuf<const uint32_t*> dTreeOffPtr;
     DevBuf<int> dNTrees;
     DevBuf<unsigned long long> dTrace;
-    DevBuf<unsigned int> dCounter;   // arrival counter of the step kernel's fused tail (self-resetting)
+    DevBuf<unsigned int> dCounter;   // arrival counters of the step kernel's fused tail (self-resetting), one per time triple
+    DevBuf<double> dTimes3;          // batched evaluation: (t_i, t_w, t_f) triples
+    DevBuf<double2> dBatchPartials, dBatchOut;
     double2* hOut = nullptr;  // pinned
     size_t hOutCap = 0;
     std::vector<std::unique_ptr<Plan>> plans;
@@ -270,6 +272,7 @@ int qiw_destroy(qiw_context* ctx) {
     ctx->dPeerPtrs.release(); ctx->dPeerStatus.release();
     ctx->dP.release(); ctx->dE.release(); ctx->dDeltas.release(); ctx->dEntries.release();
     ctx->dPerSample.release(); ctx->dTimes.release(); ctx->dHist.release(); ctx->dDiag.release(); ctx->dTrace.release(); ctx->dCounter.release();
+    ctx->dTimes3.release(); ctx->dBatchPartials.release(); ctx->dBatchOut.release();
     ctx->dDim.release(); ctx->dBoff.release(); ctx->dEoff.release(); ctx->dOpTarget.release(); ctx->dOpOff.release();
     ctx->dPool.release(); ctx->dScratch.release(); ctx->dWordsPtr.release(); ctx->dTreeOffPtr.release(); ctx->dNTrees.release();
     for (auto& t : ctx->tables) { t.y.release(); t.M.release(); }
@@ -826,7 +829,8 @@ struct FinishArgs { int k_f = -1; int normalize = 0; double2* hist = nullptr; co
 // models, step kernel + reduction kernel.  Nothing is synchronised here.  Returns through
 // `finish_done` whether the P update was fused.
 static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, double t_f, const FinishArgs* fin = nullptr,
-                        bool* finish_done = nullptr, bool collective = false, bool* collective_done = nullptr) {
+                        bool* finish_done = nullptr, bool collective = false, bool* collective_done = nullptr,
+                        int n_times = 0) {
     if (finish_done) *finish_done = false;
     if (collective_done) *collective_done = false;
     const HostModel& m = ctx->model;
@@ -840,13 +844,20 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
     sp.partials = pl.d_partials.p;
     sp.finish_k_f = -1;
     if (m.scalar && !pl.explicit_mode) {
-        if (!ctx->dCounter.p) {
-            CK(ctx->dCounter.reserve(1));
-            CK(cudaMemsetAsync(ctx->dCounter.p, 0, sizeof(unsigned int), ctx->stream));
+        const size_t need = (size_t)std::max(n_times, 1);
+        if (ctx->dCounter.cap < need) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(ctx->dCounter.reserve(std::max<size_t>(need, 1024)));
+            CK(cudaMemsetAsync(ctx->dCounter.p, 0, ctx->dCounter.cap * sizeof(unsigned int), ctx->stream));
         }
         sp.done_counter = ctx->dCounter.p;
         sp.n_call_entries = (int)pl.ids.size();
         sp.out = pl.d_out.p;
+        if (n_times > 0) {   // batched: per-triple partial rows and results, times read on the device
+            sp.times_dev = ctx->dTimes3.p;
+            sp.partials = ctx->dBatchPartials.p;
+            sp.out = ctx->dBatchOut.p;
+        }
         bool exchange_fused = false;
         if (collective && ctx->peer_ready && ctx->n_ranks > 1 && pl.ids.size() * (size_t)m.bsize * sizeof(double2) <= kPeerSlotBytes) {
             sp.peer_ranks = ctx->n_ranks; sp.peer_rank = ctx->rank; sp.peer_seq = ++ctx->peer_seq;
@@ -898,7 +909,7 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         gp.spb = g.spb[real];
         gp.spb_log2 = 0;
         while ((1 << gp.spb_log2) < gp.spb) ++gp.spb_log2;
-        dim3 grid((unsigned)pl.pitch, (unsigned)g.n_items);
+        dim3 grid((unsigned)pl.pitch, (unsigned)g.n_items, (unsigned)std::max(n_times, 1));
         {
             ProfScope ps(ctx, real ? 1 : 0);
             CK(launch_scalar_step(real != 0, gp, grid, ctx->warps * 32, g.smem[real], ctx->stream));
@@ -938,7 +949,10 @@ static int mark_ucache_valid(qiw_context* ctx, Plan& pl) {
 }
 
 static int nccl_allreduce(qiw_context* ctx, double2* buf, size_t n_complex) {
-    if (!ctx->comm) return QIW_OK;
+    if (!ctx->comm) {
+        if (ctx->n_ranks > 1) return fail(ctx, QIW_ERR_NCCL, "this call needs the NCCL communicator (qiw_comm_init) in addition to the peer mailboxes");
+        return QIW_OK;
+    }
     ProfScope ps(ctx, 6);
     int nrc = g_nccl.AllReduce(buf, buf, n_complex * 2, kNcclDouble, kNcclSum, ctx->comm, ctx->stream);
     if (nrc) return fail(ctx, QIW_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "error"));
@@ -1043,6 +1057,55 @@ int qiw_eval(qiw_context* ctx, double t_i, double t_w, double t_f, int32_t n_ent
     uint64_t start = 0, count = N_total;
     rank_sub_range(N_total, ctx->n_ranks, ctx->rank, &start, &count);
     return eval_scalar(ctx, t_i, t_w, t_f, n_entries, ids, sobol_m, sobol_x0, start, count, N_total, true, out, nullptr, 0);
+}
+
+int qiw_eval_batch(qiw_context* ctx, int32_t n_times, const double* times, int32_t n_entries, const int32_t* ids,
+                   const uint32_t* sobol_m, const uint32_t* sobol_x0, uint64_t N_total, double* out) {
+    int rc = check_entries(ctx, n_entries, ids, "qiw_eval_batch");
+    if (rc) return rc;
+    if (!out || !times || n_times <= 0 || n_times > 65535 || N_total == 0 || N_total > 0xFFFFFFFFull)
+        return fail(ctx, QIW_ERR_BAD_ARG, "qiw_eval_batch: bad argument");
+    cudaSetDevice(ctx->device);
+    const HostModel& m = ctx->model;
+    if (!m.scalar) {   // block models: one launch per triple (the block kernel has no batched form yet)
+        for (int z = 0; z < n_times; ++z) {
+            rc = qiw_eval(ctx, times[3 * z], times[3 * z + 1], times[3 * z + 2], n_entries, ids, sobol_m, sobol_x0, N_total,
+                          out + (size_t)z * n_entries * m.bsize * 2);
+            if (rc) return rc;
+        }
+        return QIW_OK;
+    }
+    uint64_t start = 0, count = N_total;
+    rank_sub_range(N_total, ctx->n_ranks, ctx->rank, &start, &count);
+    rc = sync_static_tables(ctx);
+    if (rc) return rc;
+    Plan* plp = nullptr;
+    rc = get_plan(ctx, n_entries, ids, count, false, &plp);
+    if (rc) return rc;
+    Plan& pl = *plp;
+    rc = stage_call(ctx, pl, sobol_m, sobol_x0, start, count, N_total, true);
+    if (rc) return rc;
+    const size_t n_out = (size_t)n_times * n_entries * m.bsize;
+    CK(ctx->dTimes3.upload(times, (size_t)n_times * 3, ctx->stream));
+    CK(ctx->dBatchPartials.reserve((size_t)n_times * pl.partial_rows * m.bsize));
+    CK(ctx->dBatchOut.reserve(n_out));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    rc = enqueue_step(ctx, pl, 0.0, 0.0, 0.0, nullptr, nullptr, false, nullptr, n_times);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    rc = mark_ucache_valid(ctx, pl);
+    if (rc) return rc;
+    rc = nccl_allreduce(ctx, ctx->dBatchOut.p, n_out);   // one collective for the whole batch
+    if (rc) return rc;
+    rc = ensure_host_out(ctx, n_out);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->hOut, ctx->dBatchOut.p, n_out * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_ms = ms;
+    memcpy(out, ctx->hOut, n_out * sizeof(double2));
+    return QIW_OK;
 }
 
 int qiw_eval_at_times(qiw_context* ctx, int32_t entry_id, double t_i, double t_w, double t_f, int32_t n_samples,

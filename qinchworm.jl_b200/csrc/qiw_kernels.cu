@@ -365,8 +365,11 @@ __device__ __forceinline__ double entry_scale(const DevEntry& e, const DevEntryD
 // Executed by the last CTA of a step launch: every (entry, sector) sum runs over the partial rows in
 // fixed order, so the result does not depend on which CTA happens to be last.  Optionally followed by
 // set_ppgf!(P, tau_f, result) and normalize!(P, tau_f) (src/ppgf.jl:495-504,646-668).
-__device__ void fused_tail(const StepParams& p, double t_i, double t_w, double t_f, int pitch) {
+__device__ void fused_tail(const StepParams& pp, double t_i, double t_w, double t_f, int pitch) {
+    StepParams p = pp;
     const int S = p.S, n_out = p.n_call_entries * S;
+    p.partials += (size_t)blockIdx.z * gridDim.y * gridDim.x * S;   // this time triple's rows and results
+    p.out += (size_t)blockIdx.z * n_out;
     for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
         const int i = o / S, s = o - i * S;
         const DevEntryDyn& dy = p.dyn[i];
@@ -479,7 +482,8 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
         coefs_s[c] = (c < e.n_coefs) ? N::coef_of(e.coefs[c]) : N::zero();   // last: padding records
 
     double t_i = p.t_i, t_w = p.t_w, t_f = p.t_f;
-    if (p.times_dev) { t_i = p.times_dev[0]; t_w = p.times_dev[1]; t_f = p.times_dev[2]; }
+    // batched evaluation: blockIdx.z selects one (t_i, t_w, t_f) triple of the call
+    if (p.times_dev) { const double* tz = p.times_dev + 3 * blockIdx.z; t_i = tz[0]; t_w = tz[1]; t_f = tz[2]; }
     const double lo_after = (e.mode == 0) ? t_i : t_w, len_after = t_f - lo_after;
     const double len_before = t_w - t_i;
 
@@ -641,7 +645,7 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
     if ((int)threadIdx.x < S) {
         double2 v = make_double2(0.0, 0.0);
         for (int w2 = 0; w2 < nw; ++w2) v = cadd(v, red[threadIdx.x * nw + w2]);
-        p.partials[((size_t)it.partial0 * gridDim.x + blockIdx.x) * S + threadIdx.x] = v;
+        p.partials[((size_t)blockIdx.z * gridDim.y * gridDim.x + (size_t)it.partial0 * gridDim.x + blockIdx.x) * S + threadIdx.x] = v;
     }
     if (trace && threadIdx.x == 0) trace[3] = clock64();
 
@@ -651,14 +655,14 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) {
-            const unsigned ticket = atomicAdd(p.done_counter, 1u);
+            const unsigned ticket = atomicAdd(p.done_counter + blockIdx.z, 1u);
             is_last = (ticket == gridDim.x * gridDim.y - 1u) ? 1 : 0;
         }
         __syncthreads();
         if (!is_last) return;
         __threadfence();
         fused_tail(p, t_i, t_w, t_f, (int)gridDim.x);
-        if (threadIdx.x == 0) *p.done_counter = 0u;
+        if (threadIdx.x == 0) p.done_counter[blockIdx.z] = 0u;
     }
 }
 

@@ -225,9 +225,10 @@ def inchworm(expansion, grid, orders, orders_bare, N_samples, n_pts_after_max=No
     return P_orders, P_orders_std
 
 
-def correlator_2p(expansion, grid, orders, N_samples, rand_params=None, solver=None, return_std=False):
+def correlator_2p(expansion, grid, orders, N_samples, rand_params=None, solver=None, return_std=False, batch=True):
     """correlator_2p(expansion, grid, orders, N_samples) (src/inchworm.jl:918-1086): one array
-    [n_tau] per registered pair in expansion.corr_operators."""
+    [n_tau] per registered pair in expansion.corr_operators.  With the default RandomizationParams all grid
+    points of a pair are evaluated by one qiw_eval_batch launch (batch=False: one qiw_eval per point)."""
     assert N_samples == 0 or (N_samples & (N_samples - 1)) == 0
     rand_params = rand_params or RandomizationParams()
     solver = solver or Solver(expansion)
@@ -247,7 +248,10 @@ def correlator_2p(expansion, grid, orders, N_samples, rand_params=None, solver=N
                     top_data.append(td)
         g = np.zeros(n_tau, dtype=complex)
         g_std = np.zeros(n_tau, dtype=complex)
+        batched = batch and rand_params.rng is None and rand_params.N_seqs == 1 and n_tau > 1 and top_data
         for k in range(n_tau):
+            if batched and k > 0:
+                break
             tds = top_data
             if k == 0:  # only order 0 contributes at tau_A = tau_B (:1013-1024)
                 tds = top_data[:1] if top_data and top_data[0].order == 0 else []
@@ -256,6 +260,12 @@ def correlator_2p(expansion, grid, orders, N_samples, rand_params=None, solver=N
             mean, std = solver.eval_entries(grid.tau[0], grid.tau[k], grid.tau[-1], tds)
             g[k] = mean[:, diag].sum() / Z      # tr(...) / partition_function (:869,889)
             g_std[k] = std[:, diag].sum() / Z
+        if batched:
+            # every grid point tau_k, k >= 1, in ONE launch: the (pair, tau) evaluations are independent (:995-1046)
+            times = np.array([[grid.tau[0], grid.tau[k], grid.tau[-1]] for k in range(1, n_tau)])
+            res = solver.ctx.eval_batch(times, [td.entry_id for td in top_data], N_samples)
+            g[1:] = res[:, :, diag].sum(axis=(1, 2)) / Z
+            g_std[1:] = np.nan if any(td.order > 0 for td in top_data) else 0.0   # std of one sequence (src/randomization.jl:99)
         out.append(g)
         out_std.append(g_std)
     return (out, out_std) if return_std else out

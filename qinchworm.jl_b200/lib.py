@@ -64,6 +64,7 @@ _SIGNATURES = {
     "qiw_entry_records": (C.c_int, [C.c_void_p, C.c_int32, i32p, u32p, C.POINTER(C.c_uint16)]),
     "qiw_eval": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int32, i32p, u32p, u32p,
                            C.c_uint64, f64p]),
+    "qiw_eval_batch": (C.c_int, [C.c_void_p, C.c_int32, f64p, C.c_int32, i32p, u32p, u32p, C.c_uint64, f64p]),
     "qiw_eval_range": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int32, i32p, u32p, u32p,
                                  C.c_uint64, C.c_uint64, C.c_uint64, f64p]),
     "qiw_eval_at_times": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32,
@@ -311,6 +312,16 @@ class Context:
         _m, _x, pm, px = self._sobol_args(ids, sobol)
         self._ck(self.L.qiw_eval(self.h, t_i, t_w, t_f, len(ids), _ptr(ids, i32p), pm, px, N_total,
                                  _ptr(out.view(np.float64), f64p)))
+        return out
+
+    def eval_batch(self, times, entry_ids, N_total, sobol=None):
+        """qiw_eval_batch: times[n_times, 3] = (t_i, t_w, t_f); returns [n_times, n_entries, bsize]."""
+        ids = np.ascontiguousarray(entry_ids, dtype=np.int32)
+        times = np.ascontiguousarray(times, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros((times.shape[0], len(ids), self.bsize), dtype=np.complex128)
+        _m, _x, pm, px = self._sobol_args(ids, sobol)
+        self._ck(self.L.qiw_eval_batch(self.h, times.shape[0], _ptr(times, f64p), len(ids), _ptr(ids, i32p), pm, px,
+                                       N_total, _ptr(out.view(np.float64), f64p)))
         return out
 
     def eval_range(self, t_i, t_w, t_f, entry_ids, N_total, start, count, sobol=None):

@@ -284,3 +284,17 @@ def test_multi_gpu_allreduce(qlib):
                           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(here, "multigpu_check.py")],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "multigpu_check OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+def test_correlator_batched_vs_stepped(gpu_ctx, qlib, oracle_lib):
+    """bench/bethe_gf_convergence (C2): correlator_2p with all grid points in one qiw_eval_batch launch equals
+    the point-by-point evaluation and the oracle's driver."""
+    from qinchworm_b200.inchworm import Solver, correlator_2p, inchworm
+    ex, grid, f = models.bethe_two_state(n_tau=24)
+    solver = Solver(ex, ctx=gpu_ctx)
+    inchworm(ex, grid, range(0, 4), range(0, 4), 2 ** 8, solver=solver)
+    g_b = correlator_2p(ex, grid, range(0, 4), 2 ** 8, solver=solver)[0]
+    g_s = correlator_2p(ex, grid, range(0, 4), 2 ** 8, solver=solver, batch=False)[0]
+    assert relerr(g_b, g_s) < 1e-13
+    ref = oracle_lib.correlator_2p(ex.flatten(), ex.P, range(0, 4), 2 ** 8)
+    assert relerr(g_b, ref) < RTOL
