@@ -1,0 +1,16 @@
+#!/bin/bash
+# Round-1 profiling pass (run on the GPU box through gpurun; outputs land in gpurun_out/ and the
+# summaries are copied into profiles/ by hand).  Numbers printed by runs under ncu are not bench values.
+set -x
+TAG=${1:-r1}
+# 1. launch list of the bench command (per-launch durations, cold-cache and serialised)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_${TAG}.csv \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
+# 2. full capture of the dominant kernel inside the C1 run (N = 2^10, one bold step in the middle of the run)
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:scalar_step_kernel -s 120 -c 1 \
+    -o gpurun_out/ncu_${TAG}_c1_step -f python profiles/prof_c1.py 200 1024 1 > gpurun_out/ncu_${TAG}_c1.log 2>&1
+# 3. the same kernel at a sample count that fills the machine (N = 2^17, orders 0:4) and at orders 0:6
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:scalar_step_kernel -s 6 -c 1 \
+    -o gpurun_out/ncu_${TAG}_o4_bigN -f python profiles/throughput.py 4 131072 > gpurun_out/ncu_${TAG}_o4.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:scalar_step_kernel -s 6 -c 1 \
+    -o gpurun_out/ncu_${TAG}_o6 -f python profiles/throughput.py 6 16384 > gpurun_out/ncu_${TAG}_o6.log 2>&1
