@@ -26,6 +26,8 @@ cudaError_t launch_sobol_points(int D, const uint32_t* m, const uint32_t* x0, un
                                 unsigned long long count, uint32_t* out, cudaStream_t st);
 cudaError_t launch_dfma_peak(double* out, int blocks, int iters, cudaStream_t st);
 cudaError_t launch_block_step(const StepParams& p, const BlockParams& bp, dim3 grid, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_block_walk(const StepParams& p, const BlockParams& bp, const BlockWalkParams& wp, dim3 grid, int threads,
+                              size_t smem, cudaStream_t st);
 }  // namespace qiw
 
 using namespace qiw;
@@ -91,6 +93,7 @@ struct EntryDev {
     DevBuf<uint16_t> segdef;
     bool imag_coefs = false;     // every folded coefficient is purely imaginary (real-mode precondition)
     DevBuf<uint64_t> words;      // block models: tree word stream
+    DevBuf<uint4> xwords;        // block models: expanded words of the real-arithmetic walker
     DevBuf<uint32_t> tree_off;
     DevBuf<double2> coefs;
     DevBuf<int4> dslots;
@@ -121,6 +124,9 @@ struct Plan {   // launch plan of one qiw_eval call shape, cached
     int pitch = 1;
     int block_threads = 0;                 // block models: threads per CTA
     size_t scratch_per_thread = 0;
+    bool block_real = false;               // block models: planned for the real-arithmetic tree replay
+    DevBuf<int> d_bounds;                  // [n_items][warps + 1] tree ranges (block_walk_kernel)
+    int bw_warps = 0, bw_max_sp = 0, bw_nI = 0, bw_nD = 0;
     DevBuf<uint32_t> d_sobol;
     std::vector<size_t> sobol_off;         // per call entry, offset into d_sobol
     std::vector<uint32_t> h_sobol;
@@ -160,8 +166,11 @@ struct qiw_context {
     DevBuf<int> dDim, dBoff, dEoff, dOpTarget;
     DevBuf<long long> dOpOff;
     DevBuf<double2> dPool, dScratch;
+    DevBuf<double> dPoolRe;
+    bool pool_real = false;
     DevBuf<const uint64_t*> dWordsPtr;
     DevBuf<const uint32_t*> dTreeOffPtr;
+    DevBuf<const uint4*> dXWordsPtr;
     DevBuf<int> dNTrees;
     DevBuf<unsigned long long> dTrace;
     DevBuf<unsigned int> dCounter;   // arrival counters of the step kernel's fused tail (self-resetting), one per time triple
@@ -274,10 +283,10 @@ int qiw_destroy(qiw_context* ctx) {
     ctx->dPerSample.release(); ctx->dTimes.release(); ctx->dHist.release(); ctx->dDiag.release(); ctx->dTrace.release(); ctx->dCounter.release();
     ctx->dTimes3.release(); ctx->dBatchPartials.release(); ctx->dBatchOut.release();
     ctx->dDim.release(); ctx->dBoff.release(); ctx->dEoff.release(); ctx->dOpTarget.release(); ctx->dOpOff.release();
-    ctx->dPool.release(); ctx->dScratch.release(); ctx->dWordsPtr.release(); ctx->dTreeOffPtr.release(); ctx->dNTrees.release();
+    ctx->dPool.release(); ctx->dPoolRe.release(); ctx->dScratch.release(); ctx->dWordsPtr.release(); ctx->dTreeOffPtr.release(); ctx->dXWordsPtr.release(); ctx->dNTrees.release();
     for (auto& t : ctx->tables) { t.y.release(); t.M.release(); }
     for (auto& e : ctx->entries)
-        if (e) { e->records.release(); e->segdef.release(); e->words.release(); e->tree_off.release(); e->coefs.release(); e->dslots.release(); e->sobol.release(); }
+        if (e) { e->records.release(); e->segdef.release(); e->words.release(); e->xwords.release(); e->tree_off.release(); e->coefs.release(); e->dslots.release(); e->sobol.release(); }
     for (auto& pl : ctx->plans) release_plan(*pl);
     ctx->plans.clear();
     if (ctx->hOut) cudaFreeHost(ctx->hOut);
@@ -346,6 +355,10 @@ int qiw_set_model(qiw_context* ctx, int32_t S, const int32_t* dims, const double
         std::vector<long long> off64(m.op_off.begin(), m.op_off.end());
         CK(ctx->dOpOff.upload(off64.data(), off64.size(), ctx->stream));
         CK(ctx->dPool.upload((const double2*)m.pool.data(), m.pool.size(), ctx->stream));
+        std::vector<double> pre(std::max<size_t>(m.pool.size(), 1), 0.0);
+        ctx->pool_real = true;
+        for (size_t k = 0; k < m.pool.size(); ++k) { pre[k] = m.pool[k].real(); if (m.pool[k].imag() != 0.0) ctx->pool_real = false; }
+        CK(ctx->dPoolRe.upload(pre.data(), pre.size(), ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     if (m.maxdim > 4) return fail(ctx, QIW_ERR_UNSUPPORTED, "qiw_set_model: sector blocks larger than 4x4 are not supported");
@@ -461,6 +474,36 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
     }
     if (!ctx->model.scalar) {
         CK(ed.words.upload(pr.words.data(), pr.words.size(), ctx->stream));
+        {   // expanded words: everything the walker needs about an edge, resolved against the model here
+            const HostModel& hm = ctx->model;
+            std::vector<uint4> xw(pr.words.size(), make_uint4(0, 0, 0, 0));
+            std::vector<char> is_root(pr.words.size(), 0);
+            for (size_t t = 0; t + 1 < pr.tree_off.size(); ++t) is_root[pr.tree_off[t]] = 1;
+            const size_t n_real = pr.tree_off.empty() ? 0 : pr.tree_off.back();
+            for (size_t k = 0; k < n_real; ++k) {
+                const uint64_t w = pr.words[k];
+                const uint32_t sA = (uint32_t)w & 0xFFFu, sB = ((uint32_t)w >> 12) & 0xFFFu, nc = ((uint32_t)w >> 24) & 0xFFu;
+                const uint32_t aux = (uint32_t)(w >> 32) & 0xFFFFu;
+                const int op = (int)((w >> 48) & 0xFFF) - 1;
+                uint4 x;
+                if (is_root[k]) {   // slotA = sector after the node at position 1, aux = initial sector
+                    const int s_init = (int)aux, s_next = (int)sA;
+                    x.x = (uint32_t)hm.dim[s_init] | ((uint32_t)hm.dim[s_next] << 4) | ((op >= 0 ? 1u : 0u) << 8) | (nc << 16);
+                    x.y = 0;
+                    x.z = op >= 0 ? (uint32_t)hm.op_off[(size_t)op * hm.S + s_init] : 0u;
+                    x.w = (uint32_t)hm.boff[s_init];
+                } else {
+                    const int s = (int)sA;
+                    const int tgt = op >= 0 ? hm.target(op, s) : s;
+                    x.x = (uint32_t)hm.dim[s] | ((uint32_t)hm.dim[tgt] << 4) | ((op >= 0 ? 1u : 0u) << 8) | (nc << 16);
+                    x.y = (uint32_t)hm.boff[s] | ((sB ? (sB - (uint32_t)pr.nP + 1u) : 0u) << 16);
+                    x.z = op >= 0 ? (uint32_t)hm.op_off[(size_t)op * hm.S + s] : 0u;
+                    x.w = aux;
+                }
+                xw[k] = x;
+            }
+            CK(ed.xwords.upload(xw.data(), xw.size(), ctx->stream));
+        }
         CK(ed.tree_off.upload(pr.tree_off.data(), pr.tree_off.size(), ctx->stream));
     }
     std::vector<double2> cf(std::max<size_t>(pr.coefs.size(), 1));
@@ -568,14 +611,16 @@ static int sync_static_tables(qiw_context* ctx) {
         if (!ctx->model.scalar) {
             std::vector<const uint64_t*> wp(de.size(), nullptr);
             std::vector<const uint32_t*> tp(de.size(), nullptr);
+            std::vector<const uint4*> xp(de.size(), nullptr);
             std::vector<int> nt(de.size(), 0);
             for (size_t i = 0; i < ctx->entries.size(); ++i) {
                 if (!ctx->entries[i] || !ctx->entries[i]->valid) continue;
-                wp[i] = ctx->entries[i]->words.p; tp[i] = ctx->entries[i]->tree_off.p;
+                wp[i] = ctx->entries[i]->words.p; tp[i] = ctx->entries[i]->tree_off.p; xp[i] = ctx->entries[i]->xwords.p;
                 nt[i] = (int)ctx->entries[i]->prog.tree_off.size() - 1;
             }
             CK(ctx->dWordsPtr.upload(wp.data(), wp.size(), ctx->stream));
             CK(ctx->dTreeOffPtr.upload(tp.data(), tp.size(), ctx->stream));
+            CK(ctx->dXWordsPtr.upload(xp.data(), xp.size(), ctx->stream));
             CK(ctx->dNTrees.upload(nt.data(), nt.size(), ctx->stream));
         }
         CK(cudaStreamSynchronize(ctx->stream));
@@ -585,7 +630,7 @@ static int sync_static_tables(qiw_context* ctx) {
 }
 
 static void release_plan(Plan& pl) {
-    pl.d_items.release(); pl.d_sobol.release(); pl.d_ucache.release();
+    pl.d_items.release(); pl.d_sobol.release(); pl.d_ucache.release(); pl.d_bounds.release();
     pl.d_dyn.release(); pl.d_partials.release(); pl.d_out.release();
 }
 
@@ -593,7 +638,7 @@ static void release_plan(Plan& pl) {
 // purely imaginary, the folded coefficients purely imaginary.  QIW_FORCE_COMPLEX=1
 // disables it (tests compare the two modes).
 static bool real_mode_possible(qiw_context* ctx, int n_entries, const int32_t* ids) {
-    if (!ctx->model.scalar) return false;
+    if (!ctx->model.scalar && !ctx->pool_real) return false;
     if (const char* env = getenv("QIW_FORCE_COMPLEX")) if (env[0] == '1') return false;
     for (auto& t : ctx->tables) if (t.n > 0 && !t.imag_only) return false;
     for (uint8_t c : ctx->p_row_complex) if (c) return false;
@@ -607,7 +652,8 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
     for (auto& up : ctx->plans) {
         Plan& c = *up;
         if (c.count == count && c.explicit_mode == explicit_mode && (int)c.ids.size() == n_entries &&
-            std::equal(ids, ids + n_entries, c.ids.begin())) { *out = &c; return QIW_OK; }
+            std::equal(ids, ids + n_entries, c.ids.begin()) &&
+            (ctx->model.scalar || c.block_real == (!explicit_mode && real_mode_possible(ctx, n_entries, ids)))) { *out = &c; return QIW_OK; }
     }
     if (ctx->plans.size() >= 6) { release_plan(*ctx->plans.front()); ctx->plans.erase(ctx->plans.begin()); }
     std::unique_ptr<Plan> pl(new Plan());
@@ -617,8 +663,76 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
     const int S = ctx->model.S;
     int ndev_sm = 148;
     cudaDeviceGetAttribute(&ndev_sm, cudaDevAttrMultiProcessorCount, ctx->device);
-    if (!ctx->model.scalar) {
-        // Block models: one thread per (sample, chunk of trees); 64 samples per CTA.
+    if (!ctx->model.scalar && !explicit_mode && real_mode_possible(ctx, n_entries, ids)) {
+        // Block models, real arithmetic: CTA = (entry, 32 samples, group of tree chunks), W warps per CTA,
+        // every warp replays a contiguous range of the entry's trees of about equal cost (live edges).
+        pl->block_real = true;
+        const int bs = ctx->model.bsize;
+        int nI_max = 1, nD_max = 1, max_order = 0;
+        double total_cost = 0;
+        uint64_t n_sb = 1;
+        for (int i = 0; i < n_entries; ++i) {
+            const EntryProgram& p = ctx->entries[ids[i]]->prog;
+            nI_max = std::max(nI_max, p.n_nodes - 1);
+            nD_max = std::max(nD_max, (int)p.dslots.size());
+            max_order = std::max(max_order, p.order);
+            total_cost += (double)p.n_edges;
+            n_sb = std::max<uint64_t>(n_sb, ((p.order == 0 ? 1 : count) + 31) / 32);
+        }
+        const int max_sp = max_order + 2;
+        auto smem_of = [&](int Wn) {
+            return ((size_t)nI_max * bs * 32 + (size_t)nD_max * 32 + (size_t)Wn * bs + (size_t)Wn * max_sp * 16 * 32 +
+                    (size_t)Wn * max_sp * 32 + (size_t)(kDevMaxNodes + 1) * 32 + (size_t)kDevMaxDim * 32) * sizeof(double) +
+                   (32 + (size_t)Wn * max_sp * 4) * sizeof(int) + 64;
+        };
+        int Wn = 4;
+        while (Wn > 1 && smem_of(Wn) > (size_t)226 * 1024) --Wn;
+        if (smem_of(Wn) > (size_t)226 * 1024) return fail(ctx, QIW_ERR_UNSUPPORTED, "per-sample block tables exceed shared memory");
+        // CTA jobs: enough to fill the machine about four times over, proportional to the entries' cost
+        const double want_ctas = 4.0 * ndev_sm;
+        std::vector<int> bounds;
+        pl->item0.resize(n_entries); pl->n_items.resize(n_entries);
+        for (int i = 0; i < n_entries; ++i) {
+            const EntryProgram& p = ctx->entries[ids[i]]->prog;
+            const int n_trees = (int)p.tree_off.size() - 1;
+            int jobs = (int)std::ceil(want_ctas * (double)p.n_edges / std::max(total_cost, 1.0) / (double)n_sb);
+            jobs = std::max(1, std::min(jobs, (n_trees + Wn - 1) / Wn));
+            const int n_chunks = jobs * Wn;
+            // chunk boundaries at equal cumulative cost
+            std::vector<double> cum(n_trees + 1, 0.0);
+            for (int t = 0; t < n_trees; ++t) cum[t + 1] = cum[t] + (double)p.tree_cost[t] + 4.0;
+            pl->item0[i] = (int)pl->items.size();
+            int t_prev = 0;
+            for (int j = 0; j < jobs; ++j) {
+                WorkItem it;
+                it.entry = ids[i]; it.slot = i; it.chunk0 = j * Wn; it.n_chunks = Wn; it.n_chunks_total = n_chunks;
+                it.partial0 = (int)pl->items.size();
+                pl->items.push_back(it);
+                bounds.push_back(t_prev);
+                for (int w2 = 1; w2 <= Wn; ++w2) {
+                    const double target = cum[n_trees] * (double)(j * Wn + w2) / (double)n_chunks;
+                    int t_end = (int)(std::lower_bound(cum.begin(), cum.end(), target - 1e-9) - cum.begin());
+                    t_end = std::max(t_prev, std::min(t_end, n_trees));
+                    if (j == jobs - 1 && w2 == Wn) t_end = n_trees;
+                    bounds.push_back(t_end);
+                    t_prev = t_end;
+                }
+            }
+            pl->n_items[i] = jobs;
+        }
+        CK(pl->d_bounds.upload(bounds.data(), bounds.size(), ctx->stream));
+        Plan::Group g;
+        g.maxl = 0; g.item0 = 0; g.max_slots = 1; g.max_dslots = 1; g.max_coefs = 1; g.max_segdef = 1;
+        g.n_items = (int)pl->items.size();
+        g.smem[0] = g.smem[1] = smem_of(Wn);
+        g.spb[0] = g.spb[1] = 32;
+        pl->groups.push_back(g);
+        pl->max_sb = n_sb;
+        pl->block_threads = 0;
+        pl->bw_warps = Wn; pl->bw_max_sp = max_sp; pl->bw_nI = nI_max; pl->bw_nD = nD_max;
+    } else if (!ctx->model.scalar) {
+        // Block models, complex arithmetic (general fallback on the device) and per-sample evaluation:
+        // one thread per (sample, chunk of trees); 64 samples per CTA.
         const int TPB = 64;
         uint64_t n_sb_max = 1;
         for (int i = 0; i < n_entries; ++i) {
@@ -891,7 +1005,15 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         StepParams gp = sp;
         gp.items = pl.d_items.p;
         dim3 grid((unsigned)pl.pitch, (unsigned)pl.items.size());
-        {
+        if (pl.block_real) {
+            BlockWalkParams wp;
+            wp.pool_re = ctx->dPoolRe.p; wp.xwords = ctx->dXWordsPtr.p; wp.chunk_bounds = pl.d_bounds.p; wp.warps = pl.bw_warps; wp.max_sp = pl.bw_max_sp;
+            wp.nI_max = pl.bw_nI; wp.nD_max = pl.bw_nD;
+            ctx->last_real_mode = 1;
+            ProfScope ps(ctx, 7);
+            CK(launch_block_walk(gp, bp, wp, grid, pl.bw_warps * 32, pl.groups[0].smem[0], ctx->stream));
+        } else {
+            ctx->last_real_mode = 0;
             ProfScope ps(ctx, 7);
             CK(launch_block_step(gp, bp, grid, pl.block_threads, pl.groups[0].smem[0], ctx->stream));
         }
@@ -1204,7 +1326,7 @@ int qiw_inchworm_run(qiw_context* ctx, int32_t n_bare, const int32_t* bare_ids, 
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_ms = ms;
     // rows written in complex arithmetic may carry a real part: the next qiw_set_P re-examines them
-    if (!(m.scalar && ctx->last_real_mode)) for (int k = 1; k < n_tau; ++k) ctx->p_row_complex[k] = 1;
+    if (!ctx->last_real_mode) for (int k = 1; k < n_tau; ++k) ctx->p_row_complex[k] = 1;
     if (coll_done) return check_peer_status(ctx);
     return QIW_OK;
 }

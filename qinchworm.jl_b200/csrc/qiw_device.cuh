@@ -127,6 +127,15 @@ struct DevModel {
     int S, bsize, maxdim, n_ops;
 };
 
+// Real-arithmetic tree replay for block models (block_walk_kernel).
+struct BlockWalkParams {
+    const double* pool_re;        // operator blocks, real parts, same offsets as DevModel::pool
+    const uint4* const* xwords;   // per compiled entry id: expanded program words (layout: qiw_kernels.cu)
+    const int* chunk_bounds;      // [n_items][warps + 1] tree ranges of every warp of every CTA job
+    int warps, max_sp;            // warps per CTA; stack frames reserved per warp
+    int nI_max, nD_max;           // table sizes reserved in shared memory
+};
+
 struct BlockParams {
     DevModel m;
     const uint64_t* const* words;      // per compiled entry id: tree word stream

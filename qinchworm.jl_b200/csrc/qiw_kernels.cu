@@ -985,3 +985,303 @@ cudaError_t launch_block_step(const StepParams& p, const BlockParams& bp, dim3 g
 }
 
 }  // namespace qiw
+
+namespace qiw {
+
+// ---- sector blocks larger than 1x1, real arithmetic: lane = sample, warp-uniform tree replay ---------
+// The pruned configuration trees (src/topology_eval.jl:454-556 with the dead branches removed at
+// compile time) are identical for every sample, so a warp takes 32 samples and replays the tree in
+// lock step: no divergence, the program words are warp-uniform, the data are per lane.
+//   CTA = (entry, 32 samples, group of tree chunks); its W warps walk different chunks of the entry's
+//   trees over the SAME samples and share the per-sample tables in shared memory:
+//     TP[(interval, element of the packed block vector)][lane] = Re(i P_s(t_pos, t_pos-1))   (:357-374)
+//     TD[pair-interaction slot][lane]                          = Re(i Delta(t_tail, t_head))  (:397-416)
+//   The running product A_pos ... A_1 (src/utility.jl:234-323) of the current node lives in REGISTERS
+//   (dims <= 4 x 4, fully unrolled matrix-vector products specialised on the block shape); it is saved to
+//   a small shared-memory stack only at nodes with more than one child — the reference's prefix
+//   sharing with a stack as deep as the number of branch points (<= order + 1), not the tree depth.
+//   The scalar pair-interaction weights (:506-507) are carried as one running product per lane and
+//   applied at the leaf together with the coefficient (topology sign, :431).
+// Preconditions checked by the host: operator blocks real, P and Delta purely imaginary, coefficients
+// purely imaginary (then every product is real, exactly).  Otherwise block_step_kernel (complex) runs.
+template <int DR, int DS, int D0>
+__device__ __forceinline__ void block_edge(const double* __restrict__ Pm, int lane_stride, const double* __restrict__ O,
+                                           bool has_op, const double (&V)[16], double (&Vc)[16]) {
+    // tmp = iP_s * V   (DS x D0), then Vc = O * tmp (DR x D0) or tmp itself for identity nodes
+    double Pv[DS * DS];
+#pragma unroll
+    for (int k = 0; k < DS * DS; ++k) Pv[k] = Pm[(size_t)k * lane_stride];
+    double tmp[DS * D0];
+#pragma unroll
+    for (int j = 0; j < D0; ++j)
+#pragma unroll
+        for (int i = 0; i < DS; ++i) {
+            double a = Pv[i] * V[4 * j];
+#pragma unroll
+            for (int k = 1; k < DS; ++k) a = fma(Pv[i + DS * k], V[k + 4 * j], a);
+            tmp[i + DS * j] = a;
+        }
+    if (has_op) {
+        double Ov[DR * DS];
+#pragma unroll
+        for (int k = 0; k < DR * DS; ++k) Ov[k] = __ldg(O + k);
+#pragma unroll
+        for (int j = 0; j < D0; ++j)
+#pragma unroll
+            for (int i = 0; i < DR; ++i) {
+                double a = Ov[i] * tmp[DS * j];
+#pragma unroll
+                for (int k = 1; k < DS; ++k) a = fma(Ov[i + DR * k], tmp[k + DS * j], a);
+                Vc[i + 4 * j] = a;
+            }
+    } else {
+#pragma unroll
+        for (int j = 0; j < D0; ++j)
+#pragma unroll
+            for (int i = 0; i < DS; ++i) Vc[i + 4 * j] = tmp[i + DS * j];
+    }
+}
+
+template <int D0>
+__device__ __forceinline__ void block_edge_dispatch(int dr, int ds, const double* Pm, int lane_stride, const double* O,
+                                                    bool has_op, const double (&V)[16], double (&Vc)[16]) {
+#define QIW_BE(R_, S_) case (R_ * 8 + S_): block_edge<R_, S_, D0>(Pm, lane_stride, O, has_op, V, Vc); break;
+    switch (dr * 8 + ds) {
+        QIW_BE(1, 1) QIW_BE(1, 2) QIW_BE(1, 3) QIW_BE(1, 4) QIW_BE(2, 1) QIW_BE(2, 2) QIW_BE(2, 3) QIW_BE(2, 4)
+        QIW_BE(3, 1) QIW_BE(3, 2) QIW_BE(3, 3) QIW_BE(3, 4) QIW_BE(4, 1) QIW_BE(4, 2) QIW_BE(4, 3) QIW_BE(4, 4)
+        default: break;
+    }
+#undef QIW_BE
+}
+
+// Expanded program word of the block walker (built on the host from the tree words and the model, so the
+// device loop needs no model look-ups and can prefetch one edge ahead):
+//   x = ds | dr << 4 | has_op << 8 | nchild << 16      (source / target block dimension of the edge)
+//   y = element offset of the source sector's block in the packed block vector | (Delta slot + 1) << 16
+//   z = offset of the operator block in pool_re
+//   w = leaf: coefficient index; root: element offset of the initial sector's block
+// Replays one tree for the warp's 32 samples and adds the sum over the samples of
+// Im(coef) * dprod * chain (D0 x D0) to wacc (the warp's block sums of the tree's initial sector).
+template <int D0>
+__device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, uint32_t pc, const double* __restrict__ pool_re,
+                                                const double2* __restrict__ coefs, const double* TP, const double* TD,
+                                                int bsize, double* stackV, double* stackD, int* stackI, int lane, double* wacc) {
+    double acc[4 * D0];
+#pragma unroll
+    for (int k = 0; k < 4 * D0; ++k) acc[k] = 0.0;
+    const uint4 root = __ldg(xw + pc);
+    ++pc;
+    double V[16], Vc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) V[k] = 0.0;
+    if ((root.x >> 8) & 1u) {   // operator node at position 1: bare matrix (:377,540)
+        const int dcur = (int)((root.x >> 4) & 0xFu);
+        const double* O = pool_re + root.z;
+#pragma unroll
+        for (int j = 0; j < D0; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i < dcur) V[i + 4 * j] = __ldg(O + i + dcur * j);
+    } else {
+#pragma unroll
+        for (int j = 0; j < D0; ++j) V[j + 4 * j] = 1.0;
+    }
+    double dprod = 1.0;
+    int depth = 1, sp = 0;
+    int nch = (int)(root.x >> 16);
+    uint4 w = __ldg(xw + pc);   // the next edge is always the next word of the pre-order stream
+    while (nch > 0) {
+        if (nch > 1) {   // branch point: save the running product for the later siblings
+#pragma unroll
+            for (int k = 0; k < 4 * D0; ++k) stackV[((size_t)sp * 16 + k) * 32 + lane] = V[k];
+            stackD[sp * 32 + lane] = dprod;
+            if (lane == 0) { stackI[sp * 2 + 0] = nch - 1; stackI[sp * 2 + 1] = depth; }
+            ++sp;
+            __syncwarp();
+        }
+        // one edge: node at position depth + 1, interval depth - 1
+        const uint4 cur = w;
+        ++pc;
+        w = __ldg(xw + pc);     // prefetch (the stream is padded by one word)
+        const int ds = (int)(cur.x & 0xFu), dr = (int)((cur.x >> 4) & 0xFu);
+        const bool has_op = (cur.x >> 8) & 1u;
+        const double* Pm = TP + ((size_t)(depth - 1) * bsize + (cur.y & 0xFFFFu)) * 32 + lane;
+        block_edge_dispatch<D0>(dr, ds, Pm, 32, pool_re + cur.z, has_op, V, Vc);
+        const uint32_t sbq = cur.y >> 16;
+        if (sbq) dprod *= TD[(size_t)(sbq - 1) * 32 + lane];   // interaction weight at the arc's tail (:506-507)
+        nch = (int)(cur.x >> 16);
+        if (nch == 0) {   // leaf: top_result[s_init] += weight * product (:465)
+            const double c = __ldg(&coefs[cur.w].y) * dprod;
+#pragma unroll
+            for (int k = 0; k < 4 * D0; ++k)
+                if ((k & 3) < D0) acc[k] = fma(c, Vc[k], acc[k]);
+            if (sp == 0) break;
+            // back to the nearest branch point with children left
+            --sp;
+            const int rem = stackI[sp * 2 + 0];
+            depth = stackI[sp * 2 + 1];
+#pragma unroll
+            for (int k = 0; k < 4 * D0; ++k) V[k] = stackV[((size_t)sp * 16 + k) * 32 + lane];
+            dprod = stackD[sp * 32 + lane];
+            __syncwarp();
+            if (rem > 1) {   // more siblings after this one: keep the frame
+                if (lane == 0) stackI[sp * 2 + 0] = rem - 1;
+                ++sp;
+                __syncwarp();
+            }
+            nch = 1;   // continue with exactly one child of the restored node (the frame handles the rest)
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4 * D0; ++k) V[k] = Vc[k];
+            ++depth;
+        }
+    }
+    // sum over the warp's samples, then one lane adds to the warp's block sums
+#pragma unroll
+    for (int j = 0; j < D0; ++j)
+#pragma unroll
+        for (int i = 0; i < D0; ++i) {
+            double v = acc[i + 4 * j];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, off);
+            if (lane == 0) wacc[i + D0 * j] += v;
+        }
+}
+
+__global__ void __launch_bounds__(128) block_walk_kernel(const StepParams p, const BlockParams bp, const BlockWalkParams wp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, nthr = blockDim.x;
+    const WorkItem it = p.items[blockIdx.y];
+    const DevEntry& e = p.entries[it.entry];
+    const DevEntryDyn& dy = p.dyn[it.slot];
+    const DevModel& m = bp.m;
+    const int S = m.S, bsize = m.bsize, D = e.D, n_nodes = e.n_nodes, d_after = e.d_after, nD = e.nD, nI = n_nodes - 1;
+    // shared memory carve-up
+    double* TP = reinterpret_cast<double*>(smem_raw);                       // [nI_max * bsize][32]
+    double* TD = TP + (size_t)wp.nI_max * bsize * 32;                       // [nD_max][32]
+    double* accs = TD + (size_t)wp.nD_max * 32;                             // [nw][bsize] per-warp block sums
+    double* stackV = accs + (size_t)nw * bsize;                             // [nw][max_sp][16][32]
+    double* stackD = stackV + (size_t)nw * wp.max_sp * 16 * 32;             // [nw][max_sp][32]
+    double* times = stackD + (size_t)nw * wp.max_sp * 32;                   // [kDevMaxNodes + 1][32]
+    double* pw = times + (kDevMaxNodes + 1) * 32;                           // [kDevMaxDim][32]
+    int* okflag = reinterpret_cast<int*>(pw + kDevMaxDim * 32);             // [32]
+    int* stackI = okflag + 32;                                              // [nw][max_sp][4]
+
+    const double t_i = p.t_i, t_w = p.t_w, t_f = p.t_f;
+    const double lo_after = (e.mode == 0) ? t_i : t_w, len_after = t_f - lo_after, len_before = t_w - t_i;
+    const unsigned long long count = dy.count;
+    const int n_sb = (int)((count + 31ull) >> 5);
+    const uint4* __restrict__ xw = wp.xwords[it.entry];
+    const uint32_t* __restrict__ toff = bp.tree_off[it.entry];
+    const int* bounds = wp.chunk_bounds + (size_t)blockIdx.y * (wp.warps + 1);
+    const int tree0 = bounds[warp], tree1 = bounds[warp + 1];
+    double* my_acc = accs + (size_t)warp * bsize;
+    for (int k = lane; k < bsize; k += 32) my_acc[k] = 0.0;
+    __syncwarp();
+
+    for (int sb = blockIdx.x; sb < n_sb; sb += gridDim.x) {
+        const unsigned long long local0 = (unsigned long long)sb * 32ull;
+        // -- 1. roots, 2. times (as in the scalar kernel) ---------------------------------------------------
+        if (threadIdx.x < 32) okflag[threadIdx.x] = (local0 + threadIdx.x < count) ? 1 : 0;
+        for (int task = threadIdx.x; task < D * 32; task += nthr) {
+            const int j = task >> 5, smp = task & 31;
+            const uint32_t xi = sobol_coord(dy.sobol + j * 32, __ldg(dy.sobol + D * 32 + j), (uint32_t)(dy.start + local0 + smp));
+            const double x = (double)xi * 2.3283064365386963e-10;
+            const int den = (j < d_after) ? (d_after - j) : (D - j);
+            pw[j * 32 + smp] = (den == 1) ? x : pow(x, 1.0 / (double)den);
+        }
+        __syncthreads();
+        for (int task = threadIdx.x; task < n_nodes * 32; task += nthr) {
+            const int pos = 1 + (task >> 5), smp = task & 31;
+            const int src = e.pos_src[pos];
+            double t;
+            if (src == -1) t = t_i;
+            else if (src == -2) t = t_w;
+            else if (src == -3) t = t_f;
+            else {
+                const int j0 = (src < d_after) ? 0 : d_after;
+                double u = pw[j0 * 32 + smp];
+                for (int j = j0 + 1; j <= src; ++j) u = __dmul_rn(u, pw[j * 32 + smp]);
+                if (src < d_after) t = __dadd_rn(__dmul_rn(u, len_after), lo_after);
+                else t = __dadd_rn(__dmul_rn(u, len_before), t_i);
+                if (!(t >= 0.0)) okflag[smp] = 0;
+            }
+            times[pos * 32 + smp] = t;
+        }
+        __syncthreads();
+        // -- 3. tables: Re(i P) for every interval and block element, Re(i Delta) for every slot -------------
+        for (int task = threadIdx.x; task < (nI + nD) * 32; task += nthr) {
+            const int q = task >> 5, smp = task & 31;
+            const bool ok = okflag[smp] != 0;
+            if (q < nI) {
+                const double ta = times[(q + 1) * 32 + smp];
+                double tb = times[(q + 2) * 32 + smp];
+                if (tb < ta) tb = ta;
+                double* dst = TP + (size_t)q * bsize * 32 + smp;
+                if (e.mode == 0) {
+                    for (int s = 0; s < S; ++s) {
+                        const int d = m.dim[s], bo = m.boff[s];
+                        for (int el = 0; el < d * d; ++el) {
+                            const int r = el % d, cc = el / d;
+                            const double v = (r == cc) ? exp(-(tb - ta) * __ldg(p.E + m.eoff[s] + r)) : 0.0;
+                            dst[(size_t)(bo + el) * 32] = ok ? v : 0.0;
+                        }
+                    }
+                } else {
+                    const GridCell cell = grid_cell(p.n_tau, p.inv_h, tb, ta);
+                    for (int el = 0; el < bsize; ++el) {
+                        const double v = cell_apply_i<true>(p.P + el, bsize, cell);
+                        dst[(size_t)el * 32] = ok ? v : 0.0;
+                    }
+                }
+            } else {
+                const int4 ds = __ldg(e.dslots + (q - nI));
+                const double th = times[ds.y * 32 + smp];
+                double tt = times[ds.x * 32 + smp];
+                if (tt < th) tt = th;
+                const double v = delta_apply_i<true>(p.deltas[ds.z], tt, th);
+                TD[(size_t)(q - nI) * 32 + smp] = ok ? v : 0.0;
+            }
+        }
+        __syncthreads();
+        // -- 4. this warp's trees ----------------------------------------------------------------------------
+        for (int t = tree0; t < tree1; ++t) {
+            const uint32_t pc = toff[t];
+            const uint4 root = __ldg(xw + pc);
+            const int d0 = (int)(root.x & 0xFu);          // root word: ds field = dimension of the initial sector
+            double* sV = stackV + (size_t)warp * wp.max_sp * 16 * 32;
+            double* sD = stackD + (size_t)warp * wp.max_sp * 32;
+            int* sI = stackI + warp * wp.max_sp * 4;
+            double* a = my_acc + root.w;
+            switch (d0) {
+                case 1: block_walk_tree<1>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, sV, sD, sI, lane, a); break;
+                case 2: block_walk_tree<2>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, sV, sD, sI, lane, a); break;
+                case 3: block_walk_tree<3>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, sV, sD, sI, lane, a); break;
+                default: block_walk_tree<4>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, sV, sD, sI, lane, a); break;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    // -- 5. CTA result: sum over the warps, coefficient's factor i restored ------------------------------------
+    for (int k = threadIdx.x; k < bsize; k += nthr) {
+        double v = 0.0;
+        for (int w2 = 0; w2 < nw; ++w2) v += accs[(size_t)w2 * bsize + k];
+        p.partials[((size_t)it.partial0 * gridDim.x + blockIdx.x) * bsize + k] = make_double2(0.0, v);
+    }
+}
+
+cudaError_t launch_block_walk(const StepParams& p, const BlockParams& bp, const BlockWalkParams& wp, dim3 grid, int threads,
+                              size_t smem, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(block_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    block_walk_kernel<<<grid, threads, smem, st>>>(p, bp, wp);
+    return cudaGetLastError();
+}
+
+}  // namespace qiw
