@@ -175,9 +175,105 @@ function eval_entries(s::Session, mode, t_i, t_w, t_f, top_data; corr_idx = 0)
     return samples
 end
 
-# The three worker overloads build (sum, Dict order => SBM, Dict order => SBM_std) / (ComplexF64, ComplexF64)
-# from `eval_entries` exactly as src/inchworm.jl:193-204, 296-304, 881-889 do; omitted here for brevity
-# of the untested shim — see qinchworm.jl_b200/inchworm.py (_order_sums, correlator_2p) for the tested
-# statement of the same glue.
+"mean / std over the randomised sequences (src/randomization.jl:93-99): std of a single sequence is NaN."
+function mean_std(samples::Vector{Matrix{ComplexF64}})
+    n = length(samples)
+    μ = sum(samples) / n
+    σ = n > 1 ? sqrt.(sum(abs2.(x .- μ) for x in samples) / (n - 1)) .+ 0im : fill(ComplexF64(NaN), size(μ))
+    return μ, σ
+end
+
+"(sum, Dict order => SBM, Dict order => SBM_std), exactly as src/inchworm.jl:193-204 / :296-304 build it."
+function order_sums(s::Session, top_data, μ, σ)
+    orders = unique(td.order for td in top_data)
+    contribs = Dict(o => zeros(SectorBlockMatrix, s.expansion.ed) for o in orders)
+    contribs_std = Dict(o => zeros(SectorBlockMatrix, s.expansion.ed) for o in orders)
+    for (j, td) in enumerate(top_data)
+        contribs[td.order] += unpack(s, μ[:, j])
+        contribs_std[td.order] += td.order == 0 ? zeros(SectorBlockMatrix, s.expansion.ed) : unpack(s, σ[:, j])
+    end
+    return sum(values(contribs)), contribs, contribs_std
+end
+
+"Drop-in for QInchworm.inchworm.inchworm_step_bare (src/inchworm.jl:228)."
+function inchworm_step_bare(s::Session, τ_i::kd.TimeGridPoint, τ_f::kd.TimeGridPoint, top_data)
+    t_i, t_f = -imag(τ_i.bpoint.val), -imag(τ_f.bpoint.val)      # imaginary-time branch: val = -iτ
+    μ, σ = mean_std(eval_entries(s, 0, t_i, t_i, t_f, top_data))
+    return order_sums(s, top_data, μ, σ)
+end
+
+"Drop-in for QInchworm.inchworm.inchworm_step (src/inchworm.jl:123).  The caller uploads P first (upload_P!)."
+function inchworm_step(s::Session, τ_i::kd.TimeGridPoint, τ_w::kd.TimeGridPoint, τ_f::kd.TimeGridPoint, top_data)
+    t_i, t_w, t_f = (-imag(τ.bpoint.val) for τ in (τ_i, τ_w, τ_f))
+    upload_P!(s)
+    μ, σ = mean_std(eval_entries(s, 1, t_i, t_w, t_f, top_data))
+    return order_sums(s, top_data, μ, σ)
+end
+
+"Drop-in for the single-τ QInchworm.inchworm.correlator_2p (src/inchworm.jl:805): returns (value, std)."
+function correlator_2p(s::Session, grid::kd.ImaginaryTimeGrid, A_B_pair_idx::Integer, τ::kd.TimeGridPoint, top_data)
+    t_i, t_f = 0.0, grid.contour.β
+    t_w = -imag(τ.bpoint.val)
+    μ, σ = mean_std(eval_entries(s, 2, t_i, t_w, t_f, top_data; corr_idx = A_B_pair_idx - 1))
+    Z = QInchworm.ppgf.partition_function(s.expansion.P)
+    tr_of(v) = sum(tr(unpack(s, v)[sec][2]) for sec in 1:length(s.dims))
+    return sum(tr_of(μ[:, j]) for j in 1:size(μ, 2)) / Z, sum(tr_of(σ[:, j]) for j in 1:size(σ, 2)) / Z
+end
+
+"""
+All grid points of one correlator in ONE launch (qiw_eval_batch): replaces the loop over τ of the
+correlator_2p driver (src/inchworm.jl:1035-1046) when the default RandomizationParams are used.
+Returns the vector of tr(...)/Z for grid points 2:n_τ (the τ = 0 point has order 0 only).
+"""
+function correlator_2p_all_tau(s::Session, grid::kd.ImaginaryTimeGrid, A_B_pair_idx::Integer, top_data)
+    ids = Int32[entry_id!(s, td, 2, A_B_pair_idx - 1) for td in top_data]
+    β = grid.contour.β
+    times = Float64[x for k in 2:length(grid) for x in (0.0, -imag(grid[k].bpoint.val), β)]
+    n_times = length(grid) - 1
+    out = zeros(ComplexF64, s.bsize, length(ids), n_times)
+    check(s.ctx, ccall((:qiw_eval_batch, lib), Cint,
+        (Ctx, Int32, Ptr{Float64}, Int32, Ptr{Int32}, Ptr{UInt32}, Ptr{UInt32}, UInt64, Ptr{ComplexF64}),
+        s.ctx, n_times, times, length(ids), ids, C_NULL, C_NULL, top_data[1].N_samples, out))
+    Z = QInchworm.ppgf.partition_function(s.expansion.P)
+    tr_of(v) = sum(tr(unpack(s, v)[sec][2]) for sec in 1:length(s.dims))
+    return [sum(tr_of(out[:, j, k]) for j in 1:length(ids)) / Z for k in 1:n_times]
+end
+
+"""
+The whole loop of inchworm! on the device (qiw_inchworm_run, src/inchworm.jl:400-493): set_ppgf! and
+normalize! run on the GPU between steps.  `bare`/`bold` are the TopologiesInputData vectors inchworm!
+builds (:380-447).  On return expansion.P holds the final table; the per-entry contributions are
+returned as an array (bsize, n_entries, n_τ).
+"""
+function inchworm_run!(s::Session, bare, bold, N_samples::Integer)
+    upload_P!(s)
+    bare_ids = Int32[entry_id!(s, td, 0) for td in bare]
+    bold_ids = Int32[entry_id!(s, td, 1) for td in bold]
+    hist = zeros(ComplexF64, s.bsize, length(bare_ids) + length(bold_ids), s.n_tau)
+    check(s.ctx, ccall((:qiw_inchworm_run, lib), Cint,
+        (Ctx, Int32, Ptr{Int32}, Int32, Ptr{Int32}, Ptr{UInt32}, Ptr{UInt32}, UInt64, Ptr{ComplexF64}),
+        s.ctx, length(bare_ids), bare_ids, length(bold_ids), bold_ids, C_NULL, C_NULL, N_samples, hist))
+    rows = zeros(ComplexF64, s.bsize, s.n_tau)
+    check(s.ctx, ccall((:qiw_get_P, lib), Cint, (Ctx, Int32, Int32, Ptr{ComplexF64}), s.ctx, 0, s.n_tau, rows))
+    off = 0
+    for (sec, P_s) in enumerate(s.expansion.P)
+        data = hasproperty(P_s, :GF) ? P_s.GF.mat.data : P_s.mat.data
+        d = s.dims[sec]
+        data[:, :, :] = reshape(rows[off+1:off+d*d, :], d, d, s.n_tau)
+        off += d * d
+    end
+    return hist
+end
+
+"Map every rank's mailbox into this process so that the all-reduce runs inside the step kernel (qiw_peer_*)."
+function init_peer!(s::Session)
+    comm = MPI.COMM_WORLD
+    MPI.Comm_size(comm) > 1 || return
+    mine = zeros(UInt8, 64)
+    check(s.ctx, ccall((:qiw_peer_handle, lib), Cint, (Ctx, Ptr{UInt8}), s.ctx, mine))
+    all = MPI.Allgather(mine, comm)
+    check(s.ctx, ccall((:qiw_peer_init, lib), Cint, (Ctx, Int32, Int32, Ptr{UInt8}),
+                       s.ctx, MPI.Comm_size(comm), MPI.Comm_rank(comm), all))
+end
 
 end # module
