@@ -298,3 +298,70 @@ def test_correlator_batched_vs_stepped(gpu_ctx, qlib, oracle_lib):
     assert relerr(g_b, g_s) < 1e-13
     ref = oracle_lib.correlator_2p(ex.flatten(), ex.P, range(0, 4), 2 ** 8)
     assert relerr(g_b, ref) < RTOL
+
+
+def test_edge_cases(gpu_ctx, qlib, oracle_lib, monkeypatch):
+    """Ragged and degenerate inputs: a single sample, an empty sample range, order-0-only calls, the
+    first Sobol point (x = 0 collapses every time onto its lower bound), a scrambled sequence in the
+    device-resident run, the complex block kernel, and argument errors."""
+    from qinchworm_b200.inchworm import Solver
+    ex, grid, f = models.anderson(n_tau=16)
+    pl = gpu_ctx.set_expansion(ex)
+    o = oracle_lib.Oracle(pl, ex.P)
+    ids = []
+    for order in range(0, 3):
+        for k in ([0] if order == 0 else range(1, 2 * order)):
+            pr, pa = qlib.topologies(order, k)
+            gpu_ctx.set_topologies(len(ids), qlib.MODE_BOLD, order, k, pr, pa)
+            o.set_topologies(len(ids), qlib.MODE_BOLD, order, k, pr, pa)
+            ids.append(len(ids))
+    tau = grid.tau
+    # N = 1: only the first point of the sequence (all times on their lower bounds)
+    assert relerr(gpu_ctx.eval(0.0, tau[7], tau[8], ids, 1), o.eval(0.0, tau[7], tau[8], ids, 1)) < RTOL
+    # empty range: sampled entries contribute nothing, the exact order-0 entry is still evaluated
+    got = gpu_ctx.eval_range(0.0, tau[7], tau[8], ids, 64, 10, 0)
+    ref = o.eval(0.0, tau[7], tau[8], ids, 64, start=10, count=0)
+    assert np.abs(got - ref).max() < 1e-300 + RTOL * np.abs(ref).max()
+    # order 0 alone
+    assert relerr(gpu_ctx.eval(0.0, tau[7], tau[8], ids[:1], 8), o.eval(0.0, tau[7], tau[8], ids[:1], 8)) < RTOL
+    # a non-power-of-two range that is not a multiple of the 32-sample blocks, at the end of the sequence
+    got = gpu_ctx.eval_range(0.0, tau[3], tau[4], ids, 1000, 1000 - 77, 77)
+    ref = o.eval(0.0, tau[3], tau[4], ids, 1000, start=1000 - 77, count=77)
+    assert relerr(got, ref) < RTOL
+    # batched evaluation with a scrambled sequence
+    rng = np.random.default_rng(5)
+    sob = []
+    for e in ids:
+        D = 2 * gpu_ctx.entry_order[e]
+        m = qlib.sobol_direction_numbers(D)
+        sob.append(qlib.sobol_scramble(m, rng.integers(0, 2, (D, 32)), rng.integers(0, 2, (D, 32, 32))) if D
+                   else (m, np.zeros(0, dtype=np.uint32)))
+    times = np.array([[0.0, tau[k], tau[k + 1]] for k in (2, 9, 13)])
+    got = gpu_ctx.eval_batch(times, ids, 128, sobol=sob)
+    for z in range(3):
+        ref = o.eval(times[z, 0], times[z, 1], times[z, 2], ids, 128, sobol=sob)
+        assert relerr(got[z], ref) < RTOL
+    # argument errors are reported, not crashes
+    with pytest.raises(qlib.QiwError):
+        gpu_ctx.eval(0.0, tau[7], tau[8], [999], 8)
+    with pytest.raises(qlib.QiwError):
+        gpu_ctx.eval(0.0, tau[7], tau[8], [0, 0], 8)
+    with pytest.raises(qlib.QiwError):
+        gpu_ctx.eval_range(0.0, tau[7], tau[8], ids, 8, 5, 9)
+    # block model through the general complex kernel (the real-arithmetic walker is the default)
+    ex2, grid2, _ = models.two_level_mixed(n_tau=10, theta=0.4)
+    pl2 = gpu_ctx.set_expansion(ex2)
+    o2 = oracle_lib.Oracle(pl2, ex2.P)
+    ids2 = []
+    for order in range(0, 3):
+        for k in ([0] if order == 0 else range(1, 2 * order)):
+            pr, pa = qlib.topologies(order, k)
+            gpu_ctx.set_topologies(len(ids2), qlib.MODE_BOLD, order, k, pr, pa)
+            o2.set_topologies(len(ids2), qlib.MODE_BOLD, order, k, pr, pa)
+            ids2.append(len(ids2))
+    ref = o2.eval(0.0, grid2.tau[4], grid2.tau[5], ids2, 64)
+    got_real = gpu_ctx.eval(0.0, grid2.tau[4], grid2.tau[5], ids2, 64)
+    monkeypatch.setenv("QIW_FORCE_COMPLEX", "1")
+    got_cplx = gpu_ctx.eval(0.0, grid2.tau[4], grid2.tau[5], ids2, 64)
+    monkeypatch.delenv("QIW_FORCE_COMPLEX")
+    assert relerr(got_real, ref) < RTOL and relerr(got_cplx, ref) < RTOL
