@@ -94,6 +94,7 @@ struct EntryDev {
     bool imag_coefs = false;     // every folded coefficient is purely imaginary (real-mode precondition)
     DevBuf<uint64_t> words;      // block models: tree word stream
     DevBuf<uint4> xwords;        // block models: expanded words of the real-arithmetic walker
+    std::vector<double> walk_cost;   // block models: estimated cost of every tree for the walker (load balancing)
     DevBuf<uint32_t> tree_off;
     DevBuf<double2> coefs;
     DevBuf<int4> dslots;
@@ -503,6 +504,17 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
                 xw[k] = x;
             }
             CK(ed.xwords.upload(xw.data(), xw.size(), ctx->stream));
+            // cost of a tree for the walker: multiply-adds of every edge plus a fixed per-edge overhead
+            ed.walk_cost.assign(pr.tree_off.empty() ? 0 : pr.tree_off.size() - 1, 0.0);
+            for (size_t t = 0; t + 1 < pr.tree_off.size(); ++t) {
+                const uint32_t d0 = xw[pr.tree_off[t]].x & 0xFu;
+                double c = 0;
+                for (size_t k = pr.tree_off[t] + 1; k < pr.tree_off[t + 1]; ++k) {
+                    const uint32_t ds = xw[k].x & 0xFu, dr = (xw[k].x >> 4) & 0xFu;
+                    c += (double)(ds * ds + dr * ds) * d0 + 50.0;
+                }
+                ed.walk_cost[t] = c;
+            }
         }
         CK(ed.tree_off.upload(pr.tree_off.data(), pr.tree_off.size(), ctx->stream));
     }
@@ -670,13 +682,14 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         const int bs = ctx->model.bsize;
         int nI_max = 1, nD_max = 1, max_order = 0;
         double total_cost = 0;
+        std::vector<double> entry_cost;
         uint64_t n_sb = 1;
         for (int i = 0; i < n_entries; ++i) {
             const EntryProgram& p = ctx->entries[ids[i]]->prog;
             nI_max = std::max(nI_max, p.n_nodes - 1);
             nD_max = std::max(nD_max, (int)p.dslots.size());
             max_order = std::max(max_order, p.order);
-            total_cost += (double)p.n_edges;
+            { double c = 0; for (double x : ctx->entries[ids[i]]->walk_cost) c += x; total_cost += c; entry_cost.push_back(c); }
             n_sb = std::max<uint64_t>(n_sb, ((p.order == 0 ? 1 : count) + 31) / 32);
         }
         const int max_sp = max_order + 2;
@@ -695,12 +708,13 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         for (int i = 0; i < n_entries; ++i) {
             const EntryProgram& p = ctx->entries[ids[i]]->prog;
             const int n_trees = (int)p.tree_off.size() - 1;
-            int jobs = (int)std::ceil(want_ctas * (double)p.n_edges / std::max(total_cost, 1.0) / (double)n_sb);
+            int jobs = (int)std::ceil(want_ctas * entry_cost[i] / std::max(total_cost, 1.0) / (double)n_sb);
             jobs = std::max(1, std::min(jobs, (n_trees + Wn - 1) / Wn));
             const int n_chunks = jobs * Wn;
             // chunk boundaries at equal cumulative cost
             std::vector<double> cum(n_trees + 1, 0.0);
-            for (int t = 0; t < n_trees; ++t) cum[t + 1] = cum[t] + (double)p.tree_cost[t] + 4.0;
+            const std::vector<double>& wc = ctx->entries[ids[i]]->walk_cost;
+            for (int t = 0; t < n_trees; ++t) cum[t + 1] = cum[t] + (t < (int)wc.size() ? wc[t] : (double)p.tree_cost[t]) + 4.0;
             pl->item0[i] = (int)pl->items.size();
             int t_prev = 0;
             for (int j = 0; j < jobs; ++j) {

@@ -1006,46 +1006,54 @@ namespace qiw {
 // purely imaginary (then every product is real, exactly).  Otherwise block_step_kernel (complex) runs.
 template <int DR, int DS, int D0>
 __device__ __forceinline__ void block_edge(const double* __restrict__ Pm, int lane_stride, const double* __restrict__ O,
-                                           bool has_op, const double (&V)[16], double (&Vc)[16]) {
-    // tmp = iP_s * V   (DS x D0), then Vc = O * tmp (DR x D0) or tmp itself for identity nodes
+                                           bool has_op, double (&V)[16]) {
+    // V <- O * (iP_s * V), column by column and in place (columns are independent): DS x D0 -> DR x D0
     double Pv[DS * DS];
 #pragma unroll
     for (int k = 0; k < DS * DS; ++k) Pv[k] = Pm[(size_t)k * lane_stride];
-    double tmp[DS * D0];
-#pragma unroll
-    for (int j = 0; j < D0; ++j)
-#pragma unroll
-        for (int i = 0; i < DS; ++i) {
-            double a = Pv[i] * V[4 * j];
-#pragma unroll
-            for (int k = 1; k < DS; ++k) a = fma(Pv[i + DS * k], V[k + 4 * j], a);
-            tmp[i + DS * j] = a;
-        }
     if (has_op) {
         double Ov[DR * DS];
 #pragma unroll
         for (int k = 0; k < DR * DS; ++k) Ov[k] = __ldg(O + k);
 #pragma unroll
-        for (int j = 0; j < D0; ++j)
+        for (int j = 0; j < D0; ++j) {
+            double t[DS];
+#pragma unroll
+            for (int i = 0; i < DS; ++i) {
+                double a = Pv[i] * V[4 * j];
+#pragma unroll
+                for (int k = 1; k < DS; ++k) a = fma(Pv[i + DS * k], V[k + 4 * j], a);
+                t[i] = a;
+            }
 #pragma unroll
             for (int i = 0; i < DR; ++i) {
-                double a = Ov[i] * tmp[DS * j];
+                double a = Ov[i] * t[0];
 #pragma unroll
-                for (int k = 1; k < DS; ++k) a = fma(Ov[i + DR * k], tmp[k + DS * j], a);
-                Vc[i + 4 * j] = a;
+                for (int k = 1; k < DS; ++k) a = fma(Ov[i + DR * k], t[k], a);
+                V[i + 4 * j] = a;
             }
+        }
     } else {
 #pragma unroll
-        for (int j = 0; j < D0; ++j)
+        for (int j = 0; j < D0; ++j) {
+            double t[DS];
 #pragma unroll
-            for (int i = 0; i < DS; ++i) Vc[i + 4 * j] = tmp[i + DS * j];
+            for (int i = 0; i < DS; ++i) {
+                double a = Pv[i] * V[4 * j];
+#pragma unroll
+                for (int k = 1; k < DS; ++k) a = fma(Pv[i + DS * k], V[k + 4 * j], a);
+                t[i] = a;
+            }
+#pragma unroll
+            for (int i = 0; i < DS; ++i) V[i + 4 * j] = t[i];
+        }
     }
 }
 
 template <int D0>
 __device__ __forceinline__ void block_edge_dispatch(int dr, int ds, const double* Pm, int lane_stride, const double* O,
-                                                    bool has_op, const double (&V)[16], double (&Vc)[16]) {
-#define QIW_BE(R_, S_) case (R_ * 8 + S_): block_edge<R_, S_, D0>(Pm, lane_stride, O, has_op, V, Vc); break;
+                                                    bool has_op, double (&V)[16]) {
+#define QIW_BE(R_, S_) case (R_ * 8 + S_): block_edge<R_, S_, D0>(Pm, lane_stride, O, has_op, V); break;
     switch (dr * 8 + ds) {
         QIW_BE(1, 1) QIW_BE(1, 2) QIW_BE(1, 3) QIW_BE(1, 4) QIW_BE(2, 1) QIW_BE(2, 2) QIW_BE(2, 3) QIW_BE(2, 4)
         QIW_BE(3, 1) QIW_BE(3, 2) QIW_BE(3, 3) QIW_BE(3, 4) QIW_BE(4, 1) QIW_BE(4, 2) QIW_BE(4, 3) QIW_BE(4, 4)
@@ -1071,7 +1079,7 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
     for (int k = 0; k < 4 * D0; ++k) acc[k] = 0.0;
     const uint4 root = __ldg(xw + pc);
     ++pc;
-    double V[16], Vc[16];
+    double V[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) V[k] = 0.0;
     if ((root.x >> 8) & 1u) {   // operator node at position 1: bare matrix (:377,540)
@@ -1106,7 +1114,7 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
         const int ds = (int)(cur.x & 0xFu), dr = (int)((cur.x >> 4) & 0xFu);
         const bool has_op = (cur.x >> 8) & 1u;
         const double* Pm = TP + ((size_t)(depth - 1) * bsize + (cur.y & 0xFFFFu)) * 32 + lane;
-        block_edge_dispatch<D0>(dr, ds, Pm, 32, pool_re + cur.z, has_op, V, Vc);
+        block_edge_dispatch<D0>(dr, ds, Pm, 32, pool_re + cur.z, has_op, V);
         const uint32_t sbq = cur.y >> 16;
         if (sbq) dprod *= TD[(size_t)(sbq - 1) * 32 + lane];   // interaction weight at the arc's tail (:506-507)
         nch = (int)(cur.x >> 16);
@@ -1114,7 +1122,7 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
             const double c = __ldg(&coefs[cur.w].y) * dprod;
 #pragma unroll
             for (int k = 0; k < 4 * D0; ++k)
-                if ((k & 3) < D0) acc[k] = fma(c, Vc[k], acc[k]);
+                if ((k & 3) < D0) acc[k] = fma(c, V[k], acc[k]);
             if (sp == 0) break;
             // back to the nearest branch point with children left
             --sp;
@@ -1131,8 +1139,6 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
             }
             nch = 1;   // continue with exactly one child of the restored node (the frame handles the rest)
         } else {
-#pragma unroll
-            for (int k = 0; k < 4 * D0; ++k) V[k] = Vc[k];
             ++depth;
         }
     }
@@ -1174,7 +1180,7 @@ __global__ void __launch_bounds__(128) block_walk_kernel(const StepParams p, con
     const uint4* __restrict__ xw = wp.xwords[it.entry];
     const uint32_t* __restrict__ toff = bp.tree_off[it.entry];
     const int* bounds = wp.chunk_bounds + (size_t)blockIdx.y * (wp.warps + 1);
-    const int tree0 = bounds[warp], tree1 = bounds[warp + 1];
+    const int tree0 = bounds[warp], tree1 = bounds[warp + 1];   // contiguous range of about equal cost per warp
     double* my_acc = accs + (size_t)warp * bsize;
     for (int k = lane; k < bsize; k += 32) my_acc[k] = 0.0;
     __syncwarp();
