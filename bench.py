@@ -240,8 +240,11 @@ def main():
     dom_name = "step_real" if "step_real" in prof else "step_complex"
     dom = prof.get(dom_name, {"ms": float("nan"), "launches": 1})
     n_count = mpi.split_count(N, world)[rank]
-    dom_ms = dom["ms"] / max(dom["launches"], 1)
-    dom_flops = flops_bold_sample * n_count                       # algorithmic chain FLOPs of one launch
+    # one inchworm step = one launch of the step kernel (reduction, all-reduce and P update are fused into its
+    # tail), so its average duration over the timed region is the device time of the run / number of launches
+    n_step_launches = N_TAU - 1
+    dom_ms = ms_per_step / n_step_launches
+    dom_flops = flops_bold_sample * n_count                       # algorithmic chain FLOPs of one bold-step launch
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12
     total_prof = sum(v["ms"] for v in prof.values())
     roofline = {"bound": "fp64_fma", "kernel": "scalar_step_kernel<%s> (all bold entries, orders 0-4)" % ("real" if dom_name == "step_real" else "complex"), "achieved": achieved,
@@ -249,7 +252,9 @@ def main():
                 "peak_source": "measured in this process by qiw_measure_fp64_peak (DFMA-saturating kernel); "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "flops_per_launch": dom_flops, "ms_per_launch": dom_ms, "traffic": None,
+                "launches_per_run": n_step_launches,
                 "kernel_share_of_step": dom["ms"] / total_prof if total_prof else None,
+                "ms_per_launch_profiled": dom["ms"] / max(dom["launches"], 1),
                 "profile_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
                 "profile_launches": {k: v["launches"] for k, v in prof.items()},
                 "whole_run_frac": (flops_bold_sample * n_count * (N_TAU - 2)) / (ms_per_step * 1e-3) / 1e12 / fp64_peak}
