@@ -1043,6 +1043,12 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         gp.max_coefs = g.max_coefs;
         gp.max_segdef = g.max_segdef;
         gp.spb = g.spb[real];
+        {
+            // measured on B200 (C1): overlapping consecutive steps gains nothing (7.25 vs 6.96 ms per run), because
+            // the dependent grid can only start once the last wave of the running grid has started; off by default
+            const char* env = getenv("QIW_PDL");
+            gp.allow_overlap = (env && env[0] == '1') ? 1 : 0;
+        }
         gp.spb_log2 = 0;
         while ((1 << gp.spb_log2) < gp.spb) ++gp.spb_log2;
         dim3 grid((unsigned)pl.pitch, (unsigned)g.n_items, (unsigned)std::max(n_times, 1));

@@ -454,6 +454,8 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
     typedef typename Num<REAL>::T T;
     typedef Num<REAL> N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // let the next step's grid start as soon as every CTA of this one is running (it waits before it touches P)
+    asm volatile("griddepcontrol.launch_dependents;");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, nthr = blockDim.x;
     const WorkItem it = p.items[blockIdx.y];
     const DevEntry& e = p.entries[it.entry];
@@ -577,11 +579,35 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
         //       (src/qmc_integrate.jl:503,608) and samples past the range get zero rows.
         {
             const int nI = n_nodes - 1;
-            for (int task = threadIdx.x; task < (nI + nD) * spb; task += nthr) {
+            // pair interactions first: they do not depend on the bold propagators, so in the device-resident
+            // loop this part (like everything above) overlaps the previous step's tail (see below)
+            for (int task = threadIdx.x; task < nD * spb; task += nthr) {
                 const int q = task >> spb_sh, smp = task & spb_mask;
                 const bool ok = okflag[smp] != 0;
                 T* myrow = reinterpret_cast<T*>(Tb + smp * row_bytes);
-                if (q < nI) {
+                const int4 ds = dslots_s[q];
+                const double th = times[ds.y * 32 + smp];
+                double tt = times[ds.x * 32 + smp];
+                if (tt < th) tt = th;                       // :407-410
+                const DevDelta& dt = ds.z < kInlineTables ? p.deltas_inline[ds.z] : p.deltas[ds.z];
+                T val;
+                if (dt.kind == 0 && dt.n == p.n_tau && dt.inv_h == p.inv_h) {   // table on the P grid: reuse the cells
+                    const int ih = ds.y * 32 + smp, it2 = (tt == th) ? ih : ds.x * 32 + smp;
+                    val = cell_apply_i<REAL>(dt.y, 1, grid_cell_from(cella[it2], cellw[it2], cella[ih], cellw[ih]));
+                } else {
+                    val = delta_apply_i<REAL>(dt, tt, th);
+                }
+                myrow[nP + q] = ok ? val : N::zero();
+            }
+            // Programmatic dependent launch: this grid may have been started while the previous step's grid
+            // was still finishing.  Everything up to here used only data no kernel writes; the P table, the
+            // partial-sum rows and the arrival counter belong to the previous grid until it has completed.
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            for (int task = threadIdx.x; task < nI * spb; task += nthr) {
+                const int q = task >> spb_sh, smp = task & spb_mask;
+                const bool ok = okflag[smp] != 0;
+                T* myrow = reinterpret_cast<T*>(Tb + smp * row_bytes);
+                {
                     const double ta = times[(q + 1) * 32 + smp];
                     double tb = times[(q + 2) * 32 + smp];
                     if (tb < ta) tb = ta;                       // src/topology_eval.jl:362-364
@@ -600,20 +626,6 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
                             myrow[q * S + s] = ok ? val : N::zero();
                         }
                     }
-                } else {
-                    const int4 ds = dslots_s[q - nI];
-                    const double th = times[ds.y * 32 + smp];
-                    double tt = times[ds.x * 32 + smp];
-                    if (tt < th) tt = th;                       // :407-410
-                    const DevDelta& dt = ds.z < kInlineTables ? p.deltas_inline[ds.z] : p.deltas[ds.z];
-                    T val;
-                    if (dt.kind == 0 && dt.n == p.n_tau && dt.inv_h == p.inv_h) {   // table on the P grid: reuse the cells
-                        const int ih = ds.y * 32 + smp, it2 = (tt == th) ? ih : ds.x * 32 + smp;
-                        val = cell_apply_i<REAL>(dt.y, 1, grid_cell_from(cella[it2], cellw[it2], cella[ih], cellw[ih]));
-                    } else {
-                        val = delta_apply_i<REAL>(dt, tt, th);
-                    }
-                    myrow[nP + (q - nI)] = ok ? val : N::zero();
                 }
             }
         }
@@ -641,7 +653,8 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
 
     if constexpr (PER_SAMPLE) return;
 
-    // -- 6. CTA result: warps summed in fixed order -----------------------------------------------
+    // -- 6. CTA result: warps summed in fixed order (CTAs without a sample block have not waited yet) --
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if ((int)threadIdx.x < S) {
         double2 v = make_double2(0.0, 0.0);
         for (int w2 = 0; w2 < nw; ++w2) v = cadd(v, red[threadIdx.x * nw + w2]);
@@ -754,8 +767,14 @@ static cudaError_t launch_scalar_t(const StepParams& p, dim3 grid, int threads, 
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    scalar_step_kernel<REAL, PER_SAMPLE><<<grid, threads, smem, st>>>(p);
-    return cudaGetLastError();
+    // programmatic dependent launch: consecutive step kernels of a stream may overlap prologue and tail
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = p.allow_overlap ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, scalar_step_kernel<REAL, PER_SAMPLE>, p);
 }
 
 // `real_mode`: every table and coefficient in use has been verified purely imaginary by the host.
