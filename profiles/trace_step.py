@@ -10,7 +10,8 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 ex, grid, f = models.anderson(n_tau=200)
 ctx = lib.Context(device=0)
 solver = Solver(ex, ctx=ctx)
-bold = _bold_entries(solver, range(0, 5), N, None, None)
+max_order = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+bold = _bold_entries(solver, range(0, max_order + 1), N, None, None)
 ids = [t.entry_id for t in bold]
 tau = grid.tau
 for _ in range(5):
@@ -21,6 +22,7 @@ print("device ms", ctx.last_device_ms())
 del os.environ["QIW_TRACE"]
 t = np.loadtxt(os.path.join(ROOT, "gpurun_out", "trace.csv"), delimiter=",", skiprows=1)
 clk = 1.965e3  # cycles per us at max clock
+t = np.atleast_2d(t)
 t0 = t[:, 8].min()
 print("CTAs", len(t), "start spread us", (t[:, 8].max() - t0) / 1e3)
 m = t[:, 2] > 0
@@ -30,6 +32,10 @@ print("  of which roots %.2f times %.2f fill %.2f segments %.2f (means)" % (((t[
 print("kernel span us (first CTA start .. last CTA end, globaltimer + cycles): %.2f" % ((t[m, 8] - t0) / 1e3 + (t[m, 4] - t[m, 1]) / clk).max())
 print("walk  us: mean %.2f max %.2f" % (((t[m, 3] - t[m, 2]) / clk).mean(), ((t[m, 3] - t[m, 2]) / clk).max()))
 print("tail  us: mean %.2f max %.2f" % (((t[m, 4] - t[m, 3]) / clk).mean(), ((t[m, 4] - t[m, 3]) / clk).max()))
+lt = t[:, 12] > 0
+if lt.any():
+    print("last CTA: walk end -> tail end %.2f us; its start offset %.2f us; kernel span incl. tail %.2f us" % (
+        ((t[lt, 12] - t[lt, 4]) / clk).max(), ((t[lt, 8] - t0) / 1e3).max(), ((t[lt, 8] - t0) / 1e3 + (t[lt, 12] - t[lt, 1]) / clk).max()))
 print("start offsets us: pctl", np.percentile((t[:, 8] - t0) / 1e3, [0, 25, 50, 75, 90, 100]))
 for e in sorted(set(t[:, 6])):
     k = (t[:, 6] == e) & m

@@ -1063,10 +1063,10 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         CK(cudaMemcpyAsync(tr.data(), ctx->dTrace.p, trace_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (FILE* f = fopen(trace_path, "w")) {
-            fprintf(f, "cta,start_clk,tables_clk,walk_clk,end_clk,smid,entry,groups_warp0,start_ns,roots_clk,times_clk,fill_clk\n");
+            fprintf(f, "cta,start_clk,tables_clk,walk_clk,end_clk,smid,entry,groups_warp0,start_ns,roots_clk,times_clk,fill_clk,tail_clk\n");
             for (size_t c = 0; c < trace_words / 12; ++c)
-                fprintf(f, "%zu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu\n", c, tr[c * 12], tr[c * 12 + 1], tr[c * 12 + 2], tr[c * 12 + 3],
-                        tr[c * 12 + 4], tr[c * 12 + 5], tr[c * 12 + 6], tr[c * 12 + 7], tr[c * 12 + 8], tr[c * 12 + 9], tr[c * 12 + 10]);
+                fprintf(f, "%zu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu\n", c, tr[c * 12], tr[c * 12 + 1], tr[c * 12 + 2], tr[c * 12 + 3],
+                        tr[c * 12 + 4], tr[c * 12 + 5], tr[c * 12 + 6], tr[c * 12 + 7], tr[c * 12 + 8], tr[c * 12 + 9], tr[c * 12 + 10], tr[c * 12 + 11]);
             fclose(f);
         }
     }

@@ -349,8 +349,14 @@ __device__ __forceinline__ void walk_dispatch(int L, const uint32_t* rec_t, int 
 // out = weight * (-i)^d * Jacobian * sum(rows): the factors of contour_integral / qmc_integral
 // (src/qmc_integrate.jl:497-507,565-569,597-612) and of the simplex maps (:46,458-463).
 __device__ __forceinline__ double simplex_volume(int d, double edge) {
+    // prod_{i<=d} edge / i (src/qmc_integrate.jl:46) with the reciprocals tabulated: FP64 division costs
+    // hundreds of cycles and this sits on the critical path of every step's tail
+    const double inv[17] = {1.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10,
+                            1.0 / 11, 1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16};
     double v = 1.0;
-    for (int i = 1; i <= d; ++i) v *= edge / (double)i;
+#pragma unroll
+    for (int i = 1; i <= 16; ++i)
+        if (i <= d) v *= edge * inv[i];
     return v;
 }
 
@@ -370,20 +376,24 @@ __device__ void fused_tail(const StepParams& pp, double t_i, double t_w, double 
     const int S = p.S, n_out = p.n_call_entries * S;
     p.partials += (size_t)blockIdx.z * gridDim.y * gridDim.x * S;   // this time triple's rows and results
     p.out += (size_t)blockIdx.z * n_out;
-    for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
-        const int i = o / S, s = o - i * S;
-        const DevEntryDyn& dy = p.dyn[i];
-        const DevEntry& e = p.entries[dy.entry];
-        const double scale = entry_scale(e, dy, t_i, t_w, t_f);
-        const size_t row0 = (size_t)dy.item0 * pitch, nrows = (size_t)dy.n_items * pitch;
-        double2 v0 = make_double2(0.0, 0.0), v1 = v0;
-        size_t r = 0;
-        for (; r + 1 < nrows; r += 2) {
-            v0 = cadd(v0, __ldcg(p.partials + (row0 + r) * S + s));
-            v1 = cadd(v1, __ldcg(p.partials + (row0 + r + 1) * S + s));
+    // four lanes per (entry, sector) output: lane g adds rows g, g+4, ... in order, then the four partial sums
+    // are combined in a fixed butterfly — the same operation order whichever CTA runs the tail
+    for (int o0 = 0; o0 < n_out; o0 += (int)blockDim.x / 4) {
+        const int o = o0 + (int)threadIdx.x / 4, g = (int)threadIdx.x & 3;
+        double2 v = make_double2(0.0, 0.0);
+        double scale = 0.0;
+        int oi = 0;
+        if (o < n_out) {
+            const int i = o / S, s = o - i * S;
+            const DevEntryDyn& dy = p.dyn[i];
+            const size_t row0 = (size_t)dy.item0 * pitch, nrows = (size_t)dy.n_items * pitch;
+            for (size_t r = g; r < nrows; r += 4) v = cadd(v, __ldcg(p.partials + (row0 + r) * S + s));
+            if (g == 0) scale = entry_scale(p.entries[dy.entry], dy, t_i, t_w, t_f);
+            oi = dy.out_index * S + s;
         }
-        if (r < nrows) v0 = cadd(v0, __ldcg(p.partials + (row0 + r) * S + s));
-        p.out[(size_t)dy.out_index * S + s] = cscale(scale, cadd(v0, v1));
+        v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, 1); v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, 1);
+        v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, 2); v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, 2);
+        if (o < n_out && g == 0) p.out[oi] = cscale(scale, v);
     }
     if (p.peer_ranks > 1) {
         // ---- all-reduce over peer memory (replaces all_reduce!, src/mpi.jl:104-127) ----
@@ -676,6 +686,7 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
         __threadfence();
         fused_tail(p, t_i, t_w, t_f, (int)gridDim.x);
         if (threadIdx.x == 0) p.done_counter[blockIdx.z] = 0u;
+        if (trace && threadIdx.x == 0) trace[11] = clock64();
     }
 }
 
