@@ -274,7 +274,8 @@ int qiw_comm_destroy(qiw_context* ctx);
  * Every rank calls qiw_peer_handle (allocates its mailbox, returns the CUDA IPC handle), the host
  * all-gathers the 64-byte handles (MPI.Allgather in Julia, torch.distributed here) and passes all of
  * them, in rank order, to qiw_peer_init.  Payloads larger than 64 KiB per call and block models fall
- * back to the NCCL communicator of qiw_comm_init (which must then exist). */
+ * back to the NCCL communicator of qiw_comm_init (which must then exist).  If any rank fails to map the
+ * mailboxes, ALL ranks must call qiw_peer_init(ctx, 0, 0, NULL) to switch the peer path off again. */
 int qiw_peer_handle(qiw_context* ctx, uint8_t handle[QIW_PEER_HANDLE_BYTES]);
 int qiw_peer_init(qiw_context* ctx, int32_t n_ranks, int32_t rank, const uint8_t* handles);
 

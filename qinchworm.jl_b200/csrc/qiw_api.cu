@@ -1442,6 +1442,10 @@ int qiw_peer_handle(qiw_context* ctx, uint8_t handle[QIW_PEER_HANDLE_BYTES]) {
 }
 
 int qiw_peer_init(qiw_context* ctx, int32_t n_ranks, int32_t rank, const uint8_t* handles) {
+    if (ctx && n_ranks == 0) {   // switch the peer path off again (e.g. another rank could not map the mailboxes)
+        ctx->peer_ready = false;
+        return QIW_OK;
+    }
     if (!ctx || n_ranks <= 0 || n_ranks > kMaxPeers || rank < 0 || rank >= n_ranks || !handles)
         return fail(ctx, QIW_ERR_BAD_ARG, "qiw_peer_init: bad argument (at most 16 ranks)");
     if (ctx->no_device) return fail(ctx, QIW_ERR_CUDA, "planning-only context cannot communicate");

@@ -395,6 +395,9 @@ class Context:
         h = np.ascontiguousarray(handles, dtype=np.uint8).reshape(n_ranks * PEER_HANDLE_BYTES)
         self._ck(self.L.qiw_peer_init(self.h, n_ranks, rank, _ptr(h, u8p)))
 
+    def peer_disable(self):
+        self._ck(self.L.qiw_peer_init(self.h, 0, 0, None))
+
     def measure_fp64_peak(self):
         v = C.c_double(0)
         self._ck(self.L.qiw_measure_fp64_peak(self.h, C.byref(v)))

@@ -74,6 +74,8 @@ def init_comm(ctx, peer=None):
     flags = [None] * size
     dist.all_gather_object(flags, ok)
     if not all(flags):
-        raise RuntimeError("peer-memory mailboxes could not be mapped on every rank (no P2P access?); "
-                           "run with QIW_NO_PEER=1 to use the NCCL all-reduce")
+        # no peer access between some GPUs (or CUDA IPC not permitted): every rank leaves the peer path,
+        # the NCCL all-reduce of qiw_comm_init carries the collective
+        ctx.peer_disable()
+        return "nccl"
     return "peer"
