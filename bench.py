@@ -247,11 +247,24 @@ def main():
     dom_flops = flops_bold_sample * n_count                       # algorithmic chain FLOPs of one bold-step launch
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12
     total_prof = sum(v["ms"] for v in prof.values())
+    # DRAM traffic of the same kernel from the committed ncu --set full capture (profiles/), per launch
+    traffic, traffic_src = None, None
+    try:
+        src = os.path.join(ROOT, "profiles", "r1_ncu_c1_step_summary.csv")
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for line in open(src):
+            f_ = line.strip().split(",")
+            if f_[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f_[2]) * mult[f_[1]]
+        traffic, traffic_src = tot, "profiles/r1_ncu_c1_step_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+    except Exception:
+        pass
     roofline = {"bound": "fp64_fma", "kernel": "scalar_step_kernel<%s> (all bold entries, orders 0-4)" % ("real" if dom_name == "step_real" else "complex"), "achieved": achieved,
                 "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 "peak_source": "measured in this process by qiw_measure_fp64_peak (DFMA-saturating kernel); "
                                "MEASURED_PEAKS.json has no FP64 entry",
-                "flops_per_launch": dom_flops, "ms_per_launch": dom_ms, "traffic": None,
+                "flops_per_launch": dom_flops, "ms_per_launch": dom_ms, "traffic": traffic, "traffic_unit": "bytes", "traffic_source": traffic_src,
                 "launches_per_run": n_step_launches,
                 "kernel_share_of_step": dom["ms"] / total_prof if total_prof else None,
                 "ms_per_launch_profiled": dom["ms"] / max(dom["launches"], 1),
