@@ -365,3 +365,42 @@ def test_edge_cases(gpu_ctx, qlib, oracle_lib, monkeypatch):
     got_cplx = gpu_ctx.eval(0.0, grid2.tau[4], grid2.tau[5], ids2, 64)
     monkeypatch.delenv("QIW_FORCE_COMPLEX")
     assert relerr(got_real, ref) < RTOL and relerr(got_cplx, ref) < RTOL
+
+
+def test_full_size_properties(gpu_ctx, qlib):
+    """BASELINE.json configs[0] at full size (README Anderson model, n_tau = 200, orders 0:4, N = 2^10), where
+    the oracle would take minutes: size-independent properties instead.
+      * Z and rho_imp against the regression anchors of SURVEY.md (R3: restatement predictions for the
+        current algorithm, good to ~1e-6) and rho against README.md:204 (2e-5);
+      * Tr rho = 1, spin symmetry rho_up = rho_dn exactly (the two flavours run through identical arithmetic);
+      * bit-identical results run to run (fixed-order reductions);
+      * additivity over disjoint Sobol index ranges at N = 2^17 (what the multi-GPU sharding relies on)."""
+    from qinchworm_b200 import ppgf
+    from qinchworm_b200.inchworm import Solver, inchworm, _bold_entries
+    ex, grid, f = models.anderson(n_tau=200)
+    P0 = ex.P.copy()
+    solver = Solver(ex, ctx=gpu_ctx)
+    inchworm(ex, grid, range(0, 5), range(0, 5), 2 ** 10, solver=solver)
+    P1 = ex.P.copy()
+    Z = ppgf.partition_function(ex)
+    assert abs(Z - 1.9428382858) < 5e-6 * 1.94
+    ppgf.normalize(ex)
+    rho = np.array([d[0, 0].real for d in ppgf.density_matrix(ex)])
+    assert np.abs(rho - np.array([0.5147108781, 0.2304382136, 0.2304382136, 0.0244126947])).max() < 2e-6
+    assert np.abs(rho - np.array([0.5147267752890132, 0.23043341978635334, 0.23043341978635334, 0.02440638513828009])).max() < 3e-5
+    assert abs(rho.sum() - 1.0) < 1e-12 and rho[1] == rho[2]
+    ex.P[:] = P0
+    inchworm(ex, grid, range(0, 5), range(0, 5), 2 ** 10, solver=solver)
+    assert np.array_equal(ex.P, P1)
+    # additivity over sample ranges with the machine full
+    ex.P[:] = P1
+    solver.upload_P()
+    N = 2 ** 17
+    bold = _bold_entries(solver, range(0, 5), N, None, None)
+    ids = [t.entry_id for t in bold]
+    tau = grid.tau
+    whole = gpu_ctx.eval(0.0, tau[120], tau[121], ids, N)
+    cuts = [0, 12345, 65536, 100001, N]
+    parts = sum(gpu_ctx.eval_range(0.0, tau[120], tau[121], ids, N, a, b - a) for a, b in zip(cuts[:-1], cuts[1:]))
+    parts[0] = whole[0]      # the exact order-0 entry is evaluated in full by every range call
+    assert relerr(parts, whole) < 1e-12
