@@ -60,30 +60,56 @@ def diagram_evals(N, n_tau=N_TAU, bold_steps=None):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons sampled DURING the timed region: NVML every ~5 ms (nvidia_ml_py), falling
+    back to nvidia-smi polling."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, device_index):
         super().__init__(daemon=True)
         self.dev, self.samples, self.reasons, self.stop_flag, self.max_mhz = device_index, [], set(), False, None
+        self.source = "nvidia-smi"
+
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[self.dev]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.dev
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        self.source = "nvml"
+        while not self.stop_flag:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for n, b_ in bits.items():
+                if r & b_:
+                    self.reasons.add(n)
+            time.sleep(0.005)
 
     def run(self):
+        try:
+            return self._run_nvml()
+        except Exception:
+            self.source = "nvidia-smi"
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip().split(",")
                 self.samples.append(float(out[0]))
                 self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
+                for n, v in zip(self.NAMES, out[2:]):
                     if v.strip().lower().startswith("active"):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}
 
 
 def cpu_port_run(threads, bold_steps, N):

@@ -172,3 +172,67 @@ def test_block_basis_rotation_invariance(oracle_lib):
         from qinchworm_b200 import ppgf
         vals.append(ex.ed.to_fock_basis(ppgf.density_matrix(ex)))
     assert np.abs(vals[0] - vals[1]).max() < 1e-12
+
+
+def test_block_brute_force_fock_space(oracle_lib):
+    """d_s > 1 is unpinned at the reference level: check the oracle's sector-block DFS against
+    a brute-force evaluation of the naive formula (src/configuration.jl:402-411,492-520) in the FULL Fock
+    space — dense matrices, every pair assigned to every arc, no sector bookkeeping, no pruning:
+        value = sum_topologies (-i) parity (-1)^n  sum_{pair per arc}  prod_arcs[i Delta_p(t_tail, t_head)]
+                * O_N iP(t_N, t_N-1) O_N-1 ... iP(t_2, t_1) O_1 ."""
+    import itertools
+    from program_interp import grid_interp
+    from oracle.oracle import topologies
+    ex, grid, f = models.two_level_mixed(n_tau=12, theta=0.6)
+    rng = np.random.default_rng(4)
+    ex.P = ex.P * (1.0 + 0.1 * rng.random(ex.P.shape))
+    pl = ex.flatten()
+    o = oracle_lib.Oracle(pl, ex.P)
+    ed, h, dimF = ex.ed, grid.beta / (grid.n_tau - 1), ex.ed.fock.dim
+    tau = grid.tau
+
+    def iP_full(t_f, t_i):
+        out = np.zeros((dimF, dimF), dtype=complex)
+        for s, (sp, u) in enumerate(zip(ed.subspaces, ed.unitaries)):
+            Ps = ex.P_sector(s)                       # [n_tau, d, d]
+            d = len(sp)
+            blk = np.array([[grid_interp(Ps[:, i, j], h, max(t_f, t_i), t_i) for j in range(d)] for i in range(d)])
+            out[np.ix_(sp, sp)] = u @ (1j * blk) @ u.conj().T
+        return out
+
+    def delta(p, t_f, t_i):
+        return 1j * grid_interp(np.asarray(ex.pairs[p].propagator.data), h, max(t_f, t_i), t_i)
+
+    eid = 0
+    for order, k in ((1, 1), (2, 1), (2, 3), (3, 2)):
+        pairs, parity = topologies(order, k)
+        o.set_topologies(eid, oracle_lib.MODE_BOLD, order, k, pairs, parity)
+        t_i, t_w, t_f = 0.0, tau[6], tau[7]
+        times = np.concatenate([np.sort(rng.uniform(t_w, t_f, k))[::-1], np.sort(rng.uniform(t_i, t_w, 2 * order - k))[::-1]])
+        ref = o.eval_at_times(eid, t_i, t_w, t_f, times[None, :])[0]
+        # backbone: positions in increasing time; fixed nodes t_i (pos 1), t_w (pos d_before + 2), t_f (last)
+        d_before = 2 * order - k
+        n_nodes = 2 * order + 3
+        tpos = np.zeros(n_nodes + 1)
+        free = [p for p in range(n_nodes, 0, -1) if p not in (1, d_before + 2, n_nodes)]   # high -> low = vertex 1, 2, ...
+        tpos[1], tpos[d_before + 2], tpos[n_nodes] = t_i, t_w, t_f
+        for v, p in enumerate(free):
+            tpos[p] = times[v]
+        total = np.zeros((dimF, dimF), dtype=complex)
+        I = np.eye(dimF)
+        for top, par in zip(pairs, parity):
+            for assign in itertools.product(range(len(ex.pairs)), repeat=order):
+                ops = {p: I for p in range(1, n_nodes + 1)}
+                w = 1.0 + 0j
+                for a, (va, vb) in enumerate(top):
+                    p_tail, p_head = free[va - 1], free[vb - 1]          # vertex a < b: a is the later time (tail)
+                    ops[p_tail] = np.asarray(ex.pairs[assign[a]].operator_f, dtype=complex)
+                    ops[p_head] = np.asarray(ex.pairs[assign[a]].operator_i, dtype=complex)
+                    w *= delta(assign[a], tpos[p_tail], tpos[p_head])
+                chain = ops[1]
+                for p in range(2, n_nodes + 1):
+                    chain = ops[p] @ iP_full(tpos[p], tpos[p - 1]) @ chain
+                total += (-1j) * par * (-1) ** order * w * chain
+        got = ex.pack_blocks([u.conj().T @ total[np.ix_(sp, sp)] @ u for sp, u in zip(ed.subspaces, ed.unitaries)])
+        assert np.abs(got - ref).max() < 1e-12 * max(np.abs(ref).max(), 1e-300), (order, k)
+        eid += 1
