@@ -967,6 +967,9 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
     sp.entries = ctx->dEntries.p; sp.dyn = pl.d_dyn.p;
     sp.P = ctx->dP.p; sp.E = ctx->dE.p; sp.deltas = ctx->dDeltas.p;
     for (int t = 0; t < kInlineTables && t < (int)ctx->hDeltas.size(); ++t) sp.deltas_inline[t] = ctx->hDeltas[t];
+    sp.tables_on_grid = (ctx->tables.size() <= (size_t)kInlineTables) ? 1 : 0;
+    for (auto& tb : ctx->tables)
+        if (tb.n > 0 && (tb.kind != 0 || tb.n != ctx->n_tau || tb.beta != ctx->beta)) sp.tables_on_grid = 0;
     sp.S = m.S; sp.bsize = m.bsize; sp.n_tau = ctx->n_tau; sp.h = ctx->beta / (ctx->n_tau - 1); sp.inv_h = 1.0 / sp.h;
     sp.t_i = t_i; sp.t_w = t_w; sp.t_f = t_f;
     sp.partials = pl.d_partials.p;

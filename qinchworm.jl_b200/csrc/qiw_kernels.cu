@@ -161,6 +161,32 @@ __device__ __forceinline__ GridCell grid_cell_from(int a, double w1, int b, doub
     else { c.c00 = (1.0 - w1) * (1.0 - w2); c.c10 = w1 * (1.0 - w2); c.c01 = (1.0 - w1) * w2; c.c11 = w1 * w2; }
     return c;
 }
+// Branch-free form used by the table fill: three table indices and three coefficients,
+//   value = ck D[i0] + cp D[ip] + cm D[im]
+// (k = 0: (1 - w) D[0] + w D[1]; else (c00 + c11) D[k] + c10 D[k+1] + c01 D[k-1]); differs from the reference's
+// operation order by O(ulp), and lets the compiler overlap the loads of consecutive table slots.
+struct GridCell3 { int i0, ip, im; double ck, cp, cm; };
+__device__ __forceinline__ GridCell3 grid_cell3_from(int a, double w1, int b, double w2) {
+    GridCell3 c;
+    const int k = a - b;
+    const bool dg = (k == 0);
+    const double u1 = 1.0 - w1, u2 = 1.0 - w2, w = w1 - w2;
+    c.i0 = k; c.ip = k + 1; c.im = dg ? 0 : k - 1;
+    c.ck = dg ? 1.0 - w : fma(u1, u2, w1 * w2);
+    c.cp = dg ? w : w1 * u2;
+    c.cm = dg ? 0.0 : u1 * w2;
+    return c;
+}
+template <bool REAL>
+__device__ __forceinline__ typename Num<REAL>::T cell3_apply_i(const double2* __restrict__ D, int stride, const GridCell3& c) {
+    if constexpr (!REAL) {
+        const double2 dk = __ldg(D + (size_t)c.i0 * stride), dp = __ldg(D + (size_t)c.ip * stride), dm = __ldg(D + (size_t)c.im * stride);
+        return make_double2(-(c.ck * dk.y + c.cp * dp.y + c.cm * dm.y), c.ck * dk.x + c.cp * dp.x + c.cm * dm.x);
+    } else {
+        const double dk = __ldg(&D[(size_t)c.i0 * stride].y), dp = __ldg(&D[(size_t)c.ip * stride].y), dm = __ldg(&D[(size_t)c.im * stride].y);
+        return -(c.ck * dk + c.cp * dp + c.cm * dm);
+    }
+}
 // i * D(t_f, t_i) for a table D[k] = G(k h) with element stride `stride` (same operation order as
 // grid_interp; the real mode works on the imaginary components only).
 template <bool REAL>
@@ -591,23 +617,36 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
             const int nI = n_nodes - 1;
             // pair interactions first: they do not depend on the bold propagators, so in the device-resident
             // loop this part (like everything above) overlaps the previous step's tail (see below)
-            for (int task = threadIdx.x; task < nD * spb; task += nthr) {
-                const int q = task >> spb_sh, smp = task & spb_mask;
-                const bool ok = okflag[smp] != 0;
-                T* myrow = reinterpret_cast<T*>(Tb + smp * row_bytes);
-                const int4 ds = dslots_s[q];
-                const double th = times[ds.y * 32 + smp];
-                double tt = times[ds.x * 32 + smp];
-                if (tt < th) tt = th;                       // :407-410
-                const DevDelta& dt = ds.z < kInlineTables ? p.deltas_inline[ds.z] : p.deltas[ds.z];
-                T val;
-                if (dt.kind == 0 && dt.n == p.n_tau && dt.inv_h == p.inv_h) {   // table on the P grid: reuse the cells
-                    const int ih = ds.y * 32 + smp, it2 = (tt == th) ? ih : ds.x * 32 + smp;
-                    val = cell_apply_i<REAL>(dt.y, 1, grid_cell_from(cella[it2], cellw[it2], cella[ih], cellw[ih]));
-                } else {
-                    val = delta_apply_i<REAL>(dt, tt, th);
+            if (p.tables_on_grid) {   // every Delta table is a plain grid function on the P grid: branch-free, cells reused
+#pragma unroll 2
+                for (int task = threadIdx.x; task < nD * spb; task += nthr) {
+                    const int q = task >> spb_sh, smp = task & spb_mask;
+                    const int4 ds = dslots_s[q];
+                    const int ih = ds.y * 32 + smp;
+                    const int it2 = (times[ds.x * 32 + smp] <= times[ih]) ? ih : ds.x * 32 + smp;   // clamp (:407-410)
+                    const DevDelta& dt = p.deltas_inline[ds.z];
+                    const T val = cell3_apply_i<REAL>(dt.y, 1, grid_cell3_from(cella[it2], cellw[it2], cella[ih], cellw[ih]));
+                    reinterpret_cast<T*>(Tb + smp * row_bytes)[nP + q] = okflag[smp] ? val : N::zero();
                 }
-                myrow[nP + q] = ok ? val : N::zero();
+            } else {
+                for (int task = threadIdx.x; task < nD * spb; task += nthr) {
+                    const int q = task >> spb_sh, smp = task & spb_mask;
+                    const bool ok = okflag[smp] != 0;
+                    T* myrow = reinterpret_cast<T*>(Tb + smp * row_bytes);
+                    const int4 ds = dslots_s[q];
+                    const double th = times[ds.y * 32 + smp];
+                    double tt = times[ds.x * 32 + smp];
+                    if (tt < th) tt = th;                       // :407-410
+                    const DevDelta& dt = ds.z < kInlineTables ? p.deltas_inline[ds.z] : p.deltas[ds.z];
+                    T val;
+                    if (dt.kind == 0 && dt.n == p.n_tau && dt.inv_h == p.inv_h) {   // table on the P grid: reuse the cells
+                        const int ih = ds.y * 32 + smp, it2 = (tt == th) ? ih : ds.x * 32 + smp;
+                        val = cell_apply_i<REAL>(dt.y, 1, grid_cell_from(cella[it2], cellw[it2], cella[ih], cellw[ih]));
+                    } else {
+                        val = delta_apply_i<REAL>(dt, tt, th);
+                    }
+                    myrow[nP + q] = ok ? val : N::zero();
+                }
             }
             // Programmatic dependent launch: this grid may have been started while the previous step's grid
             // was still finishing.  Everything up to here used only data no kernel writes; the P table, the
@@ -630,9 +669,10 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
                     } else {
                         const bool sw = times[(q + 2) * 32 + smp] < ta;   // clamped: both ends in the earlier time's cell
                         const int ia = (q + 1) * 32 + smp, ib = sw ? ia : ia + 32;
-                        const GridCell cell = grid_cell_from(cella[ib], cellw[ib], cella[ia], cellw[ia]);
+                        const GridCell3 cell = grid_cell3_from(cella[ib], cellw[ib], cella[ia], cellw[ia]);
+#pragma unroll 4
                         for (int s = 0; s < S; ++s) {
-                            const T val = cell_apply_i<REAL>(p.P + s, p.bsize, cell);
+                            const T val = cell3_apply_i<REAL>(p.P + s, p.bsize, cell);
                             myrow[q * S + s] = ok ? val : N::zero();
                         }
                     }
