@@ -258,7 +258,7 @@ int qiw_create(const qiw_options* opts, qiw_context** out) {
     }
     qiw_context* ctx = new qiw_context();
     int dev = -1;
-    if (opts) { dev = opts->device; if (opts->warps_per_block > 0) ctx->warps = std::min(8, opts->warps_per_block); }
+    if (opts) { dev = opts->device; if (opts->warps_per_block > 0) { int w = std::min(8, opts->warps_per_block); ctx->warps = 1; while (ctx->warps * 2 <= w) ctx->warps *= 2; } }   // power of two
     if (dev < 0) cudaGetDevice(&dev);
     ctx->device = dev;
     if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||

@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
             // pair interactions first: they do not depend on the bold propagators, so in the device-resident
             // loop this part (like everything above) overlaps the previous step's tail (see below)
             if (p.tables_on_grid) {   // every Delta table is a plain grid function on the P grid: branch-free, cells reused
-#pragma unroll 2
+#pragma unroll 4
                 for (int task = threadIdx.x; task < nD * spb; task += nthr) {
                     const int q = task >> spb_sh, smp = task & spb_mask;
                     const int4 ds = dslots_s[q];
@@ -705,10 +705,20 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
 
     // -- 6. CTA result: warps summed in fixed order (CTAs without a sample block have not waited yet) --
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if ((int)threadIdx.x < S) {
-        double2 v = make_double2(0.0, 0.0);
-        for (int w2 = 0; w2 < nw; ++w2) v = cadd(v, red[threadIdx.x * nw + w2]);
-        p.partials[((size_t)blockIdx.z * gridDim.y * gridDim.x + (size_t)it.partial0 * gridDim.x + blockIdx.x) * S + threadIdx.x] = v;
+    if (warp == 0) {
+        // one load per lane and a fixed butterfly over the warps' sums instead of a chain of dependent loads
+        // (the shared-memory pipe is busy with the other CTAs' walks at this point); nw is a power of two <= 8
+        const int per = 32 / nw;                       // sectors per pass
+        for (int s0 = 0; s0 < S; s0 += per) {
+            const int s = s0 + lane / nw;
+            double2 v = (s < S) ? red[s * nw + (lane % nw)] : make_double2(0.0, 0.0);
+            for (int off = nw >> 1; off > 0; off >>= 1) {
+                v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, off);
+                v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, off);
+            }
+            if (s < S && (lane % nw) == 0)
+                p.partials[((size_t)blockIdx.z * gridDim.y * gridDim.x + (size_t)it.partial0 * gridDim.x + blockIdx.x) * S + s] = v;
+        }
     }
     if (trace && threadIdx.x == 0) trace[3] = clock64();
 
