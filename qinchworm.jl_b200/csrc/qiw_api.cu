@@ -990,7 +990,7 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
             sp.out = ctx->dBatchOut.p;
         }
         bool exchange_fused = false;
-        if (collective && ctx->peer_ready && ctx->n_ranks > 1 && pl.ids.size() * (size_t)m.bsize * sizeof(double2) <= kPeerSlotBytes) {
+        if (collective && ctx->peer_ready && ctx->n_ranks > 1 && pl.ids.size() * (size_t)m.bsize * sizeof(double2) * 2 <= kPeerSlotBytes) {   // every double travels as two 8-byte words
             sp.peer_ranks = ctx->n_ranks; sp.peer_rank = ctx->rank; sp.peer_seq = ++ctx->peer_seq;
             sp.peer_mail = ctx->dPeerPtrs.p; sp.peer_status = ctx->dPeerStatus.p;
             exchange_fused = true;

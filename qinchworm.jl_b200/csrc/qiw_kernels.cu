@@ -423,34 +423,45 @@ __device__ void fused_tail(const StepParams& pp, double t_i, double t_w, double 
     }
     if (p.peer_ranks > 1) {
         // ---- all-reduce over peer memory (replaces all_reduce!, src/mpi.jl:104-127) ----
+        // Low-latency protocol: every 8-byte store carries 4 bytes of payload and the 4-byte sequence number of
+        // this collective, so the receiver needs no separate flag and the sender no system-wide fence: a word is
+        // valid as soon as its flag matches (8-byte stores are single transactions on NVLink).  Each double
+        // travels as two such words.  Buffers alternate with the parity of the sequence number: a slot is
+        // rewritten two collectives later, after every peer has provably finished reading it.
         __syncthreads();
         const int par = (int)(p.peer_seq & 1ull);
+        const unsigned int seq32 = (unsigned int)(p.peer_seq % 0xFFFFFFFFull) + 1u;   // never 0 (the mailbox starts zeroed)
         const size_t my_slot = kPeerFlagBytes + ((size_t)p.peer_rank * 2 + par) * kPeerSlotBytes;
-        for (int q = 0; q < p.peer_ranks; ++q) {
-            double2* dst = reinterpret_cast<double2*>(p.peer_mail[q] + my_slot);
-            for (int o = threadIdx.x; o < n_out; o += blockDim.x) dst[o] = p.out[o];
+        const int n_dbl = 2 * n_out, n_words = 2 * n_dbl;
+        const double* outd = reinterpret_cast<const double*>(p.out);
+        for (int k = threadIdx.x; k < n_words; k += blockDim.x) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(outd[k >> 1]);
+            const unsigned int half = (k & 1) ? (unsigned int)(bits >> 32) : (unsigned int)bits;
+            const uint2 wd = make_uint2(half, seq32);
+            for (int q = 0; q < p.peer_ranks; ++q) {
+                if (q == p.peer_rank) continue;
+                uint2* dst = reinterpret_cast<uint2*>(p.peer_mail[q] + my_slot) + k;
+                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(wd.x), "r"(wd.y) : "memory");
+            }
         }
-        __threadfence_system();
-        __syncthreads();
-        if ((int)threadIdx.x < p.peer_ranks) {
-            // raise my flag in peer `threadIdx.x`'s mailbox, then wait for that peer's flag in mine
-            unsigned long long* theirs = reinterpret_cast<unsigned long long*>(p.peer_mail[threadIdx.x]) + p.peer_rank * 2 + par;
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(p.peer_seq) : "memory");
-            const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(p.peer_mail[p.peer_rank]) + threadIdx.x * 2 + par;
-            const unsigned long long t0 = globaltimer_ns();
-            unsigned long long seen;
-            do {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-                if (seen != p.peer_seq && globaltimer_ns() - t0 > 10000000000ull) { *p.peer_status = 1; break; }   // 10 s
-            } while (seen != p.peer_seq);
-        }
-        __syncthreads();
+        // receive: poll every word until its flag shows this collective, add the contributions in rank order
         const unsigned char* base = p.peer_mail[p.peer_rank] + kPeerFlagBytes;
-        for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
-            double2 v = make_double2(0.0, 0.0);
-            for (int q = 0; q < p.peer_ranks; ++q)
-                v = cadd(v, __ldcv(reinterpret_cast<const double2*>(base + ((size_t)q * 2 + par) * kPeerSlotBytes) + o));
-            p.out[o] = v;
+        const unsigned long long t0 = globaltimer_ns();
+        for (int j = threadIdx.x; j < n_dbl; j += blockDim.x) {
+            double v = 0.0;
+            for (int q = 0; q < p.peer_ranks; ++q) {
+                if (q == p.peer_rank) { v += outd[j]; continue; }
+                const uint2* src = reinterpret_cast<const uint2*>(base + ((size_t)q * 2 + par) * kPeerSlotBytes) + 2 * j;
+                uint2 lo, hi;
+                bool ok = true;
+                do {
+                    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo.x), "=r"(lo.y) : "l"(src) : "memory");
+                    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hi.x), "=r"(hi.y) : "l"(src + 1) : "memory");
+                    if ((lo.y != seq32 || hi.y != seq32) && globaltimer_ns() - t0 > 10000000000ull) { *p.peer_status = 1; ok = false; break; }   // 10 s
+                } while (lo.y != seq32 || hi.y != seq32);
+                if (ok) v += __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | (unsigned long long)lo.x));
+            }
+            reinterpret_cast<double*>(p.out)[j] = v;   // element j is read and written by this thread only
         }
     }
     if (p.finish_k_f < 0) return;
