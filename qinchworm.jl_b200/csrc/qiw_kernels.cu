@@ -1,16 +1,22 @@
 // qiw_kernels.cu — hand-written CUDA kernels (sm_100a) of the qMC diagram-evaluation hot path.
 //
-// Mapping: one LANE owns one scrambled-Sobol sample; a CTA owns 32 samples of one
-// entry (one TopologiesInputData) and a group of up to `warps` chunks of that entry's configuration
-// trees.  All warps of the CTA first build the per-sample tables in shared memory —
+// scalar_step_kernel (1x1 sector blocks): a CTA owns a block of <= 32 scrambled-Sobol samples
+// of one entry (one TopologiesInputData).  All warps first build the per-sample operand tables in shared
+// memory T[sample][slot] —
 //   Sobol point by Gray-code random access      (src/scrambled_sobol.jl:158-197)
 //   cube -> ordered-time simplex                (src/qmc_integrate.jl:225-235,425-449)
 //   i*P_s(t_pos, t_pos-1) for every interval/sector, i*Delta for every used arc/table
 //                                               (src/topology_eval.jl:357-374,397-416)
-// laid out [slot][lane] so that the 16-byte loads of the walk are bank-conflict free — and then
-// every warp replays its chunk of the pre-compiled, pruned configuration trees in lock step
-// (src/topology_eval.jl:454-556): the program word is warp-uniform, the data are per lane, partial
-// products of the chain live in registers (one complex per tree level).
+//   products of the propagators over segments of the backbone (factorised records, qiw_compile.cpp)
+// — and then every LANE takes one pre-compiled, pruned configuration (src/topology_eval.jl:454-556) whose
+// record of K + order operand slots it keeps in registers, and loops over the CTA's samples.  The last CTA
+// to finish reduces all partial sums in fixed order, exchanges them with the peer GPUs and applies
+// set_ppgf! / normalize! (fused tail).  In real mode (everything purely imaginary-time) the same kernel runs
+// in real arithmetic.
+//
+// block_walk_kernel (sector blocks up to 4x4, real arithmetic): lane = sample, warp-uniform replay of the
+// pruned configuration tree with the running matrix product in registers.  block_step_kernel is the general
+// complex path for block models.
 #include <cstdio>
 
 #include "qiw_device.cuh"
