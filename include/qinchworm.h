@@ -183,6 +183,15 @@ int qiw_eval_batch(qiw_context* ctx, int32_t n_times, const double* times, int32
                    const int32_t* entry_ids, const uint32_t* sobol_m, const uint32_t* sobol_x0,
                    uint64_t N_total, double* out);
 
+/* Randomised-qMC form of qiw_eval: the same entries at the same times with `n_seqs` independently scrambled
+ * Sobol sequences in ONE launch — the loop of mean_std_from_randomization (src/randomization.jl:93-99) when
+ * no early stop is requested (target_std = 0).  sobol_m / sobol_x0 hold, per sequence, the per-entry
+ * concatenated parameters exactly as in qiw_eval; out[n_seqs][n_entries] packed block vectors, from which the
+ * host forms mean and standard deviation. */
+int qiw_eval_seqs(qiw_context* ctx, double t_i, double t_w, double t_f, int32_t n_seqs, int32_t n_entries,
+                  const int32_t* entry_ids, const uint32_t* sobol_m, const uint32_t* sobol_x0, uint64_t N_total,
+                  double* out);
+
 /* Same, but evaluates only Sobol indices [start, start+count) and does NOT all-reduce: the
  * rank-local partial sum (already divided by N_total).  Used by hosts that own the collective. */
 int qiw_eval_range(qiw_context* ctx, double t_i, double t_w, double t_f, int32_t n_entries,

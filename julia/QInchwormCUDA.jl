@@ -154,25 +154,27 @@ unpack(s::Session, v::AbstractVector{ComplexF64}) = begin
     sbm
 end
 
-"One library call per scrambled sequence (mean_std_from_randomization stays in Julia, src/randomization.jl:86)."
+"""
+All scrambled sequences of `mean_std_from_randomization` (src/randomization.jl:86-100) in one library call
+(qiw_eval_seqs; target_std = 0, i.e. no early stop).  The sequences are constructed in the reference's order —
+entry by entry, N_seqs sequences each, because the reference calls mean_std_from_randomization per entry
+(src/inchworm.jl:142,174) — so the user's RNG stream is consumed identically.
+"""
 function eval_entries(s::Session, mode, t_i, t_w, t_f, top_data; corr_idx = 0)
     ids = Int32[entry_id!(s, td, mode, corr_idx) for td in top_data]
     N = top_data[1].N_samples
     rp = top_data[1].rand_params
-    samples = Matrix{ComplexF64}[]
-    for _ in 1:rp.N_seqs
-        m = UInt32[]; x0 = UInt32[]
-        for td in top_data
-            seq = ScrambledSobolSeq(2 * td.order, scramble_rng = rp.rng)   # consumes the user's RNG stream
-            append!(m, vec(permutedims(seq.m))); append!(x0, seq.x)        # C layout m[D][32]
-        end
-        out = zeros(ComplexF64, s.bsize, length(ids))
-        check(s.ctx, ccall((:qiw_eval, lib), Cint,
-            (Ctx, Float64, Float64, Float64, Int32, Ptr{Int32}, Ptr{UInt32}, Ptr{UInt32}, UInt64, Ptr{ComplexF64}),
-            s.ctx, t_i, t_w, t_f, length(ids), ids, m, x0, N, out))
-        push!(samples, out)
+    per_entry = [[ScrambledSobolSeq(2 * td.order, scramble_rng = rp.rng) for _ in 1:rp.N_seqs] for td in top_data]
+    m = UInt32[]; x0 = UInt32[]
+    for q in 1:rp.N_seqs, j in 1:length(top_data)
+        seq = per_entry[j][q]
+        append!(m, vec(permutedims(seq.m))); append!(x0, seq.x)          # C layout m[D][32]
     end
-    return samples
+    out = zeros(ComplexF64, s.bsize, length(ids), rp.N_seqs)
+    check(s.ctx, ccall((:qiw_eval_seqs, lib), Cint,
+        (Ctx, Float64, Float64, Float64, Int32, Int32, Ptr{Int32}, Ptr{UInt32}, Ptr{UInt32}, UInt64, Ptr{ComplexF64}),
+        s.ctx, t_i, t_w, t_f, rp.N_seqs, length(ids), ids, m, x0, N, out))
+    return [out[:, :, q] for q in 1:rp.N_seqs]
 end
 
 "mean / std over the randomised sequences (src/randomization.jl:93-99): std of a single sequence is NaN."

@@ -177,6 +177,8 @@ struct qiw_context {
     DevBuf<unsigned int> dCounter;   // arrival counters of the step kernel's fused tail (self-resetting), one per time triple
     DevBuf<double> dTimes3;          // batched evaluation: (t_i, t_w, t_f) triples
     DevBuf<double2> dBatchPartials, dBatchOut;
+    DevBuf<uint32_t> dSeqSobol;      // randomised qMC: per-sequence Sobol parameters
+    DevBuf<DevEntryDyn> dSeqDyn;
     double2* hOut = nullptr;  // pinned
     size_t hOutCap = 0;
     std::vector<std::unique_ptr<Plan>> plans;
@@ -282,7 +284,7 @@ int qiw_destroy(qiw_context* ctx) {
     ctx->dPeerPtrs.release(); ctx->dPeerStatus.release();
     ctx->dP.release(); ctx->dE.release(); ctx->dDeltas.release(); ctx->dEntries.release();
     ctx->dPerSample.release(); ctx->dTimes.release(); ctx->dHist.release(); ctx->dDiag.release(); ctx->dTrace.release(); ctx->dCounter.release();
-    ctx->dTimes3.release(); ctx->dBatchPartials.release(); ctx->dBatchOut.release();
+    ctx->dTimes3.release(); ctx->dBatchPartials.release(); ctx->dBatchOut.release(); ctx->dSeqSobol.release(); ctx->dSeqDyn.release();
     ctx->dDim.release(); ctx->dBoff.release(); ctx->dEoff.release(); ctx->dOpTarget.release(); ctx->dOpOff.release();
     ctx->dPool.release(); ctx->dPoolRe.release(); ctx->dScratch.release(); ctx->dWordsPtr.release(); ctx->dTreeOffPtr.release(); ctx->dXWordsPtr.release(); ctx->dNTrees.release();
     for (auto& t : ctx->tables) { t.y.release(); t.M.release(); }
@@ -958,13 +960,13 @@ struct FinishArgs { int k_f = -1; int normalize = 0; double2* hist = nullptr; co
 // `finish_done` whether the P update was fused.
 static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, double t_f, const FinishArgs* fin = nullptr,
                         bool* finish_done = nullptr, bool collective = false, bool* collective_done = nullptr,
-                        int n_times = 0) {
+                        int n_times = 0, const uint32_t* dev_seq_sobol = nullptr, int sobol_z_stride = 0) {
     if (finish_done) *finish_done = false;
     if (collective_done) *collective_done = false;
     const HostModel& m = ctx->model;
     StepParams sp;
     memset(&sp, 0, sizeof(sp));
-    sp.entries = ctx->dEntries.p; sp.dyn = pl.d_dyn.p;
+    sp.entries = ctx->dEntries.p; sp.dyn = dev_seq_sobol ? ctx->dSeqDyn.p : pl.d_dyn.p;
     sp.P = ctx->dP.p; sp.E = ctx->dE.p; sp.deltas = ctx->dDeltas.p;
     for (int t = 0; t < kInlineTables && t < (int)ctx->hDeltas.size(); ++t) sp.deltas_inline[t] = ctx->hDeltas[t];
     sp.tables_on_grid = (ctx->tables.size() <= (size_t)kInlineTables) ? 1 : 0;
@@ -974,6 +976,7 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
     sp.t_i = t_i; sp.t_w = t_w; sp.t_f = t_f;
     sp.partials = pl.d_partials.p;
     sp.finish_k_f = -1;
+    sp.sobol_z_stride = sobol_z_stride;
     if (m.scalar && !pl.explicit_mode) {
         const size_t need = (size_t)std::max(n_times, 1);
         if (ctx->dCounter.cap < need) {
@@ -1241,6 +1244,76 @@ int qiw_eval_batch(qiw_context* ctx, int32_t n_times, const double* times, int32
     rc = mark_ucache_valid(ctx, pl);
     if (rc) return rc;
     rc = nccl_allreduce(ctx, ctx->dBatchOut.p, n_out);   // one collective for the whole batch
+    if (rc) return rc;
+    rc = ensure_host_out(ctx, n_out);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->hOut, ctx->dBatchOut.p, n_out * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_ms = ms;
+    memcpy(out, ctx->hOut, n_out * sizeof(double2));
+    return QIW_OK;
+}
+
+int qiw_eval_seqs(qiw_context* ctx, double t_i, double t_w, double t_f, int32_t n_seqs, int32_t n_entries, const int32_t* ids,
+                  const uint32_t* sobol_m, const uint32_t* sobol_x0, uint64_t N_total, double* out) {
+    int rc = check_entries(ctx, n_entries, ids, "qiw_eval_seqs");
+    if (rc) return rc;
+    if (!out || !sobol_m || !sobol_x0 || n_seqs <= 0 || n_seqs > 65535 || N_total == 0 || N_total > 0xFFFFFFFFull)
+        return fail(ctx, QIW_ERR_BAD_ARG, "qiw_eval_seqs: bad argument");
+    cudaSetDevice(ctx->device);
+    const HostModel& m = ctx->model;
+    size_t md = 0, xd = 0;     // words per sequence in the caller's arrays
+    for (int i = 0; i < n_entries; ++i) { md += (size_t)ctx->entries[ids[i]]->prog.D * 32; xd += ctx->entries[ids[i]]->prog.D; }
+    if (!m.scalar) {   // block models: one launch per sequence
+        for (int z = 0; z < n_seqs; ++z) {
+            rc = qiw_eval(ctx, t_i, t_w, t_f, n_entries, ids, sobol_m + (size_t)z * md, sobol_x0 + (size_t)z * xd, N_total,
+                          out + (size_t)z * n_entries * m.bsize * 2);
+            if (rc) return rc;
+        }
+        return QIW_OK;
+    }
+    uint64_t start = 0, count = N_total;
+    rank_sub_range(N_total, ctx->n_ranks, ctx->rank, &start, &count);
+    rc = sync_static_tables(ctx);
+    if (rc) return rc;
+    Plan* plp = nullptr;
+    rc = get_plan(ctx, n_entries, ids, count, false, &plp);
+    if (rc) return rc;
+    Plan& pl = *plp;
+    rc = stage_call(ctx, pl, sobol_m, sobol_x0, start, count, N_total, true);   // weights, ranges (sequence 0's parameters)
+    if (rc) return rc;
+    // per-sequence parameter blocks in the plan's per-entry layout (m[D][32] then x0[D] per entry)
+    const size_t tot = pl.h_sobol.size();
+    std::vector<uint32_t> hs(tot * (size_t)n_seqs, 0u);
+    for (int z = 0; z < n_seqs; ++z) {
+        size_t moff = 0, xoff = 0;
+        for (int i = 0; i < n_entries; ++i) {
+            const int D = ctx->entries[ids[i]]->prog.D;
+            uint32_t* sb = hs.data() + (size_t)z * tot + pl.sobol_off[i];
+            memcpy(sb, sobol_m + (size_t)z * md + moff, (size_t)D * 32 * sizeof(uint32_t));
+            memcpy(sb + (size_t)D * 32, sobol_x0 + (size_t)z * xd + xoff, (size_t)D * sizeof(uint32_t));
+            moff += (size_t)D * 32; xoff += D;
+        }
+    }
+    CK(ctx->dSeqSobol.upload(hs.data(), hs.size(), ctx->stream));
+    std::vector<DevEntryDyn> dyn = pl.h_dyn;
+    for (int i = 0; i < n_entries; ++i) { dyn[i].sobol = ctx->dSeqSobol.p + pl.sobol_off[i]; dyn[i].ucache = nullptr; dyn[i].ucache_valid = 0; }
+    CK(ctx->dSeqDyn.upload(dyn.data(), dyn.size(), ctx->stream));
+    pl.ucache_valid = false;   // stage_call recorded sequence 0 as the plan's sequence: its cached roots are not trustworthy
+    pl.default_sobol_resident = false;
+    std::vector<double> times((size_t)n_seqs * 3);
+    for (int z = 0; z < n_seqs; ++z) { times[3 * z] = t_i; times[3 * z + 1] = t_w; times[3 * z + 2] = t_f; }
+    const size_t n_out = (size_t)n_seqs * n_entries * m.bsize;
+    CK(ctx->dTimes3.upload(times.data(), times.size(), ctx->stream));
+    CK(ctx->dBatchPartials.reserve((size_t)n_seqs * pl.partial_rows * m.bsize));
+    CK(ctx->dBatchOut.reserve(n_out));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    rc = enqueue_step(ctx, pl, t_i, t_w, t_f, nullptr, nullptr, false, nullptr, n_seqs, ctx->dSeqSobol.p, (int)tot);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    rc = nccl_allreduce(ctx, ctx->dBatchOut.p, n_out);
     if (rc) return rc;
     rc = ensure_host_out(ctx, n_out);
     if (rc) return rc;

@@ -80,6 +80,7 @@ struct StepParams {
     int max_slots;                 // operands per sample row reserved in shared memory
     int max_coefs, max_segdef;     // shared-memory staging sizes (largest entry of the launch)
     int spb, spb_log2;             // samples per CTA pass (power of two <= 32)
+    int sobol_z_stride;            // > 0: blockIdx.z selects a Sobol sequence (words between the sequences' parameter blocks)
     int tables_on_grid;            // every Delta table is a plain grid function on the P grid and described inline
     int allow_overlap;             // launch with programmatic stream serialization (QIW_PDL=1 enables; off by default)
     // explicit-times mode (qiw_eval_at_times): times[count][D], per-sample output, no reduction

@@ -542,7 +542,8 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
     const double lo_after = (e.mode == 0) ? t_i : t_w, len_after = t_f - lo_after;
     const double len_before = t_w - t_i;
 
-    const uint32_t* __restrict__ sm = dy.sobol;
+    // randomised qMC: blockIdx.z selects one of several scrambled sequences (no root cache then)
+    const uint32_t* __restrict__ sm = dy.sobol + (size_t)blockIdx.z * p.sobol_z_stride;
     const unsigned long long count = dy.count;
     const int n_sb = (int)((count + (unsigned long long)spb - 1ull) / (unsigned long long)spb);
 
@@ -576,7 +577,7 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
         //       host provides a cache they are computed once per run and re-read afterwards.
         if ((int)threadIdx.x < spb) okflag[threadIdx.x] = (local0 + threadIdx.x < count) ? 1 : 0;
         if (p.explicit_times == nullptr) {
-            double* uc = dy.ucache;
+            double* uc = p.sobol_z_stride ? nullptr : dy.ucache;
             for (int task = threadIdx.x; task < D * spb; task += nthr) {
                 const int j = task >> spb_sh, smp = task & spb_mask;
                 const unsigned long long local = local0 + smp;

@@ -119,13 +119,21 @@ class Solver:
         rp = top_data[0].rand_params
         assert all(td.N_samples == N for td in top_data)
         samples = []
-        for s in range(rp.N_seqs):
-            sobol = None
-            if rp.rng is not None:
-                sobol = [_scrambled_sequence(2 * td.order, rp.rng) for td in top_data]
-            samples.append(self.ctx.eval(t_i, t_w, t_f, ids, N, sobol=sobol))
-            if s > 0 and np.max(np.abs(np.std(samples, axis=0, ddof=1))) <= rp.target_std:
-                break
+        if rp.rng is not None and rp.N_seqs > 1 and rp.target_std == 0.0:
+            # no early stop: all sequences in ONE launch.  The scrambling bits are drawn in the reference's order —
+            # entry by entry, N_seqs sequences each (mean_std_from_randomization is called per entry,
+            # src/inchworm.jl:142,174) — so a host RNG stream is consumed identically.
+            per_entry = [[_scrambled_sequence(2 * td.order, rp.rng) for _ in range(rp.N_seqs)] for td in top_data]
+            seqs = [[per_entry[j][s] for j in range(len(top_data))] for s in range(rp.N_seqs)]
+            samples = list(self.ctx.eval_seqs(t_i, t_w, t_f, ids, N, seqs))
+        else:
+            for s in range(rp.N_seqs):
+                sobol = None
+                if rp.rng is not None:
+                    sobol = [_scrambled_sequence(2 * td.order, rp.rng) for td in top_data]
+                samples.append(self.ctx.eval(t_i, t_w, t_f, ids, N, sobol=sobol))
+                if s > 0 and np.max(np.abs(np.std(samples, axis=0, ddof=1))) <= rp.target_std:
+                    break
         mean = np.mean(samples, axis=0)
         with np.errstate(invalid="ignore", divide="ignore"):
             std = np.std(samples, axis=0, ddof=1) if len(samples) > 1 else np.full_like(mean, np.nan)

@@ -65,6 +65,8 @@ _SIGNATURES = {
     "qiw_eval": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int32, i32p, u32p, u32p,
                            C.c_uint64, f64p]),
     "qiw_eval_batch": (C.c_int, [C.c_void_p, C.c_int32, f64p, C.c_int32, i32p, u32p, u32p, C.c_uint64, f64p]),
+    "qiw_eval_seqs": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, i32p, u32p, u32p,
+                                C.c_uint64, f64p]),
     "qiw_eval_range": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int32, i32p, u32p, u32p,
                                  C.c_uint64, C.c_uint64, C.c_uint64, f64p]),
     "qiw_eval_at_times": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32,
@@ -322,6 +324,20 @@ class Context:
         _m, _x, pm, px = self._sobol_args(ids, sobol)
         self._ck(self.L.qiw_eval_batch(self.h, times.shape[0], _ptr(times, f64p), len(ids), _ptr(ids, i32p), pm, px,
                                        N_total, _ptr(out.view(np.float64), f64p)))
+        return out
+
+    def eval_seqs(self, t_i, t_w, t_f, entry_ids, N_total, sobol_seqs):
+        """qiw_eval_seqs: sobol_seqs[n_seqs][n_entries] = (m, x0); returns [n_seqs, n_entries, bsize]."""
+        ids = np.ascontiguousarray(entry_ids, dtype=np.int32)
+        ms, xs = [], []
+        for seq in sobol_seqs:
+            ms += [np.asarray(m, dtype=np.uint32).reshape(-1) for m, _ in seq]
+            xs += [np.asarray(x, dtype=np.uint32).reshape(-1) for _, x in seq]
+        mcat = np.ascontiguousarray(np.concatenate(ms + [np.zeros(1, np.uint32)]))
+        xcat = np.ascontiguousarray(np.concatenate(xs + [np.zeros(1, np.uint32)]))
+        out = np.zeros((len(sobol_seqs), len(ids), self.bsize), dtype=np.complex128)
+        self._ck(self.L.qiw_eval_seqs(self.h, t_i, t_w, t_f, len(sobol_seqs), len(ids), _ptr(ids, i32p), _ptr(mcat, u32p),
+                                      _ptr(xcat, u32p), N_total, _ptr(out.view(np.float64), f64p)))
         return out
 
     def eval_range(self, t_i, t_w, t_f, entry_ids, N_total, start, count, sobol=None):

@@ -404,3 +404,37 @@ def test_full_size_properties(gpu_ctx, qlib):
     parts = sum(gpu_ctx.eval_range(0.0, tau[120], tau[121], ids, N, a, b - a) for a, b in zip(cuts[:-1], cuts[1:]))
     parts[0] = whole[0]      # the exact order-0 entry is evaluated in full by every range call
     assert relerr(parts, whole) < 1e-12
+
+
+def test_randomised_sequences_in_one_launch(gpu_ctx, qlib, oracle_lib):
+    """qiw_eval_seqs (all scrambled sequences of mean_std_from_randomization in one launch) equals
+    one qiw_eval per sequence and the oracle; the host driver returns mean and std over the sequences."""
+    from qinchworm_b200.inchworm import RandomizationParams, Solver, inchworm_step, _bold_entries
+    ex, grid, f = models.anderson(n_tau=20)
+    solver = Solver(ex, ctx=gpu_ctx)
+    o = oracle_lib.Oracle(solver.payload, ex.P)
+    rp = RandomizationParams(rng=np.random.default_rng(3), N_seqs=5, target_std=0.0)
+    top_data = _bold_entries(solver, range(0, 4), 2 ** 8, rp, None)
+    ids = [td.entry_id for td in top_data]
+    for j, td in enumerate(top_data):
+        o.set_topologies(j, qlib.MODE_BOLD, td.order, td.n_pts_after, td.topologies[0], td.topologies[1])
+    rng = np.random.default_rng(17)
+    seqs = []
+    for s_ in range(3):
+        one = []
+        for td in top_data:
+            D = 2 * td.order
+            m = qlib.sobol_direction_numbers(D)
+            one.append(qlib.sobol_scramble(m, rng.integers(0, 2, (D, 32)), rng.integers(0, 2, (D, 32, 32))) if D
+                       else (m, np.zeros(0, dtype=np.uint32)))
+        seqs.append(one)
+    tau = grid.tau
+    got = gpu_ctx.eval_seqs(0.0, tau[9], tau[10], ids, 2 ** 8, seqs)
+    for z in range(3):
+        one = gpu_ctx.eval(0.0, tau[9], tau[10], ids, 2 ** 8, sobol=seqs[z])
+        ref = o.eval(0.0, tau[9], tau[10], list(range(len(ids))), 2 ** 8, sobol=seqs[z])
+        assert relerr(got[z], one) < 1e-13 and relerr(got[z], ref) < RTOL
+    # afterwards the default (unscrambled) sequence must be back in place
+    assert relerr(gpu_ctx.eval(0.0, tau[9], tau[10], ids, 2 ** 8), o.eval(0.0, tau[9], tau[10], list(range(len(ids))), 2 ** 8)) < RTOL
+    value, contribs, contribs_std = inchworm_step(solver, grid, 0, 9, 10, top_data)
+    assert np.isfinite(contribs_std[3]).all() and np.abs(contribs_std[3]).max() > 0 and np.abs(contribs_std[0]).max() == 0
