@@ -1,5 +1,5 @@
 """Profiling driver: README Anderson configuration (C1), `runs` device-resident inchworm! runs.
-Used under ncu (see profiles/README.md); numbers printed by a run under ncu are not bench values."""
+Used under ncu (profiles/run_profiles.sh); numbers printed by a run under ncu are not bench values."""
 import os
 import sys
 
