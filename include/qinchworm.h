@@ -151,6 +151,11 @@ int qiw_entry_program(qiw_context* ctx, int32_t entry_id, int64_t* n_words, uint
  *   rec2[n_leaves][L2 + 1], segdef[nSeg][seg_stride] */
 int qiw_entry_records(qiw_context* ctx, int32_t entry_id, int32_t* info, uint32_t* rec2, uint16_t* segdef);
 
+/* Paired form of the same records (csrc/qiw_host.hpp EntryProgram::rec_pair / rec_left) — what the summing walk
+ * of the step kernel executes.  info[4] = n_pairs, words per pair record (2 + 2K + order), n_left, words per
+ * leftover record (L2 + 1).  Call with NULL arrays to get the sizes. */
+int qiw_entry_pair_records(qiw_context* ctx, int32_t entry_id, int32_t* info, uint32_t* rec_pair, uint32_t* rec_left);
+
 /* ---- the hot path ---------------------------------------------------------------------------- */
 
 /* Evaluate `n_entries` entries at the fixed times (t_i, t_w, t_f) with N_total Sobol points each.

@@ -17,7 +17,7 @@
 #include "qiw_host.hpp"
 
 namespace qiw {
-cudaError_t launch_scalar_step(bool real_mode, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_scalar_step(bool real_mode, bool pairs, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st);
 cudaError_t launch_reduce(const DevEntryDyn* dyn, const DevEntry* entries, const double2* partials, int pitch, int S,
                           double t_i, double t_w, double t_f, double2* out, int n_entries, cudaStream_t st);
 cudaError_t launch_finish_step(double2* P, int n_tau, int bsize, const int* diag, int n_diag, double h, int k_f,
@@ -89,7 +89,7 @@ struct DevBuf {
 struct EntryDev {
     EntryProgram prog;
     bool valid = false;
-    DevBuf<uint32_t> records;
+    DevBuf<uint32_t> records, records_pair, records_left;
     DevBuf<uint16_t> segdef;
     bool imag_coefs = false;     // every folded coefficient is purely imaginary (real-mode precondition)
     DevBuf<uint64_t> words;      // block models: tree word stream
@@ -289,7 +289,7 @@ int qiw_destroy(qiw_context* ctx) {
     ctx->dPool.release(); ctx->dPoolRe.release(); ctx->dScratch.release(); ctx->dWordsPtr.release(); ctx->dTreeOffPtr.release(); ctx->dXWordsPtr.release(); ctx->dNTrees.release();
     for (auto& t : ctx->tables) { t.y.release(); t.M.release(); }
     for (auto& e : ctx->entries)
-        if (e) { e->records.release(); e->segdef.release(); e->words.release(); e->xwords.release(); e->tree_off.release(); e->coefs.release(); e->dslots.release(); e->sobol.release(); }
+        if (e) { e->records.release(); e->records_pair.release(); e->records_left.release(); e->segdef.release(); e->words.release(); e->xwords.release(); e->tree_off.release(); e->coefs.release(); e->dslots.release(); e->sobol.release(); }
     for (auto& pl : ctx->plans) release_plan(*pl);
     ctx->plans.clear();
     if (ctx->hOut) cudaFreeHost(ctx->hOut);
@@ -463,6 +463,27 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
                 }
             }
         CK(ed.records.upload(rec.data(), rec.size(), ctx->stream));
+        {   // the same configurations as pairs + leftovers (what the summing walk executes), transposed alike
+            auto transpose = [&](const std::vector<uint32_t>& src, int64_t n_rec, int RLs, bool pair, DevBuf<uint32_t>& dst_buf) -> cudaError_t {
+                const int64_t ngs = (n_rec + 31) / 32;
+                std::vector<uint32_t> t((size_t)std::max<int64_t>(ngs, 1) * RLs * 32, 0u);
+                for (int64_t g = 0; g < ngs; ++g)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int64_t r = g * 32 + lane;
+                        uint32_t* dst = t.data() + (size_t)g * RLs * 32 + lane;
+                        if (r < n_rec) {
+                            for (int q = 0; q < RLs; ++q) dst[(size_t)q * 32] = src[(size_t)r * RLs + q];
+                        } else {   // padding lanes: zero coefficient(s), sector of the last record
+                            const uint32_t s_last = n_rec ? (src[(size_t)(n_rec - 1) * RLs] >> 16) : 0u;
+                            dst[0] = (uint32_t)pr.coefs.size() | (s_last << 16);
+                            if (pair) dst[32] = (uint32_t)pr.coefs.size();
+                        }
+                    }
+                return dst_buf.upload(t.data(), t.size(), ctx->stream);
+            };
+            CK(transpose(pr.rec_pair, pr.n_pairs, 2 + 2 * pr.K + pr.order, true, ed.records_pair));
+            CK(transpose(pr.rec_left, pr.n_left, pr.L2 + 1, false, ed.records_left));
+        }
         {   // segment definitions transposed into groups of 32 entries; padding -> the constant-one slot
             const int nsg = (pr.nSeg + 31) / 32, st = pr.seg_stride;
             const uint16_t one = (uint16_t)(pr.nP + (int)pr.dslots.size() + pr.nSeg);
@@ -584,6 +605,17 @@ int qiw_entry_records(qiw_context* ctx, int32_t id, int32_t* info, uint32_t* rec
     return QIW_OK;
 }
 
+int qiw_entry_pair_records(qiw_context* ctx, int32_t id, int32_t* info, uint32_t* rec_pair, uint32_t* rec_left) {
+    if (!ctx || id < 0 || id >= (int)ctx->entries.size() || !ctx->entries[id] || !ctx->entries[id]->valid)
+        return fail(ctx, QIW_ERR_BAD_ARG, "qiw_entry_pair_records: unknown entry");
+    const EntryProgram& p = ctx->entries[id]->prog;
+    if (!p.scalar) return fail(ctx, QIW_ERR_UNSUPPORTED, "qiw_entry_pair_records: only 1x1-block models have configuration records");
+    if (info) { info[0] = (int32_t)p.n_pairs; info[1] = 2 + 2 * p.K + p.order; info[2] = (int32_t)p.n_left; info[3] = p.L2 + 1; }
+    if (rec_pair) memcpy(rec_pair, p.rec_pair.data(), p.rec_pair.size() * sizeof(uint32_t));
+    if (rec_left) memcpy(rec_left, p.rec_left.data(), p.rec_left.size() * sizeof(uint32_t));
+    return QIW_OK;
+}
+
 }  // extern "C"
 
 // ---- launch planning ---------------------------------------------------------------------------
@@ -617,6 +649,8 @@ static int sync_static_tables(qiw_context* ctx) {
             d.nP = p.nP; d.nD = (int)p.dslots.size();
             d.L2 = p.L2; d.n_leaves = (int)p.n_leaves; d.n_groups = (int)((p.n_leaves + 31) / 32); d.n_coefs = (int)p.coefs.size();
             d.nSeg = p.nSeg; d.seg_stride = p.seg_stride; d.segdef = ed.segdef.p;
+            d.records_pair = ed.records_pair.p; d.records_left = ed.records_left.p; d.K = p.K;
+            d.n_groups_pair = (int)((p.n_pairs + 31) / 32); d.n_groups_left = (int)((p.n_left + 31) / 32);
             d.exact = (p.order == 0);
             for (int k = 0; k <= kDevMaxNodes; ++k) d.pos_src[k] = p.pos_src[k];
             d.records = ed.records.p; d.coefs = ed.coefs.p; d.dslots = ed.dslots.p;
@@ -1060,7 +1094,9 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         dim3 grid((unsigned)pl.pitch, (unsigned)g.n_items, (unsigned)std::max(n_times, 1));
         {
             ProfScope ps(ctx, real ? 1 : 0);
-            CK(launch_scalar_step(real != 0, gp, grid, ctx->warps * 32, g.smem[real], ctx->stream));
+            bool pairs = false;
+            for (int id : pl.ids) if (ctx->entries[id]->prog.n_pairs > 0) pairs = true;
+            CK(launch_scalar_step(real != 0, pairs, gp, grid, ctx->warps * 32, g.smem[real], ctx->stream));
         }
         ctx->launches++;
     }

@@ -33,6 +33,10 @@ struct DevEntry {
     int nSeg, seg_stride;       // segment-product table: entries, propagator slots per entry
     const uint32_t* records;    // transposed: [n_groups][L2 + 1][32 lanes]; word 0 = coef | s_i << 16,
                                 // words 1..L2 = operand slot inside a sample's table row
+    // paired form of the same configurations (EntryProgram::rec_pair / rec_left), what the summing walk executes:
+    const uint32_t* records_pair;   // transposed [n_groups_pair][2 + 2K + order][32 lanes]
+    const uint32_t* records_left;   // transposed [n_groups_left][L2 + 1][32 lanes]
+    int n_groups_pair, n_groups_left, K;
     const uint16_t* segdef;     // transposed [groups of 32 entries][seg_stride][32 lanes]: propagator slots of each
                                 // segment product; unused positions point at the row's constant-one slot
     const double2* coefs;

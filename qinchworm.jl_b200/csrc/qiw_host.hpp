@@ -76,6 +76,14 @@ struct EntryProgram {
     //   rec2[K+1..K+order] = slot of the pair-interaction factor (nP + dslot index)
     // segdef[nSeg][seg_stride]: propagator slots multiplied into each segment product (0xFFFF = unused).
     std::vector<uint32_t> rec2;
+    // Paired records.  Configurations that share all pair-interaction factors and the initial sector (they
+    // differ in the flavours running along the backbone, hence in the segment products) are evaluated two at
+    // a time:  prod(Delta) * (coefA * prod(segA) + coefB * prod(segB))  — the Delta operands are loaded once.
+    //   rec_pair[0] = coefA | initial sector << 16, rec_pair[1] = coefB,
+    //   rec_pair[2..2+K) = segA slots, [2+K..2+2K) = segB slots, [2+2K..2+2K+order) = Delta slots
+    // rec_left holds the configurations without a partner in the rec2 format.
+    std::vector<uint32_t> rec_pair, rec_left;
+    int64_t n_pairs = 0, n_left = 0;
     std::vector<uint16_t> segdef;
     int K = 0, L2 = 0, nSeg = 0, seg_stride = 0;
     // statistics

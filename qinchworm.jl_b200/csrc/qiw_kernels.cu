@@ -362,6 +362,99 @@ __device__ __forceinline__ void config_walk(const uint32_t* __restrict__ rec_t, 
     }
 }
 
+// Paired records (EntryProgram::rec_pair): two configurations with identical pair-interaction operands and
+// initial sector,  prod(Delta) * (coefA * prod(segA) + coefB * prod(segB)):  ND + 2K operands instead of 2 (ND + K).
+template <int ND, int K, bool REAL>
+__device__ __forceinline__ void pair_walk(const uint32_t* __restrict__ rec_t, int g0, int g1, const unsigned char* Tb,
+                                          int row_bytes, int spb, const typename Num<REAL>::T* coefs_s, double2* red,
+                                          int nw, int warp, int lane) {
+    typedef typename Num<REAL>::T T;
+    typedef Num<REAL> N;
+    constexpr int SH = REAL ? 3 : 4;
+    constexpr int RL = 2 + 2 * K + ND;
+    for (int g = g0; g < g1; ++g) {
+        uint32_t w[RL];
+        const uint32_t* rp = rec_t + (size_t)g * RL * 32 + lane;
+#pragma unroll
+        for (int q = 0; q < RL; ++q) w[q] = __ldg(rp + q * 32);
+#pragma unroll
+        for (int q = 2; q < RL; ++q) w[q] <<= SH;
+        const int s_i = (int)(w[0] >> 16);
+        const T coefA = coefs_s[w[0] & 0xFFFFu], coefB = coefs_s[w[1] & 0xFFFFu];
+        const int smin = (int)__reduce_min_sync(0xFFFFFFFFu, (unsigned)s_i);
+        const int smax = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)s_i);
+        T accA = N::zero(), accB = N::zero();
+        // four samples in flight per iteration (spb is a power of two; blocks smaller than 4 take the scalar loop)
+        int smp = 0;
+        for (; smp + 3 < spb; smp += 4) {
+            const unsigned char* row = Tb + smp * row_bytes;
+            T d[4], sa[4], sb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned char* r = row + u * row_bytes;
+                d[u] = *reinterpret_cast<const T*>(r + w[2 + 2 * K]);
+                sa[u] = *reinterpret_cast<const T*>(r + w[2]);
+                sb[u] = *reinterpret_cast<const T*>(r + w[2 + K]);
+            }
+#pragma unroll
+            for (int f = 1; f < ND; ++f)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) d[u] = N::mul(d[u], *reinterpret_cast<const T*>(row + u * row_bytes + w[2 + 2 * K + f]));
+#pragma unroll
+            for (int f = 1; f < K; ++f)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    sa[u] = N::mul(sa[u], *reinterpret_cast<const T*>(row + u * row_bytes + w[2 + f]));
+                    sb[u] = N::mul(sb[u], *reinterpret_cast<const T*>(row + u * row_bytes + w[2 + K + f]));
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                accA = N::add(accA, N::mul(d[u], sa[u]));
+                accB = N::add(accB, N::mul(d[u], sb[u]));
+            }
+        }
+        for (; smp < spb; ++smp) {
+            const unsigned char* row = Tb + smp * row_bytes;
+            T d = *reinterpret_cast<const T*>(row + w[2 + 2 * K]);
+#pragma unroll
+            for (int f = 1; f < ND; ++f) d = N::mul(d, *reinterpret_cast<const T*>(row + w[2 + 2 * K + f]));
+            T sa = *reinterpret_cast<const T*>(row + w[2]);
+            T sb = *reinterpret_cast<const T*>(row + w[2 + K]);
+#pragma unroll
+            for (int f = 1; f < K; ++f) {
+                sa = N::mul(sa, *reinterpret_cast<const T*>(row + w[2 + f]));
+                sb = N::mul(sb, *reinterpret_cast<const T*>(row + w[2 + K + f]));
+            }
+            accA = N::add(accA, N::mul(d, sa));
+            accB = N::add(accB, N::mul(d, sb));
+        }
+        const double2 c = cadd(N::result(coefA, accA), N::result(coefB, accB));
+        for (int s = smin; s <= smax; ++s) {
+            double2 r = (s_i == s) ? c : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                if constexpr (!REAL) r.x += __shfl_down_sync(0xFFFFFFFFu, r.x, off);
+                r.y += __shfl_down_sync(0xFFFFFFFFu, r.y, off);
+            }
+            if (lane == 0) red[s * nw + warp] = cadd(red[s * nw + warp], r);
+        }
+    }
+}
+
+template <bool REAL>
+__device__ __forceinline__ void pair_dispatch(int nd, int K, const uint32_t* rec_t, int g0, int g1, const unsigned char* Tb,
+                                              int row_bytes, int spb, const typename Num<REAL>::T* coefs_s, double2* red,
+                                              int nw, int warp, int lane) {
+#define QIW_PC(D_, K_) case (D_ * 8 + K_): pair_walk<D_, K_, REAL>(rec_t, g0, g1, Tb, row_bytes, spb, coefs_s, red, nw, warp, lane); break;
+#define QIW_PK(D_) QIW_PC(D_, 1) QIW_PC(D_, 2) QIW_PC(D_, 3) QIW_PC(D_, 4)
+    switch (nd * 8 + K) {
+        QIW_PK(1) QIW_PK(2) QIW_PK(3) QIW_PK(4) QIW_PK(5) QIW_PK(6) QIW_PK(7) QIW_PK(8)
+        default: break;
+    }
+#undef QIW_PK
+#undef QIW_PC
+}
+
 // Record lengths: K + order operands, K <= 4 segments, order <= 8.
 template <bool REAL, bool PER_SAMPLE>
 __device__ __forceinline__ void walk_dispatch(int L, const uint32_t* rec_t, int g0, int g1, const unsigned char* Tb,
@@ -502,7 +595,9 @@ __device__ void fused_tail(const StepParams& pp, double t_i, double t_w, double 
 
 // ---- the step kernel (scalar models: every sector block is 1x1) ------------------------------
 
-template <bool REAL, bool PER_SAMPLE>
+// PAIRS: the launch contains entries with paired records (their walk code is only in this instantiation, so
+// that the common orders <= 4 case keeps a small instruction footprint — the N = 2^10 step is latency-bound).
+template <bool REAL, bool PER_SAMPLE, bool PAIRS>
 __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p) {
     typedef typename Num<REAL>::T T;
     typedef Num<REAL> N;
@@ -547,12 +642,17 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
     const unsigned long long count = dy.count;
     const int n_sb = (int)((count + (unsigned long long)spb - 1ull) / (unsigned long long)spb);
 
-    // this warp's share of the entry's configuration groups (32 configurations per group)
-    int g0 = 0, g1 = 0;
+    // this warp's share of the entry's configuration groups (32 records per group): all records for the
+    // per-sample evaluation, pairs + leftovers for the summing walk
+    int g0 = 0, g1 = 0, pg0 = 0, pg1 = 0;
     if (warp < it.n_chunks) {
-        const long long c = it.chunk0 + warp, nct = it.n_chunks_total, ng = e.n_groups;
+        const long long c = it.chunk0 + warp, nct = it.n_chunks_total;
+        const long long ng = PAIRS ? e.n_groups_left : e.n_groups, npg = PAIRS ? e.n_groups_pair : 0;
         g0 = (int)(c * ng / nct);
         g1 = (int)((c + 1) * ng / nct);
+        // pairs are dealt in the opposite direction so that a warp short on pairs gets more leftovers
+        pg0 = (int)((nct - 1 - c) * npg / nct);
+        pg1 = (int)((nct - c) * npg / nct);
     }
 
     // optional per-CTA timeline (diagnostics; compiled in only with -DQIW_TRACE_BUILD because
@@ -711,9 +811,12 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
         if (trace && threadIdx.x == 0) trace[1] = clock64();
 
         // -- 5. this warp's configurations -----------------------------------------------------
+        if constexpr (PAIRS) {
+            if (pg0 < pg1) pair_dispatch<REAL>(e.order, e.K, e.records_pair, pg0, pg1, Tb, row_bytes, spb, coefs_s, red, nw, warp, lane);
+        }
         if (g0 < g1) {
-            walk_dispatch<REAL, PER_SAMPLE>(e.L2, e.records, g0, g1, Tb, row_bytes, spb, coefs_s, red, nw, warp, lane, S,
-                                            p.per_sample_out, local0, count);
+            walk_dispatch<REAL, PER_SAMPLE>(e.L2, PAIRS ? e.records_left : e.records, g0, g1, Tb, row_bytes, spb, coefs_s, red,
+                                            nw, warp, lane, S, p.per_sample_out, local0, count);
         }
         __syncthreads();
         if (trace && threadIdx.x == 0) trace[2] = clock64();
@@ -838,11 +941,11 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) 
 
 // ---- host-callable launchers -----------------------------------------------------------------
 
-template <bool REAL, bool PER_SAMPLE>
+template <bool REAL, bool PER_SAMPLE, bool PAIRS>
 static cudaError_t launch_scalar_t(const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(scalar_step_kernel<REAL, PER_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(scalar_step_kernel<REAL, PER_SAMPLE, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -853,15 +956,17 @@ static cudaError_t launch_scalar_t(const StepParams& p, dim3 grid, int threads, 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = p.allow_overlap ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, scalar_step_kernel<REAL, PER_SAMPLE>, p);
+    return cudaLaunchKernelEx(&cfg, scalar_step_kernel<REAL, PER_SAMPLE, PAIRS>, p);
 }
 
 // `real_mode`: every table and coefficient in use has been verified purely imaginary by the host.
-cudaError_t launch_scalar_step(bool real_mode, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+// `pairs`: some entry of the launch has paired records (then every entry is walked as pairs + leftovers).
+cudaError_t launch_scalar_step(bool real_mode, bool pairs, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
     if (p.per_sample_out) {
-        return real_mode ? launch_scalar_t<true, true>(p, grid, threads, smem, st) : launch_scalar_t<false, true>(p, grid, threads, smem, st);
+        return real_mode ? launch_scalar_t<true, true, false>(p, grid, threads, smem, st) : launch_scalar_t<false, true, false>(p, grid, threads, smem, st);
     }
-    return real_mode ? launch_scalar_t<true, false>(p, grid, threads, smem, st) : launch_scalar_t<false, false>(p, grid, threads, smem, st);
+    if (pairs) return real_mode ? launch_scalar_t<true, false, true>(p, grid, threads, smem, st) : launch_scalar_t<false, false, true>(p, grid, threads, smem, st);
+    return real_mode ? launch_scalar_t<true, false, false>(p, grid, threads, smem, st) : launch_scalar_t<false, false, false>(p, grid, threads, smem, st);
 }
 
 cudaError_t launch_reduce(const DevEntryDyn* dyn, const DevEntry* entries, const double2* partials, int pitch, int S,

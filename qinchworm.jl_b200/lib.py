@@ -62,6 +62,7 @@ _SIGNATURES = {
     "qiw_entry_program": (C.c_int, [C.c_void_p, C.c_int32, i64p, C.POINTER(C.c_uint64), i64p, u32p, i64p, f64p,
                                     i64p, i32p, i32p, i32p]),
     "qiw_entry_records": (C.c_int, [C.c_void_p, C.c_int32, i32p, u32p, C.POINTER(C.c_uint16)]),
+    "qiw_entry_pair_records": (C.c_int, [C.c_void_p, C.c_int32, i32p, u32p, u32p]),
     "qiw_eval": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int32, i32p, u32p, u32p,
                            C.c_uint64, f64p]),
     "qiw_eval_batch": (C.c_int, [C.c_void_p, C.c_int32, f64p, C.c_int32, i32p, u32p, u32p, C.c_uint64, f64p]),
@@ -298,6 +299,16 @@ class Context:
                                           segdef.ctypes.data_as(C.POINTER(C.c_uint16))))
         return dict(K=K, L2=L2, n_leaves=nl, nSeg=nseg, seg_stride=stride, nP=nP, nD=nD, rec2=rec2[:nl],
                     segdef=segdef[:nseg])
+
+    def entry_pair_records(self, entry_id):
+        """Paired configuration records of a compiled entry (qiw_entry_pair_records)."""
+        info = np.zeros(4, dtype=np.int32)
+        self._ck(self.L.qiw_entry_pair_records(self.h, entry_id, _ptr(info, i32p), None, None))
+        npair, lp, nleft, ll = (int(x) for x in info)
+        rp = np.zeros((max(npair, 1), lp), dtype=np.uint32)
+        rl = np.zeros((max(nleft, 1), ll), dtype=np.uint32)
+        self._ck(self.L.qiw_entry_pair_records(self.h, entry_id, _ptr(info, i32p), _ptr(rp, u32p), _ptr(rl, u32p)))
+        return dict(rec_pair=rp[:npair], rec_left=rl[:nleft])
 
     # -- hot path
     def _sobol_args(self, ids, sobol):

@@ -70,6 +70,31 @@ def run_records(rec, prog, expansion, payload, mode, t_i, t_w, t_f, times):
     return out
 
 
+def run_pair_records(pairs, rec, prog, expansion, payload, mode, t_i, t_w, t_f, times):
+    """Replays the paired records (qiw_entry_pair_records) as the summing walk of the CUDA kernel does:
+    prod(Delta) * (coefA * prod(segA) + coefB * prod(segB)) per pair, plus the leftover single records."""
+    T = sample_table(prog, expansion, payload, mode, t_i, t_w, t_f, times)
+    seg = np.ones(rec["nSeg"], dtype=complex)
+    for j in range(rec["nSeg"]):
+        for q in rec["segdef"][j]:
+            if q != 0xFFFF:
+                seg[j] *= T[q]
+    T = np.concatenate([T, seg])
+    K = rec["K"]
+    out = np.zeros(prog["S"], dtype=complex)
+    for r in pairs["rec_pair"]:
+        d = np.prod([T[int(q)] for q in r[2 + 2 * K:]])
+        sa = np.prod([T[int(q)] for q in r[2:2 + K]])
+        sb = np.prod([T[int(q)] for q in r[2 + K:2 + 2 * K]])
+        out[int(r[0]) >> 16] += d * (prog["coefs"][int(r[0]) & 0xFFFF] * sa + prog["coefs"][int(r[1]) & 0xFFFF] * sb)
+    for r in pairs["rec_left"]:
+        v = prog["coefs"][int(r[0]) & 0xFFFF]
+        for q in r[1:]:
+            v = v * T[int(q)]
+        out[int(r[0]) >> 16] += v
+    return out
+
+
 def run_program(prog, expansion, payload, mode, t_i, t_w, t_f, times):
     """Per-sample evaluator value (packed, scalar models): sum over trees of leaf coef * chain."""
     S = prog["S"]

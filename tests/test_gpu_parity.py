@@ -438,3 +438,39 @@ def test_randomised_sequences_in_one_launch(gpu_ctx, qlib, oracle_lib):
     assert relerr(gpu_ctx.eval(0.0, tau[9], tau[10], ids, 2 ** 8), o.eval(0.0, tau[9], tau[10], list(range(len(ids))), 2 ** 8)) < RTOL
     value, contribs, contribs_std = inchworm_step(solver, grid, 0, 9, 10, top_data)
     assert np.isfinite(contribs_std[3]).all() and np.abs(contribs_std[3]).max() > 0 and np.abs(contribs_std[0]).max() == 0
+
+
+@pytest.mark.parametrize("arith", ["real", "complex"])
+def test_paired_records(gpu_ctx, qlib, oracle_lib, monkeypatch, arith):
+    """The paired form of the configuration records (shared pair-interaction operands; default from order 5 on)
+    forced on for every order, in both arithmetic modes, bold + bare + correlator, plus one genuine order-5 entry."""
+    monkeypatch.setenv("QIW_PAIR_MIN_ORDER", "1")
+    if arith == "complex":
+        monkeypatch.setenv("QIW_FORCE_COMPLEX", "1")
+    ex, grid, f = models.anderson(n_tau=30, corr=True)
+    rng = np.random.default_rng(21)
+    ex.P = ex.P * (1.0 + 0.05 * rng.random(ex.P.shape))
+    pl = gpu_ctx.set_expansion(ex)
+    o = oracle_lib.Oracle(pl, ex.P)
+    tau = grid.tau
+    eid = 0
+    for mode, (ki, kw, kf), orders in ((qlib.MODE_BOLD, (0, 14, 15), range(0, 5)), (qlib.MODE_BARE, (0, 0, 1), range(0, 4)),
+                                       (qlib.MODE_CORR, (0, 11, len(tau) - 1), range(0, 4)), (qlib.MODE_BOLD, (0, 20, 21), [5])):
+        ids = []
+        for order in orders:
+            ks = [None] if mode == qlib.MODE_BARE else ([0] if order == 0 else ([3] if order == 5 else range(1, 2 * order)))
+            for k in ks:
+                pr, pa = qlib.topologies(order, None if mode == qlib.MODE_BARE else k, mode == qlib.MODE_CORR)
+                if len(pa) == 0:
+                    continue
+                kk = 2 * order if mode == qlib.MODE_BARE else k
+                gpu_ctx.set_topologies(eid, mode, order, kk, pr, pa)
+                o.set_topologies(eid, mode, order, kk, pr, pa)
+                ids.append(eid)
+                eid += 1
+        N = 2 ** 7 if 5 in orders else 2 ** 9
+        got = gpu_ctx.eval(tau[ki], tau[kw], tau[kf], ids, N)
+        ref = o.eval(tau[ki], tau[kw], tau[kf], ids, N)
+        assert relerr(got, ref) < RTOL, (mode, relerr(got, ref))
+    prs = gpu_ctx.entry_pair_records(ids[-1])
+    assert len(prs["rec_pair"]) > 0

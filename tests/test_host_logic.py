@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import models
-from program_interp import run_program, run_records
+from program_interp import run_pair_records, run_program, run_records
 
 
 def test_library_exports_every_declared_symbol(qlib):
@@ -140,6 +140,10 @@ def test_compiled_programs_replay_to_oracle(qlib, oracle_lib, model):
                     assert rec["n_leaves"] == lv and rec["L2"] == rec["K"] + order
                     got2 = np.array([run_records(rec, prog, ex, pl, mode, t_i, t_w, t_f, times[i]) for i in range(2)])
                     assert np.abs(got2 - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1e-300)
+                    pairs = ctx.entry_pair_records(eid)   # ... and their paired form (shared Delta operands)
+                    assert 2 * len(pairs["rec_pair"]) + len(pairs["rec_left"]) == lv
+                    got3 = np.array([run_pair_records(pairs, rec, prog, ex, pl, mode, t_i, t_w, t_f, times[i]) for i in range(2)])
+                    assert np.abs(got3 - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1e-300)
                     assert st["n_leaves"] == lv and st["flops_per_sample"] == fl and st["n_top"] == len(pa)
                     eid += 1
     assert eid > 10
