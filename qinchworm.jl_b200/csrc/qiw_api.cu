@@ -729,16 +729,18 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
             n_sb = std::max<uint64_t>(n_sb, ((p.order == 0 ? 1 : count) + 31) / 32);
         }
         const int max_sp = max_order + 2;
+        if (max_sp > kWalkMaxSp) return fail(ctx, QIW_ERR_UNSUPPORTED, "expansion order too high for the block walker's branch stack");
+        // shared memory: the per-sample tables of 32 samples + per-warp block sums (the branch-point stack
+        // lives in per-thread local memory), so two CTAs of up to 8 warps share an SM
         auto smem_of = [&](int Wn) {
-            return ((size_t)nI_max * bs * 32 + (size_t)nD_max * 32 + (size_t)Wn * bs + (size_t)Wn * max_sp * 16 * 32 +
-                    (size_t)Wn * max_sp * 32 + (size_t)(kDevMaxNodes + 1) * 32 + (size_t)kDevMaxDim * 32) * sizeof(double) +
-                   (32 + (size_t)Wn * max_sp * 4) * sizeof(int) + 64;
+            return ((size_t)nI_max * bs * 32 + (size_t)nD_max * 32 + (size_t)Wn * bs + (size_t)(kDevMaxNodes + 1) * 32 +
+                    (size_t)kDevMaxDim * 32) * sizeof(double) + 32 * sizeof(int) + 64;
         };
-        int Wn = 4;
-        while (Wn > 1 && smem_of(Wn) > (size_t)226 * 1024) --Wn;
+        int Wn = 8;
+        if (const char* ev = getenv("QIW_WALK_WARPS")) { const int v = atoi(ev); if (v >= 1 && v <= 8) Wn = v; }
         if (smem_of(Wn) > (size_t)226 * 1024) return fail(ctx, QIW_ERR_UNSUPPORTED, "per-sample block tables exceed shared memory");
         // CTA jobs: enough to fill the machine about four times over, proportional to the entries' cost
-        const double want_ctas = 4.0 * ndev_sm;
+        const double want_ctas = 8.0 * ndev_sm;
         std::vector<int> bounds;
         pl->item0.resize(n_entries); pl->n_items.resize(n_entries);
         for (int i = 0; i < n_entries; ++i) {

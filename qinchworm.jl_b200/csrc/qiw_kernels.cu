@@ -1276,7 +1276,12 @@ __device__ __forceinline__ void block_edge_dispatch(int dr, int ds, const double
 template <int D0>
 __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, uint32_t pc, const double* __restrict__ pool_re,
                                                 const double2* __restrict__ coefs, const double* TP, const double* TD,
-                                                int bsize, double* stackV, double* stackD, int* stackI, int lane, double* wacc) {
+                                                int bsize, int lane, double* wacc) {
+    // branch-point stack: per-thread local memory (lane-interleaved by the hardware, L1-resident), so the
+    // CTA's shared memory holds only the per-sample tables and several CTAs fit on an SM
+    double stackV[kWalkMaxSp * 4 * D0];
+    double stackD[kWalkMaxSp];
+    int stackRem[kWalkMaxSp], stackDepth[kWalkMaxSp];
     double acc[4 * D0];
 #pragma unroll
     for (int k = 0; k < 4 * D0; ++k) acc[k] = 0.0;
@@ -1304,11 +1309,10 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
     while (nch > 0) {
         if (nch > 1) {   // branch point: save the running product for the later siblings
 #pragma unroll
-            for (int k = 0; k < 4 * D0; ++k) stackV[((size_t)sp * 16 + k) * 32 + lane] = V[k];
-            stackD[sp * 32 + lane] = dprod;
-            if (lane == 0) { stackI[sp * 2 + 0] = nch - 1; stackI[sp * 2 + 1] = depth; }
+            for (int k = 0; k < 4 * D0; ++k) stackV[sp * 4 * D0 + k] = V[k];
+            stackD[sp] = dprod;
+            stackRem[sp] = nch - 1; stackDepth[sp] = depth;
             ++sp;
-            __syncwarp();
         }
         // one edge: node at position depth + 1, interval depth - 1
         const uint4 cur = w;
@@ -1329,16 +1333,14 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
             if (sp == 0) break;
             // back to the nearest branch point with children left
             --sp;
-            const int rem = stackI[sp * 2 + 0];
-            depth = stackI[sp * 2 + 1];
+            const int rem = stackRem[sp];
+            depth = stackDepth[sp];
 #pragma unroll
-            for (int k = 0; k < 4 * D0; ++k) V[k] = stackV[((size_t)sp * 16 + k) * 32 + lane];
-            dprod = stackD[sp * 32 + lane];
-            __syncwarp();
+            for (int k = 0; k < 4 * D0; ++k) V[k] = stackV[sp * 4 * D0 + k];
+            dprod = stackD[sp];
             if (rem > 1) {   // more siblings after this one: keep the frame
-                if (lane == 0) stackI[sp * 2 + 0] = rem - 1;
+                stackRem[sp] = rem - 1;
                 ++sp;
-                __syncwarp();
             }
             nch = 1;   // continue with exactly one child of the restored node (the frame handles the rest)
         } else {
@@ -1357,7 +1359,7 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
         }
 }
 
-__global__ void __launch_bounds__(128) block_walk_kernel(const StepParams p, const BlockParams bp, const BlockWalkParams wp) {
+__global__ void __launch_bounds__(256, 2) block_walk_kernel(const StepParams p, const BlockParams bp, const BlockWalkParams wp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, nthr = blockDim.x;
     const WorkItem it = p.items[blockIdx.y];
@@ -1369,12 +1371,9 @@ __global__ void __launch_bounds__(128) block_walk_kernel(const StepParams p, con
     double* TP = reinterpret_cast<double*>(smem_raw);                       // [nI_max * bsize][32]
     double* TD = TP + (size_t)wp.nI_max * bsize * 32;                       // [nD_max][32]
     double* accs = TD + (size_t)wp.nD_max * 32;                             // [nw][bsize] per-warp block sums
-    double* stackV = accs + (size_t)nw * bsize;                             // [nw][max_sp][16][32]
-    double* stackD = stackV + (size_t)nw * wp.max_sp * 16 * 32;             // [nw][max_sp][32]
-    double* times = stackD + (size_t)nw * wp.max_sp * 32;                   // [kDevMaxNodes + 1][32]
+    double* times = accs + (size_t)nw * bsize;                              // [kDevMaxNodes + 1][32]
     double* pw = times + (kDevMaxNodes + 1) * 32;                           // [kDevMaxDim][32]
     int* okflag = reinterpret_cast<int*>(pw + kDevMaxDim * 32);             // [32]
-    int* stackI = okflag + 32;                                              // [nw][max_sp][4]
 
     const double t_i = p.t_i, t_w = p.t_w, t_f = p.t_f;
     const double lo_after = (e.mode == 0) ? t_i : t_w, len_after = t_f - lo_after, len_before = t_w - t_i;
@@ -1458,15 +1457,12 @@ __global__ void __launch_bounds__(128) block_walk_kernel(const StepParams p, con
             const uint32_t pc = toff[t];
             const uint4 root = __ldg(xw + pc);
             const int d0 = (int)(root.x & 0xFu);          // root word: ds field = dimension of the initial sector
-            double* sV = stackV + (size_t)warp * wp.max_sp * 16 * 32;
-            double* sD = stackD + (size_t)warp * wp.max_sp * 32;
-            int* sI = stackI + warp * wp.max_sp * 4;
             double* a = my_acc + root.w;
             switch (d0) {
-                case 1: block_walk_tree<1>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, sV, sD, sI, lane, a); break;
-                case 2: block_walk_tree<2>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, sV, sD, sI, lane, a); break;
-                case 3: block_walk_tree<3>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, sV, sD, sI, lane, a); break;
-                default: block_walk_tree<4>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, sV, sD, sI, lane, a); break;
+                case 1: block_walk_tree<1>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, lane, a); break;
+                case 2: block_walk_tree<2>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, lane, a); break;
+                case 3: block_walk_tree<3>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, lane, a); break;
+                default: block_walk_tree<4>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, lane, a); break;
             }
             __syncwarp();
         }
