@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -96,6 +97,8 @@ struct EntryDev {
     DevBuf<uint4> xwords;        // block models: expanded words of the real-arithmetic walker
     std::vector<double> walk_cost;   // block models: estimated cost of every tree for the walker (load balancing)
     DevBuf<uint32_t> tree_off;
+    DevBuf<uint32_t> xtree_off;              // block models: [n_units + 1] word offsets of the walker's units in xwords
+    std::vector<uint32_t> xtree_off_h;
     DevBuf<double2> coefs;
     DevBuf<int4> dslots;
     DevBuf<uint32_t> sobol;   // m[D][32] + x0[D] of the current call
@@ -172,6 +175,7 @@ struct qiw_context {
     DevBuf<const uint64_t*> dWordsPtr;
     DevBuf<const uint32_t*> dTreeOffPtr;
     DevBuf<const uint4*> dXWordsPtr;
+    DevBuf<const uint32_t*> dXTreeOffPtr;
     DevBuf<int> dNTrees;
     DevBuf<unsigned long long> dTrace;
     DevBuf<unsigned int> dCounter;   // arrival counters of the step kernel's fused tail (self-resetting), one per time triple
@@ -286,10 +290,10 @@ int qiw_destroy(qiw_context* ctx) {
     ctx->dPerSample.release(); ctx->dTimes.release(); ctx->dHist.release(); ctx->dDiag.release(); ctx->dTrace.release(); ctx->dCounter.release();
     ctx->dTimes3.release(); ctx->dBatchPartials.release(); ctx->dBatchOut.release(); ctx->dSeqSobol.release(); ctx->dSeqDyn.release();
     ctx->dDim.release(); ctx->dBoff.release(); ctx->dEoff.release(); ctx->dOpTarget.release(); ctx->dOpOff.release();
-    ctx->dPool.release(); ctx->dPoolRe.release(); ctx->dScratch.release(); ctx->dWordsPtr.release(); ctx->dTreeOffPtr.release(); ctx->dXWordsPtr.release(); ctx->dNTrees.release();
+    ctx->dPool.release(); ctx->dPoolRe.release(); ctx->dScratch.release(); ctx->dWordsPtr.release(); ctx->dTreeOffPtr.release(); ctx->dXWordsPtr.release(); ctx->dXTreeOffPtr.release(); ctx->dNTrees.release();
     for (auto& t : ctx->tables) { t.y.release(); t.M.release(); }
     for (auto& e : ctx->entries)
-        if (e) { e->records.release(); e->records_pair.release(); e->records_left.release(); e->segdef.release(); e->words.release(); e->xwords.release(); e->tree_off.release(); e->coefs.release(); e->dslots.release(); e->sobol.release(); }
+        if (e) { e->records.release(); e->records_pair.release(); e->records_left.release(); e->segdef.release(); e->words.release(); e->xwords.release(); e->xtree_off.release(); e->tree_off.release(); e->coefs.release(); e->dslots.release(); e->sobol.release(); }
     for (auto& pl : ctx->plans) release_plan(*pl);
     ctx->plans.clear();
     if (ctx->hOut) cudaFreeHost(ctx->hOut);
@@ -526,18 +530,79 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
                 }
                 xw[k] = x;
             }
-            CK(ed.xwords.upload(xw.data(), xw.size(), ctx->stream));
-            // cost of a tree for the walker: multiply-adds of every edge plus a fixed per-edge overhead
-            ed.walk_cost.assign(pr.tree_off.empty() ? 0 : pr.tree_off.size() - 1, 0.0);
+            // Walk units.  A tree (one topology, one initial sector) is too coarse a unit of work for a warp
+            // — an entry has a few dozen trees of very different cost — so trees are cut into sub-trees of
+            // bounded cost: a unit = root word, the path from the root down to the sub-tree's root (words
+            // copied with one child each, replayed per unit), the sub-tree's pre-order words verbatim.
+            // The table offset of an edge's interval is folded into the word here (y, low 16 bits), so the
+            // device loop does not track the depth.
+            auto edge_cost = [&](const uint4& x, uint32_t d0) {
+                const uint32_t ds = x.x & 0xFu, dr = (x.x >> 4) & 0xFu;
+                return (double)(ds * ds + ((x.x >> 8) & 1u) * dr * ds) * d0 + 40.0;
+            };
+            std::vector<size_t> sub_end(xw.size(), 0);
+            std::vector<double> sub_cost(xw.size(), 0.0);
+            bool fits = true;
+            double entry_cost = 0;
             for (size_t t = 0; t + 1 < pr.tree_off.size(); ++t) {
-                const uint32_t d0 = xw[pr.tree_off[t]].x & 0xFu;
-                double c = 0;
-                for (size_t k = pr.tree_off[t] + 1; k < pr.tree_off[t + 1]; ++k) {
-                    const uint32_t ds = xw[k].x & 0xFu, dr = (xw[k].x >> 4) & 0xFu;
-                    c += (double)(ds * ds + dr * ds) * d0 + 50.0;
+                const size_t r = pr.tree_off[t];
+                const uint32_t d0 = xw[r].x & 0xFu;
+                struct Frame { size_t k; uint32_t left; };
+                std::vector<Frame> st;
+                st.push_back({r, xw[r].x >> 16});
+                size_t k = r + 1;
+                // iterative pre-order scan: depth of an edge = stack size when it is read
+                while (!st.empty()) {
+                    if (st.back().left == 0) {
+                        const Frame f = st.back(); st.pop_back();
+                        sub_end[f.k] = k;
+                        if (!st.empty()) sub_cost[st.back().k] += sub_cost[f.k];
+                        continue;
+                    }
+                    --st.back().left;
+                    const size_t interval = st.size() - 1;
+                    const uint32_t off = (uint32_t)(interval * (size_t)hm.bsize) + (xw[k].y & 0xFFFFu);
+                    if (off > 0xFFFFu) fits = false;
+                    xw[k].y = (xw[k].y & 0xFFFF0000u) | (off & 0xFFFFu);
+                    sub_cost[k] = edge_cost(xw[k], d0);
+                    st.push_back({k, xw[k].x >> 16});
+                    ++k;
                 }
-                ed.walk_cost[t] = c;
+                entry_cost += sub_cost[r];
             }
+            if (!fits) return fail(ctx, QIW_ERR_UNSUPPORTED, "block tables too large for the walker's word format");
+            const double target = std::max(4000.0, entry_cost / 1024.0);
+            std::vector<uint4> units;
+            ed.xtree_off_h.clear(); ed.walk_cost.clear();
+            for (size_t t = 0; t + 1 < pr.tree_off.size(); ++t) {
+                const size_t r = pr.tree_off[t];
+                const uint32_t d0 = xw[r].x & 0xFu;
+                std::vector<size_t> path;
+                auto emit = [&](size_t k) {
+                    ed.xtree_off_h.push_back((uint32_t)units.size());
+                    double c = sub_cost[k];
+                    if (k == r) { units.insert(units.end(), xw.begin() + r, xw.begin() + sub_end[r]); }
+                    else {
+                        uint4 rw = xw[r]; rw.x = (rw.x & 0xFFFFu) | (1u << 16); units.push_back(rw);
+                        for (size_t q : path) { uint4 w = xw[q]; w.x = (w.x & 0xFFFFu) | (1u << 16); units.push_back(w); c += edge_cost(w, d0); }
+                        units.insert(units.end(), xw.begin() + k, xw.begin() + sub_end[k]);
+                    }
+                    ed.walk_cost.push_back(c);
+                };
+                std::function<void(size_t)> split = [&](size_t k) {
+                    const uint32_t nc = xw[k].x >> 16;
+                    if (sub_cost[k] <= target || nc == 0) { emit(k); return; }
+                    if (k != r) path.push_back(k);
+                    size_t c = k + 1;
+                    for (uint32_t i = 0; i < nc; ++i) { split(c); c = sub_end[c]; }
+                    if (k != r) path.pop_back();
+                };
+                if (sub_end[r] > r) split(r);
+            }
+            ed.xtree_off_h.push_back((uint32_t)units.size());
+            units.push_back(make_uint4(0, 0, 0, 0));   // the walker prefetches one word ahead
+            CK(ed.xwords.upload(units.data(), units.size(), ctx->stream));
+            CK(ed.xtree_off.upload(ed.xtree_off_h.data(), ed.xtree_off_h.size(), ctx->stream));
         }
         CK(ed.tree_off.upload(pr.tree_off.data(), pr.tree_off.size(), ctx->stream));
     }
@@ -660,15 +725,18 @@ static int sync_static_tables(qiw_context* ctx) {
             std::vector<const uint64_t*> wp(de.size(), nullptr);
             std::vector<const uint32_t*> tp(de.size(), nullptr);
             std::vector<const uint4*> xp(de.size(), nullptr);
+            std::vector<const uint32_t*> xtp(de.size(), nullptr);
             std::vector<int> nt(de.size(), 0);
             for (size_t i = 0; i < ctx->entries.size(); ++i) {
                 if (!ctx->entries[i] || !ctx->entries[i]->valid) continue;
                 wp[i] = ctx->entries[i]->words.p; tp[i] = ctx->entries[i]->tree_off.p; xp[i] = ctx->entries[i]->xwords.p;
+                xtp[i] = ctx->entries[i]->xtree_off.p;
                 nt[i] = (int)ctx->entries[i]->prog.tree_off.size() - 1;
             }
             CK(ctx->dWordsPtr.upload(wp.data(), wp.size(), ctx->stream));
             CK(ctx->dTreeOffPtr.upload(tp.data(), tp.size(), ctx->stream));
             CK(ctx->dXWordsPtr.upload(xp.data(), xp.size(), ctx->stream));
+            CK(ctx->dXTreeOffPtr.upload(xtp.data(), xtp.size(), ctx->stream));
             CK(ctx->dNTrees.upload(nt.data(), nt.size(), ctx->stream));
         }
         CK(cudaStreamSynchronize(ctx->stream));
@@ -745,14 +813,14 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         pl->item0.resize(n_entries); pl->n_items.resize(n_entries);
         for (int i = 0; i < n_entries; ++i) {
             const EntryProgram& p = ctx->entries[ids[i]]->prog;
-            const int n_trees = (int)p.tree_off.size() - 1;
+            const int n_trees = (int)ctx->entries[ids[i]]->xtree_off_h.size() - 1;   // walk units
             int jobs = (int)std::ceil(want_ctas * entry_cost[i] / std::max(total_cost, 1.0) / (double)n_sb);
             jobs = std::max(1, std::min(jobs, (n_trees + Wn - 1) / Wn));
             const int n_chunks = jobs * Wn;
             // chunk boundaries at equal cumulative cost
             std::vector<double> cum(n_trees + 1, 0.0);
             const std::vector<double>& wc = ctx->entries[ids[i]]->walk_cost;
-            for (int t = 0; t < n_trees; ++t) cum[t + 1] = cum[t] + (t < (int)wc.size() ? wc[t] : (double)p.tree_cost[t]) + 4.0;
+            for (int t = 0; t < n_trees; ++t) cum[t + 1] = cum[t] + wc[t] + 60.0;
             pl->item0[i] = (int)pl->items.size();
             int t_prev = 0;
             for (int j = 0; j < jobs; ++j) {
@@ -1063,7 +1131,7 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         dim3 grid((unsigned)pl.pitch, (unsigned)pl.items.size());
         if (pl.block_real) {
             BlockWalkParams wp;
-            wp.pool_re = ctx->dPoolRe.p; wp.xwords = ctx->dXWordsPtr.p; wp.chunk_bounds = pl.d_bounds.p; wp.warps = pl.bw_warps; wp.max_sp = pl.bw_max_sp;
+            wp.pool_re = ctx->dPoolRe.p; wp.xwords = ctx->dXWordsPtr.p; wp.unit_off = ctx->dXTreeOffPtr.p; wp.chunk_bounds = pl.d_bounds.p; wp.warps = pl.bw_warps; wp.max_sp = pl.bw_max_sp;
             wp.nI_max = pl.bw_nI; wp.nD_max = pl.bw_nD;
             ctx->last_real_mode = 1;
             ProfScope ps(ctx, 7);

@@ -139,7 +139,8 @@ struct DevModel {
 struct BlockWalkParams {
     const double* pool_re;        // operator blocks, real parts, same offsets as DevModel::pool
     const uint4* const* xwords;   // per compiled entry id: expanded program words (layout: qiw_kernels.cu)
-    const int* chunk_bounds;      // [n_items][warps + 1] tree ranges of every warp of every CTA job
+    const uint32_t* const* unit_off;   // per compiled entry id: [n_units + 1] word offsets of the walk units
+    const int* chunk_bounds;      // [n_items][warps + 1] unit ranges of every warp of every CTA job
     int warps, max_sp;            // warps per CTA; stack frames reserved per warp
     int nI_max, nD_max;           // table sizes reserved in shared memory
 };

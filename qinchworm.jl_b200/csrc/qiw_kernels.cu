@@ -1207,56 +1207,59 @@ namespace qiw {
 //   applied at the leaf together with the coefficient (topology sign, :431).
 // Preconditions checked by the host: operator blocks real, P and Delta purely imaginary, coefficients
 // purely imaginary (then every product is real, exactly).  Otherwise block_step_kernel (complex) runs.
-template <int DR, int DS, int D0>
-__device__ __forceinline__ void block_edge(const double* __restrict__ Pm, int lane_stride, const double* __restrict__ O,
-                                           bool has_op, double (&V)[16]) {
-    // V <- O * (iP_s * V), column by column and in place (columns are independent): DS x D0 -> DR x D0
+// One edge = two stages, each dispatched on its own block shape so that the code the walker touches stays
+// small (the SM's instruction cache holds 32 KB): V <- iP_s * V (DS x DS times DS x D0), then, at nodes
+// with an operator, V <- O * V (DR x DS times DS x D0).  Both run column by column and in place.
+template <int DS, int D0>
+__device__ __forceinline__ void block_mul_P(const double* __restrict__ Pm, double (&V)[16]) {
     double Pv[DS * DS];
 #pragma unroll
-    for (int k = 0; k < DS * DS; ++k) Pv[k] = Pm[(size_t)k * lane_stride];
-    if (has_op) {
-        double Ov[DR * DS];
+    for (int k = 0; k < DS * DS; ++k) Pv[k] = Pm[k * 32];
 #pragma unroll
-        for (int k = 0; k < DR * DS; ++k) Ov[k] = __ldg(O + k);
+    for (int j = 0; j < D0; ++j) {
+        double t[DS];
 #pragma unroll
-        for (int j = 0; j < D0; ++j) {
-            double t[DS];
+        for (int i = 0; i < DS; ++i) {
+            double a = Pv[i] * V[4 * j];
 #pragma unroll
-            for (int i = 0; i < DS; ++i) {
-                double a = Pv[i] * V[4 * j];
-#pragma unroll
-                for (int k = 1; k < DS; ++k) a = fma(Pv[i + DS * k], V[k + 4 * j], a);
-                t[i] = a;
-            }
-#pragma unroll
-            for (int i = 0; i < DR; ++i) {
-                double a = Ov[i] * t[0];
-#pragma unroll
-                for (int k = 1; k < DS; ++k) a = fma(Ov[i + DR * k], t[k], a);
-                V[i + 4 * j] = a;
-            }
+            for (int k = 1; k < DS; ++k) a = fma(Pv[i + DS * k], V[k + 4 * j], a);
+            t[i] = a;
         }
-    } else {
 #pragma unroll
-        for (int j = 0; j < D0; ++j) {
-            double t[DS];
+        for (int i = 0; i < DS; ++i) V[i + 4 * j] = t[i];
+    }
+}
+
+template <int DR, int DS, int D0>
+__device__ __forceinline__ void block_mul_O(const double* __restrict__ O, double (&V)[16]) {
+    double Ov[DR * DS];
 #pragma unroll
-            for (int i = 0; i < DS; ++i) {
-                double a = Pv[i] * V[4 * j];
+    for (int k = 0; k < DR * DS; ++k) Ov[k] = __ldg(O + k);
 #pragma unroll
-                for (int k = 1; k < DS; ++k) a = fma(Pv[i + DS * k], V[k + 4 * j], a);
-                t[i] = a;
-            }
+    for (int j = 0; j < D0; ++j) {
+        double t[DS];
 #pragma unroll
-            for (int i = 0; i < DS; ++i) V[i + 4 * j] = t[i];
+        for (int k = 0; k < DS; ++k) t[k] = V[k + 4 * j];
+#pragma unroll
+        for (int i = 0; i < DR; ++i) {
+            double a = Ov[i] * t[0];
+#pragma unroll
+            for (int k = 1; k < DS; ++k) a = fma(Ov[i + DR * k], t[k], a);
+            V[i + 4 * j] = a;
         }
     }
 }
 
 template <int D0>
-__device__ __forceinline__ void block_edge_dispatch(int dr, int ds, const double* Pm, int lane_stride, const double* O,
-                                                    bool has_op, double (&V)[16]) {
-#define QIW_BE(R_, S_) case (R_ * 8 + S_): block_edge<R_, S_, D0>(Pm, lane_stride, O, has_op, V); break;
+__device__ __forceinline__ void block_edge_dispatch(int dr, int ds, const double* Pm, const double* O, bool has_op, double (&V)[16]) {
+    switch (ds) {
+        case 1: block_mul_P<1, D0>(Pm, V); break;
+        case 2: block_mul_P<2, D0>(Pm, V); break;
+        case 3: block_mul_P<3, D0>(Pm, V); break;
+        default: block_mul_P<4, D0>(Pm, V); break;
+    }
+    if (!has_op) return;
+#define QIW_BE(R_, S_) case (R_ * 8 + S_): block_mul_O<R_, S_, D0>(O, V); break;
     switch (dr * 8 + ds) {
         QIW_BE(1, 1) QIW_BE(1, 2) QIW_BE(1, 3) QIW_BE(1, 4) QIW_BE(2, 1) QIW_BE(2, 2) QIW_BE(2, 3) QIW_BE(2, 4)
         QIW_BE(3, 1) QIW_BE(3, 2) QIW_BE(3, 3) QIW_BE(3, 4) QIW_BE(4, 1) QIW_BE(4, 2) QIW_BE(4, 3) QIW_BE(4, 4)
@@ -1268,7 +1271,8 @@ __device__ __forceinline__ void block_edge_dispatch(int dr, int ds, const double
 // Expanded program word of the block walker (built on the host from the tree words and the model, so the
 // device loop needs no model look-ups and can prefetch one edge ahead):
 //   x = ds | dr << 4 | has_op << 8 | nchild << 16      (source / target block dimension of the edge)
-//   y = element offset of the source sector's block in the packed block vector | (Delta slot + 1) << 16
+//   y = offset of the source sector's block of the edge's interval in the table TP, in elements
+//       (interval * bsize + block offset; folded on the host) | (Delta slot + 1) << 16
 //   z = offset of the operator block in pool_re
 //   w = leaf: coefficient index; root: element offset of the initial sector's block
 // Replays one tree for the warp's 32 samples and adds the sum over the samples of
@@ -1281,7 +1285,7 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
     // CTA's shared memory holds only the per-sample tables and several CTAs fit on an SM
     double stackV[kWalkMaxSp * 4 * D0];
     double stackD[kWalkMaxSp];
-    int stackRem[kWalkMaxSp], stackDepth[kWalkMaxSp];
+    int stackRem[kWalkMaxSp];
     double acc[4 * D0];
 #pragma unroll
     for (int k = 0; k < 4 * D0; ++k) acc[k] = 0.0;
@@ -1303,7 +1307,7 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
         for (int j = 0; j < D0; ++j) V[j + 4 * j] = 1.0;
     }
     double dprod = 1.0;
-    int depth = 1, sp = 0;
+    int sp = 0;
     int nch = (int)(root.x >> 16);
     uint4 w = __ldg(xw + pc);   // the next edge is always the next word of the pre-order stream
     while (nch > 0) {
@@ -1311,17 +1315,17 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
 #pragma unroll
             for (int k = 0; k < 4 * D0; ++k) stackV[sp * 4 * D0 + k] = V[k];
             stackD[sp] = dprod;
-            stackRem[sp] = nch - 1; stackDepth[sp] = depth;
+            stackRem[sp] = nch - 1;
             ++sp;
         }
-        // one edge: node at position depth + 1, interval depth - 1
+        // one edge
         const uint4 cur = w;
         ++pc;
         w = __ldg(xw + pc);     // prefetch (the stream is padded by one word)
         const int ds = (int)(cur.x & 0xFu), dr = (int)((cur.x >> 4) & 0xFu);
         const bool has_op = (cur.x >> 8) & 1u;
-        const double* Pm = TP + ((size_t)(depth - 1) * bsize + (cur.y & 0xFFFFu)) * 32 + lane;
-        block_edge_dispatch<D0>(dr, ds, Pm, 32, pool_re + cur.z, has_op, V);
+        const double* Pm = TP + (cur.y & 0xFFFFu) * 32 + lane;
+        block_edge_dispatch<D0>(dr, ds, Pm, pool_re + cur.z, has_op, V);
         const uint32_t sbq = cur.y >> 16;
         if (sbq) dprod *= TD[(size_t)(sbq - 1) * 32 + lane];   // interaction weight at the arc's tail (:506-507)
         nch = (int)(cur.x >> 16);
@@ -1334,7 +1338,6 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
             // back to the nearest branch point with children left
             --sp;
             const int rem = stackRem[sp];
-            depth = stackDepth[sp];
 #pragma unroll
             for (int k = 0; k < 4 * D0; ++k) V[k] = stackV[sp * 4 * D0 + k];
             dprod = stackD[sp];
@@ -1343,8 +1346,6 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
                 ++sp;
             }
             nch = 1;   // continue with exactly one child of the restored node (the frame handles the rest)
-        } else {
-            ++depth;
         }
     }
     // sum over the warp's samples, then one lane adds to the warp's block sums
@@ -1380,7 +1381,7 @@ __global__ void __launch_bounds__(256, 2) block_walk_kernel(const StepParams p, 
     const unsigned long long count = dy.count;
     const int n_sb = (int)((count + 31ull) >> 5);
     const uint4* __restrict__ xw = wp.xwords[it.entry];
-    const uint32_t* __restrict__ toff = bp.tree_off[it.entry];
+    const uint32_t* __restrict__ toff = wp.unit_off[it.entry];
     const int* bounds = wp.chunk_bounds + (size_t)blockIdx.y * (wp.warps + 1);
     const int tree0 = bounds[warp], tree1 = bounds[warp + 1];   // contiguous range of about equal cost per warp
     double* my_acc = accs + (size_t)warp * bsize;
