@@ -600,7 +600,7 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
                 if (sub_end[r] > r) split(r);
             }
             ed.xtree_off_h.push_back((uint32_t)units.size());
-            units.push_back(make_uint4(0, 0, 0, 0));   // the walker prefetches one word ahead
+            units.insert(units.end(), (size_t)kWalkPrefetch + 1, make_uint4(0, 0, 0, 0));   // the walker reads one word ahead and prefetches kWalkPrefetch ahead
             CK(ed.xwords.upload(units.data(), units.size(), ctx->stream));
             CK(ed.xtree_off.upload(ed.xtree_off_h.data(), ed.xtree_off_h.size(), ctx->stream));
         }

@@ -9,6 +9,7 @@ namespace qiw {
 
 constexpr int kDevMaxNodes = 19;
 constexpr int kWalkMaxSp = 10;     // branch-point stack frames of the block walker (order + 2 <= 10)
+constexpr int kWalkPrefetch = 24;   // words the block walker prefetches ahead of its program counter
 constexpr int kDevMaxDim = 16;      // Sobol dimensions handled per entry (2 * order <= 16)
 constexpr int kMaxTables = 64;
 constexpr int kInlineTables = 8;     // propagator tables described directly in the kernel parameters

@@ -1321,7 +1321,10 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
         // one edge
         const uint4 cur = w;
         ++pc;
-        w = __ldg(xw + pc);     // prefetch (the stream is padded by one word)
+        w = __ldg(xw + pc);     // one word ahead (the stream is padded by one word) ...
+        // ... and its cache line well ahead: the words are read once per block of samples, so every new
+        // 128-byte line (8 words) would otherwise come from L2 with the warp waiting on it
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(xw + pc + kWalkPrefetch));
         const int ds = (int)(cur.x & 0xFu), dr = (int)((cur.x >> 4) & 0xFu);
         const bool has_op = (cur.x >> 8) & 1u;
         const double* Pm = TP + (cur.y & 0xFFFFu) * 32 + lane;
