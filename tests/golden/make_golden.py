@@ -70,7 +70,34 @@ def readme_counts():
     print("readme_counts.json", out)
 
 
+def h5_encodings():
+    """On-disk encodings HDF5.jl / libhdf5 produced for the reference's golden files: the header messages of
+    one complex dataset, one real dataset, the superblock prefix and the root group's structures.  They pin the
+    byte layout the product's HDF5 writer (qinchworm_b200/h5out.py) emits."""
+    import struct
+    out = {}
+    h = H5File(os.path.join(REF, "test", "inchworm.h5"))
+    for key, path in (("complex_dataset", "/inchworm/P/1"),):
+        out[key] = {"shape": list(h.read(path).shape),
+                    "messages": {"%04x" % t: h.b[b:b + n].hex() for t, b, n in h.messages(h.lookup(path))}}
+    h2 = H5File(os.path.join(REF, "test", "topology_eval.h5"))
+    out["real_dataset"] = {"shape": list(h2.read("/x1_list").shape),
+                           "messages": {"%04x" % t: h2.b[b:b + n].hex() for t, b, n in h2.messages(h2.lookup("/x1_list"))}}
+    out["superblock_prefix"] = h.b[:32].hex()          # signature, versions, sizes, K values, flags, base address
+    out["root_header"] = h.b[h.root:h.root + 24].hex()   # v1 object header prefix + symbol-table message header
+    heap = struct.unpack_from("<Q", h.b, h.root + 32)[0]
+    out["heap_header_prefix"] = h.b[heap:heap + 8].hex()
+    btree = struct.unpack_from("<Q", h.b, h.root + 24)[0]
+    out["btree_header"] = h.b[btree:btree + 24].hex()
+    snod = struct.unpack_from("<Q", h.b, btree + 32)[0]
+    out["snod_header_prefix"] = h.b[snod:snod + 6].hex()
+    with open(os.path.join(HERE, "h5_encodings.json"), "w") as f:
+        json.dump(out, f, indent=0)
+    print("h5_encodings.json", list(out))
+
+
 if __name__ == "__main__":
+    h5_encodings()
     dump_h5("inchworm.h5", "inchworm_h5.json")
     dump_h5("topology_eval.h5", "topology_eval_h5.json")
     dump_h5("bethe.h5", "bethe_h5.json")
