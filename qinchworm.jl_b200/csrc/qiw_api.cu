@@ -564,11 +564,11 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
                     const uint32_t off = (uint32_t)(interval * (size_t)hm.bsize) + (xw[k].y & 0xFFFFu);
                     if (off > 0xFFFFu) fits = false;
                     xw[k].y = (xw[k].y & 0xFFFF0000u) | (off & 0xFFFFu);
-                    sub_cost[k] = edge_cost(xw[k], d0);
+                    sub_cost[k] = edge_cost(xw[k], std::min(d0, 2u));   // per column group (at most two columns)
                     st.push_back({k, xw[k].x >> 16});
                     ++k;
                 }
-                entry_cost += sub_cost[r];
+                entry_cost += sub_cost[r] * (double)((d0 + 1) / 2);
             }
             if (!fits) return fail(ctx, QIW_ERR_UNSUPPORTED, "block tables too large for the walker's word format");
             const double target = std::max(4000.0, entry_cost / 1024.0);
@@ -578,16 +578,22 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
                 const size_t r = pr.tree_off[t];
                 const uint32_t d0 = xw[r].x & 0xFu;
                 std::vector<size_t> path;
+                // one unit per group of at most two columns of the running product (kernel: block_walk_tree)
                 auto emit = [&](size_t k) {
-                    ed.xtree_off_h.push_back((uint32_t)units.size());
-                    double c = sub_cost[k];
-                    if (k == r) { units.insert(units.end(), xw.begin() + r, xw.begin() + sub_end[r]); }
-                    else {
-                        uint4 rw = xw[r]; rw.x = (rw.x & 0xFFFFu) | (1u << 16); units.push_back(rw);
-                        for (size_t q : path) { uint4 w = xw[q]; w.x = (w.x & 0xFFFFu) | (1u << 16); units.push_back(w); c += edge_cost(w, d0); }
-                        units.insert(units.end(), xw.begin() + k, xw.begin() + sub_end[k]);
+                    for (uint32_t c0 = 0; c0 < d0; c0 += 2) {
+                        const uint32_t nc = std::min(2u, d0 - c0);
+                        ed.xtree_off_h.push_back((uint32_t)units.size());
+                        uint4 rw = xw[r];
+                        rw.x |= (nc << 9) | (c0 << 11);
+                        double c = sub_cost[k];
+                        if (k == r) { units.push_back(rw); units.insert(units.end(), xw.begin() + r + 1, xw.begin() + sub_end[r]); }
+                        else {
+                            rw.x = (rw.x & 0xFFFFu) | (1u << 16); units.push_back(rw);
+                            for (size_t q : path) { uint4 w = xw[q]; w.x = (w.x & 0xFFFFu) | (1u << 16); units.push_back(w); c += edge_cost(w, nc); }
+                            units.insert(units.end(), xw.begin() + k, xw.begin() + sub_end[k]);
+                        }
+                        ed.walk_cost.push_back(c);
                     }
-                    ed.walk_cost.push_back(c);
                 };
                 std::function<void(size_t)> split = [&](size_t k) {
                     const uint32_t nc = xw[k].x >> 16;
@@ -804,8 +810,8 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
             return ((size_t)nI_max * bs * 32 + (size_t)nD_max * 32 + (size_t)Wn * bs + (size_t)(kDevMaxNodes + 1) * 32 +
                     (size_t)kDevMaxDim * 32) * sizeof(double) + 32 * sizeof(int) + 64;
         };
-        int Wn = 8;
-        if (const char* ev = getenv("QIW_WALK_WARPS")) { const int v = atoi(ev); if (v >= 1 && v <= 8) Wn = v; }
+        int Wn = 12;
+        if (const char* ev = getenv("QIW_WALK_WARPS")) { const int v = atoi(ev); if (v >= 1 && v <= 12) Wn = v; }
         if (smem_of(Wn) > (size_t)226 * 1024) return fail(ctx, QIW_ERR_UNSUPPORTED, "per-sample block tables exceed shared memory");
         // CTA jobs: enough to fill the machine about four times over, proportional to the entries' cost
         const double want_ctas = 8.0 * ndev_sm;

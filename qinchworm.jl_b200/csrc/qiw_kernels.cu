@@ -1211,7 +1211,7 @@ namespace qiw {
 // small (the SM's instruction cache holds 32 KB): V <- iP_s * V (DS x DS times DS x D0), then, at nodes
 // with an operator, V <- O * V (DR x DS times DS x D0).  Both run column by column and in place.
 template <int DS, int D0>
-__device__ __forceinline__ void block_mul_P(const double* __restrict__ Pm, double (&V)[16]) {
+__device__ __forceinline__ void block_mul_P(const double* __restrict__ Pm, double (&V)[4 * D0]) {
     double Pv[DS * DS];
 #pragma unroll
     for (int k = 0; k < DS * DS; ++k) Pv[k] = Pm[k * 32];
@@ -1231,7 +1231,7 @@ __device__ __forceinline__ void block_mul_P(const double* __restrict__ Pm, doubl
 }
 
 template <int DR, int DS, int D0>
-__device__ __forceinline__ void block_mul_O(const double* __restrict__ O, double (&V)[16]) {
+__device__ __forceinline__ void block_mul_O(const double* __restrict__ O, double (&V)[4 * D0]) {
     double Ov[DR * DS];
 #pragma unroll
     for (int k = 0; k < DR * DS; ++k) Ov[k] = __ldg(O + k);
@@ -1251,7 +1251,7 @@ __device__ __forceinline__ void block_mul_O(const double* __restrict__ O, double
 }
 
 template <int D0>
-__device__ __forceinline__ void block_edge_dispatch(int dr, int ds, const double* Pm, const double* O, bool has_op, double (&V)[16]) {
+__device__ __forceinline__ void block_edge_dispatch(int dr, int ds, const double* Pm, const double* O, bool has_op, double (&V)[4 * D0]) {
     switch (ds) {
         case 1: block_mul_P<1, D0>(Pm, V); break;
         case 2: block_mul_P<2, D0>(Pm, V); break;
@@ -1275,8 +1275,14 @@ __device__ __forceinline__ void block_edge_dispatch(int dr, int ds, const double
 //       (interval * bsize + block offset; folded on the host) | (Delta slot + 1) << 16
 //   z = offset of the operator block in pool_re
 //   w = leaf: coefficient index; root: element offset of the initial sector's block
-// Replays one tree for the warp's 32 samples and adds the sum over the samples of
-// Im(coef) * dprod * chain (D0 x D0) to wacc (the warp's block sums of the tree's initial sector).
+//   root only: x also carries the column group of this unit: number of columns << 9 | first column << 11
+// The columns of the running product are independent (V <- A V acts column by column), so a tree whose
+// initial sector has dimension d0 > 2 is replayed once per group of at most two columns: the walker then
+// holds at most 4 x 2 doubles of V per lane whatever the sector sizes (template parameter D0 below = columns
+// of the group), which keeps it at 85 registers, 24 warps per SM, and halves the code it touches.
+// Replays one unit for the warp's 32 samples and adds the sum over the samples of
+// Im(coef) * dprod * chain (columns c0 .. c0 + D0 - 1 of the d0 x d0 result) to wacc (the warp's block sums of
+// the tree's initial sector).
 template <int D0>
 __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, uint32_t pc, const double* __restrict__ pool_re,
                                                 const double2* __restrict__ coefs, const double* TP, const double* TD,
@@ -1291,9 +1297,10 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
     for (int k = 0; k < 4 * D0; ++k) acc[k] = 0.0;
     const uint4 root = __ldg(xw + pc);
     ++pc;
-    double V[16];
+    const int d0 = (int)(root.x & 0xFu), c0 = (int)((root.x >> 11) & 0x3u);
+    double V[4 * D0];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) V[k] = 0.0;
+    for (int k = 0; k < 4 * D0; ++k) V[k] = 0.0;
     if ((root.x >> 8) & 1u) {   // operator node at position 1: bare matrix (:377,540)
         const int dcur = (int)((root.x >> 4) & 0xFu);
         const double* O = pool_re + root.z;
@@ -1301,10 +1308,12 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
         for (int j = 0; j < D0; ++j)
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (i < dcur) V[i + 4 * j] = __ldg(O + i + dcur * j);
+                if (i < dcur) V[i + 4 * j] = __ldg(O + i + dcur * (c0 + j));
     } else {
 #pragma unroll
-        for (int j = 0; j < D0; ++j) V[j + 4 * j] = 1.0;
+        for (int j = 0; j < D0; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) V[i + 4 * j] = (i == c0 + j) ? 1.0 : 0.0;
     }
     double dprod = 1.0;
     int sp = 0;
@@ -1332,11 +1341,10 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
         const uint32_t sbq = cur.y >> 16;
         if (sbq) dprod *= TD[(size_t)(sbq - 1) * 32 + lane];   // interaction weight at the arc's tail (:506-507)
         nch = (int)(cur.x >> 16);
-        if (nch == 0) {   // leaf: top_result[s_init] += weight * product (:465)
+        if (nch == 0) {   // leaf: top_result[s_init] += weight * product (:465); rows >= d0 of V are stale
             const double c = __ldg(&coefs[cur.w].y) * dprod;
 #pragma unroll
-            for (int k = 0; k < 4 * D0; ++k)
-                if ((k & 3) < D0) acc[k] = fma(c, V[k], acc[k]);
+            for (int k = 0; k < 4 * D0; ++k) acc[k] = fma(c, ((k & 3) < d0) ? V[k] : 0.0, acc[k]);
             if (sp == 0) break;
             // back to the nearest branch point with children left
             --sp;
@@ -1355,15 +1363,15 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
 #pragma unroll
     for (int j = 0; j < D0; ++j)
 #pragma unroll
-        for (int i = 0; i < D0; ++i) {
+        for (int i = 0; i < 4; ++i) {
             double v = acc[i + 4 * j];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, off);
-            if (lane == 0) wacc[i + D0 * j] += v;
+            if (lane == 0 && i < d0) wacc[i + d0 * (c0 + j)] += v;
         }
 }
 
-__global__ void __launch_bounds__(256, 2) block_walk_kernel(const StepParams p, const BlockParams bp, const BlockWalkParams wp) {
+__global__ void __launch_bounds__(384, 2) block_walk_kernel(const StepParams p, const BlockParams bp, const BlockWalkParams wp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, nthr = blockDim.x;
     const WorkItem it = p.items[blockIdx.y];
@@ -1460,14 +1468,9 @@ __global__ void __launch_bounds__(256, 2) block_walk_kernel(const StepParams p, 
         for (int t = tree0; t < tree1; ++t) {
             const uint32_t pc = toff[t];
             const uint4 root = __ldg(xw + pc);
-            const int d0 = (int)(root.x & 0xFu);          // root word: ds field = dimension of the initial sector
             double* a = my_acc + root.w;
-            switch (d0) {
-                case 1: block_walk_tree<1>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, lane, a); break;
-                case 2: block_walk_tree<2>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, lane, a); break;
-                case 3: block_walk_tree<3>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, lane, a); break;
-                default: block_walk_tree<4>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, lane, a); break;
-            }
+            if (((root.x >> 9) & 0x3u) == 1u) block_walk_tree<1>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, lane, a);
+            else block_walk_tree<2>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, lane, a);
             __syncwarp();
         }
         __syncthreads();
