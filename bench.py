@@ -320,6 +320,30 @@ def main():
                                 "algorithmic_tflops": fl * n_sat / (m_ * 1e-3) / 1e12,
                                 "frac_of_measured_fp64_peak": fl * n_sat / (m_ * 1e-3) / 1e12 / fp64_peak}
 
+    # ---- sector blocks larger than 1x1: one bold step of the two-band e_g model (C4), block_walk_kernel ----
+    block_model = None
+    if world == 1:
+        ex4, grid4, _ = models.two_band(n_tau=64)
+        ctx4 = lib.Context(device=local)
+        solver4 = Solver(ex4, ctx=ctx4)
+        n4 = 2 ** 12
+        ent = _bold_entries(solver4, range(0, 4), n4, None, None)
+        sids = [t.entry_id for t in ent]
+        sst = [ctx4.entry_stats(i) for i in sids]
+        fl = sum(x["flops_per_sample"] for x in sst)
+        tops = sum(x["n_top"] for x in sst)
+        ms = []
+        for k in range(4):
+            ctx4.eval(0.0, grid4.tau[30], grid4.tau[31], sids, n4)
+            if k:
+                ms.append(ctx4.last_device_ms())
+        m_ = float(np.median(ms))
+        block_model = {"workload": "two-band e_g model (9 sectors, blocks 1/2/4), orders 0:3, one bold step, N = 2^12",
+                       "ms_per_launch": m_, "diagram_evals_per_s": n4 * tops / (m_ * 1e-3),
+                       "algorithmic_tflops": fl * n4 / (m_ * 1e-3) / 1e12,
+                       "frac_of_measured_fp64_peak": fl * n4 / (m_ * 1e-3) / 1e12 / fp64_peak}
+        ctx4.close()
+
     # ---- CPU baseline: oracle port on a bounded sample, rank 0 at N=1 only ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -344,7 +368,7 @@ def main():
                                      "h2d_bytes_per_step": (N_TAU - 1) * N_TAU * bs * 16,
                                      "d2h_bytes_per_step": len(bare_ids) * bs * 16 + (N_TAU - 2) * len(bold_ids) * bs * 16,
                                      "max_rel_diff_vs_device_resident": parity_stepped}},
-            "gpu_launches": int(launches), "collective": comm_kind, "roofline": roofline, "saturated_step_kernel": saturated, "cpu_baseline": cpu, "clocks": sampler.summary()}))
+            "gpu_launches": int(launches), "collective": comm_kind, "roofline": roofline, "saturated_step_kernel": saturated, "block_model_step": block_model, "cpu_baseline": cpu, "clocks": sampler.summary()}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -14,3 +14,11 @@ ncu --set full --clock-control none --import-source on --kernel-name-base demang
     -o gpurun_out/ncu_${TAG}_o4_bigN -f python profiles/throughput.py 4 131072 > gpurun_out/ncu_${TAG}_o4.log 2>&1
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:scalar_step_kernel -s 6 -c 1 \
     -o gpurun_out/ncu_${TAG}_o6 -f python profiles/throughput.py 6 16384 > gpurun_out/ncu_${TAG}_o6.log 2>&1
+# 4. sector-block models: full capture of the block walker (two-band model, orders 0:3, N = 2^12), its throughput
+#    vs N, and the Hubbard-dimer (C3) / two-band (C4) configurations as whole inchworm! runs next to the CPU port
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:block_walk_kernel -s 3 -c 1 \
+    -o gpurun_out/ncu_${TAG}_block_walk -f python profiles/throughput_block.py 3 4096 > gpurun_out/ncu_${TAG}_bw.log 2>&1
+python profiles/throughput_block.py 3 1024 4096 16384 > gpurun_out/${TAG}_throughput_block.log 2>&1
+python profiles/bench_c34.py c3 3 64 32768 8 2>/dev/null | tail -1 > gpurun_out/${TAG}_bench_c3.json
+python profiles/bench_c34.py c4 3 32 1024 2 2>/dev/null | tail -1 > gpurun_out/${TAG}_bench_c4.json
+python profiles/bench_c34.py c4 4 6 256 0 2>/dev/null | tail -1 > gpurun_out/${TAG}_bench_c4_orders04.json
