@@ -115,6 +115,25 @@ def two_level_mixed(n_tau=12, beta=2.0, theta=0.0):
     return ex, grid, f
 
 
+def three_orbital(n_tau=12, beta=2.0):
+    """Three spinless orbitals coupled by hopping: sectors by total particle number with dimensions
+    {1, 3, 3, 1}.  Exercises 3x3 blocks (odd column group of the block walker, 3-dimensional edge shapes)."""
+    lab = ["a", "b", "c"]
+    f = FockSpace([[x] for x in lab])
+    n, c, cd = f.n_op, f.c, f.c_dag
+    H = 0.2 * n("a") + 0.35 * n("b") - 0.1 * n("c") + 0.5 * (n("a") @ n("b") + n("b") @ n("c")) + 0.8 * n("a") @ n("c")
+    H = H + 0.3 * (cd("a") @ c("b") + cd("b") @ c("a")) + 0.45 * (cd("b") @ c("c") + cd("c") @ c("b"))
+    ed = EDCore(f, H)
+    grid = ImaginaryTimeGrid(beta, n_tau)
+    D = delta_dos_gf(grid, [0.4, -0.6], [0.3, 0.2])
+    pairs = []
+    for x, y in (("a", "a"), ("b", "b"), ("c", "c"), ("a", "c"), ("c", "a")):
+        pairs += [InteractionPair(cd(x), c(y), D), InteractionPair(c(y), cd(x), ph_conj(D))]
+    ex = Expansion(ed, grid, pairs)
+    add_corr_operators(ex, (c("b"), cd("b")))
+    return ex, grid, f
+
+
 def two_band(n_tau=16, beta=8.0, U=2.0, J=0.2, e_k=2.3):
     """bench/two_band_eg_model_discrete_bath: two-band e_g model, 16 Fock states, 9 sectors with
     dimensions {1,1,1,1,2,2,2,2,4}, 16 interaction pairs, discrete bath."""

@@ -170,7 +170,7 @@ def test_readme_anderson_run(gpu_ctx, qlib, oracle_lib):
     assert np.abs(rho[0] - rho[3]) < 2e-3
 
 
-@pytest.mark.parametrize("name", ["two_level_mixed", "two_band"])
+@pytest.mark.parametrize("name", ["two_level_mixed", "three_orbital", "two_band"])
 def test_block_models_vs_oracle(gpu_ctx, qlib, oracle_lib, name):
     """Sector blocks larger than 1x1 (unpinned at the reference level; the oracle is
     self-validated by basis-rotation invariance): bold / bare / correlator entries against the oracle,
@@ -178,6 +178,10 @@ def test_block_models_vs_oracle(gpu_ctx, qlib, oracle_lib, name):
     from qinchworm_b200.inchworm import Solver, inchworm
     if name == "two_level_mixed":
         ex, grid, f = models.two_level_mixed(n_tau=12, theta=0.6)
+        orders, N = range(0, 4), 2 ** 7
+    elif name == "three_orbital":
+        ex, grid, f = models.three_orbital(n_tau=12)
+        assert sorted(ex.dims) == [1, 1, 3, 3]
         orders, N = range(0, 4), 2 ** 7
     else:
         ex, grid, f = models.two_band(n_tau=10)
@@ -224,7 +228,8 @@ def test_block_models_vs_oracle(gpu_ctx, qlib, oracle_lib, name):
     st = gpu_ctx.entry_stats(eid)
     assert st["n_leaves"] == lv and st["flops_per_sample"] == fl
     # full run on the device vs the oracle's driver
-    ex2 = models.two_level_mixed(n_tau=12, theta=0.6)[0] if name == "two_level_mixed" else models.two_band(n_tau=10)[0]
+    ex2 = {"two_level_mixed": lambda: models.two_level_mixed(n_tau=12, theta=0.6), "three_orbital": lambda: models.three_orbital(n_tau=12),
+           "two_band": lambda: models.two_band(n_tau=10)}[name]()[0]
     refP = oracle_lib.inchworm(ex2.flatten(), ex2.P, range(0, 3), range(0, 3), 2 ** 5)["P"]
     inchworm(ex2, ex2.grid, range(0, 3), range(0, 3), 2 ** 5, solver=Solver(ex2, ctx=gpu_ctx), device_resident=True)
     assert relerr(ex2.P, refP) < RTOL

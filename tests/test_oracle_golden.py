@@ -174,7 +174,8 @@ def test_block_basis_rotation_invariance(oracle_lib):
     assert np.abs(vals[0] - vals[1]).max() < 1e-12
 
 
-def test_block_brute_force_fock_space(oracle_lib):
+@pytest.mark.parametrize("name", ["two_level_mixed", "three_orbital"])
+def test_block_brute_force_fock_space(oracle_lib, name):
     """d_s > 1 is unpinned at the reference level: check the oracle's sector-block DFS against
     a brute-force evaluation of the naive formula (src/configuration.jl:402-411,492-520) in the FULL Fock
     space — dense matrices, every pair assigned to every arc, no sector bookkeeping, no pruning:
@@ -183,7 +184,12 @@ def test_block_brute_force_fock_space(oracle_lib):
     import itertools
     from program_interp import grid_interp
     from oracle.oracle import topologies
-    ex, grid, f = models.two_level_mixed(n_tau=12, theta=0.6)
+    if name == "two_level_mixed":
+        ex, grid, f = models.two_level_mixed(n_tau=12, theta=0.6)
+        cases = ((1, 1), (2, 1), (2, 3), (3, 2))
+    else:   # 3x3 sector blocks, 10 pairs: orders <= 2 keep the brute force (pairs^order assignments) short
+        ex, grid, f = models.three_orbital(n_tau=12)
+        cases = ((1, 1), (2, 1), (2, 3))
     rng = np.random.default_rng(4)
     ex.P = ex.P * (1.0 + 0.1 * rng.random(ex.P.shape))
     pl = ex.flatten()
@@ -204,7 +210,7 @@ def test_block_brute_force_fock_space(oracle_lib):
         return 1j * grid_interp(np.asarray(ex.pairs[p].propagator.data), h, max(t_f, t_i), t_i)
 
     eid = 0
-    for order, k in ((1, 1), (2, 1), (2, 3), (3, 2)):
+    for order, k in cases:
         pairs, parity = topologies(order, k)
         o.set_topologies(eid, oracle_lib.MODE_BOLD, order, k, pairs, parity)
         t_i, t_w, t_f = 0.0, tau[6], tau[7]
