@@ -156,6 +156,14 @@ int qiw_entry_records(qiw_context* ctx, int32_t entry_id, int32_t* info, uint32_
  * leftover record (L2 + 1).  Call with NULL arrays to get the sizes. */
 int qiw_entry_pair_records(qiw_context* ctx, int32_t entry_id, int32_t* info, uint32_t* rec_pair, uint32_t* rec_left);
 
+/* Walk units of a compiled entry of a sector-block model (blocks larger than 1x1) — what block_walk_kernel
+ * replays: the pruned configuration trees of src/topology_eval.jl:454-556 cut into sub-trees of bounded cost,
+ * each emitted once per group of at most two columns of the running product (word layout: csrc/qiw_kernels.cu,
+ * "Expanded program word").  Call with NULL arrays to get the sizes.
+ *   unit_off[n_units + 1] : first word of every unit;  words[n_words][4] */
+int qiw_entry_walk_units(qiw_context* ctx, int32_t entry_id, int64_t* n_units, int64_t* n_words, uint32_t* unit_off,
+                         uint32_t* words);
+
 /* ---- the hot path ---------------------------------------------------------------------------- */
 
 /* Evaluate `n_entries` entries at the fixed times (t_i, t_w, t_f) with N_total Sobol points each.

@@ -99,6 +99,7 @@ struct EntryDev {
     DevBuf<uint32_t> tree_off;
     DevBuf<uint32_t> xtree_off;              // block models: [n_units + 1] word offsets of the walker's units in xwords
     std::vector<uint32_t> xtree_off_h;
+    std::vector<uint4> xunits_h;             // block models: the walk units' words (host copy)
     DevBuf<double2> coefs;
     DevBuf<int4> dslots;
     DevBuf<uint32_t> sobol;   // m[D][32] + x0[D] of the current call
@@ -435,6 +436,118 @@ int qiw_get_P(qiw_context* ctx, int32_t first, int32_t count, double* rows) {
     return QIW_OK;
 }
 
+// Walk units of a block-model entry (host only; also built by planning-only contexts so that the CPU tests
+// can replay them): expanded words + the cut into sub-trees and column groups described below.
+static int build_walk_units(const HostModel& hm, const EntryProgram& pr, EntryDev& ed, std::string& err) {
+    // expanded words: everything the walker needs about an edge, resolved against the model here
+    std::vector<uint4> xw(pr.words.size(), make_uint4(0, 0, 0, 0));
+    std::vector<char> is_root(pr.words.size(), 0);
+    for (size_t t = 0; t + 1 < pr.tree_off.size(); ++t) is_root[pr.tree_off[t]] = 1;
+    const size_t n_real = pr.tree_off.empty() ? 0 : pr.tree_off.back();
+    for (size_t k = 0; k < n_real; ++k) {
+        const uint64_t w = pr.words[k];
+        const uint32_t sA = (uint32_t)w & 0xFFFu, sB = ((uint32_t)w >> 12) & 0xFFFu, nc = ((uint32_t)w >> 24) & 0xFFu;
+        const uint32_t aux = (uint32_t)(w >> 32) & 0xFFFFu;
+        const int op = (int)((w >> 48) & 0xFFF) - 1;
+        uint4 x;
+        if (is_root[k]) {   // slotA = sector after the node at position 1, aux = initial sector
+            const int s_init = (int)aux, s_next = (int)sA;
+            x.x = (uint32_t)hm.dim[s_init] | ((uint32_t)hm.dim[s_next] << 4) | ((op >= 0 ? 1u : 0u) << 8) | (nc << 16);
+            x.y = 0;
+            x.z = op >= 0 ? (uint32_t)hm.op_off[(size_t)op * hm.S + s_init] : 0u;
+            x.w = (uint32_t)hm.boff[s_init];
+        } else {
+            const int s = (int)sA;
+            const int tgt = op >= 0 ? hm.target(op, s) : s;
+            x.x = (uint32_t)hm.dim[s] | ((uint32_t)hm.dim[tgt] << 4) | ((op >= 0 ? 1u : 0u) << 8) | (nc << 16);
+            x.y = (uint32_t)hm.boff[s] | ((sB ? (sB - (uint32_t)pr.nP + 1u) : 0u) << 16);
+            x.z = op >= 0 ? (uint32_t)hm.op_off[(size_t)op * hm.S + s] : 0u;
+            x.w = aux;
+        }
+        xw[k] = x;
+    }
+    // Walk units.  A tree (one topology, one initial sector) is too coarse a unit of work for a warp
+    // — an entry has a few dozen trees of very different cost — so trees are cut into sub-trees of
+    // bounded cost: a unit = root word, the path from the root down to the sub-tree's root (words
+    // copied with one child each, replayed per unit), the sub-tree's pre-order words verbatim.
+    // The table offset of an edge's interval is folded into the word here (y, low 16 bits), so the
+    // device loop does not track the depth.
+    auto edge_cost = [&](const uint4& x, uint32_t d0) {
+        const uint32_t ds = x.x & 0xFu, dr = (x.x >> 4) & 0xFu;
+        return (double)(ds * ds + ((x.x >> 8) & 1u) * dr * ds) * d0 + 40.0;
+    };
+    std::vector<size_t> sub_end(xw.size(), 0);
+    std::vector<double> sub_cost(xw.size(), 0.0);
+    bool fits = true;
+    double entry_cost = 0;
+    for (size_t t = 0; t + 1 < pr.tree_off.size(); ++t) {
+        const size_t r = pr.tree_off[t];
+        const uint32_t d0 = xw[r].x & 0xFu;
+        struct Frame { size_t k; uint32_t left; };
+        std::vector<Frame> st;
+        st.push_back({r, xw[r].x >> 16});
+        size_t k = r + 1;
+        // iterative pre-order scan: depth of an edge = stack size when it is read
+        while (!st.empty()) {
+            if (st.back().left == 0) {
+                const Frame f = st.back(); st.pop_back();
+                sub_end[f.k] = k;
+                if (!st.empty()) sub_cost[st.back().k] += sub_cost[f.k];
+                continue;
+            }
+            --st.back().left;
+            const size_t interval = st.size() - 1;
+            const uint32_t off = (uint32_t)(interval * (size_t)hm.bsize) + (xw[k].y & 0xFFFFu);
+            if (off > 0xFFFFu) fits = false;
+            xw[k].y = (xw[k].y & 0xFFFF0000u) | (off & 0xFFFFu);
+            sub_cost[k] = edge_cost(xw[k], std::min(d0, 2u));   // per column group (at most two columns)
+            st.push_back({k, xw[k].x >> 16});
+            ++k;
+        }
+        entry_cost += sub_cost[r] * (double)((d0 + 1) / 2);
+    }
+    if (!fits) { err = "block tables too large for the walker's word format"; return QIW_ERR_UNSUPPORTED; }
+    double target = std::max(4000.0, entry_cost / 1024.0);
+    if (const char* ev = getenv("QIW_WALK_UNIT_COST")) target = std::max(1.0, atof(ev));   // tests: force deep cuts
+    std::vector<uint4> units;
+    ed.xtree_off_h.clear(); ed.walk_cost.clear();
+    for (size_t t = 0; t + 1 < pr.tree_off.size(); ++t) {
+        const size_t r = pr.tree_off[t];
+        const uint32_t d0 = xw[r].x & 0xFu;
+        std::vector<size_t> path;
+        // one unit per group of at most two columns of the running product (kernel: block_walk_tree)
+        auto emit = [&](size_t k) {
+            for (uint32_t c0 = 0; c0 < d0; c0 += 2) {
+                const uint32_t nc = std::min(2u, d0 - c0);
+                ed.xtree_off_h.push_back((uint32_t)units.size());
+                uint4 rw = xw[r];
+                rw.x |= (nc << 9) | (c0 << 11);
+                double c = sub_cost[k];
+                if (k == r) { units.push_back(rw); units.insert(units.end(), xw.begin() + r + 1, xw.begin() + sub_end[r]); }
+                else {
+                    rw.x = (rw.x & 0xFFFFu) | (1u << 16); units.push_back(rw);
+                    for (size_t q : path) { uint4 w = xw[q]; w.x = (w.x & 0xFFFFu) | (1u << 16); units.push_back(w); c += edge_cost(w, nc); }
+                    units.insert(units.end(), xw.begin() + k, xw.begin() + sub_end[k]);
+                }
+                ed.walk_cost.push_back(c);
+            }
+        };
+        std::function<void(size_t)> split = [&](size_t k) {
+            const uint32_t nc = xw[k].x >> 16;
+            if (sub_cost[k] <= target || nc == 0) { emit(k); return; }
+            if (k != r) path.push_back(k);
+            size_t c = k + 1;
+            for (uint32_t i = 0; i < nc; ++i) { split(c); c = sub_end[c]; }
+            if (k != r) path.pop_back();
+        };
+        if (sub_end[r] > r) split(r);
+    }
+    ed.xtree_off_h.push_back((uint32_t)units.size());
+    units.insert(units.end(), (size_t)kWalkPrefetch + 1, make_uint4(0, 0, 0, 0));   // the walker reads one word ahead and prefetches kWalkPrefetch ahead
+    ed.xunits_h.swap(units);
+    return QIW_OK;
+}
+
 int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t order, int32_t n_pts_after,
                        int32_t corr_idx, int32_t n_top, const int32_t* pairs, const int32_t* parity) {
     if (!ctx || !ctx->have_model || entry_id < 0 || entry_id > 4095 || n_top < 0 || (n_top > 0 && (!parity || (order > 0 && !pairs))))
@@ -448,6 +561,10 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
     int rc = compile_entry(ctx->model, mode, order, n_pts_after, corr_idx, n_top, pairs, parity, ed.prog, err);
     if (rc) return fail(ctx, rc, "qiw_set_topologies: " + err);
     const EntryProgram& pr = ed.prog;
+    if (!ctx->model.scalar) {
+        rc = build_walk_units(ctx->model, pr, ed, err);
+        if (rc) return fail(ctx, rc, "qiw_set_topologies: " + err);
+    }
     if (ctx->no_device) { ed.valid = true; return QIW_OK; }
     if (ctx->model.scalar) {   // configuration records, transposed into groups of 32 so that lane l of a warp reads record
         // 32 g + l with coalesced loads; the last group is padded with null records (zero coefficient)
@@ -502,114 +619,8 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
     }
     if (!ctx->model.scalar) {
         CK(ed.words.upload(pr.words.data(), pr.words.size(), ctx->stream));
-        {   // expanded words: everything the walker needs about an edge, resolved against the model here
-            const HostModel& hm = ctx->model;
-            std::vector<uint4> xw(pr.words.size(), make_uint4(0, 0, 0, 0));
-            std::vector<char> is_root(pr.words.size(), 0);
-            for (size_t t = 0; t + 1 < pr.tree_off.size(); ++t) is_root[pr.tree_off[t]] = 1;
-            const size_t n_real = pr.tree_off.empty() ? 0 : pr.tree_off.back();
-            for (size_t k = 0; k < n_real; ++k) {
-                const uint64_t w = pr.words[k];
-                const uint32_t sA = (uint32_t)w & 0xFFFu, sB = ((uint32_t)w >> 12) & 0xFFFu, nc = ((uint32_t)w >> 24) & 0xFFu;
-                const uint32_t aux = (uint32_t)(w >> 32) & 0xFFFFu;
-                const int op = (int)((w >> 48) & 0xFFF) - 1;
-                uint4 x;
-                if (is_root[k]) {   // slotA = sector after the node at position 1, aux = initial sector
-                    const int s_init = (int)aux, s_next = (int)sA;
-                    x.x = (uint32_t)hm.dim[s_init] | ((uint32_t)hm.dim[s_next] << 4) | ((op >= 0 ? 1u : 0u) << 8) | (nc << 16);
-                    x.y = 0;
-                    x.z = op >= 0 ? (uint32_t)hm.op_off[(size_t)op * hm.S + s_init] : 0u;
-                    x.w = (uint32_t)hm.boff[s_init];
-                } else {
-                    const int s = (int)sA;
-                    const int tgt = op >= 0 ? hm.target(op, s) : s;
-                    x.x = (uint32_t)hm.dim[s] | ((uint32_t)hm.dim[tgt] << 4) | ((op >= 0 ? 1u : 0u) << 8) | (nc << 16);
-                    x.y = (uint32_t)hm.boff[s] | ((sB ? (sB - (uint32_t)pr.nP + 1u) : 0u) << 16);
-                    x.z = op >= 0 ? (uint32_t)hm.op_off[(size_t)op * hm.S + s] : 0u;
-                    x.w = aux;
-                }
-                xw[k] = x;
-            }
-            // Walk units.  A tree (one topology, one initial sector) is too coarse a unit of work for a warp
-            // — an entry has a few dozen trees of very different cost — so trees are cut into sub-trees of
-            // bounded cost: a unit = root word, the path from the root down to the sub-tree's root (words
-            // copied with one child each, replayed per unit), the sub-tree's pre-order words verbatim.
-            // The table offset of an edge's interval is folded into the word here (y, low 16 bits), so the
-            // device loop does not track the depth.
-            auto edge_cost = [&](const uint4& x, uint32_t d0) {
-                const uint32_t ds = x.x & 0xFu, dr = (x.x >> 4) & 0xFu;
-                return (double)(ds * ds + ((x.x >> 8) & 1u) * dr * ds) * d0 + 40.0;
-            };
-            std::vector<size_t> sub_end(xw.size(), 0);
-            std::vector<double> sub_cost(xw.size(), 0.0);
-            bool fits = true;
-            double entry_cost = 0;
-            for (size_t t = 0; t + 1 < pr.tree_off.size(); ++t) {
-                const size_t r = pr.tree_off[t];
-                const uint32_t d0 = xw[r].x & 0xFu;
-                struct Frame { size_t k; uint32_t left; };
-                std::vector<Frame> st;
-                st.push_back({r, xw[r].x >> 16});
-                size_t k = r + 1;
-                // iterative pre-order scan: depth of an edge = stack size when it is read
-                while (!st.empty()) {
-                    if (st.back().left == 0) {
-                        const Frame f = st.back(); st.pop_back();
-                        sub_end[f.k] = k;
-                        if (!st.empty()) sub_cost[st.back().k] += sub_cost[f.k];
-                        continue;
-                    }
-                    --st.back().left;
-                    const size_t interval = st.size() - 1;
-                    const uint32_t off = (uint32_t)(interval * (size_t)hm.bsize) + (xw[k].y & 0xFFFFu);
-                    if (off > 0xFFFFu) fits = false;
-                    xw[k].y = (xw[k].y & 0xFFFF0000u) | (off & 0xFFFFu);
-                    sub_cost[k] = edge_cost(xw[k], std::min(d0, 2u));   // per column group (at most two columns)
-                    st.push_back({k, xw[k].x >> 16});
-                    ++k;
-                }
-                entry_cost += sub_cost[r] * (double)((d0 + 1) / 2);
-            }
-            if (!fits) return fail(ctx, QIW_ERR_UNSUPPORTED, "block tables too large for the walker's word format");
-            const double target = std::max(4000.0, entry_cost / 1024.0);
-            std::vector<uint4> units;
-            ed.xtree_off_h.clear(); ed.walk_cost.clear();
-            for (size_t t = 0; t + 1 < pr.tree_off.size(); ++t) {
-                const size_t r = pr.tree_off[t];
-                const uint32_t d0 = xw[r].x & 0xFu;
-                std::vector<size_t> path;
-                // one unit per group of at most two columns of the running product (kernel: block_walk_tree)
-                auto emit = [&](size_t k) {
-                    for (uint32_t c0 = 0; c0 < d0; c0 += 2) {
-                        const uint32_t nc = std::min(2u, d0 - c0);
-                        ed.xtree_off_h.push_back((uint32_t)units.size());
-                        uint4 rw = xw[r];
-                        rw.x |= (nc << 9) | (c0 << 11);
-                        double c = sub_cost[k];
-                        if (k == r) { units.push_back(rw); units.insert(units.end(), xw.begin() + r + 1, xw.begin() + sub_end[r]); }
-                        else {
-                            rw.x = (rw.x & 0xFFFFu) | (1u << 16); units.push_back(rw);
-                            for (size_t q : path) { uint4 w = xw[q]; w.x = (w.x & 0xFFFFu) | (1u << 16); units.push_back(w); c += edge_cost(w, nc); }
-                            units.insert(units.end(), xw.begin() + k, xw.begin() + sub_end[k]);
-                        }
-                        ed.walk_cost.push_back(c);
-                    }
-                };
-                std::function<void(size_t)> split = [&](size_t k) {
-                    const uint32_t nc = xw[k].x >> 16;
-                    if (sub_cost[k] <= target || nc == 0) { emit(k); return; }
-                    if (k != r) path.push_back(k);
-                    size_t c = k + 1;
-                    for (uint32_t i = 0; i < nc; ++i) { split(c); c = sub_end[c]; }
-                    if (k != r) path.pop_back();
-                };
-                if (sub_end[r] > r) split(r);
-            }
-            ed.xtree_off_h.push_back((uint32_t)units.size());
-            units.insert(units.end(), (size_t)kWalkPrefetch + 1, make_uint4(0, 0, 0, 0));   // the walker reads one word ahead and prefetches kWalkPrefetch ahead
-            CK(ed.xwords.upload(units.data(), units.size(), ctx->stream));
-            CK(ed.xtree_off.upload(ed.xtree_off_h.data(), ed.xtree_off_h.size(), ctx->stream));
-        }
+        CK(ed.xwords.upload(ed.xunits_h.data(), ed.xunits_h.size(), ctx->stream));
+        CK(ed.xtree_off.upload(ed.xtree_off_h.data(), ed.xtree_off_h.size(), ctx->stream));
         CK(ed.tree_off.upload(pr.tree_off.data(), pr.tree_off.size(), ctx->stream));
     }
     std::vector<double2> cf(std::max<size_t>(pr.coefs.size(), 1));
@@ -673,6 +684,18 @@ int qiw_entry_records(qiw_context* ctx, int32_t id, int32_t* info, uint32_t* rec
     }
     if (rec2) memcpy(rec2, p.rec2.data(), p.rec2.size() * sizeof(uint32_t));
     if (segdef) memcpy(segdef, p.segdef.data(), (size_t)p.nSeg * p.seg_stride * sizeof(uint16_t));
+    return QIW_OK;
+}
+
+int qiw_entry_walk_units(qiw_context* ctx, int32_t id, int64_t* n_units, int64_t* n_words, uint32_t* unit_off, uint32_t* words) {
+    if (!ctx || id < 0 || id >= (int)ctx->entries.size() || !ctx->entries[id] || !ctx->entries[id]->valid)
+        return fail(ctx, QIW_ERR_BAD_ARG, "qiw_entry_walk_units: unknown entry");
+    const EntryDev& ed = *ctx->entries[id];
+    if (ed.prog.scalar) return fail(ctx, QIW_ERR_UNSUPPORTED, "qiw_entry_walk_units: only sector-block models have walk units");
+    if (n_units) *n_units = (int64_t)ed.xtree_off_h.size() - 1;
+    if (n_words) *n_words = ed.xtree_off_h.empty() ? 0 : (int64_t)ed.xtree_off_h.back();
+    if (unit_off) memcpy(unit_off, ed.xtree_off_h.data(), ed.xtree_off_h.size() * sizeof(uint32_t));
+    if (words && !ed.xtree_off_h.empty()) memcpy(words, ed.xunits_h.data(), (size_t)ed.xtree_off_h.back() * sizeof(uint4));
     return QIW_OK;
 }
 

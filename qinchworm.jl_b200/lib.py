@@ -63,6 +63,7 @@ _SIGNATURES = {
                                     i64p, i32p, i32p, i32p]),
     "qiw_entry_records": (C.c_int, [C.c_void_p, C.c_int32, i32p, u32p, C.POINTER(C.c_uint16)]),
     "qiw_entry_pair_records": (C.c_int, [C.c_void_p, C.c_int32, i32p, u32p, u32p]),
+    "qiw_entry_walk_units": (C.c_int, [C.c_void_p, C.c_int32, i64p, i64p, u32p, u32p]),
     "qiw_eval": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int32, i32p, u32p, u32p,
                            C.c_uint64, f64p]),
     "qiw_eval_batch": (C.c_int, [C.c_void_p, C.c_int32, f64p, C.c_int32, i32p, u32p, u32p, C.c_uint64, f64p]),
@@ -309,6 +310,15 @@ class Context:
         rl = np.zeros((max(nleft, 1), ll), dtype=np.uint32)
         self._ck(self.L.qiw_entry_pair_records(self.h, entry_id, _ptr(info, i32p), _ptr(rp, u32p), _ptr(rl, u32p)))
         return dict(rec_pair=rp[:npair], rec_left=rl[:nleft])
+
+    def entry_walk_units(self, entry_id):
+        """Walk units of a compiled entry of a sector-block model (qiw_entry_walk_units)."""
+        nu, nw = C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.qiw_entry_walk_units(self.h, entry_id, C.byref(nu), C.byref(nw), None, None))
+        off = np.zeros(nu.value + 1, dtype=np.uint32)
+        words = np.zeros((max(nw.value, 1), 4), dtype=np.uint32)
+        self._ck(self.L.qiw_entry_walk_units(self.h, entry_id, C.byref(nu), C.byref(nw), _ptr(off, u32p), _ptr(words, u32p)))
+        return dict(unit_off=off, words=words[:nw.value])
 
     # -- hot path
     def _sobol_args(self, ids, sobol):

@@ -122,3 +122,83 @@ def run_program(prog, expansion, payload, mode, t_i, t_w, t_f, times):
             out[s_i] += node(1.0 + 0j)
         assert pc[0] == int(prog["tree_off"][k + 1]) or k == len(prog["tree_off"]) - 2
     return out
+
+
+def run_walk_units(units, prog, expansion, payload, mode, t_i, t_w, t_f, times):
+    """Replays the walk units of a sector-block model (qiw_entry_walk_units) the way block_walk_kernel does —
+    pre-order word stream, running product of at most two columns, branch-point stack — in complex numpy
+    arithmetic.  Returns the packed block vector [sum d^2] of one sample."""
+    dims = [int(d) for d in payload["dims"]]
+    bsize = sum(d * d for d in dims)
+    n_nodes = prog["n_nodes"]
+    beta, n_tau = payload["beta"], payload["n_tau"]
+    h = beta / (n_tau - 1)
+    t = np.zeros(n_nodes + 1)
+    for pos in range(1, n_nodes + 1):
+        src = int(prog["pos_src"][pos])
+        t[pos] = {-1: t_i, -2: t_w, -3: t_f}[src] if src < 0 else times[src]
+    # tables: TP[interval * bsize + element] = i P (column-major blocks), TD[slot] = i Delta
+    nI = n_nodes - 1
+    TP = np.zeros(nI * bsize, dtype=complex)
+    for q in range(nI):
+        ta, tb = t[q + 1], max(t[q + 2], t[q + 1])
+        off = 0
+        for s, d in enumerate(dims):
+            for el in range(d * d):
+                r, c = el % d, el // d
+                if mode == 0:
+                    TP[q * bsize + off + el] = np.exp(-(tb - ta) * payload["energies"][sum(dims[:s]) + r]) if r == c else 0.0
+                else:
+                    TP[q * bsize + off + el] = 1j * grid_interp(expansion.P[:, off + el], h, tb, ta)
+            off += d * d
+    TD = np.zeros(len(prog["dslots"]), dtype=complex)
+    for j, (pt, ph, tab) in enumerate(prog["dslots"]):
+        kind, data = payload["tables"][tab]
+        th, tt = t[ph], max(t[pt], t[ph])
+        TD[j] = (1j * natural_spline(data, beta / (len(data) - 1))(tt - th)) if kind == 1 else \
+            1j * grid_interp(data, beta / (len(data) - 1), tt, th)
+    pool = np.asarray(payload["op_pool"])
+    words, off = units["words"], units["unit_off"]
+    out = np.zeros(bsize, dtype=complex)
+    for u in range(len(off) - 1):
+        pc = int(off[u])
+        x, y, z, w = (int(v) for v in words[pc]); pc += 1
+        d0, dcur, has_op = x & 0xF, (x >> 4) & 0xF, (x >> 8) & 1
+        nc, c0, nch = (x >> 9) & 3, (x >> 11) & 3, x >> 16
+        assert 1 <= nc <= 2 and c0 + nc <= d0
+        if has_op:
+            V = pool[z:z + dcur * d0].reshape(d0, dcur).T[:, c0:c0 + nc].astype(complex)     # column-major dcur x d0
+        else:
+            V = np.eye(d0, dtype=complex)[:, c0:c0 + nc]
+        acc = np.zeros((d0, nc), dtype=complex)
+        dprod = 1.0 + 0j
+        stack = []
+        while nch > 0:
+            if nch > 1:
+                stack.append([V.copy(), dprod, nch - 1])
+            x, y, z, w = (int(v) for v in words[pc]); pc += 1
+            ds, dr, has_op = x & 0xF, (x >> 4) & 0xF, (x >> 8) & 1
+            assert V.shape[0] == ds
+            Pm = TP[(y & 0xFFFF):(y & 0xFFFF) + ds * ds].reshape(ds, ds).T
+            V = Pm @ V
+            if has_op:
+                V = pool[z:z + dr * ds].reshape(ds, dr).T @ V
+            if y >> 16:
+                dprod = dprod * TD[(y >> 16) - 1]
+            nch = x >> 16
+            if nch == 0:
+                acc += prog["coefs"][w] * dprod * V
+                if not stack:
+                    break
+                V, dprod, rem = stack[-1]
+                V = V.copy()
+                if rem > 1:
+                    stack[-1][2] = rem - 1
+                else:
+                    stack.pop()
+                nch = 1
+        assert pc == int(off[u + 1])
+        boff = int(words[int(off[u])][3])
+        for j in range(nc):
+            out[boff + d0 * (c0 + j): boff + d0 * (c0 + j) + d0] += acc[:, j]
+    return out

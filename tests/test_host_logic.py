@@ -149,6 +149,66 @@ def test_compiled_programs_replay_to_oracle(qlib, oracle_lib, model):
     assert eid > 10
 
 
+@pytest.mark.parametrize("unit_cost", [None, "150"])
+@pytest.mark.parametrize("model", ["two_level_mixed", "three_orbital", "two_band"])
+def test_walk_units_replay_to_oracle(qlib, oracle_lib, model, unit_cost, monkeypatch):
+    """Sector blocks larger than 1x1: the walk units block_walk_kernel executes (sub-trees of bounded cost, one
+    unit per group of at most two columns; built on the host by qiw_set_topologies) replayed in numpy equal the
+    oracle's recursive evaluator, all three modes."""
+    from program_interp import run_walk_units
+    if unit_cost:      # cost bound of a unit (default max(4000, entry cost / 1024)): a small one cuts every tree deeply
+        monkeypatch.setenv("QIW_WALK_UNIT_COST", unit_cost)
+    rng = np.random.default_rng(5)
+    if model == "two_level_mixed":
+        ex, grid, f = models.two_level_mixed(n_tau=12, theta=0.6)
+        max_order = 3
+    elif model == "three_orbital":
+        ex, grid, f = models.three_orbital(n_tau=12)
+        max_order = 2
+    else:
+        ex, grid, f = models.two_band(n_tau=10)
+        max_order = 2
+    ex.P = ex.P * (1 + 0.1 * rng.random(ex.P.shape))
+    pl = ex.flatten()
+    ctx = qlib.Context(device=qlib.DEVICE_NONE)
+    ctx.set_expansion(ex)
+    o = oracle_lib.Oracle(pl, ex.P)
+    tau = grid.tau
+    eid, n_units, n_split = 0, 0, 0
+    for mode in (qlib.MODE_BOLD, qlib.MODE_BARE, qlib.MODE_CORR):
+        for order in range(0, max_order + 1):
+            ks = [None] if mode == qlib.MODE_BARE else ([0] if order == 0 else (1, 2 * order - 1))
+            for k in ks:
+                pr, pa = qlib.topologies(order, None if mode == qlib.MODE_BARE else k, mode == qlib.MODE_CORR)
+                if len(pa) == 0:
+                    continue
+                kk = 2 * order if mode == qlib.MODE_BARE else k
+                ctx.set_topologies(eid, mode, order, kk, pr, pa)
+                o.set_topologies(eid, mode, order, kk, pr, pa)
+                prog, units = ctx.entry_program(eid), ctx.entry_walk_units(eid)
+                if mode == qlib.MODE_BARE:
+                    t_i, t_w, t_f = 0.0, tau[0], tau[1]
+                elif mode == qlib.MODE_BOLD:
+                    t_i, t_w, t_f = 0.0, tau[5], tau[6]
+                else:
+                    t_i, t_w, t_f = 0.0, tau[4], tau[-1]
+                times = np.zeros(2 * order)
+                if mode == qlib.MODE_BARE:
+                    times[:] = np.sort(rng.uniform(t_i, t_f, 2 * order))[::-1]
+                else:
+                    times[:kk] = np.sort(rng.uniform(t_w, t_f, kk))[::-1]
+                    times[kk:] = np.sort(rng.uniform(t_i, t_w, 2 * order - kk))[::-1]
+                ref = o.eval_at_times(eid, t_i, t_w, t_f, times[None, :])[0]
+                got = run_walk_units(units, prog, ex, pl, mode, t_i, t_w, t_f, times)
+                assert np.abs(got - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1e-300), (mode, order, k)
+                n_units += len(units["unit_off"]) - 1
+                n_split += (len(units["unit_off"]) - 1) > (len(prog["tree_off"]) - 1)
+                eid += 1
+    assert eid >= 8 and n_split > 0     # some entries were cut into more units than trees
+    if unit_cost:
+        assert n_units > 20 * eid
+
+
 def test_offdiagonal_block_is_an_error(qlib):
     """Under-resolved sectors must be reported like the reference's @assert
     (src/topology_eval.jl:462), at compile time."""
