@@ -22,3 +22,12 @@ python profiles/throughput_block.py 3 1024 4096 16384 > gpurun_out/${TAG}_throug
 python profiles/bench_c34.py c3 3 64 32768 8 2>/dev/null | tail -1 > gpurun_out/${TAG}_bench_c3.json
 python profiles/bench_c34.py c4 3 32 1024 2 2>/dev/null | tail -1 > gpurun_out/${TAG}_bench_c4.json
 python profiles/bench_c34.py c4 4 6 256 0 2>/dev/null | tail -1 > gpurun_out/${TAG}_bench_c4_orders04.json
+# 5. condense the reports here (the .ncu-rep files with imported sources exceed what gpurun copies back)
+LIB=qinchworm.jl_b200/libqinchworm_cuda.so
+for r in c1_step o4_bigN o6; do
+    python profiles/ncu_summary.py gpurun_out/ncu_${TAG}_${r}.ncu-rep > gpurun_out/${TAG}_ncu_${r}_summary.csv
+    python profiles/ncu_lines.py gpurun_out/ncu_${TAG}_${r}.ncu-rep scalar_step_kernel $LIB 30 > gpurun_out/${TAG}_ncu_${r}_lines.txt
+done
+python profiles/ncu_summary.py gpurun_out/ncu_${TAG}_block_walk.ncu-rep > gpurun_out/${TAG}_ncu_block_walk_summary.csv
+python profiles/ncu_lines.py gpurun_out/ncu_${TAG}_block_walk.ncu-rep block_walk $LIB 30 > gpurun_out/${TAG}_ncu_block_walk_lines.txt
+rm -f gpurun_out/ncu_${TAG}_*.ncu-rep
