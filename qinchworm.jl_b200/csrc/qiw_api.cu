@@ -827,17 +827,20 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         }
         const int max_sp = max_order + 2;
         if (max_sp > kWalkMaxSp) return fail(ctx, QIW_ERR_UNSUPPORTED, "expansion order too high for the block walker's branch stack");
-        // shared memory: the per-sample tables of 32 samples + per-warp block sums (the branch-point stack
-        // lives in per-thread local memory), so two CTAs of up to 8 warps share an SM
+        // shared memory: the per-sample tables of 32 samples + per-warp block sums.  The branch-point stack lives in
+        // per-thread local memory, and ONE CTA of 24 warps runs per SM: its 24 warps share one set of tables, which
+        // leaves most of the SM's 256 KB to L1 — where the stack frames and the word streams then stay (measured:
+        // two CTAs of 12 warps with two sets of tables 41.6 ms, one CTA of 24 warps 35.3 ms on the two-band model)
         auto smem_of = [&](int Wn) {
             return ((size_t)nI_max * bs * 32 + (size_t)nD_max * 32 + (size_t)Wn * bs + (size_t)(kDevMaxNodes + 1) * 32 +
                     (size_t)kDevMaxDim * 32) * sizeof(double) + 32 * sizeof(int) + 64;
         };
-        int Wn = 12;
-        if (const char* ev = getenv("QIW_WALK_WARPS")) { const int v = atoi(ev); if (v >= 1 && v <= 12) Wn = v; }
+        int Wn = 24;
+        if (const char* ev = getenv("QIW_WALK_WARPS")) { const int v = atoi(ev); if (v >= 1 && v <= 24) Wn = v; }
         if (smem_of(Wn) > (size_t)226 * 1024) return fail(ctx, QIW_ERR_UNSUPPORTED, "per-sample block tables exceed shared memory");
         // CTA jobs: enough to fill the machine about four times over, proportional to the entries' cost
-        const double want_ctas = 8.0 * ndev_sm;
+        double want_ctas = 4.0 * ndev_sm;   // one 24-warp CTA is resident per SM; about four rounds of jobs
+        if (const char* ev = getenv("QIW_WALK_CTAS_PER_SM")) want_ctas = std::max(1.0, atof(ev)) * ndev_sm;
         std::vector<int> bounds;
         pl->item0.resize(n_entries); pl->n_items.resize(n_entries);
         for (int i = 0; i < n_entries; ++i) {

@@ -1371,7 +1371,7 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
         }
 }
 
-__global__ void __launch_bounds__(384, 2) block_walk_kernel(const StepParams p, const BlockParams bp, const BlockWalkParams wp) {
+__global__ void __launch_bounds__(768, 1) block_walk_kernel(const StepParams p, const BlockParams bp, const BlockWalkParams wp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, nthr = blockDim.x;
     const WorkItem it = p.items[blockIdx.y];
