@@ -111,7 +111,7 @@ struct Plan {   // launch plan of one qiw_eval call shape, cached
     uint64_t count = 0;
     bool explicit_mode = false;
     struct Group {
-        int maxl; int item0, n_items; int max_slots; int max_dslots; int max_coefs; int max_segdef;
+        int maxl; int item0, n_items; int max_slots; int max_dslots; int max_coefs; int max_segdef; int max_nodes1 = 2;
         size_t smem[2]; int spb[2];   // [0] complex arithmetic, [1] real arithmetic
     };
     std::vector<Group> groups;
@@ -936,6 +936,7 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         g.max_slots = std::max(g.max_slots, (p.nP + (int)p.dslots.size() + p.nSeg + 1) | 1);
         g.max_dslots = std::max(g.max_dslots, (int)p.dslots.size());
         g.max_segdef = std::max(g.max_segdef, p.nSeg * p.seg_stride);
+        g.max_nodes1 = std::max(g.max_nodes1, p.n_nodes + 1);
     }
     // samples per CTA pass and shared memory, for complex (16-byte operands) and real (8-byte) arithmetic:
     // the largest power of two <= 32 whose tables leave room for two CTAs per SM, else whatever fits
@@ -944,8 +945,9 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         auto smem_of = [&](int spb) {
             size_t b = (size_t)g.max_slots * spb * opsz;
             b = (b + 15) & ~(size_t)15;
-            return b + (size_t)S * W * sizeof(double2) + (size_t)(kDevMaxNodes + 1) * 32 * sizeof(double) +
-                   (size_t)kDevMaxDim * 32 * sizeof(double) + (size_t)(kDevMaxNodes + 1) * 32 * (sizeof(double) + sizeof(int)) +
+            b = std::max(b, (size_t)kDevMaxDim * 32 * sizeof(double));   // the roots alias the start of the table
+            return b + (size_t)S * W * sizeof(double2) + (size_t)g.max_nodes1 * 32 * sizeof(double) +
+                   (size_t)g.max_nodes1 * 32 * (sizeof(double) + sizeof(int)) +
                    32 * sizeof(int) + (size_t)g.max_dslots * sizeof(int4) +
                    (size_t)(g.max_coefs + 1) * opsz + 16;
         };
@@ -1181,6 +1183,7 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         const int real = real_mode_possible(ctx, (int)pl.ids.size(), pl.ids.data()) ? 1 : 0;
         ctx->last_real_mode = real;
         gp.max_slots = g.max_slots;
+        gp.max_nodes1 = g.max_nodes1;
         gp.max_dslots = g.max_dslots;
         gp.max_coefs = g.max_coefs;
         gp.max_segdef = g.max_segdef;

@@ -84,6 +84,7 @@ struct StepParams {
     double t_i, t_w, t_f;
     const double* times_dev;
     int max_slots;                 // operands per sample row reserved in shared memory
+    int max_nodes1;                // largest number of backbone positions of the launch's entries, plus one
     int max_coefs, max_segdef;     // shared-memory staging sizes (largest entry of the launch)
     int spb, spb_log2;             // samples per CTA pass (power of two <= 32)
     int sobol_z_stride;            // > 0: blockIdx.z selects a Sobol sequence (words between the sequences' parameter blocks)

@@ -618,11 +618,14 @@ __global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p)
     const int row_bytes = (n_slots | 1) * (int)sizeof(T);
     unsigned char* Tb = smem_raw;                                                            // [spb][max_row]
     double2* red = reinterpret_cast<double2*>(smem_raw + (size_t)p.max_slots * spb * sizeof(T));   // [S][nw]
-    double* times = reinterpret_cast<double*>(red + (size_t)S * nw);             // [kDevMaxNodes+1][32]
-    double* pw = times + (kDevMaxNodes + 1) * 32;                                // [kDevMaxDim][32]
-    double* cellw = pw + kDevMaxDim * 32;                                        // [kDevMaxNodes+1][32] fractional cell weight
-    int* cella = reinterpret_cast<int*>(cellw + (kDevMaxNodes + 1) * 32);        // [kDevMaxNodes+1][32] grid cell of each time
-    int* okflag = cella + (kDevMaxNodes + 1) * 32;                               // [32]
+    // The small per-sample arrays are sized for the launch's largest entry (p.max_nodes1 = positions + 1), and the
+    // roots pw[D][32] — dead once the times exist — live at the start of the table T, which is filled afterwards:
+    // 63 instead of 73 KB per CTA for the README model, so three CTAs leave 60 KB of the SM to L1 instead of 28.
+    double* times = reinterpret_cast<double*>(red + (size_t)S * nw);             // [max_nodes1][32]
+    double* pw = reinterpret_cast<double*>(Tb);                                  // [D][32], aliases T (phases 1-2 only)
+    double* cellw = times + p.max_nodes1 * 32;                                   // [max_nodes1][32] fractional cell weight
+    int* cella = reinterpret_cast<int*>(cellw + p.max_nodes1 * 32);              // [max_nodes1][32] grid cell of each time
+    int* okflag = cella + p.max_nodes1 * 32;                                     // [32]
     int4* dslots_s = reinterpret_cast<int4*>(okflag + 32);                       // [max_dslots]
     T* coefs_s = reinterpret_cast<T*>(dslots_s + p.max_dslots);                  // [max_coefs + 1]
     const int seg_stride = e.seg_stride;
