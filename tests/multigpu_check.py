@@ -64,6 +64,35 @@ def main():
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         assert torch.equal(lo, hi), "ranks disagree"
         ctx.close()
+    # sector blocks larger than 1x1 (block_walk_kernel + reduction kernel + NCCL all-reduce): step and whole run
+    ex, grid, f = models.three_orbital(n_tau=10)
+    ctx = lib.Context(device=local)
+    mpi.init_comm(ctx, peer=True)
+    solver = Solver(ex, ctx=ctx)
+    o = orc.Oracle(solver.payload, ex.P)
+    ids = []
+    for order in range(0, 3):
+        for k in ([0] if order == 0 else range(1, 2 * order)):
+            pr, pa = lib.topologies(order, k)
+            ctx.set_topologies(100 + len(ids), lib.MODE_BOLD, order, k, pr, pa)
+            o.set_topologies(len(ids), lib.MODE_BOLD, order, k, pr, pa)
+            ids.append(len(ids))
+    got = ctx.eval(0.0, grid.tau[5], grid.tau[6], [100 + i for i in ids], 2 ** 8)
+    ref = o.eval(0.0, grid.tau[5], grid.tau[6], ids, 2 ** 8)
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    worst = max(worst, err)
+    assert err < 1e-10, ("block step", err)
+    refP = orc.inchworm(ex.flatten(), ex.P, range(0, 3), range(0, 3), 2 ** 7)["P"]
+    inchworm(ex, grid, range(0, 3), range(0, 3), 2 ** 7, solver=solver, device_resident=True)
+    err = np.abs(ex.P - refP).max() / np.abs(refP).max()
+    worst = max(worst, err)
+    assert err < 1e-10, ("block run", err)
+    t = torch.from_numpy(ex.P.view(np.float64).copy()).cuda()
+    lo, hi = t.clone(), t.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi), "ranks disagree (block model)"
+    ctx.close()
     if rank == 0:
         print("multigpu_check OK: world %d, worst rel err %.2e" % (world, worst))
     dist.barrier()
