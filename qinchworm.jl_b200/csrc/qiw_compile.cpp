@@ -8,6 +8,8 @@
 // tree is emitted as a flat pre-order word stream that every sample (= one GPU lane) replays in
 // lock step.  Node order inside a tree is the reference's own DFS order.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <tuple>
@@ -188,6 +190,7 @@ int compile_entry(const HostModel& m, int mode, int order, int n_pts_after, int 
         if (v != 2 * n) { err = "internal: free position count"; return 1; }
     }
 
+    const auto t_start = std::chrono::steady_clock::now();
     Builder b(m, e);
     e.n_top = n_top;
     e.tree_off.clear(); e.tree_cost.clear();
@@ -245,11 +248,17 @@ int compile_entry(const HostModel& m, int mode, int order, int n_pts_after, int 
     e.words.push_back(0);
     e.n_leaves = b.leaves; e.n_edges = b.edges; e.flops_per_sample = b.flops;
     if (e.nP + (int)e.dslots.size() > 4095 || e.coefs.size() > 65535) { err = "program table overflow"; return 5; }
+    const auto t_walk = std::chrono::steady_clock::now();
     if (e.scalar) {
         int K = 0;
         if (const char* env = getenv("QIW_SEGMENTS")) K = atoi(env);
         factorise_records(e, m.S, K);
         if (e.nP + (int)e.dslots.size() + e.nSeg > 65535) { err = "segment table overflow"; return 5; }
+    }
+    if (getenv("QIW_COMPILE_TIMING")) {
+        const std::chrono::duration<double, std::milli> walk = t_walk - t_start, fact = std::chrono::steady_clock::now() - t_walk;
+        fprintf(stderr, "qiw compile: mode %d order %d k %d: %lld configurations, tree walk %.1f ms, factorise %.1f ms\n",
+                mode, order, n_pts_after, (long long)e.n_leaves, walk.count(), fact.count());
     }
     return 0;
 }

@@ -28,7 +28,7 @@ class QiwError(RuntimeError):
 def build(force=False, verbose=False):
     """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     csrc = os.path.join(HERE, "csrc")
-    cmd = ["make", "-C", csrc] + (["-B"] if force else [])
+    cmd = ["make", "-C", csrc, "-j%d" % min(4, os.cpu_count() or 1)] + (["-B"] if force else [])
     out = subprocess.run(cmd, capture_output=True, text=True)
     if out.returncode != 0:
         raise RuntimeError("building libqinchworm_cuda.so failed:\n" + out.stdout + out.stderr)
