@@ -286,7 +286,8 @@ def main():
         traffic, traffic_src = tot, "profiles/r1_ncu_c1_step_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
     except Exception:
         pass
-    roofline = {"bound": "fp64_fma", "kernel": "scalar_step_kernel<%s> (all bold entries, orders 0-4)" % ("real" if dom_name == "step_real" else "complex"), "achieved": achieved,
+    roofline = {"bound": "fp64_fma", "bound_note": "FP64 FMA pipe: the path is neither HBM-bound (tables < 1 MB, dram traffic below) "
+                "nor tensor-core work (blocks <= 4x4, DESIGN.md section 4); BASELINE.json asks for the fraction of FP64 peak", "kernel": "scalar_step_kernel<%s> (all bold entries, orders 0-4)" % ("real" if dom_name == "step_real" else "complex"), "achieved": achieved,
                 "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 "peak_source": "measured in this process by qiw_measure_fp64_peak (DFMA-saturating kernel); "
                                "MEASURED_PEAKS.json has no FP64 entry",
