@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <memory>
+#include <thread>
 #include <tuple>
 
 #include "qiw_host.hpp"
@@ -146,6 +148,54 @@ struct Builder {
         }
         return total;
     }
+
+    // All trees with initial sector s_i, in the reference's topology order.  Returns non-zero on a malformed topology.
+    int walk_sector(int s_i, int n_top, const int32_t* pairs, const int32_t* parity, const int* kind0, const int* vertex_pos,
+                    std::string& err) {
+        Builder& b = *this;
+        const int n = e.order;
+        for (int t = 0; t < n_top; ++t) {
+            for (int pos = 1; pos <= e.n_nodes; ++pos) { b.kind[pos] = kind0[pos]; b.arc_of[pos] = -1; }
+            for (int a = 0; a < n; ++a) {
+                const int va = pairs[((size_t)t * n + a) * 2], vb = pairs[((size_t)t * n + a) * 2 + 1];
+                if (va < 1 || vb < 1 || va > 2 * n || vb > 2 * n || va >= vb) { err = "bad topology pair"; return 1; }
+                const int pos_tail = vertex_pos[va], pos_head = vertex_pos[vb];  // :398-403
+                b.kind[pos_tail] = K_TAIL; b.arc_of[pos_tail] = a;
+                b.kind[pos_head] = K_HEAD; b.arc_of[pos_head] = a;
+                b.head_pos_of_arc[a] = pos_head;
+            }
+            // result += -i * parity * (-1)^order * top_result  (src/topology_eval.jl:431)
+            b.top_sign = cplx(0, -1) * (double)parity[t] * ((n & 1) ? -1.0 : 1.0);
+            b.s_init = s_i;
+            const size_t root = e.words.size();
+            const int64_t edges0 = b.edges;
+            e.words.push_back(0);
+            // position 1 is always a fixed node: identity (no factor) or operator B (bare matrix)
+            cplx coef(1.0, 0.0);
+            int s_next = s_i;
+            uint32_t rootop = 0;
+            bool first = true;
+            if (kind0[1] == K_OPER) {
+                const int op = e.fixed_op[1];
+                s_next = m.target(op, s_i);
+                if (s_next < 0) { e.words.resize(root); continue; }
+                if (e.scalar) coef *= m.block(op, s_i)[0];
+                rootop = (uint32_t)(op + 1);
+                b.edges += 1;  // pushed as the (free) first factor
+                first = false;
+            }
+            uint32_t nchild = 0;
+            const double flops0 = b.flops;
+            b.path.clear();
+            const int64_t below = b.node(2, s_next, coef, first, nchild);
+            if (below == 0) { e.words.resize(root); b.edges = edges0; b.flops = flops0; continue; }
+            e.words[root] = make_word((uint32_t)s_next, 0, nchild, (uint32_t)s_i, rootop);
+            b.leaves += below;
+            e.tree_off.push_back((uint32_t)root);
+            e.tree_cost.push_back((uint32_t)(b.edges - edges0));
+        }
+        return 0;
+    }
 };
 
 }  // namespace
@@ -191,51 +241,80 @@ int compile_entry(const HostModel& m, int mode, int order, int n_pts_after, int 
     }
 
     const auto t_start = std::chrono::steady_clock::now();
-    Builder b(m, e);
     e.n_top = n_top;
     e.tree_off.clear(); e.tree_cost.clear();
     // Trees are grouped by initial sector (outer) so that an executor flushes its accumulator
     // rarely; inside a sector group the reference's topology order is kept.
-    for (int s_i = 0; s_i < m.S; ++s_i) {
-        for (int t = 0; t < n_top; ++t) {
-            for (int pos = 1; pos <= e.n_nodes; ++pos) { b.kind[pos] = kind[pos]; b.arc_of[pos] = -1; }
-            for (int a = 0; a < n; ++a) {
-                const int va = pairs[((size_t)t * n + a) * 2], vb = pairs[((size_t)t * n + a) * 2 + 1];
-                if (va < 1 || vb < 1 || va > 2 * n || vb > 2 * n || va >= vb) { err = "bad topology pair"; return 1; }
-                const int pos_tail = vertex_pos[va], pos_head = vertex_pos[vb];  // :398-403
-                b.kind[pos_tail] = K_TAIL; b.arc_of[pos_tail] = a;
-                b.kind[pos_head] = K_HEAD; b.arc_of[pos_head] = a;
-                b.head_pos_of_arc[a] = pos_head;
+    // The sector groups are independent of each other except for the numbering of the distinct coefficients and
+    // pair-interaction slots (first seen, first numbered).  Big entries are therefore walked one sector group per
+    // host thread into private fragments, which are then appended in sector order with their local numbers mapped to
+    // the global first-seen numbering — the resulting program is identical, bit for bit, to the sequential one
+    // (QIW_COMPILE_THREADS=1 forces the sequential walk; the host-logic tests compare both).
+    int n_threads = (int)std::min<unsigned>((unsigned)m.S, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char* env = getenv("QIW_COMPILE_THREADS")) n_threads = std::max(1, std::min(atoi(env), m.S));
+    {   // small entries: a thread costs more than the walk.  Work estimate: trees x (attachable pairs per sector)^order
+        double attach = 0;
+        for (int s = 0; s < m.S; ++s) attach += (double)m.attachable[s].size();
+        attach = std::max(1.0, attach / std::max(1, m.S));
+        double est = (double)n_top * m.S;
+        for (int a = 0; a < order; ++a) est *= attach;
+        if (est < 2e4) n_threads = 1;
+    }
+    Builder b(m, e);
+    if (n_threads <= 1) {
+        for (int s_i = 0; s_i < m.S; ++s_i)
+            if (b.walk_sector(s_i, n_top, pairs, parity, kind, vertex_pos, err)) return 1;
+    } else {
+        struct Fragment { EntryProgram e; std::unique_ptr<Builder> b; std::string err; int rc = 0; };
+        std::vector<std::unique_ptr<Fragment>> frag(m.S);
+        for (int s_i = 0; s_i < m.S; ++s_i) {
+            frag[s_i].reset(new Fragment());
+            EntryProgram& fe = frag[s_i]->e;
+            fe.mode = e.mode; fe.order = e.order; fe.n_pts_after = e.n_pts_after; fe.corr_idx = e.corr_idx;
+            fe.scalar = e.scalar; fe.D = e.D; fe.n_nodes = e.n_nodes; fe.nP = e.nP; fe.L = e.L; fe.RL = e.RL; fe.n_top = n_top;
+            for (int p = 0; p <= kMaxNodes; ++p) { fe.pos_src[p] = e.pos_src[p]; fe.fixed_op[p] = e.fixed_op[p]; }
+            frag[s_i]->b.reset(new Builder(m, fe));
+        }
+        std::vector<std::thread> pool;
+        for (int w = 0; w < n_threads; ++w)
+            pool.emplace_back([&, w]() {
+                for (int s_i = w; s_i < m.S; s_i += n_threads)
+                    frag[s_i]->rc = frag[s_i]->b->walk_sector(s_i, n_top, pairs, parity, kind, vertex_pos, frag[s_i]->err);
+            });
+        for (auto& t : pool) t.join();
+        for (int s_i = 0; s_i < m.S; ++s_i)
+            if (frag[s_i]->rc) { err = frag[s_i]->err; return 1; }
+        for (int s_i = 0; s_i < m.S; ++s_i) {
+            const EntryProgram& fe = frag[s_i]->e;
+            const Builder& fb = *frag[s_i]->b;
+            if (fe.nP + (int)fe.dslots.size() > 4095 || fe.coefs.size() > 65535) { err = "program table overflow"; return 5; }
+            std::vector<uint32_t> cmap(fe.coefs.size()), dmap(fe.dslots.size());
+            for (size_t i = 0; i < fe.coefs.size(); ++i) cmap[i] = (uint32_t)b.coef_id(fe.coefs[i]);
+            for (size_t i = 0; i < fe.dslots.size(); ++i)
+                dmap[i] = (uint32_t)b.dslot_id(fe.dslots[i].pos_tail, fe.dslots[i].pos_head, fe.dslots[i].table);
+            if (e.nP + (int)e.dslots.size() > 4095 || e.coefs.size() > 65535) { err = "program table overflow"; return 5; }
+            const size_t base = e.words.size();
+            for (uint32_t off : fe.tree_off) e.tree_off.push_back((uint32_t)(base + off));
+            e.tree_cost.insert(e.tree_cost.end(), fe.tree_cost.begin(), fe.tree_cost.end());
+            size_t next_root = 0;   // index into fe.tree_off: root words carry the initial sector in aux and are left alone
+            for (size_t i = 0; i < fe.words.size(); ++i) {
+                uint64_t w = fe.words[i];
+                if (next_root < fe.tree_off.size() && fe.tree_off[next_root] == i) { ++next_root; e.words.push_back(w); continue; }
+                const uint32_t slotB = (uint32_t)(w >> 12) & 0xFFFu, nchild = (uint32_t)(w >> 24) & 0xFFu;
+                if (slotB) w = (w & ~((uint64_t)0xFFF << 12)) | ((uint64_t)((uint32_t)fe.nP + dmap[slotB - (uint32_t)fe.nP]) << 12);
+                if (nchild == 0) w = (w & ~((uint64_t)0xFFFF << 32)) | ((uint64_t)cmap[(uint32_t)(w >> 32) & 0xFFFFu] << 32);
+                e.words.push_back(w);
             }
-            // result += -i * parity * (-1)^order * top_result  (src/topology_eval.jl:431)
-            b.top_sign = cplx(0, -1) * (double)parity[t] * ((n & 1) ? -1.0 : 1.0);
-            b.s_init = s_i;
-            const size_t root = e.words.size();
-            const int64_t edges0 = b.edges;
-            e.words.push_back(0);
-            // position 1 is always a fixed node: identity (no factor) or operator B (bare matrix)
-            cplx coef(1.0, 0.0);
-            int s_next = s_i;
-            uint32_t rootop = 0;
-            bool first = true;
-            if (kind[1] == K_OPER) {
-                const int op = e.fixed_op[1];
-                s_next = m.target(op, s_i);
-                if (s_next < 0) { e.words.resize(root); continue; }
-                if (e.scalar) coef *= m.block(op, s_i)[0];
-                rootop = (uint32_t)(op + 1);
-                b.edges += 1;  // pushed as the (free) first factor
-                first = false;
+            const size_t r0 = e.records.size();
+            e.records.insert(e.records.end(), fe.records.begin(), fe.records.end());
+            for (size_t r = r0; r < e.records.size(); r += (size_t)e.RL) {
+                uint32_t* rec = e.records.data() + r;
+                rec[0] = cmap[rec[0] & 0xFFFFu] | (rec[0] & 0xFFFF0000u);
+                for (int q = 1; q <= e.L; ++q)
+                    if ((int)rec[q] >= e.nP) rec[q] = (uint32_t)e.nP + dmap[rec[q] - (uint32_t)e.nP];
             }
-            uint32_t nchild = 0;
-            const double flops0 = b.flops;
-            b.path.clear();
-            const int64_t below = b.node(2, s_next, coef, first, nchild);
-            if (below == 0) { e.words.resize(root); b.edges = edges0; b.flops = flops0; continue; }
-            e.words[root] = make_word((uint32_t)s_next, 0, nchild, (uint32_t)s_i, rootop);
-            b.leaves += below;
-            e.tree_off.push_back((uint32_t)root);
-            e.tree_cost.push_back((uint32_t)(b.edges - edges0));
+            b.leaves += fb.leaves; b.edges += fb.edges; b.flops += fb.flops;
+            b.offdiag = b.offdiag || fb.offdiag;
         }
     }
     if (b.offdiag) {
@@ -257,8 +336,8 @@ int compile_entry(const HostModel& m, int mode, int order, int n_pts_after, int 
     }
     if (getenv("QIW_COMPILE_TIMING")) {
         const std::chrono::duration<double, std::milli> walk = t_walk - t_start, fact = std::chrono::steady_clock::now() - t_walk;
-        fprintf(stderr, "qiw compile: mode %d order %d k %d: %lld configurations, tree walk %.1f ms, factorise %.1f ms\n",
-                mode, order, n_pts_after, (long long)e.n_leaves, walk.count(), fact.count());
+        fprintf(stderr, "qiw compile: mode %d order %d k %d: %lld configurations, tree walk %.1f ms on %d thread(s), factorise %.1f ms\n",
+                mode, order, n_pts_after, (long long)e.n_leaves, walk.count(), n_threads, fact.count());
     }
     return 0;
 }
@@ -274,22 +353,20 @@ void factorise_records(EntryProgram& e, int S, int K_req) {
     const int64_t nl = e.n_leaves;
     // candidate segmentations: K equal parts; keep the cheapest in shared-memory operand loads
     //   cost(K) = leaves * (K + n)  +  sum over segments (entries * segment length)
-    int bestK = 1;
-    double best_cost = 1e300;
-    std::vector<uint32_t> best_rec;
-    std::vector<uint16_t> best_def;
-    int best_nseg = 0, best_stride = 0;
     const int Kmin = (nI + 8) / 9;   // the kernel handles segments of up to 9 intervals
     const int Kmax = std::max(Kmin, std::min(nI, 4));
     const int K_lo = K_req > 0 ? std::max(Kmin, std::min(K_req, nI)) : Kmin, K_hi = K_req > 0 ? K_lo : Kmax;
-    for (int K = K_lo; K <= K_hi; ++K) {
+    struct Candidate { std::vector<uint32_t> rec; std::vector<uint16_t> def; int nseg = 0, stride = 0; double cost = 1e300; };
+    std::vector<Candidate> cand(K_hi - K_lo + 1);
+    auto build = [&](int K, Candidate& c) {
         std::vector<int> bound(K + 1);
         for (int g = 0; g <= K; ++g) bound[g] = (int)((int64_t)g * nI / K);
         int stride = 0;
         for (int g = 0; g < K; ++g) stride = std::max(stride, bound[g + 1] - bound[g]);
         std::vector<std::map<std::vector<uint16_t>, int>> index(K);
-        std::vector<uint16_t> def;
-        std::vector<uint32_t> rec((size_t)nl * (K + n + 1));
+        std::vector<uint16_t>& def = c.def;
+        std::vector<uint32_t>& rec = c.rec;
+        rec.assign((size_t)nl * (K + n + 1), 0u);
         int nseg = 0;
         double seg_cost = 0;
         for (int64_t l = 0; l < nl; ++l) {
@@ -318,11 +395,25 @@ void factorise_records(EntryProgram& e, int S, int K_req) {
         }
         // slots per sample row bound the CTA's shared memory: penalise tables beyond ~4 KB of doubles
         const double row = nP + nD + nseg;
-        double cost = (double)nl * (K + n) + seg_cost + (row > 512 ? 1e6 * (row - 512) : 0.0);
-        if (cost < best_cost) {
-            best_cost = cost; bestK = K; best_rec.swap(rec); best_def.swap(def); best_nseg = nseg; best_stride = stride;
-        }
+        c.cost = (double)nl * (K + n) + seg_cost + (row > 512 ? 1e6 * (row - 512) : 0.0);
+        c.nseg = nseg; c.stride = stride;
+    };
+    // the candidates are independent: one host thread each when the entry is big enough to pay for it
+    bool threaded = cand.size() > 1 && nl >= 4096 && std::thread::hardware_concurrency() > 1;
+    if (const char* env = getenv("QIW_COMPILE_THREADS")) threaded = threaded && atoi(env) > 1;
+    if (threaded) {
+        std::vector<std::thread> pool;
+        for (int K = K_lo; K <= K_hi; ++K) pool.emplace_back([&, K]() { build(K, cand[K - K_lo]); });
+        for (auto& t : pool) t.join();
+    } else {
+        for (int K = K_lo; K <= K_hi; ++K) build(K, cand[K - K_lo]);
     }
+    int bestK = K_lo;
+    for (int K = K_lo; K <= K_hi; ++K)          // first of the cheapest, as the sequential search picks
+        if (cand[K - K_lo].cost < cand[bestK - K_lo].cost) bestK = K;
+    std::vector<uint32_t>& best_rec = cand[bestK - K_lo].rec;
+    std::vector<uint16_t>& best_def = cand[bestK - K_lo].def;
+    const int best_nseg = cand[bestK - K_lo].nseg, best_stride = cand[bestK - K_lo].stride;
     e.K = bestK; e.L2 = bestK + n; e.nSeg = best_nseg; e.seg_stride = std::max(best_stride, 1);
     e.rec2.swap(best_rec); e.segdef.swap(best_def);
     if (e.segdef.empty()) e.segdef.assign(1, 0xFFFF);

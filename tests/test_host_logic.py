@@ -249,3 +249,53 @@ def test_readme_work_counts(qlib):
     pr, pa = qlib.topologies(4)
     ctx.set_topologies(eid, qlib.MODE_BARE, 4, 8, pr, pa)
     assert ctx.entry_stats(eid)["n_leaves"] == 2656
+
+
+def _digest(obj, h):
+    if isinstance(obj, dict):
+        for k in sorted(obj):
+            h.update(str(k).encode())
+            _digest(obj[k], h)
+    elif isinstance(obj, np.ndarray):
+        h.update(str(obj.shape).encode())
+        h.update(np.ascontiguousarray(obj).tobytes())
+    elif isinstance(obj, (list, tuple)):
+        for x in obj:
+            _digest(x, h)
+    else:
+        h.update(repr(obj).encode())
+
+
+@pytest.mark.parametrize("model", ["anderson", "two_band"])
+def test_threaded_compile_is_bit_identical(qlib, model, monkeypatch):
+    """qiw_set_topologies walks big entries one initial-sector group per host thread and renumbers the fragments'
+    coefficients and pair-interaction slots into the global first-seen order: the program, the factorised / paired
+    records and the walk units must equal the sequential compilation (QIW_COMPILE_THREADS=1) bit for bit."""
+    import hashlib
+    if model == "anderson":
+        ex, grid, f = models.anderson(n_tau=20, corr=True)
+        cases = [(qlib.MODE_BOLD, 5, 1, 0), (qlib.MODE_BOLD, 5, 6, 0), (qlib.MODE_BARE, 5, 10, 0), (qlib.MODE_CORR, 5, 3, 1),
+                 (qlib.MODE_BOLD, 6, 11, 0)]
+    else:
+        ex, grid, f = models.two_band(n_tau=8)
+        cases = [(qlib.MODE_BOLD, 3, 1, 0), (qlib.MODE_BOLD, 3, 4, 0), (qlib.MODE_CORR, 3, 2, 0), (qlib.MODE_BARE, 3, 6, 0)]
+    digests = {}
+    for threads in ("1", "8"):
+        monkeypatch.setenv("QIW_COMPILE_THREADS", threads)
+        ctx = qlib.Context(device=qlib.DEVICE_NONE)
+        ctx.set_expansion(ex)
+        h = hashlib.sha256()
+        for eid, (mode, order, k, corr) in enumerate(cases):
+            pr, pa = qlib.topologies(order, None if mode == qlib.MODE_BARE else k, mode == qlib.MODE_CORR)
+            assert len(pa) > 0
+            ctx.set_topologies(eid, mode, order, k, pr, pa, corr_idx=corr)
+            _digest(ctx.entry_stats(eid), h)
+            _digest(ctx.entry_program(eid), h)
+            if model == "anderson":
+                _digest(ctx.entry_records(eid), h)
+                _digest(ctx.entry_pair_records(eid), h)
+            else:
+                _digest(ctx.entry_walk_units(eid), h)
+        digests[threads] = h.hexdigest()
+        ctx.close()
+    assert digests["1"] == digests["8"]
