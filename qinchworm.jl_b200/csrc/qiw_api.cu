@@ -11,6 +11,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/qinchworm.h"
@@ -478,9 +479,32 @@ static int build_walk_units(const HostModel& hm, const EntryProgram& pr, EntryDe
     };
     std::vector<size_t> sub_end(xw.size(), 0);
     std::vector<double> sub_cost(xw.size(), 0.0);
-    bool fits = true;
-    double entry_cost = 0;
-    for (size_t t = 0; t + 1 < pr.tree_off.size(); ++t) {
+    // Trees are independent: big entries are scanned and cut on several host threads, each over a contiguous range
+    // of trees; sums and the unit stream are put together in tree order, so the result does not depend on the
+    // number of threads (QIW_COMPILE_THREADS=1: sequential; tests compare both bit for bit).
+    const size_t n_trees = pr.tree_off.empty() ? 0 : pr.tree_off.size() - 1;
+    int n_threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    if (n_real < 100000) n_threads = 1;   // small entries: a thread costs more than the work
+    if (const char* ev = getenv("QIW_COMPILE_THREADS")) n_threads = std::max(1, std::min(atoi(ev), 64));   // an explicit request wins
+    n_threads = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(n_trees, 1));
+    auto for_tree_ranges = [&](const std::function<void(int, size_t, size_t)>& fn) {
+        if (n_threads <= 1) { fn(0, 0, n_trees); return; }
+        std::vector<std::thread> pool;
+        for (int w = 0; w < n_threads; ++w)   // ranges of equal word count, not equal tree count
+            pool.emplace_back([&, w]() {
+                auto cut = [&](int i) {
+                    const size_t want = n_real * (size_t)i / (size_t)n_threads;
+                    return (size_t)(std::lower_bound(pr.tree_off.begin(), pr.tree_off.begin() + n_trees, (uint32_t)want) - pr.tree_off.begin());
+                };
+                fn(w, w == 0 ? 0 : cut(w), w == n_threads - 1 ? n_trees : cut(w + 1));
+            });
+        for (auto& t : pool) t.join();
+    };
+    std::vector<char> fits_w(n_threads, 1);
+    std::vector<double> tree_cost_sum(n_trees, 0.0);
+    for_tree_ranges([&](int w_idx, size_t t_begin, size_t t_end) {
+    for (size_t t = t_begin; t < t_end; ++t) {
+        bool fits = true;
         const size_t r = pr.tree_off[t];
         const uint32_t d0 = xw[r].x & 0xFu;
         struct Frame { size_t k; uint32_t left; };
@@ -504,14 +528,25 @@ static int build_walk_units(const HostModel& hm, const EntryProgram& pr, EntryDe
             st.push_back({k, xw[k].x >> 16});
             ++k;
         }
-        entry_cost += sub_cost[r] * (double)((d0 + 1) / 2);
+        tree_cost_sum[t] = sub_cost[r] * (double)((d0 + 1) / 2);
+        if (!fits) fits_w[w_idx] = 0;
     }
+    });
+    bool fits = true;
+    double entry_cost = 0;
+    for (int w = 0; w < n_threads; ++w) fits = fits && fits_w[w];
+    for (size_t t = 0; t < n_trees; ++t) entry_cost += tree_cost_sum[t];
     if (!fits) { err = "block tables too large for the walker's word format"; return QIW_ERR_UNSUPPORTED; }
     double target = std::max(4000.0, entry_cost / 1024.0);
     if (const char* ev = getenv("QIW_WALK_UNIT_COST")) target = std::max(1.0, atof(ev));   // tests: force deep cuts
-    std::vector<uint4> units;
+    struct Part { std::vector<uint4> units; std::vector<uint32_t> off; std::vector<double> cost; };
+    std::vector<Part> parts(n_threads);
     ed.xtree_off_h.clear(); ed.walk_cost.clear();
-    for (size_t t = 0; t + 1 < pr.tree_off.size(); ++t) {
+    for_tree_ranges([&](int w_idx, size_t t_begin, size_t t_end) {
+    std::vector<uint4>& units = parts[w_idx].units;
+    std::vector<uint32_t>& xtree_off_part = parts[w_idx].off;
+    std::vector<double>& walk_cost_part = parts[w_idx].cost;
+    for (size_t t = t_begin; t < t_end; ++t) {
         const size_t r = pr.tree_off[t];
         const uint32_t d0 = xw[r].x & 0xFu;
         std::vector<size_t> path;
@@ -519,7 +554,7 @@ static int build_walk_units(const HostModel& hm, const EntryProgram& pr, EntryDe
         auto emit = [&](size_t k) {
             for (uint32_t c0 = 0; c0 < d0; c0 += 2) {
                 const uint32_t nc = std::min(2u, d0 - c0);
-                ed.xtree_off_h.push_back((uint32_t)units.size());
+                xtree_off_part.push_back((uint32_t)units.size());
                 uint4 rw = xw[r];
                 rw.x |= (nc << 9) | (c0 << 11);
                 double c = sub_cost[k];
@@ -529,7 +564,7 @@ static int build_walk_units(const HostModel& hm, const EntryProgram& pr, EntryDe
                     for (size_t q : path) { uint4 w = xw[q]; w.x = (w.x & 0xFFFFu) | (1u << 16); units.push_back(w); c += edge_cost(w, nc); }
                     units.insert(units.end(), xw.begin() + k, xw.begin() + sub_end[k]);
                 }
-                ed.walk_cost.push_back(c);
+                walk_cost_part.push_back(c);
             }
         };
         std::function<void(size_t)> split = [&](size_t k) {
@@ -541,6 +576,20 @@ static int build_walk_units(const HostModel& hm, const EntryProgram& pr, EntryDe
             if (k != r) path.pop_back();
         };
         if (sub_end[r] > r) split(r);
+    }
+    });
+    std::vector<uint4> units;
+    {
+        size_t total = 0;
+        for (const Part& pt : parts) total += pt.units.size();
+        units.reserve(total + (size_t)kWalkPrefetch + 1);
+        for (Part& pt : parts) {
+            const uint32_t base = (uint32_t)units.size();
+            for (uint32_t o : pt.off) ed.xtree_off_h.push_back(base + o);
+            ed.walk_cost.insert(ed.walk_cost.end(), pt.cost.begin(), pt.cost.end());
+            units.insert(units.end(), pt.units.begin(), pt.units.end());
+            std::vector<uint4>().swap(pt.units);
+        }
     }
     ed.xtree_off_h.push_back((uint32_t)units.size());
     units.insert(units.end(), (size_t)kWalkPrefetch + 1, make_uint4(0, 0, 0, 0));   // the walker reads one word ahead and prefetches kWalkPrefetch ahead

@@ -251,7 +251,6 @@ int compile_entry(const HostModel& m, int mode, int order, int n_pts_after, int 
     // the global first-seen numbering — the resulting program is identical, bit for bit, to the sequential one
     // (QIW_COMPILE_THREADS=1 forces the sequential walk; the host-logic tests compare both).
     int n_threads = (int)std::min<unsigned>((unsigned)m.S, std::max(1u, std::thread::hardware_concurrency()));
-    if (const char* env = getenv("QIW_COMPILE_THREADS")) n_threads = std::max(1, std::min(atoi(env), m.S));
     {   // small entries: a thread costs more than the walk.  Work estimate: trees x (attachable pairs per sector)^order
         double attach = 0;
         for (int s = 0; s < m.S; ++s) attach += (double)m.attachable[s].size();
@@ -260,6 +259,7 @@ int compile_entry(const HostModel& m, int mode, int order, int n_pts_after, int 
         for (int a = 0; a < order; ++a) est *= attach;
         if (est < 2e4) n_threads = 1;
     }
+    if (const char* env = getenv("QIW_COMPILE_THREADS")) n_threads = std::max(1, std::min(atoi(env), m.S));   // an explicit request wins
     Builder b(m, e);
     if (n_threads <= 1) {
         for (int s_i = 0; s_i < m.S; ++s_i)

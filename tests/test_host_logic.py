@@ -279,6 +279,7 @@ def test_threaded_compile_is_bit_identical(qlib, model, monkeypatch):
     else:
         ex, grid, f = models.two_band(n_tau=8)
         cases = [(qlib.MODE_BOLD, 3, 1, 0), (qlib.MODE_BOLD, 3, 4, 0), (qlib.MODE_CORR, 3, 2, 0), (qlib.MODE_BARE, 3, 6, 0)]
+        monkeypatch.setenv("QIW_WALK_UNIT_COST", "150")     # deep cuts: many units per tree, long replayed paths
     digests = {}
     for threads in ("1", "8"):
         monkeypatch.setenv("QIW_COMPILE_THREADS", threads)
