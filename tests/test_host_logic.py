@@ -63,8 +63,11 @@ def test_topologies_bit_exact(qlib, oracle_lib):
             for ext in (False, True):
                 a, b = qlib.topologies(n, k, ext), oracle_lib.topologies(n, k, ext)
                 assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (n, k, ext)
-    assert len(qlib.topologies(6, 1)[1]) == 2830 + 0 or True
-    assert [len(qlib.topologies(n, 1)[1]) for n in range(1, 7)] == [1, 1, 4, 27, 248, 2830]
+    # test/diagrammatics.jl:53-60 irreducible counts, (2n-1)!! totals (:26-42); order 7 is SURVEY N1's target size
+    assert [len(qlib.topologies(n, 1)[1]) for n in range(1, 8)] == [1, 1, 4, 27, 248, 2830, 38232]
+    assert [len(qlib.topologies(n)[1]) for n in range(8)] == [1, 1, 3, 15, 105, 945, 10395, 135135]
+    a, b = qlib.topologies(6, 5), oracle_lib.topologies(6, 5)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
 def test_partitioning(qlib, oracle_lib):
