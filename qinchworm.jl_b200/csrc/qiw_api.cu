@@ -11,6 +11,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -489,15 +490,19 @@ static int build_walk_units(const HostModel& hm, const EntryProgram& pr, EntryDe
     n_threads = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(n_trees, 1));
     auto for_tree_ranges = [&](const std::function<void(int, size_t, size_t)>& fn) {
         if (n_threads <= 1) { fn(0, 0, n_trees); return; }
+        auto work = [&](int w) {   // ranges of equal word count, not equal tree count
+            auto cut = [&](int i) {
+                const size_t want = n_real * (size_t)i / (size_t)n_threads;
+                return (size_t)(std::lower_bound(pr.tree_off.begin(), pr.tree_off.begin() + n_trees, (uint32_t)want) - pr.tree_off.begin());
+            };
+            fn(w, w == 0 ? 0 : cut(w), w == n_threads - 1 ? n_trees : cut(w + 1));
+        };
         std::vector<std::thread> pool;
-        for (int w = 0; w < n_threads; ++w)   // ranges of equal word count, not equal tree count
-            pool.emplace_back([&, w]() {
-                auto cut = [&](int i) {
-                    const size_t want = n_real * (size_t)i / (size_t)n_threads;
-                    return (size_t)(std::lower_bound(pr.tree_off.begin(), pr.tree_off.begin() + n_trees, (uint32_t)want) - pr.tree_off.begin());
-                };
-                fn(w, w == 0 ? 0 : cut(w), w == n_threads - 1 ? n_trees : cut(w + 1));
-            });
+        int started = 0;
+        try {
+            for (; started < n_threads - 1; ++started) pool.emplace_back(work, started);
+        } catch (const std::system_error&) {}   // no more threads to be had: the caller does the rest itself
+        for (int w = started; w < n_threads; ++w) work(w);
         for (auto& t : pool) t.join();
     };
     std::vector<char> fits_w(n_threads, 1);

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <map>
 #include <memory>
+#include <system_error>
 #include <thread>
 #include <tuple>
 
@@ -275,12 +276,16 @@ int compile_entry(const HostModel& m, int mode, int order, int n_pts_after, int 
             for (int p = 0; p <= kMaxNodes; ++p) { fe.pos_src[p] = e.pos_src[p]; fe.fixed_op[p] = e.fixed_op[p]; }
             frag[s_i]->b.reset(new Builder(m, fe));
         }
+        auto work = [&](int w) {
+            for (int s_i = w; s_i < m.S; s_i += n_threads)
+                frag[s_i]->rc = frag[s_i]->b->walk_sector(s_i, n_top, pairs, parity, kind, vertex_pos, frag[s_i]->err);
+        };
         std::vector<std::thread> pool;
-        for (int w = 0; w < n_threads; ++w)
-            pool.emplace_back([&, w]() {
-                for (int s_i = w; s_i < m.S; s_i += n_threads)
-                    frag[s_i]->rc = frag[s_i]->b->walk_sector(s_i, n_top, pairs, parity, kind, vertex_pos, frag[s_i]->err);
-            });
+        int started = 0;
+        try {
+            for (; started < n_threads - 1; ++started) pool.emplace_back(work, started);
+        } catch (const std::system_error&) {}   // no more threads to be had: the caller does the rest itself
+        for (int w = started; w < n_threads; ++w) work(w);
         for (auto& t : pool) t.join();
         for (int s_i = 0; s_i < m.S; ++s_i)
             if (frag[s_i]->rc) { err = frag[s_i]->err; return 1; }
@@ -403,7 +408,11 @@ void factorise_records(EntryProgram& e, int S, int K_req) {
     if (const char* env = getenv("QIW_COMPILE_THREADS")) threaded = threaded && atoi(env) > 1;
     if (threaded) {
         std::vector<std::thread> pool;
-        for (int K = K_lo; K <= K_hi; ++K) pool.emplace_back([&, K]() { build(K, cand[K - K_lo]); });
+        int K = K_lo;
+        try {
+            for (; K < K_hi; ++K) pool.emplace_back([&, K]() { build(K, cand[K - K_lo]); });
+        } catch (const std::system_error&) {}   // no more threads to be had: the caller does the rest itself
+        for (; K <= K_hi; ++K) build(K, cand[K - K_lo]);
         for (auto& t : pool) t.join();
     } else {
         for (int K = K_lo; K <= K_hi; ++K) build(K, cand[K - K_lo]);
