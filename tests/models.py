@@ -86,6 +86,14 @@ def hubbard_dimer_exact_rho(beta=1.0, U=4.0, eps2=0.0, V=0.5):
     return red
 
 
+def two_site_dimer_exact_rho(beta=1.0, e1=0.5, e2=2.0, V=0.5):
+    """Exact occupation probabilities (empty, occupied) of level 1 of the two-site dimer of test/dimers.jl:38-59."""
+    w, v = np.linalg.eigh(np.array([[e1, V], [V, e2]]))
+    Z = 1 + np.exp(-beta * w).sum() + np.exp(-beta * (e1 + e2))
+    occ = ((v[0] ** 2 * np.exp(-beta * w)).sum() + np.exp(-beta * (e1 + e2))) / Z
+    return np.array([1 - occ, occ])
+
+
 def bold_entries(make, orders, n_pts_after_max=None):
     out = []
     for o in orders:

@@ -479,3 +479,19 @@ def test_paired_records(gpu_ctx, qlib, oracle_lib, monkeypatch, arith):
         assert relerr(got, ref) < RTOL, (mode, relerr(got, ref))
     prs = gpu_ctx.entry_pair_records(ids[-1])
     assert len(prs["rec_pair"]) > 0
+
+
+@pytest.mark.parametrize("spline", [True, False])
+def test_two_site_dimer_physics(gpu_ctx, qlib, oracle_lib, spline):
+    """test/dimers.jl:34-119 through the product path: rho of the two-site dimer (orders 0:3, n_tau = 32, N = 128,
+    spline-interpolated and plain grid functions) within the reference's 1e-4 of exact diagonalisation, and P(tau)
+    equal to the oracle's."""
+    from qinchworm_b200 import ppgf
+    from qinchworm_b200.inchworm import Solver, inchworm
+    ex, grid, f = models.single_level(n_tau=32, beta=1.0, mu=-0.5, eps=2.0, V=0.5, spline=spline, rev="reverse")
+    ref = oracle_lib.inchworm(ex.flatten(), ex.P, range(0, 4), range(0, 4), 8 * 2 ** 4)["P"]
+    inchworm(ex, grid, range(0, 4), range(0, 4), 8 * 2 ** 4, solver=Solver(ex, ctx=gpu_ctx))
+    assert relerr(ex.P, ref) < RTOL
+    ppgf.normalize(ex)
+    rho = np.array([d[0, 0].real for d in ppgf.density_matrix(ex)])
+    assert np.abs(rho - models.two_site_dimer_exact_rho()).max() < 1e-4

@@ -142,6 +142,22 @@ def test_dimer_physics(oracle_lib):
     assert np.isclose(np.trace(rho).real, 1.0)
 
 
+@pytest.mark.parametrize("spline", [True, False])
+@pytest.mark.parametrize("max_order", [1, 3])
+def test_two_site_dimer_physics(oracle_lib, spline, max_order):
+    """test/dimers.jl:34-119 ("Dimer": one level eps_1 = 0.5 hybridised with one bath level eps_2 = 2, V = 0.5,
+    beta = 1, n_tau = 32, N = 128; orders 0:1 and 0:3; spline-interpolated and plain grid functions):
+    |rho - rho_exact| < 1e-4, the reference's own tolerance."""
+    from qinchworm_b200 import ppgf
+    ex, grid, f = models.single_level(n_tau=32, beta=1.0, mu=-0.5, eps=2.0, V=0.5, spline=spline, rev="reverse")
+    orders = range(0, max_order + 1)
+    ex.P = oracle_lib.inchworm(ex.flatten(), ex.P, orders, orders, 8 * 2 ** 4)["P"]
+    ppgf.normalize(ex)
+    rho = np.array([d[0, 0].real for d in ppgf.density_matrix(ex)])
+    assert np.abs(rho - models.two_site_dimer_exact_rho()).max() < 1e-4
+    assert abs(rho.sum() - 1) < 1e-12
+
+
 def test_block_basis_rotation_invariance(oracle_lib):
     """d_s > 1 is unpinned at the reference level: the oracle must at least be
     invariant under a rotation of the basis inside a degenerate multi-dimensional sector."""
