@@ -43,6 +43,19 @@ def anderson(n_tau=200, beta=10.0, eps=0.1, U=1.0, D=2.0, V=0.5, corr=False):
     return ex, grid, f
 
 
+def bethe_two_orbital(n_tau=128, mu_bethe=0.25, beta=10.0, V=0.5, t_bethe=0.5):
+    """test/bethe.jl:61-89: two non-interacting spin orbitals (H = 0), each hybridised with a Bethe bath centred at
+    mu_bethe; pairs as the `hybridization=` constructor generates them (src/expansion.jl:239-258)."""
+    f = FockSpace([[1], [2]])
+    ed = EDCore(f, 0.0 * f.n_op(1))
+    grid = ImaginaryTimeGrid(beta, n_tau)
+    D = bethe_dos_gf(grid, t=t_bethe, eps=mu_bethe) * V ** 2
+    pairs = []
+    for o in (1, 2):
+        pairs += [InteractionPair(f.c_dag(o), f.c(o), D), InteractionPair(f.c(o), f.c_dag(o), reverse_gf(D))]
+    return Expansion(ed, grid, pairs), grid, f
+
+
 def bethe_two_state(n_tau=64, beta=8.0, V=1.0, t_bethe=1.0, mu=0.0):
     """bench/bethe_gf_convergence: spinless level on a Bethe bath (2 sectors), G = <c(tau) c^dag(0)>."""
     f = FockSpace([["0"]])
