@@ -193,6 +193,28 @@ def test_bethe_dlr_references(oracle_lib, max_order, own, limit):
             assert diff[own] < diff[other], (own, other, diff)
 
 
+@pytest.mark.parametrize("max_order,N,own,other,rho_limit,g_limit", [(1, 8 * 2 ** 5, "NCA", "OCA", 2e-3, 3e-3),
+                                                                       (2, 8 * 2 ** 6, "OCA", "NCA", 2e-3, 1e-3)])
+def test_bethe_gf_dlr_references(oracle_lib, max_order, N, own, other, rho_limit, g_limit):
+    """test/bethe_gf.jl:120-157 against test/bethe.h5 (/rho/*, /g/*): inchworm! at orders 0:n, then
+    g = -correlator_2p at orders_gf 0:n-1 (n_tau = 128, mu_bethe = 0.25), with the reference's own tolerances
+    (its order-3 block is @test_skip)."""
+    from qinchworm_b200 import ppgf
+    from qinchworm_b200.expansion import add_corr_operators
+    G = load_golden("bethe_h5.json")
+    ex, grid, f = models.bethe_two_orbital(n_tau=128, mu_bethe=0.25)
+    orders = range(0, max_order + 1)
+    ex.P = oracle_lib.inchworm(ex.flatten(), ex.P, orders, orders, N, n_ranks=4)["P"]
+    ppgf.normalize(ex)
+    rho = np.diag(ex.ed.to_fock_basis(ppgf.density_matrix(ex))).real
+    d_rho = {k: float(np.abs(rho - np.diag(np.asarray(G["/rho/" + k]).reshape(4, 4)).real).max()) for k in ("NCA", "OCA", "TCA", "exact")}
+    assert d_rho[own] < rho_limit and all(d_rho[own] < d_rho[k] for k in d_rho if k != own)
+    add_corr_operators(ex, (f.c(1), f.c_dag(1)))
+    g = -oracle_lib.correlator_2p(ex.flatten(), ex.P, range(0, max_order), N, threads=4)
+    d_g = {k: float(np.abs(G["/g/" + k].ravel() - g).max()) for k in ("NCA", "OCA", "TCA")}
+    assert d_g[own] < g_limit and d_g[own] < d_g[other]
+
+
 def test_block_basis_rotation_invariance(oracle_lib):
     """d_s > 1 is unpinned at the reference level: the oracle must at least be
     invariant under a rotation of the basis inside a degenerate multi-dimensional sector."""
