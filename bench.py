@@ -20,7 +20,14 @@ index range, one ncclAllReduce per inchworm step).  One "step" = one complete in
     cpu_baseline : the CPU oracle port (faithful restatement of the reference algorithm), all host
                    cores, on a bounded sample of the same workload
 
-`--impl reference` times the CPU port alone (the Julia reference cannot run here: no Julia).
+    parity       : the same workload on the CPU oracle (the cpu_baseline leg runs it anyway): P(tau), Z, rho_imp and
+                   G(tau) element-wise against the GPU's, tolerance 1e-10; above it the bench exits non-zero.  At N > 1
+                   GPUs rank 0 checks the first bold steps of the sharded run against the oracle at the same N_samples.
+    stress_c5_step : BASELINE.json configs[4] (orders 0:6, n_tau = 400, N_samples = 2^20 FIXED, i.e. strong scaling over
+                   the GPUs of the job), a few bold steps in the middle of the run, with its own oracle check at N = 2^6.
+
+`--impl reference` times the CPU port alone (the Julia reference cannot run here: no Julia), at the SAME N_samples
+as the GPU arm of the same --gpus (2^10 per GPU), on a bounded number of steps.
 """
 import argparse
 import json
@@ -112,15 +119,27 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}
 
 
-def cpu_port_run(threads, bold_steps, N):
+PARITY_TOL = 1e-10
+
+
+def relerr_elem(a, b, floor=1e-3):
+    """Element-wise relative difference; components below `floor` x the largest are compared with that floor."""
+    a, b = np.asarray(a), np.asarray(b)
+    scale = np.maximum(np.abs(b), floor * max(float(np.abs(b).max()), 1e-300))
+    return float((np.abs(a - b) / scale).max())
+
+
+def cpu_port_run(threads, bold_steps, N, pool=True, keep=False):
     """Bounded sample of the workload on the CPU oracle port: bare step + first `bold_steps` bold steps."""
     import models
     from oracle import oracle as orc
     ex, grid, f = models.anderson(n_tau=N_TAU)
     pl = ex.flatten()
     t0 = time.perf_counter()
-    res = orc.inchworm(pl, ex.P, ORDERS, ORDERS, N, threads=threads, max_bold_steps=bold_steps)
+    res = orc.inchworm(pl, ex.P, ORDERS, ORDERS, N, threads=threads, max_bold_steps=bold_steps, pool=pool)
     dt = time.perf_counter() - t0
+    if keep:
+        return res["evals"] / dt, dt, res["evals"], res
     return res["evals"] / dt, dt, res["evals"]
 
 
@@ -131,8 +150,8 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    bold_steps = 40
-    N = N_PER_GPU
+    N = N_PER_GPU * max(args.gpus, 1)            # the GPU arm's N_samples at this --gpus (weak scaling)
+    bold_steps = max(2, 40 // max(args.gpus, 1))  # bounded: the same CPU work per step whatever --gpus
     vals = []
     for i in range(args.warmup + args.steps):
         v, dt, ev = cpu_port_run(cores, bold_steps, N)
@@ -148,7 +167,8 @@ def run_reference(args):
         "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus, N),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "oracle port (C++ restatement of the reference algorithm); the Julia+MPI reference itself cannot run: no Julia in the image"}))
+        "note": "oracle port (C++ restatement of the reference algorithm, persistent worker threads = ranks); the Julia+MPI "
+                "reference itself cannot run: no Julia in the image"}))
 
 
 def main():
@@ -158,6 +178,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stress", action="store_true", help="skip the C5 stress-step section")
+    ap.add_argument("--stress-log2n", type=int, default=20)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -233,6 +255,9 @@ def main():
     wall_ms = max_over_ranks(wall_ms)
     value = evals_per_run / (ms_per_step * 1e-3)
     P_dev = ctx.get_P()
+    ctx.set_P(0, P_atomic)
+    hist_dev = ctx.inchworm_run(bare_ids, bold_ids, N, want_contribs=True)   # untimed: per-entry contributions of every step
+    assert np.array_equal(ctx.get_P(), P_dev), "device-resident run is not reproducible bit for bit"
 
     # ---- e2e: the public API call with host buffers (wall clock around the call) ----
     def host_run(device_resident):
@@ -345,6 +370,54 @@ def main():
                        "frac_of_measured_fp64_peak": fl * n4 / (m_ * 1e-3) / 1e12 / fp64_peak}
         ctx4.close()
 
+    # ---- C5 stress step (BASELINE.json configs[4]): orders 0:6, n_tau = 400, N_samples = 2^20 FIXED and sharded over
+    #      the GPUs of the job (strong scaling), three bold steps in the middle of the run, through qiw_eval (one launch
+    #      + all-reduce per step).  Checked against the oracle at N = 2^6 on the same entries (the oracle cannot do 2^20).
+    stress = None
+    if not args.no_stress:
+        ex5, grid5, _ = models.anderson(n_tau=400)
+        ctx5 = lib.Context(device=local)
+        solver5 = Solver(ex5, ctx=ctx5)
+        kind5 = mpi.init_comm(ctx5) if world > 1 else "single"
+        t0 = time.perf_counter()
+        N5 = 2 ** args.stress_log2n
+        ent5 = _bold_entries(solver5, range(0, 7), N5, None, None)
+        t_compile = time.perf_counter() - t0
+        ids5 = [t.entry_id for t in ent5]
+        st5 = [ctx5.entry_stats(i) for i in ids5]
+        tops5 = sum(x["n_top"] for x in st5)
+        fl5 = sum(x["flops_per_sample"] for x in st5)
+        tau5 = grid5.tau
+        # parity at N = 2^6: all 37 entries (orders 0-6) against the oracle, element-wise per entry
+        got = ctx5.eval(0.0, tau5[200], tau5[201], ids5, 64)
+        c5_par = None
+        if rank == 0:
+            from oracle import oracle as orc
+            o5 = orc.Oracle(solver5.payload, ex5.P, threads=os.cpu_count() or 1)
+            for j, t in enumerate(ent5):
+                o5.set_topologies(j, lib.MODE_BOLD, t.order, t.n_pts_after, t.topologies[0], t.topologies[1])
+            ref = o5.eval(0.0, tau5[200], tau5[201], list(range(len(ent5))), 64)
+            c5_par = max(relerr_elem(got[j], ref[j]) for j in range(len(ent5)))
+        ctx5.eval(0.0, tau5[200], tau5[201], ids5, N5)      # warm-up: fills the simplex-root cache
+        barrier()
+        dms = []
+        t0 = time.perf_counter()
+        for k in range(3):
+            ctx5.eval(0.0, tau5[200 + k], tau5[201 + k], ids5, N5)
+            dms.append(ctx5.last_device_ms())
+        torch.cuda.synchronize()
+        wall5 = max_over_ranks((time.perf_counter() - t0) / 3)
+        dev5 = max_over_ranks(float(np.mean(dms)))
+        stress = {"workload": "C5: Anderson orders 0:6, n_tau=400, N_samples=2^%d total (strong scaling), one bold step; mean of 3"
+                              % args.stress_log2n, "n_gpus": world, "scaling": "strong", "collective": kind5,
+                  "topologies": tops5, "configurations": sum(x["n_leaves"] for x in st5), "host_compile_s": t_compile,
+                  "step_ms_device_max": dev5, "step_ms_wall_max": wall5,
+                  "diagram_evals_per_s": N5 * tops5 / (wall5), "algorithmic_tflops": fl5 * N5 / wall5 / 1e12,
+                  "algorithmic_frac_of_fp64_peak_per_gpu": fl5 * N5 / wall5 / 1e12 / fp64_peak / world,
+                  "projected_full_run_s": wall5 * 398,
+                  "parity_N64_vs_oracle_max_rel_elem": c5_par, "parity_pass": (c5_par is None or c5_par < PARITY_TOL)}
+        ctx5.close()
+
     # ---- cold call: what a user pays the first time (fresh context, model upload, host compilation of all
     #      entries, then the run); the e2e figure above reuses the compiled session, as a production run over
     #      many inchworm! calls on one Expansion does.  Reported, never the headline; a failure here is recorded. ----
@@ -367,14 +440,60 @@ def main():
         except Exception as e:      # noqa: BLE001
             first_call = {"error": repr(e)}
 
-    # ---- CPU baseline: oracle port on a bounded sample, rank 0 at N=1 only ----
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    # ---- CPU baseline + parity: the oracle port runs the WHOLE C1 workload once (rank 0, N=1 GPU); its P table, Z, rho
+    #      and G(tau) are the reference the GPU results are held to (element-wise, 1e-10) ----
+    cpu, parity_rec = None, None
+    g_dev = None
+    if world == 1 and not args.no_cpu_baseline:
+        # G(tau) = correlator_2p(expansion, grid, orders 0:3, N) on the converged P of the device-resident run (all ranks)
+        from qinchworm_b200.expansion import add_corr_operators
+        from qinchworm_b200.inchworm import correlator_2p
+        ex.P[:] = P_dev
+        add_corr_operators(ex, (f.c("up"), f.c_dag("up")))
+        t = time.perf_counter()
+        g_dev = correlator_2p(ex, grid, range(0, 4), N, solver=solver)[0]
+        g_ms = (time.perf_counter() - t) * 1e3
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
         cores = os.cpu_count() or 1
-        v, dt, ev = cpu_port_run(cores, None, N_PER_GPU)          # the complete inchworm! run (about 10 s on 16 cores)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt, "inchworm_wall_ms": dt * 1e3,
-               "sample": "the whole workload once: bare step + all %d bold steps at N_samples=%d (%.3g diagram evals), "
-                         "%d threads (reference's split_count rule)" % (N_TAU - 2, N_PER_GPU, ev, cores)}
+        if world == 1:
+            v, dt, ev, res = cpu_port_run(cores, None, N, keep=True)          # the complete inchworm! run
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt, "inchworm_wall_ms": dt * 1e3,
+                   "sample": "the whole workload once: bare step + all %d bold steps at N_samples=%d (%.3g diagram evals), "
+                             "%d persistent worker threads (reference's split_count rule)" % (N_TAU - 2, N, ev, cores)}
+            v_old, dt_old, _ = cpu_port_run(cores, 20, N, pool=False)
+            v_new, dt_new, _ = cpu_port_run(cores, 20, N, pool=True)
+            cpu["thread_per_call_vs_pool"] = {"sample": "bare + 20 bold steps", "round1_thread_per_entry_call_evals_per_s": v_old,
+                                              "persistent_pool_evals_per_s": v_new}
+            P_ref = res["P"]
+            Zd, Zr = (1j * P_dev[-1]).sum(), (1j * P_ref[-1]).sum()
+            t = time.perf_counter()
+            g_ref = orc.correlator_2p(ex.flatten(), P_ref, range(0, 4), N, threads=cores)
+            g_cpu_s = time.perf_counter() - t
+            # G on the GPU was computed from the GPU's own P: the comparison covers inchworm! and correlator_2p end to end
+            parity_rec = {"against": "CPU oracle, whole C1 workload (n_tau=200, orders 0:4, N=2^10; G: orders 0:3)",
+                          "measure": "max over elements of |gpu - oracle| / max(|oracle|, 1e-3 max|oracle|)",
+                          "max_rel_diff_vs_oracle_P": relerr_elem(P_dev, P_ref),
+                          "max_rel_diff_vs_oracle_P_orders": max(relerr_elem(sum(hist_dev[:, j] for j, t_ in enumerate(bare + bold) if t_.order == o_),
+                                                                             res["P_orders"][o_]) for o_ in ORDERS),
+                          "max_rel_diff_vs_oracle_Z": float(abs(Zd - Zr) / abs(Zr)),
+                          "max_rel_diff_vs_oracle_rho": relerr_elem(1j * P_dev[-1] / Zd, 1j * P_ref[-1] / Zr),
+                          "max_rel_diff_vs_oracle_G": relerr_elem(g_dev, g_ref),
+                          "Z": [Zd.real, Zd.imag], "rho": [float(x) for x in (1j * P_dev[-1] / Zd).real],
+                          "G_gpu_ms": g_ms, "G_oracle_s": g_cpu_s, "tolerance": PARITY_TOL}
+        else:
+            # sharded run: the oracle at the SAME N_samples for the bare step and the first bold steps; the per-order
+            # contributions of those steps are un-normalised, so they compare one to one with the device's
+            n_chk = 3
+            res = orc.inchworm(ex.flatten(), P_atomic, ORDERS, ORDERS, N, threads=cores, max_bold_steps=n_chk)
+            worst = 0.0
+            for o_ in ORDERS:
+                dev_o = sum(hist_dev[:, j] for j, t_ in enumerate(bare + bold) if t_.order == o_)
+                worst = max(worst, relerr_elem(dev_o[1:n_chk + 2], res["P_orders"][o_][1:n_chk + 2]))
+            parity_rec = {"against": "CPU oracle at the same N_samples=%d: bare step + first %d bold steps, per-order contributions "
+                                     "(all ranks hold bit-identical sums by construction; tests/multigpu_check.py checks that)" % (N, n_chk),
+                          "max_rel_diff_vs_oracle_P_orders": worst, "tolerance": PARITY_TOL}
+        parity_rec["pass"] = all(v < PARITY_TOL for k, v in parity_rec.items() if k.startswith("max_rel_diff"))
 
     if rank == 0:
         print(json.dumps({
@@ -392,11 +511,18 @@ def main():
                                      "h2d_bytes_per_step": (N_TAU - 1) * N_TAU * bs * 16,
                                      "d2h_bytes_per_step": len(bare_ids) * bs * 16 + (N_TAU - 2) * len(bold_ids) * bs * 16,
                                      "max_rel_diff_vs_device_resident": parity_stepped}},
+            "e2e_stepped": {"value": evals_per_run / (stepped_ms * 1e-3), "unit": UNIT, "ms": stepped_ms,
+                            "api": "inchworm(..., device_resident=False): one qiw_eval per step through the three-worker seam "
+                                   "(inchworm_step_bare / inchworm_step), set_ppgf!/normalize! on the host",
+                            "note": "the headline e2e goes through the optional whole-run entry qiw_inchworm_run; this is the drop-in seam of INTEGRATION.md"},
+            "parity": parity_rec, "stress_c5_step": stress,
             "gpu_launches": int(launches), "collective": comm_kind, "roofline": roofline, "saturated_step_kernel": saturated, "block_model_step": block_model, "cpu_baseline": cpu, "clocks": sampler.summary()}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+    if rank == 0 and ((parity_rec and not parity_rec["pass"]) or (stress and not stress["parity_pass"])):
+        raise SystemExit("bench.py: GPU results differ from the oracle by more than %g" % PARITY_TOL)
 
 
 if __name__ == "__main__":

@@ -39,7 +39,7 @@ def lib():
         L.qo_create.restype = C.c_void_p
         L.qo_last_error.restype = C.c_char_p
         L.qo_set_and_normalize.restype = C.c_double
-        for name in ("qo_destroy", "qo_last_error", "qo_set_threads", "qo_set_model", "qo_set_delta",
+        for name in ("qo_destroy", "qo_last_error", "qo_set_threads", "qo_set_pool", "qo_set_model", "qo_set_delta",
                      "qo_set_grid", "qo_set_P", "qo_get_P", "qo_set_topologies", "qo_eval",
                      "qo_eval_at_times", "qo_last_counts", "qo_set_and_normalize"):
             getattr(L, name).argtypes = None
@@ -166,6 +166,10 @@ class Oracle:
     def set_threads(self, n):
         self.L.qo_set_threads(self.h, C.c_int(n))
 
+    def set_pool(self, on):
+        """True (default): persistent worker threads with cached evaluators; False: a thread per (entry, call)."""
+        self.L.qo_set_pool(self.h, C.c_int(int(on)))
+
     def set_P(self, first, rows):
         r, rv = _c2d(np.atleast_2d(rows))
         self.L.qo_set_P(self.h, C.c_int(first), C.c_int(r.shape[0]), rv.ctypes.data_as(C.POINTER(C.c_double)))
@@ -243,7 +247,7 @@ def _diag_idx(dims):
 
 
 def inchworm(payload, P0_table, orders, orders_bare, N_samples, n_pts_after_max=None, threads=1,
-             n_ranks=1, max_bold_steps=None):
+             n_ranks=1, max_bold_steps=None, pool=True):
     """inchworm!(expansion, grid, orders, orders_bare, N_samples) on the oracle.
 
     Returns dict(P=[n_tau,bsize] final (per-step normalised) table, P_orders={order: [n_tau,bsize]},
@@ -251,6 +255,7 @@ def inchworm(payload, P0_table, orders, orders_bare, N_samples, n_pts_after_max=
     (src/mpi.jl:49-54): every "rank" evaluates its sub-range and the partial sums are added.
     """
     o = Oracle(payload, P0_table, threads=threads)
+    o.set_pool(pool)
     n_tau, beta = o.n_tau, o.beta
     tau = np.linspace(0.0, beta, n_tau)
     orders, orders_bare = list(orders), list(orders_bare)

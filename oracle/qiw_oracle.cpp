@@ -22,7 +22,11 @@
 #include <complex>
 #include <cstdint>
 #include <cstring>
+#include <condition_variable>
 #include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -224,6 +228,12 @@ struct Oracle {
     std::vector<cplx> P;  // [k][bsize]
     std::vector<Entry> entries;
     int n_threads = 1;
+    // host threads: a persistent pool whose workers keep one evaluator per entry across calls (the moral
+    // equivalent of persistent MPI ranks, src/mpi.jl:49-54); use_pool = 0 restores one std::thread per
+    // (entry, call) with a fresh evaluator each, as the reference rebuilds its TopologyEvaluator every step
+    int use_pool = 1;
+    uint64_t cache_epoch = 0;      // bumped whenever the model or an entry changes: cached evaluators are stale
+    struct Pool* pool = nullptr;
     std::string err;
     // flop counter of the last evaluation (8*m*k*n per live edge + 8*d_i*d_f per leaf)
     double last_flops_per_sample = 0, last_leaves = 0, last_edges = 0;
@@ -412,6 +422,14 @@ struct Evaluator {
         ident_mats.assign(n_nodes, std::vector<cplx>(o.bsize));
     }
 
+    // a cached evaluator is re-used at the next step: only the times of the fixed nodes change
+    void set_fixed_times(int n_pts_after, double t_i, double t_w, double t_f) {
+        const int n = order;
+        if (mode == QO_MODE_BARE) { times[0] = t_i; times[2 * n + 1] = t_f; }
+        else { times[0] = t_i; times[2 * n - n_pts_after + 1] = t_w; times[2 * n + 2] = t_f; }
+        flops = 0; leaves = 0;
+    }
+
     // i * P_s(t_f, t_i) for every sector  (:357-374; bare: src/exact_atomic_ppgf.jl:109-118)
     void fill_ppgf(int i, double t_i, double t_f) {
         if (t_f < t_i) t_f = t_i;  // :362-364
@@ -565,19 +583,21 @@ static void double_simplex_transform(int d_lesser, int d_greater, double u_i, do
 // N_total points: returns sum / N_total, i.e. rank_weight * contour_integral(...) of
 // src/inchworm.jl:176-188 (bold), :281-293 (bare), :855-875 (correlator, trace taken by caller).
 // contour_integral / qmc_integral: src/qmc_integrate.jl:497-507,597-612.
-static void eval_entry_range(Oracle& o, const Entry& e, double t_i, double t_w, double t_f, int corr_idx,
+static bool eval_entry_range_core(Oracle& o, const Entry& e, double t_i, double t_w, double t_f, int corr_idx,
                              const uint32_t* m, const uint32_t* x0, uint64_t start, uint64_t count,
-                             uint64_t N_total, cplx* out, double* flops, double* leaves) {
+                             uint64_t N_total, cplx* out, double* flops, double* leaves, Evaluator* cached = nullptr) {
     int n = e.order, d = 2 * n;
-    Evaluator ev(o, e.mode, n, e.n_pts_after, t_i, t_w, t_f, corr_idx);
+    std::unique_ptr<Evaluator> own;
+    if (!cached) own.reset(new Evaluator(o, e.mode, n, e.n_pts_after, t_i, t_w, t_f, corr_idx));
+    else cached->set_fixed_times(e.n_pts_after, t_i, t_w, t_f);
+    Evaluator& ev = cached ? *cached : *own;
     std::vector<cplx> acc(o.bsize, cplx(0));
     if (n == 0) {  // exact, no sampling: src/inchworm.jl:148-156,258-266,833-841
         const std::vector<cplx>& r = ev(e.tops, nullptr);
         for (int k = 0; k < o.bsize; ++k) out[k] = r[k];
         if (flops) *flops = ev.flops;
         if (leaves) *leaves = ev.leaves;
-        if (ev.offdiag_error) o.err = "block off-diagonal contribution (src/topology_eval.jl:462)";
-        return;
+        return ev.offdiag_error;
     }
     SobolSeq seq;
     seq.D = d; seq.n = 0;
@@ -605,7 +625,20 @@ static void eval_entry_range(Oracle& o, const Entry& e, double t_i, double t_w, 
     for (int k = 0; k < o.bsize; ++k) out[k] = acc[k] / (double)N_total;
     if (flops) *flops = count ? ev.flops / (double)count : 0;
     if (leaves) *leaves = count ? ev.leaves / (double)count : 0;
-    if (ev.offdiag_error) o.err = "block off-diagonal contribution (src/topology_eval.jl:462)";
+    return ev.offdiag_error;
+}
+
+static void eval_entry_range(Oracle& o, const Entry& e, double t_i, double t_w, double t_f, int corr_idx,
+                             const uint32_t* m, const uint32_t* x0, uint64_t start, uint64_t count,
+                             uint64_t N_total, cplx* out, double* flops, double* leaves) {
+    if (eval_entry_range_core(o, e, t_i, t_w, t_f, corr_idx, m, x0, start, count, N_total, out, flops, leaves))
+        o.err = "block off-diagonal contribution (src/topology_eval.jl:462)";
+}
+// for the pool's workers: the sector-mismatch flag stays in the evaluator (the caller collects it)
+static void eval_entry_range_quiet(Oracle& o, const Entry& e, double t_i, double t_w, double t_f, int corr_idx,
+                                   const uint32_t* m, const uint32_t* x0, uint64_t start, uint64_t count,
+                                   uint64_t N_total, cplx* out, double* flops, double* leaves, Evaluator* ev) {
+    eval_entry_range_core(o, e, t_i, t_w, t_f, corr_idx, m, x0, start, count, N_total, out, flops, leaves, ev);
 }
 
 // split_count / range_from_chunks_and_idx: src/utility.jl:164-179 (0-based start returned)
@@ -617,8 +650,51 @@ static void rank_sub_range(uint64_t N, int n_ranks, int rank, uint64_t* start, u
     *count = (uint64_t)rank < r ? q + 1 : q;
 }
 
+// Persistent host threads.  Worker r plays MPI rank r of the reference (src/mpi.jl:49-54): in every call it
+// evaluates its rank_sub_range of every sampled entry, one after the other, with evaluators it keeps from call to
+// call (keyed by entry id and correlator index; dropped when the model or an entry changes).
+struct Pool {
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    uint64_t gen = 0;
+    int pending = 0;
+    bool stop = false;
+    std::function<void(int)> job;
+    struct Cache { uint64_t epoch = ~0ull; std::map<std::pair<int, int>, std::unique_ptr<Evaluator>> ev; };
+    std::vector<Cache> cache;
+    explicit Pool(int nt) : cache(nt) {
+        for (int r = 0; r < nt; ++r)
+            th.emplace_back([this, r]() {
+                uint64_t seen = 0;
+                for (;;) {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv_go.wait(lk, [&] { return stop || gen != seen; });
+                    if (stop) return;
+                    seen = gen;
+                    lk.unlock();
+                    job(r);
+                    lk.lock();
+                    if (--pending == 0) cv_done.notify_one();
+                }
+            });
+    }
+    ~Pool() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv_go.notify_all();
+        for (auto& t : th) t.join();
+    }
+    void run(const std::function<void(int)>& f) {
+        std::unique_lock<std::mutex> lk(mu);
+        job = f; pending = (int)th.size(); ++gen;
+        cv_go.notify_all();
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+};
+
 // Whole range [start, start+count) split over host threads with the same rule the reference uses
-// over MPI ranks (src/mpi.jl:49-54), partial sums added (src/mpi.jl:104-127).
+// over MPI ranks (src/mpi.jl:49-54), partial sums added in rank order (src/mpi.jl:104-127).
+// use_pool = 0: one std::thread per (entry, call), each with a fresh evaluator.
 static void eval_entry(Oracle& o, const Entry& e, double t_i, double t_w, double t_f, int corr_idx,
                        const uint32_t* m, const uint32_t* x0, uint64_t start, uint64_t count,
                        uint64_t N_total, cplx* out) {
@@ -641,6 +717,54 @@ static void eval_entry(Oracle& o, const Entry& e, double t_i, double t_w, double
     for (auto& t : th) t.join();
     for (int k = 0; k < o.bsize; ++k) { out[k] = 0; for (int r = 0; r < nt; ++r) out[k] += parts[r][k]; }
     o.last_flops_per_sample = fl[0]; o.last_leaves = lv[0];
+}
+
+// All entries of one call on the persistent pool; `out` is [n_entries][bsize].
+static void eval_entries_pooled(Oracle& o, int n_entries, const int32_t* ids, double t_i, double t_w, double t_f, int corr_idx,
+                                const uint32_t* sobol_m, const uint32_t* sobol_x0, uint64_t start, uint64_t count,
+                                uint64_t N_total, cplx* out) {
+    const int nt = std::max(1, o.n_threads);
+    if (!o.pool || (int)o.pool->th.size() != nt) { delete o.pool; o.pool = new Pool(nt); }
+    std::vector<size_t> moff(n_entries), xoff(n_entries);
+    size_t mo = 0, xo = 0;
+    for (int i = 0; i < n_entries; ++i) { moff[i] = mo; xoff[i] = xo; mo += (size_t)2 * o.entries[ids[i]].order * 32; xo += 2 * o.entries[ids[i]].order; }
+    std::vector<cplx> parts((size_t)nt * n_entries * o.bsize, cplx(0));
+    std::vector<double> fl((size_t)nt * n_entries, 0), lv((size_t)nt * n_entries, 0);
+    std::vector<char> bad(nt, 0);
+    const uint64_t epoch = o.cache_epoch;
+    o.pool->run([&](int r) {
+        Pool::Cache& c = o.pool->cache[r];
+        if (c.epoch != epoch) { c.ev.clear(); c.epoch = epoch; }
+        uint64_t s, n;
+        rank_sub_range(count, nt, r, &s, &n);
+        for (int i = 0; i < n_entries; ++i) {
+            const Entry& e = o.entries[ids[i]];
+            if (e.order == 0) continue;   // exact entries: evaluated once by the caller below
+            std::unique_ptr<Evaluator>& ev = c.ev[std::make_pair((int)ids[i], corr_idx)];
+            if (!ev) ev.reset(new Evaluator(o, e.mode, e.order, e.n_pts_after, t_i, t_w, t_f, corr_idx));
+            ev->offdiag_error = false;
+            eval_entry_range_quiet(o, e, t_i, t_w, t_f, corr_idx, sobol_m + moff[i], sobol_x0 + xoff[i], start + s, n, N_total,
+                                   parts.data() + ((size_t)r * n_entries + i) * o.bsize, &fl[(size_t)r * n_entries + i],
+                                   &lv[(size_t)r * n_entries + i], ev.get());
+            if (ev->offdiag_error) bad[r] = 1;
+        }
+    });
+    for (int i = 0; i < n_entries; ++i) {
+        const Entry& e = o.entries[ids[i]];
+        cplx* dst = out + (size_t)i * o.bsize;
+        if (e.order == 0) {
+            eval_entry_range(o, e, t_i, t_w, t_f, corr_idx, sobol_m + moff[i], sobol_x0 + xoff[i], start, count, N_total, dst,
+                             &o.last_flops_per_sample, &o.last_leaves);
+            continue;
+        }
+        for (int k = 0; k < o.bsize; ++k) {
+            cplx v = 0;
+            for (int r = 0; r < nt; ++r) v += parts[((size_t)r * n_entries + i) * o.bsize + k];
+            dst[k] = v;
+        }
+        o.last_flops_per_sample = fl[i]; o.last_leaves = lv[i];
+    }
+    for (int r = 0; r < nt; ++r) if (bad[r]) o.err = "block off-diagonal contribution (src/topology_eval.jl:462)";
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -696,9 +820,11 @@ void qo_rank_sub_range(uint64_t N, int n_ranks, int rank, uint64_t* start, uint6
 }
 
 Oracle* qo_create() { return new Oracle(); }
-void qo_destroy(Oracle* o) { delete o; }
+void qo_destroy(Oracle* o) { delete o->pool; delete o; }
 const char* qo_last_error(Oracle* o) { return o->err.c_str(); }
 void qo_set_threads(Oracle* o, int n) { o->n_threads = n; }
+// 1 (default): persistent worker pool with cached evaluators; 0: one std::thread per (entry, call)
+void qo_set_pool(Oracle* o, int on) { o->use_pool = on; }
 
 // Model: sectors, P0 energies (E + lambda0 per state), operators as sector-block matrices,
 // interaction pairs (operator_i, operator_f, Delta table), correlator operator pairs (A, B).
@@ -707,6 +833,7 @@ int qo_set_model(Oracle* o, int S, const int32_t* dims, const double* energies, 
                  const int32_t* op_target, const int64_t* op_mat_off, const double* op_pool,
                  int n_pairs, const int32_t* pair_op_i, const int32_t* pair_op_f,
                  const int32_t* pair_table, int n_corr, const int32_t* corr_A, const int32_t* corr_B) {
+    ++o->cache_epoch;
     o->S = S;
     o->dim.assign(dims, dims + S);
     o->boff.assign(S, 0);
@@ -775,6 +902,7 @@ int qo_get_P(Oracle* o, int first, int count, double* data) {
 
 int qo_set_topologies(Oracle* o, int entry_id, int mode, int order, int n_pts_after, int n_top,
                       const int32_t* pairs, const int32_t* parity) {
+    ++o->cache_epoch;
     if ((int)o->entries.size() <= entry_id) o->entries.resize(entry_id + 1);
     Entry& e = o->entries[entry_id];
     e.mode = mode; e.order = order; e.n_pts_after = n_pts_after;
@@ -799,6 +927,12 @@ int qo_eval(Oracle* o, double t_i, double t_w, double t_f, int corr_idx, int n_e
     o->err.clear();
     size_t moff = 0, xoff = 0;
     std::vector<cplx> buf(o->bsize);
+    if (o->use_pool && o->n_threads > 1 && count >= (uint64_t)o->n_threads * 4) {
+        std::vector<cplx> res((size_t)n_entries * o->bsize);
+        eval_entries_pooled(*o, n_entries, entry_ids, t_i, t_w, t_f, corr_idx, sobol_m, sobol_x0, start, count, N_total, res.data());
+        for (size_t k = 0; k < res.size(); ++k) { out[2 * k] = res[k].real(); out[2 * k + 1] = res[k].imag(); }
+        return o->err.empty() ? 0 : 4;
+    }
     for (int i = 0; i < n_entries; ++i) {
         const Entry& e = o->entries[entry_ids[i]];
         int d = 2 * e.order;

@@ -16,6 +16,15 @@ def relerr(a, b):
     return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
 
 
+def relerr_elem(a, b, floor=1e-3):
+    """Element-wise relative error: every component is compared with its OWN magnitude (components below
+    `floor` times the largest one are compared with that floor), so that small sectors — e.g. the doubly
+    occupied one of the Anderson model, 2 % of the largest — are held to the same 1e-10 as the large ones."""
+    a, b = np.asarray(a), np.asarray(b)
+    scale = np.maximum(np.abs(b), floor * max(np.abs(b).max(), 1e-300))
+    return float((np.abs(a - b) / scale).max())
+
+
 def test_sobol_points_bit_exact(gpu_ctx, qlib, oracle_lib):
     for D in (1, 5, 12):
         m = qlib.sobol_direction_numbers(D)
@@ -495,3 +504,85 @@ def test_two_site_dimer_physics(gpu_ctx, qlib, oracle_lib, spline):
     ppgf.normalize(ex)
     rho = np.array([d[0, 0].real for d in ppgf.density_matrix(ex)])
     assert np.abs(rho - models.two_site_dimer_exact_rho()).max() < 1e-4
+
+
+@pytest.mark.parametrize("arith", ["real", "complex"])
+@pytest.mark.parametrize("order", [5, 6])
+def test_high_order_entries_vs_oracle(gpu_ctx, qlib, oracle_lib, monkeypatch, arith, order):
+    """BASELINE.json configs[4] (stress, orders up to 6): EVERY bold entry of order 5 (9 entries) and order 6
+    (11 entries) against the oracle at N = 2^6, entry by entry and element-wise, in real and in complex
+    arithmetic.  These orders run through their own record format / kernel instantiation."""
+    import os
+    if arith == "complex":
+        monkeypatch.setenv("QIW_FORCE_COMPLEX", "1")
+    ex, grid, f = models.anderson(n_tau=40)
+    rng = np.random.default_rng(50 + order)
+    ex.P = ex.P * (1.0 + 0.05 * rng.random(ex.P.shape))
+    pl = gpu_ctx.set_expansion(ex)
+    o = oracle_lib.Oracle(pl, ex.P, threads=os.cpu_count() or 1)
+    ids = []
+    for k in range(1, 2 * order):
+        pr, pa = qlib.topologies(order, k)
+        assert len(pa) > 0
+        gpu_ctx.set_topologies(len(ids), qlib.MODE_BOLD, order, k, pr, pa)
+        o.set_topologies(len(ids), qlib.MODE_BOLD, order, k, pr, pa)
+        ids.append(len(ids))
+    assert len(ids) == 2 * order - 1
+    tau = grid.tau
+    N = 2 ** 6
+    got = gpu_ctx.eval(0.0, tau[23], tau[24], ids, N)
+    ref = o.eval(0.0, tau[23], tau[24], ids, N)
+    for j in ids:
+        assert relerr_elem(got[j], ref[j]) < RTOL, (order, j + 1, relerr_elem(got[j], ref[j]))
+
+
+def test_c1_full_size_vs_oracle(gpu_ctx, qlib, oracle_lib):
+    """BASELINE.json configs[0] at FULL size (README.md:34-158: n_tau = 200, orders 0:4, N = 2^10): P(tau) for
+    all 200 grid points and 4 sectors, Z, rho_imp and G(tau) (correlator_2p, orders 0:3) of the CUDA path
+    against the oracle's own drivers, element-wise, tolerance 1e-10."""
+    import os
+    from qinchworm_b200 import ppgf
+    from qinchworm_b200.expansion import add_corr_operators
+    from qinchworm_b200.inchworm import Solver, correlator_2p, inchworm
+    threads = os.cpu_count() or 1
+    ex, grid, f = models.anderson(n_tau=200)
+    ref = oracle_lib.inchworm(ex.flatten(), ex.P, range(0, 5), range(0, 5), 2 ** 10, threads=threads)["P"]
+    solver = Solver(ex, ctx=gpu_ctx)
+    inchworm(ex, grid, range(0, 5), range(0, 5), 2 ** 10, solver=solver)
+    assert relerr_elem(ex.P, ref) < RTOL, relerr_elem(ex.P, ref)
+    Z, Zref = ppgf.partition_function(ex), (1j * ref[-1]).sum()
+    assert abs(Z - Zref) < RTOL * abs(Zref)
+    rho = np.array([d[0, 0] for d in ppgf.density_matrix(ex)])
+    rho_ref = 1j * ref[-1] / Zref
+    assert relerr_elem(rho, rho_ref) < RTOL
+    # G(tau) on the converged P, both sides starting from the SAME table (the oracle's)
+    ex.P[:] = ref
+    add_corr_operators(ex, (f.c("up"), f.c_dag("up")))
+    g = correlator_2p(ex, grid, range(0, 4), 2 ** 10, solver=solver)[0]
+    g_ref = oracle_lib.correlator_2p(ex.flatten(), ref, range(0, 4), 2 ** 10, threads=threads)
+    assert relerr_elem(g, g_ref) < RTOL, relerr_elem(g, g_ref)
+
+
+def test_c4_order4_bold_step_vs_oracle(gpu_ctx, qlib, oracle_lib):
+    """BASELINE.json configs[3] (two-band e_g model, 9 sectors with blocks 1/2/4, 16 pairs) at ORDER 4: one bold step
+    with all seven order-4 entries (21.3 M configurations per sample-set) against the oracle at N = 2^4."""
+    import os
+    ex, grid, f = models.two_band(n_tau=10)
+    rng = np.random.default_rng(44)
+    ex.P = ex.P * (1.0 + 0.05 * rng.random(ex.P.shape))
+    pl = gpu_ctx.set_expansion(ex)
+    o = oracle_lib.Oracle(pl, ex.P, threads=os.cpu_count() or 1)
+    ids = []
+    for k in range(1, 8):
+        pr, pa = qlib.topologies(4, k)
+        gpu_ctx.set_topologies(len(ids), qlib.MODE_BOLD, 4, k, pr, pa)
+        o.set_topologies(len(ids), qlib.MODE_BOLD, 4, k, pr, pa)
+        ids.append(len(ids))
+    tau = grid.tau
+    N = 2 ** 4
+    got = gpu_ctx.eval(0.0, tau[5], tau[6], ids, N)
+    ref = o.eval(0.0, tau[5], tau[6], ids, N)
+    for j in ids:
+        assert relerr(got[j], ref[j]) < RTOL, (j + 1, relerr(got[j], ref[j]))
+    tot, tot_ref = got.sum(axis=0), ref.sum(axis=0)
+    assert relerr_elem(tot, tot_ref) < RTOL

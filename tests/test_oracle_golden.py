@@ -247,7 +247,7 @@ def test_block_basis_rotation_invariance(oracle_lib):
     assert np.abs(vals[0] - vals[1]).max() < 1e-12
 
 
-@pytest.mark.parametrize("name", ["two_level_mixed", "three_orbital"])
+@pytest.mark.parametrize("name", ["two_level_mixed", "three_orbital", "two_band"])
 def test_block_brute_force_fock_space(oracle_lib, name):
     """d_s > 1 is unpinned at the reference level: check the oracle's sector-block DFS against
     a brute-force evaluation of the naive formula (src/configuration.jl:402-411,492-520) in the FULL Fock
@@ -260,9 +260,13 @@ def test_block_brute_force_fock_space(oracle_lib, name):
     if name == "two_level_mixed":
         ex, grid, f = models.two_level_mixed(n_tau=12, theta=0.6)
         cases = ((1, 1), (2, 1), (2, 3), (3, 2))
-    else:   # 3x3 sector blocks, 10 pairs: orders <= 2 keep the brute force (pairs^order assignments) short
+    elif name == "three_orbital":   # 3x3 sector blocks, 10 pairs: orders <= 2 keep the brute force (pairs^order assignments) short
         ex, grid, f = models.three_orbital(n_tau=12)
         cases = ((1, 1), (2, 1), (2, 3))
+    else:   # the C4 model itself (bench/two_band_eg_model_discrete_bath): 9 sectors, blocks 1/2/4, 16 pairs
+        ex, grid, f = models.two_band(n_tau=12)
+        assert sorted(ex.dims) == [1, 1, 1, 1, 2, 2, 2, 2, 4] and len(ex.pairs) == 16
+        cases = ((1, 1), (2, 1), (2, 2), (2, 3))
     rng = np.random.default_rng(4)
     ex.P = ex.P * (1.0 + 0.1 * rng.random(ex.P.shape))
     pl = ex.flatten()
@@ -299,6 +303,7 @@ def test_block_brute_force_fock_space(oracle_lib, name):
             tpos[p] = times[v]
         total = np.zeros((dimF, dimF), dtype=complex)
         I = np.eye(dimF)
+        iPs = {p: iP_full(tpos[p], tpos[p - 1]) for p in range(2, n_nodes + 1)}
         for top, par in zip(pairs, parity):
             for assign in itertools.product(range(len(ex.pairs)), repeat=order):
                 ops = {p: I for p in range(1, n_nodes + 1)}
@@ -310,7 +315,7 @@ def test_block_brute_force_fock_space(oracle_lib, name):
                     w *= delta(assign[a], tpos[p_tail], tpos[p_head])
                 chain = ops[1]
                 for p in range(2, n_nodes + 1):
-                    chain = ops[p] @ iP_full(tpos[p], tpos[p - 1]) @ chain
+                    chain = ops[p] @ iPs[p] @ chain
                 total += (-1j) * par * (-1) ** order * w * chain
         got = ex.pack_blocks([u.conj().T @ total[np.ix_(sp, sp)] @ u for sp, u in zip(ed.subspaces, ed.unitaries)])
         assert np.abs(got - ref).max() < 1e-12 * max(np.abs(ref).max(), 1e-300), (order, k)
