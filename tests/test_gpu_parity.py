@@ -552,7 +552,7 @@ def test_c1_full_size_vs_oracle(gpu_ctx, qlib, oracle_lib):
     assert relerr_elem(ex.P, ref) < RTOL, relerr_elem(ex.P, ref)
     Z, Zref = ppgf.partition_function(ex), (1j * ref[-1]).sum()
     assert abs(Z - Zref) < RTOL * abs(Zref)
-    rho = np.array([d[0, 0] for d in ppgf.density_matrix(ex)])
+    rho = np.array([d[0, 0] for d in ppgf.density_matrix(ex)]) / Z     # rho_imp = i P(beta) / Z (README.md:150-158)
     rho_ref = 1j * ref[-1] / Zref
     assert relerr_elem(rho, rho_ref) < RTOL
     # G(tau) on the converged P, both sides starting from the SAME table (the oracle's)
