@@ -151,10 +151,18 @@ int qiw_entry_program(qiw_context* ctx, int32_t entry_id, int64_t* n_words, uint
  *   rec2[n_leaves][L2 + 1], segdef[nSeg][seg_stride] */
 int qiw_entry_records(qiw_context* ctx, int32_t entry_id, int32_t* info, uint32_t* rec2, uint16_t* segdef);
 
-/* Paired form of the same records (csrc/qiw_host.hpp EntryProgram::rec_pair / rec_left) — what the summing walk
- * of the step kernel executes.  info[4] = n_pairs, words per pair record (2 + 2K + order), n_left, words per
- * leftover record (L2 + 1).  Call with NULL arrays to get the sizes. */
-int qiw_entry_pair_records(qiw_context* ctx, int32_t entry_id, int32_t* info, uint32_t* rec_pair, uint32_t* rec_left);
+/* Lane program of a compiled entry of a 1x1-block model — what the step kernel executes with lane = sample
+ * (layout: csrc/qiw_host.hpp EntryProgram::lane_*).  Configurations sharing all pair-interaction operands and the
+ * initial sector form groups, cut into records of M = 4, 2 or 1 members:
+ *     record value = prod(T[Delta slots]) * sum_members prod(T[segment slots of the member])
+ * with every member's coefficient folded into its first segment product.  Call with NULL arrays to get the sizes.
+ *   info[8]             : n_sections, n_items, nSegL, seg_stride, K, order, first slot of the segment table, cost
+ *   sections[n_sections][4] : initial sector, M, number of records, first item
+ *   items[n_items]      : per record `order` Delta slots, then M * K segment slots, padded to a multiple of 4
+ *   segdef[nSegL][seg_stride] : propagator slots of every segment product (0xFFFF = unused)
+ *   seg_coef[nSegL]     : index of the coefficient folded into the product (0xFFFF = none) */
+int qiw_entry_lane_program(qiw_context* ctx, int32_t entry_id, int32_t* info, int32_t* sections, uint32_t* items,
+                           uint16_t* segdef, uint16_t* seg_coef);
 
 /* Walk units of a compiled entry of a sector-block model (blocks larger than 1x1) — what block_walk_kernel
  * replays: the pruned configuration trees of src/topology_eval.jl:454-556 cut into sub-trees of bounded cost,
@@ -225,7 +233,8 @@ int qiw_last_device_ms(qiw_context* ctx, double* ms);
 int qiw_launch_count(qiw_context* ctx, int64_t* n);
 
 /* Per-kernel device timing (CUDA events on the launching stream around every launch).  Classes:
- * 0 step kernel in complex arithmetic, 1 step kernel in real arithmetic (1x1-block models), 4 reduction,
+ * 0 step kernel in complex arithmetic, 1 step kernel in real arithmetic (1x1-block models), 2 persistent run kernel
+ * (all bold steps of qiw_inchworm_run in one launch), 4 reduction,
  * 5 per-step state update, 6 NCCL all-reduce, 7 step kernel for sector blocks larger than 1x1.  Profiling serialises nothing but adds two event records per launch; keep it
  * off for timed runs.  qiw_profile_read synchronises, returns accumulated ms and launch counts per
  * class (arrays of QIW_PROFILE_CLASSES) and optionally resets them. */

@@ -27,7 +27,8 @@ for f in os.listdir(tmp):
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
         if m:
-            cur = int(m.group(2)) if m.group(1).endswith("qiw_kernels.cu") else cur
+            if "/csrc/" in m.group(1) or m.group(1).startswith("qiw_"):
+                cur = (os.path.basename(m.group(1)), int(m.group(2)))
             continue
         if re.match(r"\s*/\*[0-9a-f]{4,}\*/", ln):
             lst.append(cur)
@@ -46,8 +47,19 @@ for k, r in enumerate(sass):
     a = agg[ln]
     a[0] += int(r[c_s] or 0); a[1] += int(r[c_i] or 0); a[2] += int(r[c_w] or 0)
 ts, ti = sum(a[0] for a in agg.values()), sum(a[1] for a in agg.values())
-src = open(os.path.join(os.path.dirname(os.path.abspath(lib)), "csrc", "qiw_kernels.cu")).read().splitlines()
+csrc = os.path.join(os.path.dirname(os.path.abspath(lib)), "csrc")
+srcs = {}
+def text_of(ln):
+    if not ln:
+        return "?"
+    f, n = ln
+    if f not in srcs:
+        try:
+            srcs[f] = open(os.path.join(csrc, f)).read().splitlines()
+        except OSError:
+            srcs[f] = []
+    return srcs[f][n - 1].strip()[:110] if 0 < n <= len(srcs[f]) else "?"
 print("samples %d  warp instructions %d" % (ts, ti))
 for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-    text = src[ln - 1].strip()[:110] if ln and ln <= len(src) else "?"
-    print("%5.1f%% samples %5.1f%% inst  smem wavefronts %11d | %4s: %s" % (100 * a[0] / ts, 100 * a[1] / ti, a[2], ln, text))
+    where = "%s:%d" % (ln[0].replace("qiw_", "").replace(".cuh", "").replace(".cu", ""), ln[1]) if ln else "?"
+    print("%5.1f%% samples %5.1f%% inst  smem wavefronts %11d | %12s: %s" % (100 * a[0] / ts, 100 * a[1] / ti, a[2], where, text_of(ln)))

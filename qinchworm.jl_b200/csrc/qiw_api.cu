@@ -20,7 +20,9 @@
 #include "qiw_host.hpp"
 
 namespace qiw {
-cudaError_t launch_scalar_step(bool real_mode, bool pairs, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_scalar_step(bool real_mode, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_scalar_run(bool real_mode, const RunParams& rp, int n_ctas, int threads, size_t smem, cudaStream_t st);
+int scalar_run_max_ctas(bool real_mode, int threads, size_t smem, int n_sm);
 cudaError_t launch_reduce(const DevEntryDyn* dyn, const DevEntry* entries, const double2* partials, int pitch, int S,
                           double t_i, double t_w, double t_f, double2* out, int n_entries, cudaStream_t st);
 cudaError_t launch_finish_step(double2* P, int n_tau, int bsize, const int* diag, int n_diag, double h, int k_f,
@@ -92,8 +94,8 @@ struct DevBuf {
 struct EntryDev {
     EntryProgram prog;
     bool valid = false;
-    DevBuf<uint32_t> records, records_pair, records_left;
-    DevBuf<uint16_t> segdef;
+    DevBuf<uint4> lane_items;            // scalar models: records of the lane program (+ padding for the prefetch)
+    DevBuf<uint4> lane_segdef4;          // packed definitions of the segment-product table
     bool imag_coefs = false;     // every folded coefficient is purely imaginary (real-mode precondition)
     DevBuf<uint64_t> words;      // block models: tree word stream
     DevBuf<uint4> xwords;        // block models: expanded words of the real-arithmetic walker
@@ -113,8 +115,8 @@ struct Plan {   // launch plan of one qiw_eval call shape, cached
     uint64_t count = 0;
     bool explicit_mode = false;
     struct Group {
-        int maxl; int item0, n_items; int max_slots; int max_dslots; int max_coefs; int max_segdef; int max_nodes1 = 2;
-        size_t smem[2]; int spb[2];   // [0] complex arithmetic, [1] real arithmetic
+        int item0, n_items; int max_slots; int max_dslots; int max_nodes1 = 2;
+        size_t smem[2]; int spb[2], warps[2], aux_off[2], red_off[2];   // [0] complex arithmetic, [1] real arithmetic
     };
     std::vector<Group> groups;
     std::vector<WorkItem> items;
@@ -139,6 +141,24 @@ struct Plan {   // launch plan of one qiw_eval call shape, cached
     std::vector<uint32_t> h_sobol;
     bool default_sobol_resident = false;
     DevBuf<WorkItem> d_items;
+    DevBuf<uint32_t> d_chunk_off;          // scalar models: [chunks + 1] first run of every chunk of every CTA job
+    DevBuf<LaneRun> d_runs;                // runs of records (equal shape and initial sector) the chunks consist of
+    // persistent run kernel (qiw_inchworm_run on small steps): one job per CTA for the whole run
+    struct RunPlan {
+        int state = 0;                     // 0 = not built, 1 = usable, -1 = this plan does not fit the run kernel
+        int real = -1;
+        int n_jobs = 0, n_ctas = 0, threads = 0;
+        size_t smem = 0;
+        int ok_off = 0, pw_off = 0, red_off = 0, ds_off = 0, P_off = 0, D_off = 0, out_off = 0, rows_staged = 0;
+        bool by_sm = false; int ctas_per_sm = 1;
+        DevBuf<RunJob> d_jobs;
+        DevBuf<int> d_entry_job0, d_cta_job0;
+        DevBuf<WorkItem> d_items;
+        DevBuf<uint32_t> d_chunk_off;
+        DevBuf<LaneRun> d_runs;
+        DevBuf<double2> d_partials;
+        DevBuf<unsigned int> d_barrier;
+    } run;
 };
 }  // namespace
 
@@ -296,7 +316,7 @@ int qiw_destroy(qiw_context* ctx) {
     ctx->dPool.release(); ctx->dPoolRe.release(); ctx->dScratch.release(); ctx->dWordsPtr.release(); ctx->dTreeOffPtr.release(); ctx->dXWordsPtr.release(); ctx->dXTreeOffPtr.release(); ctx->dNTrees.release();
     for (auto& t : ctx->tables) { t.y.release(); t.M.release(); }
     for (auto& e : ctx->entries)
-        if (e) { e->records.release(); e->records_pair.release(); e->records_left.release(); e->segdef.release(); e->words.release(); e->xwords.release(); e->xtree_off.release(); e->tree_off.release(); e->coefs.release(); e->dslots.release(); e->sobol.release(); }
+        if (e) { e->lane_items.release(); e->lane_segdef4.release(); e->words.release(); e->xwords.release(); e->xtree_off.release(); e->tree_off.release(); e->coefs.release(); e->dslots.release(); e->sobol.release(); }
     for (auto& pl : ctx->plans) release_plan(*pl);
     ctx->plans.clear();
     if (ctx->hOut) cudaFreeHost(ctx->hOut);
@@ -620,56 +640,20 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
         if (rc) return fail(ctx, rc, "qiw_set_topologies: " + err);
     }
     if (ctx->no_device) { ed.valid = true; return QIW_OK; }
-    if (ctx->model.scalar) {   // configuration records, transposed into groups of 32 so that lane l of a warp reads record
-        // 32 g + l with coalesced loads; the last group is padded with null records (zero coefficient)
-        const int L = pr.L2, RL = pr.L2 + 1;
-        const int64_t nl = pr.n_leaves, ng = (nl + 31) / 32;
-        std::vector<uint32_t> rec((size_t)std::max<int64_t>(ng, 1) * (L + 1) * 32, 0u);
-        for (int64_t g = 0; g < ng; ++g)
-            for (int lane = 0; lane < 32; ++lane) {
-                const int64_t leaf = g * 32 + lane;
-                uint32_t* dst = rec.data() + (size_t)g * (L + 1) * 32 + lane;
-                if (leaf < nl) {
-                    const uint32_t* src = pr.rec2.data() + (size_t)leaf * RL;
-                    for (int q = 0; q <= L; ++q) dst[(size_t)q * 32] = src[q];
-                } else {
-                    const uint32_t s_last = nl ? (pr.rec2[(size_t)(nl - 1) * RL] >> 16) : 0u;
-                    dst[0] = (uint32_t)pr.coefs.size() | (s_last << 16);   // index of the appended zero coefficient
-                }
-            }
-        CK(ed.records.upload(rec.data(), rec.size(), ctx->stream));
-        {   // the same configurations as pairs + leftovers (what the summing walk executes), transposed alike
-            auto transpose = [&](const std::vector<uint32_t>& src, int64_t n_rec, int RLs, bool pair, DevBuf<uint32_t>& dst_buf) -> cudaError_t {
-                const int64_t ngs = (n_rec + 31) / 32;
-                std::vector<uint32_t> t((size_t)std::max<int64_t>(ngs, 1) * RLs * 32, 0u);
-                for (int64_t g = 0; g < ngs; ++g)
-                    for (int lane = 0; lane < 32; ++lane) {
-                        const int64_t r = g * 32 + lane;
-                        uint32_t* dst = t.data() + (size_t)g * RLs * 32 + lane;
-                        if (r < n_rec) {
-                            for (int q = 0; q < RLs; ++q) dst[(size_t)q * 32] = src[(size_t)r * RLs + q];
-                        } else {   // padding lanes: zero coefficient(s), sector of the last record
-                            const uint32_t s_last = n_rec ? (src[(size_t)(n_rec - 1) * RLs] >> 16) : 0u;
-                            dst[0] = (uint32_t)pr.coefs.size() | (s_last << 16);
-                            if (pair) dst[32] = (uint32_t)pr.coefs.size();
-                        }
-                    }
-                return dst_buf.upload(t.data(), t.size(), ctx->stream);
-            };
-            CK(transpose(pr.rec_pair, pr.n_pairs, 2 + 2 * pr.K + pr.order, true, ed.records_pair));
-            CK(transpose(pr.rec_left, pr.n_left, pr.L2 + 1, false, ed.records_left));
+    if (ctx->model.scalar) {   // the lane program: records (padded by 8 words: the walk fetches one record ahead) and
+        // the segment-product table's definitions
+        std::vector<uint4> items(pr.lane_items.size() / 4 + 8, make_uint4(0u, 0u, 0u, 0u));
+        memcpy(items.data(), pr.lane_items.data(), pr.lane_items.size() * sizeof(uint32_t));
+        CK(ed.lane_items.upload(items.data(), items.size(), ctx->stream));
+        const int st = pr.seg_stride, nw4 = st > 7 ? 2 : 1;
+        std::vector<uint16_t> defs((size_t)std::max(pr.nSegL, 1) * nw4 * 8, (uint16_t)0xFFFF);
+        for (int j = 0; j < pr.nSegL; ++j) {
+            uint16_t* d = defs.data() + (size_t)j * nw4 * 8;
+            d[0] = pr.lane_seg_coef[j];
+            for (int i = 0; i < st; ++i) d[1 + i] = pr.lane_segdef[(size_t)j * st + i];
         }
-        {   // segment definitions transposed into groups of 32 entries; padding -> the constant-one slot
-            const int nsg = (pr.nSeg + 31) / 32, st = pr.seg_stride;
-            const uint16_t one = (uint16_t)(pr.nP + (int)pr.dslots.size() + pr.nSeg);
-            std::vector<uint16_t> sd((size_t)std::max(nsg, 1) * st * 32, one);
-            for (int j = 0; j < pr.nSeg; ++j)
-                for (int i = 0; i < st; ++i) {
-                    const uint16_t q = pr.segdef[(size_t)j * st + i];
-                    sd[((size_t)(j / 32) * st + i) * 32 + (j % 32)] = (q == 0xFFFFu) ? one : q;
-                }
-            CK(ed.segdef.upload(sd.data(), sd.size(), ctx->stream));
-        }
+        CK(ed.lane_segdef4.upload(reinterpret_cast<const uint4*>(defs.data()), defs.size() / 8, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));   // the staging vectors go out of scope
     }
     if (!ctx->model.scalar) {
         CK(ed.words.upload(pr.words.data(), pr.words.size(), ctx->stream));
@@ -753,14 +737,24 @@ int qiw_entry_walk_units(qiw_context* ctx, int32_t id, int64_t* n_units, int64_t
     return QIW_OK;
 }
 
-int qiw_entry_pair_records(qiw_context* ctx, int32_t id, int32_t* info, uint32_t* rec_pair, uint32_t* rec_left) {
+int qiw_entry_lane_program(qiw_context* ctx, int32_t id, int32_t* info, int32_t* sections, uint32_t* items, uint16_t* segdef,
+                           uint16_t* seg_coef) {
     if (!ctx || id < 0 || id >= (int)ctx->entries.size() || !ctx->entries[id] || !ctx->entries[id]->valid)
-        return fail(ctx, QIW_ERR_BAD_ARG, "qiw_entry_pair_records: unknown entry");
+        return fail(ctx, QIW_ERR_BAD_ARG, "qiw_entry_lane_program: unknown entry");
     const EntryProgram& p = ctx->entries[id]->prog;
-    if (!p.scalar) return fail(ctx, QIW_ERR_UNSUPPORTED, "qiw_entry_pair_records: only 1x1-block models have configuration records");
-    if (info) { info[0] = (int32_t)p.n_pairs; info[1] = 2 + 2 * p.K + p.order; info[2] = (int32_t)p.n_left; info[3] = p.L2 + 1; }
-    if (rec_pair) memcpy(rec_pair, p.rec_pair.data(), p.rec_pair.size() * sizeof(uint32_t));
-    if (rec_left) memcpy(rec_left, p.rec_left.data(), p.rec_left.size() * sizeof(uint32_t));
+    if (!p.scalar) return fail(ctx, QIW_ERR_UNSUPPORTED, "qiw_entry_lane_program: only 1x1-block models have a lane program");
+    if (info) {
+        info[0] = (int32_t)p.lane_sections.size(); info[1] = (int32_t)p.lane_items.size(); info[2] = p.nSegL; info[3] = p.seg_stride;
+        info[4] = p.K; info[5] = p.order; info[6] = p.nP + (int32_t)p.dslots.size(); info[7] = (int32_t)p.lane_cost;
+    }
+    if (sections)
+        for (size_t k = 0; k < p.lane_sections.size(); ++k) {
+            const auto& sc = p.lane_sections[k];
+            sections[4 * k] = sc.s_i; sections[4 * k + 1] = sc.M; sections[4 * k + 2] = (int32_t)sc.n_rec; sections[4 * k + 3] = (int32_t)(sc.chunk0 * 4u);
+        }
+    if (items) memcpy(items, p.lane_items.data(), p.lane_items.size() * sizeof(uint32_t));
+    if (segdef) memcpy(segdef, p.lane_segdef.data(), (size_t)p.nSegL * p.seg_stride * sizeof(uint16_t));
+    if (seg_coef) memcpy(seg_coef, p.lane_seg_coef.data(), (size_t)p.nSegL * sizeof(uint16_t));
     return QIW_OK;
 }
 
@@ -795,13 +789,12 @@ static int sync_static_tables(qiw_context* ctx) {
             d.d_after = (p.mode == 0) ? p.D : p.n_pts_after;
             d.d_before = p.D - d.d_after;
             d.nP = p.nP; d.nD = (int)p.dslots.size();
-            d.L2 = p.L2; d.n_leaves = (int)p.n_leaves; d.n_groups = (int)((p.n_leaves + 31) / 32); d.n_coefs = (int)p.coefs.size();
-            d.nSeg = p.nSeg; d.seg_stride = p.seg_stride; d.segdef = ed.segdef.p;
-            d.records_pair = ed.records_pair.p; d.records_left = ed.records_left.p; d.K = p.K;
-            d.n_groups_pair = (int)((p.n_pairs + 31) / 32); d.n_groups_left = (int)((p.n_left + 31) / 32);
+            d.n_coefs = (int)p.coefs.size();
+            d.K = p.K; d.nSegL = p.nSegL; d.seg_stride = p.seg_stride;
+            d.lane_items = ed.lane_items.p; d.lane_segdef4 = ed.lane_segdef4.p;
             d.exact = (p.order == 0);
             for (int k = 0; k <= kDevMaxNodes; ++k) d.pos_src[k] = p.pos_src[k];
-            d.records = ed.records.p; d.coefs = ed.coefs.p; d.dslots = ed.dslots.p;
+            d.coefs = ed.coefs.p; d.dslots = ed.dslots.p;
         }
         CK(ctx->dEntries.upload(de.data(), de.size(), ctx->stream));
         if (!ctx->model.scalar) {
@@ -830,7 +823,9 @@ static int sync_static_tables(qiw_context* ctx) {
 
 static void release_plan(Plan& pl) {
     pl.d_items.release(); pl.d_sobol.release(); pl.d_ucache.release(); pl.d_bounds.release();
-    pl.d_dyn.release(); pl.d_partials.release(); pl.d_out.release();
+    pl.d_dyn.release(); pl.d_partials.release(); pl.d_out.release(); pl.d_chunk_off.release(); pl.d_runs.release();
+    pl.run.d_jobs.release(); pl.run.d_entry_job0.release(); pl.run.d_cta_job0.release(); pl.run.d_items.release(); pl.run.d_chunk_off.release();
+    pl.run.d_runs.release(); pl.run.d_partials.release(); pl.run.d_barrier.release();
 }
 
 // Real arithmetic is exact when every operand is (real number) * i: the stored P rows and Delta tables
@@ -843,6 +838,30 @@ static bool real_mode_possible(qiw_context* ctx, int n_entries, const int32_t* i
     for (uint8_t c : ctx->p_row_complex) if (c) return false;
     for (int i = 0; i < n_entries; ++i) if (!ctx->entries[ids[i]]->imag_coefs) return false;
     return true;
+}
+
+// Cuts an entry's lane program into `n_chunks` chunks of equal cumulative cost and appends them: one entry of
+// `chunk_off` per chunk (the caller terminates the array), a chunk being a list of runs — one per section it touches.
+static void append_entry_chunks(const EntryProgram& p, int n_chunks, std::vector<uint32_t>& chunk_off, std::vector<LaneRun>& runs) {
+    size_t si = 0; uint32_t r_in = 0;   // cursor: section, record inside it
+    int64_t done = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        chunk_off.push_back((uint32_t)runs.size());
+        const int64_t target = (int64_t)((double)p.lane_cost * (double)(c + 1) / (double)n_chunks + 0.5);
+        const bool last = (c + 1 == n_chunks);
+        while (si < p.lane_sections.size() && (last || done < target)) {
+            const auto& sec = p.lane_sections[si];
+            uint32_t take = sec.n_rec - r_in;
+            if (!last) take = (uint32_t)std::min<int64_t>(take, std::max<int64_t>(1, (target - done + sec.cost - 1) / sec.cost));
+            const int ni = lane_record_items(p.order, p.K, sec.M) / 4;
+            const uint32_t mc = sec.M == 1 ? 0u : (sec.M == 2 ? 1u : 2u);
+            runs.push_back(make_uint4(sec.chunk0 + r_in * (uint32_t)ni, take, (uint32_t)sec.s_i,
+                                      (uint32_t)(p.order * 16 + (p.K - 1) * 4) + mc));
+            done += (int64_t)take * sec.cost;
+            r_in += take;
+            if (r_in == sec.n_rec) { ++si; r_in = 0; }
+        }
+    }
 }
 
 // Splits every entry's trees into chunks of similar cost and groups chunks into CTA jobs.
@@ -858,7 +877,6 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
     std::unique_ptr<Plan> pl(new Plan());
     pl->ids.assign(ids, ids + n_entries);
     pl->count = count; pl->explicit_mode = explicit_mode;
-    const int W = ctx->warps;
     const int S = ctx->model.S;
     int ndev_sm = 148;
     cudaDeviceGetAttribute(&ndev_sm, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -928,7 +946,7 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         }
         CK(pl->d_bounds.upload(bounds.data(), bounds.size(), ctx->stream));
         Plan::Group g;
-        g.maxl = 0; g.item0 = 0; g.max_slots = 1; g.max_dslots = 1; g.max_coefs = 1; g.max_segdef = 1;
+        g.item0 = 0; g.max_slots = 1; g.max_dslots = 1;
         g.n_items = (int)pl->items.size();
         g.smem[0] = g.smem[1] = smem_of(Wn);
         g.spb[0] = g.spb[1] = 32;
@@ -948,7 +966,7 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         const int split = explicit_mode ? 1 : (int)std::max<double>(1.0, std::ceil(4.0 * ndev_sm / ((double)n_entries * (double)n_sb_max)));
         pl->item0.resize(n_entries); pl->n_items.resize(n_entries);
         Plan::Group g;
-        g.maxl = 0; g.item0 = 0; g.max_slots = 1; g.max_dslots = 1;
+        g.item0 = 0; g.max_slots = 1; g.max_dslots = 1;
         size_t spt = 1;
         for (int i = 0; i < n_entries; ++i) {
             const EntryProgram& p = ctx->entries[ids[i]]->prog;
@@ -973,91 +991,108 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         pl->scratch_per_thread = spt;
     } else {
     // Chunking.  A CTA owns (entry, 32 samples) and builds that sample block's tables once, so the
-    // fewer CTAs share an entry the less set-up work is repeated: by default an entry's
-    // configurations are split into exactly W chunks (one per warp, one CTA job).  Only entries
-    // whose chunks would exceed `chunk_cap` configurations are split further (their set-up cost is
-    // then amortised anyway), and when the call is too small to fill the machine the cap is
-    // lowered to expose more CTAs.
-    double max_groups = 1;
+    // fewer CTAs share an entry the less set-up work is repeated: by default an entry's lane program
+    // is split into exactly W chunks of equal cost (one per warp, one CTA job).  Only entries whose chunks
+    // would exceed `chunk_cap` operand loads are split further (their set-up cost is then amortised
+    // anyway), and when the call is too small to fill the machine the cap is lowered to expose more CTAs.
+    double max_cost = 1;
     uint64_t n_sb_all = 1;
+    int max_pd = 1;
     Plan::Group g;
-    g.maxl = 1; g.item0 = 0; g.max_slots = 1; g.max_dslots = 1; g.max_coefs = 1; g.max_segdef = 1;
+    g.item0 = 0; g.max_slots = 1; g.max_dslots = 1;
     for (int i = 0; i < n_entries; ++i) {
         const EntryProgram& p = ctx->entries[ids[i]]->prog;
-        max_groups = std::max(max_groups, (double)((p.n_leaves + 31) / 32));
-        g.maxl = std::max(g.maxl, p.L2);
-        g.max_coefs = std::max(g.max_coefs, (int)p.coefs.size());
-        g.max_slots = std::max(g.max_slots, (p.nP + (int)p.dslots.size() + p.nSeg + 1) | 1);
+        max_cost = std::max(max_cost, (double)p.lane_cost);
+        max_pd = std::max(max_pd, p.nP + (int)p.dslots.size());
+        g.max_slots = std::max(g.max_slots, p.nP + (int)p.dslots.size() + p.nSegL);
         g.max_dslots = std::max(g.max_dslots, (int)p.dslots.size());
-        g.max_segdef = std::max(g.max_segdef, p.nSeg * p.seg_stride);
         g.max_nodes1 = std::max(g.max_nodes1, p.n_nodes + 1);
     }
-    // samples per CTA pass and shared memory, for complex (16-byte operands) and real (8-byte) arithmetic:
-    // the largest power of two <= 32 whose tables leave room for two CTAs per SM, else whatever fits
+    // samples per CTA pass, warps per CTA and shared memory, for complex (16-byte operands) and real (8-byte)
+    // arithmetic: 32 samples (one per lane) unless the tables of the largest entry do not fit, then the largest power of
+    // two that does; 24 warps per SM as 3 CTAs of 8, 2 of 12 or 1 of 24, whichever the table size allows (all warps of
+    // a CTA share one table, and the walk needs the warps: its operand loads are latency-bound below ~6 per scheduler)
+    const size_t aux_bytes = (size_t)g.max_nodes1 * 32 * (2 * sizeof(double) + sizeof(int)) + 32 * sizeof(int);
     for (int real = 0; real < 2; ++real) {
         const size_t opsz = real ? sizeof(double) : sizeof(double2);
-        auto smem_of = [&](int spb) {
-            size_t b = (size_t)g.max_slots * spb * opsz;
-            b = (b + 15) & ~(size_t)15;
-            b = std::max(b, (size_t)kDevMaxDim * 32 * sizeof(double));   // the roots alias the start of the table
-            return b + (size_t)S * W * sizeof(double2) + (size_t)g.max_nodes1 * 32 * sizeof(double) +
-                   (size_t)g.max_nodes1 * 32 * (sizeof(double) + sizeof(int)) +
-                   32 * sizeof(int) + (size_t)g.max_dslots * sizeof(int4) +
-                   (size_t)(g.max_coefs + 1) * opsz + 16;
+        auto aux_off_of = [&](int spb) {   // after the propagator / interaction rows and the roots, inside the table if it is long enough
+            size_t lo = std::max((size_t)max_pd * spb * opsz, (size_t)kDevMaxDim * 32 * sizeof(double));
+            size_t tb = (size_t)g.max_slots * spb * opsz;
+            size_t off = std::max(lo, tb > aux_bytes ? tb - aux_bytes : (size_t)0);
+            return (off + 15) & ~(size_t)15;
         };
+        auto red_off_of = [&](int spb) {
+            return (std::max((size_t)g.max_slots * spb * opsz, aux_off_of(spb) + aux_bytes) + 15) & ~(size_t)15;
+        };
+        auto smem_of = [&](int spb, int Wn) {
+            return red_off_of(spb) + (size_t)S * Wn * sizeof(double2) + (size_t)g.max_dslots * sizeof(uint32_t) + 16;
+        };
+        const size_t cap = (size_t)226 * 1024;
         int spb = 32;
-        while (spb > 1 && smem_of(spb) > (size_t)110 * 1024) spb >>= 1;
-        if (spb < 16) { spb = 32; while (spb > 1 && smem_of(spb) > (size_t)226 * 1024) spb >>= 1; }
-        if (smem_of(spb) > (size_t)226 * 1024) return fail(ctx, QIW_ERR_UNSUPPORTED, "per-sample tables exceed shared memory (too many sectors for the scalar kernel)");
+        while (spb > 1 && smem_of(spb, 24) > cap) spb >>= 1;
+        if (smem_of(spb, 24) > cap) return fail(ctx, QIW_ERR_UNSUPPORTED, "per-sample tables exceed shared memory (too many sectors for the scalar kernel)");
         if (const char* env = getenv("QIW_SPB")) {   // tuning override (power of two <= 32)
             const int v = atoi(env);
-            if (v >= 1 && v <= 32 && (v & (v - 1)) == 0 && smem_of(v) <= (size_t)226 * 1024) spb = v;
+            if (v >= 1 && v <= 32 && (v & (v - 1)) == 0 && smem_of(v, 24) <= cap) spb = v;
         }
-        g.spb[real] = spb;
-        g.smem[real] = smem_of(g.spb[real]);
+        const size_t per_sm = (size_t)227 * 1024;    // 1 KB per resident CTA is reserved by the system
+        int Wn = 24;
+        if (3 * (smem_of(spb, 8) + 1024) <= per_sm) Wn = 8;
+        else if (2 * (smem_of(spb, 12) + 1024) <= per_sm) Wn = 12;
+        if (const char* env = getenv("QIW_STEP_WARPS")) { const int v = atoi(env); if (v >= 1 && v <= 24 && smem_of(spb, v) <= cap) Wn = v; }
+        g.spb[real] = spb; g.warps[real] = Wn;
+        g.smem[real] = smem_of(spb, Wn);
+        g.aux_off[real] = (int)aux_off_of(spb); g.red_off[real] = (int)red_off_of(spb);
     }
-    const int spb_plan = g.spb[real_mode_possible(ctx, n_entries, ids) ? 1 : 0];
+    const int real_plan = real_mode_possible(ctx, n_entries, ids) ? 1 : 0;
+    const int W = g.warps[real_plan];
+    const int spb_plan = g.spb[real_plan];
     for (int i = 0; i < n_entries; ++i) {
         const EntryProgram& p = ctx->entries[ids[i]]->prog;
         const uint64_t c = p.order == 0 ? 1 : count;
         n_sb_all = std::max<uint64_t>(n_sb_all, (c + spb_plan - 1) / spb_plan);
     }
-    double chunk_cap = 16.0;   // groups of 32 configurations per warp and sample block
+    double chunk_cap = 3072.0;   // operand loads per warp and sample block
+    if (const char* env = getenv("QIW_CHUNK_CAP")) chunk_cap = std::max(16.0, atof(env));
     {
         // CTAs available if every entry is one job; lower the cap until ~3 CTAs per SM exist
         const double ctas = (double)n_entries * (double)n_sb_all;
         const double want = 3.0 * ndev_sm;
-        if (ctas < want) chunk_cap = std::max(1.0, std::floor(max_groups / W / std::ceil(want / ctas)));
+        if (ctas < want) chunk_cap = std::max(16.0, std::min(chunk_cap, std::floor(max_cost / W / std::ceil(want / ctas))));
     }
     pl->item0.resize(n_entries); pl->n_items.resize(n_entries);
     // heavy entries first: their CTAs are the critical path of the launch
     std::vector<int> order_idx(n_entries);
     for (int i = 0; i < n_entries; ++i) order_idx[i] = i;
     std::stable_sort(order_idx.begin(), order_idx.end(), [&](int a2, int b2) {
-        const EntryProgram &pa = ctx->entries[ids[a2]]->prog, &pb2 = ctx->entries[ids[b2]]->prog;
-        return (double)pa.n_leaves * pa.L2 > (double)pb2.n_leaves * pb2.L2; });
+        return ctx->entries[ids[a2]]->prog.lane_cost > ctx->entries[ids[b2]]->prog.lane_cost; });
     {
-        const int spb_min = spb_plan;
+        std::vector<uint32_t> chunk_off;
+        std::vector<LaneRun> runs;
         for (int i : order_idx) {
             const EntryProgram& p = ctx->entries[ids[i]]->prog;
             const uint64_t c = p.order == 0 ? 1 : count;
-            pl->max_sb = std::max<uint64_t>(pl->max_sb, (c + spb_min - 1) / spb_min);
-            const int64_t ng = (p.n_leaves + 31) / 32;
-            int n_chunks = 1;
-            if (!explicit_mode && ng > 0) {
-                const int jobs = (int)std::max(1.0, std::ceil((double)ng / (W * chunk_cap)));
-                n_chunks = (int)std::min<int64_t>(ng, (int64_t)W * jobs);
-            }
+            pl->max_sb = std::max<uint64_t>(pl->max_sb, (c + spb_plan - 1) / spb_plan);
+            int64_t n_rec = 0;
+            for (const auto& sec : p.lane_sections) n_rec += sec.n_rec;
+            const int jobs = (int)std::max(1.0, std::ceil((double)p.lane_cost / (W * chunk_cap)));
+            const int n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(n_rec, (int64_t)W * jobs));
             pl->item0[i] = (int)pl->items.size();
             for (int c0 = 0; c0 < n_chunks; c0 += W) {
                 WorkItem it;
-                it.entry = ids[i]; it.slot = i; it.chunk0 = c0; it.n_chunks = std::min(W, n_chunks - c0);
+                it.entry = ids[i]; it.slot = i; it.chunk0 = (int)chunk_off.size() + c0; it.n_chunks = std::min(W, n_chunks - c0);
                 it.n_chunks_total = n_chunks;
                 it.partial0 = (int)pl->items.size();
                 pl->items.push_back(it);
             }
+            append_entry_chunks(p, n_chunks, chunk_off, runs);
             pl->n_items[i] = (int)pl->items.size() - pl->item0[i];
         }
+        chunk_off.push_back((uint32_t)runs.size());
+        if (runs.empty()) runs.push_back(make_uint4(0u, 0u, 0u, 0u));
+        CK(pl->d_chunk_off.upload(chunk_off.data(), chunk_off.size(), ctx->stream));
+        CK(pl->d_runs.upload(runs.data(), runs.size(), ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
         g.n_items = (int)pl->items.size() - g.item0;
         pl->groups.push_back(g);
     }
@@ -1239,9 +1274,9 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         gp.max_slots = g.max_slots;
         gp.max_nodes1 = g.max_nodes1;
         gp.max_dslots = g.max_dslots;
-        gp.max_coefs = g.max_coefs;
-        gp.max_segdef = g.max_segdef;
+        gp.chunk_off = pl.d_chunk_off.p; gp.runs = pl.d_runs.p;
         gp.spb = g.spb[real];
+        gp.aux_off = g.aux_off[real]; gp.red_off = g.red_off[real];
         {
             // measured on B200 (C1): overlapping consecutive steps gains nothing (7.25 vs 6.96 ms per run), because
             // the dependent grid can only start once the last wave of the running grid has started; off by default
@@ -1253,9 +1288,7 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         dim3 grid((unsigned)pl.pitch, (unsigned)g.n_items, (unsigned)std::max(n_times, 1));
         {
             ProfScope ps(ctx, real ? 1 : 0);
-            bool pairs = false;
-            for (int id : pl.ids) if (ctx->entries[id]->prog.n_pairs > 0) pairs = true;
-            CK(launch_scalar_step(real != 0, pairs, gp, grid, ctx->warps * 32, g.smem[real], ctx->stream));
+            CK(launch_scalar_step(real != 0, gp, grid, g.warps[real] * 32, g.smem[real], ctx->stream));
         }
         ctx->launches++;
     }
@@ -1279,6 +1312,291 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         }
         ctx->launches++;
     }
+    return QIW_OK;
+}
+
+// ---- persistent run kernel: planning and launch ----------------------------------------------------
+// The bold steps of qiw_inchworm_run as ONE cooperative launch (scalar_run_kernel) when a step is too small to fill
+// the machine: every (entry, group of sample blocks, part of the lane program) becomes a job, one job per CTA for
+// the whole run.  Light entries take m = 2, 4, 8, 16 sample blocks per job (their tables are small), heavy entries
+// are split over several jobs, until the jobs are about equally long and fit the co-resident CTAs.
+// `*used` = false when the plan does not fit (too many samples, tables off the P grid, shared memory): the caller then
+// issues one step kernel per step as before.
+static int enqueue_run(qiw_context* ctx, Plan& pl, int k_first, int n_steps, double2* hist, size_t hist_stride, size_t hist_off,
+                       const int* diag, int n_diag, bool collective, bool* used) {
+    *used = false;
+    const bool verbose = getenv("QIW_RUN_VERBOSE") != nullptr;
+    auto skip = [&](const char* why) { if (verbose) fprintf(stderr, "qiw run kernel not used: %s\n", why); return QIW_OK; };
+    const HostModel& m = ctx->model;
+    if (!m.scalar || pl.explicit_mode || n_steps < 2) return skip("block model / explicit times / fewer than two steps");
+    if (const char* env = getenv("QIW_NO_RUN_KERNEL")) if (env[0] == '1') return skip("QIW_NO_RUN_KERNEL");
+    if (ctx->tables.size() > (size_t)kInlineTables) return skip("too many pair-interaction tables");
+    for (auto& tb : ctx->tables)
+        if (tb.n > 0 && (tb.kind != 0 || tb.n != ctx->n_tau || tb.beta != ctx->beta)) return skip("a pair-interaction table is not a plain function on the P grid");
+    if (collective && ctx->n_ranks > 1 && !ctx->peer_ready) return skip("multi-GPU without peer mailboxes");
+    const int n_ent = (int)pl.ids.size(), S = m.S, n_tau = ctx->n_tau;
+    if (collective && ctx->n_ranks > 1 && (size_t)n_ent * m.bsize * sizeof(double2) * 2 > kPeerSlotBytes) return skip("block sums exceed a mailbox slot");
+    const int real = real_mode_possible(ctx, n_ent, pl.ids.data()) ? 1 : 0;
+    Plan::RunPlan& rn = pl.run;
+    if (rn.state != 0 && rn.real != real) rn.state = 0;
+    if (rn.state < 0) return skip("plan does not fit (cached decision)");
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+    if (rn.state == 0) {
+        rn.state = -1; rn.real = real;
+        int W = 12, ctas_per_sm = 2;     // tuning overrides: QIW_RUN_WARPS (<= 12), QIW_RUN_CTAS_PER_SM
+        if (const char* env = getenv("QIW_RUN_WARPS")) { const int v = atoi(env); if (v >= 1 && v <= 12) W = v; }
+        if (const char* env = getenv("QIW_RUN_CTAS_PER_SM")) { const int v = atoi(env); if (v >= 1 && v <= 4) ctas_per_sm = v; }
+        const int threads = W * 32;
+        const int G = ctas_per_sm * n_sm;
+        const size_t cap = (size_t)228 * 1024 / ctas_per_sm - 1024;     // 228 KB per SM, 1 KB per resident CTA reserved by the system
+        const size_t opsz = real ? sizeof(double) : sizeof(double2);
+        const int n_tables = (int)ctx->tables.size();
+        struct Ent { const EntryProgram* p; int64_t n_sb; int mm, r; int slots, pd; int64_t n_rec; };
+        std::vector<Ent> ev(n_ent);
+        int max_dslots = 1;
+        for (int i = 0; i < n_ent; ++i) {
+            const EntryProgram& p = ctx->entries[pl.ids[i]]->prog;
+            Ent& x = ev[i];
+            x.p = &p; x.mm = 1; x.r = 1;
+            x.n_sb = p.order == 0 ? 1 : (int64_t)((pl.count + 31) / 32);
+            x.pd = p.nP + (int)p.dslots.size(); x.slots = x.pd + p.nSegL;
+            x.n_rec = 0;
+            for (const auto& sec : p.lane_sections) x.n_rec += sec.n_rec;
+            max_dslots = std::max(max_dslots, (int)p.dslots.size());
+        }
+        auto jobs_of = [&](const Ent& x) { return (int64_t)((x.n_sb + x.mm - 1) / x.mm) * x.r; };
+        auto n_chunks_job = [&](const Ent& x) { return (int)std::max<int64_t>(1, std::min<int64_t>(std::max(1, W / x.mm), x.n_rec / x.r)); };
+        // Cost of one job in shared-memory operations per 32 samples (what binds a step: calibrated on the per-phase
+        // timeline of the README configuration, profiles/trace_run.py): configuration sums, table fill, segment products
+        auto time_of = [&](const Ent& x) {
+            const double walk = (double)x.p->lane_cost / x.r;
+            const double build = 1.4 * (12.0 * x.p->dslots.size() + (7.0 + 4.0 * S) * (x.p->n_nodes - 1)) + 9.8 * x.p->nSegL + 30.0 * x.p->n_nodes;
+            return 300.0 + x.mm * (walk + build);
+        };
+        auto aux_bytes = [&](const Ent& x) { return (size_t)(x.p->n_nodes + 1) * 32 * x.mm * (2 * sizeof(double) + sizeof(int)); };
+        auto aux_off = [&](const Ent& x) {
+            const size_t ns = (size_t)32 * x.mm, tb = (size_t)x.slots * ns * opsz, lo = (size_t)x.pd * ns * opsz, ab = aux_bytes(x);
+            return (std::max(lo, tb > ab ? tb - ab : (size_t)0) + 15) & ~(size_t)15;
+        };
+        struct Layout { size_t ok, pw, red, ds, P, D, out, total; };
+        auto layout = [&]() {
+            size_t table = 0, okb = 0, pwb = 0;
+            for (const Ent& x : ev) {
+                const size_t ns = (size_t)32 * x.mm;
+                table = std::max(table, std::max((size_t)x.slots * ns * opsz, aux_off(x) + aux_bytes(x)));
+                okb = std::max(okb, ns * sizeof(int));
+                pwb = std::max(pwb, (size_t)std::max(x.p->D, 1) * ns * sizeof(double));
+            }
+            Layout L;
+            L.ok = (table + 15) & ~(size_t)15;
+            L.pw = L.ok + okb;
+            L.red = L.pw + pwb;
+            L.ds = L.red + (size_t)S * W * sizeof(double2);
+            L.P = (L.ds + (size_t)max_dslots * sizeof(uint32_t) + 15) & ~(size_t)15;
+            L.D = L.P + (((size_t)n_tau * S * opsz + 15) & ~(size_t)15);
+            L.out = L.D + (((size_t)std::max(n_tables, 1) * n_tau * opsz + 15) & ~(size_t)15);
+            L.total = L.out + (size_t)n_ent * S * sizeof(double2) + (size_t)n_ent * sizeof(double) + (size_t)(n_ent + 2) * sizeof(int) + 16;
+            return L;
+        };
+        if (layout().total > cap) return skip("tables exceed shared memory");
+        auto total_jobs = [&]() { int64_t t = 0; for (const Ent& x : ev) t += jobs_of(x); return t; };
+        // 1. too many jobs: let the cheapest jobs take twice the samples, as far as shared memory allows
+        while (total_jobs() > G) {
+            int best = -1;
+            for (int i = 0; i < n_ent; ++i) {
+                Ent& x = ev[i];
+                if (x.mm >= 16 || x.mm >= x.n_sb) continue;
+                x.mm *= 2;
+                const size_t need = layout().total;
+                const bool fits = need <= cap;
+                x.mm /= 2;
+                if (verbose && !fits) fprintf(stderr, "  merge: entry %d (order %d) m %d -> %d would need %zu B\n", pl.ids[i], x.p->order, x.mm, 2 * x.mm, need);
+                if (!fits) continue;
+                if (best < 0 || time_of(x) < time_of(ev[best])) best = i;
+            }
+            if (best < 0) break;             // the rest is packed: some CTAs take more than one job per step
+            ev[best].mm *= 2;
+            if (verbose) fprintf(stderr, "  merge: entry %d (order %d) -> m %d, jobs %lld, shared memory %zu of %zu\n", pl.ids[best], ev[best].p->order, ev[best].mm, (long long)total_jobs(), layout().total, cap);
+        }
+        if (total_jobs() > 8 * (int64_t)G) return skip("steps large enough to fill the machine: one step kernel per step");
+        // 2. CTAs to spare: split the longest jobs
+        for (;;) {
+            int worst = 0;
+            for (int i = 1; i < n_ent; ++i) if (time_of(ev[i]) > time_of(ev[worst])) worst = i;
+            Ent& x = ev[worst];
+            const int64_t more = (x.n_sb + x.mm - 1) / x.mm;
+            if (total_jobs() + more > G || x.n_rec / (x.r + 1) < 2 * std::max(1, W / x.mm)) break;
+            x.r += 1;
+        }
+        // 3. work items, chunks, jobs
+        const Layout L = layout();
+        std::vector<WorkItem> items;
+        std::vector<uint32_t> chunk_off;
+        std::vector<LaneRun> runs;
+        std::vector<RunJob> jobs;
+        std::vector<double> jtime;
+        std::vector<int> jent;
+        std::vector<int> entry_job0(n_ent + 1, 0);
+        for (int i = 0; i < n_ent; ++i) {
+            const Ent& x = ev[i];
+            entry_job0[i] = (int)jobs.size();
+            const int ncj = n_chunks_job(x);
+            const int item0 = (int)items.size();
+            for (int r = 0; r < x.r; ++r) {
+                WorkItem it;
+                it.entry = pl.ids[i]; it.slot = i; it.chunk0 = (int)chunk_off.size() + r * ncj; it.n_chunks = ncj;
+                it.n_chunks_total = ncj * x.r; it.partial0 = 0;
+                items.push_back(it);
+            }
+            append_entry_chunks(*x.p, ncj * x.r, chunk_off, runs);
+            for (int r = 0; r < x.r; ++r)
+                for (int64_t sb0 = 0; sb0 < x.n_sb; sb0 += x.mm) {
+                    RunJob j;
+                    memset(&j, 0, sizeof(j));
+                    j.item = item0 + r; j.sb0 = (int)sb0; j.n_sub = x.mm; j.aux_off = (int)aux_off(x); j.row = (int)jobs.size();
+                    j.stash_off = -1;
+                    jobs.push_back(j);
+                    jtime.push_back(time_of(x));
+                    jent.push_back(i);
+                }
+        }
+        entry_job0[n_ent] = (int)jobs.size();
+        chunk_off.push_back((uint32_t)runs.size());
+        if (runs.empty()) runs.push_back(make_uint4(0u, 0u, 0u, 0u));
+        // on-chip copy of a job's part of the lane program (records, runs, chunk table, segment definitions and
+        // coefficients), placed behind its operand table when the launch's table space leaves room (layout mirrored by
+        // scalar_run_kernel's prologue); used when the job is its CTA's only one
+        const size_t rows_bytes = jobs.size() * (size_t)S * opsz;
+        const bool rows_staged = rows_bytes <= L.ok;
+        for (size_t k = 0; k < jobs.size(); ++k) {
+            const Ent& x = ev[jent[k]];
+            const WorkItem& it = items[jobs[k].item];
+            const uint32_t r0 = chunk_off[it.chunk0], r1 = chunk_off[it.chunk0 + it.n_chunks];
+            size_t n4 = 8;
+            for (uint32_t q = r0; q < r1; ++q) {
+                const uint32_t code = runs[q].w, ni = (code >> 4) + ((((code >> 2) & 3u) + 1u) << (code & 3u));
+                n4 += (size_t)runs[q].y * ((ni + 3u) / 4u);
+            }
+            const int NW = x.p->seg_stride > 7 ? 2 : 1;
+            const size_t bytes = n4 * 16 + (size_t)(r1 - r0) * 16 + (((size_t)(it.n_chunks + 1) * 4 + 15) & ~(size_t)15) +
+                                 (size_t)x.p->nSegL * NW * 16 + (((size_t)x.p->nSegL * opsz + 15) & ~(size_t)15);
+            const size_t ns = (size_t)32 * x.mm;
+            const size_t region_end = std::max((size_t)x.slots * ns * opsz, aux_off(x) + aux_bytes(x));
+            const size_t off = (std::max(region_end, rows_staged ? rows_bytes : (size_t)0) + 15) & ~(size_t)15;
+            if (off + bytes <= L.ok) jobs[k].stash_off = (int)off;
+        }
+        // Jobs -> SMs -> CTAs at about equal estimated cost (longest job first onto the least loaded bin): a step is bound
+        // by the shared-memory pipe of the busiest SM, so the unit of balance is the SM; the CTAs that the hardware places
+        // on one SM claim the job lists of one bin at run time (scalar_run_kernel).  With fewer jobs than CTA slots the
+        // lists are simply one per CTA.
+        const int max_ctas = scalar_run_max_ctas(real != 0, threads, L.total, n_sm);
+        if (max_ctas < n_sm) return skip("occupancy below one CTA per SM");
+        const bool by_sm = (int)jobs.size() > n_sm && max_ctas >= G && !getenv("QIW_RUN_NO_SM_BINS");
+        const int n_ctas = by_sm ? G : (int)std::min<size_t>(jobs.size(), (size_t)std::min(G, max_ctas));
+        std::vector<int> ord(jobs.size());
+        for (size_t k = 0; k < ord.size(); ++k) ord[k] = (int)k;
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return jtime[a] > jtime[b]; });
+        std::vector<std::vector<int>> lists(n_ctas);
+        std::vector<double> load(n_ctas, 0.0);
+        if (by_sm) {
+            std::vector<std::vector<int>> bins(n_sm);
+            std::vector<double> bload(n_sm, 0.0);
+            for (int j : ord) {
+                const int b = (int)(std::min_element(bload.begin(), bload.end()) - bload.begin());
+                bins[b].push_back(j); bload[b] += jtime[j];
+            }
+            for (int b = 0; b < n_sm; ++b)            // inside a bin: longest first onto the least loaded of its CTAs
+                for (int j : bins[b]) {
+                    int best = b * ctas_per_sm;
+                    for (int q = 1; q < ctas_per_sm; ++q) if (load[b * ctas_per_sm + q] < load[best]) best = b * ctas_per_sm + q;
+                    lists[best].push_back(j); load[best] += jtime[j];
+                }
+        } else {
+            for (int j : ord) {
+                const int b = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+                lists[b].push_back(j); load[b] += jtime[j];
+            }
+        }
+        std::vector<RunJob> placed;
+        std::vector<int> cta_job0(n_ctas + 1, 0);
+        for (int k = 0; k < n_ctas; ++k) {
+            cta_job0[k] = (int)placed.size();
+            for (int j : lists[k]) placed.push_back(jobs[j]);
+        }
+        cta_job0[n_ctas] = (int)placed.size();
+        rn.by_sm = by_sm; rn.ctas_per_sm = ctas_per_sm;
+        CK(rn.d_cta_job0.upload(cta_job0.data(), cta_job0.size(), ctx->stream));
+        CK(rn.d_jobs.upload(placed.data(), placed.size(), ctx->stream));
+        CK(rn.d_entry_job0.upload(entry_job0.data(), entry_job0.size(), ctx->stream));
+        CK(rn.d_items.upload(items.data(), items.size(), ctx->stream));
+        CK(rn.d_chunk_off.upload(chunk_off.data(), chunk_off.size(), ctx->stream));
+        CK(rn.d_runs.upload(runs.data(), runs.size(), ctx->stream));
+        CK(rn.d_partials.reserve(2 * placed.size() * (size_t)S));
+        CK(rn.d_barrier.reserve(2052));     // [0, 2049): SM map of the run kernel, [2049]: grid barrier counter
+        CK(cudaStreamSynchronize(ctx->stream));
+        rn.n_jobs = (int)placed.size(); rn.n_ctas = n_ctas; rn.threads = threads; rn.smem = L.total;
+        rn.ok_off = (int)L.ok; rn.pw_off = (int)L.pw; rn.red_off = (int)L.red; rn.ds_off = (int)L.ds; rn.P_off = (int)L.P;
+        rn.D_off = (int)L.D; rn.out_off = (int)L.out; rn.rows_staged = rows_staged ? 1 : 0;
+        rn.state = 1;
+        if (getenv("QIW_RUN_VERBOSE")) {
+            fprintf(stderr, "qiw run kernel: %d jobs on %d CTAs (max %d), %zu B shared memory, %s arithmetic, CTA load %.0f .. %.0f\n", rn.n_jobs, n_ctas, max_ctas, rn.smem, real ? "real" : "complex", *std::min_element(load.begin(), load.end()), *std::max_element(load.begin(), load.end()));
+            for (int i = 0; i < n_ent; ++i)
+                fprintf(stderr, "  entry %d order %d k %d: cost %lld slots %d -> m %d, split %d, %lld jobs of %d chunks, est %.0f\n", pl.ids[i], ev[i].p->order,
+                        ev[i].p->n_pts_after, (long long)ev[i].p->lane_cost, ev[i].slots, ev[i].mm, ev[i].r, (long long)jobs_of(ev[i]), n_chunks_job(ev[i]), time_of(ev[i]));
+        }
+    }
+    RunParams rp;
+    memset(&rp, 0, sizeof(rp));
+    StepParams& sp = rp.sp;
+    sp.entries = ctx->dEntries.p; sp.dyn = pl.d_dyn.p; sp.items = rn.d_items.p; sp.chunk_off = rn.d_chunk_off.p; sp.runs = rn.d_runs.p;
+    sp.P = ctx->dP.p; sp.E = ctx->dE.p; sp.deltas = ctx->dDeltas.p;
+    for (int t = 0; t < kInlineTables && t < (int)ctx->hDeltas.size(); ++t) sp.deltas_inline[t] = ctx->hDeltas[t];
+    sp.tables_on_grid = 1;
+    sp.S = S; sp.bsize = m.bsize; sp.n_tau = n_tau; sp.h = ctx->beta / (n_tau - 1); sp.inv_h = 1.0 / sp.h;
+    sp.n_call_entries = n_ent;
+    sp.finish_P = ctx->dP.p; sp.finish_diag = diag; sp.finish_n_diag = n_diag;
+    if (collective && ctx->peer_ready && ctx->n_ranks > 1) {
+        sp.peer_ranks = ctx->n_ranks; sp.peer_rank = ctx->rank; sp.peer_seq = ctx->peer_seq + 1;
+        ctx->peer_seq += (unsigned long long)n_steps;
+        sp.peer_mail = ctx->dPeerPtrs.p; sp.peer_status = ctx->dPeerStatus.p;
+    }
+    rp.jobs = rn.d_jobs.p; rp.cta_job0 = rn.d_cta_job0.p; rp.entry_job0 = rn.d_entry_job0.p; rp.n_jobs = rn.n_jobs;
+    rp.k_first = k_first; rp.n_steps = n_steps;
+    rp.partials = rn.d_partials.p; rp.barrier = rn.d_barrier.p + 2049;
+    rp.sm_map = rn.by_sm ? rn.d_barrier.p : nullptr; rp.ctas_per_sm = rn.ctas_per_sm;
+    rp.n_tables = (int)ctx->tables.size();
+    rp.ok_off = rn.ok_off; rp.pw_off = rn.pw_off; rp.red_off = rn.red_off; rp.ds_off = rn.ds_off; rp.P_off = rn.P_off;
+    rp.D_off = rn.D_off; rp.out_off = rn.out_off; rp.rows_staged = rn.rows_staged;
+    rp.hist = hist; rp.hist_stride = hist_stride; rp.hist_off = hist_off;
+    CK(cudaMemsetAsync(rn.d_barrier.p, 0, 2052 * sizeof(unsigned int), ctx->stream));
+    const char* trace_path = getenv("QIW_TRACE");   // diagnostics (make trace): per-CTA timeline of the middle step
+    if (trace_path) {
+        CK(ctx->dTrace.reserve((size_t)rn.n_ctas * 16));
+        CK(cudaMemsetAsync(ctx->dTrace.p, 0, (size_t)rn.n_ctas * 16 * sizeof(unsigned long long), ctx->stream));
+        sp.trace = ctx->dTrace.p;
+    }
+    ctx->last_real_mode = real;
+    {
+        ProfScope ps(ctx, 2);
+        CK(launch_scalar_run(real != 0, rp, rn.n_ctas, rn.threads, rn.smem, ctx->stream));
+    }
+    ctx->launches++;
+    if (trace_path) {
+        std::vector<unsigned long long> tr((size_t)rn.n_ctas * 16);
+        CK(cudaMemcpyAsync(tr.data(), ctx->dTrace.p, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (FILE* f = fopen(trace_path, "w")) {
+            fprintf(f, "cta,t0,times,fill,seg,walk,jobs_done,barrier,reduce,update,smid,n_jobs,entry,n_sub,end_ns\n");
+            for (int c2 = 0; c2 < rn.n_ctas; ++c2) {
+                const unsigned long long* t = tr.data() + (size_t)c2 * 16;
+                fprintf(f, "%d,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu,%llu\n", c2, t[0], t[1] - t[0], t[2] - t[0], t[3] - t[0], t[4] - t[0], t[5] - t[0],
+                        t[6] - t[0], t[7] - t[0], t[8] - t[0], t[9], t[10], t[11], t[12], t[13]);
+            }
+            fclose(f);
+        }
+    }
+    *used = true;
     return QIW_OK;
 }
 
@@ -1593,8 +1911,17 @@ int qiw_inchworm_run(qiw_context* ctx, int32_t n_bare, const int32_t* bare_ids, 
                               order_contribs ? ctx->dHist.p + (size_t)1 * n_hist * bs : nullptr, ctx->stream));
         ctx->launches++;
     }
-    // bold steps n = 2 .. n_tau-1 (1-based): tau_w = grid[n], tau_f = grid[n+1] (:474-493)
-    for (int n = 1; n_bold > 0 && n < n_tau - 1; ++n) {
+    // bold steps n = 2 .. n_tau-1 (1-based): tau_w = grid[n], tau_f = grid[n+1] (:474-493): one persistent launch when
+    // the steps are small, else one step kernel per step
+    bool run_used = false;
+    if (n_bold > 0 && n_tau > 2) {
+        rc = enqueue_run(ctx, *pd, 1, n_tau - 2, order_contribs ? ctx->dHist.p : nullptr, (size_t)n_hist * bs, (size_t)n_bare * bs,
+                         ctx->dDiag.p, (int)diag.size(), true, &run_used);
+        if (rc) return rc;
+        if (run_used && ctx->n_ranks > 1) coll_done = true;
+        if (run_used) { rc = mark_ucache_valid(ctx, *pd); if (rc) return rc; }   // the run kernel's prologue filled the root cache
+    }
+    for (int n = 1; !run_used && n_bold > 0 && n < n_tau - 1; ++n) {
         fin.k_f = n + 1; fin.normalize = 1;
         fin.hist = order_contribs ? ctx->dHist.p + ((size_t)(n + 1) * n_hist + n_bare) * bs : nullptr;
         rc = enqueue_step(ctx, *pd, 0.0, n * h, (n + 1) * h, &fin, &fused, true, &coll_done);

@@ -356,12 +356,11 @@ int compile_entry(const HostModel& m, int mode, int order, int n_pts_after, int 
 void factorise_records(EntryProgram& e, int S, int K_req) {
     const int nI = e.n_nodes - 1, n = e.order, nP = e.nP, nD = (int)e.dslots.size();
     const int64_t nl = e.n_leaves;
-    // candidate segmentations: K equal parts; keep the cheapest in shared-memory operand loads
-    //   cost(K) = leaves * (K + n)  +  sum over segments (entries * segment length)
+    // candidate segmentations: K equal parts; keep the cheapest in shared-memory operations per sample (see `build`)
     const int Kmin = (nI + 8) / 9;   // the kernel handles segments of up to 9 intervals
     const int Kmax = std::max(Kmin, std::min(nI, 4));
     const int K_lo = K_req > 0 ? std::max(Kmin, std::min(K_req, nI)) : Kmin, K_hi = K_req > 0 ? K_lo : Kmax;
-    struct Candidate { std::vector<uint32_t> rec; std::vector<uint16_t> def; int nseg = 0, stride = 0; double cost = 1e300; };
+    struct Candidate { std::vector<uint32_t> rec; std::vector<uint16_t> def; int nseg = 0, stride = 0, n_lane_seg = 0; double cost = 1e300; };
     std::vector<Candidate> cand(K_hi - K_lo + 1);
     auto build = [&](int K, Candidate& c) {
         std::vector<int> bound(K + 1);
@@ -373,7 +372,6 @@ void factorise_records(EntryProgram& e, int S, int K_req) {
         std::vector<uint32_t>& rec = c.rec;
         rec.assign((size_t)nl * (K + n + 1), 0u);
         int nseg = 0;
-        double seg_cost = 0;
         for (int64_t l = 0; l < nl; ++l) {
             const uint32_t* src = e.records.data() + (size_t)l * e.RL;
             uint32_t* dst = rec.data() + (size_t)l * (K + n + 1);
@@ -393,14 +391,42 @@ void factorise_records(EntryProgram& e, int S, int K_req) {
                     id = nseg++;
                     index[g][key] = id;
                     for (int i = 0; i < stride; ++i) def.push_back(i < (int)key.size() ? key[i] : (uint16_t)0xFFFF);
-                    seg_cost += (double)key.size();
                 } else id = it->second;
                 dst[1 + g] = (uint32_t)(nP + nD + id);
             }
         }
-        // slots per sample row bound the CTA's shared memory: penalise tables beyond ~4 KB of doubles
-        const double row = nP + nD + nseg;
-        c.cost = (double)nl * (K + n) + seg_cost + (row > 512 ? 1e6 * (row - 512) : 0.0);
+        // Cost of the candidate in shared-memory operations per sample, as the step kernel executes it (lane program):
+        // records of M = 4, 2, 1 configurations sharing their pair-interaction operands cost order + M K loads (+ 2 for
+        // the record fetch), a segment-table entry its operands + 3 (definition, coefficient, store) — and the table
+        // is rebuilt for every sample, so its entries weigh as much as the records.
+        double rec_cost = 0, tab_cost = 0;
+        {
+            std::map<std::vector<uint32_t>, int> members;                 // (initial sector, sorted interaction slots) -> configurations
+            std::map<std::pair<uint32_t, uint32_t>, int> first_seg;       // (coefficient, first segment entry): entries of their own
+            std::vector<uint32_t> key;
+            for (int64_t l = 0; l < nl; ++l) {
+                const uint32_t* r = rec.data() + (size_t)l * (K + n + 1);
+                key.assign(r + 1 + K, r + 1 + K + n);
+                std::sort(key.begin(), key.end());
+                key.push_back(r[0] >> 16);
+                ++members[key];
+                first_seg[std::make_pair(r[0] & 0xFFFFu, r[1])] = 1;
+            }
+            for (const auto& kv : members) {
+                const int nm = kv.second;
+                rec_cost += (nm / 4) * (n + 4 * K + 2) + ((nm % 4) / 2) * (n + 2 * K + 2) + (nm % 2) * (n + K + 2);
+            }
+            std::vector<char> is_first(nseg, 0);
+            for (const auto& kv : first_seg) is_first[kv.first.second - (uint32_t)(nP + nD)] = 1;
+            auto len_of = [&](int id) { int len = 0; for (int i = 0; i < stride; ++i) len += def[(size_t)id * stride + i] != 0xFFFF; return len; };
+            for (int id = 0; id < nseg; ++id) if (!is_first[id]) tab_cost += len_of(id) + 3;
+            for (const auto& kv : first_seg) tab_cost += len_of((int)(kv.first.second - (uint32_t)(nP + nD))) + 3;
+            c.n_lane_seg = (int)first_seg.size();
+            for (int id = 0; id < nseg; ++id) c.n_lane_seg += !is_first[id];
+        }
+        // slots per sample bound the CTA's shared memory: penalise tables beyond ~4 KB of doubles per sample
+        const double row = nP + nD + c.n_lane_seg;
+        c.cost = rec_cost + tab_cost + (row > 512 ? 1e6 * (row - 512) : 0.0);
         c.nseg = nseg; c.stride = stride;
     };
     // the candidates are independent: one host thread each when the entry is big enough to pay for it
@@ -426,43 +452,81 @@ void factorise_records(EntryProgram& e, int S, int K_req) {
     e.K = bestK; e.L2 = bestK + n; e.nSeg = best_nseg; e.seg_stride = std::max(best_stride, 1);
     e.rec2.swap(best_rec); e.segdef.swap(best_def);
     if (e.segdef.empty()) e.segdef.assign(1, 0xFFFF);
-    // pair up configurations with identical pair-interaction operands and initial sector
-    {
-        const int K = e.K, RL = e.L2 + 1;
-        e.rec_pair.clear(); e.rec_left.clear(); e.n_pairs = 0; e.n_left = 0;
-        std::map<std::vector<uint32_t>, int64_t> open_member;   // key: (s_init, Delta slots) -> leaf waiting for a partner
-        std::vector<char> used(nl, 0);
-        std::vector<int64_t> partner(nl, -1);
-        // measured on B200: pairing pays from order 5 on (orders 0:6: +16 % throughput); at order <= 4 the shorter
-        // operand lists do not make up for the second record stream (QIW_PAIR_MIN_ORDER overrides)
-        int pair_min_order = 5;
-        if (const char* env = getenv("QIW_PAIR_MIN_ORDER")) pair_min_order = atoi(env);
-        if (n >= 1 && n >= pair_min_order)
-            for (int64_t l = 0; l < nl; ++l) {
-                const uint32_t* r = e.rec2.data() + (size_t)l * RL;
-                std::vector<uint32_t> key(r + 1 + K, r + 1 + K + n);
-                key.push_back(r[0] >> 16);
-                auto it = open_member.find(key);
-                if (it == open_member.end()) open_member[key] = l;
-                else { partner[it->second] = l; used[l] = 1; open_member.erase(it); }
+    build_lane_program(e);
+}
+
+void build_lane_program(EntryProgram& e) {
+    const int K = e.K, n = e.order, RL = e.L2 + 1, nP = e.nP, nD = (int)e.dslots.size(), stride = e.seg_stride;
+    const int64_t nl = e.n_leaves;
+    e.lane_sections.clear(); e.lane_items.clear(); e.lane_segdef.clear(); e.lane_seg_coef.clear(); e.nSegL = 0; e.lane_cost = 0;
+    // 1. segment table with the coefficient folded into the first segment of every configuration: entries are
+    //    (coefficient or none, entry of the plain table), numbered in order of first use
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> seg_index;
+    auto seg_id = [&](uint32_t coef, uint32_t plain) {
+        auto key = std::make_pair(coef, plain);
+        auto it = seg_index.find(key);
+        if (it != seg_index.end()) return it->second;
+        const uint32_t id = (uint32_t)e.nSegL++;
+        seg_index[key] = id;
+        const uint16_t* def = e.segdef.data() + (size_t)(plain - (uint32_t)(nP + nD)) * stride;
+        e.lane_segdef.insert(e.lane_segdef.end(), def, def + stride);
+        e.lane_seg_coef.push_back((uint16_t)coef);
+        return id;
+    };
+    // 2. groups: (initial sector, sorted Delta slots) -> members, in order of first appearance
+    struct Group { uint32_t s_i; std::vector<uint32_t> dsl; std::vector<uint32_t> members; };   // members: K slots each
+    std::vector<Group> groups;
+    std::map<std::vector<uint32_t>, size_t> gindex;
+    std::vector<uint32_t> key;
+    for (int64_t l = 0; l < nl; ++l) {
+        const uint32_t* r = e.rec2.data() + (size_t)l * RL;
+        key.assign(r + 1 + K, r + 1 + K + n);
+        std::sort(key.begin(), key.end());
+        key.push_back(r[0] >> 16);
+        auto it = gindex.find(key);
+        size_t g;
+        if (it == gindex.end()) {
+            g = groups.size();
+            gindex[key] = g;
+            groups.emplace_back();
+            groups[g].s_i = r[0] >> 16;
+            groups[g].dsl.assign(key.begin(), key.end() - 1);
+        } else g = it->second;
+        for (int q = 0; q < K; ++q)
+            groups[g].members.push_back((uint32_t)(nP + nD) + seg_id(q == 0 ? (r[0] & 0xFFFFu) : 0xFFFFu, r[1 + q]));
+    }
+    // 3. fixed-shape records: every group is cut greedily into records of 4, 2 and 1 members; sections = (M, sector)
+    int S = 0;
+    for (const Group& g : groups) S = std::max(S, (int)g.s_i + 1);
+    const int Ms[3] = {4, 2, 1};
+    for (int mi = 0; mi < 3; ++mi) {
+        const int M = Ms[mi], ni = lane_record_items(n, K, M);
+        for (int s = 0; s < S; ++s) {
+            EntryProgram::LaneSection sec;
+            sec.s_i = s; sec.M = M; sec.rec0 = 0; sec.n_rec = 0; sec.chunk0 = (uint32_t)(e.lane_items.size() / 4);
+            sec.cost = (uint32_t)(n + M * K + 2);
+            for (const Group& g : groups) {
+                if ((int)g.s_i != s) continue;
+                // members of this group that fall into records of M members under the greedy 4-2-1 cut
+                const int nm = (int)(g.members.size() / std::max(K, 1));
+                int first = 0, count = 0;     // first member / number of records of this class
+                if (M == 4) { count = nm / 4; first = 0; }
+                else if (M == 2) { count = (nm % 4) / 2; first = (nm / 4) * 4; }
+                else { count = nm % 2; first = (nm / 2) * 2; }
+                for (int c = 0; c < count; ++c) {
+                    const size_t base = e.lane_items.size();
+                    for (uint32_t d : g.dsl) e.lane_items.push_back(d);
+                    for (int q = 0; q < M * K; ++q) e.lane_items.push_back(g.members[(size_t)(first + c * M) * K + q]);
+                    e.lane_items.resize(base + ni, 0);
+                    ++sec.n_rec;
+                }
             }
-        for (int64_t l = 0; l < nl; ++l) {
-            if (used[l]) continue;
-            const uint32_t* a = e.rec2.data() + (size_t)l * RL;
-            if (partner[l] >= 0) {
-                const uint32_t* b = e.rec2.data() + (size_t)partner[l] * RL;
-                e.rec_pair.push_back(a[0]);
-                e.rec_pair.push_back(b[0] & 0xFFFFu);
-                for (int g = 0; g < K; ++g) e.rec_pair.push_back(a[1 + g]);
-                for (int g = 0; g < K; ++g) e.rec_pair.push_back(b[1 + g]);
-                for (int q = 0; q < n; ++q) e.rec_pair.push_back(a[1 + K + q]);
-                ++e.n_pairs;
-            } else {
-                e.rec_left.insert(e.rec_left.end(), a, a + RL);
-                ++e.n_left;
-            }
+            if (sec.n_rec) { e.lane_sections.push_back(sec); e.lane_cost += (int64_t)sec.n_rec * sec.cost; }
         }
     }
+    uint32_t rec0 = 0;
+    for (auto& sec : e.lane_sections) { sec.rec0 = rec0; rec0 += sec.n_rec; }
+    if (e.lane_segdef.empty()) e.lane_segdef.assign(std::max(stride, 1), 0xFFFF);
 }
 
 }  // namespace qiw

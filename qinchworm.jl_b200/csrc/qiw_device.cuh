@@ -31,16 +31,11 @@ struct DevEntry {
     int exact;                  // order 0: one deterministic evaluation
     int pos_src[kDevMaxNodes + 1];
     int n_coefs;
-    int L2, n_leaves, n_groups; // operands per configuration (K segments + order), records, groups of 32
-    int nSeg, seg_stride;       // segment-product table: entries, propagator slots per entry
-    const uint32_t* records;    // transposed: [n_groups][L2 + 1][32 lanes]; word 0 = coef | s_i << 16,
-                                // words 1..L2 = operand slot inside a sample's table row
-    // paired form of the same configurations (EntryProgram::rec_pair / rec_left), what the summing walk executes:
-    const uint32_t* records_pair;   // transposed [n_groups_pair][2 + 2K + order][32 lanes]
-    const uint32_t* records_left;   // transposed [n_groups_left][L2 + 1][32 lanes]
-    int n_groups_pair, n_groups_left, K;
-    const uint16_t* segdef;     // transposed [groups of 32 entries][seg_stride][32 lanes]: propagator slots of each
-                                // segment product; unused positions point at the row's constant-one slot
+    // lane program (EntryProgram::lane_*): what the step kernel executes with lane = sample
+    int K, nSegL, seg_stride;   // segments per configuration; entries / propagator slots per entry of the segment table
+    const uint4* lane_items;    // records: `order` Delta slots then M * K segment slots, 32 bits each, padded to 4
+    const uint4* lane_segdef4;  // [nSegL][seg_stride > 7 ? 2 : 1] packed 16-bit fields: index of the coefficient folded into
+                                // the product (0xFFFF = none), then its propagator slots (0xFFFF = unused)
     const double2* coefs;
     const int4* dslots;         // (pos_tail, pos_head, table, 0)
 };
@@ -58,20 +53,27 @@ struct DevEntryDyn {
     int item0, n_items;         // this entry's CTA jobs (consecutive rows of the partials buffer)
 };
 
-// One CTA job: a group of up to `warps` consecutive chunks of one entry.
+// One CTA job: up to `warps` consecutive chunks of one entry's lane program (one chunk per warp).
 struct WorkItem {
     int entry;        // id of the compiled entry (index into the DevEntry table)
-    int slot;         // index of the entry within the call (DevEntryDyn, chunk tables)
-    int chunk0;       // first chunk of the group
-    int n_chunks;     // chunks in the group (<= warps per CTA)
-    int n_chunks_total;  // chunks the entry's configurations are split into
+    int slot;         // index of the entry within the call (DevEntryDyn)
+    int chunk0;       // first chunk of the job: index into StepParams::chunk_off
+    int n_chunks;     // chunks in the job (<= warps per CTA)
+    int n_chunks_total;  // block models: chunks the entry's trees are split into
     int partial0;     // first row of this item in the partials buffer
 };
+
+// A run of consecutive records of one section (same shape, same initial sector) inside a chunk.
+//   x = first 128-bit word of the run in DevEntry::lane_items, y = number of records,
+//   z = initial sector, w = shape code: order * 16 + (K - 1) * 4 + (0, 1, 2 for M = 1, 2, 4)
+typedef uint4 LaneRun;
 
 struct StepParams {
     const DevEntry* entries;
     const DevEntryDyn* dyn;
     const WorkItem* items;
+    const uint32_t* chunk_off;     // scalar models: [chunks + 1] first run of every chunk
+    const LaneRun* runs;
     // model
     const double2* P;              // [n_tau][bsize]
     const double* E;               // [S] (scalar models) energies + lambda
@@ -83,9 +85,10 @@ struct StepParams {
     // times; when `times_dev` is non-null the triple is read from device memory (run-level API)
     double t_i, t_w, t_f;
     const double* times_dev;
-    int max_slots;                 // operands per sample row reserved in shared memory
+    int max_slots;                 // operands per sample reserved in shared memory
+    int aux_off, red_off;          // shared-memory offsets: times / grid cells (dead once the propagator and interaction
+                                   // slots are filled: they overlap the segment-product rows of T), per-warp sums
     int max_nodes1;                // largest number of backbone positions of the launch's entries, plus one
-    int max_coefs, max_segdef;     // shared-memory staging sizes (largest entry of the launch)
     int spb, spb_log2;             // samples per CTA pass (power of two <= 32)
     int sobol_z_stride;            // > 0: blockIdx.z selects a Sobol sequence (words between the sequences' parameter blocks)
     int tables_on_grid;            // every Delta table is a plain grid function on the P grid and described inline
@@ -114,6 +117,29 @@ struct StepParams {
     unsigned long long peer_seq;   // sequence number of this collective (flags carry it; parity selects the buffer)
     unsigned char* const* peer_mail;   // [peer_ranks] base address of every rank's mailbox (own included)
     int* peer_status;              // set to 1 if a peer did not answer within the time-out
+};
+
+// One CTA of the persistent run kernel: a work item (entry + chunks of its lane program) on 32 * n_sub consecutive
+// samples starting at sample block sb0, for every step of the run.
+struct RunJob { int item, sb0, n_sub, aux_off, row, stash_off, pad_[2]; };   // row: this job's row of the partial sums;
+                                                                              // stash_off: on-chip copy of its program, or -1
+
+struct RunParams {
+    StepParams sp;                 // tables, entries, work items, runs; finish_P = the global P table; peer_* as in a step
+    const RunJob* jobs;            // [n_jobs], grouped by CTA
+    const int* cta_job0;           // [gridDim.x + 1] first job of every CTA (jobs are packed at equal estimated time)
+    const int* entry_job0;         // [n_call_entries + 1] first partial row of every entry of the call (rows of an entry are consecutive)
+    int n_jobs;
+    int k_first, n_steps;          // step i: tau_w = grid[k_first + i], tau_f = grid[k_first + i + 1]
+    void* partials;                // [2][n_jobs][S] per-job sums (kernel arithmetic), alternating with the step's parity
+    unsigned int* barrier;         // arrival counter of the grid barrier, zero at launch
+    unsigned int* sm_map;          // null, or [1024] CTAs arrived per SM, [1024] bin claimed by the SM (+1), [1] bins claimed; zero at launch
+    int ctas_per_sm;               // job lists per bin (cta_job0 is then indexed by bin * ctas_per_sm + arrival order on the SM)
+    int n_tables;                  // pair-interaction tables staged in shared memory (all on the P grid)
+    int rows_staged;               // the partial rows of a step fit the operand table's space: reduce them from shared memory
+    int ok_off, pw_off, red_off, ds_off, P_off, D_off, out_off;   // shared-memory layout (bytes)
+    double2* hist;                 // optional per-entry contributions: hist[k_f * hist_stride + hist_off + entry * S + s]
+    size_t hist_stride, hist_off;
 };
 
 // Mailbox layout (per rank): flags[kMaxPeers][2] (uint64), then data[kMaxPeers][2][kPeerSlotBytes].

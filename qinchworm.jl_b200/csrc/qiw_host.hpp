@@ -76,14 +76,22 @@ struct EntryProgram {
     //   rec2[K+1..K+order] = slot of the pair-interaction factor (nP + dslot index)
     // segdef[nSeg][seg_stride]: propagator slots multiplied into each segment product (0xFFFF = unused).
     std::vector<uint32_t> rec2;
-    // Paired records.  Configurations that share all pair-interaction factors and the initial sector (they
-    // differ in the flavours running along the backbone, hence in the segment products) are evaluated two at
-    // a time:  prod(Delta) * (coefA * prod(segA) + coefB * prod(segB))  — the Delta operands are loaded once.
-    //   rec_pair[0] = coefA | initial sector << 16, rec_pair[1] = coefB,
-    //   rec_pair[2..2+K) = segA slots, [2+K..2+2K) = segB slots, [2+2K..2+2K+order) = Delta slots
-    // rec_left holds the configurations without a partner in the rec2 format.
-    std::vector<uint32_t> rec_pair, rec_left;
-    int64_t n_pairs = 0, n_left = 0;
+    // Lane program (scalar models; what the step kernel executes with lane = sample).  Configurations that share
+    // all pair-interaction operands and the initial sector differ only in the flavours running along the backbone,
+    // i.e. in their segment products; they form a GROUP:
+    //     sum over the group = prod(Delta operands) * sum_members prod(segment products of the member).
+    // The coefficient of a member is folded into its first segment product (a table entry of its own per distinct
+    // (coefficient, segment) combination: lane_segdef / lane_seg_coef), so a member is a plain product of table slots.
+    // Groups are cut into fixed-shape records of M = 4, 2 or 1 members and sorted into sections of equal
+    // (M, initial sector); a record is `order` Delta slots followed by M * K segment slots, 32 bits each (plain slot
+    // numbers of the per-sample table), padded to a multiple of 4 items (one warp-uniform 128-bit load per 4 items).
+    struct LaneSection { int32_t s_i, M; uint32_t rec0, n_rec; uint32_t chunk0, cost; };   // chunk0: first 128-bit word; cost per record
+    std::vector<LaneSection> lane_sections;
+    std::vector<uint32_t> lane_items;
+    std::vector<uint16_t> lane_segdef;     // [nSegL][seg_stride] propagator slots (0xFFFF = unused)
+    std::vector<uint16_t> lane_seg_coef;   // [nSegL] index of the folded coefficient, 0xFFFF = none
+    int nSegL = 0;
+    int64_t lane_cost = 0;                 // sum over sections of n_rec * cost (operand loads per sample)
     std::vector<uint16_t> segdef;
     int K = 0, L2 = 0, nSeg = 0, seg_stride = 0;
     // statistics
@@ -96,6 +104,9 @@ int compile_entry(const HostModel& m, int mode, int order, int n_pts_after, int 
                   const int32_t* pairs, const int32_t* parity, EntryProgram& out, std::string& err);
 // Regroup the flat leaf records into factorised records with `K` segments (0 = choose).
 void factorise_records(EntryProgram& e, int S, int K);
+// Group the factorised records into the lane program (EntryProgram::lane_*).
+void build_lane_program(EntryProgram& e);
+inline int lane_record_items(int order, int K, int M) { return ((order + M * K + 3) / 4) * 4; }
 
 // Host Sobol / topology helpers (qiw_seq.cpp)
 int sobol_direction_numbers(int D, uint32_t* m);

@@ -1,100 +1,15 @@
-// qiw_kernels.cu — hand-written CUDA kernels (sm_100a) of the qMC diagram-evaluation hot path.
-//
-// scalar_step_kernel (1x1 sector blocks): a CTA owns a block of <= 32 scrambled-Sobol samples
-// of one entry (one TopologiesInputData).  All warps first build the per-sample operand tables in shared
-// memory T[sample][slot] —
-//   Sobol point by Gray-code random access      (src/scrambled_sobol.jl:158-197)
-//   cube -> ordered-time simplex                (src/qmc_integrate.jl:225-235,425-449)
-//   i*P_s(t_pos, t_pos-1) for every interval/sector, i*Delta for every used arc/table
-//                                               (src/topology_eval.jl:357-374,397-416)
-//   products of the propagators over segments of the backbone (factorised records, qiw_compile.cpp)
-// — and then every LANE takes one pre-compiled, pruned configuration (src/topology_eval.jl:454-556) whose
-// record of K + order operand slots it keeps in registers, and loops over the CTA's samples.  The last CTA
-// to finish reduces all partial sums in fixed order, exchanges them with the peer GPUs and applies
-// set_ppgf! / normalize! (fused tail).  In real mode (everything purely imaginary-time) the same kernel runs
-// in real arithmetic.
+// qiw_kernels.cu — hand-written CUDA kernels (sm_100a) of the qMC diagram-evaluation hot path, part 2:
+// the kernels for sector blocks larger than 1x1 and the small service kernels.  The step / run kernels of
+// 1x1-block models live in qiw_scalar.cu.
 //
 // block_walk_kernel (sector blocks up to 4x4, real arithmetic): lane = sample, warp-uniform replay of the
 // pruned configuration tree with the running matrix product in registers.  block_step_kernel is the general
 // complex path for block models.
 #include <cstdio>
 
-#include "qiw_device.cuh"
+#include "qiw_devfn.cuh"
 
 namespace qiw {
-
-// ---- small complex helpers -------------------------------------------------------------------
-
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
-    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {  // a*b + c
-    return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
-}
-__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ double2 cscale(double a, double2 b) { return make_double2(a * b.x, a * b.y); }
-__device__ __forceinline__ double2 times_i(double2 a) { return make_double2(-a.y, a.x); }
-
-// ---- interpolation ---------------------------------------------------------------------------
-
-// Keldysh.jl's generic grid interpolation of a translation-invariant imaginary-time function
-// stored as D[k] = G(k h): bilinear on the cell (a, b) of the (t_f, t_i) grid, linear on the
-// triangle when both times share a cell (rule: DESIGN.md §2; call sites
-// src/topology_eval.jl:368,414).
-__device__ __forceinline__ double2 grid_interp(const double2* __restrict__ D, int stride, int n, double inv_h,
-                                               double t_f, double t_i) {
-    // t * (1/h) instead of t / h: may pick the neighbouring cell when t sits on a grid point to the
-    // last bit, where the interpolant is continuous, so the value changes by O(ulp) only
-    const double qf = t_f * inv_h, qi = t_i * inv_h;
-    int a = (int)floor(qf), b = (int)floor(qi);
-    a = min(max(a, 0), n - 2);
-    b = min(max(b, 0), n - 2);
-    const double w1 = qf - (double)a, w2 = qi - (double)b;
-    if (a == b) {
-        const double2 d0 = __ldg(D), d1 = __ldg(D + stride);
-        const double w = w1 - w2;
-        return make_double2(d0.x + w * (d1.x - d0.x), d0.y + w * (d1.y - d0.y));
-    }
-    const int k = a - b;
-    const double2 dk = __ldg(D + (size_t)k * stride), dp = __ldg(D + (size_t)(k + 1) * stride),
-                  dm = __ldg(D + (size_t)(k - 1) * stride);
-    const double c00 = (1.0 - w1) * (1.0 - w2), c10 = w1 * (1.0 - w2), c01 = (1.0 - w1) * w2, c11 = w1 * w2;
-    return make_double2(c00 * dk.x + c10 * dp.x + c01 * dm.x + c11 * dk.x,
-                        c00 * dk.y + c10 * dp.y + c01 * dm.y + c11 * dk.y);
-}
-
-// Natural cubic spline in dt = t_f - t_i (src/spline_gf.jl:208-219).
-__device__ __forceinline__ double2 spline_eval(const DevDelta& t, double dt) {
-    const double h = t.h;
-    int j = (int)floor(dt * t.inv_h);
-    j = min(max(j, 0), t.n - 2);
-    const double xa = dt - (double)j * h, xb = (double)(j + 1) * h - dt;
-    const double2 y0 = __ldg(t.y + j), y1 = __ldg(t.y + j + 1), m0 = __ldg(t.M + j), m1 = __ldg(t.M + j + 1);
-    const double i6h = t.inv_h * (1.0 / 6.0), h6 = h * (1.0 / 6.0), ih = t.inv_h;
-    const double ca = xa * xa * xa * i6h, cb = xb * xb * xb * i6h;
-    return make_double2(m0.x * cb + m1.x * ca + (y0.x * ih - m0.x * h6) * xb + (y1.x * ih - m1.x * h6) * xa,
-                        m0.y * cb + m1.y * ca + (y0.y * ih - m0.y * h6) * xb + (y1.y * ih - m1.y * h6) * xa);
-}
-
-__device__ __forceinline__ double2 delta_eval(const DevDelta& t, double t_f, double t_i) {
-    if (t.kind == 1) return spline_eval(t, t_f - t_i);
-    return grid_interp(t.y, 1, t.n, t.inv_h, t_f, t_i);
-}
-
-// ---- Sobol -----------------------------------------------------------------------------------
-
-// Point k (0-based) of a digital sequence: x0 xor the direction numbers selected by gray(k);
-// identical to k calls of next! (src/scrambled_sobol.jl:158-173).
-__device__ __forceinline__ uint32_t sobol_coord(const uint32_t* __restrict__ m, uint32_t x0, uint32_t k) {
-    uint32_t g = k ^ (k >> 1), x = x0;
-    int b = 0;
-    while (g) {
-        if (g & 1u) x ^= __ldg(m + b);
-        g >>= 1;
-        ++b;
-    }
-    return x;
-}
 
 __global__ void sobol_points_kernel(int D, const uint32_t* __restrict__ m, const uint32_t* __restrict__ x0,
                                     unsigned long long start, unsigned long long count, uint32_t* __restrict__ out) {
@@ -104,769 +19,6 @@ __global__ void sobol_points_kernel(int D, const uint32_t* __restrict__ m, const
     const int d = (int)(i % D);
     out[i] = sobol_coord(m + d * 32, x0[d], (uint32_t)(start + k));
 }
-
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
-// ---- arithmetic modes ----------------------------------------------------------------------------
-// On the imaginary-time branch every factor of a configuration's weight is i*P or i*Delta with P and
-// Delta purely imaginary, and the folded coefficient (operator matrix elements times -i * parity *
-// (-1)^order) is purely imaginary: the whole product is (real number) * i, exactly.  When the host has
-// verified that for the tables and coefficients in use (DESIGN.md §3 "real mode") the kernel runs in
-// real arithmetic — bit-identical results, one FP64 multiply and one 8-byte shared-memory operand per
-// factor instead of four and 16 bytes.  Anything else runs the same code in complex arithmetic.
-template <bool REAL> struct Num;
-template <> struct Num<true> {
-    typedef double T;
-    static __device__ __forceinline__ T zero() { return 0.0; }
-    static __device__ __forceinline__ T mul(T a, T b) { return a * b; }
-    static __device__ __forceinline__ T add(T a, T b) { return a + b; }
-    static __device__ __forceinline__ T from_real(double x) { return x; }
-    static __device__ __forceinline__ T times_i_of(double2 v) { return -v.y; }          // Re(i v), Im(i v) = v.x = 0
-    static __device__ __forceinline__ T coef_of(double2 c) { return c.y; }               // coef = i * c.y
-    static __device__ __forceinline__ double2 result(T coef, T acc) { return make_double2(0.0, coef * acc); }
-    static __device__ __forceinline__ T shfl_down(T v, int off) { return __shfl_down_sync(0xFFFFFFFFu, v, off); }
-};
-template <> struct Num<false> {
-    typedef double2 T;
-    static __device__ __forceinline__ T zero() { return make_double2(0.0, 0.0); }
-    static __device__ __forceinline__ T mul(T a, T b) { return cmul(a, b); }
-    static __device__ __forceinline__ T add(T a, T b) { return cadd(a, b); }
-    static __device__ __forceinline__ T from_real(double x) { return make_double2(x, 0.0); }
-    static __device__ __forceinline__ T times_i_of(double2 v) { return times_i(v); }
-    static __device__ __forceinline__ T coef_of(double2 c) { return c; }
-    static __device__ __forceinline__ double2 result(T coef, T acc) { return cmul(coef, acc); }
-    static __device__ __forceinline__ T shfl_down(T v, int off) {
-        return make_double2(__shfl_down_sync(0xFFFFFFFFu, v.x, off), __shfl_down_sync(0xFFFFFFFFu, v.y, off));
-    }
-};
-
-// Cell and weights of the Keldysh.jl grid rule for one (t_f, t_i) pair; shared by every sector / table
-// evaluated at that pair.  k = 0: both times in one cell (triangular rule).
-struct GridCell { int k; double c00, c10, c01, c11; };
-__device__ __forceinline__ GridCell grid_cell(int n, double inv_h, double t_f, double t_i) {
-    const double qf = t_f * inv_h, qi = t_i * inv_h;
-    int a = __double2int_rd(qf), b = __double2int_rd(qi);
-    a = min(max(a, 0), n - 2);
-    b = min(max(b, 0), n - 2);
-    const double w1 = qf - (double)a, w2 = qi - (double)b;
-    GridCell c;
-    c.k = a - b;
-    if (c.k == 0) { c.c00 = w1 - w2; c.c10 = c.c01 = c.c11 = 0.0; }
-    else { c.c00 = (1.0 - w1) * (1.0 - w2); c.c10 = w1 * (1.0 - w2); c.c01 = (1.0 - w1) * w2; c.c11 = w1 * w2; }
-    return c;
-}
-// The same from per-time cell indices and fractional weights computed once per backbone position.
-__device__ __forceinline__ GridCell grid_cell_from(int a, double w1, int b, double w2) {
-    GridCell c;
-    c.k = a - b;
-    if (c.k == 0) { c.c00 = w1 - w2; c.c10 = c.c01 = c.c11 = 0.0; }
-    else { c.c00 = (1.0 - w1) * (1.0 - w2); c.c10 = w1 * (1.0 - w2); c.c01 = (1.0 - w1) * w2; c.c11 = w1 * w2; }
-    return c;
-}
-// Branch-free form used by the table fill: three table indices and three coefficients,
-//   value = ck D[i0] + cp D[ip] + cm D[im]
-// (k = 0: (1 - w) D[0] + w D[1]; else (c00 + c11) D[k] + c10 D[k+1] + c01 D[k-1]); differs from the reference's
-// operation order by O(ulp), and lets the compiler overlap the loads of consecutive table slots.
-struct GridCell3 { int i0, ip, im; double ck, cp, cm; };
-__device__ __forceinline__ GridCell3 grid_cell3_from(int a, double w1, int b, double w2) {
-    GridCell3 c;
-    const int k = a - b;
-    const bool dg = (k == 0);
-    const double u1 = 1.0 - w1, u2 = 1.0 - w2, w = w1 - w2;
-    c.i0 = k; c.ip = k + 1; c.im = dg ? 0 : k - 1;
-    c.ck = dg ? 1.0 - w : fma(u1, u2, w1 * w2);
-    c.cp = dg ? w : w1 * u2;
-    c.cm = dg ? 0.0 : u1 * w2;
-    return c;
-}
-template <bool REAL>
-__device__ __forceinline__ typename Num<REAL>::T cell3_apply_i(const double2* __restrict__ D, int stride, const GridCell3& c) {
-    if constexpr (!REAL) {
-        const double2 dk = __ldg(D + (size_t)c.i0 * stride), dp = __ldg(D + (size_t)c.ip * stride), dm = __ldg(D + (size_t)c.im * stride);
-        return make_double2(-(c.ck * dk.y + c.cp * dp.y + c.cm * dm.y), c.ck * dk.x + c.cp * dp.x + c.cm * dm.x);
-    } else {
-        const double dk = __ldg(&D[(size_t)c.i0 * stride].y), dp = __ldg(&D[(size_t)c.ip * stride].y), dm = __ldg(&D[(size_t)c.im * stride].y);
-        return -(c.ck * dk + c.cp * dp + c.cm * dm);
-    }
-}
-// i * D(t_f, t_i) for a table D[k] = G(k h) with element stride `stride` (same operation order as
-// grid_interp; the real mode works on the imaginary components only).
-template <bool REAL>
-__device__ __forceinline__ typename Num<REAL>::T cell_apply_i(const double2* __restrict__ D, int stride, const GridCell& c) {
-    if constexpr (!REAL) {
-        if (c.k == 0) {
-            const double2 d0 = __ldg(D), d1 = __ldg(D + stride);
-            return make_double2(-(d0.y + c.c00 * (d1.y - d0.y)), d0.x + c.c00 * (d1.x - d0.x));
-        }
-        const double2 dk = __ldg(D + (size_t)c.k * stride), dp = __ldg(D + (size_t)(c.k + 1) * stride),
-                      dm = __ldg(D + (size_t)(c.k - 1) * stride);
-        return make_double2(-(c.c00 * dk.y + c.c10 * dp.y + c.c01 * dm.y + c.c11 * dk.y),
-                            c.c00 * dk.x + c.c10 * dp.x + c.c01 * dm.x + c.c11 * dk.x);
-    } else {
-        if (c.k == 0) {
-            const double d0 = __ldg(&D[0].y), d1 = __ldg(&D[stride].y);
-            return -(d0 + c.c00 * (d1 - d0));
-        }
-        const double dk = __ldg(&D[(size_t)c.k * stride].y), dp = __ldg(&D[(size_t)(c.k + 1) * stride].y),
-                     dm = __ldg(&D[(size_t)(c.k - 1) * stride].y);
-        return -(c.c00 * dk + c.c10 * dp + c.c01 * dm + c.c11 * dk);
-    }
-}
-
-template <bool REAL>
-__device__ __forceinline__ typename Num<REAL>::T delta_apply_i(const DevDelta& t, double t_f, double t_i) {
-    if constexpr (!REAL) {
-        return times_i(delta_eval(t, t_f, t_i));
-    } else {
-        if (t.kind == 1) {
-            const double dt = t_f - t_i, h = t.h;
-            int j = (int)floor(dt * t.inv_h);
-            j = min(max(j, 0), t.n - 2);
-            const double xa = dt - (double)j * h, xb = (double)(j + 1) * h - dt;
-            const double y0 = __ldg(&t.y[j].y), y1 = __ldg(&t.y[j + 1].y), m0 = __ldg(&t.M[j].y), m1 = __ldg(&t.M[j + 1].y);
-            const double i6h = t.inv_h * (1.0 / 6.0), h6 = h * (1.0 / 6.0), ih = t.inv_h;
-            const double ca = xa * xa * xa * i6h, cb = xb * xb * xb * i6h;
-            return -(m0 * cb + m1 * ca + (y0 * ih - m0 * h6) * xb + (y1 * ih - m1 * h6) * xa);
-        }
-        return cell_apply_i<true>(t.y, 1, grid_cell(t.n, t.inv_h, t_f, t_i));
-    }
-}
-
-// Segment products (EntryProgram::segdef): lane = table entry, loop over the samples of a range; the
-// entry's propagator slots live in registers.  Shorter segments are padded with the row's constant-one slot.
-template <int LEN, bool REAL>
-__device__ __forceinline__ void segment_products(const uint16_t* __restrict__ segdef_t, int n_seg, int out0,
-                                                 unsigned char* Tb, int row_bytes, int spb, int warp, int nw, int lane) {
-    typedef typename Num<REAL>::T T;
-    typedef Num<REAL> N;
-    constexpr int SH = REAL ? 3 : 4;
-    const int n_groups = (n_seg + 31) >> 5;
-    // tasks = (group of 32 entries) x (sample sub-range); split the samples so that every warp has work
-    int split = 1;
-    while (n_groups * split < nw && split < spb) split <<= 1;
-    const int per = spb / split;
-    for (int task = warp; task < n_groups * split; task += nw) {
-        const int g = task / split, part = task - g * split;
-        const int j = g * 32 + lane;
-        uint32_t q[LEN];
-        const uint16_t* sd = segdef_t + (size_t)g * LEN * 32 + lane;
-#pragma unroll
-        for (int i = 0; i < LEN; ++i) q[i] = (uint32_t)sd[i * 32] << SH;
-        if (j >= n_seg) continue;
-        unsigned char* row = Tb + (size_t)part * per * row_bytes;
-#pragma unroll 2
-        for (int smp = 0; smp < per; ++smp, row += row_bytes) {
-            T v = *reinterpret_cast<const T*>(row + q[0]);
-#pragma unroll
-            for (int i = 1; i < LEN; ++i) v = N::mul(v, *reinterpret_cast<const T*>(row + q[i]));
-            reinterpret_cast<T*>(row)[out0 + j] = v;
-        }
-    }
-}
-
-// ---- configuration walk ------------------------------------------------------------------------
-// Every surviving configuration of an entry is a fixed-length record (qiw_host.hpp: EntryProgram::rec2)
-// of K + order operand slots in the per-sample table: K segment products of propagators and one
-// pair-interaction factor per arc; the operator matrix elements and the topology sign
-// (-i * parity * (-1)^order, src/topology_eval.jl:431) are folded into the record's coefficient.
-//
-// Mapping: one LANE owns one configuration (its record lives in registers for the whole sample
-// block) and loops over the samples of the CTA, whose tables sit in shared memory as T[sample][slot].
-// Per factor that is one LDS feeding one multiply (real mode) or four FP64 instructions (complex).
-template <int L, bool REAL, bool PER_SAMPLE>
-__device__ __forceinline__ void config_walk(const uint32_t* __restrict__ rec_t, int g0, int g1, const unsigned char* Tb,
-                                            int row_bytes, int spb, const typename Num<REAL>::T* coefs_s, double2* red,
-                                            int nw, int warp, int lane, int S, double2* sample_out,
-                                            unsigned long long local0, unsigned long long count) {
-    typedef typename Num<REAL>::T T;
-    typedef Num<REAL> N;
-    constexpr int SH = REAL ? 3 : 4;
-    for (int g = g0; g < g1; ++g) {
-        uint32_t w[L + 1];
-        const uint32_t* rp = rec_t + (size_t)g * (L + 1) * 32 + lane;
-#pragma unroll
-        for (int q = 0; q <= L; ++q) w[q] = __ldg(rp + q * 32);
-#pragma unroll
-        for (int q = 1; q <= L; ++q) w[q] <<= SH;
-        const int s_i = (int)(w[0] >> 16);
-        const T coef = coefs_s[w[0] & 0xFFFFu];
-        const int smin = (int)__reduce_min_sync(0xFFFFFFFFu, (unsigned)s_i);
-        const int smax = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)s_i);
-        T acc0 = N::zero(), acc1 = N::zero();
-        if constexpr (PER_SAMPLE) {
-            for (int smp = 0; smp < spb; ++smp) {
-                const unsigned char* row = Tb + smp * row_bytes;
-                T va = *reinterpret_cast<const T*>(row + w[1]);
-#pragma unroll
-                for (int f = 2; f <= L; ++f) va = N::mul(va, *reinterpret_cast<const T*>(row + w[f]));
-                // qiw_eval_at_times: the evaluator's value for every sample separately
-                const double2 c = N::result(coef, va);
-                for (int s = smin; s <= smax; ++s) {
-                    double2 r = (s_i == s) ? c : make_double2(0.0, 0.0);
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) {
-                        r.x += __shfl_down_sync(0xFFFFFFFFu, r.x, off);
-                        r.y += __shfl_down_sync(0xFFFFFFFFu, r.y, off);
-                    }
-                    if (lane == 0 && local0 + smp < count) {
-                        double2* o = sample_out + (local0 + smp) * S + s;
-                        *o = cadd(*o, r);
-                    }
-                }
-            }
-        } else {
-            // four samples in flight per iteration: independent multiply chains
-            int smp = 0;
-            for (; smp + 3 < spb; smp += 4) {
-                const unsigned char* r0 = Tb + smp * row_bytes;
-                const unsigned char* r1 = r0 + row_bytes;
-                const unsigned char* r2 = r1 + row_bytes;
-                const unsigned char* r3 = r2 + row_bytes;
-                T va = *reinterpret_cast<const T*>(r0 + w[1]);
-                T vb = *reinterpret_cast<const T*>(r1 + w[1]);
-                T vc = *reinterpret_cast<const T*>(r2 + w[1]);
-                T vd = *reinterpret_cast<const T*>(r3 + w[1]);
-#pragma unroll
-                for (int f = 2; f <= L; ++f) {
-                    va = N::mul(va, *reinterpret_cast<const T*>(r0 + w[f]));
-                    vb = N::mul(vb, *reinterpret_cast<const T*>(r1 + w[f]));
-                    vc = N::mul(vc, *reinterpret_cast<const T*>(r2 + w[f]));
-                    vd = N::mul(vd, *reinterpret_cast<const T*>(r3 + w[f]));
-                }
-                acc0 = N::add(acc0, N::add(va, vc));
-                acc1 = N::add(acc1, N::add(vb, vd));
-            }
-            for (; smp < spb; ++smp) {
-                const unsigned char* r0 = Tb + smp * row_bytes;
-                T va = *reinterpret_cast<const T*>(r0 + w[1]);
-#pragma unroll
-                for (int f = 2; f <= L; ++f) va = N::mul(va, *reinterpret_cast<const T*>(r0 + w[f]));
-                acc0 = N::add(acc0, va);
-            }
-            // sum over the lanes' configurations, separately for every initial sector present
-            const double2 c = N::result(coef, N::add(acc0, acc1));
-            for (int s = smin; s <= smax; ++s) {
-                double2 r = (s_i == s) ? c : make_double2(0.0, 0.0);
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    if constexpr (!REAL) r.x += __shfl_down_sync(0xFFFFFFFFu, r.x, off);
-                    r.y += __shfl_down_sync(0xFFFFFFFFu, r.y, off);
-                }
-                if (lane == 0) red[s * nw + warp] = cadd(red[s * nw + warp], r);
-            }
-        }
-    }
-}
-
-// Paired records (EntryProgram::rec_pair): two configurations with identical pair-interaction operands and
-// initial sector,  prod(Delta) * (coefA * prod(segA) + coefB * prod(segB)):  ND + 2K operands instead of 2 (ND + K).
-template <int ND, int K, bool REAL>
-__device__ __forceinline__ void pair_walk(const uint32_t* __restrict__ rec_t, int g0, int g1, const unsigned char* Tb,
-                                          int row_bytes, int spb, const typename Num<REAL>::T* coefs_s, double2* red,
-                                          int nw, int warp, int lane) {
-    typedef typename Num<REAL>::T T;
-    typedef Num<REAL> N;
-    constexpr int SH = REAL ? 3 : 4;
-    constexpr int RL = 2 + 2 * K + ND;
-    for (int g = g0; g < g1; ++g) {
-        uint32_t w[RL];
-        const uint32_t* rp = rec_t + (size_t)g * RL * 32 + lane;
-#pragma unroll
-        for (int q = 0; q < RL; ++q) w[q] = __ldg(rp + q * 32);
-#pragma unroll
-        for (int q = 2; q < RL; ++q) w[q] <<= SH;
-        const int s_i = (int)(w[0] >> 16);
-        const T coefA = coefs_s[w[0] & 0xFFFFu], coefB = coefs_s[w[1] & 0xFFFFu];
-        const int smin = (int)__reduce_min_sync(0xFFFFFFFFu, (unsigned)s_i);
-        const int smax = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)s_i);
-        T accA = N::zero(), accB = N::zero();
-        // four samples in flight per iteration (spb is a power of two; blocks smaller than 4 take the scalar loop)
-        int smp = 0;
-        for (; smp + 3 < spb; smp += 4) {
-            const unsigned char* row = Tb + smp * row_bytes;
-            T d[4], sa[4], sb[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const unsigned char* r = row + u * row_bytes;
-                d[u] = *reinterpret_cast<const T*>(r + w[2 + 2 * K]);
-                sa[u] = *reinterpret_cast<const T*>(r + w[2]);
-                sb[u] = *reinterpret_cast<const T*>(r + w[2 + K]);
-            }
-#pragma unroll
-            for (int f = 1; f < ND; ++f)
-#pragma unroll
-                for (int u = 0; u < 4; ++u) d[u] = N::mul(d[u], *reinterpret_cast<const T*>(row + u * row_bytes + w[2 + 2 * K + f]));
-#pragma unroll
-            for (int f = 1; f < K; ++f)
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    sa[u] = N::mul(sa[u], *reinterpret_cast<const T*>(row + u * row_bytes + w[2 + f]));
-                    sb[u] = N::mul(sb[u], *reinterpret_cast<const T*>(row + u * row_bytes + w[2 + K + f]));
-                }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                accA = N::add(accA, N::mul(d[u], sa[u]));
-                accB = N::add(accB, N::mul(d[u], sb[u]));
-            }
-        }
-        for (; smp < spb; ++smp) {
-            const unsigned char* row = Tb + smp * row_bytes;
-            T d = *reinterpret_cast<const T*>(row + w[2 + 2 * K]);
-#pragma unroll
-            for (int f = 1; f < ND; ++f) d = N::mul(d, *reinterpret_cast<const T*>(row + w[2 + 2 * K + f]));
-            T sa = *reinterpret_cast<const T*>(row + w[2]);
-            T sb = *reinterpret_cast<const T*>(row + w[2 + K]);
-#pragma unroll
-            for (int f = 1; f < K; ++f) {
-                sa = N::mul(sa, *reinterpret_cast<const T*>(row + w[2 + f]));
-                sb = N::mul(sb, *reinterpret_cast<const T*>(row + w[2 + K + f]));
-            }
-            accA = N::add(accA, N::mul(d, sa));
-            accB = N::add(accB, N::mul(d, sb));
-        }
-        const double2 c = cadd(N::result(coefA, accA), N::result(coefB, accB));
-        for (int s = smin; s <= smax; ++s) {
-            double2 r = (s_i == s) ? c : make_double2(0.0, 0.0);
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                if constexpr (!REAL) r.x += __shfl_down_sync(0xFFFFFFFFu, r.x, off);
-                r.y += __shfl_down_sync(0xFFFFFFFFu, r.y, off);
-            }
-            if (lane == 0) red[s * nw + warp] = cadd(red[s * nw + warp], r);
-        }
-    }
-}
-
-template <bool REAL>
-__device__ __forceinline__ void pair_dispatch(int nd, int K, const uint32_t* rec_t, int g0, int g1, const unsigned char* Tb,
-                                              int row_bytes, int spb, const typename Num<REAL>::T* coefs_s, double2* red,
-                                              int nw, int warp, int lane) {
-#define QIW_PC(D_, K_) case (D_ * 8 + K_): pair_walk<D_, K_, REAL>(rec_t, g0, g1, Tb, row_bytes, spb, coefs_s, red, nw, warp, lane); break;
-#define QIW_PK(D_) QIW_PC(D_, 1) QIW_PC(D_, 2) QIW_PC(D_, 3) QIW_PC(D_, 4)
-    switch (nd * 8 + K) {
-        QIW_PK(1) QIW_PK(2) QIW_PK(3) QIW_PK(4) QIW_PK(5) QIW_PK(6) QIW_PK(7) QIW_PK(8)
-        default: break;
-    }
-#undef QIW_PK
-#undef QIW_PC
-}
-
-// Record lengths: K + order operands, K <= 4 segments, order <= 8.
-template <bool REAL, bool PER_SAMPLE>
-__device__ __forceinline__ void walk_dispatch(int L, const uint32_t* rec_t, int g0, int g1, const unsigned char* Tb,
-                                              int row_bytes, int spb, const typename Num<REAL>::T* coefs_s, double2* red,
-                                              int nw, int warp, int lane, int S, double2* so, unsigned long long local0,
-                                              unsigned long long count) {
-#define QIW_CASE(N_) case N_: config_walk<N_, REAL, PER_SAMPLE>(rec_t, g0, g1, Tb, row_bytes, spb, coefs_s, red, nw, warp, lane, S, so, local0, count); break;
-    switch (L) {
-        QIW_CASE(1) QIW_CASE(2) QIW_CASE(3) QIW_CASE(4) QIW_CASE(5) QIW_CASE(6) QIW_CASE(7) QIW_CASE(8)
-        QIW_CASE(9) QIW_CASE(10) QIW_CASE(11) QIW_CASE(12)
-        default: break;
-    }
-#undef QIW_CASE
-}
-
-// ---- fused tail of the step kernel ---------------------------------------------------------------
-// out = weight * (-i)^d * Jacobian * sum(rows): the factors of contour_integral / qmc_integral
-// (src/qmc_integrate.jl:497-507,565-569,597-612) and of the simplex maps (:46,458-463).
-__device__ __forceinline__ double simplex_volume(int d, double edge) {
-    // prod_{i<=d} edge / i (src/qmc_integrate.jl:46) with the reciprocals tabulated: FP64 division costs
-    // hundreds of cycles and this sits on the critical path of every step's tail
-    const double inv[17] = {1.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10,
-                            1.0 / 11, 1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16};
-    double v = 1.0;
-#pragma unroll
-    for (int i = 1; i <= 16; ++i)
-        if (i <= d) v *= edge * inv[i];
-    return v;
-}
-
-__device__ __forceinline__ double entry_scale(const DevEntry& e, const DevEntryDyn& dy, double t_i, double t_w, double t_f) {
-    if (e.exact) return dy.weight;
-    const double jac = (e.mode == 0) ? simplex_volume(e.D, t_f - t_i)
-                                     : simplex_volume(e.d_before, t_w - t_i) * simplex_volume(e.d_after, t_f - t_w);
-    const double dir = (e.order & 1) ? -1.0 : 1.0;   // (-i)^(2 order)
-    return dir * jac * dy.weight;
-}
-
-// Executed by the last CTA of a step launch: every (entry, sector) sum runs over the partial rows in
-// fixed order, so the result does not depend on which CTA happens to be last.  Optionally followed by
-// set_ppgf!(P, tau_f, result) and normalize!(P, tau_f) (src/ppgf.jl:495-504,646-668).
-__device__ void fused_tail(const StepParams& pp, double t_i, double t_w, double t_f, int pitch) {
-    StepParams p = pp;
-    const int S = p.S, n_out = p.n_call_entries * S;
-    p.partials += (size_t)blockIdx.z * gridDim.y * gridDim.x * S;   // this time triple's rows and results
-    p.out += (size_t)blockIdx.z * n_out;
-    // four lanes per (entry, sector) output: lane g adds rows g, g+4, ... in order, then the four partial sums
-    // are combined in a fixed butterfly — the same operation order whichever CTA runs the tail
-    for (int o0 = 0; o0 < n_out; o0 += (int)blockDim.x / 4) {
-        const int o = o0 + (int)threadIdx.x / 4, g = (int)threadIdx.x & 3;
-        double2 v = make_double2(0.0, 0.0);
-        double scale = 0.0;
-        int oi = 0;
-        if (o < n_out) {
-            const int i = o / S, s = o - i * S;
-            const DevEntryDyn& dy = p.dyn[i];
-            const size_t row0 = (size_t)dy.item0 * pitch, nrows = (size_t)dy.n_items * pitch;
-            for (size_t r = g; r < nrows; r += 4) v = cadd(v, __ldcg(p.partials + (row0 + r) * S + s));
-            if (g == 0) scale = entry_scale(p.entries[dy.entry], dy, t_i, t_w, t_f);
-            oi = dy.out_index * S + s;
-        }
-        v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, 1); v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, 1);
-        v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, 2); v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, 2);
-        if (o < n_out && g == 0) p.out[oi] = cscale(scale, v);
-    }
-    if (p.peer_ranks > 1) {
-        // ---- all-reduce over peer memory (replaces all_reduce!, src/mpi.jl:104-127) ----
-        // Low-latency protocol: every 8-byte store carries 4 bytes of payload and the 4-byte sequence number of
-        // this collective, so the receiver needs no separate flag and the sender no system-wide fence: a word is
-        // valid as soon as its flag matches (8-byte stores are single transactions on NVLink).  Each double
-        // travels as two such words.  Buffers alternate with the parity of the sequence number: a slot is
-        // rewritten two collectives later, after every peer has provably finished reading it.
-        __syncthreads();
-        const int par = (int)(p.peer_seq & 1ull);
-        const unsigned int seq32 = (unsigned int)(p.peer_seq % 0xFFFFFFFFull) + 1u;   // never 0 (the mailbox starts zeroed)
-        const size_t my_slot = kPeerFlagBytes + ((size_t)p.peer_rank * 2 + par) * kPeerSlotBytes;
-        const int n_dbl = 2 * n_out, n_words = 2 * n_dbl;
-        const double* outd = reinterpret_cast<const double*>(p.out);
-        for (int k = threadIdx.x; k < n_words; k += blockDim.x) {
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(outd[k >> 1]);
-            const unsigned int half = (k & 1) ? (unsigned int)(bits >> 32) : (unsigned int)bits;
-            const uint2 wd = make_uint2(half, seq32);
-            for (int q = 0; q < p.peer_ranks; ++q) {
-                if (q == p.peer_rank) continue;
-                uint2* dst = reinterpret_cast<uint2*>(p.peer_mail[q] + my_slot) + k;
-                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(wd.x), "r"(wd.y) : "memory");
-            }
-        }
-        // receive: poll every word until its flag shows this collective, add the contributions in rank order
-        const unsigned char* base = p.peer_mail[p.peer_rank] + kPeerFlagBytes;
-        const unsigned long long t0 = globaltimer_ns();
-        for (int j = threadIdx.x; j < n_dbl; j += blockDim.x) {
-            double v = 0.0;
-            for (int q = 0; q < p.peer_ranks; ++q) {
-                if (q == p.peer_rank) { v += outd[j]; continue; }
-                const uint2* src = reinterpret_cast<const uint2*>(base + ((size_t)q * 2 + par) * kPeerSlotBytes) + 2 * j;
-                uint2 lo, hi;
-                bool ok = true;
-                do {
-                    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo.x), "=r"(lo.y) : "l"(src) : "memory");
-                    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hi.x), "=r"(hi.y) : "l"(src + 1) : "memory");
-                    if ((lo.y != seq32 || hi.y != seq32) && globaltimer_ns() - t0 > 10000000000ull) { *p.peer_status = 1; ok = false; break; }   // 10 s
-                } while (lo.y != seq32 || hi.y != seq32);
-                if (ok) v += __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | (unsigned long long)lo.x));
-            }
-            reinterpret_cast<double*>(p.out)[j] = v;   // element j is read and written by this thread only
-        }
-    }
-    if (p.finish_k_f < 0) return;
-    __syncthreads();
-    __shared__ double lambda_s;
-    const int bsize = p.bsize, k_f = p.finish_k_f;
-    double2* P = p.finish_P;
-    for (int el = threadIdx.x; el < bsize; el += blockDim.x) {
-        double2 v = make_double2(0.0, 0.0);
-        for (int j = 0; j < p.n_call_entries; ++j) {
-            const double2 c = p.out[(size_t)j * bsize + el];
-            v = cadd(v, c);
-            if (p.finish_hist) p.finish_hist[(size_t)j * bsize + el] = c;
-        }
-        P[(size_t)k_f * bsize + el] = v;
-    }
-    __syncthreads();
-    if (!p.finish_normalize) return;
-    if (threadIdx.x == 0) {
-        double pmax = -1.0e300;
-        for (int i = 0; i < p.finish_n_diag; ++i) pmax = fmax(pmax, -P[(size_t)k_f * bsize + p.finish_diag[i]].y);
-        lambda_s = log(pmax) / ((double)k_f * p.h);
-    }
-    __syncthreads();
-    const double lambda = lambda_s;
-    for (int idx = threadIdx.x; idx < p.n_tau * bsize; idx += blockDim.x) {
-        const int k = idx / bsize;
-        const double f = exp(-((double)k * p.h) * lambda);
-        P[idx] = cscale(f, P[idx]);
-    }
-}
-
-// ---- the step kernel (scalar models: every sector block is 1x1) ------------------------------
-
-// PAIRS: the launch contains entries with paired records (their walk code is only in this instantiation, so
-// that the common orders <= 4 case keeps a small instruction footprint — the N = 2^10 step is latency-bound).
-template <bool REAL, bool PER_SAMPLE, bool PAIRS>
-__global__ void __launch_bounds__(256, 3) scalar_step_kernel(const StepParams p) {
-    typedef typename Num<REAL>::T T;
-    typedef Num<REAL> N;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // let the next step's grid start as soon as every CTA of this one is running (it waits before it touches P)
-    asm volatile("griddepcontrol.launch_dependents;");
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, nthr = blockDim.x;
-    const WorkItem it = p.items[blockIdx.y];
-    const DevEntry& e = p.entries[it.entry];
-    const DevEntryDyn& dy = p.dyn[it.slot];
-    const int S = p.S, D = e.D, n_nodes = e.n_nodes, nP = e.nP, nD = e.nD, nSeg = e.nSeg;
-    const int n_slots = nP + nD + nSeg + 1;   // + the constant-one slot that pads short segment products
-    const int d_after = e.d_after;
-    const int spb = p.spb, spb_sh = p.spb_log2, spb_mask = spb - 1;   // spb is a power of two
-    // shared memory carve-up (sizes fixed per launch from the largest entry, see host):
-    // T[spb samples][row] with an odd row pitch (in operand units) so that the lanes' stores during
-    // the fill hit different banks
-    const int row_bytes = (n_slots | 1) * (int)sizeof(T);
-    unsigned char* Tb = smem_raw;                                                            // [spb][max_row]
-    double2* red = reinterpret_cast<double2*>(smem_raw + (size_t)p.max_slots * spb * sizeof(T));   // [S][nw]
-    // The small per-sample arrays are sized for the launch's largest entry (p.max_nodes1 = positions + 1), and the
-    // roots pw[D][32] — dead once the times exist — live at the start of the table T, which is filled afterwards:
-    // 63 instead of 73 KB per CTA for the README model, so three CTAs leave 60 KB of the SM to L1 instead of 28.
-    double* times = reinterpret_cast<double*>(red + (size_t)S * nw);             // [max_nodes1][32]
-    double* pw = reinterpret_cast<double*>(Tb);                                  // [D][32], aliases T (phases 1-2 only)
-    double* cellw = times + p.max_nodes1 * 32;                                   // [max_nodes1][32] fractional cell weight
-    int* cella = reinterpret_cast<int*>(cellw + p.max_nodes1 * 32);              // [max_nodes1][32] grid cell of each time
-    int* okflag = cella + p.max_nodes1 * 32;                                     // [32]
-    int4* dslots_s = reinterpret_cast<int4*>(okflag + 32);                       // [max_dslots]
-    T* coefs_s = reinterpret_cast<T*>(dslots_s + p.max_dslots);                  // [max_coefs + 1]
-    const int seg_stride = e.seg_stride;
-    for (int c = threadIdx.x; c < nD; c += nthr) dslots_s[c] = e.dslots[c];
-    for (int c = threadIdx.x; c < S * nw; c += nthr) red[c] = make_double2(0.0, 0.0);
-    for (int c = threadIdx.x; c <= e.n_coefs; c += nthr)
-        coefs_s[c] = (c < e.n_coefs) ? N::coef_of(e.coefs[c]) : N::zero();   // last: padding records
-
-    double t_i = p.t_i, t_w = p.t_w, t_f = p.t_f;
-    // batched evaluation: blockIdx.z selects one (t_i, t_w, t_f) triple of the call
-    if (p.times_dev) { const double* tz = p.times_dev + 3 * blockIdx.z; t_i = tz[0]; t_w = tz[1]; t_f = tz[2]; }
-    const double lo_after = (e.mode == 0) ? t_i : t_w, len_after = t_f - lo_after;
-    const double len_before = t_w - t_i;
-
-    // randomised qMC: blockIdx.z selects one of several scrambled sequences (no root cache then)
-    const uint32_t* __restrict__ sm = dy.sobol + (size_t)blockIdx.z * p.sobol_z_stride;
-    const unsigned long long count = dy.count;
-    const int n_sb = (int)((count + (unsigned long long)spb - 1ull) / (unsigned long long)spb);
-
-    // this warp's share of the entry's configuration groups (32 records per group): all records for the
-    // per-sample evaluation, pairs + leftovers for the summing walk
-    int g0 = 0, g1 = 0, pg0 = 0, pg1 = 0;
-    if (warp < it.n_chunks) {
-        const long long c = it.chunk0 + warp, nct = it.n_chunks_total;
-        const long long ng = PAIRS ? e.n_groups_left : e.n_groups, npg = PAIRS ? e.n_groups_pair : 0;
-        g0 = (int)(c * ng / nct);
-        g1 = (int)((c + 1) * ng / nct);
-        // pairs are dealt in the opposite direction so that a warp short on pairs gets more leftovers
-        pg0 = (int)((nct - 1 - c) * npg / nct);
-        pg1 = (int)((nct - c) * npg / nct);
-    }
-
-    // optional per-CTA timeline (diagnostics; compiled in only with -DQIW_TRACE_BUILD because
-    // reading %globaltimer costs microseconds): start / tables ready / walk done / end
-#ifdef QIW_TRACE_BUILD
-    unsigned long long* trace = p.trace ? p.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 12 : nullptr;
-#else
-    constexpr unsigned long long* trace = nullptr;
-#endif
-    if (trace && threadIdx.x == 0) {
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        trace[7] = globaltimer_ns();   // one wall-clock stamp; phase durations use the SM cycle counter
-        trace[0] = clock64(); trace[4] = smid; trace[5] = it.entry; trace[6] = (unsigned long long)(g1 - g0);
-    }
-
-    for (int sb = blockIdx.x; sb < n_sb; sb += gridDim.x) {
-        const unsigned long long local0 = (unsigned long long)sb * (unsigned long long)spb;
-
-        // -- 1. Sobol coordinates and the independent roots x_j^(1/(remaining dims)) ----------
-        //       The roots depend only on (entry, Sobol sequence, sample), not on the time step: when the
-        //       host provides a cache they are computed once per run and re-read afterwards.
-        if ((int)threadIdx.x < spb) okflag[threadIdx.x] = (local0 + threadIdx.x < count) ? 1 : 0;
-        if (p.explicit_times == nullptr) {
-            double* uc = p.sobol_z_stride ? nullptr : dy.ucache;
-            for (int task = threadIdx.x; task < D * spb; task += nthr) {
-                const int j = task >> spb_sh, smp = task & spb_mask;
-                const unsigned long long local = local0 + smp;
-                const bool active = local < count;
-                double r;
-                if (uc && dy.ucache_valid) {
-                    r = active ? uc[(size_t)j * count + local] : 0.0;
-                } else {
-                    const uint32_t xi = sobol_coord(sm + j * 32, __ldg(sm + D * 32 + j), (uint32_t)(dy.start + local));
-                    const double x = (double)xi * 2.3283064365386963e-10;  // ldexp(x, -32), exact
-                    const int den = (j < d_after) ? (d_after - j) : (D - j);
-                    r = (den == 1) ? x : pow(x, 1.0 / (double)den);
-                    if (uc && active && it.chunk0 == 0) uc[(size_t)j * count + local] = r;
-                }
-                pw[j * 32 + smp] = r;
-            }
-        }
-        __syncthreads();
-        if (trace && threadIdx.x == 0) trace[8] = clock64();
-
-        // -- 2. ordered times of every backbone position: thread = (position, sample).  The running
-        //       product u_j = ((r_0 r_1) r_2) ... r_j is re-evaluated from the start of its simplex so that
-        //       positions are independent (same operation order as the sequential map, bit-identical).
-        for (int task = threadIdx.x; task < n_nodes * spb; task += nthr) {
-            const int pos = 1 + (task >> spb_sh), smp = task & spb_mask;
-            const int src = e.pos_src[pos];
-            double t;
-            if (src == -1) t = t_i;
-            else if (src == -2) t = t_w;
-            else if (src == -3) t = t_f;
-            else if (p.explicit_times) {
-                t = (local0 + smp < count) ? p.explicit_times[(local0 + smp) * D + src] : 0.0;
-            } else {
-                const int j0 = (src < d_after) ? 0 : d_after;
-                double u = pw[j0 * 32 + smp];
-                for (int j = j0 + 1; j <= src; ++j) u = __dmul_rn(u, pw[j * 32 + smp]);
-                if (src < d_after) t = __dadd_rn(__dmul_rn(u, len_after), lo_after);
-                else t = __dadd_rn(__dmul_rn(u, len_before), t_i);
-                if (!(t >= 0.0)) okflag[smp] = 0;   // all(refs .>= 0) (src/qmc_integrate.jl:608)
-            }
-            times[pos * 32 + smp] = t;
-            // grid cell and weight of this time on the P grid (Keldysh.jl rule, shared by all slots)
-            const double q = t * p.inv_h;
-            const int a = min(max(__double2int_rd(q), 0), p.n_tau - 2);
-            cella[pos * 32 + smp] = a;
-            cellw[pos * 32 + smp] = q - (double)a;
-        }
-        __syncthreads();
-        if (trace && threadIdx.x == 0) trace[9] = clock64();
-
-        // -- 3. per-sample tables.  Propagators: thread = (backbone interval, sample) evaluates all
-        //       sectors; pair interactions: thread = (slot, sample).  Discarded samples
-        //       (src/qmc_integrate.jl:503,608) and samples past the range get zero rows.
-        {
-            const int nI = n_nodes - 1;
-            // pair interactions first: they do not depend on the bold propagators, so in the device-resident
-            // loop this part (like everything above) overlaps the previous step's tail (see below)
-            if (p.tables_on_grid) {   // every Delta table is a plain grid function on the P grid: branch-free, cells reused
-#pragma unroll 4
-                for (int task = threadIdx.x; task < nD * spb; task += nthr) {
-                    const int q = task >> spb_sh, smp = task & spb_mask;
-                    const int4 ds = dslots_s[q];
-                    const int ih = ds.y * 32 + smp;
-                    const int it2 = (times[ds.x * 32 + smp] <= times[ih]) ? ih : ds.x * 32 + smp;   // clamp (:407-410)
-                    const DevDelta& dt = p.deltas_inline[ds.z];
-                    const T val = cell3_apply_i<REAL>(dt.y, 1, grid_cell3_from(cella[it2], cellw[it2], cella[ih], cellw[ih]));
-                    reinterpret_cast<T*>(Tb + smp * row_bytes)[nP + q] = okflag[smp] ? val : N::zero();
-                }
-            } else {
-                for (int task = threadIdx.x; task < nD * spb; task += nthr) {
-                    const int q = task >> spb_sh, smp = task & spb_mask;
-                    const bool ok = okflag[smp] != 0;
-                    T* myrow = reinterpret_cast<T*>(Tb + smp * row_bytes);
-                    const int4 ds = dslots_s[q];
-                    const double th = times[ds.y * 32 + smp];
-                    double tt = times[ds.x * 32 + smp];
-                    if (tt < th) tt = th;                       // :407-410
-                    const DevDelta& dt = ds.z < kInlineTables ? p.deltas_inline[ds.z] : p.deltas[ds.z];
-                    T val;
-                    if (dt.kind == 0 && dt.n == p.n_tau && dt.inv_h == p.inv_h) {   // table on the P grid: reuse the cells
-                        const int ih = ds.y * 32 + smp, it2 = (tt == th) ? ih : ds.x * 32 + smp;
-                        val = cell_apply_i<REAL>(dt.y, 1, grid_cell_from(cella[it2], cellw[it2], cella[ih], cellw[ih]));
-                    } else {
-                        val = delta_apply_i<REAL>(dt, tt, th);
-                    }
-                    myrow[nP + q] = ok ? val : N::zero();
-                }
-            }
-            // Programmatic dependent launch: this grid may have been started while the previous step's grid
-            // was still finishing.  Everything up to here used only data no kernel writes; the P table, the
-            // partial-sum rows and the arrival counter belong to the previous grid until it has completed.
-            asm volatile("griddepcontrol.wait;" ::: "memory");
-            for (int task = threadIdx.x; task < nI * spb; task += nthr) {
-                const int q = task >> spb_sh, smp = task & spb_mask;
-                const bool ok = okflag[smp] != 0;
-                T* myrow = reinterpret_cast<T*>(Tb + smp * row_bytes);
-                {
-                    const double ta = times[(q + 1) * 32 + smp];
-                    double tb = times[(q + 2) * 32 + smp];
-                    if (tb < ta) tb = ta;                       // src/topology_eval.jl:362-364
-                    if (q == 0) myrow[n_slots - 1] = N::from_real(1.0);
-                    if (e.mode == 0) {
-                        for (int s = 0; s < S; ++s) {           // bare: i * (-i) exp(-dt (E + lambda))
-                            const T val = N::from_real(exp(-(tb - ta) * __ldg(p.E + s)));
-                            myrow[q * S + s] = ok ? val : N::zero();
-                        }
-                    } else {
-                        const bool sw = times[(q + 2) * 32 + smp] < ta;   // clamped: both ends in the earlier time's cell
-                        const int ia = (q + 1) * 32 + smp, ib = sw ? ia : ia + 32;
-                        const GridCell3 cell = grid_cell3_from(cella[ib], cellw[ib], cella[ia], cellw[ia]);
-#pragma unroll 4
-                        for (int s = 0; s < S; ++s) {
-                            const T val = cell3_apply_i<REAL>(p.P + s, p.bsize, cell);
-                            myrow[q * S + s] = ok ? val : N::zero();
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        if (trace && threadIdx.x == 0) trace[10] = clock64();
-
-        // -- 4. segment products -----------------------------------------------------------------------
-        switch (seg_stride) {
-#define QIW_SEG(N_) case N_: segment_products<N_, REAL>(e.segdef, nSeg, nP + nD, Tb, row_bytes, spb, warp, nw, lane); break;
-            QIW_SEG(1) QIW_SEG(2) QIW_SEG(3) QIW_SEG(4) QIW_SEG(5) QIW_SEG(6) QIW_SEG(7) QIW_SEG(8) QIW_SEG(9)
-#undef QIW_SEG
-            default: break;
-        }
-        __syncthreads();
-        if (trace && threadIdx.x == 0) trace[1] = clock64();
-
-        // -- 5. this warp's configurations -----------------------------------------------------
-        if constexpr (PAIRS) {
-            if (pg0 < pg1) pair_dispatch<REAL>(e.order, e.K, e.records_pair, pg0, pg1, Tb, row_bytes, spb, coefs_s, red, nw, warp, lane);
-        }
-        if (g0 < g1) {
-            walk_dispatch<REAL, PER_SAMPLE>(e.L2, PAIRS ? e.records_left : e.records, g0, g1, Tb, row_bytes, spb, coefs_s, red,
-                                            nw, warp, lane, S, p.per_sample_out, local0, count);
-        }
-        __syncthreads();
-        if (trace && threadIdx.x == 0) trace[2] = clock64();
-    }
-
-    if constexpr (PER_SAMPLE) return;
-
-    // -- 6. CTA result: warps summed in fixed order (CTAs without a sample block have not waited yet) --
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (warp == 0) {
-        // one load per lane and a fixed butterfly over the warps' sums instead of a chain of dependent loads
-        // (the shared-memory pipe is busy with the other CTAs' walks at this point); nw is a power of two <= 8
-        const int per = 32 / nw;                       // sectors per pass
-        for (int s0 = 0; s0 < S; s0 += per) {
-            const int s = s0 + lane / nw;
-            double2 v = (s < S) ? red[s * nw + (lane % nw)] : make_double2(0.0, 0.0);
-            for (int off = nw >> 1; off > 0; off >>= 1) {
-                v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, off);
-                v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, off);
-            }
-            if (s < S && (lane % nw) == 0)
-                p.partials[((size_t)blockIdx.z * gridDim.y * gridDim.x + (size_t)it.partial0 * gridDim.x + blockIdx.x) * S + s] = v;
-        }
-    }
-    if (trace && threadIdx.x == 0) trace[3] = clock64();
-
-    // -- 7. fused tail: the last CTA to arrive reduces all partial sums (and updates P) ---------------
-    if (p.done_counter) {
-        __shared__ int is_last;
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned ticket = atomicAdd(p.done_counter + blockIdx.z, 1u);
-            is_last = (ticket == gridDim.x * gridDim.y - 1u) ? 1 : 0;
-        }
-        __syncthreads();
-        if (!is_last) return;
-        __threadfence();
-        fused_tail(p, t_i, t_w, t_f, (int)gridDim.x);
-        if (threadIdx.x == 0) p.done_counter[blockIdx.z] = 0u;
-        if (trace && threadIdx.x == 0) trace[11] = clock64();
-    }
-}
-
-}  // namespace qiw
-
-namespace qiw {
 
 // ---- deterministic reduction of the per-CTA partial sums -------------------------------------
 // One CTA per entry of the call; rows of an entry are consecutive.
@@ -943,34 +95,6 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) 
 }
 
 // ---- host-callable launchers -----------------------------------------------------------------
-
-template <bool REAL, bool PER_SAMPLE, bool PAIRS>
-static cudaError_t launch_scalar_t(const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(scalar_step_kernel<REAL, PER_SAMPLE, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    // programmatic dependent launch: consecutive step kernels of a stream may overlap prologue and tail
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = p.allow_overlap ? 1 : 0;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, scalar_step_kernel<REAL, PER_SAMPLE, PAIRS>, p);
-}
-
-// `real_mode`: every table and coefficient in use has been verified purely imaginary by the host.
-// `pairs`: some entry of the launch has paired records (then every entry is walked as pairs + leftovers).
-cudaError_t launch_scalar_step(bool real_mode, bool pairs, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    if (p.per_sample_out) {
-        return real_mode ? launch_scalar_t<true, true, false>(p, grid, threads, smem, st) : launch_scalar_t<false, true, false>(p, grid, threads, smem, st);
-    }
-    if (pairs) return real_mode ? launch_scalar_t<true, false, true>(p, grid, threads, smem, st) : launch_scalar_t<false, false, true>(p, grid, threads, smem, st);
-    return real_mode ? launch_scalar_t<true, false, false>(p, grid, threads, smem, st) : launch_scalar_t<false, false, false>(p, grid, threads, smem, st);
-}
 
 cudaError_t launch_reduce(const DevEntryDyn* dyn, const DevEntry* entries, const double2* partials, int pitch, int S,
                           double t_i, double t_w, double t_f, double2* out, int n_entries, cudaStream_t st) {

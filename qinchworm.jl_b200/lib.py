@@ -62,7 +62,7 @@ _SIGNATURES = {
     "qiw_entry_program": (C.c_int, [C.c_void_p, C.c_int32, i64p, C.POINTER(C.c_uint64), i64p, u32p, i64p, f64p,
                                     i64p, i32p, i32p, i32p]),
     "qiw_entry_records": (C.c_int, [C.c_void_p, C.c_int32, i32p, u32p, C.POINTER(C.c_uint16)]),
-    "qiw_entry_pair_records": (C.c_int, [C.c_void_p, C.c_int32, i32p, u32p, u32p]),
+    "qiw_entry_lane_program": (C.c_int, [C.c_void_p, C.c_int32, i32p, i32p, u32p, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)]),
     "qiw_entry_walk_units": (C.c_int, [C.c_void_p, C.c_int32, i64p, i64p, u32p, u32p]),
     "qiw_eval": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int32, i32p, u32p, u32p,
                            C.c_uint64, f64p]),
@@ -301,15 +301,20 @@ class Context:
         return dict(K=K, L2=L2, n_leaves=nl, nSeg=nseg, seg_stride=stride, nP=nP, nD=nD, rec2=rec2[:nl],
                     segdef=segdef[:nseg])
 
-    def entry_pair_records(self, entry_id):
-        """Paired configuration records of a compiled entry (qiw_entry_pair_records)."""
-        info = np.zeros(4, dtype=np.int32)
-        self._ck(self.L.qiw_entry_pair_records(self.h, entry_id, _ptr(info, i32p), None, None))
-        npair, lp, nleft, ll = (int(x) for x in info)
-        rp = np.zeros((max(npair, 1), lp), dtype=np.uint32)
-        rl = np.zeros((max(nleft, 1), ll), dtype=np.uint32)
-        self._ck(self.L.qiw_entry_pair_records(self.h, entry_id, _ptr(info, i32p), _ptr(rp, u32p), _ptr(rl, u32p)))
-        return dict(rec_pair=rp[:npair], rec_left=rl[:nleft])
+    def entry_lane_program(self, entry_id):
+        """Lane program of a compiled entry (qiw_entry_lane_program): what the step kernel executes."""
+        info = np.zeros(8, dtype=np.int32)
+        self._ck(self.L.qiw_entry_lane_program(self.h, entry_id, _ptr(info, i32p), None, None, None, None))
+        nsec, nit, nseg, stride, K, order, seg0, cost = (int(x) for x in info)
+        sections = np.zeros((max(nsec, 1), 4), dtype=np.int32)
+        items = np.zeros(max(nit, 1), dtype=np.uint32)
+        segdef = np.zeros((max(nseg, 1), stride), dtype=np.uint16)
+        seg_coef = np.zeros(max(nseg, 1), dtype=np.uint16)
+        u16p = C.POINTER(C.c_uint16)
+        self._ck(self.L.qiw_entry_lane_program(self.h, entry_id, _ptr(info, i32p), _ptr(sections, i32p), _ptr(items, u32p),
+                                               segdef.ctypes.data_as(u16p), seg_coef.ctypes.data_as(u16p)))
+        return dict(sections=sections[:nsec], items=items[:nit], segdef=segdef[:nseg], seg_coef=seg_coef[:nseg],
+                    K=K, order=order, seg0=seg0, cost=cost, seg_stride=stride)
 
     def entry_walk_units(self, entry_id):
         """Walk units of a compiled entry of a sector-block model (qiw_entry_walk_units)."""
@@ -388,7 +393,7 @@ class Context:
                                          _ptr(hist.view(np.float64), f64p) if want_contribs else None))
         return hist
 
-    PROFILE_CLASSES = ("step_complex", "step_real", "unused2", "unused3", "reduce", "finish_step",
+    PROFILE_CLASSES = ("step_complex", "step_real", "run_kernel", "unused3", "reduce", "finish_step",
                        "nccl_allreduce", "step_block")
 
     def profile_enable(self, on=True):

@@ -70,29 +70,32 @@ def run_records(rec, prog, expansion, payload, mode, t_i, t_w, t_f, times):
     return out
 
 
-def run_pair_records(pairs, rec, prog, expansion, payload, mode, t_i, t_w, t_f, times):
-    """Replays the paired records (qiw_entry_pair_records) as the summing walk of the CUDA kernel does:
-    prod(Delta) * (coefA * prod(segA) + coefB * prod(segB)) per pair, plus the leftover single records."""
+def run_lane_program(lp, prog, expansion, payload, mode, t_i, t_w, t_f, times):
+    """Replays the lane program (qiw_entry_lane_program) as the step kernel does for one sample: segment products with
+    the folded coefficients, then per record prod(Delta operands) * sum over the members of prod(segment products)."""
     T = sample_table(prog, expansion, payload, mode, t_i, t_w, t_f, times)
-    seg = np.ones(rec["nSeg"], dtype=complex)
-    for j in range(rec["nSeg"]):
-        for q in rec["segdef"][j]:
+    assert len(T) == lp["seg0"]
+    seg = np.ones(len(lp["segdef"]), dtype=complex)
+    for j, d in enumerate(lp["segdef"]):
+        assert d[0] != 0xFFFF
+        for q in d:
             if q != 0xFFFF:
                 seg[j] *= T[q]
+        if lp["seg_coef"][j] != 0xFFFF:
+            seg[j] *= prog["coefs"][int(lp["seg_coef"][j])]
     T = np.concatenate([T, seg])
-    K = rec["K"]
+    K, n = lp["K"], lp["order"]
     out = np.zeros(prog["S"], dtype=complex)
-    for r in pairs["rec_pair"]:
-        d = np.prod([T[int(q)] for q in r[2 + 2 * K:]])
-        sa = np.prod([T[int(q)] for q in r[2:2 + K]])
-        sb = np.prod([T[int(q)] for q in r[2 + K:2 + 2 * K]])
-        out[int(r[0]) >> 16] += d * (prog["coefs"][int(r[0]) & 0xFFFF] * sa + prog["coefs"][int(r[1]) & 0xFFFF] * sb)
-    for r in pairs["rec_left"]:
-        v = prog["coefs"][int(r[0]) & 0xFFFF]
-        for q in r[1:]:
-            v = v * T[int(q)]
-        out[int(r[0]) >> 16] += v
-    return out
+    n_members = 0
+    for s_i, M, n_rec, item0 in lp["sections"]:
+        ni = (n + M * K + 3) // 4 * 4
+        for r in range(n_rec):
+            it = lp["items"][item0 + r * ni: item0 + (r + 1) * ni]
+            d = np.prod([T[int(q)] for q in it[:n]]) if n else 1.0
+            sm = sum(np.prod([T[int(q)] for q in it[n + m * K: n + (m + 1) * K]]) for m in range(M))
+            out[s_i] += d * sm
+            n_members += M
+    return out, n_members
 
 
 def run_program(prog, expansion, payload, mode, t_i, t_w, t_f, times):

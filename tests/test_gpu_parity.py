@@ -486,8 +486,8 @@ def test_paired_records(gpu_ctx, qlib, oracle_lib, monkeypatch, arith):
         got = gpu_ctx.eval(tau[ki], tau[kw], tau[kf], ids, N)
         ref = o.eval(tau[ki], tau[kw], tau[kf], ids, N)
         assert relerr(got, ref) < RTOL, (mode, relerr(got, ref))
-    prs = gpu_ctx.entry_pair_records(ids[-1])
-    assert len(prs["rec_pair"]) > 0
+    lp = gpu_ctx.entry_lane_program(ids[-1])
+    assert len(lp["sections"]) > 0 and any(M == 4 for _, M, _, _ in lp["sections"])
 
 
 @pytest.mark.parametrize("spline", [True, False])

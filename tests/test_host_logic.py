@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import models
-from program_interp import run_pair_records, run_program, run_records
+from program_interp import run_lane_program, run_program, run_records
 
 
 def test_library_exports_every_declared_symbol(qlib):
@@ -143,9 +143,10 @@ def test_compiled_programs_replay_to_oracle(qlib, oracle_lib, model):
                     assert rec["n_leaves"] == lv and rec["L2"] == rec["K"] + order
                     got2 = np.array([run_records(rec, prog, ex, pl, mode, t_i, t_w, t_f, times[i]) for i in range(2)])
                     assert np.abs(got2 - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1e-300)
-                    pairs = ctx.entry_pair_records(eid)   # ... and their paired form (shared Delta operands)
-                    assert 2 * len(pairs["rec_pair"]) + len(pairs["rec_left"]) == lv
-                    got3 = np.array([run_pair_records(pairs, rec, prog, ex, pl, mode, t_i, t_w, t_f, times[i]) for i in range(2)])
+                    lp = ctx.entry_lane_program(eid)   # ... and the lane program the step kernel executes (lane = sample)
+                    res3 = [run_lane_program(lp, prog, ex, pl, mode, t_i, t_w, t_f, times[i]) for i in range(2)]
+                    assert all(nm == lv for _, nm in res3)
+                    got3 = np.array([r for r, _ in res3])
                     assert np.abs(got3 - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1e-300)
                     assert st["n_leaves"] == lv and st["flops_per_sample"] == fl and st["n_top"] == len(pa)
                     eid += 1
@@ -272,8 +273,7 @@ def _digest(obj, h):
 @pytest.mark.parametrize("model", ["anderson", "two_band"])
 def test_threaded_compile_is_bit_identical(qlib, model, monkeypatch):
     """qiw_set_topologies walks big entries one initial-sector group per host thread and renumbers the fragments'
-    coefficients and pair-interaction slots into the global first-seen order: the program, the factorised / paired
-    records and the walk units must equal the sequential compilation (QIW_COMPILE_THREADS=1) bit for bit."""
+    coefficients and pair-interaction slots into the global first-seen order: the program, the factorised records / lane program and the walk units must equal the sequential compilation (QIW_COMPILE_THREADS=1) bit for bit."""
     import hashlib
     if model == "anderson":
         ex, grid, f = models.anderson(n_tau=20, corr=True)
@@ -297,7 +297,7 @@ def test_threaded_compile_is_bit_identical(qlib, model, monkeypatch):
             _digest(ctx.entry_program(eid), h)
             if model == "anderson":
                 _digest(ctx.entry_records(eid), h)
-                _digest(ctx.entry_pair_records(eid), h)
+                _digest(ctx.entry_lane_program(eid), h)
             else:
                 _digest(ctx.entry_walk_units(eid), h)
         digests[threads] = h.hexdigest()
