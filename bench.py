@@ -444,6 +444,7 @@ def main():
                 o5.set_topologies(j, lib.MODE_BOLD, t.order, t.n_pts_after, t.topologies[0], t.topologies[1])
             ref = o5.eval(0.0, tau5[200], tau5[201], list(range(len(ent5))), 64)
             c5_par = max(relerr_elem(got[j], ref[j]) for j in range(len(ent5)))
+        barrier()                                           # rank 0 has spent seconds in the oracle: line the ranks up again
         ctx5.eval(0.0, tau5[200], tau5[201], ids5, N5)      # warm-up: fills the simplex-root cache
         barrier()
         dms = []

@@ -109,6 +109,13 @@ int qiw_set_grid(qiw_context* ctx, int32_t n_tau, double beta);
 int qiw_set_delta(qiw_context* ctx, int32_t table_id, int32_t kind, int32_t n_knots, double beta,
                   const double* values);
 
+/* set_ppgf! + normalize! across the step seam without re-sending the table (src/ppgf.jl:495-504,646-668): writes row
+ * k_f of the device's P table (`row`: bsize complex values; NULL keeps the device's row) and then multiplies every
+ * stored row k by exp(-lambda * tau_k) (lambda = 0: no rescaling).  The host applies the same lambda to its own copy
+ * (normalize!), so the two tables agree to rounding; qiw_set_P re-synchronises them exactly.  Asynchronous: no host
+ * synchronisation, the caller's `row` may be reused at return. */
+int qiw_scale_P(qiw_context* ctx, int32_t k_f, const double* row, double lambda);
+
 /* Rows [first, first+count) of the bold propagator table: for each grid point the packed block
  * vector of P_s(tau_k) (P[s].mat.data, layout (d_s, d_s, n_tau)).  Replaces nothing in the
  * reference: it is how `expansion.P` reaches the device after set_ppgf!/normalize!

@@ -1,9 +1,11 @@
 # QInchwormCUDA.jl — thin `ccall` shim that routes QInchworm.jl's three qMC worker functions to
 # libqinchworm_cuda.so (include/qinchworm.h).
 #
-# STATUS: written against the C header, NOT executed in this build environment (the image has no
-# Julia toolchain).  The Python host layer `qinchworm.jl_b200/` drives the identical symbols through
-# ctypes and is what the tests exercise; this file shows the reference-side binding a maintainer adds.
+# STATUS: EXPERIMENTAL — written against the C header, NOT executed in this build environment (the image has
+# no Julia toolchain).  The Python host layer `qinchworm.jl_b200/` drives the identical symbols through
+# ctypes and is what the tests exercise; tests/test_bindings.py checks statically that every ccall below names
+# a symbol of include/qinchworm.h with the right number of arguments.  This file shows the reference-side
+# binding a maintainer adds.
 #
 # What it replaces (same signatures and return values as the reference):
 #   QInchworm.inchworm.inchworm_step_bare(expansion, c, τ_i, τ_f, top_data)          src/inchworm.jl:228
@@ -40,7 +42,11 @@ mutable struct Session
     n_tau::Int
     bsize::Int
     dims::Vector{Int}
-    entry_ids::Dict{UInt, Int32}   # objectid(td) => compiled entry
+    # (mode, order, n_pts_after, corr_idx) => compiled entry.  The reference builds fresh TopologiesInputData on
+    # every inchworm! / correlator_2p call (src/inchworm.jl:380-447), so the key is what determines the compiled
+    # program, not the object: entries are compiled once per Session and reused across calls.
+    entry_ids::Dict{NTuple{4, Int}, Int32}
+    n_top::Dict{NTuple{4, Int}, Int}   # topology count the entry was compiled from (guards against a different list)
     next_entry::Int32
 end
 
@@ -114,8 +120,10 @@ function Session(expansion::Expansion, grid::kd.ImaginaryTimeGrid; device::Integ
         check(ctx, ccall((:qiw_comm_init, lib), Cint, (Ctx, Int32, Int32, Ptr{UInt8}),
                          ctx, MPI.Comm_size(comm), MPI.Comm_rank(comm), id))
     end
-    s = Session(ctx, expansion, length(grid), sum(d^2 for d in dims), Int.(dims), Dict{UInt, Int32}(), 0)
+    s = Session(ctx, expansion, length(grid), sum(d^2 for d in dims), Int.(dims), Dict{NTuple{4, Int}, Int32}(),
+                Dict{NTuple{4, Int}, Int}(), 0)
     finalizer(x -> ccall((:qiw_destroy, lib), Cint, (Ctx,), x.ctx), s)
+    init_peer!(s)      # all-reduce inside the step kernel over peer memory (no-op on one rank)
     return s
 end
 
@@ -133,17 +141,22 @@ function upload_P!(s::Session)
 end
 
 function entry_id!(s::Session, td::TopologiesInputData, mode::Integer, corr_idx::Integer = 0)
-    get!(s.entry_ids, hash((objectid(td), mode, corr_idx))) do
+    key = (Int(mode), Int(td.order), Int(td.n_pts_after), Int(corr_idx))
+    id = get!(s.entry_ids, key) do
         id = s.next_entry
         s.next_entry += 1
+        id
+    end
+    if get(s.n_top, key, -1) != length(td.topologies)      # first use of the key (or a different list): compile in place
         n_top = length(td.topologies)
         pairs = Int32[x for top in td.topologies for p in top.pairs for x in (p.first, p.second)]
         parity = Int32[top.parity for top in td.topologies]
         check(s.ctx, ccall((:qiw_set_topologies, lib), Cint,
             (Ctx, Int32, Int32, Int32, Int32, Int32, Int32, Ptr{Int32}, Ptr{Int32}),
             s.ctx, id, mode, td.order, td.n_pts_after, corr_idx, n_top, pairs, parity))
-        id
+        s.n_top[key] = n_top
     end
+    return id
 end
 
 unpack(s::Session, v::AbstractVector{ComplexF64}) = begin
@@ -155,26 +168,43 @@ unpack(s::Session, v::AbstractVector{ComplexF64}) = begin
 end
 
 """
-All scrambled sequences of `mean_std_from_randomization` (src/randomization.jl:86-100) in one library call
-(qiw_eval_seqs; target_std = 0, i.e. no early stop).  The sequences are constructed in the reference's order —
-entry by entry, N_seqs sequences each, because the reference calls mean_std_from_randomization per entry
-(src/inchworm.jl:142,174) — so the user's RNG stream is consumed identically.
+`mean_std_from_randomization` (src/randomization.jl:86-100) for all entries of a step.
+target_std = 0 (the default): all N_seqs scrambled sequences in ONE library call (qiw_eval_seqs); the sequences are
+constructed in the reference's order — entry by entry, N_seqs sequences each, because the reference calls
+mean_std_from_randomization per entry (src/inchworm.jl:142,174) — so the user's RNG stream is consumed identically.
+target_std > 0: the reference's early stop (:93-99), one library call per sequence, stopping as soon as the largest
+standard deviation over the entries is below the target.
 """
 function eval_entries(s::Session, mode, t_i, t_w, t_f, top_data; corr_idx = 0)
     ids = Int32[entry_id!(s, td, mode, corr_idx) for td in top_data]
     N = top_data[1].N_samples
     rp = top_data[1].rand_params
-    per_entry = [[ScrambledSobolSeq(2 * td.order, scramble_rng = rp.rng) for _ in 1:rp.N_seqs] for td in top_data]
-    m = UInt32[]; x0 = UInt32[]
-    for q in 1:rp.N_seqs, j in 1:length(top_data)
-        seq = per_entry[j][q]
-        append!(m, vec(permutedims(seq.m))); append!(x0, seq.x)          # C layout m[D][32]
+    call_seqs(seqs_per_entry, n_seqs) = begin
+        m = UInt32[]; x0 = UInt32[]
+        for q in 1:n_seqs, j in 1:length(top_data)
+            seq = seqs_per_entry[j][q]
+            append!(m, vec(permutedims(seq.m))); append!(x0, seq.x)          # C layout m[D][32]
+        end
+        out = zeros(ComplexF64, s.bsize, length(ids), n_seqs)
+        check(s.ctx, ccall((:qiw_eval_seqs, lib), Cint,
+            (Ctx, Float64, Float64, Float64, Int32, Int32, Ptr{Int32}, Ptr{UInt32}, Ptr{UInt32}, UInt64, Ptr{ComplexF64}),
+            s.ctx, t_i, t_w, t_f, n_seqs, length(ids), ids, m, x0, N, out))
+        [out[:, :, q] for q in 1:n_seqs]
     end
-    out = zeros(ComplexF64, s.bsize, length(ids), rp.N_seqs)
-    check(s.ctx, ccall((:qiw_eval_seqs, lib), Cint,
-        (Ctx, Float64, Float64, Float64, Int32, Int32, Ptr{Int32}, Ptr{UInt32}, Ptr{UInt32}, UInt64, Ptr{ComplexF64}),
-        s.ctx, t_i, t_w, t_f, rp.N_seqs, length(ids), ids, m, x0, N, out))
-    return [out[:, :, q] for q in 1:rp.N_seqs]
+    if rp.target_std <= 0 || rp.N_seqs == 1
+        per_entry = [[ScrambledSobolSeq(2 * td.order, scramble_rng = rp.rng) for _ in 1:rp.N_seqs] for td in top_data]
+        return call_seqs(per_entry, rp.N_seqs)
+    end
+    samples = Matrix{ComplexF64}[]
+    for q in 1:rp.N_seqs
+        one = [[ScrambledSobolSeq(2 * td.order, scramble_rng = rp.rng)] for td in top_data]
+        append!(samples, call_seqs(one, 1))
+        if q > 1
+            _, σ = mean_std(samples)
+            maximum(abs, σ) <= rp.target_std && break
+        end
+    end
+    return samples
 end
 
 "mean / std over the randomised sequences (src/randomization.jl:93-99): std of a single sequence is NaN."
@@ -204,12 +234,28 @@ function inchworm_step_bare(s::Session, τ_i::kd.TimeGridPoint, τ_f::kd.TimeGri
     return order_sums(s, top_data, μ, σ)
 end
 
-"Drop-in for QInchworm.inchworm.inchworm_step (src/inchworm.jl:123).  The caller uploads P first (upload_P!)."
+"""
+Drop-in for QInchworm.inchworm.inchworm_step (src/inchworm.jl:123).  The device's P table must be current: call
+`upload_P!` once before the first step, and `scale_P!` after every host-side `set_ppgf!` + `normalize!` (it sends the
+new row and λ instead of the whole table).
+"""
 function inchworm_step(s::Session, τ_i::kd.TimeGridPoint, τ_w::kd.TimeGridPoint, τ_f::kd.TimeGridPoint, top_data)
     t_i, t_w, t_f = (-imag(τ.bpoint.val) for τ in (τ_i, τ_w, τ_f))
-    upload_P!(s)
     μ, σ = mean_std(eval_entries(s, 1, t_i, t_w, t_f, top_data))
     return order_sums(s, top_data, μ, σ)
+end
+
+"""
+The step seam (qiw_scale_P): after `set_ppgf!(P, τ_i, τ_f, result)` and `normalize!(P, τ_f)` on the host
+(src/inchworm.jl:486-488), bring the device's table up to date with ONE row and λ: row k_f := `result` (packed), then
+every stored row k times exp(-λ τ_k) — λ as normalize! computes it (src/ppgf.jl:649-650), 0 for no rescaling.
+"""
+function scale_P!(s::Session, k_f::Integer, result::SectorBlockMatrix, λ::Real)
+    row = ComplexF64[]
+    for sec in 1:length(s.dims)
+        append!(row, vec(result[sec][2]))
+    end
+    check(s.ctx, ccall((:qiw_scale_P, lib), Cint, (Ctx, Int32, Ptr{ComplexF64}, Float64), s.ctx, k_f - 1, row, λ))
 end
 
 "Drop-in for the single-τ QInchworm.inchworm.correlator_2p (src/inchworm.jl:805): returns (value, std)."

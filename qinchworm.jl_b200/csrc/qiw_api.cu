@@ -27,6 +27,7 @@ cudaError_t launch_reduce(const DevEntryDyn* dyn, const DevEntry* entries, const
                           double t_i, double t_w, double t_f, double2* out, int n_entries, cudaStream_t st);
 cudaError_t launch_finish_step(double2* P, int n_tau, int bsize, const int* diag, int n_diag, double h, int k_f,
                                const double2* contribs, int n_contrib, int do_normalize, double2* hist, cudaStream_t st);
+cudaError_t launch_scale_P(double2* P, int n_tau, int bsize, double h, double lambda, cudaStream_t st);
 cudaError_t launch_sobol_points(int D, const uint32_t* m, const uint32_t* x0, unsigned long long start,
                                 unsigned long long count, uint32_t* out, cudaStream_t st);
 cudaError_t launch_dfma_peak(double* out, int blocks, int iters, cudaStream_t st);
@@ -252,6 +253,8 @@ struct ProfScope {   // records an event pair around one launch when profiling i
     }
 };
 
+static int ensure_host_out_impl(qiw_context* ctx, size_t n);
+static inline int ensure_host_out(qiw_context* ctx, size_t n) { return ensure_host_out_impl(ctx, n); }
 static void release_plan(Plan& pl);
 static void drop_plans(qiw_context* ctx) {
     for (auto& pl : ctx->plans) release_plan(*pl);
@@ -444,6 +447,29 @@ int qiw_set_P(qiw_context* ctx, int32_t first, int32_t count, const double* rows
     }
     CK(cudaMemcpyAsync(ctx->dP.p + (size_t)first * bs, rows, (size_t)count * bs * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return QIW_OK;
+}
+
+int qiw_scale_P(qiw_context* ctx, int32_t k_f, const double* row, double lambda) {
+    if (!ctx || ctx->n_tau == 0 || k_f < 0 || k_f >= ctx->n_tau || !std::isfinite(lambda))
+        return fail(ctx, QIW_ERR_BAD_ARG, "qiw_scale_P: bad argument (grid first)");
+    if (ctx->no_device) return fail(ctx, QIW_ERR_CUDA, "planning-only context has no device tables");
+    cudaSetDevice(ctx->device);
+    const size_t bs = ctx->model.bsize;
+    if (row) {
+        uint8_t c = 0;
+        for (size_t el = 0; el < bs; ++el) if (row[2 * el] != 0.0) { c = 1; break; }
+        ctx->p_row_complex[k_f] = c;
+        int rc = ensure_host_out(ctx, bs);      // pinned staging: the copy is asynchronous, the caller's buffer is free at return
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(ctx->stream)); // the staging buffer may still feed the previous call's copy
+        memcpy(ctx->hOut, row, bs * sizeof(double2));
+        CK(cudaMemcpyAsync(ctx->dP.p + (size_t)k_f * bs, ctx->hOut, bs * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (lambda != 0.0) {
+        CK(launch_scale_P(ctx->dP.p, ctx->n_tau, (int)bs, ctx->beta / (ctx->n_tau - 1), lambda, ctx->stream));
+        ctx->launches++;
+    }
     return QIW_OK;
 }
 
@@ -1178,6 +1204,14 @@ static int stage_call(qiw_context* ctx, Plan& pl, const uint32_t* sobol_m, const
     return QIW_OK;
 }
 
+// How long a rank waits inside the kernel for its peers' block sums before it gives up (poisons the sums, raises the
+// status flag): ranks reach a collective seconds apart when one of them compiles a big entry or checks results on the host.
+static unsigned long long peer_timeout_ns() {
+    double s = 60.0;
+    if (const char* env = getenv("QIW_PEER_TIMEOUT_S")) { const double v = atof(env); if (v > 0) s = v; }
+    return (unsigned long long)(s * 1e9);
+}
+
 // What the step kernel's last CTA does after the reduction in the device-resident loop.
 struct FinishArgs { int k_f = -1; int normalize = 0; double2* hist = nullptr; const int* diag = nullptr; int n_diag = 0; };
 
@@ -1204,7 +1238,7 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
     sp.partials = pl.d_partials.p;
     sp.finish_k_f = -1;
     sp.sobol_z_stride = sobol_z_stride;
-    if (m.scalar && !pl.explicit_mode) {
+    if ((m.scalar || pl.block_real) && !pl.explicit_mode) {
         const size_t need = (size_t)std::max(n_times, 1);
         if (ctx->dCounter.cap < need) {
             CK(cudaStreamSynchronize(ctx->stream));
@@ -1222,7 +1256,7 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         bool exchange_fused = false;
         if (collective && ctx->peer_ready && ctx->n_ranks > 1 && pl.ids.size() * (size_t)m.bsize * sizeof(double2) * 2 <= kPeerSlotBytes) {   // every double travels as two 8-byte words
             sp.peer_ranks = ctx->n_ranks; sp.peer_rank = ctx->rank; sp.peer_seq = ++ctx->peer_seq;
-            sp.peer_mail = ctx->dPeerPtrs.p; sp.peer_status = ctx->dPeerStatus.p;
+            sp.peer_mail = ctx->dPeerPtrs.p; sp.peer_status = ctx->dPeerStatus.p; sp.peer_timeout_ns = peer_timeout_ns();
             exchange_fused = true;
             if (collective_done) *collective_done = true;
         }
@@ -1251,7 +1285,7 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         bp.scratch = ctx->dScratch.p; bp.scratch_per_thread = pl.scratch_per_thread;
         StepParams gp = sp;
         gp.items = pl.d_items.p;
-        dim3 grid((unsigned)pl.pitch, (unsigned)pl.items.size());
+        dim3 grid((unsigned)pl.pitch, (unsigned)pl.items.size(), (unsigned)(pl.block_real ? std::max(n_times, 1) : 1));
         if (pl.block_real) {
             BlockWalkParams wp;
             wp.pool_re = ctx->dPoolRe.p; wp.xwords = ctx->dXWordsPtr.p; wp.unit_off = ctx->dXTreeOffPtr.p; wp.chunk_bounds = pl.d_bounds.p; wp.warps = pl.bw_warps; wp.max_sp = pl.bw_max_sp;
@@ -1304,7 +1338,7 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
             fclose(f);
         }
     }
-    if (!pl.explicit_mode && !m.scalar) {
+    if (!pl.explicit_mode && !m.scalar && !pl.block_real) {
         {
             ProfScope ps(ctx, 4);
             CK(launch_reduce(pl.d_dyn.p, ctx->dEntries.p, pl.d_partials.p, pl.pitch, m.bsize, t_i, t_w, t_f, pl.d_out.p,
@@ -1559,7 +1593,7 @@ static int enqueue_run(qiw_context* ctx, Plan& pl, int k_first, int n_steps, dou
     if (collective && ctx->peer_ready && ctx->n_ranks > 1) {
         sp.peer_ranks = ctx->n_ranks; sp.peer_rank = ctx->rank; sp.peer_seq = ctx->peer_seq + 1;
         ctx->peer_seq += (unsigned long long)n_steps;
-        sp.peer_mail = ctx->dPeerPtrs.p; sp.peer_status = ctx->dPeerStatus.p;
+        sp.peer_mail = ctx->dPeerPtrs.p; sp.peer_status = ctx->dPeerStatus.p; sp.peer_timeout_ns = peer_timeout_ns();
     }
     rp.jobs = rn.d_jobs.p; rp.cta_job0 = rn.d_cta_job0.p; rp.entry_job0 = rn.d_entry_job0.p; rp.n_jobs = rn.n_jobs;
     rp.k_first = k_first; rp.n_steps = n_steps;
@@ -1632,7 +1666,7 @@ static int check_peer_status(qiw_context* ctx) {
     return QIW_OK;
 }
 
-static int ensure_host_out(qiw_context* ctx, size_t n) {
+static int ensure_host_out_impl(qiw_context* ctx, size_t n) {
     if (ctx->hOutCap < n) {
         if (ctx->hOut) cudaFreeHost(ctx->hOut);
         ctx->hOut = nullptr; ctx->hOutCap = 0;
@@ -1728,14 +1762,6 @@ int qiw_eval_batch(qiw_context* ctx, int32_t n_times, const double* times, int32
         return fail(ctx, QIW_ERR_BAD_ARG, "qiw_eval_batch: bad argument");
     cudaSetDevice(ctx->device);
     const HostModel& m = ctx->model;
-    if (!m.scalar) {   // block models: one launch per triple (the block kernel has no batched form yet)
-        for (int z = 0; z < n_times; ++z) {
-            rc = qiw_eval(ctx, times[3 * z], times[3 * z + 1], times[3 * z + 2], n_entries, ids, sobol_m, sobol_x0, N_total,
-                          out + (size_t)z * n_entries * m.bsize * 2);
-            if (rc) return rc;
-        }
-        return QIW_OK;
-    }
     uint64_t start = 0, count = N_total;
     rank_sub_range(N_total, ctx->n_ranks, ctx->rank, &start, &count);
     rc = sync_static_tables(ctx);
@@ -1744,6 +1770,14 @@ int qiw_eval_batch(qiw_context* ctx, int32_t n_times, const double* times, int32
     rc = get_plan(ctx, n_entries, ids, count, false, &plp);
     if (rc) return rc;
     Plan& pl = *plp;
+    if (!m.scalar && !pl.block_real) {   // block models in complex arithmetic: one launch per triple (the general block kernel has no batched form)
+        for (int z = 0; z < n_times; ++z) {
+            rc = qiw_eval(ctx, times[3 * z], times[3 * z + 1], times[3 * z + 2], n_entries, ids, sobol_m, sobol_x0, N_total,
+                          out + (size_t)z * n_entries * m.bsize * 2);
+            if (rc) return rc;
+        }
+        return QIW_OK;
+    }
     rc = stage_call(ctx, pl, sobol_m, sobol_x0, start, count, N_total, true);
     if (rc) return rc;
     const size_t n_out = (size_t)n_times * n_entries * m.bsize;
@@ -1779,14 +1813,6 @@ int qiw_eval_seqs(qiw_context* ctx, double t_i, double t_w, double t_f, int32_t 
     const HostModel& m = ctx->model;
     size_t md = 0, xd = 0;     // words per sequence in the caller's arrays
     for (int i = 0; i < n_entries; ++i) { md += (size_t)ctx->entries[ids[i]]->prog.D * 32; xd += ctx->entries[ids[i]]->prog.D; }
-    if (!m.scalar) {   // block models: one launch per sequence
-        for (int z = 0; z < n_seqs; ++z) {
-            rc = qiw_eval(ctx, t_i, t_w, t_f, n_entries, ids, sobol_m + (size_t)z * md, sobol_x0 + (size_t)z * xd, N_total,
-                          out + (size_t)z * n_entries * m.bsize * 2);
-            if (rc) return rc;
-        }
-        return QIW_OK;
-    }
     uint64_t start = 0, count = N_total;
     rank_sub_range(N_total, ctx->n_ranks, ctx->rank, &start, &count);
     rc = sync_static_tables(ctx);
@@ -1795,6 +1821,14 @@ int qiw_eval_seqs(qiw_context* ctx, double t_i, double t_w, double t_f, int32_t 
     rc = get_plan(ctx, n_entries, ids, count, false, &plp);
     if (rc) return rc;
     Plan& pl = *plp;
+    if (!m.scalar && !pl.block_real) {   // block models in complex arithmetic: one launch per sequence
+        for (int z = 0; z < n_seqs; ++z) {
+            rc = qiw_eval(ctx, t_i, t_w, t_f, n_entries, ids, sobol_m + (size_t)z * md, sobol_x0 + (size_t)z * xd, N_total,
+                          out + (size_t)z * n_entries * m.bsize * 2);
+            if (rc) return rc;
+        }
+        return QIW_OK;
+    }
     rc = stage_call(ctx, pl, sobol_m, sobol_x0, start, count, N_total, true);   // weights, ranges (sequence 0's parameters)
     if (rc) return rc;
     // per-sequence parameter blocks in the plan's per-entry layout (m[D][32] then x0[D] per entry)

@@ -117,6 +117,7 @@ struct StepParams {
     unsigned long long peer_seq;   // sequence number of this collective (flags carry it; parity selects the buffer)
     unsigned char* const* peer_mail;   // [peer_ranks] base address of every rank's mailbox (own included)
     int* peer_status;              // set to 1 if a peer did not answer within the time-out
+    unsigned long long peer_timeout_ns;   // how long a rank waits for its peers (QIW_PEER_TIMEOUT_S, default 60 s)
 };
 
 // One CTA of the persistent run kernel: a work item (entry + chunks of its lane program) on 32 * n_sub consecutive

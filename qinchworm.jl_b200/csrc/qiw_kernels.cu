@@ -82,6 +82,16 @@ __global__ void __launch_bounds__(256) finish_step_kernel(double2* __restrict__ 
     }
 }
 
+// normalize!(P, lambda) alone (src/ppgf.jl:662-668): every stored grid value times exp(-lambda tau_k).  Used across the
+// step seam (qiw_scale_P) so that a host-stepped loop sends one row and lambda instead of the whole table.
+__global__ void __launch_bounds__(256) scale_P_kernel(double2* __restrict__ P, int n_tau, int bsize, double h, double lambda) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_tau * bsize) return;
+    const int k = idx / bsize;
+    const double f = exp(-((double)k * h) * lambda);
+    P[idx] = cscale(f, P[idx]);
+}
+
 // ---- FP64 FMA peak probe ---------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0,
@@ -105,6 +115,11 @@ cudaError_t launch_reduce(const DevEntryDyn* dyn, const DevEntry* entries, const
 cudaError_t launch_finish_step(double2* P, int n_tau, int bsize, const int* diag, int n_diag, double h, int k_f,
                                const double2* contribs, int n_contrib, int do_normalize, double2* hist, cudaStream_t st) {
     finish_step_kernel<<<1, 256, 0, st>>>(P, n_tau, bsize, diag, n_diag, h, k_f, contribs, n_contrib, do_normalize, hist);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scale_P(double2* P, int n_tau, int bsize, double h, double lambda, cudaStream_t st) {
+    scale_P_kernel<<<(n_tau * bsize + 255) / 256, 256, 0, st>>>(P, n_tau, bsize, h, lambda);
     return cudaGetLastError();
 }
 
@@ -514,7 +529,10 @@ __global__ void __launch_bounds__(768, 1) block_walk_kernel(const StepParams p, 
     double* pw = times + (kDevMaxNodes + 1) * 32;                           // [kDevMaxDim][32]
     int* okflag = reinterpret_cast<int*>(pw + kDevMaxDim * 32);             // [32]
 
-    const double t_i = p.t_i, t_w = p.t_w, t_f = p.t_f;
+    double t_i = p.t_i, t_w = p.t_w, t_f = p.t_f;
+    // batched evaluation: blockIdx.z selects one (t_i, t_w, t_f) triple of the call, or one scrambled Sobol sequence
+    if (p.times_dev) { const double* tz = p.times_dev + 3 * blockIdx.z; t_i = tz[0]; t_w = tz[1]; t_f = tz[2]; }
+    const uint32_t* __restrict__ sm = dy.sobol + (size_t)blockIdx.z * p.sobol_z_stride;
     const double lo_after = (e.mode == 0) ? t_i : t_w, len_after = t_f - lo_after, len_before = t_w - t_i;
     const unsigned long long count = dy.count;
     const int n_sb = (int)((count + 31ull) >> 5);
@@ -532,7 +550,7 @@ __global__ void __launch_bounds__(768, 1) block_walk_kernel(const StepParams p, 
         if (threadIdx.x < 32) okflag[threadIdx.x] = (local0 + threadIdx.x < count) ? 1 : 0;
         for (int task = threadIdx.x; task < D * 32; task += nthr) {
             const int j = task >> 5, smp = task & 31;
-            const uint32_t xi = sobol_coord(dy.sobol + j * 32, __ldg(dy.sobol + D * 32 + j), (uint32_t)(dy.start + local0 + smp));
+            const uint32_t xi = sobol_coord(sm + j * 32, __ldg(sm + D * 32 + j), (uint32_t)(dy.start + local0 + smp));
             const double x = (double)xi * 2.3283064365386963e-10;
             const int den = (j < d_after) ? (d_after - j) : (D - j);
             pw[j * 32 + smp] = (den == 1) ? x : pow(x, 1.0 / (double)den);
@@ -607,18 +625,42 @@ __global__ void __launch_bounds__(768, 1) block_walk_kernel(const StepParams p, 
     for (int k = threadIdx.x; k < bsize; k += nthr) {
         double v = 0.0;
         for (int w2 = 0; w2 < nw; ++w2) v += accs[(size_t)w2 * bsize + k];
-        p.partials[((size_t)it.partial0 * gridDim.x + blockIdx.x) * bsize + k] = make_double2(0.0, v);
+        p.partials[((size_t)blockIdx.z * gridDim.y * gridDim.x + (size_t)it.partial0 * gridDim.x + blockIdx.x) * bsize + k] = make_double2(0.0, v);
     }
+    // -- 6. fused tail, as in the scalar step kernel: the last CTA to arrive reduces all partial rows in fixed order,
+    //       exchanges the block sums with the peer GPUs and (device-resident loop) performs set_ppgf! + normalize! -----
+    if (p.done_counter) {
+        __shared__ int is_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned ticket = atomicAdd(p.done_counter + blockIdx.z, 1u);
+            is_last = (ticket == gridDim.x * gridDim.y - 1u) ? 1 : 0;
+        }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        fused_tail(p, t_i, t_w, t_f, (int)gridDim.x);
+        if (threadIdx.x == 0) p.done_counter[blockIdx.z] = 0u;
+    }
+}
+
+// per-device opt-in to more than 48 KB of dynamic shared memory (one bit per device)
+static cudaError_t optin_smem_block(const void* kernel, unsigned long long* mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && ((__atomic_load_n(mask, __ATOMIC_RELAXED) >> dev) & 1ull)) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    if (dev < 64) __atomic_fetch_or(mask, 1ull << dev, __ATOMIC_RELAXED);
+    return cudaSuccess;
 }
 
 cudaError_t launch_block_walk(const StepParams& p, const BlockParams& bp, const BlockWalkParams& wp, dim3 grid, int threads,
                               size_t smem, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(block_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static unsigned long long mask = 0ull;
+    cudaError_t e = optin_smem_block((const void*)block_walk_kernel, &mask);
+    if (e != cudaSuccess) return e;
     block_walk_kernel<<<grid, threads, smem, st>>>(p, bp, wp);
     return cudaGetLastError();
 }

@@ -125,110 +125,6 @@ __device__ __forceinline__ void segment_products(const DevEntry& e, const uint4*
     }
 }
 
-// ---- fused tail of the step kernel ---------------------------------------------------------------
-// Executed by the last CTA of a step launch: every (entry, sector) sum runs over the partial rows in
-// fixed order, so the result does not depend on which CTA happens to be last.  Optionally followed by
-// set_ppgf!(P, tau_f, result) and normalize!(P, tau_f) (src/ppgf.jl:495-504,646-668).
-__device__ void fused_tail(const StepParams& pp, double t_i, double t_w, double t_f, int pitch) {
-    StepParams p = pp;
-    const int S = p.S, n_out = p.n_call_entries * S;
-    p.partials += (size_t)blockIdx.z * gridDim.y * gridDim.x * S;   // this time triple's rows and results
-    p.out += (size_t)blockIdx.z * n_out;
-    // four lanes per (entry, sector) output: lane g adds rows g, g+4, ... in order, then the four partial sums
-    // are combined in a fixed butterfly — the same operation order whichever CTA runs the tail
-    for (int o0 = 0; o0 < n_out; o0 += (int)blockDim.x / 4) {
-        const int o = o0 + (int)threadIdx.x / 4, g = (int)threadIdx.x & 3;
-        double2 v = make_double2(0.0, 0.0);
-        double scale = 0.0;
-        int oi = 0;
-        if (o < n_out) {
-            const int i = o / S, s = o - i * S;
-            const DevEntryDyn& dy = p.dyn[i];
-            const size_t row0 = (size_t)dy.item0 * pitch, nrows = (size_t)dy.n_items * pitch;
-            for (size_t r = g; r < nrows; r += 4) v = cadd(v, __ldcg(p.partials + (row0 + r) * S + s));
-            if (g == 0) scale = entry_scale(p.entries[dy.entry], dy, t_i, t_w, t_f);
-            oi = dy.out_index * S + s;
-        }
-        v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, 1); v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, 1);
-        v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, 2); v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, 2);
-        if (o < n_out && g == 0) p.out[oi] = cscale(scale, v);
-    }
-    if (p.peer_ranks > 1) {
-        // ---- all-reduce over peer memory (replaces all_reduce!, src/mpi.jl:104-127) ----
-        // Low-latency protocol: every 8-byte store carries 4 bytes of payload and the 4-byte sequence number of
-        // this collective, so the receiver needs no separate flag and the sender no system-wide fence: a word is
-        // valid as soon as its flag matches (8-byte stores are single transactions on NVLink).  Each double
-        // travels as two such words.  Buffers alternate with the parity of the sequence number: a slot is
-        // rewritten two collectives later, after every peer has provably finished reading it.
-        __syncthreads();
-        const int par = (int)(p.peer_seq & 1ull);
-        const unsigned int seq32 = (unsigned int)(p.peer_seq % 0xFFFFFFFFull) + 1u;   // never 0 (the mailbox starts zeroed)
-        const size_t my_slot = kPeerFlagBytes + ((size_t)p.peer_rank * 2 + par) * kPeerSlotBytes;
-        const int n_dbl = 2 * n_out, n_words = 2 * n_dbl;
-        const double* outd = reinterpret_cast<const double*>(p.out);
-        for (int k = threadIdx.x; k < n_words; k += blockDim.x) {
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(outd[k >> 1]);
-            const unsigned int half = (k & 1) ? (unsigned int)(bits >> 32) : (unsigned int)bits;
-            const uint2 wd = make_uint2(half, seq32);
-            for (int q = 0; q < p.peer_ranks; ++q) {
-                if (q == p.peer_rank) continue;
-                uint2* dst = reinterpret_cast<uint2*>(p.peer_mail[q] + my_slot) + k;
-                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(wd.x), "r"(wd.y) : "memory");
-            }
-        }
-        // receive: poll every word until its flag shows this collective, add the contributions in rank order.
-        // A peer that does not answer within the time-out raises the status flag AND poisons the sum with NaN, so
-        // that a device-resident run cannot silently continue on a partial sum (the host reports the error).
-        const unsigned char* base = p.peer_mail[p.peer_rank] + kPeerFlagBytes;
-        const unsigned long long t0 = globaltimer_ns();
-        for (int j = threadIdx.x; j < n_dbl; j += blockDim.x) {
-            double v = 0.0;
-            for (int q = 0; q < p.peer_ranks; ++q) {
-                if (q == p.peer_rank) { v += outd[j]; continue; }
-                const uint2* src = reinterpret_cast<const uint2*>(base + ((size_t)q * 2 + par) * kPeerSlotBytes) + 2 * j;
-                uint2 lo, hi;
-                bool ok = true;
-                do {
-                    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo.x), "=r"(lo.y) : "l"(src) : "memory");
-                    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hi.x), "=r"(hi.y) : "l"(src + 1) : "memory");
-                    if ((lo.y != seq32 || hi.y != seq32) && globaltimer_ns() - t0 > 10000000000ull) { *p.peer_status = 1; ok = false; break; }   // 10 s
-                } while (lo.y != seq32 || hi.y != seq32);
-                if (ok) v += __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | (unsigned long long)lo.x));
-                else v = __longlong_as_double(0x7FF8000000000000ll);
-            }
-            reinterpret_cast<double*>(p.out)[j] = v;   // element j is read and written by this thread only
-        }
-    }
-    if (p.finish_k_f < 0) return;
-    __syncthreads();
-    __shared__ double lambda_s;
-    const int bsize = p.bsize, k_f = p.finish_k_f;
-    double2* P = p.finish_P;
-    for (int el = threadIdx.x; el < bsize; el += blockDim.x) {
-        double2 v = make_double2(0.0, 0.0);
-        for (int j = 0; j < p.n_call_entries; ++j) {
-            const double2 c = p.out[(size_t)j * bsize + el];
-            v = cadd(v, c);
-            if (p.finish_hist) p.finish_hist[(size_t)j * bsize + el] = c;
-        }
-        P[(size_t)k_f * bsize + el] = v;
-    }
-    __syncthreads();
-    if (!p.finish_normalize) return;
-    if (threadIdx.x == 0) {
-        double pmax = -1.0e300;
-        for (int i = 0; i < p.finish_n_diag; ++i) pmax = fmax(pmax, -P[(size_t)k_f * bsize + p.finish_diag[i]].y);
-        lambda_s = log(pmax) / ((double)k_f * p.h);
-    }
-    __syncthreads();
-    const double lambda = lambda_s;
-    for (int idx = threadIdx.x; idx < p.n_tau * bsize; idx += blockDim.x) {
-        const int k = idx / bsize;
-        const double f = exp(-((double)k * p.h) * lambda);
-        P[idx] = cscale(f, P[idx]);
-    }
-}
-
 // ---- per-CTA view of one job and the phases both kernels are made of -------------------------------------
 // A job = (entry, `ns` consecutive samples, chunks of the entry's lane program).  ns is a power of two: <= 32 in the
 // step kernel; 32 m in the persistent run kernel, where a CTA takes m sample blocks of a light entry at once.
@@ -844,7 +740,7 @@ __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) 
                     do {
                         asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo.x), "=r"(lo.y) : "l"(src) : "memory");
                         asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hi.x), "=r"(hi.y) : "l"(src + 1) : "memory");
-                        if ((lo.y != seq32 || hi.y != seq32) && globaltimer_ns() - t0 > 10000000000ull) { *p.peer_status = 1; ok = false; break; }   // 10 s
+                        if ((lo.y != seq32 || hi.y != seq32) && globaltimer_ns() - t0 > p.peer_timeout_ns) { *p.peer_status = 1; ok = false; break; }
                     } while (lo.y != seq32 || hi.y != seq32);
                     if (ok) v += __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | (unsigned long long)lo.x));
                     else v = __longlong_as_double(0x7FF8000000000000ll);   // poison: the run must not continue on a partial sum

@@ -107,39 +107,58 @@ class Solver:
         self._entries[key] = (td.entry_id, tops)
         return td
 
-    def eval_entries(self, t_i, t_w, t_f, top_data):
-        """mean/std over randomised sequences of the per-entry qMC integrals
-        (mean_std_from_randomization, src/randomization.jl:86-100).  Returns (mean, std) arrays
-        [n_entries, bsize]; std is NaN for a single sequence, as in the reference."""
+    def eval_samples(self, t_i, t_w, t_f, top_data):
+        """The randomised estimates of every entry's qMC integral: a list, per entry, of arrays [n_seqs_used, bsize]
+        (mean_std_from_randomization is called per entry, src/inchworm.jl:142,174 and src/randomization.jl:86-100:
+        every entry has its own early stop, and a host RNG stream is consumed entry by entry, N_seqs sequences each;
+        order-0 entries are exact and draw nothing, src/inchworm.jl:148-157)."""
         if not top_data:
-            z = np.zeros((0, self.ctx.bsize), dtype=complex)
-            return z, z
+            return []
         ids = [td.entry_id for td in top_data]
         N = top_data[0].N_samples
         rp = top_data[0].rand_params
         assert all(td.N_samples == N for td in top_data)
-        samples = []
-        if rp.rng is not None and rp.N_seqs > 1 and rp.target_std == 0.0:
-            # no early stop: all sequences in ONE launch.  The scrambling bits are drawn in the reference's order —
-            # entry by entry, N_seqs sequences each (mean_std_from_randomization is called per entry,
-            # src/inchworm.jl:142,174) — so a host RNG stream is consumed identically.
-            per_entry = [[_scrambled_sequence(2 * td.order, rp.rng) for _ in range(rp.N_seqs)] for td in top_data]
+        if rp.rng is None and rp.N_seqs == 1:
+            # the default: one unscrambled sequence, every entry in ONE launch
+            res = self.ctx.eval(t_i, t_w, t_f, ids, N)
+            return [res[j][None, :] for j in range(len(ids))]
+        if rp.target_std == 0.0:
+            # no early stop (std == 0 exactly never triggers it in practice): all sequences of all entries in ONE launch;
+            # the scrambling bits are drawn in the reference's order
+            per_entry = [[_scrambled_sequence(2 * td.order, rp.rng if td.order > 0 else None) for _ in range(rp.N_seqs)]
+                         for td in top_data]
             seqs = [[per_entry[j][s] for j in range(len(top_data))] for s in range(rp.N_seqs)]
-            samples = list(self.ctx.eval_seqs(t_i, t_w, t_f, ids, N, seqs))
-        else:
-            for s in range(rp.N_seqs):
-                sobol = None
-                if rp.rng is not None:
-                    sobol = [_scrambled_sequence(2 * td.order, rp.rng) for td in top_data]
-                samples.append(self.ctx.eval(t_i, t_w, t_f, ids, N, sobol=sobol))
-                if s > 0 and np.max(np.abs(np.std(samples, axis=0, ddof=1))) <= rp.target_std:
+            res = self.ctx.eval_seqs(t_i, t_w, t_f, ids, N, seqs)      # [n_seqs, n_entries, bsize]
+            return [res[:1, j] if td.order == 0 else res[:, j] for j, td in enumerate(top_data)]
+        out = []
+        for td in top_data:          # early stop: entry by entry, one library call per sequence
+            if td.order == 0:
+                out.append(self.ctx.eval(t_i, t_w, t_f, [td.entry_id], N))
+                continue
+            smp = []
+            for s_ in range(rp.N_seqs):
+                seq = _scrambled_sequence(2 * td.order, rp.rng)
+                smp.append(self.ctx.eval(t_i, t_w, t_f, [td.entry_id], N, sobol=[seq])[0])
+                if s_ > 0 and np.max(np.abs(np.std(smp, axis=0, ddof=1))) <= rp.target_std:
                     break
-        mean = np.mean(samples, axis=0)
-        with np.errstate(invalid="ignore", divide="ignore"):
-            std = np.std(samples, axis=0, ddof=1) if len(samples) > 1 else np.full_like(mean, np.nan)
-        for j, td in enumerate(top_data):
+            out.append(np.array(smp))
+        return out
+
+    def eval_entries(self, t_i, t_w, t_f, top_data):
+        """mean/std over randomised sequences of the per-entry qMC integrals
+        (mean_std_from_randomization, src/randomization.jl:86-100).  Returns (mean, std) arrays
+        [n_entries, bsize]; std is NaN for a single sequence, as in the reference, and 0 for the exact order-0 entries."""
+        if not top_data:
+            z = np.zeros((0, self.ctx.bsize), dtype=complex)
+            return z, z
+        samples = self.eval_samples(t_i, t_w, t_f, top_data)
+        mean = np.array([x.mean(axis=0) for x in samples])
+        std = np.full_like(mean, np.nan)
+        for j, (td, x) in enumerate(zip(top_data, samples)):
             if td.order == 0:
                 std[j] = 0.0  # exact evaluation (src/inchworm.jl:155)
+            elif len(x) > 1:
+                std[j] = np.std(x, axis=0, ddof=1)
         return mean, std
 
 
@@ -197,6 +216,11 @@ def inchworm(expansion, grid, orders, orders_bare, N_samples, n_pts_after_max=No
         device_resident = rand_params.rng is None and rand_params.N_seqs == 1
     n_tau = grid.n_tau
     orders, orders_bare = list(orders), list(orders_bare)
+    if N_samples == 0:
+        # the reference skips every sampled entry (`td.N_samples <= 0 && continue`, src/inchworm.jl:159,258) and
+        # evaluates order 0 only; the exact entries need no samples, the library wants a positive count
+        orders, orders_bare = [o for o in orders if o == 0], [o for o in orders_bare if o == 0]
+        N_samples = 1
     P_orders = {o: np.zeros((n_tau, solver.ctx.bsize), dtype=complex) for o in set(orders) | set(orders_bare)}
     P_orders_std = {o: np.zeros((n_tau, solver.ctx.bsize), dtype=complex) for o in P_orders}
     if device_resident:
@@ -208,8 +232,9 @@ def inchworm(expansion, grid, orders, orders_bare, N_samples, n_pts_after_max=No
         expansion.P[:] = solver.ctx.get_P()
         for j, td in enumerate(bare + bold):
             P_orders[td.order] += hist[:, j, :]
-        for o in P_orders_std:
-            P_orders_std[o][:] = np.nan   # std of a single sequence (src/randomization.jl:99)
+        for o in P_orders_std:         # std of a single sequence is NaN (src/randomization.jl:99); order 0 is exact
+            if o > 0:                  # (:155), and grid point 0 is never evaluated
+                P_orders_std[o][1:] = np.nan
         return P_orders, P_orders_std
     # first step: bare diagrams (:373-416)
     top_data = [solver.make_entry(MODE_BARE, o, 2 * o, N_samples, rand_params) for o in orders_bare]
@@ -221,12 +246,13 @@ def inchworm(expansion, grid, orders, orders_bare, N_samples, n_pts_after_max=No
         P_orders_std[o][1] = contribs_std[o]
     # the rest of inching (:420-493)
     top_data = _bold_entries(solver, orders, N_samples, rand_params, n_pts_after_max)
-    solver.upload_P()
+    solver.ctx.scale_P(1, value)
     for n in range(1, n_tau - 1):
         value, contribs, contribs_std = inchworm_step(solver, grid, 0, n, n + 1, top_data)
         ppgf.set_ppgf(expansion, n + 1, value)
-        ppgf.normalize_at(expansion, n + 1)  # suppress exponential growth (:488)
-        solver.upload_P()
+        lam = ppgf.normalize_at(expansion, n + 1)  # suppress exponential growth (:488)
+        # the device's table follows with one row and lambda (qiw_scale_P) instead of a re-upload of the whole table
+        solver.ctx.scale_P(n + 1, value, lam)
         for o in contribs:
             P_orders[o][n + 1] = contribs[o]
             P_orders_std[o][n + 1] = contribs_std[o]
@@ -240,6 +266,8 @@ def correlator_2p(expansion, grid, orders, N_samples, rand_params=None, solver=N
     assert N_samples == 0 or (N_samples & (N_samples - 1)) == 0
     rand_params = rand_params or RandomizationParams()
     solver = solver or Solver(expansion)
+    if N_samples == 0:       # sampled entries are skipped (src/inchworm.jl:843): order 0 only
+        orders, N_samples = [o for o in orders if o == 0], 1
     if solver._n_corr_uploaded != len(expansion.corr_operators_mat):
         solver.refresh_model()
     solver.upload_P()
@@ -265,9 +293,13 @@ def correlator_2p(expansion, grid, orders, N_samples, rand_params=None, solver=N
                 tds = top_data[:1] if top_data and top_data[0].order == 0 else []
                 if not tds:
                     continue
-            mean, std = solver.eval_entries(grid.tau[0], grid.tau[k], grid.tau[-1], tds)
-            g[k] = mean[:, diag].sum() / Z      # tr(...) / partition_function (:869,889)
-            g_std[k] = std[:, diag].sum() / Z
+            samples = solver.eval_samples(grid.tau[0], grid.tau[k], grid.tau[-1], tds)
+            # per entry: mean and std over the sequences of tr(...) (the reference integrates the trace, :862-872);
+            # sums over the entries, divided by the partition function (:882-889)
+            for td, x in zip(tds, samples):
+                trs = x[:, diag].sum(axis=1)
+                g[k] += trs.mean() / Z
+                g_std[k] += (0.0 if td.order == 0 else (np.std(trs, ddof=1) if len(trs) > 1 else np.nan)) / Z
         if batched:
             # every grid point tau_k, k >= 1, in ONE launch: the (pair, tau) evaluations are independent (:995-1046)
             times = np.array([[grid.tau[0], grid.tau[k], grid.tau[-1]] for k in range(1, n_tau)])

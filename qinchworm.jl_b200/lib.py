@@ -55,6 +55,7 @@ _SIGNATURES = {
     "qiw_set_grid": (C.c_int, [C.c_void_p, C.c_int32, C.c_double]),
     "qiw_set_delta": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, f64p]),
     "qiw_set_P": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, f64p]),
+    "qiw_scale_P": (C.c_int, [C.c_void_p, C.c_int32, f64p, C.c_double]),
     "qiw_get_P": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, f64p]),
     "qiw_set_topologies": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_int32, i32p, i32p]),
@@ -252,6 +253,15 @@ class Context:
     def set_P(self, first, rows):
         r, rv = _cview(np.atleast_2d(rows))
         self._ck(self.L.qiw_set_P(self.h, first, r.shape[0], _ptr(rv, f64p)))
+
+    def scale_P(self, k_f, row=None, lam=0.0):
+        """qiw_scale_P: set_ppgf! + normalize! across the step seam — row k_f := row (None keeps it), then every stored
+        row k times exp(-lam tau_k); one row and lambda travel instead of the whole table."""
+        if row is None:
+            self._ck(self.L.qiw_scale_P(self.h, k_f, None, float(lam)))
+        else:
+            r, rv = _cview(np.atleast_2d(row))
+            self._ck(self.L.qiw_scale_P(self.h, k_f, _ptr(rv, f64p), float(lam)))
 
     def get_P(self, first=0, count=None):
         count = self.n_tau - first if count is None else count

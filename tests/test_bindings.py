@@ -102,7 +102,25 @@ def test_julia_shim_matches_header():
         assert got == want, "%s: argument classes %s, header %s" % (name, got, want)
     # the reference-facing worker path must be covered: model upload, topologies, P, evaluation, device-resident run
     assert {"qiw_create", "qiw_destroy", "qiw_set_model", "qiw_set_delta", "qiw_set_grid", "qiw_set_P", "qiw_set_topologies",
-            "qiw_eval_seqs", "qiw_eval_batch", "qiw_inchworm_run", "qiw_get_P", "qiw_comm_init", "qiw_peer_init"} <= {c[0] for c in calls}
+            "qiw_eval_seqs", "qiw_eval_batch", "qiw_inchworm_run", "qiw_get_P", "qiw_comm_init", "qiw_peer_init",
+            "qiw_scale_P"} <= {c[0] for c in calls}
+
+
+def test_julia_shim_session_semantics():
+    """What can be checked without a Julia toolchain: the entry cache is keyed on what determines the
+    compiled program — (mode, order, n_pts_after, corr_idx), as inchworm.py does — not on object identity; Session maps
+    the peer mailboxes; the randomisation loop has the reference's early stop (src/randomization.jl:93-99); the step
+    seam sends one row and lambda (qiw_scale_P) instead of re-uploading the table inside inchworm_step."""
+    src = open(os.path.join(ROOT, "julia", "QInchwormCUDA.jl")).read()
+    code = "\n".join(line.split("#")[0] for line in src.splitlines())
+    assert "objectid" not in code
+    assert "key = (Int(mode), Int(td.order), Int(td.n_pts_after), Int(corr_idx))" in code
+    session_ctor = code[code.index("function Session("):code.index("function upload_P!")]
+    assert "init_peer!(s)" in session_ctor
+    ev = code[code.index("function eval_entries("):code.index("function mean_std(")]
+    assert "rp.target_std" in ev and "break" in ev
+    step = code[code.index("function inchworm_step(s::Session"):code.index("function scale_P!")]
+    assert "upload_P!" not in step
 
 
 def _ctypes_class(t):

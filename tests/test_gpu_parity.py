@@ -586,3 +586,142 @@ def test_c4_order4_bold_step_vs_oracle(gpu_ctx, qlib, oracle_lib):
         assert relerr(got[j], ref[j]) < RTOL, (j + 1, relerr(got[j], ref[j]))
     tot, tot_ref = got.sum(axis=0), ref.sum(axis=0)
     assert relerr_elem(tot, tot_ref) < RTOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("arith", ["real", "complex"])
+def test_run_kernel_vs_step_launches(gpu_ctx, qlib, oracle_lib, monkeypatch, arith):
+    """qiw_inchworm_run: the persistent cooperative run kernel (all bold steps in one launch; P and the pair-interaction
+    tables staged in shared memory, one grid barrier per step) against one step kernel per step (QIW_NO_RUN_KERNEL=1)
+    and against the oracle, in both arithmetic modes; sample counts with one job per CTA and with several; a model whose
+    pair-interaction tables are splines (off the P grid) must take the per-step path and still be right."""
+    from qinchworm_b200.inchworm import MODE_BARE, Solver, _bold_entries
+    if arith == "complex":
+        monkeypatch.setenv("QIW_FORCE_COMPLEX", "1")
+    ex, grid, f = models.anderson(n_tau=40)
+    P0 = ex.P.copy()
+    solver = Solver(ex, ctx=gpu_ctx)
+    for N in (2 ** 8, 2 ** 12):
+        bare = [solver.make_entry(MODE_BARE, o, 2 * o, N) for o in range(4)]
+        bold = _bold_entries(solver, range(4), N, None, None)
+        res = {}
+        for mode in ("run", "step"):
+            monkeypatch.setenv("QIW_NO_RUN_KERNEL", "0" if mode == "run" else "1")
+            gpu_ctx.set_P(0, P0)
+            l0 = gpu_ctx.launch_count()
+            hist = gpu_ctx.inchworm_run([t.entry_id for t in bare], [t.entry_id for t in bold], N, want_contribs=True)
+            res[mode] = (gpu_ctx.get_P(), hist, gpu_ctx.launch_count() - l0)
+        assert res["run"][2] == 2 and res["step"][2] == grid.n_tau - 1       # bare step + one run kernel
+        assert relerr(res["run"][0], res["step"][0]) < 1e-13
+        assert relerr(res["run"][1], res["step"][1]) < 1e-13
+        if N == 2 ** 8:
+            ref = oracle_lib.inchworm(ex.flatten(), P0, range(4), range(4), N)["P"]
+            assert relerr(res["run"][0], ref) < RTOL
+    monkeypatch.setenv("QIW_NO_RUN_KERNEL", "0")
+    ex2, grid2, _ = models.single_level(n_tau=20, spline=True)
+    solver2 = Solver(ex2, ctx=gpu_ctx)
+    bare = [solver2.make_entry(MODE_BARE, o, 2 * o, 2 ** 8) for o in range(3)]
+    bold = _bold_entries(solver2, range(4), 2 ** 8, None, None)
+    l0 = gpu_ctx.launch_count()
+    solver2.upload_P()
+    gpu_ctx.inchworm_run([t.entry_id for t in bare], [t.entry_id for t in bold], 2 ** 8, want_contribs=False)
+    assert gpu_ctx.launch_count() - l0 == grid2.n_tau - 1
+    G = load_golden("inchworm_h5.json")
+    assert relerr(gpu_ctx.get_P()[:, 1], G["/inchworm/P/1"].ravel()) < RTOL
+
+
+@pytest.mark.gpu
+def test_block_model_single_launch_and_batching(gpu_ctx, qlib, oracle_lib):
+    """Sector blocks larger than 1x1 (C4-type models): one launch per step (reduction, all-reduce and P update fused into
+    block_walk_kernel's tail), and the batched forms — all grid points of a correlator / all scrambled sequences in one
+    launch (gridDim.z) — equal to the one-by-one evaluation and to the oracle."""
+    from qinchworm_b200.inchworm import Solver, correlator_2p, inchworm
+    ex, grid, f = models.two_band(n_tau=10)
+    solver = Solver(ex, ctx=gpu_ctx)
+    l0 = gpu_ctx.launch_count()
+    inchworm(ex, grid, range(0, 3), range(0, 3), 2 ** 7, solver=solver, device_resident=True)
+    assert gpu_ctx.launch_count() - l0 == grid.n_tau - 1                      # one kernel per step, nothing else
+    refP = oracle_lib.inchworm(ex.flatten(), models.two_band(n_tau=10)[0].P, range(0, 3), range(0, 3), 2 ** 7)["P"]
+    assert relerr(ex.P, refP) < RTOL
+    l0 = gpu_ctx.launch_count()
+    g_b = correlator_2p(ex, grid, range(0, 3), 2 ** 7, solver=solver)[0]
+    n_batched = gpu_ctx.launch_count() - l0
+    g_s = correlator_2p(ex, grid, range(0, 3), 2 ** 7, solver=solver, batch=False)[0]
+    assert n_batched <= 2                                                     # tau = 0 (order 0 only) + all other grid points
+    assert relerr(g_b, g_s) < 1e-13
+    assert relerr(g_b, oracle_lib.correlator_2p(ex.flatten(), ex.P, range(0, 3), 2 ** 7)) < RTOL
+    # scrambled sequences: qiw_eval_seqs in one launch vs one qiw_eval per sequence
+    ids, tds = [], []
+    for order in range(0, 3):
+        for k in ([0] if order == 0 else range(1, 2 * order)):
+            td = solver.make_entry(qlib.MODE_BOLD, order, k, 2 ** 7)
+            if td is not None:
+                ids.append(td.entry_id); tds.append(td)
+    rng = np.random.default_rng(5)
+    seqs = []
+    for s_ in range(3):
+        one = []
+        for td in tds:
+            D = 2 * td.order
+            m = qlib.sobol_direction_numbers(D)
+            one.append(qlib.sobol_scramble(m, rng.integers(0, 2, (D, 32)), rng.integers(0, 2, (D, 32, 32))) if D
+                       else (m, np.zeros(0, dtype=np.uint32)))
+        seqs.append(one)
+    tau = grid.tau
+    l0 = gpu_ctx.launch_count()
+    got = gpu_ctx.eval_seqs(0.0, tau[5], tau[6], ids, 2 ** 7, seqs)
+    assert gpu_ctx.launch_count() - l0 == 1
+    for z in range(3):
+        assert relerr(got[z], gpu_ctx.eval(0.0, tau[5], tau[6], ids, 2 ** 7, sobol=seqs[z])) < 1e-13
+
+
+@pytest.mark.gpu
+def test_step_seam_scale_P(gpu_ctx, qlib):
+    """qiw_scale_P (set_ppgf! + normalize! across the step seam): row k_f := row, then every stored row k times
+    exp(-lambda tau_k) — the device's table follows the host's without a re-upload; N_samples = 0 evaluates order 0 only,
+    as the reference does (src/inchworm.jl:159,258)."""
+    from qinchworm_b200.inchworm import Solver, inchworm
+    ex, grid, f = models.anderson(n_tau=16)
+    solver = Solver(ex, ctx=gpu_ctx)
+    solver.upload_P()
+    P = ex.P.copy()
+    row = (0.3 + 0.1 * np.arange(gpu_ctx.bsize)) * 1j
+    lam = 0.37
+    gpu_ctx.scale_P(5, row, lam)
+    P[5] = row
+    P *= np.exp(-grid.tau * lam)[:, None]
+    assert relerr(gpu_ctx.get_P(), P) < 1e-15
+    gpu_ctx.scale_P(7, row)                       # lambda = 0: the row alone
+    P[7] = row
+    assert relerr(gpu_ctx.get_P(), P) < 1e-15
+    ex0, grid0, _ = models.anderson(n_tau=16)
+    ex1, grid1, _ = models.anderson(n_tau=16)
+    Po0, _ = inchworm(ex0, grid0, range(0, 4), range(0, 4), 0, solver=Solver(ex0, ctx=gpu_ctx))
+    Po1, _ = inchworm(ex1, grid1, [0], [0], 2 ** 6, solver=Solver(ex1, ctx=gpu_ctx))
+    assert relerr(ex0.P, ex1.P) < 1e-15 and set(Po0) == {0}
+
+
+@pytest.mark.gpu
+def test_randomisation_early_stop_per_entry(gpu_ctx, qlib):
+    """mean_std_from_randomization is called per entry (src/inchworm.jl:174, src/randomization.jl:93-99): with a target_std
+    every entry stops on its own criterion — here a huge target stops every sampled entry after its second sequence, so the
+    number of library calls is 1 (order 0, exact, no sequence drawn) + 2 per sampled entry — and a host RNG is consumed
+    entry by entry."""
+    from qinchworm_b200.inchworm import RandomizationParams, Solver, _bold_entries, _scrambled_sequence
+    ex, grid, f = models.anderson(n_tau=16)
+    solver = Solver(ex, ctx=gpu_ctx)
+    rp = RandomizationParams(rng=np.random.default_rng(11), N_seqs=6, target_std=1e6)
+    top = _bold_entries(solver, range(0, 3), 2 ** 6, rp, None)
+    l0 = gpu_ctx.launch_count()
+    smp = solver.eval_samples(0.0, grid.tau[7], grid.tau[8], top)
+    assert gpu_ctx.launch_count() - l0 == 1 + 2 * (len(top) - 1)
+    assert [len(x) for x in smp] == [1] + [2] * (len(top) - 1)
+    # the same stream drawn by hand in the reference's order: entry by entry, two sequences each
+    rng = np.random.default_rng(11)
+    for td, x in zip(top[1:], smp[1:]):
+        for s_ in range(2):
+            seq = _scrambled_sequence(2 * td.order, rng)
+            one = gpu_ctx.eval(0.0, grid.tau[7], grid.tau[8], [td.entry_id], 2 ** 6, sobol=[seq])[0]
+            assert relerr(x[s_], one) < 1e-15
+    mean, std = solver.eval_entries(0.0, grid.tau[7], grid.tau[8], top)
+    assert np.abs(std[0]).max() == 0 and np.isfinite(std[1:]).all()
