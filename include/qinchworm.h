@@ -165,7 +165,7 @@ int qiw_entry_records(qiw_context* ctx, int32_t entry_id, int32_t* info, uint32_
  * with every member's coefficient folded into its first segment product.  Call with NULL arrays to get the sizes.
  *   info[8]             : n_sections, n_items, nSegL, seg_stride, K, order, first slot of the segment table, cost
  *   sections[n_sections][4] : initial sector, M, number of records, first item
- *   items[n_items]      : per record `order` Delta slots, then M * K segment slots, padded to a multiple of 4
+ *   items[n_items]      : per record `order` Delta slots, then M * K segment slots, padded to a multiple of 8
  *   segdef[nSegL][seg_stride] : propagator slots of every segment product (0xFFFF = unused)
  *   seg_coef[nSegL]     : index of the coefficient folded into the product (0xFFFF = none) */
 int qiw_entry_lane_program(qiw_context* ctx, int32_t entry_id, int32_t* info, int32_t* sections, uint32_t* items,

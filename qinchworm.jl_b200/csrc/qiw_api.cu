@@ -668,8 +668,8 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
     if (ctx->no_device) { ed.valid = true; return QIW_OK; }
     if (ctx->model.scalar) {   // the lane program: records (padded by 8 words: the walk fetches one record ahead) and
         // the segment-product table's definitions
-        std::vector<uint4> items(pr.lane_items.size() / 4 + 8, make_uint4(0u, 0u, 0u, 0u));
-        memcpy(items.data(), pr.lane_items.data(), pr.lane_items.size() * sizeof(uint32_t));
+        std::vector<uint4> items(pr.lane_items.size() / 8 + 8, make_uint4(0u, 0u, 0u, 0u));
+        memcpy(items.data(), pr.lane_items.data(), pr.lane_items.size() * sizeof(uint16_t));
         CK(ed.lane_items.upload(items.data(), items.size(), ctx->stream));
         const int st = pr.seg_stride, nw4 = st > 7 ? 2 : 1;
         std::vector<uint16_t> defs((size_t)std::max(pr.nSegL, 1) * nw4 * 8, (uint16_t)0xFFFF);
@@ -776,9 +776,9 @@ int qiw_entry_lane_program(qiw_context* ctx, int32_t id, int32_t* info, int32_t*
     if (sections)
         for (size_t k = 0; k < p.lane_sections.size(); ++k) {
             const auto& sc = p.lane_sections[k];
-            sections[4 * k] = sc.s_i; sections[4 * k + 1] = sc.M; sections[4 * k + 2] = (int32_t)sc.n_rec; sections[4 * k + 3] = (int32_t)(sc.chunk0 * 4u);
+            sections[4 * k] = sc.s_i; sections[4 * k + 1] = sc.M; sections[4 * k + 2] = (int32_t)sc.n_rec; sections[4 * k + 3] = (int32_t)(sc.chunk0 * 8u);
         }
-    if (items) memcpy(items, p.lane_items.data(), p.lane_items.size() * sizeof(uint32_t));
+    if (items) for (size_t k = 0; k < p.lane_items.size(); ++k) items[k] = p.lane_items[k];
     if (segdef) memcpy(segdef, p.lane_segdef.data(), (size_t)p.nSegL * p.seg_stride * sizeof(uint16_t));
     if (seg_coef) memcpy(seg_coef, p.lane_seg_coef.data(), (size_t)p.nSegL * sizeof(uint16_t));
     return QIW_OK;
@@ -879,7 +879,7 @@ static void append_entry_chunks(const EntryProgram& p, int n_chunks, std::vector
             const auto& sec = p.lane_sections[si];
             uint32_t take = sec.n_rec - r_in;
             if (!last) take = (uint32_t)std::min<int64_t>(take, std::max<int64_t>(1, (target - done + sec.cost - 1) / sec.cost));
-            const int ni = lane_record_items(p.order, p.K, sec.M) / 4;
+            const int ni = lane_record_items(p.order, p.K, sec.M) / 8;
             const uint32_t mc = sec.M == 1 ? 0u : (sec.M == 2 ? 1u : 2u);
             runs.push_back(make_uint4(sec.chunk0 + r_in * (uint32_t)ni, take, (uint32_t)sec.s_i,
                                       (uint32_t)(p.order * 16 + (p.K - 1) * 4) + mc));
@@ -1510,7 +1510,7 @@ static int enqueue_run(qiw_context* ctx, Plan& pl, int k_first, int n_steps, dou
             size_t n4 = 8;
             for (uint32_t q = r0; q < r1; ++q) {
                 const uint32_t code = runs[q].w, ni = (code >> 4) + ((((code >> 2) & 3u) + 1u) << (code & 3u));
-                n4 += (size_t)runs[q].y * ((ni + 3u) / 4u);
+                n4 += (size_t)runs[q].y * ((ni + 7u) / 8u);
             }
             const int NW = x.p->seg_stride > 7 ? 2 : 1;
             const size_t bytes = n4 * 16 + (size_t)(r1 - r0) * 16 + (((size_t)(it.n_chunks + 1) * 4 + 15) & ~(size_t)15) +

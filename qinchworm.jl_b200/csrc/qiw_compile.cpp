@@ -503,7 +503,7 @@ void build_lane_program(EntryProgram& e) {
         const int M = Ms[mi], ni = lane_record_items(n, K, M);
         for (int s = 0; s < S; ++s) {
             EntryProgram::LaneSection sec;
-            sec.s_i = s; sec.M = M; sec.rec0 = 0; sec.n_rec = 0; sec.chunk0 = (uint32_t)(e.lane_items.size() / 4);
+            sec.s_i = s; sec.M = M; sec.rec0 = 0; sec.n_rec = 0; sec.chunk0 = (uint32_t)(e.lane_items.size() / 8);
             sec.cost = (uint32_t)(n + M * K + 2);
             for (const Group& g : groups) {
                 if ((int)g.s_i != s) continue;
@@ -515,8 +515,8 @@ void build_lane_program(EntryProgram& e) {
                 else { count = nm % 2; first = (nm / 2) * 2; }
                 for (int c = 0; c < count; ++c) {
                     const size_t base = e.lane_items.size();
-                    for (uint32_t d : g.dsl) e.lane_items.push_back(d);
-                    for (int q = 0; q < M * K; ++q) e.lane_items.push_back(g.members[(size_t)(first + c * M) * K + q]);
+                    for (uint32_t d : g.dsl) e.lane_items.push_back((uint16_t)d);
+                    for (int q = 0; q < M * K; ++q) e.lane_items.push_back((uint16_t)g.members[(size_t)(first + c * M) * K + q]);
                     e.lane_items.resize(base + ni, 0);
                     ++sec.n_rec;
                 }

@@ -33,7 +33,7 @@ struct DevEntry {
     int n_coefs;
     // lane program (EntryProgram::lane_*): what the step kernel executes with lane = sample
     int K, nSegL, seg_stride;   // segments per configuration; entries / propagator slots per entry of the segment table
-    const uint4* lane_items;    // records: `order` Delta slots then M * K segment slots, 32 bits each, padded to 4
+    const uint4* lane_items;    // records: `order` Delta slots then M * K segment slots, 16 bits each, padded to 8
     const uint4* lane_segdef4;  // [nSegL][seg_stride > 7 ? 2 : 1] packed 16-bit fields: index of the coefficient folded into
                                 // the product (0xFFFF = none), then its propagator slots (0xFFFF = unused)
     const double2* coefs;

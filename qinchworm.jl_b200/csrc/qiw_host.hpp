@@ -83,11 +83,12 @@ struct EntryProgram {
     // The coefficient of a member is folded into its first segment product (a table entry of its own per distinct
     // (coefficient, segment) combination: lane_segdef / lane_seg_coef), so a member is a plain product of table slots.
     // Groups are cut into fixed-shape records of M = 4, 2 or 1 members and sorted into sections of equal
-    // (M, initial sector); a record is `order` Delta slots followed by M * K segment slots, 32 bits each (plain slot
-    // numbers of the per-sample table), padded to a multiple of 4 items (one warp-uniform 128-bit load per 4 items).
+    // (M, initial sector); a record is `order` Delta slots followed by M * K segment slots, 16 bits each (plain slot
+    // numbers of the per-sample table), padded to a multiple of 8 items (one warp-uniform 128-bit load per 8 items:
+    // the record stream shares the load pipe with the operand loads, so its width matters).
     struct LaneSection { int32_t s_i, M; uint32_t rec0, n_rec; uint32_t chunk0, cost; };   // chunk0: first 128-bit word; cost per record
     std::vector<LaneSection> lane_sections;
-    std::vector<uint32_t> lane_items;
+    std::vector<uint16_t> lane_items;
     std::vector<uint16_t> lane_segdef;     // [nSegL][seg_stride] propagator slots (0xFFFF = unused)
     std::vector<uint16_t> lane_seg_coef;   // [nSegL] index of the folded coefficient, 0xFFFF = none
     int nSegL = 0;
@@ -106,7 +107,7 @@ int compile_entry(const HostModel& m, int mode, int order, int n_pts_after, int 
 void factorise_records(EntryProgram& e, int S, int K);
 // Group the factorised records into the lane program (EntryProgram::lane_*).
 void build_lane_program(EntryProgram& e);
-inline int lane_record_items(int order, int K, int M) { return ((order + M * K + 3) / 4) * 4; }
+inline int lane_record_items(int order, int K, int M) { return ((order + M * K + 7) / 8) * 8; }
 
 // Host Sobol / topology helpers (qiw_seq.cpp)
 int sobol_direction_numbers(int D, uint32_t* m);

@@ -29,18 +29,21 @@ __device__ __noinline__ typename Num<REAL>::T lane_walk(const uint4* rec, int n_
                                                         unsigned row_bytes) {
     typedef typename Num<REAL>::T T;
     typedef Num<REAL> N;
-    constexpr int NI = ND + M * K, NC = (NI + 3) / 4;
+    constexpr int NI = ND + M * K, NC = (NI + 7) / 8;       // 128-bit words per record: eight 16-bit slot numbers each
     T acc = N::zero();
     uint4 nx[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) nx[c] = rec[c];        // generic loads: the records live in global or shared memory
     for (int r = 0; r < n_rec; ++r) {
-        uint32_t it[NC * 4];
+        uint32_t wd[NC * 4];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) { it[4 * c] = nx[c].x; it[4 * c + 1] = nx[c].y; it[4 * c + 2] = nx[c].z; it[4 * c + 3] = nx[c].w; }
+        for (int c = 0; c < NC; ++c) { wd[4 * c] = nx[c].x; wd[4 * c + 1] = nx[c].y; wd[4 * c + 2] = nx[c].z; wd[4 * c + 3] = nx[c].w; }
         rec += NC;   // the item array is padded: the fetch past the last record stays inside it
 #pragma unroll
         for (int c = 0; c < NC; ++c) nx[c] = rec[c];
+        uint32_t it[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) it[i] = (i & 1) ? (wd[i >> 1] >> 16) : (wd[i >> 1] & 0xFFFFu);
         T v[NI];
 #pragma unroll
         for (int i = 0; i < NI; ++i) v[i] = *reinterpret_cast<const T*>(Tl + it[i] * row_bytes);
@@ -373,7 +376,15 @@ __global__ void __launch_bounds__(768, 1) scalar_step_kernel(const StepParams p)
     // let the next step's grid start as soon as every CTA of this one is running (it waits before it touches P)
     asm volatile("griddepcontrol.launch_dependents;");
     const WorkItem it = p.items[blockIdx.y];
-    const DevEntry& e = p.entries[it.entry];
+    // the entry's description is read in every phase of every sample block: one copy in shared memory
+    __shared__ DevEntry e_s;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.entries + it.entry);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&e_s);
+        for (int k = threadIdx.x; k < (int)(sizeof(DevEntry) / 4); k += blockDim.x) dst[k] = __ldg(src + k);
+    }
+    __syncthreads();
+    const DevEntry& e = e_s;
     const DevEntryDyn& dy = p.dyn[it.slot];
     const int S = p.S, nD = e.nD;
     Cta<REAL> c;
@@ -541,8 +552,14 @@ __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) 
     for (int k = threadIdx.x; k <= n_ent; k += blockDim.x) ejob0_s[k] = rp.entry_job0[k];
     __shared__ double lambda_s;
     const StagedTables<REAL> st = {Ps, Ds};
-    auto view = [&](const RunJob& job, const WorkItem& it, const DevEntry& e) {
-        c.e = &e;
+    __shared__ DevEntry e_s;      // the current job's entry description (read in every phase)
+    auto view = [&](const RunJob& job, const WorkItem& it, const DevEntry& e) {      // followed by a CTA barrier
+        {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(&e);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(&e_s);
+            for (int k = threadIdx.x; k < (int)(sizeof(DevEntry) / 4); k += blockDim.x) dst[k] = __ldg(src + k);
+        }
+        c.e = &e_s;
         c.items = e.lane_items; c.runs = p.runs; c.chunk_off = p.chunk_off; c.chunk0 = it.chunk0; c.n_chunks = it.n_chunks;
         c.segdefs = e.lane_segdef4; c.segcoef = nullptr;
         c.ns = 32 * job.n_sub; c.ns_sh = 31 - __clz(c.ns);
@@ -573,7 +590,7 @@ __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) 
                 uint32_t n4 = 0;
                 for (uint32_t k = r0; k < r1; ++k) {
                     const LaneRun rn = __ldg(p.runs + k);
-                    const uint32_t code = rn.w, ni = (code >> 4) + ((((code >> 2) & 3u) + 1u) << (code & 3u)), len = rn.y * ((ni + 3u) / 4u);
+                    const uint32_t code = rn.w, ni = (code >> 4) + ((((code >> 2) & 3u) + 1u) << (code & 3u)), len = rn.y * ((ni + 7u) / 8u);
                     for (uint32_t q = threadIdx.x; q < len; q += c.nthr) items_s[n4 + q] = __ldg(e.lane_items + rn.x + q);
                     n4 += len;
                 }
@@ -584,7 +601,7 @@ __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) 
                     uint32_t off = 0;
                     for (uint32_t k = r0; k < r1; ++k) {
                         LaneRun rn = __ldg(p.runs + k);
-                        const uint32_t code = rn.w, ni = (code >> 4) + ((((code >> 2) & 3u) + 1u) << (code & 3u)), len = rn.y * ((ni + 3u) / 4u);
+                        const uint32_t code = rn.w, ni = (code >> 4) + ((((code >> 2) & 3u) + 1u) << (code & 3u)), len = rn.y * ((ni + 7u) / 8u);
                         rn.x = off; off += len;
                         runs_s[k - r0] = rn;
                     }
@@ -628,7 +645,7 @@ __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) 
             const DevEntry& e = p.entries[it.entry];
             const DevEntryDyn& dy = p.dyn[it.slot];
             const unsigned long long count = dy.count, local0 = (unsigned long long)job.sb0 * 32ull;
-            if (!single) view(job, it, e);
+            if (!single) { view(job, it, e); __syncthreads(); }
             if (!single) {     // the roots written in the prologue (or recomputed, if the call has no root cache)
                 phase_roots<REAL>(c, dy.sobol, dy.start, local0, count, dy.ucache, dy.ucache != nullptr, false);
                 for (int k = threadIdx.x; k < e.nD; k += c.nthr) { const int4 d = e.dslots[k]; dslots_s[k] = (uint32_t)d.x | ((uint32_t)d.y << 8) | ((uint32_t)d.z << 16); }

@@ -88,7 +88,7 @@ def run_lane_program(lp, prog, expansion, payload, mode, t_i, t_w, t_f, times):
     out = np.zeros(prog["S"], dtype=complex)
     n_members = 0
     for s_i, M, n_rec, item0 in lp["sections"]:
-        ni = (n + M * K + 3) // 4 * 4
+        ni = (n + M * K + 7) // 8 * 8
         for r in range(n_rec):
             it = lp["items"][item0 + r * ni: item0 + (r + 1) * ni]
             d = np.prod([T[int(q)] for q in it[:n]]) if n else 1.0
