@@ -394,7 +394,7 @@ int qiw_set_model(qiw_context* ctx, int32_t S, const int32_t* dims, const double
         CK(ctx->dPoolRe.upload(pre.data(), pre.size(), ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
-    if (m.maxdim > 4) return fail(ctx, QIW_ERR_UNSUPPORTED, "qiw_set_model: sector blocks larger than 4x4 are not supported");
+    if (m.maxdim > 8) return fail(ctx, QIW_ERR_UNSUPPORTED, "qiw_set_model: sector blocks larger than 8x8 are not supported");
     for (auto& e : ctx->entries) if (e) e->valid = false;   // programs depend on the model
     ctx->entries_dirty = true;
     drop_plans(ctx);
@@ -661,7 +661,7 @@ int qiw_set_topologies(qiw_context* ctx, int32_t entry_id, int32_t mode, int32_t
     int rc = compile_entry(ctx->model, mode, order, n_pts_after, corr_idx, n_top, pairs, parity, ed.prog, err);
     if (rc) return fail(ctx, rc, "qiw_set_topologies: " + err);
     const EntryProgram& pr = ed.prog;
-    if (!ctx->model.scalar) {
+    if (!ctx->model.scalar && ctx->model.maxdim <= 4) {
         rc = build_walk_units(ctx->model, pr, ed, err);
         if (rc) return fail(ctx, rc, "qiw_set_topologies: " + err);
     }
@@ -858,7 +858,7 @@ static void release_plan(Plan& pl) {
 // purely imaginary, the folded coefficients purely imaginary.  QIW_FORCE_COMPLEX=1
 // disables it (tests compare the two modes).
 static bool real_mode_possible(qiw_context* ctx, int n_entries, const int32_t* ids) {
-    if (!ctx->model.scalar && !ctx->pool_real) return false;
+    if (!ctx->model.scalar && (!ctx->pool_real || ctx->model.maxdim > 4)) return false;   // the real-arithmetic walker has shapes up to 4x4
     if (const char* env = getenv("QIW_FORCE_COMPLEX")) if (env[0] == '1') return false;
     for (auto& t : ctx->tables) if (t.n > 0 && !t.imag_only) return false;
     for (uint8_t c : ctx->p_row_complex) if (c) return false;

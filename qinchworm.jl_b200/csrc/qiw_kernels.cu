@@ -144,9 +144,9 @@ namespace qiw {
 // src/topology_eval.jl:454-556 with the reference's own prefix sharing: the running product
 // A_pos ... A_1 (src/utility.jl:234-323) is kept on a per-thread stack, one (d x d_init) matrix per tree
 // level.  Node matrix = operator block times i P_s(t_pos, t_pos-1) (:376-388).  Blocks are at most
-// kMaxBlockDim x kMaxBlockDim.  This path favours generality over speed: all BASELINE headline
-// configurations have 1x1 blocks and use the scalar kernel.
-constexpr int kMaxBlockDim = 4;
+// MAXD x MAXD (instantiated for 4 and 8).  This path favours generality over speed: complex hybridisation functions,
+// per-sample evaluation (qiw_eval_at_times) and sector blocks of 5 to 8 rows, for which the real-arithmetic walker
+// (block_walk_kernel, blocks <= 4x4) has no shapes; all BASELINE configurations run on the scalar kernel or the walker.
 
 __device__ __forceinline__ double2 zero2() { return make_double2(0.0, 0.0); }
 // tree word fields (qiw_host.hpp make_word)
@@ -155,6 +155,7 @@ __device__ __forceinline__ uint32_t w_slotB(uint64_t w) { return ((uint32_t)w >>
 __device__ __forceinline__ uint32_t w_nchild(uint64_t w) { return ((uint32_t)w >> 24) & 0xFFu; }
 __device__ __forceinline__ uint32_t w_aux(uint64_t w) { return (uint32_t)(w >> 32) & 0xFFFFu; }
 
+template <int MAXD>
 __global__ void __launch_bounds__(64) block_step_kernel(const StepParams p, const BlockParams bp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const WorkItem it = p.items[blockIdx.y];
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(64) block_step_kernel(const StepParams p, cons
             dl[q] = times_i(delta_eval(p.deltas[ds.z], tt, th));
         }
         // -- replay the trees --------------------------------------------------------------------------
-        double2 V[kDevMaxNodes + 1][kMaxBlockDim * kMaxBlockDim];   // V[level]: (dim_cur x d_init), column-major
+        double2 V[kDevMaxNodes + 1][MAXD * MAXD];   // V[level]: (dim_cur x d_init), column-major
         int rem[kDevMaxNodes + 1];
         for (int t = tree0; t < tree1; ++t) {
             uint32_t pc = toff[t];
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(64) block_step_kernel(const StepParams p, cons
                 const int iv = depth - 1;   // the node sits at position depth+1: interval depth-1
                 const double2* Pm = iP + (size_t)iv * bsize + m.boff[s];
                 const double2* Vp = V[depth];
-                double2 tmp[kMaxBlockDim * kMaxBlockDim];
+                double2 tmp[MAXD * MAXD];
                 for (int j = 0; j < d0; ++j)           // tmp = iP_s * V_parent   (d_s x d0)
                     for (int i = 0; i < ds_; ++i) {
                         double2 a = zero2();
@@ -325,7 +326,8 @@ __global__ void __launch_bounds__(64) block_step_kernel(const StepParams p, cons
 }
 
 cudaError_t launch_block_step(const StepParams& p, const BlockParams& bp, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    block_step_kernel<<<grid, threads, smem, st>>>(p, bp);
+    if (bp.m.maxdim <= 4) block_step_kernel<4><<<grid, threads, smem, st>>>(p, bp);
+    else block_step_kernel<8><<<grid, threads, smem, st>>>(p, bp);
     return cudaGetLastError();
 }
 

@@ -151,6 +151,13 @@ class Solver:
         if not top_data:
             z = np.zeros((0, self.ctx.bsize), dtype=complex)
             return z, z
+        rp = top_data[0].rand_params
+        if rp.rng is None and rp.N_seqs == 1:
+            # the default (one unscrambled sequence): the estimate itself, no statistics — one library call, no per-entry work
+            mean = self.ctx.eval(t_i, t_w, t_f, [td.entry_id for td in top_data], top_data[0].N_samples)
+            std = np.full_like(mean, np.nan)
+            std[[j for j, td in enumerate(top_data) if td.order == 0]] = 0.0  # exact evaluation (src/inchworm.jl:155)
+            return mean, std
         samples = self.eval_samples(t_i, t_w, t_f, top_data)
         mean = np.array([x.mean(axis=0) for x in samples])
         std = np.full_like(mean, np.nan)
@@ -164,11 +171,9 @@ class Solver:
 
 def _order_sums(top_data, mean, std, bsize):
     orders = sorted({td.order for td in top_data})
-    contribs = {o: np.zeros(bsize, dtype=complex) for o in orders}
-    contribs_std = {o: np.zeros(bsize, dtype=complex) for o in orders}
-    for j, td in enumerate(top_data):
-        contribs[td.order] = contribs[td.order] + mean[j]
-        contribs_std[td.order] = contribs_std[td.order] + std[j]
+    ord_of = np.array([td.order for td in top_data])
+    contribs = {o: mean[ord_of == o].sum(axis=0) if len(mean) else np.zeros(bsize, dtype=complex) for o in orders}
+    contribs_std = {o: std[ord_of == o].sum(axis=0) if len(std) else np.zeros(bsize, dtype=complex) for o in orders}
     total = sum(contribs.values()) if contribs else np.zeros(bsize, dtype=complex)
     return total, contribs, contribs_std
 

@@ -155,7 +155,7 @@ def three_orbital(n_tau=12, beta=2.0):
     return ex, grid, f
 
 
-def two_band(n_tau=16, beta=8.0, U=2.0, J=0.2, e_k=2.3):
+def two_band(n_tau=16, beta=8.0, U=2.0, J=0.2, e_k=2.3, big_blocks=False):
     """bench/two_band_eg_model_discrete_bath: two-band e_g model, 16 Fock states, 9 sectors with
     dimensions {1,1,1,1,2,2,2,2,4}, 16 interaction pairs, discrete bath."""
     labels = [[s, o] for s in ("up", "dn") for o in (1, 2)]
@@ -168,6 +168,11 @@ def two_band(n_tau=16, beta=8.0, U=2.0, J=0.2, e_k=2.3):
     H = H - J * sum(cd("up", o1) @ cd("dn", o1) @ c("up", o2) @ c("dn", o2) for o1 in (1, 2) for o2 in (1, 2) if o1 != o2)
     H = H - J * sum(cd("up", o1) @ cd("dn", o2) @ c("up", o2) @ c("dn", o1) for o1 in (1, 2) for o2 in (1, 2) if o1 != o2)
     sb = [cd("up", 1) @ c("up", 2) + cd("up", 2) @ c("up", 1), cd("dn", 1) @ c("dn", 2) + cd("dn", 2) @ c("dn", 1)]
+    if big_blocks:
+        # the same model resolved by particle number only (a spin-flip breaker merges the S_z sectors): sector
+        # dimensions {1,4,6,4,1}, i.e. blocks larger than 4x4 (north_star's "sector blocks large enough to be a dense
+        # contraction"); physics unchanged, only the bookkeeping of the blocks differs
+        sb = sb + [sum(cd("up", o) @ c("dn", o) + cd("dn", o) @ c("up", o) for o in (1, 2))]
     ed = EDCore(f, H, sb)
     grid = ImaginaryTimeGrid(beta, n_tau)
     Delta = delta_dos_gf(grid, [e_k, -e_k], [1.0, 1.0])

@@ -725,3 +725,44 @@ def test_randomisation_early_stop_per_entry(gpu_ctx, qlib):
             assert relerr(x[s_], one) < 1e-15
     mean, std = solver.eval_entries(0.0, grid.tau[7], grid.tau[8], top)
     assert np.abs(std[0]).max() == 0 and np.isfinite(std[1:]).all()
+
+
+@pytest.mark.gpu
+def test_blocks_larger_than_4x4(gpu_ctx, qlib, oracle_lib):
+    """Sector blocks of 5 to 8 rows (north_star's "sector blocks large enough to be a dense contraction"): the two-band
+    model resolved by particle number only has blocks {1,4,6,4,1}.  Bold / bare / correlator steps against the oracle
+    (itself checked against the brute-force Fock-space formula for this model, tests/test_oracle_golden.py), and — a
+    size-independent property — the whole run must give the same partition function and the same density matrix in the
+    Fock basis as the 9-sector bookkeeping {1,1,1,1,2,2,2,2,4} of the same model on the same Sobol points."""
+    from qinchworm_b200 import ppgf
+    from qinchworm_b200.inchworm import Solver, inchworm
+    ex, grid, f = models.two_band(n_tau=10, big_blocks=True)
+    assert max(ex.dims) == 6
+    solver = Solver(ex, ctx=gpu_ctx)
+    o = oracle_lib.Oracle(solver.payload, ex.P)
+    tau = grid.tau
+    eid = 0
+    for mode, (ki, kw, kf) in ((qlib.MODE_BOLD, (0, 5, 6)), (qlib.MODE_BARE, (0, 0, 1)), (qlib.MODE_CORR, (0, 4, 9))):
+        ids = []
+        for order in range(0, 3):
+            ks = [None] if mode == qlib.MODE_BARE else ([0] if order == 0 else (1, 2 * order - 1))
+            for k in ks:
+                pr, pa = qlib.topologies(order, None if mode == qlib.MODE_BARE else k, mode == qlib.MODE_CORR)
+                if len(pa) == 0:
+                    continue
+                kk = 2 * order if mode == qlib.MODE_BARE else k
+                gpu_ctx.set_topologies(200 + eid, mode, order, kk, pr, pa)
+                o.set_topologies(eid, mode, order, kk, pr, pa)
+                ids.append(eid)
+                eid += 1
+        got = gpu_ctx.eval(tau[ki], tau[kw], tau[kf], [200 + i for i in ids], 2 ** 6)
+        ref = o.eval(tau[ki], tau[kw], tau[kf], ids, 2 ** 6)
+        assert relerr(got, ref) < RTOL, (mode, relerr(got, ref))
+    rho = []
+    for big in (True, False):
+        exr, gridr, _ = models.two_band(n_tau=8, big_blocks=big)
+        inchworm(exr, gridr, range(0, 3), range(0, 3), 2 ** 6, solver=Solver(exr, ctx=gpu_ctx))
+        Z = ppgf.partition_function(exr)
+        rho.append(exr.ed.to_fock_basis(ppgf.density_matrix(exr)) / Z)
+        assert abs(np.trace(rho[-1]) - 1.0) < 1e-13
+    assert np.abs(rho[0] - rho[1]).max() < 1e-10

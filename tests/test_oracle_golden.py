@@ -247,7 +247,7 @@ def test_block_basis_rotation_invariance(oracle_lib):
     assert np.abs(vals[0] - vals[1]).max() < 1e-12
 
 
-@pytest.mark.parametrize("name", ["two_level_mixed", "three_orbital", "two_band"])
+@pytest.mark.parametrize("name", ["two_level_mixed", "three_orbital", "two_band", "two_band_big_blocks"])
 def test_block_brute_force_fock_space(oracle_lib, name):
     """d_s > 1 is unpinned at the reference level: check the oracle's sector-block DFS against
     a brute-force evaluation of the naive formula (src/configuration.jl:402-411,492-520) in the FULL Fock
@@ -263,6 +263,10 @@ def test_block_brute_force_fock_space(oracle_lib, name):
     elif name == "three_orbital":   # 3x3 sector blocks, 10 pairs: orders <= 2 keep the brute force (pairs^order assignments) short
         ex, grid, f = models.three_orbital(n_tau=12)
         cases = ((1, 1), (2, 1), (2, 3))
+    elif name == "two_band_big_blocks":   # the same model resolved by particle number only: blocks up to 6x6 (> 4x4)
+        ex, grid, f = models.two_band(n_tau=12, big_blocks=True)
+        assert sorted(ex.dims) == [1, 1, 4, 4, 6] and len(ex.pairs) == 16
+        cases = ((1, 1), (2, 2))
     else:   # the C4 model itself (bench/two_band_eg_model_discrete_bath): 9 sectors, blocks 1/2/4, 16 pairs
         ex, grid, f = models.two_band(n_tau=12)
         assert sorted(ex.dims) == [1, 1, 1, 1, 2, 2, 2, 2, 4] and len(ex.pairs) == 16
