@@ -632,6 +632,10 @@ __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) 
 #else
 #define QIW_RT(k_)
 #endif
+    // single-job CTAs: the times and the pair-interaction rows of the COMING step do not depend on this step's result;
+    // they are prepared between sending this rank's block sums to the peers and waiting for theirs (`pre`), which takes
+    // the NVLink round trip of the all-reduce off the step's critical path
+    bool pre = false;
     for (int step = 0; step < rp.n_steps; ++step) {
         const int k_w = rp.k_first + step, k_f = k_w + 1;
         const double t_i = 0.0, t_w = (double)k_w * h, t_f = (double)k_f * h;
@@ -652,10 +656,12 @@ __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) 
             }
             for (int k = threadIdx.x; k < S * c.nw; k += c.nthr) c.red[k] = make_double2(0.0, 0.0);
             if (!single) __syncthreads();
-            phase_times<REAL>(c, t_i, t_w, t_f, n_tau, p.inv_h, nullptr, local0, count);
-            __syncthreads();
+            if (!pre) {
+                phase_times<REAL>(c, t_i, t_w, t_f, n_tau, p.inv_h, nullptr, local0, count);
+                __syncthreads();
+                phase_fill_delta<REAL, true>(c, p, st);
+            }
             if (jj == jb0) { QIW_RT(1) }
-            phase_fill_delta<REAL, true>(c, p, st);
             phase_fill_P<REAL, true>(c, p, st);
             __syncthreads();
             if (jj == jb0) { QIW_RT(2) }
@@ -744,6 +750,15 @@ __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) 
                         asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(half), "r"(seq32) : "memory");
                     }
                 }
+            }
+            // the coming step's times and pair-interaction rows while the peers' sums are in flight
+            if (single && step + 1 < rp.n_steps) {
+                const RunJob job = rp.jobs[jb0];
+                const unsigned long long count = p.dyn[p.items[job.item].slot].count, local0 = (unsigned long long)job.sb0 * 32ull;
+                phase_times<REAL>(c, 0.0, (double)(k_w + 1) * h, (double)(k_f + 1) * h, n_tau, p.inv_h, nullptr, local0, count);
+                __syncthreads();
+                phase_fill_delta<REAL, true>(c, p, st);
+                pre = true;
             }
             const unsigned char* base = p.peer_mail[p.peer_rank] + kPeerFlagBytes;
             const unsigned long long t0 = globaltimer_ns();
