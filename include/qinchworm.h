@@ -241,7 +241,7 @@ int qiw_launch_count(qiw_context* ctx, int64_t* n);
 
 /* Per-kernel device timing (CUDA events on the launching stream around every launch).  Classes:
  * 0 step kernel in complex arithmetic, 1 step kernel in real arithmetic (1x1-block models), 2 persistent run kernel
- * (all bold steps of qiw_inchworm_run in one launch), 4 reduction,
+ * (all bold steps of qiw_inchworm_run in one launch), 3 FP64 tensor-core kernel for sector blocks of 5 to 8 rows, 4 reduction,
  * 5 per-step state update, 6 NCCL all-reduce, 7 step kernel for sector blocks larger than 1x1.  Profiling serialises nothing but adds two event records per launch; keep it
  * off for timed runs.  qiw_profile_read synchronises, returns accumulated ms and launch counts per
  * class (arrays of QIW_PROFILE_CLASSES) and optionally resets them. */

@@ -32,6 +32,8 @@ cudaError_t launch_sobol_points(int D, const uint32_t* m, const uint32_t* x0, un
                                 unsigned long long count, uint32_t* out, cudaStream_t st);
 cudaError_t launch_dfma_peak(double* out, int blocks, int iters, cudaStream_t st);
 cudaError_t launch_block_step(const StepParams& p, const BlockParams& bp, dim3 grid, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_block_mma(const StepParams& p, const BlockParams& bp, const BlockWalkParams& wp, dim3 grid, int threads,
+                             size_t smem, cudaStream_t st);
 cudaError_t launch_block_walk(const StepParams& p, const BlockParams& bp, const BlockWalkParams& wp, dim3 grid, int threads,
                               size_t smem, cudaStream_t st);
 }  // namespace qiw
@@ -134,7 +136,8 @@ struct Plan {   // launch plan of one qiw_eval call shape, cached
     int pitch = 1;
     int block_threads = 0;                 // block models: threads per CTA
     size_t scratch_per_thread = 0;
-    bool block_real = false;               // block models: planned for the real-arithmetic tree replay
+    bool block_real = false;               // block models: planned for the real-arithmetic tree replay (blocks up to 4x4)
+    bool block_mma = false;                // block models with blocks of 5 to 8 rows, real arithmetic: FP64 tensor-core kernel
     DevBuf<int> d_bounds;                  // [n_items][warps + 1] tree ranges (block_walk_kernel)
     int bw_warps = 0, bw_max_sp = 0, bw_nI = 0, bw_nD = 0;
     DevBuf<uint32_t> d_sobol;
@@ -858,7 +861,7 @@ static void release_plan(Plan& pl) {
 // purely imaginary, the folded coefficients purely imaginary.  QIW_FORCE_COMPLEX=1
 // disables it (tests compare the two modes).
 static bool real_mode_possible(qiw_context* ctx, int n_entries, const int32_t* ids) {
-    if (!ctx->model.scalar && (!ctx->pool_real || ctx->model.maxdim > 4)) return false;   // the real-arithmetic walker has shapes up to 4x4
+    if (!ctx->model.scalar && !ctx->pool_real) return false;
     if (const char* env = getenv("QIW_FORCE_COMPLEX")) if (env[0] == '1') return false;
     for (auto& t : ctx->tables) if (t.n > 0 && !t.imag_only) return false;
     for (uint8_t c : ctx->p_row_complex) if (c) return false;
@@ -897,7 +900,7 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         Plan& c = *up;
         if (c.count == count && c.explicit_mode == explicit_mode && (int)c.ids.size() == n_entries &&
             std::equal(ids, ids + n_entries, c.ids.begin()) &&
-            (ctx->model.scalar || c.block_real == (!explicit_mode && real_mode_possible(ctx, n_entries, ids)))) { *out = &c; return QIW_OK; }
+            (ctx->model.scalar || (c.block_real || c.block_mma) == (!explicit_mode && real_mode_possible(ctx, n_entries, ids)))) { *out = &c; return QIW_OK; }
     }
     if (ctx->plans.size() >= 6) { release_plan(*ctx->plans.front()); ctx->plans.erase(ctx->plans.begin()); }
     std::unique_ptr<Plan> pl(new Plan());
@@ -906,7 +909,7 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
     const int S = ctx->model.S;
     int ndev_sm = 148;
     cudaDeviceGetAttribute(&ndev_sm, cudaDevAttrMultiProcessorCount, ctx->device);
-    if (!ctx->model.scalar && !explicit_mode && real_mode_possible(ctx, n_entries, ids)) {
+    if (!ctx->model.scalar && !explicit_mode && ctx->model.maxdim <= 4 && real_mode_possible(ctx, n_entries, ids)) {
         // Block models, real arithmetic: CTA = (entry, 32 samples, group of tree chunks), W warps per CTA,
         // every warp replays a contiguous range of the entry's trees of about equal cost (live edges).
         pl->block_real = true;
@@ -980,6 +983,50 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         pl->max_sb = n_sb;
         pl->block_threads = 0;
         pl->bw_warps = Wn; pl->bw_max_sp = max_sp; pl->bw_nI = nI_max; pl->bw_nD = nD_max;
+    } else if (!ctx->model.scalar && !explicit_mode && real_mode_possible(ctx, n_entries, ids)) {
+        // Blocks of 5 to 8 rows, real arithmetic: FP64 tensor cores (block_mma_kernel), warp = sample.
+        // CTA = (entry, chunk of its trees, Wn consecutive samples).
+        pl->block_mma = true;
+        const int bs = ctx->model.bsize;
+        int nI_max = 1, nD_max = 1;
+        for (int i = 0; i < n_entries; ++i) {
+            const EntryProgram& p = ctx->entries[ids[i]]->prog;
+            nI_max = std::max(nI_max, p.n_nodes - 1);
+            nD_max = std::max(nD_max, (int)p.dslots.size());
+        }
+        auto smem_of = [&](int Wn) { return (size_t)Wn * ((size_t)nI_max * bs + nD_max + (kDevMaxNodes + 1) + bs) * sizeof(double); };
+        int Wn = 8;
+        while (Wn > 1 && smem_of(Wn) > (size_t)100 * 1024) Wn >>= 1;      // two CTAs per SM
+        if (smem_of(Wn) > (size_t)226 * 1024) return fail(ctx, QIW_ERR_UNSUPPORTED, "per-sample block tables exceed shared memory");
+        uint64_t n_sb_max = 1;
+        for (int i = 0; i < n_entries; ++i) {
+            const EntryProgram& p = ctx->entries[ids[i]]->prog;
+            n_sb_max = std::max<uint64_t>(n_sb_max, ((p.order == 0 ? 1 : count) + Wn - 1) / Wn);
+        }
+        const int split = (int)std::max<double>(1.0, std::ceil(8.0 * ndev_sm / ((double)n_entries * (double)n_sb_max)));
+        pl->item0.resize(n_entries); pl->n_items.resize(n_entries);
+        for (int i = 0; i < n_entries; ++i) {
+            const EntryProgram& p = ctx->entries[ids[i]]->prog;
+            const int n_trees = (int)p.tree_off.size() - 1;
+            const int n_chunks = std::max(1, std::min(n_trees, split));
+            pl->item0[i] = (int)pl->items.size();
+            for (int c0 = 0; c0 < n_chunks; ++c0) {
+                WorkItem it;
+                it.entry = ids[i]; it.slot = i; it.chunk0 = c0; it.n_chunks = 1; it.n_chunks_total = n_chunks;
+                it.partial0 = (int)pl->items.size();
+                pl->items.push_back(it);
+            }
+            pl->n_items[i] = n_chunks;
+        }
+        Plan::Group g;
+        g.item0 = 0; g.max_slots = 1; g.max_dslots = 1;
+        g.n_items = (int)pl->items.size();
+        g.smem[0] = g.smem[1] = smem_of(Wn);
+        g.spb[0] = g.spb[1] = Wn;
+        pl->groups.push_back(g);
+        pl->max_sb = n_sb_max;
+        pl->block_threads = 0;
+        pl->bw_warps = Wn; pl->bw_nI = nI_max; pl->bw_nD = nD_max;
     } else if (!ctx->model.scalar) {
         // Block models, complex arithmetic (general fallback on the device) and per-sample evaluation:
         // one thread per (sample, chunk of trees); 64 samples per CTA.
@@ -1238,7 +1285,7 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
     sp.partials = pl.d_partials.p;
     sp.finish_k_f = -1;
     sp.sobol_z_stride = sobol_z_stride;
-    if ((m.scalar || pl.block_real) && !pl.explicit_mode) {
+    if ((m.scalar || pl.block_real || pl.block_mma) && !pl.explicit_mode) {
         const size_t need = (size_t)std::max(n_times, 1);
         if (ctx->dCounter.cap < need) {
             CK(cudaStreamSynchronize(ctx->stream));
@@ -1285,8 +1332,15 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         bp.scratch = ctx->dScratch.p; bp.scratch_per_thread = pl.scratch_per_thread;
         StepParams gp = sp;
         gp.items = pl.d_items.p;
-        dim3 grid((unsigned)pl.pitch, (unsigned)pl.items.size(), (unsigned)(pl.block_real ? std::max(n_times, 1) : 1));
-        if (pl.block_real) {
+        dim3 grid((unsigned)pl.pitch, (unsigned)pl.items.size(), (unsigned)((pl.block_real || pl.block_mma) ? std::max(n_times, 1) : 1));
+        if (pl.block_mma) {
+            BlockWalkParams wp;
+            memset(&wp, 0, sizeof(wp));
+            wp.pool_re = ctx->dPoolRe.p; wp.warps = pl.bw_warps; wp.nI_max = pl.bw_nI; wp.nD_max = pl.bw_nD;
+            ctx->last_real_mode = 1;
+            ProfScope ps(ctx, 3);
+            CK(launch_block_mma(gp, bp, wp, grid, pl.bw_warps * 32, pl.groups[0].smem[0], ctx->stream));
+        } else if (pl.block_real) {
             BlockWalkParams wp;
             wp.pool_re = ctx->dPoolRe.p; wp.xwords = ctx->dXWordsPtr.p; wp.unit_off = ctx->dXTreeOffPtr.p; wp.chunk_bounds = pl.d_bounds.p; wp.warps = pl.bw_warps; wp.max_sp = pl.bw_max_sp;
             wp.nI_max = pl.bw_nI; wp.nD_max = pl.bw_nD;
@@ -1338,7 +1392,7 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
             fclose(f);
         }
     }
-    if (!pl.explicit_mode && !m.scalar && !pl.block_real) {
+    if (!pl.explicit_mode && !m.scalar && !pl.block_real && !pl.block_mma) {
         {
             ProfScope ps(ctx, 4);
             CK(launch_reduce(pl.d_dyn.p, ctx->dEntries.p, pl.d_partials.p, pl.pitch, m.bsize, t_i, t_w, t_f, pl.d_out.p,
@@ -1770,7 +1824,7 @@ int qiw_eval_batch(qiw_context* ctx, int32_t n_times, const double* times, int32
     rc = get_plan(ctx, n_entries, ids, count, false, &plp);
     if (rc) return rc;
     Plan& pl = *plp;
-    if (!m.scalar && !pl.block_real) {   // block models in complex arithmetic: one launch per triple (the general block kernel has no batched form)
+    if (!m.scalar && !pl.block_real && !pl.block_mma) {   // block models in complex arithmetic: one launch per triple (the general block kernel has no batched form)
         for (int z = 0; z < n_times; ++z) {
             rc = qiw_eval(ctx, times[3 * z], times[3 * z + 1], times[3 * z + 2], n_entries, ids, sobol_m, sobol_x0, N_total,
                           out + (size_t)z * n_entries * m.bsize * 2);
@@ -1821,7 +1875,7 @@ int qiw_eval_seqs(qiw_context* ctx, double t_i, double t_w, double t_f, int32_t 
     rc = get_plan(ctx, n_entries, ids, count, false, &plp);
     if (rc) return rc;
     Plan& pl = *plp;
-    if (!m.scalar && !pl.block_real) {   // block models in complex arithmetic: one launch per sequence
+    if (!m.scalar && !pl.block_real && !pl.block_mma) {   // block models in complex arithmetic: one launch per sequence
         for (int z = 0; z < n_seqs; ++z) {
             rc = qiw_eval(ctx, t_i, t_w, t_f, n_entries, ids, sobol_m + (size_t)z * md, sobol_x0 + (size_t)z * xd, N_total,
                           out + (size_t)z * n_entries * m.bsize * 2);

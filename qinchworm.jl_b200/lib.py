@@ -403,7 +403,7 @@ class Context:
                                          _ptr(hist.view(np.float64), f64p) if want_contribs else None))
         return hist
 
-    PROFILE_CLASSES = ("step_complex", "step_real", "run_kernel", "unused3", "reduce", "finish_step",
+    PROFILE_CLASSES = ("step_complex", "step_real", "run_kernel", "block_mma", "reduce", "finish_step",
                        "nccl_allreduce", "step_block")
 
     def profile_enable(self, on=True):

@@ -728,14 +728,19 @@ def test_randomisation_early_stop_per_entry(gpu_ctx, qlib):
 
 
 @pytest.mark.gpu
-def test_blocks_larger_than_4x4(gpu_ctx, qlib, oracle_lib):
-    """Sector blocks of 5 to 8 rows (north_star's "sector blocks large enough to be a dense contraction"): the two-band
+@pytest.mark.parametrize("arith", ["real", "complex"])
+def test_blocks_larger_than_4x4(gpu_ctx, qlib, oracle_lib, monkeypatch, arith):
+    """Real arithmetic: block_mma_kernel (FP64 tensor cores, mma.sync.m8n8k4.f64, warp = sample); complex arithmetic
+    (QIW_FORCE_COMPLEX=1): the general block_step_kernel<8>.
+    Sector blocks of 5 to 8 rows (north_star's "sector blocks large enough to be a dense contraction"): the two-band
     model resolved by particle number only has blocks {1,4,6,4,1}.  Bold / bare / correlator steps against the oracle
     (itself checked against the brute-force Fock-space formula for this model, tests/test_oracle_golden.py), and — a
     size-independent property — the whole run must give the same partition function and the same density matrix in the
     Fock basis as the 9-sector bookkeeping {1,1,1,1,2,2,2,2,4} of the same model on the same Sobol points."""
     from qinchworm_b200 import ppgf
     from qinchworm_b200.inchworm import Solver, inchworm
+    if arith == "complex":
+        monkeypatch.setenv("QIW_FORCE_COMPLEX", "1")
     ex, grid, f = models.two_band(n_tau=10, big_blocks=True)
     assert max(ex.dims) == 6
     solver = Solver(ex, ctx=gpu_ctx)
@@ -758,6 +763,7 @@ def test_blocks_larger_than_4x4(gpu_ctx, qlib, oracle_lib):
         got = gpu_ctx.eval(tau[ki], tau[kw], tau[kf], [200 + i for i in ids], 2 ** 6)
         ref = o.eval(tau[ki], tau[kw], tau[kf], ids, 2 ** 6)
         assert relerr(got, ref) < RTOL, (mode, relerr(got, ref))
+        prof = gpu_ctx.profile_read(reset=True) if False else None
     rho = []
     for big in (True, False):
         exr, gridr, _ = models.two_band(n_tau=8, big_blocks=big)
