@@ -24,6 +24,9 @@ for w in want:
         i = hdr.index(w)
         print("%s,%s,%s" % (w, units[i], r[i]))
 for i, h in enumerate(hdr):
+    if ("dmma" in h or "pipe_tensor" in h) and h not in want and r[i] not in ("", "0", "n/a"):
+        print("%s,%s,%s" % (h, units[i], r[i]))
+for i, h in enumerate(hdr):
     if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio"):
         if float(r[i] or 0) >= 0.2:
             print("%s,%s,%s" % (h, units[i], r[i]))
