@@ -8,15 +8,17 @@ index range, one ncclAllReduce per inchworm step).  One "step" = one complete in
 (bare step + 198 bold steps) = 5.69e7 diagram evaluations per 2^10 samples.
 
     value : diagram evaluations/s of the device-resident run (qiw_inchworm_run; tables resident in
-            HBM, CUDA events on the library's stream around the whole run), max over ranks
+            HBM, CUDA events on the library's stream around the whole run), max over ranks.  The run is two launches: one
+            step kernel for the bare step, one persistent cooperative run kernel for the 198 bold steps
     e2e   : the same metric through the public host API inchworm(expansion, grid, orders, orders_bare,
             N_samples) with HOST buffers: the atomic P table goes host->device, the final P table and the
             order-resolved contributions come back device->host inside the timed region (compiled
-            entries are cached in the Solver, like the context).  `host_stepped` is the same call with
-            device_resident=False: one qiw_eval per step, P re-uploaded after every host-side
-            set_ppgf!/normalize! — what the thin Julia shim does.
-    roofline     : dominant kernel (step kernel, tree depth <= 11 = orders 3-4) against the FP64 FMA
-                   peak measured in the same process by a DFMA-saturating kernel
+            entries are cached in the Solver, like the context).  `e2e_stepped` is the same call with
+            device_resident=False: one qiw_eval per step through the three-worker seam, set_ppgf!/normalize! on the host,
+            the device's table following with qiw_scale_P (one row + lambda) — what the thin Julia shim does.
+    roofline     : dominant kernel (the run kernel) against the FP64 FMA peak measured in the same process by a
+                   DFMA-saturating kernel: `frac` credits the reference's complex chain, `executed` is what the kernel
+                   executes (FP64 instructions, shared-memory operands) next to ncu's counters of the committed capture
     cpu_baseline : the CPU oracle port (faithful restatement of the reference algorithm), all host
                    cores, on a bounded sample of the same workload
 
@@ -25,6 +27,9 @@ index range, one ncclAllReduce per inchworm step).  One "step" = one complete in
                    GPUs rank 0 checks the first bold steps of the sharded run against the oracle at the same N_samples.
     stress_c5_step : BASELINE.json configs[4] (orders 0:6, n_tau = 400, N_samples = 2^20 FIXED, i.e. strong scaling over
                    the GPUs of the job), a few bold steps in the middle of the run, with its own oracle check at N = 2^6.
+    other_configs : (one GPU) BASELINE.json configs[1..3] as short whole-workload runs with their own checks: C2 batched
+                   correlator_2p sweep against the oracle, C3 Hubbard dimer orders 0:4 against exact diagonalisation, C4
+                   two-band model orders 0:3 against the oracle's first steps.
 
 `--impl reference` times the CPU port alone (the Julia reference cannot run here: no Julia), at the SAME N_samples
 as the GPU arm of the same --gpus (2^10 per GPU), on a bounded number of steps.
