@@ -35,3 +35,28 @@ for N in Ns:
     dh = np.abs(res["run"][1] - res["step"][1]).max() / np.abs(res["step"][1]).max()
     print("N=%d: run kernel %.3f ms (%d launches), per-step launches %.3f ms (%d launches); max rel diff P %.2e, contributions %.2e"
           % (N, res["run"][2], res["run"][3], res["step"][2], res["step"][3], d, dh))
+
+# the step seam by itself: 198 x (qiw_eval + qiw_scale_P) with no host bookkeeping — the floor of the host-stepped loop
+import time
+N = Ns[0]
+bold = _bold_entries(solver, range(5), N, None, None)
+ids = [t.entry_id for t in bold]
+tau = grid.tau
+ctx.set_P(0, P0)
+row = P0[5].copy()
+for rep in range(3):
+    t = time.perf_counter()
+    gpu = 0.0
+    for n in range(1, n_tau - 1):
+        r = ctx.eval(0.0, tau[n], tau[n + 1], ids, N)
+        gpu += ctx.last_device_ms()
+        ctx.scale_P(n + 1, row, 0.0)
+    dt = (time.perf_counter() - t) * 1e3
+print("step seam alone: %d x (qiw_eval + qiw_scale_P) %.2f ms wall (%.1f us per step), of which kernel time %.2f ms" % (n_tau - 2, dt, dt * 1e3 / (n_tau - 2), gpu))
+from qinchworm_b200.inchworm import inchworm
+ex.P[:] = P0
+inchworm(ex, grid, range(5), range(5), N, solver=solver, device_resident=False)
+ex.P[:] = P0
+t = time.perf_counter()
+inchworm(ex, grid, range(5), range(5), N, solver=solver, device_resident=False)
+print("inchworm(..., device_resident=False): %.2f ms wall" % ((time.perf_counter() - t) * 1e3))

@@ -139,7 +139,7 @@ struct Plan {   // launch plan of one qiw_eval call shape, cached
     bool block_real = false;               // block models: planned for the real-arithmetic tree replay (blocks up to 4x4)
     bool block_mma = false;                // block models with blocks of 5 to 8 rows, real arithmetic: FP64 tensor-core kernel
     DevBuf<int> d_bounds;                  // [n_items][warps + 1] tree ranges (block_walk_kernel)
-    int bw_warps = 0, bw_max_sp = 0, bw_nI = 0, bw_nD = 0;
+    int bw_warps = 0, bw_max_sp = 0, bw_nI = 0, bw_nD = 0, bw_pool_n = 0;
     DevBuf<uint32_t> d_sobol;
     std::vector<size_t> sobol_off;         // per call entry, offset into d_sobol
     std::vector<uint32_t> h_sobol;
@@ -932,9 +932,12 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
         // per-thread local memory, and ONE CTA of 24 warps runs per SM: its 24 warps share one set of tables, which
         // leaves most of the SM's 256 KB to L1 — where the stack frames and the word streams then stay (measured:
         // two CTAs of 12 warps with two sets of tables 41.6 ms, one CTA of 24 warps 35.3 ms on the two-band model)
+        // the operator pool (real parts) rides along in shared memory when it is small
+        const size_t pool_stage = ctx->model.pool.size() <= 2048 ? ctx->model.pool.size() : 0;
+        pl->bw_pool_n = (int)pool_stage;
         auto smem_of = [&](int Wn) {
             return ((size_t)nI_max * bs * 32 + (size_t)nD_max * 32 + (size_t)Wn * bs + (size_t)(kDevMaxNodes + 1) * 32 +
-                    (size_t)kDevMaxDim * 32) * sizeof(double) + 32 * sizeof(int) + 64;
+                    (size_t)kDevMaxDim * 32) * sizeof(double) + 32 * sizeof(int) + pool_stage * sizeof(double) + 64;
         };
         int Wn = 24;
         if (const char* ev = getenv("QIW_WALK_WARPS")) { const int v = atoi(ev); if (v >= 1 && v <= 24) Wn = v; }
@@ -1342,6 +1345,7 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
             CK(launch_block_mma(gp, bp, wp, grid, pl.bw_warps * 32, pl.groups[0].smem[0], ctx->stream));
         } else if (pl.block_real) {
             BlockWalkParams wp;
+            wp.pool_n = pl.bw_pool_n;
             wp.pool_re = ctx->dPoolRe.p; wp.xwords = ctx->dXWordsPtr.p; wp.unit_off = ctx->dXTreeOffPtr.p; wp.chunk_bounds = pl.d_bounds.p; wp.warps = pl.bw_warps; wp.max_sp = pl.bw_max_sp;
             wp.nI_max = pl.bw_nI; wp.nD_max = pl.bw_nD;
             ctx->last_real_mode = 1;

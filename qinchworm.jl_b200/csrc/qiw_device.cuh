@@ -167,6 +167,7 @@ struct DevModel {
 // Real-arithmetic tree replay for block models (block_walk_kernel).
 struct BlockWalkParams {
     const double* pool_re;        // operator blocks, real parts, same offsets as DevModel::pool
+    int pool_n;                   // > 0: number of doubles of the pool, staged in shared memory by the walker
     const uint4* const* xwords;   // per compiled entry id: expanded program words (layout: qiw_kernels.cu)
     const uint32_t* const* unit_off;   // per compiled entry id: [n_units + 1] word offsets of the walk units
     const int* chunk_bounds;      // [n_items][warps + 1] unit ranges of every warp of every CTA job

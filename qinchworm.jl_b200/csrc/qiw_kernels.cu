@@ -378,7 +378,7 @@ template <int DR, int DS, int D0>
 __device__ __forceinline__ void block_mul_O(const double* __restrict__ O, double (&V)[4 * D0]) {
     double Ov[DR * DS];
 #pragma unroll
-    for (int k = 0; k < DR * DS; ++k) Ov[k] = __ldg(O + k);
+    for (int k = 0; k < DR * DS; ++k) Ov[k] = O[k];      // the operator pool is staged in shared memory when it fits (warp-uniform address: broadcast)
 #pragma unroll
     for (int j = 0; j < D0; ++j) {
         double t[DS];
@@ -452,7 +452,7 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
         for (int j = 0; j < D0; ++j)
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (i < dcur) V[i + 4 * j] = __ldg(O + i + dcur * (c0 + j));
+                if (i < dcur) V[i + 4 * j] = O[i + dcur * (c0 + j)];
     } else {
 #pragma unroll
         for (int j = 0; j < D0; ++j)
@@ -530,6 +530,16 @@ __global__ void __launch_bounds__(768, 1) block_walk_kernel(const StepParams p, 
     double* times = accs + (size_t)nw * bsize;                              // [kDevMaxNodes + 1][32]
     double* pw = times + (kDevMaxNodes + 1) * 32;                           // [kDevMaxDim][32]
     int* okflag = reinterpret_cast<int*>(pw + kDevMaxDim * 32);             // [32]
+    // the operator blocks (real parts) are read at warp-uniform addresses on every edge: a copy in shared memory when
+    // the pool is small (round 1 read them through L1, whose lines the branch stacks and word streams keep evicting:
+    // 1.0e9 global-load instructions per launch, L1 hit rate 64 %)
+    const double* pool = wp.pool_re;
+    if (wp.pool_n > 0) {
+        double* pool_s = reinterpret_cast<double*>(okflag + 32);
+        for (int k = threadIdx.x; k < wp.pool_n; k += nthr) pool_s[k] = __ldg(wp.pool_re + k);
+        pool = pool_s;
+        __syncthreads();
+    }
 
     double t_i = p.t_i, t_w = p.t_w, t_f = p.t_f;
     // batched evaluation: blockIdx.z selects one (t_i, t_w, t_f) triple of the call, or one scrambled Sobol sequence
@@ -616,8 +626,8 @@ __global__ void __launch_bounds__(768, 1) block_walk_kernel(const StepParams p, 
             const uint32_t pc = toff[t];
             const uint4 root = __ldg(xw + pc);
             double* a = my_acc + root.w;
-            if (((root.x >> 9) & 0x3u) == 1u) block_walk_tree<1>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, lane, a);
-            else block_walk_tree<2>(xw, pc, wp.pool_re, e.coefs, TP, TD, bsize, lane, a);
+            if (((root.x >> 9) & 0x3u) == 1u) block_walk_tree<1>(xw, pc, pool, e.coefs, TP, TD, bsize, lane, a);
+            else block_walk_tree<2>(xw, pc, pool, e.coefs, TP, TD, bsize, lane, a);
             __syncwarp();
         }
         __syncthreads();
