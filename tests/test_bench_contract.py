@@ -17,7 +17,7 @@ def _line(name):
     return json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
 
 
-@pytest.mark.parametrize("name", ["r1_bench_1gpu.json", "r1_bench_2gpu_peer.json", "r1_bench_8gpu_peer.json"])
+@pytest.mark.parametrize("name", ["r2_bench_1gpu.json", "r2_bench_2gpu_peer.json", "r2_bench_8gpu_peer.json"])
 def test_product_line(name):
     d = _line(name)
     assert BASE_KEYS | {"gpu_launches", "roofline", "cpu_baseline", "clocks"} <= set(d)
@@ -32,10 +32,13 @@ def test_product_line(name):
     e = d["e2e"]
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e) and e["h2d_bytes_per_step"] > 0 < e["d2h_bytes_per_step"]
     assert e["value"] < d["value"]                      # host copies and the host clock are inside the e2e region
-    assert d["gpu_launches"] >= d["steps"] * 199        # one step-kernel launch per inchworm step
+    assert d["gpu_launches"] >= d["steps"] * 2          # bare-step kernel + one persistent run kernel per inchworm! run
+    assert d["parity"]["pass"] is True and d["parity"]["tolerance"] == 1e-10
     r = d["roofline"]
-    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r)
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "executed"} <= set(r)
     assert r["frac"] == pytest.approx(r["achieved"] / r["peak"], rel=1e-9) and 0 < r["frac"] < 1
+    # the algorithmic fraction is never quoted alone: what the kernel executes and what binds it ride along
+    assert 0 < r["executed"]["executed_frac"] < r["frac"] and 0 < r["executed"]["smem_operand_frac"] < 1
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     if d["n_gpus"] == 1:
         c = d["cpu_baseline"]
@@ -43,11 +46,11 @@ def test_product_line(name):
 
 
 def test_reference_arm_line():
-    d = _line("r1_bench_reference_arm.json")
+    d = _line("r2_bench_reference_arm.json")
     assert BASE_KEYS | {"impl", "cpu_baseline"} <= set(d) and d["impl"] == "reference"
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == "port"
-    p = _line("r1_bench_1gpu.json")
+    p = _line("r2_bench_1gpu.json")
     assert (d["metric"], d["unit"], d["higher_is_better"], d["config"]) == (p["metric"], p["unit"], p["higher_is_better"], p["config"])
 
 
