@@ -467,6 +467,7 @@ __global__ void __launch_bounds__(768, 1) scalar_step_kernel(const StepParams p)
 
     // -- 6. CTA result: warps summed in fixed order (CTAs without a sample block have not waited yet) --
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    __syncthreads();     // a CTA without a sample block comes straight from zeroing `red` (found by compute-sanitizer racecheck)
     if (c.warp == 0) {
         for (int s = c.lane; s < S; s += 32) {
             double2 v = c.red[s * c.nw];
