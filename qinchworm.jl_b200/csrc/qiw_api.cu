@@ -433,6 +433,7 @@ int qiw_set_delta(qiw_context* ctx, int32_t id, int32_t kind, int32_t n, double 
     CK(t.y.upload((const double2*)y.data(), n, ctx->stream));
     CK(t.M.upload((const double2*)M.data(), n, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    drop_plans(ctx);      // shared-memory layouts of cached plans depend on the tables' sizes and kinds
     ctx->deltas_dirty = true;
     return QIW_OK;
 }
@@ -1412,8 +1413,8 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
 // the machine: every (entry, group of sample blocks, part of the lane program) becomes a job, one job per CTA for
 // the whole run.  Light entries take m = 2, 4, 8, 16 sample blocks per job (their tables are small), heavy entries
 // are split over several jobs, until the jobs are about equally long and fit the co-resident CTAs.
-// `*used` = false when the plan does not fit (too many samples, tables off the P grid, shared memory): the caller then
-// issues one step kernel per step as before.
+// `*used` = false when the plan does not fit (too many samples, more than kInlineTables tables, shared memory): the
+// caller then issues one step kernel per step as before.
 static int enqueue_run(qiw_context* ctx, Plan& pl, int k_first, int n_steps, double2* hist, size_t hist_stride, size_t hist_off,
                        const int* diag, int n_diag, bool collective, bool* used) {
     *used = false;
@@ -1423,8 +1424,13 @@ static int enqueue_run(qiw_context* ctx, Plan& pl, int k_first, int n_steps, dou
     if (!m.scalar || pl.explicit_mode || n_steps < 2) return skip("block model / explicit times / fewer than two steps");
     if (const char* env = getenv("QIW_NO_RUN_KERNEL")) if (env[0] == '1') return skip("QIW_NO_RUN_KERNEL");
     if (ctx->tables.size() > (size_t)kInlineTables) return skip("too many pair-interaction tables");
-    for (auto& tb : ctx->tables)
-        if (tb.n > 0 && (tb.kind != 0 || tb.n != ctx->n_tau || tb.beta != ctx->beta)) return skip("a pair-interaction table is not a plain function on the P grid");
+    bool on_grid = true;
+    size_t table_elems = 0;       // staged pair-interaction tables: grid values (+ second derivatives for splines)
+    for (auto& tb : ctx->tables) {
+        if (tb.n > 0 && (tb.kind != 0 || tb.n != ctx->n_tau || tb.beta != ctx->beta)) on_grid = false;
+        table_elems += (size_t)tb.n * (tb.kind == 1 ? 2 : 1);
+    }
+    if (on_grid) table_elems = ctx->tables.size() * (size_t)ctx->n_tau;
     if (collective && ctx->n_ranks > 1 && !ctx->peer_ready) return skip("multi-GPU without peer mailboxes");
     const int n_ent = (int)pl.ids.size(), S = m.S, n_tau = ctx->n_tau;
     if (collective && ctx->n_ranks > 1 && (size_t)n_ent * m.bsize * sizeof(double2) * 2 > kPeerSlotBytes) return skip("block sums exceed a mailbox slot");
@@ -1487,7 +1493,7 @@ static int enqueue_run(qiw_context* ctx, Plan& pl, int k_first, int n_steps, dou
             L.ds = L.red + (size_t)S * W * sizeof(double2);
             L.P = (L.ds + (size_t)max_dslots * sizeof(uint32_t) + 15) & ~(size_t)15;
             L.D = L.P + (((size_t)n_tau * S * opsz + 15) & ~(size_t)15);
-            L.out = L.D + (((size_t)std::max(n_tables, 1) * n_tau * opsz + 15) & ~(size_t)15);
+            L.out = L.D + ((std::max<size_t>(table_elems, 1) * opsz + 15) & ~(size_t)15);
             L.total = L.out + (size_t)n_ent * S * sizeof(double2) + (size_t)n_ent * sizeof(double) + (size_t)(n_ent + 2) * sizeof(int) + 16;
             return L;
         };
@@ -1644,7 +1650,14 @@ static int enqueue_run(qiw_context* ctx, Plan& pl, int k_first, int n_steps, dou
     sp.entries = ctx->dEntries.p; sp.dyn = pl.d_dyn.p; sp.items = rn.d_items.p; sp.chunk_off = rn.d_chunk_off.p; sp.runs = rn.d_runs.p;
     sp.P = ctx->dP.p; sp.E = ctx->dE.p; sp.deltas = ctx->dDeltas.p;
     for (int t = 0; t < kInlineTables && t < (int)ctx->hDeltas.size(); ++t) sp.deltas_inline[t] = ctx->hDeltas[t];
-    sp.tables_on_grid = 1;
+    sp.tables_on_grid = on_grid ? 1 : 0;
+    {
+        size_t off = 0;
+        for (size_t t = 0; t < ctx->tables.size() && t < (size_t)kInlineTables; ++t) {
+            rp.D_table_off[t] = (int)off;
+            off += (size_t)ctx->tables[t].n * (ctx->tables[t].kind == 1 ? 2 : 1);
+        }
+    }
     sp.S = S; sp.bsize = m.bsize; sp.n_tau = n_tau; sp.h = ctx->beta / (n_tau - 1); sp.inv_h = 1.0 / sp.h;
     sp.n_call_entries = n_ent;
     sp.finish_P = ctx->dP.p; sp.finish_diag = diag; sp.finish_n_diag = n_diag;

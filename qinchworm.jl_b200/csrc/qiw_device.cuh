@@ -136,7 +136,8 @@ struct RunParams {
     unsigned int* barrier;         // arrival counter of the grid barrier, zero at launch
     unsigned int* sm_map;          // null, or [1024] CTAs arrived per SM, [1024] bin claimed by the SM (+1), [1] bins claimed; zero at launch
     int ctas_per_sm;               // job lists per bin (cta_job0 is then indexed by bin * ctas_per_sm + arrival order on the SM)
-    int n_tables;                  // pair-interaction tables staged in shared memory (all on the P grid)
+    int n_tables;                  // pair-interaction tables staged in shared memory
+    int D_table_off[kInlineTables];   // first element of every table in the staged array (used unless sp.tables_on_grid)
     int rows_staged;               // the partial rows of a step fit the operand table's space: reduce them from shared memory
     int ok_off, pw_off, red_off, ds_off, P_off, D_off, out_off;   // shared-memory layout (bytes)
     double2* hist;                 // optional per-entry contributions: hist[k_f * hist_stride + hist_off + entry * S + s]

@@ -222,7 +222,11 @@ __device__ __forceinline__ void phase_times(const Cta<REAL>& c, double t_i, doub
 // (complex, P[k][s]); run kernel: per-CTA copies in shared memory that already hold i * value in the kernel's
 // arithmetic (T), pair-interaction table t at Ds + t * n_tau.
 template <bool REAL>
-struct StagedTables { const typename Num<REAL>::T* Ps; const typename Num<REAL>::T* Ds; };
+struct StagedTables {
+    const typename Num<REAL>::T* Ps;     // [n_tau][S]  i P
+    const typename Num<REAL>::T* Ds;     // pair-interaction tables, i * value: table t at Ds + Doff[t]; grid values, then (splines) second derivatives
+    const int* Doff;                     // null: every table is a plain function on the P grid, table t at Ds + t * n_tau
+};
 
 template <bool REAL>
 __device__ __forceinline__ typename Num<REAL>::T cell3_apply_staged(const typename Num<REAL>::T* __restrict__ D, int stride, const GridCell3& c) {
@@ -242,7 +246,7 @@ __device__ __forceinline__ void phase_fill_delta(const Cta<REAL>& c, const StepP
     const int nP = e.nP, nD = e.nD, ns = c.ns;
     T* Tt = reinterpret_cast<T*>(c.Tb);
     const double* times = c.times; const double* cellw = c.cellw; const int* cella = c.cella;
-    if (STAGED || p.tables_on_grid) {   // every Delta table is a plain grid function on the P grid: branch-free, cells reused
+    if (p.tables_on_grid) {   // every Delta table is a plain grid function on the P grid: branch-free, cells reused
 #pragma unroll 4
         for (int task = threadIdx.x; task < nD * ns; task += c.nthr) {
             const int q = task >> c.ns_sh, smp = task & (ns - 1);
@@ -254,6 +258,37 @@ __device__ __forceinline__ void phase_fill_delta(const Cta<REAL>& c, const StepP
             T val;
             if constexpr (STAGED) val = cell3_apply_staged<REAL>(st.Ds + ds.z * p.n_tau, 1, cell);
             else val = cell3_apply_i<REAL>(p.deltas_inline[ds.z].y, 1, cell);
+            Tt[(nP + q) * ns + smp] = c.okflag[smp] ? val : N::zero();
+        }
+    } else if constexpr (STAGED) {
+        // staged tables of any kind: spline-interpolated functions (natural cubic spline in t_f - t_i,
+        // src/spline_gf.jl:208-219) and grid functions on a grid of their own
+        for (int task = threadIdx.x; task < nD * ns; task += c.nthr) {
+            const int q = task >> c.ns_sh, smp = task & (ns - 1);
+            const uint32_t dsw = c.dslots_s[q];
+            const int3 ds = make_int3((int)(dsw & 0xFFu), (int)((dsw >> 8) & 0xFFu), (int)(dsw >> 16));
+            const double th = times[ds.y * ns + smp];
+            double tt = times[ds.x * ns + smp];
+            if (tt < th) tt = th;                       // :407-410
+            const DevDelta& dt = p.deltas_inline[ds.z];
+            const T* tab = st.Ds + st.Doff[ds.z];
+            T val;
+            if (dt.kind == 1) {
+                const double d_t = tt - th, h = dt.h;
+                int j = (int)floor(d_t * dt.inv_h);
+                j = min(max(j, 0), dt.n - 2);
+                const double xa = d_t - (double)j * h, xb = (double)(j + 1) * h - d_t;
+                const T y0 = tab[j], y1 = tab[j + 1], m0 = tab[dt.n + j], m1 = tab[dt.n + j + 1];
+                const double i6h = dt.inv_h * (1.0 / 6.0), h6 = h * (1.0 / 6.0), ih = dt.inv_h;
+                const double ca = xa * xa * xa * i6h, cb = xb * xb * xb * i6h;
+                if constexpr (REAL) val = m0 * cb + m1 * ca + (y0 * ih - m0 * h6) * xb + (y1 * ih - m1 * h6) * xa;
+                else val = make_double2(m0.x * cb + m1.x * ca + (y0.x * ih - m0.x * h6) * xb + (y1.x * ih - m1.x * h6) * xa,
+                                        m0.y * cb + m1.y * ca + (y0.y * ih - m0.y * h6) * xb + (y1.y * ih - m1.y * h6) * xa);
+            } else {
+                const double qf = tt * dt.inv_h, qi = th * dt.inv_h;
+                const int a = min(max(__double2int_rd(qf), 0), dt.n - 2), b = min(max(__double2int_rd(qi), 0), dt.n - 2);
+                val = cell3_apply_staged<REAL>(tab, 1, grid_cell3_from(a, qf - (double)a, b, qi - (double)b));
+            }
             Tt[(nP + q) * ns + smp] = c.okflag[smp] ? val : N::zero();
         }
     } else {
@@ -417,7 +452,7 @@ __global__ void __launch_bounds__(768, 1) scalar_step_kernel(const StepParams p)
     const uint32_t* __restrict__ sm = dy.sobol + (size_t)blockIdx.z * p.sobol_z_stride;
     const unsigned long long count = dy.count;
     const int n_sb = (int)((count + (unsigned long long)c.ns - 1ull) / (unsigned long long)c.ns);
-    const StagedTables<REAL> none = {nullptr, nullptr};
+    const StagedTables<REAL> none = {nullptr, nullptr, nullptr};
 
     // optional per-CTA timeline (diagnostics; compiled in only with -DQIW_TRACE_BUILD because
     // reading %globaltimer costs microseconds): start / tables ready / walk done / end
@@ -552,7 +587,7 @@ __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) 
     int* ejob0_s = reinterpret_cast<int*>(scales_s + n_ent);                     // [n_ent + 1] first partial row of every entry
     for (int k = threadIdx.x; k <= n_ent; k += blockDim.x) ejob0_s[k] = rp.entry_job0[k];
     __shared__ double lambda_s;
-    const StagedTables<REAL> st = {Ps, Ds};
+    const StagedTables<REAL> st = {Ps, Ds, p.tables_on_grid ? nullptr : rp.D_table_off};
     __shared__ DevEntry e_s;      // the current job's entry description (read in every phase)
     auto view = [&](const RunJob& job, const WorkItem& it, const DevEntry& e) {      // followed by a CTA barrier
         {
@@ -572,7 +607,18 @@ __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) 
 
     // ---- once per run: tables, and every job's roots (kept on chip if the CTA has one job, else in the root cache) ----
     for (int k = threadIdx.x; k < n_tau * S; k += c.nthr) Ps[k] = N::times_i_of(p.P[(size_t)(k / S) * p.bsize + (k % S)]);
-    for (int k = threadIdx.x; k < rp.n_tables * n_tau; k += c.nthr) Ds[k] = N::times_i_of(__ldg(p.deltas_inline[k / n_tau].y + (k % n_tau)));
+    if (p.tables_on_grid) {
+        for (int k = threadIdx.x; k < rp.n_tables * n_tau; k += c.nthr) Ds[k] = N::times_i_of(__ldg(p.deltas_inline[k / n_tau].y + (k % n_tau)));
+    } else {
+        for (int t = 0; t < rp.n_tables; ++t) {
+            const DevDelta& dt = p.deltas_inline[t];
+            T* tab = Ds + rp.D_table_off[t];
+            for (int k = threadIdx.x; k < dt.n; k += c.nthr) {
+                tab[k] = N::times_i_of(__ldg(dt.y + k));
+                if (dt.kind == 1) tab[dt.n + k] = N::times_i_of(__ldg(dt.M + k));
+            }
+        }
+    }
     for (int jj = jb0; jj < jb1; ++jj) {
         const RunJob job = rp.jobs[jj];
         const WorkItem it = p.items[job.item];

@@ -593,8 +593,8 @@ def test_c4_order4_bold_step_vs_oracle(gpu_ctx, qlib, oracle_lib):
 def test_run_kernel_vs_step_launches(gpu_ctx, qlib, oracle_lib, monkeypatch, arith):
     """qiw_inchworm_run: the persistent cooperative run kernel (all bold steps in one launch; P and the pair-interaction
     tables staged in shared memory, one grid barrier per step) against one step kernel per step (QIW_NO_RUN_KERNEL=1)
-    and against the oracle, in both arithmetic modes; sample counts with one job per CTA and with several; a model whose
-    pair-interaction tables are splines (off the P grid) must take the per-step path and still be right."""
+    and against the oracle, in both arithmetic modes; sample counts with one job per CTA and with several; spline-interpolated
+    pair-interaction tables (staged in shared memory as values + second derivatives)."""
     from qinchworm_b200.inchworm import MODE_BARE, Solver, _bold_entries
     if arith == "complex":
         monkeypatch.setenv("QIW_FORCE_COMPLEX", "1")
@@ -617,17 +617,23 @@ def test_run_kernel_vs_step_launches(gpu_ctx, qlib, oracle_lib, monkeypatch, ari
         if N == 2 ** 8:
             ref = oracle_lib.inchworm(ex.flatten(), P0, range(4), range(4), N)["P"]
             assert relerr(res["run"][0], ref) < RTOL
-    monkeypatch.setenv("QIW_NO_RUN_KERNEL", "0")
+    # spline-interpolated pair interactions (the reference's golden configuration): the splines' values and second
+    # derivatives are staged in shared memory like the grid tables; run kernel vs per-step launches vs test/inchworm.h5
     ex2, grid2, _ = models.single_level(n_tau=20, spline=True)
     solver2 = Solver(ex2, ctx=gpu_ctx)
     bare = [solver2.make_entry(MODE_BARE, o, 2 * o, 2 ** 8) for o in range(3)]
     bold = _bold_entries(solver2, range(4), 2 ** 8, None, None)
-    l0 = gpu_ctx.launch_count()
-    solver2.upload_P()
-    gpu_ctx.inchworm_run([t.entry_id for t in bare], [t.entry_id for t in bold], 2 ** 8, want_contribs=False)
-    assert gpu_ctx.launch_count() - l0 == grid2.n_tau - 1
     G = load_golden("inchworm_h5.json")
-    assert relerr(gpu_ctx.get_P()[:, 1], G["/inchworm/P/1"].ravel()) < RTOL
+    res2 = {}
+    for mode in ("run", "step"):
+        monkeypatch.setenv("QIW_NO_RUN_KERNEL", "0" if mode == "run" else "1")
+        solver2.upload_P()
+        l0 = gpu_ctx.launch_count()
+        gpu_ctx.inchworm_run([t.entry_id for t in bare], [t.entry_id for t in bold], 2 ** 8, want_contribs=False)
+        assert gpu_ctx.launch_count() - l0 == (2 if mode == "run" else grid2.n_tau - 1)
+        res2[mode] = gpu_ctx.get_P()
+        assert relerr(res2[mode][:, 1], G["/inchworm/P/1"].ravel()) < RTOL
+    assert relerr(res2["run"], res2["step"]) < 1e-13
 
 
 @pytest.mark.gpu
