@@ -1,17 +1,23 @@
-// qiw_scalar.cu — the step kernel of libqinchworm_cuda.so for models whose sector blocks are all 1x1
-// (sm_100a).  One launch evaluates every (entry, sample block) of a call: scrambled-Sobol points, simplex
-// maps, P / Delta interpolation, segment products and the configuration sums, followed by the deterministic
-// reduction, the peer-memory all-reduce and (device-resident loop) set_ppgf! + normalize! in the last CTA.
+// qiw_scalar.cu — the kernels of libqinchworm_cuda.so for models whose sector blocks are all 1x1 (sm_100a):
+//   scalar_step_kernel  one launch evaluates every (entry, sample block) of a call: scrambled-Sobol points, simplex
+//                       maps, P / Delta interpolation, segment products and the configuration sums, followed by the
+//                       deterministic reduction, the peer-memory all-reduce and (device-resident loop) set_ppgf! +
+//                       normalize! in the last CTA;
+//   scalar_run_kernel   all bold steps of qiw_inchworm_run in ONE cooperative launch when a step is too small to fill
+//                       the machine: one job per CTA for the whole run, P and the pair-interaction tables staged in
+//                       shared memory, one grid barrier per step.
+// Both are made of the same phases (phase_roots ... phase_walk below).
 //
-// Mapping: LANE = SAMPLE.  A CTA owns (entry, block of 32 samples[, part of the entry's lane program][, z]);
+// Mapping: LANE = SAMPLE.  A CTA owns (entry, block of 32 m samples[, part of the entry's lane program][, z]);
 // the per-sample operand table lives in shared memory as T[slot][sample], so that a warp reading one slot for
 // its 32 samples touches 32 consecutive words (no bank conflicts) and every record of the lane program
 // (EntryProgram::lane_*, qiw_host.hpp) is warp-uniform: its slot numbers arrive by one broadcast 128-bit load
-// per 4 operands and the per-sector sum is carried in one register per lane, reduced over the lanes once per
+// per 8 operands and the per-sector sum is carried in one register per lane, reduced over the lanes once per
 // run of records instead of once per 32 configurations.
 //
 // Reference: src/topology_eval.jl:350-437,454-556 (per-sample evaluation), src/qmc_integrate.jl:363-463,
-// 497-507,597-612 (transforms, integral), src/scrambled_sobol.jl:158-197 (points), src/mpi.jl:104-127.
+// 497-507,597-612 (transforms, integral), src/scrambled_sobol.jl:158-197 (points), src/mpi.jl:104-127,
+// src/inchworm.jl:474-493 and src/ppgf.jl:495-504,646-668 (the loop over steps and its state update).
 #include <cstdio>
 
 #include "qiw_devfn.cuh"
