@@ -1583,6 +1583,9 @@ static int enqueue_run(qiw_context* ctx, Plan& pl, int k_first, int n_steps, dou
             const size_t region_end = std::max((size_t)x.slots * ns * opsz, aux_off(x) + aux_bytes(x));
             const size_t off = (std::max(region_end, rows_staged ? rows_bytes : (size_t)0) + 15) & ~(size_t)15;
             if (off + bytes <= L.ok) jobs[k].stash_off = (int)off;
+            // may a part of the CTA prepare the next step's times / pair-interaction rows while the rest reduces the
+            // partial rows staged at the start of the table?  Only if the rows stay inside the propagator rows.
+            jobs[k].flags = (!rows_staged || (rows_bytes <= (size_t)x.p->nP * ns * opsz && rows_bytes <= aux_off(x))) ? 1 : 0;
         }
         // Jobs -> SMs -> CTAs at about equal estimated cost (longest job first onto the least loaded bin): a step is bound
         // by the shared-memory pipe of the busiest SM, so the unit of balance is the SM; the CTAs that the hardware places
@@ -1670,6 +1673,8 @@ static int enqueue_run(qiw_context* ctx, Plan& pl, int k_first, int n_steps, dou
     rp.k_first = k_first; rp.n_steps = n_steps;
     rp.partials = rn.d_partials.p; rp.barrier = rn.d_barrier.p + 2049;
     rp.sm_map = rn.by_sm ? rn.d_barrier.p : nullptr; rp.ctas_per_sm = rn.ctas_per_sm;
+    rp.post_warps = std::max(1, rn.threads / 64);     // half of the CTA (measured on the README run: 2 / 3 / 4 / 6 / 8 / 12 of 12 warps: 3.99 / 3.78 / 3.66 / 3.57 / 3.74 / 3.91 ms)
+    if (const char* env = getenv("QIW_RUN_POST_WARPS")) { const int v = atoi(env); if (v >= 1 && v <= 32) rp.post_warps = v; }
     rp.n_tables = (int)ctx->tables.size();
     rp.ok_off = rn.ok_off; rp.pw_off = rn.pw_off; rp.red_off = rn.red_off; rp.ds_off = rn.ds_off; rp.P_off = rn.P_off;
     rp.D_off = rn.D_off; rp.out_off = rn.out_off; rp.rows_staged = rn.rows_staged;

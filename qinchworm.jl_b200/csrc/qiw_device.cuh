@@ -122,8 +122,10 @@ struct StepParams {
 
 // One CTA of the persistent run kernel: a work item (entry + chunks of its lane program) on 32 * n_sub consecutive
 // samples starting at sample block sb0, for every step of the run.
-struct RunJob { int item, sb0, n_sub, aux_off, row, stash_off, pad_[2]; };   // row: this job's row of the partial sums;
-                                                                              // stash_off: on-chip copy of its program, or -1
+struct RunJob { int item, sb0, n_sub, aux_off, row, stash_off, flags, pad_; };   // row: this job's row of the partial sums;
+                                                                              // stash_off: on-chip copy of its program, or -1;
+                                                                              // flags & 1: the staged partial rows overlap neither its
+                                                                              // pair-interaction rows nor its times (next step's may be prepared early)
 
 struct RunParams {
     StepParams sp;                 // tables, entries, work items, runs; finish_P = the global P table; peer_* as in a step
@@ -135,6 +137,7 @@ struct RunParams {
     void* partials;                // [2][n_jobs][S] per-job sums (kernel arithmetic), alternating with the step's parity
     unsigned int* barrier;         // arrival counter of the grid barrier, zero at launch
     unsigned int* sm_map;          // null, or [1024] CTAs arrived per SM, [1024] bin claimed by the SM (+1), [1] bins claimed; zero at launch
+    int post_warps;                // warps of a CTA that reduce / exchange / update P after the barrier while the others prepare the next step
     int ctas_per_sm;               // job lists per bin (cta_job0 is then indexed by bin * ctas_per_sm + arrival order on the SM)
     int n_tables;                  // pair-interaction tables staged in shared memory
     int D_table_off[kInlineTables];   // first element of every table in the staged array (used unless sp.tables_on_grid)

@@ -157,7 +157,8 @@ struct Cta {
     int chunk0, n_chunks;
     const uint4* segdefs;         // packed definitions of the segment-product table
     const typename Num<REAL>::T* segcoef;   // coefficient of every table entry, or null (then read through DevEntry::coefs)
-    int lane, warp, nw, nthr;
+    int lane, warp, nw;
+    int tid, nthr;                // this thread's index among the `nthr` threads that execute a phase together
 };
 
 // -- 1. Sobol coordinates and the independent roots x_j^(1/(remaining dims)).  The roots depend only on (entry, Sobol
@@ -168,8 +169,8 @@ __device__ __forceinline__ void phase_roots(const Cta<REAL>& c, const uint32_t* 
                                             bool uc_write) {
     const DevEntry& e = *c.e;
     const int D = e.D, d_after = e.d_after, ns = c.ns;
-    for (int smp = threadIdx.x; smp < ns; smp += c.nthr) c.okflag[smp] = (local0 + smp < count) ? 1 : 0;
-    for (int task = threadIdx.x; task < D * ns; task += c.nthr) {
+    for (int smp = c.tid; smp < ns; smp += c.nthr) c.okflag[smp] = (local0 + smp < count) ? 1 : 0;
+    for (int task = c.tid; task < D * ns; task += c.nthr) {
         const int j = task >> c.ns_sh, smp = task & (ns - 1);
         const unsigned long long local = local0 + smp;
         const bool active = local < count;
@@ -198,7 +199,7 @@ __device__ __forceinline__ void phase_times(const Cta<REAL>& c, double t_i, doub
     const int D = e.D, d_after = e.d_after, ns = c.ns, n_nodes = e.n_nodes;
     const double lo_after = (e.mode == 0) ? t_i : t_w, len_after = t_f - lo_after;
     const double len_before = t_w - t_i;
-    for (int task = threadIdx.x; task < n_nodes * ns; task += c.nthr) {
+    for (int task = c.tid; task < n_nodes * ns; task += c.nthr) {
         const int pos = 1 + (task >> c.ns_sh), smp = task & (ns - 1);
         const int src = e.pos_src[pos];
         double t;
@@ -254,7 +255,7 @@ __device__ __forceinline__ void phase_fill_delta(const Cta<REAL>& c, const StepP
     const double* times = c.times; const double* cellw = c.cellw; const int* cella = c.cella;
     if (p.tables_on_grid) {   // every Delta table is a plain grid function on the P grid: branch-free, cells reused
 #pragma unroll 4
-        for (int task = threadIdx.x; task < nD * ns; task += c.nthr) {
+        for (int task = c.tid; task < nD * ns; task += c.nthr) {
             const int q = task >> c.ns_sh, smp = task & (ns - 1);
             const uint32_t dsw = c.dslots_s[q];
             const int3 ds = make_int3((int)(dsw & 0xFFu), (int)((dsw >> 8) & 0xFFu), (int)(dsw >> 16));
@@ -269,7 +270,7 @@ __device__ __forceinline__ void phase_fill_delta(const Cta<REAL>& c, const StepP
     } else if constexpr (STAGED) {
         // staged tables of any kind: spline-interpolated functions (natural cubic spline in t_f - t_i,
         // src/spline_gf.jl:208-219) and grid functions on a grid of their own
-        for (int task = threadIdx.x; task < nD * ns; task += c.nthr) {
+        for (int task = c.tid; task < nD * ns; task += c.nthr) {
             const int q = task >> c.ns_sh, smp = task & (ns - 1);
             const uint32_t dsw = c.dslots_s[q];
             const int3 ds = make_int3((int)(dsw & 0xFFu), (int)((dsw >> 8) & 0xFFu), (int)(dsw >> 16));
@@ -298,7 +299,7 @@ __device__ __forceinline__ void phase_fill_delta(const Cta<REAL>& c, const StepP
             Tt[(nP + q) * ns + smp] = c.okflag[smp] ? val : N::zero();
         }
     } else {
-        for (int task = threadIdx.x; task < nD * ns; task += c.nthr) {
+        for (int task = c.tid; task < nD * ns; task += c.nthr) {
             const int q = task >> c.ns_sh, smp = task & (ns - 1);
             const bool ok = c.okflag[smp] != 0;
             const uint32_t dsw = c.dslots_s[q];
@@ -328,7 +329,7 @@ __device__ __forceinline__ void phase_fill_P(const Cta<REAL>& c, const StepParam
     const int ns = c.ns, nI = e.n_nodes - 1, S = p.S;
     T* Tt = reinterpret_cast<T*>(c.Tb);
     const double* times = c.times; const double* cellw = c.cellw; const int* cella = c.cella;
-    for (int task = threadIdx.x; task < nI * ns; task += c.nthr) {
+    for (int task = c.tid; task < nI * ns; task += c.nthr) {
         const int q = task >> c.ns_sh, smp = task & (ns - 1);
         const bool ok = c.okflag[smp] != 0;
         const double ta = times[(q + 1) * ns + smp];
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(768, 1) scalar_step_kernel(const StepParams p)
     const int S = p.S, nD = e.nD;
     Cta<REAL> c;
     c.e = &e;
-    c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5; c.nw = blockDim.x >> 5; c.nthr = blockDim.x;
+    c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5; c.nw = blockDim.x >> 5; c.tid = threadIdx.x; c.nthr = blockDim.x;
     c.ns = p.spb; c.ns_sh = p.spb_log2;                          // a power of two <= 32
     // shared memory carve-up (sizes fixed per launch from the largest entry, see host): T[slot][sample] — consecutive
     // lanes = consecutive words.  The roots — dead once the times exist — live at the start of T, which is filled
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) 
     const int jb0 = rp.cta_job0[list_s], jb1 = rp.cta_job0[list_s + 1];
     const bool single = (jb1 - jb0 == 1);        // the usual case: this CTA's only job keeps its roots and slot list on chip
     Cta<REAL> c;
-    c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5; c.nw = blockDim.x >> 5; c.nthr = blockDim.x;
+    c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5; c.nw = blockDim.x >> 5; c.tid = threadIdx.x; c.nthr = blockDim.x;
     c.Tb = smem_raw;
     c.okflag = reinterpret_cast<int*>(smem_raw + rp.ok_off);                     // [max ns]
     c.pw = reinterpret_cast<double*>(smem_raw + rp.pw_off);                      // [D][ns]
@@ -686,8 +687,8 @@ __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) 
 #define QIW_RT(k_)
 #endif
     // single-job CTAs: the times and the pair-interaction rows of the COMING step do not depend on this step's result;
-    // they are prepared between sending this rank's block sums to the peers and waiting for theirs (`pre`), which takes
-    // the NVLink round trip of the all-reduce off the step's critical path
+    // a part of the CTA's warps prepares them while the others reduce, exchange and update P (`pre`), which takes them —
+    // and, on several GPUs, the NVLink round trip of the all-reduce — off the step's critical path
     bool pre = false;
     for (int step = 0; step < rp.n_steps; ++step) {
         const int k_w = rp.k_first + step, k_f = k_w + 1;
@@ -749,128 +750,138 @@ __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) 
         }
         __syncthreads();
         QIW_RT(6)
-        // ---- every CTA: block sums of every entry, same fixed order everywhere ----
-        // all rows first (independent L2 loads, one latency), into the operand table's space, which is dead by now
-        const T* rows = my_rows;
-        if (rp.rows_staged) {
-            T* rows_s = reinterpret_cast<T*>(smem_raw);
-            const int n_val = rp.n_jobs * S;
-            for (int k0 = threadIdx.x; k0 < n_val; k0 += 4 * c.nthr) {      // four loads in flight per thread
-                T tmp[4];
+        // Warp specialisation after the barrier.  Group A (the first nA warps): the reduction of the partial rows, the
+        // exchange with the peer GPUs and the update of this CTA's copy of P — a chain of latencies, not of work.  Group B
+        // (the other warps): the times and the pair-interaction rows of the COMING step, which do not depend on this
+        // step's result (`pre`).  The two groups meet at the CTA barrier below.
+        const bool do_pre = single && c.nw > rp.post_warps && step + 1 < rp.n_steps && (rp.jobs[jb0].flags & 1);
+        const int nA = do_pre ? rp.post_warps : c.nw, nthrA = nA * 32, tidA = (int)threadIdx.x;     // no group B: everybody is group A
+        auto bar_A = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(nthrA) : "memory"); };
+        if (c.warp < nA) {
+            // ---- every CTA: block sums of every entry, same fixed order everywhere ----
+            // all rows first (independent L2 loads, one latency), into the operand table's space, which is dead by now
+            const T* rows = my_rows;
+            if (rp.rows_staged) {
+                T* rows_s = reinterpret_cast<T*>(smem_raw);
+                const int n_val = rp.n_jobs * S;
+                for (int k0 = tidA; k0 < n_val; k0 += 10 * nthrA) {      // ten loads in flight per thread: one L2 round trip
+                    T tmp[10];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const int k = k0 + u * c.nthr; tmp[u] = (k < n_val) ? __ldcg(my_rows + k) : N::zero(); }
+                    for (int u = 0; u < 10; ++u) { const int k = k0 + u * nthrA; tmp[u] = (k < n_val) ? __ldcg(my_rows + k) : N::zero(); }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const int k = k0 + u * c.nthr; if (k < n_val) rows_s[k] = tmp[u]; }
+                    for (int u = 0; u < 10; ++u) { const int k = k0 + u * nthrA; if (k < n_val) rows_s[k] = tmp[u]; }
+                }
+                bar_A();
+                rows = rows_s;
             }
-            __syncthreads();
-            rows = rows_s;
-        }
-        // four lanes per (entry, sector) output: lane g adds rows g, g+4, ... in order, then a fixed butterfly
-        for (int o0 = 0; o0 < n_ent * S; o0 += c.nthr / 4) {
-            const int o = o0 + (int)threadIdx.x / 4, g = (int)threadIdx.x & 3;
-            T v = N::zero();
-            double scale = 0.0;
-            if (o < n_ent * S) {
-                const int i = o / S, s = o - i * S;
-                const int j0 = ejob0_s[i], j1 = ejob0_s[i + 1];
-                if (rp.rows_staged) for (int j = j0 + g; j < j1; j += 4) v = N::add(v, rows[(size_t)j * S + s]);
-                else for (int j = j0 + g; j < j1; j += 4) v = N::add(v, __ldcg(rows + (size_t)j * S + s));
-                scale = scales_s[i];
+            // four lanes per (entry, sector) output: lane g adds rows g, g+4, ... in order, then a fixed butterfly
+            for (int o0 = 0; o0 < n_ent * S; o0 += nthrA / 4) {
+                const int o = o0 + (int)tidA / 4, g = (int)tidA & 3;
+                T v = N::zero();
+                double scale = 0.0;
+                if (o < n_ent * S) {
+                    const int i = o / S, s = o - i * S;
+                    const int j0 = ejob0_s[i], j1 = ejob0_s[i + 1];
+                    if (rp.rows_staged) for (int j = j0 + g; j < j1; j += 4) v = N::add(v, rows[(size_t)j * S + s]);
+                    else for (int j = j0 + g; j < j1; j += 4) v = N::add(v, __ldcg(rows + (size_t)j * S + s));
+                    scale = scales_s[i];
+                }
+                v = N::add(v, N::shfl_xor(v, 1));
+                v = N::add(v, N::shfl_xor(v, 2));
+                if (o < n_ent * S && g == 0) {
+                    if constexpr (REAL) outs[o] = make_double2(0.0, scale * v);
+                    else outs[o] = cscale(scale, v);
+                }
             }
-            v = N::add(v, N::shfl_xor(v, 1));
-            v = N::add(v, N::shfl_xor(v, 2));
-            if (o < n_ent * S && g == 0) {
-                if constexpr (REAL) outs[o] = make_double2(0.0, scale * v);
-                else outs[o] = cscale(scale, v);
-            }
-        }
-        __syncthreads();
-        if (p.peer_ranks > 1) {
-            // ---- all-reduce over peer memory (protocol: fused_tail).  CTA 0 sends; every CTA of this GPU receives ----
-            const unsigned long long seq = p.peer_seq + (unsigned long long)step;
-            const int par = (int)(seq & 1ull);
-            const unsigned int seq32 = (unsigned int)(seq % 0xFFFFFFFFull) + 1u;
-            const size_t my_slot = kPeerFlagBytes + ((size_t)p.peer_rank * 2 + par) * kPeerSlotBytes;
-            const int n_dbl = 2 * n_ent * S, n_words = 2 * n_dbl;
-            const double* outd = reinterpret_cast<const double*>(outs);
-            if (blockIdx.x == 0) {
-                for (int k = threadIdx.x; k < n_words; k += c.nthr) {
-                    const unsigned long long bits = (unsigned long long)__double_as_longlong(outd[k >> 1]);
-                    const unsigned int half = (k & 1) ? (unsigned int)(bits >> 32) : (unsigned int)bits;
-                    for (int q = 0; q < p.peer_ranks; ++q) {
-                        if (q == p.peer_rank) continue;
-                        uint2* dst = reinterpret_cast<uint2*>(p.peer_mail[q] + my_slot) + k;
-                        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(half), "r"(seq32) : "memory");
+            bar_A();
+            if (p.peer_ranks > 1) {
+                // ---- all-reduce over peer memory (protocol: fused_tail).  CTA 0 sends; every CTA of this GPU receives ----
+                const unsigned long long seq = p.peer_seq + (unsigned long long)step;
+                const int par = (int)(seq & 1ull);
+                const unsigned int seq32 = (unsigned int)(seq % 0xFFFFFFFFull) + 1u;
+                const size_t my_slot = kPeerFlagBytes + ((size_t)p.peer_rank * 2 + par) * kPeerSlotBytes;
+                const int n_dbl = 2 * n_ent * S, n_words = 2 * n_dbl;
+                const double* outd = reinterpret_cast<const double*>(outs);
+                if (blockIdx.x == 0) {
+                    for (int k = tidA; k < n_words; k += nthrA) {
+                        const unsigned long long bits = (unsigned long long)__double_as_longlong(outd[k >> 1]);
+                        const unsigned int half = (k & 1) ? (unsigned int)(bits >> 32) : (unsigned int)bits;
+                        for (int q = 0; q < p.peer_ranks; ++q) {
+                            if (q == p.peer_rank) continue;
+                            uint2* dst = reinterpret_cast<uint2*>(p.peer_mail[q] + my_slot) + k;
+                            asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(half), "r"(seq32) : "memory");
+                        }
                     }
                 }
-            }
-            // the coming step's times and pair-interaction rows while the peers' sums are in flight
-            if (single && step + 1 < rp.n_steps) {
-                const RunJob job = rp.jobs[jb0];
-                const unsigned long long count = p.dyn[p.items[job.item].slot].count, local0 = (unsigned long long)job.sb0 * 32ull;
-                phase_times<REAL>(c, 0.0, (double)(k_w + 1) * h, (double)(k_f + 1) * h, n_tau, p.inv_h, nullptr, local0, count);
-                __syncthreads();
-                phase_fill_delta<REAL, true>(c, p, st);
-                pre = true;
-            }
-            const unsigned char* base = p.peer_mail[p.peer_rank] + kPeerFlagBytes;
-            const unsigned long long t0 = globaltimer_ns();
-            for (int j = threadIdx.x; j < n_dbl; j += c.nthr) {
-                double v = 0.0;
-                for (int q = 0; q < p.peer_ranks; ++q) {
-                    if (q == p.peer_rank) { v += outd[j]; continue; }
-                    const uint2* src = reinterpret_cast<const uint2*>(base + ((size_t)q * 2 + par) * kPeerSlotBytes) + 2 * j;
-                    uint2 lo, hi;
-                    bool ok = true;
-                    do {
-                        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo.x), "=r"(lo.y) : "l"(src) : "memory");
-                        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hi.x), "=r"(hi.y) : "l"(src + 1) : "memory");
-                        if ((lo.y != seq32 || hi.y != seq32) && globaltimer_ns() - t0 > p.peer_timeout_ns) { *p.peer_status = 1; ok = false; break; }
-                    } while (lo.y != seq32 || hi.y != seq32);
-                    if (ok) v += __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | (unsigned long long)lo.x));
-                    else v = __longlong_as_double(0x7FF8000000000000ll);   // poison: the run must not continue on a partial sum
+                const unsigned char* base = p.peer_mail[p.peer_rank] + kPeerFlagBytes;
+                const unsigned long long t0 = globaltimer_ns();
+                for (int j = tidA; j < n_dbl; j += nthrA) {
+                    double v = 0.0;
+                    for (int q = 0; q < p.peer_ranks; ++q) {
+                        if (q == p.peer_rank) { v += outd[j]; continue; }
+                        const uint2* src = reinterpret_cast<const uint2*>(base + ((size_t)q * 2 + par) * kPeerSlotBytes) + 2 * j;
+                        uint2 lo, hi;
+                        bool ok = true;
+                        do {
+                            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo.x), "=r"(lo.y) : "l"(src) : "memory");
+                            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hi.x), "=r"(hi.y) : "l"(src + 1) : "memory");
+                            if ((lo.y != seq32 || hi.y != seq32) && globaltimer_ns() - t0 > p.peer_timeout_ns) { *p.peer_status = 1; ok = false; break; }
+                        } while (lo.y != seq32 || hi.y != seq32);
+                        if (ok) v += __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | (unsigned long long)lo.x));
+                        else v = __longlong_as_double(0x7FF8000000000000ll);   // poison: the run must not continue on a partial sum
+                    }
+                    reinterpret_cast<double*>(outs)[j] = v;   // element j is read and written by this thread only
                 }
-                reinterpret_cast<double*>(outs)[j] = v;   // element j is read and written by this thread only
+                bar_A();
             }
-            __syncthreads();
-        }
-        QIW_RT(7)
-        // ---- set_ppgf!(P, tau_f, sum of the entries) and normalize!(P, tau_f) on this CTA's copy ----
-        // row sums: warp = sector, lanes = entries, fixed butterfly (the same sum in every CTA and on every rank)
-        for (int s = c.warp; s < S; s += c.nw) {
-            double2 v = make_double2(0.0, 0.0);
-            for (int j = c.lane; j < n_ent; j += 32) {
-                const double2 cj = outs[j * S + s];
-                v = cadd(v, cj);
-                if (blockIdx.x == 0 && rp.hist) rp.hist[(size_t)k_f * rp.hist_stride + rp.hist_off + (size_t)j * S + s] = cj;
-            }
+            QIW_RT(7)
+            // ---- set_ppgf!(P, tau_f, sum of the entries) and normalize!(P, tau_f) on this CTA's copy ----
+            // row sums: warp = sector, lanes = entries, fixed butterfly (the same sum in every CTA and on every rank)
+            for (int s = c.warp; s < S; s += nA) {
+                double2 v = make_double2(0.0, 0.0);
+                for (int j = c.lane; j < n_ent; j += 32) {
+                    const double2 cj = outs[j * S + s];
+                    v = cadd(v, cj);
+                    if (blockIdx.x == 0 && rp.hist) rp.hist[(size_t)k_f * rp.hist_stride + rp.hist_off + (size_t)j * S + s] = cj;
+                }
 #pragma unroll
-            for (int m = 16; m > 0; m >>= 1) {
-                v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, m);
-                v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, m);
+                for (int m = 16; m > 0; m >>= 1) {
+                    v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, m);
+                    v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, m);
+                }
+                if (c.lane == 0) Ps[k_f * S + s] = N::times_i_of(v);
             }
-            if (c.lane == 0) Ps[k_f * S + s] = N::times_i_of(v);
-        }
-        __syncthreads();
-        // lambda from the diagonal (every block of a scalar model is its own diagonal element)
-        if (threadIdx.x == 0) {
-            double pmax = -1.0e300;
-            for (int s = 0; s < S; ++s) {
-                double mip;   // -Im P_s(tau_f)
-                if constexpr (REAL) mip = Ps[k_f * S + s]; else mip = Ps[k_f * S + s].x;
-                pmax = fmax(pmax, mip);
+            bar_A();
+            // lambda from the diagonal (every block of a scalar model is its own diagonal element)
+            if (tidA == 0) {
+                double pmax = -1.0e300;
+                for (int s = 0; s < S; ++s) {
+                    double mip;   // -Im P_s(tau_f)
+                    if constexpr (REAL) mip = Ps[k_f * S + s]; else mip = Ps[k_f * S + s].x;
+                    pmax = fmax(pmax, mip);
+                }
+                lambda_s = log(pmax) / ((double)k_f * h);
             }
-            lambda_s = log(pmax) / ((double)k_f * h);
-        }
-        __syncthreads();
-        const double lambda = lambda_s;
-        for (int k = threadIdx.x; k < n_tau; k += c.nthr) {      // one exponential per grid point
-            const double f = exp(-((double)k * h) * lambda);
-            for (int s = 0; s < S; ++s) {
-                if constexpr (REAL) Ps[k * S + s] = f * Ps[k * S + s];
-                else Ps[k * S + s] = cscale(f, Ps[k * S + s]);
+            bar_A();
+            const double lambda = lambda_s;
+            for (int k = tidA; k < n_tau; k += nthrA) {      // one exponential per grid point
+                const double f = exp(-((double)k * h) * lambda);
+                for (int s = 0; s < S; ++s) {
+                    if constexpr (REAL) Ps[k * S + s] = f * Ps[k * S + s];
+                    else Ps[k * S + s] = cscale(f, Ps[k * S + s]);
+                }
             }
+            bar_A();
+        } else if (do_pre) {
+            const RunJob job = rp.jobs[jb0];
+            const unsigned long long count = p.dyn[p.items[job.item].slot].count, local0 = (unsigned long long)job.sb0 * 32ull;
+            Cta<REAL> cB = c;
+            cB.tid = (int)threadIdx.x - nthrA; cB.nthr = c.nthr - nthrA;
+            phase_times<REAL>(cB, 0.0, (double)(k_w + 1) * h, (double)(k_f + 1) * h, n_tau, p.inv_h, nullptr, local0, count);
+            asm volatile("bar.sync 2, %0;" ::"r"(cB.nthr) : "memory");
+            phase_fill_delta<REAL, true>(cB, p, st);
         }
+        pre = do_pre;
         __syncthreads();
         QIW_RT(8)
 #ifdef QIW_TRACE_BUILD
