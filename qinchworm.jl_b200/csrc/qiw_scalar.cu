@@ -756,27 +756,31 @@ __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) 
         // step's result (`pre`).  The two groups meet at the CTA barrier below.
         const bool do_pre = single && c.nw > rp.post_warps && step + 1 < rp.n_steps && (rp.jobs[jb0].flags & 1);
         const int nA = do_pre ? rp.post_warps : c.nw, nthrA = nA * 32, tidA = (int)threadIdx.x;     // no group B: everybody is group A
+        // On several GPUs the whole CTA reduces (the sooner this rank's sums are on the wire the better) and splits
+        // afterwards; on one GPU group B starts on the next step right away and group A reduces alone.
+        const int nR = (p.peer_ranks > 1) ? c.nw : nA, nthrR = nR * 32, tidR = (int)threadIdx.x;
         auto bar_A = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(nthrA) : "memory"); };
-        if (c.warp < nA) {
+        auto bar_R = [&]() { if (nR == c.nw) __syncthreads(); else asm volatile("bar.sync 1, %0;" ::"r"(nthrR) : "memory"); };
+        if (c.warp < nR) {
             // ---- every CTA: block sums of every entry, same fixed order everywhere ----
             // all rows first (independent L2 loads, one latency), into the operand table's space, which is dead by now
             const T* rows = my_rows;
             if (rp.rows_staged) {
                 T* rows_s = reinterpret_cast<T*>(smem_raw);
                 const int n_val = rp.n_jobs * S;
-                for (int k0 = tidA; k0 < n_val; k0 += 10 * nthrA) {      // ten loads in flight per thread: one L2 round trip
+                for (int k0 = tidR; k0 < n_val; k0 += 10 * nthrR) {      // ten loads in flight per thread: one L2 round trip
                     T tmp[10];
 #pragma unroll
-                    for (int u = 0; u < 10; ++u) { const int k = k0 + u * nthrA; tmp[u] = (k < n_val) ? __ldcg(my_rows + k) : N::zero(); }
+                    for (int u = 0; u < 10; ++u) { const int k = k0 + u * nthrR; tmp[u] = (k < n_val) ? __ldcg(my_rows + k) : N::zero(); }
 #pragma unroll
-                    for (int u = 0; u < 10; ++u) { const int k = k0 + u * nthrA; if (k < n_val) rows_s[k] = tmp[u]; }
+                    for (int u = 0; u < 10; ++u) { const int k = k0 + u * nthrR; if (k < n_val) rows_s[k] = tmp[u]; }
                 }
-                bar_A();
+                bar_R();
                 rows = rows_s;
             }
             // four lanes per (entry, sector) output: lane g adds rows g, g+4, ... in order, then a fixed butterfly
-            for (int o0 = 0; o0 < n_ent * S; o0 += nthrA / 4) {
-                const int o = o0 + (int)tidA / 4, g = (int)tidA & 3;
+            for (int o0 = 0; o0 < n_ent * S; o0 += nthrR / 4) {
+                const int o = o0 + (int)tidR / 4, g = (int)tidR & 3;
                 T v = N::zero();
                 double scale = 0.0;
                 if (o < n_ent * S) {
@@ -793,7 +797,9 @@ __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) 
                     else outs[o] = cscale(scale, v);
                 }
             }
-            bar_A();
+            bar_R();
+        }
+        if (c.warp < nA) {
             if (p.peer_ranks > 1) {
                 // ---- all-reduce over peer memory (protocol: fused_tail).  CTA 0 sends; every CTA of this GPU receives ----
                 const unsigned long long seq = p.peer_seq + (unsigned long long)step;
