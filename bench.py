@@ -72,8 +72,9 @@ def diagram_evals(N, n_tau=N_TAU, bold_steps=None):
 
 
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons sampled DURING the timed region: NVML every ~5 ms (nvidia_ml_py), falling
-    back to nvidia-smi polling."""
+    """SM clock and throttle reasons sampled DURING the timed regions: NVML every ~20 ms (nvidia_ml_py), falling
+    back to nvidia-smi polling.  (A 5 ms period cost the public-API figure 0.35 ms of a 3.8 ms call: the sampler is a
+    Python thread and takes the interpreter lock at every wake-up; profiles/e2e_breakdown.py measures the call without it.)"""
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, device_index):
@@ -97,7 +98,7 @@ class ClockSampler(threading.Thread):
             for n, b_ in bits.items():
                 if r & b_:
                     self.reasons.add(n)
-            time.sleep(0.005)
+            time.sleep(0.02)
 
     def run(self):
         try:
