@@ -2047,9 +2047,14 @@ int qiw_inchworm_run(qiw_context* ctx, int32_t n_bare, const int32_t* bare_ids, 
         }
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    if (order_contribs)
-        CK(cudaMemcpyAsync(order_contribs, ctx->dHist.p, (size_t)n_tau * n_hist * bs * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t n_hist_el = (size_t)n_tau * n_hist * bs;
+    if (order_contribs) {      // through the pinned staging buffer: a copy into pageable memory is staged by the driver in small pieces
+        rc = ensure_host_out(ctx, n_hist_el);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(ctx->hOut, ctx->dHist.p, n_hist_el * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
+    if (order_contribs) memcpy(order_contribs, ctx->hOut, n_hist_el * sizeof(double2));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_ms = ms;
