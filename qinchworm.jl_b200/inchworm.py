@@ -235,8 +235,15 @@ def inchworm(expansion, grid, orders, orders_bare, N_samples, n_pts_after_max=No
         solver.upload_P()
         hist = solver.ctx.inchworm_run([td.entry_id for td in bare], [td.entry_id for td in bold], N_samples)
         expansion.P[:] = solver.ctx.get_P()
-        for j, td in enumerate(bare + bold):      # (22 small adds: faster than masked sums or a complex tensordot here)
-            P_orders[td.order] += hist[:, j, :]
+        # per-order sums of the per-entry history: one real batched matmul, onehot[order, entry] x hist[k, entry, (el, re/im)]
+        o_list = sorted(P_orders)
+        onehot = np.zeros((len(o_list), hist.shape[1]))
+        for j, td in enumerate(bare + bold):
+            onehot[o_list.index(td.order), j] = 1.0
+        hr = np.ascontiguousarray(hist).view(np.float64).reshape(hist.shape[0], hist.shape[1], 2 * hist.shape[2])
+        sums = np.matmul(onehot, hr).reshape(hist.shape[0], len(o_list), hist.shape[2], 2).view(np.complex128)[..., 0]
+        for q, o in enumerate(o_list):
+            P_orders[o] += sums[:, q, :]
         for o in P_orders_std:         # std of a single sequence is NaN (src/randomization.jl:99); order 0 is exact
             if o > 0:                  # (:155), and grid point 0 is never evaluated
                 P_orders_std[o][1:] = np.nan
