@@ -237,6 +237,63 @@ __device__ __forceinline__ double entry_scale(const DevEntry& e, const DevEntryD
     return dir * jac * dy.weight;
 }
 
+// ---- peer-memory all-reduce: one element on the wire ----------------------------------------------
+// Low-latency protocol: a double travels as one 16-byte line {low half, seq, high half, seq}; the receiver needs no
+// separate flag and the sender no system-wide fence: each 8-byte half is valid as soon as its flag shows the
+// sequence number of the collective (the line is written and read with single 128-bit volatile accesses).
+__device__ __forceinline__ void peer_send(const StepParams& p, size_t slot_byte_off, int j, double value, unsigned int seq32) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(value);
+    const unsigned int lo = (unsigned int)bits, hi = (unsigned int)(bits >> 32);
+    for (int q = 0; q < p.peer_ranks; ++q) {
+        if (q == p.peer_rank) continue;
+        uint4* dst = reinterpret_cast<uint4*>(p.peer_mail[q] + slot_byte_off) + j;
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(seq32), "r"(hi), "r"(seq32) : "memory");
+    }
+}
+
+// Element j of the all-reduced vector: this rank's `own` value and the peers' values from this GPU's mailbox, added
+// in rank order (every rank forms the same sum).  The lines of up to eight peers are requested before the first is
+// examined — one L2 round trip when the data have arrived, not one per peer — and only lines whose flags do not
+// match yet are polled again.  A peer that does not answer within the time-out raises the status flag and the result
+// is NaN, so that a device-resident run cannot continue on a partial sum (the host reports the error).
+static __device__ __noinline__ double peer_gather_impl(const unsigned char* base, int peer_ranks, int peer_rank, int par,
+                                                       unsigned int seq32, int j, double own, unsigned long long t0,
+                                                       unsigned long long timeout_ns, int* status) {
+    double v = 0.0;
+    bool ok = true;
+    for (int q0 = 0; q0 < peer_ranks; q0 += 8) {
+        uint4 w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int q = q0 + u;
+            if (q < peer_ranks && q != peer_rank) {
+                const uint4* src = reinterpret_cast<const uint4*>(base + ((size_t)q * 2 + par) * kPeerSlotBytes) + j;
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[u].x), "=r"(w[u].y), "=r"(w[u].z), "=r"(w[u].w) : "l"(src) : "memory");
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int q = q0 + u;
+            if (q >= peer_ranks) break;
+            if (q == peer_rank) { v += own; continue; }
+            const uint4* src = reinterpret_cast<const uint4*>(base + ((size_t)q * 2 + par) * kPeerSlotBytes) + j;
+            while (ok && (w[u].y != seq32 || w[u].w != seq32)) {
+                if (globaltimer_ns() - t0 > timeout_ns) { *status = 1; ok = false; break; }
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[u].x), "=r"(w[u].y), "=r"(w[u].z), "=r"(w[u].w) : "l"(src) : "memory");
+            }
+            v += __longlong_as_double((long long)(((unsigned long long)w[u].z << 32) | (unsigned long long)w[u].x));
+        }
+    }
+    return ok ? v : __longlong_as_double(0x7FF8000000000000ll);
+}
+
+__device__ __forceinline__ double peer_gather(const StepParams& p, int par, unsigned int seq32, int j, double own,
+                                              unsigned long long t0) {
+    // (out of line, with plain arguments: the lines in flight get registers of their own instead of spilling the caller's)
+    return peer_gather_impl(p.peer_mail[p.peer_rank] + kPeerFlagBytes, p.peer_ranks, p.peer_rank, par, seq32, j, own, t0,
+                            p.peer_timeout_ns, p.peer_status);
+}
+
 // ---- fused tail of the step kernel ---------------------------------------------------------------
 // Executed by the last CTA of a step launch: every (entry, sector) sum runs over the partial rows in
 // fixed order, so the result does not depend on which CTA happens to be last.  Optionally followed by
@@ -268,49 +325,18 @@ __device__ inline void fused_tail(const StepParams& pp, double t_i, double t_w, 
     }
     if (p.peer_ranks > 1) {
         // ---- all-reduce over peer memory (replaces all_reduce!, src/mpi.jl:104-127) ----
-        // Low-latency protocol: every 8-byte store carries 4 bytes of payload and the 4-byte sequence number of
-        // this collective, so the receiver needs no separate flag and the sender no system-wide fence: a word is
-        // valid as soon as its flag matches (8-byte stores are single transactions on NVLink).  Each double
-        // travels as two such words.  Buffers alternate with the parity of the sequence number: a slot is
-        // rewritten two collectives later, after every peer has provably finished reading it.
+        // protocol: peer_send / peer_gather above.  Buffers alternate with the parity of the sequence number: a slot
+        // is rewritten two collectives later, after every peer has provably finished reading it.
         __syncthreads();
         const int par = (int)(p.peer_seq & 1ull);
         const unsigned int seq32 = (unsigned int)(p.peer_seq % 0xFFFFFFFFull) + 1u;   // never 0 (the mailbox starts zeroed)
         const size_t my_slot = kPeerFlagBytes + ((size_t)p.peer_rank * 2 + par) * kPeerSlotBytes;
-        const int n_dbl = 2 * n_out, n_words = 2 * n_dbl;
-        const double* outd = reinterpret_cast<const double*>(p.out);
-        for (int k = threadIdx.x; k < n_words; k += blockDim.x) {
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(outd[k >> 1]);
-            const unsigned int half = (k & 1) ? (unsigned int)(bits >> 32) : (unsigned int)bits;
-            const uint2 wd = make_uint2(half, seq32);
-            for (int q = 0; q < p.peer_ranks; ++q) {
-                if (q == p.peer_rank) continue;
-                uint2* dst = reinterpret_cast<uint2*>(p.peer_mail[q] + my_slot) + k;
-                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(wd.x), "r"(wd.y) : "memory");
-            }
-        }
-        // receive: poll every word until its flag shows this collective, add the contributions in rank order.
-        // A peer that does not answer within the time-out raises the status flag AND poisons the sum with NaN, so
-        // that a device-resident run cannot silently continue on a partial sum (the host reports the error).
-        const unsigned char* base = p.peer_mail[p.peer_rank] + kPeerFlagBytes;
+        const int n_dbl = 2 * n_out;
+        double* outd = reinterpret_cast<double*>(p.out);
+        for (int j = threadIdx.x; j < n_dbl; j += blockDim.x) peer_send(p, my_slot, j, outd[j], seq32);
         const unsigned long long t0 = globaltimer_ns();
-        for (int j = threadIdx.x; j < n_dbl; j += blockDim.x) {
-            double v = 0.0;
-            for (int q = 0; q < p.peer_ranks; ++q) {
-                if (q == p.peer_rank) { v += outd[j]; continue; }
-                const uint2* src = reinterpret_cast<const uint2*>(base + ((size_t)q * 2 + par) * kPeerSlotBytes) + 2 * j;
-                uint2 lo, hi;
-                bool ok = true;
-                do {
-                    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo.x), "=r"(lo.y) : "l"(src) : "memory");
-                    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hi.x), "=r"(hi.y) : "l"(src + 1) : "memory");
-                    if ((lo.y != seq32 || hi.y != seq32) && globaltimer_ns() - t0 > p.peer_timeout_ns) { *p.peer_status = 1; ok = false; break; }
-                } while (lo.y != seq32 || hi.y != seq32);
-                if (ok) v += __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | (unsigned long long)lo.x));
-                else v = __longlong_as_double(0x7FF8000000000000ll);
-            }
-            reinterpret_cast<double*>(p.out)[j] = v;   // element j is read and written by this thread only
-        }
+        for (int j = threadIdx.x; j < n_dbl; j += blockDim.x)
+            outd[j] = peer_gather(p, par, seq32, j, outd[j], t0);   // element j is read and written by this thread only
     }
     if (p.finish_k_f < 0) return;
     __syncthreads();

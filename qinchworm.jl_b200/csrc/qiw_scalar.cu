@@ -99,19 +99,19 @@ __device__ __forceinline__ typename Num<REAL>::T lane_dispatch(unsigned code, co
 // by table entry, in the kernel's arithmetic) may live in shared memory (run kernel) or `segcoef` be null.
 template <int STRIDE, bool REAL>
 __device__ __forceinline__ void segment_products(const DevEntry& e, const uint4* defs, const typename Num<REAL>::T* segcoef,
-                                                 unsigned char* Tb, unsigned row_bytes, int warp, int nw, int n_sub, int lane) {
+                                                 unsigned char* Tb, unsigned row_bytes, int warp, int nw, int sub_sh, int lane) {
     typedef typename Num<REAL>::T T;
     typedef Num<REAL> N;
     constexpr int NW = STRIDE > 7 ? 2 : 1, U = 4;
-    const int base = e.nP + e.nD, total = e.nSegL * n_sub;
+    const int base = e.nP + e.nD, total = e.nSegL << sub_sh;        // units = (table entry, sample sub-block of 32)
     for (int u0 = warp; u0 < total; u0 += U * nw) {
         uint32_t w[U][4 * NW];
         int jj[U]; unsigned col[U];
 #pragma unroll
         for (int b = 0; b < U; ++b) {
             const int u = min(u0 + b * nw, total - 1);      // the tail repeats the last unit (same value stored twice)
-            jj[b] = u / n_sub;
-            col[b] = (unsigned)((u - jj[b] * n_sub) * 32 + lane) * (unsigned)sizeof(T);
+            jj[b] = u >> sub_sh;
+            col[b] = (unsigned)((u - (jj[b] << sub_sh)) * 32 + lane) * (unsigned)sizeof(T);
             const uint4 a = defs[(size_t)jj[b] * NW];
             w[b][0] = a.x; w[b][1] = a.y; w[b][2] = a.z; w[b][3] = a.w;
             if constexpr (NW > 1) { const uint4 c2 = defs[(size_t)jj[b] * NW + 1]; w[b][4] = c2.x; w[b][5] = c2.y; w[b][6] = c2.z; w[b][7] = c2.w; }
@@ -359,10 +359,10 @@ __device__ __forceinline__ void phase_fill_P(const Cta<REAL>& c, const StepParam
 template <bool REAL>
 __device__ __forceinline__ void phase_segments(const Cta<REAL>& c) {
     const DevEntry& e = *c.e;
-    const int n_sub = max(c.ns >> 5, 1);
+    const int sub_sh = max(c.ns_sh - 5, 0);     // ns is a power of two
     if (c.lane >= c.ns) return;
     switch (e.seg_stride) {
-#define QIW_SEG(N_) case N_: segment_products<N_, REAL>(e, c.segdefs, c.segcoef, c.Tb, c.row_bytes, c.warp, c.nw, n_sub, c.lane); break;
+#define QIW_SEG(N_) case N_: segment_products<N_, REAL>(e, c.segdefs, c.segcoef, c.Tb, c.row_bytes, c.warp, c.nw, sub_sh, c.lane); break;
         QIW_SEG(1) QIW_SEG(2) QIW_SEG(3) QIW_SEG(4) QIW_SEG(5) QIW_SEG(6) QIW_SEG(7) QIW_SEG(8) QIW_SEG(9)
 #undef QIW_SEG
         default: break;
@@ -376,10 +376,10 @@ __device__ __forceinline__ void phase_walk(const Cta<REAL>& c, int S, double2* p
                                            unsigned long long count) {
     typedef typename Num<REAL>::T T;
     typedef Num<REAL> N;
-    const int n_sub = max(c.ns >> 5, 1), n_units = n_sub * c.n_chunks;
+    const int sub_sh = max(c.ns_sh - 5, 0), n_units = c.n_chunks << sub_sh;     // ns is a power of two
     const bool lane_on = c.lane < c.ns;
     for (int u = c.warp; u < n_units; u += c.nw) {
-        const int sub = u % n_sub, ch = u / n_sub;
+        const int ch = u >> sub_sh, sub = u - (ch << sub_sh);
         const unsigned col = (unsigned)(sub * 32 + (c.lane & (c.ns - 1))) * (unsigned)sizeof(T);
         const uint32_t run0 = c.chunk_off[c.chunk0 + ch], run1 = c.chunk_off[c.chunk0 + ch + 1];
         for (uint32_t k = run0; k < run1; ++k) {
@@ -806,38 +806,13 @@ __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) 
                 const int par = (int)(seq & 1ull);
                 const unsigned int seq32 = (unsigned int)(seq % 0xFFFFFFFFull) + 1u;
                 const size_t my_slot = kPeerFlagBytes + ((size_t)p.peer_rank * 2 + par) * kPeerSlotBytes;
-                const int n_dbl = 2 * n_ent * S, n_words = 2 * n_dbl;
-                const double* outd = reinterpret_cast<const double*>(outs);
-                if (blockIdx.x == 0) {
-                    for (int k = tidA; k < n_words; k += nthrA) {
-                        const unsigned long long bits = (unsigned long long)__double_as_longlong(outd[k >> 1]);
-                        const unsigned int half = (k & 1) ? (unsigned int)(bits >> 32) : (unsigned int)bits;
-                        for (int q = 0; q < p.peer_ranks; ++q) {
-                            if (q == p.peer_rank) continue;
-                            uint2* dst = reinterpret_cast<uint2*>(p.peer_mail[q] + my_slot) + k;
-                            asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(half), "r"(seq32) : "memory");
-                        }
-                    }
-                }
-                const unsigned char* base = p.peer_mail[p.peer_rank] + kPeerFlagBytes;
+                const int n_dbl = 2 * n_ent * S;
+                double* outd = reinterpret_cast<double*>(outs);
+                if (blockIdx.x == 0)
+                    for (int j = tidA; j < n_dbl; j += nthrA) peer_send(p, my_slot, j, outd[j], seq32);
                 const unsigned long long t0 = globaltimer_ns();
-                for (int j = tidA; j < n_dbl; j += nthrA) {
-                    double v = 0.0;
-                    for (int q = 0; q < p.peer_ranks; ++q) {
-                        if (q == p.peer_rank) { v += outd[j]; continue; }
-                        const uint2* src = reinterpret_cast<const uint2*>(base + ((size_t)q * 2 + par) * kPeerSlotBytes) + 2 * j;
-                        uint2 lo, hi;
-                        bool ok = true;
-                        do {
-                            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo.x), "=r"(lo.y) : "l"(src) : "memory");
-                            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hi.x), "=r"(hi.y) : "l"(src + 1) : "memory");
-                            if ((lo.y != seq32 || hi.y != seq32) && globaltimer_ns() - t0 > p.peer_timeout_ns) { *p.peer_status = 1; ok = false; break; }
-                        } while (lo.y != seq32 || hi.y != seq32);
-                        if (ok) v += __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | (unsigned long long)lo.x));
-                        else v = __longlong_as_double(0x7FF8000000000000ll);   // poison: the run must not continue on a partial sum
-                    }
-                    reinterpret_cast<double*>(outs)[j] = v;   // element j is read and written by this thread only
-                }
+                for (int j = tidA; j < n_dbl; j += nthrA)
+                    outd[j] = peer_gather(p, par, seq32, j, outd[j], t0);   // element j is read and written by this thread only
                 bar_A();
             }
             QIW_RT(7)

@@ -67,6 +67,7 @@ class Solver:
         self.payload = self.ctx.set_expansion(expansion)
         self._next_entry = 0
         self._entries = {}       # (mode, order, n_pts_after, corr_idx) -> compiled entry, reused across calls
+        self._steps = {}         # entry ids of a step -> _PreparedStep (host-stepped loop, default RandomizationParams)
         self._n_corr_uploaded = len(expansion.corr_operators_mat)
 
     def refresh_model(self):
@@ -74,6 +75,7 @@ class Solver:
         self.payload = self.ctx.set_expansion(self.expansion)
         self._next_entry = 0
         self._entries = {}
+        self._steps = {}
         self._n_corr_uploaded = len(self.expansion.corr_operators_mat)
 
     def upload_P(self, first=0, count=None):
@@ -106,6 +108,14 @@ class Solver:
         self.ctx.set_topologies(td.entry_id, mode, order, n_pts_after, tops[0], tops[1], corr_idx=corr_idx)
         self._entries[key] = (td.entry_id, tops)
         return td
+
+    def scale_P(self, k_f, value, lam=0.0):
+        """The step seam (qiw_scale_P): row k_f of the device's table := value, then every row k times exp(-lam tau_k)."""
+        if getattr(self, "_row", None) is None or self._row.shape[1] != self.ctx.bsize:
+            self._row = np.zeros((1, self.ctx.bsize), dtype=np.complex128)
+            self._row_ptr = lib._ptr(self._row.view(np.float64), lib.f64p)
+        self._row[0] = value
+        self.ctx.scale_P_prepared(k_f, self._row_ptr, float(lam))
 
     def eval_samples(self, t_i, t_w, t_f, top_data):
         """The randomised estimates of every entry's qMC integral: a list, per entry, of arrays [n_seqs_used, bsize]
@@ -178,17 +188,50 @@ def _order_sums(top_data, mean, std, bsize):
     return total, contribs, contribs_std
 
 
+class _PreparedStep:
+    """What one host-stepped step with the default RandomizationParams needs besides the library call, built once per
+    list of entries: the id array, the result buffer and their ctypes pointers, and the per-order sums as ONE real
+    matmul onehot[order, entry] x result[entry, (element, re/im)] (the interpreter, not the GPU, bounds this seam)."""
+
+    def __init__(self, ctx, top_data):
+        self.n = len(top_data)
+        self.ids = np.ascontiguousarray([td.entry_id for td in top_data], dtype=np.int32)
+        self.out = np.zeros((self.n, ctx.bsize), dtype=np.complex128)
+        self.out_real = self.out.view(np.float64)
+        self.ids_ptr, self.out_ptr = lib._ptr(self.ids, lib.i32p), lib._ptr(self.out_real, lib.f64p)
+        self.orders = sorted({td.order for td in top_data})
+        self.onehot = np.zeros((len(self.orders), self.n))
+        for j, td in enumerate(top_data):
+            self.onehot[self.orders.index(td.order), j] = 1.0
+        # the std of a single sequence is NaN (src/randomization.jl:99), of the exact order-0 entries 0 (src/inchworm.jl:155)
+        self.std = {o: np.full(ctx.bsize, 0.0 if o == 0 else np.nan, dtype=complex) for o in self.orders}
+        self.N = top_data[0].N_samples
+
+
+def _step(solver: Solver, t_i, t_w, t_f, top_data):
+    rp = top_data[0].rand_params if top_data else None
+    if rp is not None and rp.rng is None and rp.N_seqs == 1:
+        key = tuple(td.entry_id for td in top_data)
+        ps = solver._steps.get(key)
+        if ps is None:
+            assert all(td.N_samples == top_data[0].N_samples for td in top_data)
+            ps = solver._steps[key] = _PreparedStep(solver.ctx, top_data)
+        solver.ctx.eval_prepared(t_i, t_w, t_f, ps.n, ps.ids_ptr, ps.N, ps.out_ptr)
+        sums = (ps.onehot @ ps.out_real).view(np.complex128)          # [n_orders, bsize], a fresh array
+        return sums.sum(axis=0), {o: sums[q] for q, o in enumerate(ps.orders)}, ps.std
+    mean, std = solver.eval_entries(t_i, t_w, t_f, top_data)
+    return _order_sums(top_data, mean, std, solver.ctx.bsize)
+
+
 def inchworm_step_bare(solver: Solver, grid, k_i, k_f, top_data):
     """One initial step with bare propagators (src/inchworm.jl:228-304).  Returns
     (value, order_contribs, order_contribs_std) as packed block vectors."""
-    mean, std = solver.eval_entries(grid.tau[k_i], grid.tau[k_i], grid.tau[k_f], top_data)
-    return _order_sums(top_data, mean, std, solver.ctx.bsize)
+    return _step(solver, grid.tau[k_i], grid.tau[k_i], grid.tau[k_f], top_data)
 
 
 def inchworm_step(solver: Solver, grid, k_i, k_w, k_f, top_data):
     """One regular inchworm step with bold propagators (src/inchworm.jl:123-204)."""
-    mean, std = solver.eval_entries(grid.tau[k_i], grid.tau[k_w], grid.tau[k_f], top_data)
-    return _order_sums(top_data, mean, std, solver.ctx.bsize)
+    return _step(solver, grid.tau[k_i], grid.tau[k_w], grid.tau[k_f], top_data)
 
 
 def _bold_entries(solver, orders, N_samples, rand_params, n_pts_after_max):
@@ -258,13 +301,13 @@ def inchworm(expansion, grid, orders, orders_bare, N_samples, n_pts_after_max=No
         P_orders_std[o][1] = contribs_std[o]
     # the rest of inching (:420-493)
     top_data = _bold_entries(solver, orders, N_samples, rand_params, n_pts_after_max)
-    solver.ctx.scale_P(1, value)
+    solver.scale_P(1, value)
     for n in range(1, n_tau - 1):
         value, contribs, contribs_std = inchworm_step(solver, grid, 0, n, n + 1, top_data)
         ppgf.set_ppgf(expansion, n + 1, value)
         lam = ppgf.normalize_at(expansion, n + 1)  # suppress exponential growth (:488)
         # the device's table follows with one row and lambda (qiw_scale_P) instead of a re-upload of the whole table
-        solver.ctx.scale_P(n + 1, value, lam)
+        solver.scale_P(n + 1, value, lam)
         for o in contribs:
             P_orders[o][n + 1] = contribs[o]
             P_orders_std[o][n + 1] = contribs_std[o]

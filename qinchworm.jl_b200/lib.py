@@ -263,6 +263,12 @@ class Context:
             r, rv = _cview(np.atleast_2d(row))
             self._ck(self.L.qiw_scale_P(self.h, k_f, _ptr(rv, f64p), float(lam)))
 
+    def scale_P_prepared(self, k_f, row_ptr, lam):
+        """qiw_scale_P with a long-lived row buffer."""
+        rc = self.L.qiw_scale_P(self.h, k_f, row_ptr, lam)
+        if rc:
+            self._ck(rc)
+
     def get_P(self, first=0, count=None):
         count = self.n_tau - first if count is None else count
         out = np.zeros((count, self.bsize), dtype=np.complex128)
@@ -351,6 +357,13 @@ class Context:
         self._ck(self.L.qiw_eval(self.h, t_i, t_w, t_f, len(ids), _ptr(ids, i32p), pm, px, N_total,
                                  _ptr(out.view(np.float64), f64p)))
         return out
+
+    def eval_prepared(self, t_i, t_w, t_f, n, ids_ptr, N_total, out_ptr):
+        """qiw_eval with the caller's long-lived id array and result buffer (ctypes pointers made once): the host-stepped
+        loop calls this once per time step."""
+        rc = self.L.qiw_eval(self.h, t_i, t_w, t_f, n, ids_ptr, None, None, N_total, out_ptr)
+        if rc:
+            self._ck(rc)
 
     def eval_batch(self, times, entry_ids, N_total, sobol=None):
         """qiw_eval_batch: times[n_times, 3] = (t_i, t_w, t_f); returns [n_times, n_entries, bsize]."""

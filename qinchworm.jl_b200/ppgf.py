@@ -6,6 +6,8 @@ column-major inside a block).  These O(n_tau) updates stay on the host in the st
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 __all__ = ["set_ppgf", "normalize_at", "normalize", "partition_function", "density_matrix"]
@@ -17,19 +19,28 @@ def set_ppgf(expansion, k_f: int, value):
 
 
 def _diag_indices(expansion):
+    key = (tuple(expansion.dims), tuple(expansion.boff))
+    cached = getattr(expansion, "_diag_cache", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
     idx = []
     for s, d in enumerate(expansion.dims):
         idx += [expansion.boff[s] + i + d * i for i in range(d)]
-    return np.asarray(idx, dtype=int)
+    idx = np.asarray(idx, dtype=int)
+    try:
+        expansion._diag_cache = (key, idx)
+    except AttributeError:
+        pass
+    return idx
 
 
 def normalize_at(expansion, k_f: int):
     """normalize!(P, tau): lambda = log(max_s max diag(-Im P_s(tau))) / tau, then every stored grid
     value is multiplied by exp(-lambda tau_k) (src/ppgf.jl:646-668).  Returns lambda."""
     tau = expansion.grid.tau
-    p_max = np.max(-expansion.P[k_f, _diag_indices(expansion)].imag)
-    lam = np.log(p_max) / tau[k_f]
-    expansion.P *= np.exp(-tau * lam)[:, None]
+    p_max = -float(expansion.P[k_f].imag[_diag_indices(expansion)].min())
+    lam = (math.log(p_max) if p_max > 0.0 else float("nan")) / float(tau[k_f])
+    expansion.P *= np.exp(tau * -lam)[:, None]
     return lam
 
 
