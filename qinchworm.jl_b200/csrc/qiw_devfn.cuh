@@ -252,46 +252,27 @@ __device__ __forceinline__ void peer_send(const StepParams& p, size_t slot_byte_
 }
 
 // Element j of the all-reduced vector: this rank's `own` value and the peers' values from this GPU's mailbox, added
-// in rank order (every rank forms the same sum).  The lines of up to eight peers are requested before the first is
-// examined — one L2 round trip when the data have arrived, not one per peer — and only lines whose flags do not
-// match yet are polled again.  A peer that does not answer within the time-out raises the status flag and the result
-// is NaN, so that a device-resident run cannot continue on a partial sum (the host reports the error).
-static __device__ __noinline__ double peer_gather_impl(const unsigned char* base, int peer_ranks, int peer_rank, int par,
-                                                       unsigned int seq32, int j, double own, unsigned long long t0,
-                                                       unsigned long long timeout_ns, int* status) {
-    double v = 0.0;
-    bool ok = true;
-    for (int q0 = 0; q0 < peer_ranks; q0 += 8) {
-        uint4 w[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int q = q0 + u;
-            if (q < peer_ranks && q != peer_rank) {
-                const uint4* src = reinterpret_cast<const uint4*>(base + ((size_t)q * 2 + par) * kPeerSlotBytes) + j;
-                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[u].x), "=r"(w[u].y), "=r"(w[u].z), "=r"(w[u].w) : "l"(src) : "memory");
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int q = q0 + u;
-            if (q >= peer_ranks) break;
-            if (q == peer_rank) { v += own; continue; }
-            const uint4* src = reinterpret_cast<const uint4*>(base + ((size_t)q * 2 + par) * kPeerSlotBytes) + j;
-            while (ok && (w[u].y != seq32 || w[u].w != seq32)) {
-                if (globaltimer_ns() - t0 > timeout_ns) { *status = 1; ok = false; break; }
-                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[u].x), "=r"(w[u].y), "=r"(w[u].z), "=r"(w[u].w) : "l"(src) : "memory");
-            }
-            v += __longlong_as_double((long long)(((unsigned long long)w[u].z << 32) | (unsigned long long)w[u].x));
-        }
-    }
-    return ok ? v : __longlong_as_double(0x7FF8000000000000ll);
-}
-
+// in rank order (every rank forms the same sum).  A peer that does not answer within the time-out raises the status
+// flag and the result is NaN, so that a device-resident run cannot continue on a partial sum (the host reports the
+// error).  Peer by peer on purpose: requesting all peers' lines at once (eight lines in flight per thread, or one
+// thread per (peer, element) through shared memory) was measured on 4 GPUs and gains nothing — the wait is for the
+// slowest peer, not for L2 — while the extra live registers cost the run kernel 4-15 % on ONE GPU.
 __device__ __forceinline__ double peer_gather(const StepParams& p, int par, unsigned int seq32, int j, double own,
                                               unsigned long long t0) {
-    // (out of line, with plain arguments: the lines in flight get registers of their own instead of spilling the caller's)
-    return peer_gather_impl(p.peer_mail[p.peer_rank] + kPeerFlagBytes, p.peer_ranks, p.peer_rank, par, seq32, j, own, t0,
-                            p.peer_timeout_ns, p.peer_status);
+    const unsigned char* base = p.peer_mail[p.peer_rank] + kPeerFlagBytes;
+    double v = 0.0;
+    bool ok = true;
+    for (int q = 0; q < p.peer_ranks; ++q) {
+        if (q == p.peer_rank) { v += own; continue; }
+        const uint4* src = reinterpret_cast<const uint4*>(base + ((size_t)q * 2 + par) * kPeerSlotBytes) + j;
+        uint4 w;
+        do {
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(src) : "memory");
+            if ((w.y != seq32 || w.w != seq32) && globaltimer_ns() - t0 > p.peer_timeout_ns) { *p.peer_status = 1; ok = false; break; }
+        } while (w.y != seq32 || w.w != seq32);
+        v += __longlong_as_double((long long)(((unsigned long long)w.z << 32) | (unsigned long long)w.x));
+    }
+    return ok ? v : __longlong_as_double(0x7FF8000000000000ll);
 }
 
 // ---- fused tail of the step kernel ---------------------------------------------------------------

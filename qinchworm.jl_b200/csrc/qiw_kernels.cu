@@ -351,8 +351,9 @@ namespace qiw {
 //   applied at the leaf together with the coefficient (topology sign, :431).
 // Preconditions checked by the host: operator blocks real, P and Delta purely imaginary, coefficients
 // purely imaginary (then every product is real, exactly).  Otherwise block_step_kernel (complex) runs.
-// One edge = two stages: V <- iP_s * V (DS x DS times DS x D0), then, at nodes with an operator, V <- O * V
-// (DR x DS times DS x D0).  Both run column by column and in place.
+// One edge = two stages, each dispatched on its own block shape so that the code the walker touches stays
+// small (the SM's instruction cache holds 32 KB): V <- iP_s * V (DS x DS times DS x D0), then, at nodes
+// with an operator, V <- O * V (DR x DS times DS x D0).  Both run column by column and in place.
 template <int DS, int D0>
 __device__ __forceinline__ void block_mul_P(const double* __restrict__ Pm, double (&V)[4 * D0]) {
     double Pv[DS * DS];
@@ -373,25 +374,16 @@ __device__ __forceinline__ void block_mul_P(const double* __restrict__ Pm, doubl
     }
 }
 
-// Both stages of an edge in one body: the operator block's loads do not depend on V and are issued together with the
-// propagator block's, ahead of the first FMA chain; same operations in the same order as two separate stages.
 template <int DR, int DS, int D0>
-__device__ __forceinline__ void block_edge(const double* __restrict__ Pm, const double* __restrict__ O, double (&V)[4 * D0]) {
-    double Pv[DS * DS], Ov[DR * DS];
+__device__ __forceinline__ void block_mul_O(const double* __restrict__ O, double (&V)[4 * D0]) {
+    double Ov[DR * DS];
 #pragma unroll
-    for (int k = 0; k < DS * DS; ++k) Pv[k] = Pm[k * 32];
-#pragma unroll
-    for (int k = 0; k < DR * DS; ++k) Ov[k] = O[k];
+    for (int k = 0; k < DR * DS; ++k) Ov[k] = O[k];      // the operator pool is staged in shared memory when it fits (warp-uniform address: broadcast)
 #pragma unroll
     for (int j = 0; j < D0; ++j) {
         double t[DS];
 #pragma unroll
-        for (int i = 0; i < DS; ++i) {
-            double a = Pv[i] * V[4 * j];
-#pragma unroll
-            for (int k = 1; k < DS; ++k) a = fma(Pv[i + DS * k], V[k + 4 * j], a);
-            t[i] = a;
-        }
+        for (int k = 0; k < DS; ++k) t[k] = V[k + 4 * j];
 #pragma unroll
         for (int i = 0; i < DR; ++i) {
             double a = Ov[i] * t[0];
@@ -402,16 +394,17 @@ __device__ __forceinline__ void block_edge(const double* __restrict__ Pm, const 
     }
 }
 
-// ONE dispatch per edge on (has_op, dr, ds) — the low nine bits of the program word.
 template <int D0>
-__device__ __forceinline__ void block_edge_dispatch(uint32_t x, const double* Pm, const double* O, double (&V)[4 * D0]) {
-    const uint32_t key = (x & 0x100u) ? (x & 0x1FFu) : (x & 0xFu);
-#define QIW_BE(R_, S_) case (0x100 | R_ << 4 | S_): block_edge<R_, S_, D0>(Pm, O, V); break;
-    switch (key) {
+__device__ __forceinline__ void block_edge_dispatch(int dr, int ds, const double* Pm, const double* O, bool has_op, double (&V)[4 * D0]) {
+    switch (ds) {
         case 1: block_mul_P<1, D0>(Pm, V); break;
         case 2: block_mul_P<2, D0>(Pm, V); break;
         case 3: block_mul_P<3, D0>(Pm, V); break;
-        case 4: block_mul_P<4, D0>(Pm, V); break;
+        default: block_mul_P<4, D0>(Pm, V); break;
+    }
+    if (!has_op) return;
+#define QIW_BE(R_, S_) case (R_ * 8 + S_): block_mul_O<R_, S_, D0>(O, V); break;
+    switch (dr * 8 + ds) {
         QIW_BE(1, 1) QIW_BE(1, 2) QIW_BE(1, 3) QIW_BE(1, 4) QIW_BE(2, 1) QIW_BE(2, 2) QIW_BE(2, 3) QIW_BE(2, 4)
         QIW_BE(3, 1) QIW_BE(3, 2) QIW_BE(3, 3) QIW_BE(3, 4) QIW_BE(4, 1) QIW_BE(4, 2) QIW_BE(4, 3) QIW_BE(4, 4)
         default: break;
@@ -485,8 +478,10 @@ __device__ __forceinline__ void block_walk_tree(const uint4* __restrict__ xw, ui
         // ... and its cache line well ahead: the words are read once per block of samples, so every new
         // 128-byte line (8 words) would otherwise come from L2 with the warp waiting on it
         asm volatile("prefetch.global.L1 [%0];" ::"l"(xw + pc + kWalkPrefetch));
+        const int ds = (int)(cur.x & 0xFu), dr = (int)((cur.x >> 4) & 0xFu);
+        const bool has_op = (cur.x >> 8) & 1u;
         const double* Pm = TP + (cur.y & 0xFFFFu) * 32 + lane;
-        block_edge_dispatch<D0>(cur.x, Pm, pool_re + cur.z, V);
+        block_edge_dispatch<D0>(dr, ds, Pm, pool_re + cur.z, has_op, V);
         const uint32_t sbq = cur.y >> 16;
         if (sbq) dprod *= TD[(size_t)(sbq - 1) * 32 + lane];   // interaction weight at the arc's tail (:506-507)
         nch = (int)(cur.x >> 16);
