@@ -303,3 +303,54 @@ def test_threaded_compile_is_bit_identical(qlib, model, monkeypatch):
         digests[threads] = h.hexdigest()
         ctx.close()
     assert digests["1"] == digests["8"]
+
+
+def test_host_stepped_step_bookkeeping(qlib):
+    """The host-stepped loop's fast path (default RandomizationParams: long-lived id/result buffers, per-order sums as
+    one matmul) returns what the general path (eval_entries + _order_sums) returns, and normalize_at is the
+    reference's normalize! (src/ppgf.jl:646-668): lambda from the largest diagonal element, every row times
+    exp(-lambda tau_k).  The library call is replaced by a stub that fills the result buffer (no GPU here)."""
+    from qinchworm_b200 import lib, ppgf
+    from qinchworm_b200.inchworm import RandomizationParams, Solver, _bold_entries, _order_sums, inchworm_step
+    ex, grid = models.anderson(n_tau=16)[:2]
+    ctx = lib.Context(device=lib.DEVICE_NONE)
+    solver = Solver(ex, ctx=ctx)
+    top = _bold_entries(solver, range(0, 4), 64, None, None)
+    rng = np.random.default_rng(7)
+    res = rng.standard_normal((len(top), ctx.bsize)) + 1j * rng.standard_normal((len(top), ctx.bsize))
+    seen = {}
+
+    def eval_prepared(t_i, t_w, t_f, n, ids_ptr, N, out_ptr):
+        seen["args"] = (t_i, t_w, t_f, n, N)
+        seen["ids"] = np.ctypeslib.as_array(ids_ptr, shape=(n,)).copy()
+        np.ctypeslib.as_array(out_ptr, shape=(n * ctx.bsize * 2,))[:] = res.view(np.float64).reshape(-1)
+
+    ctx.eval_prepared = eval_prepared
+    total, contribs, contribs_std = inchworm_step(solver, grid, 0, 3, 4, top)
+    assert seen["args"] == (grid.tau[0], grid.tau[3], grid.tau[4], len(top), 64)
+    assert list(seen["ids"]) == [td.entry_id for td in top]
+    std = np.full_like(res, np.nan)
+    std[[j for j, td in enumerate(top) if td.order == 0]] = 0.0
+    t2, c2, s2 = _order_sums(top, res, std, ctx.bsize)
+    assert np.allclose(total, t2, rtol=1e-14, atol=1e-14)
+    assert sorted(contribs) == sorted(c2) == [0, 1, 2, 3]
+    for o in c2:
+        assert np.allclose(contribs[o], c2[o], rtol=1e-14, atol=1e-14)
+        assert np.array_equal(np.isnan(contribs_std[o]), np.isnan(s2[o])) and (o > 0 or np.all(contribs_std[o] == 0))
+    # a second call reuses the prepared buffers and must not alias the first call's results
+    res2 = res * 2.0
+    res_saved, res = res, res2
+    total_b, contribs_b, _ = inchworm_step(solver, grid, 0, 4, 5, top)
+    assert np.allclose(total_b, 2.0 * t2) and np.allclose(total, t2)
+    assert len(solver._steps) == 1
+    # a randomised call takes the general path (it needs the GPU): only check that the fast path is not chosen
+    assert RandomizationParams().rng is None and RandomizationParams().N_seqs == 1
+    # normalize_at
+    P0 = -1j * (0.5 + rng.random(ex.P.shape))
+    ex.P[:] = P0
+    lam = ppgf.normalize_at(ex, 5)
+    diag = ppgf._diag_indices(ex)
+    lam_ref = np.log(np.max(-P0[5, diag].imag)) / grid.tau[5]
+    assert abs(lam - lam_ref) < 1e-14 * max(1.0, abs(lam_ref))
+    assert np.allclose(ex.P, P0 * np.exp(-grid.tau * lam_ref)[:, None], rtol=1e-14, atol=0)
+    assert abs(np.max(-ex.P[5, diag].imag) - 1.0) < 1e-13
