@@ -20,9 +20,9 @@
 #include "qiw_host.hpp"
 
 namespace qiw {
-cudaError_t launch_scalar_step(bool real_mode, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st);
-cudaError_t launch_scalar_run(bool real_mode, const RunParams& rp, int n_ctas, int threads, size_t smem, cudaStream_t st);
-int scalar_run_max_ctas(bool real_mode, int threads, size_t smem, int n_sm);
+cudaError_t launch_scalar_step(bool real_mode, bool dual, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_scalar_run(bool real_mode, bool dual, const RunParams& rp, int n_ctas, int threads, size_t smem, cudaStream_t st);
+int scalar_run_max_ctas(bool real_mode, bool dual, int threads, size_t smem, int n_sm);
 cudaError_t launch_reduce(const DevEntryDyn* dyn, const DevEntry* entries, const double2* partials, int pitch, int S,
                           double t_i, double t_w, double t_f, double2* out, int n_entries, cudaStream_t st);
 cudaError_t launch_finish_step(double2* P, int n_tau, int bsize, const int* diag, int n_diag, double h, int k_f,
@@ -136,6 +136,7 @@ struct Plan {   // launch plan of one qiw_eval call shape, cached
     int pitch = 1;
     int block_threads = 0;                 // block models: threads per CTA
     size_t scratch_per_thread = 0;
+    bool lane_dual = false;                // some entry's lane program has records shared by two initial sectors: the kernels' DUAL instantiations run
     bool block_real = false;               // block models: planned for the real-arithmetic tree replay (blocks up to 4x4)
     bool block_mma = false;                // block models with blocks of 5 to 8 rows, real arithmetic: FP64 tensor-core kernel
     DevBuf<int> d_bounds;                  // [n_items][warps + 1] tree ranges (block_walk_kernel)
@@ -780,7 +781,7 @@ int qiw_entry_lane_program(qiw_context* ctx, int32_t id, int32_t* info, int32_t*
     if (sections)
         for (size_t k = 0; k < p.lane_sections.size(); ++k) {
             const auto& sc = p.lane_sections[k];
-            sections[4 * k] = sc.s_i; sections[4 * k + 1] = sc.M; sections[4 * k + 2] = (int32_t)sc.n_rec; sections[4 * k + 3] = (int32_t)(sc.chunk0 * 8u);
+            sections[4 * k] = sc.s_i | ((sc.s_b + 1) << 8); sections[4 * k + 1] = sc.M; sections[4 * k + 2] = (int32_t)sc.n_rec; sections[4 * k + 3] = (int32_t)(sc.chunk0 * 8u);
         }
     if (items) for (size_t k = 0; k < p.lane_items.size(); ++k) items[k] = p.lane_items[k];
     if (segdef) memcpy(segdef, p.lane_segdef.data(), (size_t)p.nSegL * p.seg_stride * sizeof(uint16_t));
@@ -885,7 +886,7 @@ static void append_entry_chunks(const EntryProgram& p, int n_chunks, std::vector
             if (!last) take = (uint32_t)std::min<int64_t>(take, std::max<int64_t>(1, (target - done + sec.cost - 1) / sec.cost));
             const int ni = lane_record_items(p.order, p.K, sec.M) / 8;
             const uint32_t mc = sec.M == 1 ? 0u : (sec.M == 2 ? 1u : 2u);
-            runs.push_back(make_uint4(sec.chunk0 + r_in * (uint32_t)ni, take, (uint32_t)sec.s_i,
+            runs.push_back(make_uint4(sec.chunk0 + r_in * (uint32_t)ni, take, (uint32_t)sec.s_i | ((uint32_t)(sec.s_b + 1) << 8),
                                       (uint32_t)(p.order * 16 + (p.K - 1) * 4) + mc));
             done += (int64_t)take * sec.cost;
             r_in += take;
@@ -1151,7 +1152,7 @@ static int get_plan(qiw_context* ctx, int n_entries, const int32_t* ids, uint64_
             const uint64_t c = p.order == 0 ? 1 : count;
             pl->max_sb = std::max<uint64_t>(pl->max_sb, (c + spb_plan - 1) / spb_plan);
             int64_t n_rec = 0;
-            for (const auto& sec : p.lane_sections) n_rec += sec.n_rec;
+            for (const auto& sec : p.lane_sections) { n_rec += sec.n_rec; if (sec.s_b >= 0) pl->lane_dual = true; }
             const int jobs = (int)std::max(1.0, std::ceil((double)p.lane_cost / (W * chunk_cap)));
             const int n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(n_rec, (int64_t)W * jobs));
             pl->item0[i] = (int)pl->items.size();
@@ -1381,7 +1382,7 @@ static int enqueue_step(qiw_context* ctx, Plan& pl, double t_i, double t_w, doub
         dim3 grid((unsigned)pl.pitch, (unsigned)g.n_items, (unsigned)std::max(n_times, 1));
         {
             ProfScope ps(ctx, real ? 1 : 0);
-            CK(launch_scalar_step(real != 0, gp, grid, g.warps[real] * 32, g.smem[real], ctx->stream));
+            CK(launch_scalar_step(real != 0, pl.lane_dual, gp, grid, g.warps[real] * 32, g.smem[real], ctx->stream));
         }
         ctx->launches++;
     }
@@ -1591,7 +1592,7 @@ static int enqueue_run(qiw_context* ctx, Plan& pl, int k_first, int n_steps, dou
         // by the shared-memory pipe of the busiest SM, so the unit of balance is the SM; the CTAs that the hardware places
         // on one SM claim the job lists of one bin at run time (scalar_run_kernel).  With fewer jobs than CTA slots the
         // lists are simply one per CTA.
-        const int max_ctas = scalar_run_max_ctas(real != 0, threads, L.total, n_sm);
+        const int max_ctas = scalar_run_max_ctas(real != 0, pl.lane_dual, threads, L.total, n_sm);
         if (max_ctas < n_sm) return skip("occupancy below one CTA per SM");
         const bool by_sm = (int)jobs.size() > n_sm && max_ctas >= G && !getenv("QIW_RUN_NO_SM_BINS");
         const int n_ctas = by_sm ? G : (int)std::min<size_t>(jobs.size(), (size_t)std::min(G, max_ctas));
@@ -1689,7 +1690,7 @@ static int enqueue_run(qiw_context* ctx, Plan& pl, int k_first, int n_steps, dou
     ctx->last_real_mode = real;
     {
         ProfScope ps(ctx, 2);
-        CK(launch_scalar_run(real != 0, rp, rn.n_ctas, rn.threads, rn.smem, ctx->stream));
+        CK(launch_scalar_run(real != 0, pl.lane_dual, rp, rn.n_ctas, rn.threads, rn.smem, ctx->stream));
     }
     ctx->launches++;
     if (trace_path) {

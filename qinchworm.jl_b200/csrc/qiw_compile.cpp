@@ -473,8 +473,9 @@ void build_lane_program(EntryProgram& e) {
         e.lane_seg_coef.push_back((uint16_t)coef);
         return id;
     };
-    // 2. groups: (initial sector, sorted Delta slots) -> members, in order of first appearance
-    struct Group { uint32_t s_i; std::vector<uint32_t> dsl; std::vector<uint32_t> members; };   // members: K slots each
+    // 2. groups: sorted Delta slots -> members by initial sector, in order of first appearance.  Configurations that
+    //    differ only in the initial sector (spin-symmetric sectors, typically) share all pair-interaction operands.
+    struct Group { std::vector<uint32_t> dsl; std::map<uint32_t, std::vector<uint32_t>> members; };   // sector -> K slots per member
     std::vector<Group> groups;
     std::map<std::vector<uint32_t>, size_t> gindex;
     std::vector<uint32_t> key;
@@ -482,47 +483,65 @@ void build_lane_program(EntryProgram& e) {
         const uint32_t* r = e.rec2.data() + (size_t)l * RL;
         key.assign(r + 1 + K, r + 1 + K + n);
         std::sort(key.begin(), key.end());
-        key.push_back(r[0] >> 16);
         auto it = gindex.find(key);
         size_t g;
         if (it == gindex.end()) {
             g = groups.size();
             gindex[key] = g;
             groups.emplace_back();
-            groups[g].s_i = r[0] >> 16;
-            groups[g].dsl.assign(key.begin(), key.end() - 1);
+            groups[g].dsl = key;
         } else g = it->second;
+        std::vector<uint32_t>& mem = groups[g].members[r[0] >> 16];
         for (int q = 0; q < K; ++q)
-            groups[g].members.push_back((uint32_t)(nP + nD) + seg_id(q == 0 ? (r[0] & 0xFFFFu) : 0xFFFFu, r[1 + q]));
+            mem.push_back((uint32_t)(nP + nD) + seg_id(q == 0 ? (r[0] & 0xFFFFu) : 0xFFFFu, r[1 + q]));
     }
-    // 3. fixed-shape records: every group is cut greedily into records of 4, 2 and 1 members; sections = (M, sector)
-    int S = 0;
-    for (const Group& g : groups) S = std::max(S, (int)g.s_i + 1);
-    const int Ms[3] = {4, 2, 1};
-    for (int mi = 0; mi < 3; ++mi) {
-        const int M = Ms[mi], ni = lane_record_items(n, K, M);
-        for (int s = 0; s < S; ++s) {
-            EntryProgram::LaneSection sec;
-            sec.s_i = s; sec.M = M; sec.rec0 = 0; sec.n_rec = 0; sec.chunk0 = (uint32_t)(e.lane_items.size() / 8);
-            sec.cost = (uint32_t)(n + M * K + 2);
-            for (const Group& g : groups) {
-                if ((int)g.s_i != s) continue;
-                // members of this group that fall into records of M members under the greedy 4-2-1 cut
-                const int nm = (int)(g.members.size() / std::max(K, 1));
-                int first = 0, count = 0;     // first member / number of records of this class
-                if (M == 4) { count = nm / 4; first = 0; }
-                else if (M == 2) { count = (nm % 4) / 2; first = (nm / 4) * 4; }
-                else { count = nm % 2; first = (nm / 2) * 2; }
-                for (int c = 0; c < count; ++c) {
-                    const size_t base = e.lane_items.size();
-                    for (uint32_t d : g.dsl) e.lane_items.push_back((uint16_t)d);
-                    for (int q = 0; q < M * K; ++q) e.lane_items.push_back((uint16_t)g.members[(size_t)(first + c * M) * K + q]);
-                    e.lane_items.resize(base + ni, 0);
-                    ++sec.n_rec;
-                }
-            }
-            if (sec.n_rec) { e.lane_sections.push_back(sec); e.lane_cost += (int64_t)sec.n_rec * sec.cost; }
+    // 3. fixed-shape records.  Per group and sector: records of four members; of the remainder, a unit of two and/or a
+    //    unit of one.  Units of equal size from two sectors of the same group share ONE record (first half of the members
+    //    -> sector a, second half -> sector b: the Delta operands are loaded once for both), what is left over becomes a
+    //    record of its own.  Sections = (members per record, sector a[, sector b]).  Shared records are used from order 5
+    //    on: 16 % fewer operand loads and a third fewer records (orders 0:6 at N = 2^14: 21.0 -> 17.8 ms), but two more
+    //    record shapes per entry, and at order <= 4 a warp runs so few records per shape that the additional code
+    //    costs more than the loads save (README run 3.52 -> 3.9 ms).  QIW_LANE_DUAL=0 / 1 overrides.
+    bool dual_ok = n >= 5;
+    if (const char* env = getenv("QIW_LANE_DUAL")) dual_ok = env[0] != '0';
+    struct SecKey { int cls; int s_a, s_b; bool operator<(const SecKey& o) const { return std::tie(cls, s_a, s_b) < std::tie(o.cls, o.s_a, o.s_b); } };
+    std::map<SecKey, std::vector<uint16_t>> sec_items;     // records of every section, in group order
+    auto emit = [&](int cls, int M, int s_a, int s_b, const Group& g, const uint32_t* ma, const uint32_t* mb) {
+        std::vector<uint16_t>& v = sec_items[SecKey{cls, s_a, s_b}];
+        const size_t base = v.size();
+        for (uint32_t d : g.dsl) v.push_back((uint16_t)d);
+        const int half = (s_b < 0) ? M : M / 2;
+        for (int q = 0; q < half * K; ++q) v.push_back((uint16_t)ma[q]);
+        if (s_b >= 0) for (int q = 0; q < half * K; ++q) v.push_back((uint16_t)mb[q]);
+        v.resize(base + lane_record_items(n, K, M), 0);
+    };
+    for (const Group& g : groups) {
+        std::vector<std::pair<int, const uint32_t*>> twos, ones;     // (sector, first member) of the remainder units
+        for (const auto& kv : g.members) {
+            const int s = (int)kv.first, nm = (int)(kv.second.size() / std::max(K, 1));
+            const uint32_t* m = kv.second.data();
+            for (int c = 0; c < nm / 4; ++c) emit(0, 4, s, -1, g, m + (size_t)c * 4 * K, nullptr);
+            int at = (nm / 4) * 4;
+            if (nm - at >= 2) { twos.push_back(std::make_pair(s, m + (size_t)at * K)); at += 2; }
+            if (nm - at >= 1) ones.push_back(std::make_pair(s, m + (size_t)at * K));
         }
+        size_t k = 0;
+        if (dual_ok) for (; k + 1 < twos.size(); k += 2) emit(1, 4, twos[k].first, twos[k + 1].first, g, twos[k].second, twos[k + 1].second);
+        for (; k < twos.size(); ++k) emit(2, 2, twos[k].first, -1, g, twos[k].second, nullptr);
+        k = 0;
+        if (dual_ok) for (; k + 1 < ones.size(); k += 2) emit(3, 2, ones[k].first, ones[k + 1].first, g, ones[k].second, ones[k + 1].second);
+        for (; k < ones.size(); ++k) emit(4, 1, ones[k].first, -1, g, ones[k].second, nullptr);
+    }
+    const int cls_M[5] = {4, 4, 2, 2, 1};
+    for (const auto& kv : sec_items) {
+        EntryProgram::LaneSection sec;
+        sec.s_i = kv.first.s_a; sec.s_b = kv.first.s_b; sec.M = cls_M[kv.first.cls]; sec.rec0 = 0;
+        sec.n_rec = (uint32_t)(kv.second.size() / (size_t)lane_record_items(n, K, sec.M));
+        sec.chunk0 = (uint32_t)(e.lane_items.size() / 8);
+        sec.cost = (uint32_t)(n + sec.M * K + 2);
+        e.lane_items.insert(e.lane_items.end(), kv.second.begin(), kv.second.end());
+        e.lane_sections.push_back(sec);
+        e.lane_cost += (int64_t)sec.n_rec * sec.cost;
     }
     uint32_t rec0 = 0;
     for (auto& sec : e.lane_sections) { sec.rec0 = rec0; rec0 += sec.n_rec; }

@@ -86,7 +86,8 @@ struct EntryProgram {
     // (M, initial sector); a record is `order` Delta slots followed by M * K segment slots, 16 bits each (plain slot
     // numbers of the per-sample table), padded to a multiple of 8 items (one warp-uniform 128-bit load per 8 items:
     // the record stream shares the load pipe with the operand loads, so its width matters).
-    struct LaneSection { int32_t s_i, M; uint32_t rec0, n_rec; uint32_t chunk0, cost; };   // chunk0: first 128-bit word; cost per record
+    // s_b < 0: all M members of a record belong to initial sector s_i; else the first M / 2 to s_i, the others to s_b
+    struct LaneSection { int32_t s_i, s_b, M; uint32_t rec0, n_rec; uint32_t chunk0, cost; };   // chunk0: first 128-bit word; cost per record
     std::vector<LaneSection> lane_sections;
     std::vector<uint16_t> lane_items;
     std::vector<uint16_t> lane_segdef;     // [nSegL][seg_stride] propagator slots (0xFFFF = unused)

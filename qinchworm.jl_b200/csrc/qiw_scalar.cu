@@ -91,6 +91,78 @@ __device__ __forceinline__ typename Num<REAL>::T lane_dispatch(unsigned code, co
     return Num<REAL>::zero();
 }
 
+// Records shared by two initial sectors (LaneRun::z): the first M / 2 members are summed for sector a, the others for
+// sector b, and both sums take the record's product of pair-interaction operands, which is loaded once for the two.
+template <bool REAL> struct Acc2 { typename Num<REAL>::T a, b; };
+
+template <int ND, int K, int M, bool REAL>
+__device__ __noinline__ Acc2<REAL> lane_walk2(const uint4* rec, int n_rec, const unsigned char* Tl, unsigned row_bytes) {
+    typedef typename Num<REAL>::T T;
+    typedef Num<REAL> N;
+    constexpr int NI = ND + M * K, NC = (NI + 7) / 8, H = M / 2;
+    Acc2<REAL> acc;
+    acc.a = N::zero(); acc.b = N::zero();
+    uint4 nx[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) nx[c] = rec[c];
+    for (int r = 0; r < n_rec; ++r) {
+        uint32_t wd[NC * 4];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { wd[4 * c] = nx[c].x; wd[4 * c + 1] = nx[c].y; wd[4 * c + 2] = nx[c].z; wd[4 * c + 3] = nx[c].w; }
+        rec += NC;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) nx[c] = rec[c];
+        uint32_t it[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) it[i] = (i & 1) ? (wd[i >> 1] >> 16) : (wd[i >> 1] & 0xFFFFu);
+        T v[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) v[i] = *reinterpret_cast<const T*>(Tl + it[i] * row_bytes);
+        T sum[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            T sm = v[ND + h * H * K];
+#pragma unroll
+            for (int q = 1; q < K; ++q) sm = N::mul(sm, v[ND + h * H * K + q]);
+#pragma unroll
+            for (int m = 1; m < H; ++m) {
+                T s = v[ND + (h * H + m) * K];
+#pragma unroll
+                for (int q = 1; q < K; ++q) s = N::mul(s, v[ND + (h * H + m) * K + q]);
+                sm = N::add(sm, s);
+            }
+            sum[h] = sm;
+        }
+        if constexpr (ND > 0) {
+            T d = v[0];
+#pragma unroll
+            for (int f = 1; f < ND; ++f) d = N::mul(d, v[f]);
+            sum[0] = N::mul(d, sum[0]);
+            sum[1] = N::mul(d, sum[1]);
+        }
+        acc.a = N::add(acc.a, sum[0]);
+        acc.b = N::add(acc.b, sum[1]);
+    }
+    return acc;
+}
+
+template <bool REAL>
+__device__ __forceinline__ Acc2<REAL> lane_dispatch2(unsigned code, const uint4* rec, int n_rec, const unsigned char* Tl, unsigned row_bytes) {
+#define QIW_LW(D_, K_, MC_, M_) case (D_ * 16 + (K_ - 1) * 4 + MC_): return lane_walk2<D_, K_, M_, REAL>(rec, n_rec, Tl, row_bytes);
+#define QIW_LK(D_, K_) QIW_LW(D_, K_, 1, 2) QIW_LW(D_, K_, 2, 4)
+#define QIW_LD(D_) QIW_LK(D_, 1) QIW_LK(D_, 2) QIW_LK(D_, 3) QIW_LK(D_, 4)
+    switch (code) {
+        QIW_LD(0) QIW_LD(1) QIW_LD(2) QIW_LD(3) QIW_LD(4) QIW_LD(5) QIW_LD(6) QIW_LD(7) QIW_LD(8)
+        default: break;
+    }
+#undef QIW_LD
+#undef QIW_LK
+#undef QIW_LW
+    Acc2<REAL> z;
+    z.a = Num<REAL>::zero(); z.b = Num<REAL>::zero();
+    return z;
+}
+
 // ---- segment products: T[nP + nD + j][sample] = [coef_j *] prod_i T[def_j[i]][sample] ----------------
 // One warp per (table entry, 32 samples), lane = sample.  A definition is warp-uniform and arrives by one broadcast
 // 128-bit load: eight 16-bit fields — the folded coefficient's index (0xFFFF = none), then the propagator slots
@@ -371,7 +443,7 @@ __device__ __forceinline__ void phase_segments(const Cta<REAL>& c) {
 
 // -- 5. configuration sums: the job's work units are (sample sub-block of 32, chunk of the lane program); warp w takes
 //       units w, w + nw, ...  A chunk is a list of runs of records of equal shape and initial sector.
-template <bool REAL>
+template <bool REAL, bool DUAL>
 __device__ __forceinline__ void phase_walk(const Cta<REAL>& c, int S, double2* per_sample_out, unsigned long long local0,
                                            unsigned long long count) {
     typedef typename Num<REAL>::T T;
@@ -384,9 +456,17 @@ __device__ __forceinline__ void phase_walk(const Cta<REAL>& c, int S, double2* p
         const uint32_t run0 = c.chunk_off[c.chunk0 + ch], run1 = c.chunk_off[c.chunk0 + ch + 1];
         for (uint32_t k = run0; k < run1; ++k) {
             const LaneRun rn = c.runs[k];
-            T acc = lane_dispatch<REAL>(rn.w, c.items + rn.x, (int)rn.y, c.Tb + col, c.row_bytes);
-            if (!lane_on) acc = N::zero();
-            const int s = (int)rn.z;
+            // s2 >= 0: records shared by two sectors (only in the DUAL instantiations of the kernels: programs without
+            // such records run the kernels that do not carry the code for them)
+            const int s = (int)(rn.z & 0xFFu), s2 = DUAL ? (int)(rn.z >> 8) - 1 : -1;
+            T acc, acc2 = N::zero();
+            if (DUAL && s2 >= 0) {
+                const Acc2<REAL> pr = lane_dispatch2<REAL>(rn.w, c.items + rn.x, (int)rn.y, c.Tb + col, c.row_bytes);
+                acc = pr.a; acc2 = pr.b;
+            } else {
+                acc = lane_dispatch<REAL>(rn.w, c.items + rn.x, (int)rn.y, c.Tb + col, c.row_bytes);
+            }
+            if (!lane_on) { acc = N::zero(); acc2 = N::zero(); }
             if (per_sample_out) {
                 // qiw_eval_at_times: the evaluator's value for every sample separately (REAL: value = i * acc)
                 const unsigned long long smp = local0 + (unsigned long long)(sub * 32 + c.lane);
@@ -394,14 +474,28 @@ __device__ __forceinline__ void phase_walk(const Cta<REAL>& c, int S, double2* p
                     double2* o = per_sample_out + smp * S + s;
                     if constexpr (REAL) atomicAdd(&o->y, acc);
                     else { atomicAdd(&o->x, acc.x); atomicAdd(&o->y, acc.y); }
+                    if (s2 >= 0) {
+                        double2* o2 = per_sample_out + smp * S + s2;
+                        if constexpr (REAL) atomicAdd(&o2->y, acc2);
+                        else { atomicAdd(&o2->x, acc2.x); atomicAdd(&o2->y, acc2.y); }
+                    }
                 }
             } else {
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) acc = N::add(acc, N::shfl_down(acc, off));
+                if (s2 >= 0) {
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) acc2 = N::add(acc2, N::shfl_down(acc2, off));
+                }
                 if (c.lane == 0) {
                     double2& r = c.red[s * c.nw + c.warp];
                     if constexpr (REAL) r.y += acc;
                     else r = cadd(r, acc);
+                    if (s2 >= 0) {
+                        double2& r2 = c.red[s2 * c.nw + c.warp];
+                        if constexpr (REAL) r2.y += acc2;
+                        else r2 = cadd(r2, acc2);
+                    }
                 }
             }
         }
@@ -411,7 +505,7 @@ __device__ __forceinline__ void phase_walk(const Cta<REAL>& c, int S, double2* p
 // ---- the step kernel ---------------------------------------------------------------------------------
 // CTA = (work item: entry + up to nw chunks of its lane program, sample blocks blockIdx.x, blockIdx.x + gridDim.x, ...
 // [, time triple / Sobol sequence blockIdx.z]).
-template <bool REAL>
+template <bool REAL, bool DUAL>
 __global__ void __launch_bounds__(768, 1) scalar_step_kernel(const StepParams p) {
     typedef typename Num<REAL>::T T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -500,7 +594,7 @@ __global__ void __launch_bounds__(768, 1) scalar_step_kernel(const StepParams p)
         phase_segments<REAL>(c);
         __syncthreads();
         if (trace && threadIdx.x == 0) trace[1] = clock64();
-        phase_walk<REAL>(c, S, p.per_sample_out, local0, count);
+        phase_walk<REAL, DUAL>(c, S, p.per_sample_out, local0, count);
         __syncthreads();
         if (trace && threadIdx.x == 0) trace[2] = clock64();
     }
@@ -548,7 +642,7 @@ __global__ void __launch_bounds__(768, 1) scalar_step_kernel(const StepParams p)
 // adds the peers' block sums from its GPU's mailbox in rank order, and applies set_ppgf! + normalize!
 // (src/ppgf.jl:495-504,646-668) to its own copy of P.  CTA 0 sends this rank's sums to the peers and keeps the global
 // P table and the per-order history up to date.
-template <bool REAL>
+template <bool REAL, bool DUAL>
 __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) {
     typedef typename Num<REAL>::T T;
     typedef Num<REAL> N;
@@ -722,7 +816,7 @@ __global__ void __launch_bounds__(384, 2) scalar_run_kernel(const RunParams rp) 
             phase_segments<REAL>(c);
             __syncthreads();
             if (jj == jb0) { QIW_RT(3) }
-            phase_walk<REAL>(c, S, nullptr, local0, count);
+            phase_walk<REAL, DUAL>(c, S, nullptr, local0, count);
             __syncthreads();
             if (jj == jb0) { QIW_RT(4) }
             if (c.warp == 0) {
@@ -900,10 +994,10 @@ static cudaError_t optin_smem(K kernel, unsigned long long* mask) {
     return cudaSuccess;
 }
 
-template <bool REAL>
+template <bool REAL, bool DUAL>
 static cudaError_t launch_scalar_t(const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
     static unsigned long long attr_mask = 0ull;
-    cudaError_t e = optin_smem(scalar_step_kernel<REAL>, &attr_mask);
+    cudaError_t e = optin_smem(scalar_step_kernel<REAL, DUAL>, &attr_mask);
     if (e != cudaSuccess) return e;
     // programmatic dependent launch: consecutive step kernels of a stream may overlap prologue and tail
     cudaLaunchConfig_t cfg = {};
@@ -912,41 +1006,43 @@ static cudaError_t launch_scalar_t(const StepParams& p, dim3 grid, int threads, 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = p.allow_overlap ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, scalar_step_kernel<REAL>, p);
+    return cudaLaunchKernelEx(&cfg, scalar_step_kernel<REAL, DUAL>, p);
 }
 
 // `real_mode`: every table and coefficient in use has been verified purely imaginary by the host.
-cudaError_t launch_scalar_step(bool real_mode, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    return real_mode ? launch_scalar_t<true>(p, grid, threads, smem, st) : launch_scalar_t<false>(p, grid, threads, smem, st);
+// `dual`: some entry of the launch has records shared by two initial sectors (LaneRun::z).
+cudaError_t launch_scalar_step(bool real_mode, bool dual, const StepParams& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    if (dual) return real_mode ? launch_scalar_t<true, true>(p, grid, threads, smem, st) : launch_scalar_t<false, true>(p, grid, threads, smem, st);
+    return real_mode ? launch_scalar_t<true, false>(p, grid, threads, smem, st) : launch_scalar_t<false, false>(p, grid, threads, smem, st);
 }
 
-template <bool REAL>
+template <bool REAL, bool DUAL>
 static cudaError_t launch_run_t(const RunParams& rp, int n_ctas, int threads, size_t smem, cudaStream_t st) {
     static unsigned long long attr_mask = 0ull;
-    cudaError_t e = optin_smem(scalar_run_kernel<REAL>, &attr_mask);
+    cudaError_t e = optin_smem(scalar_run_kernel<REAL, DUAL>, &attr_mask);
     if (e != cudaSuccess) return e;
     void* args[] = {(void*)&rp};
-    return cudaLaunchCooperativeKernel((const void*)scalar_run_kernel<REAL>, dim3((unsigned)n_ctas), dim3((unsigned)threads), args, smem, st);
+    return cudaLaunchCooperativeKernel((const void*)scalar_run_kernel<REAL, DUAL>, dim3((unsigned)n_ctas), dim3((unsigned)threads), args, smem, st);
 }
 
-cudaError_t launch_scalar_run(bool real_mode, const RunParams& rp, int n_ctas, int threads, size_t smem, cudaStream_t st) {
-    return real_mode ? launch_run_t<true>(rp, n_ctas, threads, smem, st) : launch_run_t<false>(rp, n_ctas, threads, smem, st);
+cudaError_t launch_scalar_run(bool real_mode, bool dual, const RunParams& rp, int n_ctas, int threads, size_t smem, cudaStream_t st) {
+    if (dual) return real_mode ? launch_run_t<true, true>(rp, n_ctas, threads, smem, st) : launch_run_t<false, true>(rp, n_ctas, threads, smem, st);
+    return real_mode ? launch_run_t<true, false>(rp, n_ctas, threads, smem, st) : launch_run_t<false, false>(rp, n_ctas, threads, smem, st);
 }
 
 // CTAs of the run kernel that can be co-resident on the device (cooperative launch limit).
-int scalar_run_max_ctas(bool real_mode, int threads, size_t smem, int n_sm) {
-    static unsigned long long m1 = 0ull, m0 = 0ull;
+template <bool REAL, bool DUAL>
+static int run_max_ctas_t(int threads, size_t smem, int n_sm) {
+    static unsigned long long mask = 0ull;
     int per_sm = 0;
-    cudaError_t e;
-    if (real_mode) {
-        if (optin_smem(scalar_run_kernel<true>, &m1) != cudaSuccess) return 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scalar_run_kernel<true>, threads, smem);
-    } else {
-        if (optin_smem(scalar_run_kernel<false>, &m0) != cudaSuccess) return 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scalar_run_kernel<false>, threads, smem);
-    }
-    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (optin_smem(scalar_run_kernel<REAL, DUAL>, &mask) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scalar_run_kernel<REAL, DUAL>, threads, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     return per_sm * n_sm;
+}
+
+int scalar_run_max_ctas(bool real_mode, bool dual, int threads, size_t smem, int n_sm) {
+    if (dual) return real_mode ? run_max_ctas_t<true, true>(threads, smem, n_sm) : run_max_ctas_t<false, true>(threads, smem, n_sm);
+    return real_mode ? run_max_ctas_t<true, false>(threads, smem, n_sm) : run_max_ctas_t<false, false>(threads, smem, n_sm);
 }
 
 }  // namespace qiw

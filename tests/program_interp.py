@@ -87,13 +87,21 @@ def run_lane_program(lp, prog, expansion, payload, mode, t_i, t_w, t_f, times):
     K, n = lp["K"], lp["order"]
     out = np.zeros(prog["S"], dtype=complex)
     n_members = 0
-    for s_i, M, n_rec, item0 in lp["sections"]:
+    for s_code, M, n_rec, item0 in lp["sections"]:
+        # s_code = sector a | (sector b + 1) << 8: with a second sector, the first M / 2 members of a record belong to
+        # sector a and the others to sector b (the pair-interaction operands are shared)
+        s_a, s_b = int(s_code) & 0xFF, (int(s_code) >> 8) - 1
         ni = (n + M * K + 7) // 8 * 8
         for r in range(n_rec):
             it = lp["items"][item0 + r * ni: item0 + (r + 1) * ni]
             d = np.prod([T[int(q)] for q in it[:n]]) if n else 1.0
-            sm = sum(np.prod([T[int(q)] for q in it[n + m * K: n + (m + 1) * K]]) for m in range(M))
-            out[s_i] += d * sm
+            prods = [np.prod([T[int(q)] for q in it[n + m * K: n + (m + 1) * K]]) for m in range(M)]
+            if s_b < 0:
+                out[s_a] += d * sum(prods)
+            else:
+                assert M in (2, 4)
+                out[s_a] += d * sum(prods[:M // 2])
+                out[s_b] += d * sum(prods[M // 2:])
             n_members += M
     return out, n_members
 

@@ -456,9 +456,9 @@ def test_randomised_sequences_in_one_launch(gpu_ctx, qlib, oracle_lib):
 
 @pytest.mark.parametrize("arith", ["real", "complex"])
 def test_paired_records(gpu_ctx, qlib, oracle_lib, monkeypatch, arith):
-    """The paired form of the configuration records (shared pair-interaction operands; default from order 5 on)
+    """Records shared by two initial sectors (one set of pair-interaction operands for both; default from order 5 on)
     forced on for every order, in both arithmetic modes, bold + bare + correlator, plus one genuine order-5 entry."""
-    monkeypatch.setenv("QIW_PAIR_MIN_ORDER", "1")
+    monkeypatch.setenv("QIW_LANE_DUAL", "1")
     if arith == "complex":
         monkeypatch.setenv("QIW_FORCE_COMPLEX", "1")
     ex, grid, f = models.anderson(n_tau=30, corr=True)
@@ -488,6 +488,7 @@ def test_paired_records(gpu_ctx, qlib, oracle_lib, monkeypatch, arith):
         assert relerr(got, ref) < RTOL, (mode, relerr(got, ref))
     lp = gpu_ctx.entry_lane_program(ids[-1])
     assert len(lp["sections"]) > 0 and any(M == 4 for _, M, _, _ in lp["sections"])
+    assert any(int(sc) >> 8 and M == 4 for sc, M, _, _ in lp["sections"]) and any(int(sc) >> 8 and M == 2 for sc, M, _, _ in lp["sections"])
 
 
 @pytest.mark.parametrize("spline", [True, False])

@@ -87,10 +87,14 @@ def test_partitioning(qlib, oracle_lib):
             assert tot == N
 
 
+@pytest.mark.parametrize("shared", ["0", "1"])
 @pytest.mark.parametrize("model", ["anderson", "single_level", "dimer"])
-def test_compiled_programs_replay_to_oracle(qlib, oracle_lib, model):
-    """qiw_set_topologies (host compiler) vs the oracle's recursive evaluator, all three modes."""
+def test_compiled_programs_replay_to_oracle(qlib, oracle_lib, model, shared, monkeypatch):
+    """qiw_set_topologies (host compiler) vs the oracle's recursive evaluator, all three modes; the lane program both
+    without and with records shared by two initial sectors (QIW_LANE_DUAL; the default turns them on at order 5)."""
     from qinchworm_b200.expansion import add_corr_operators
+    monkeypatch.setenv("QIW_LANE_DUAL", shared)
+    n_shared = 0
     rng = np.random.default_rng(11)
     if model == "anderson":
         ex, grid, f = models.anderson(n_tau=30, corr=True)
@@ -144,6 +148,8 @@ def test_compiled_programs_replay_to_oracle(qlib, oracle_lib, model):
                     got2 = np.array([run_records(rec, prog, ex, pl, mode, t_i, t_w, t_f, times[i]) for i in range(2)])
                     assert np.abs(got2 - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1e-300)
                     lp = ctx.entry_lane_program(eid)   # ... and the lane program the step kernel executes (lane = sample)
+                    n_shared += sum(int(n) for sc, _, n, _ in lp["sections"] if int(sc) >> 8)
+                    assert shared == "1" or all(int(sc) >> 8 == 0 for sc, _, _, _ in lp["sections"])
                     res3 = [run_lane_program(lp, prog, ex, pl, mode, t_i, t_w, t_f, times[i]) for i in range(2)]
                     assert all(nm == lv for _, nm in res3)
                     got3 = np.array([r for r, _ in res3])
@@ -151,6 +157,7 @@ def test_compiled_programs_replay_to_oracle(qlib, oracle_lib, model):
                     assert st["n_leaves"] == lv and st["flops_per_sample"] == fl and st["n_top"] == len(pa)
                     eid += 1
     assert eid > 10
+    assert shared == "0" or model == "single_level" or n_shared > 0      # (two sectors that never share a Delta set there)
 
 
 @pytest.mark.parametrize("unit_cost", [None, "150"])
