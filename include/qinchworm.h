@@ -164,7 +164,10 @@ int qiw_entry_records(qiw_context* ctx, int32_t entry_id, int32_t* info, uint32_
  *     record value = prod(T[Delta slots]) * sum_members prod(T[segment slots of the member])
  * with every member's coefficient folded into its first segment product.  Call with NULL arrays to get the sizes.
  *   info[8]             : n_sections, n_items, nSegL, seg_stride, K, order, first slot of the segment table, cost
- *   sections[n_sections][4] : initial sector, M, number of records, first item
+ *   sections[n_sections][4] : sector code, M, number of records, first item; sector code = initial sector a |
+ *                         (sector b + 1) << 8: with a second sector (records shared by two initial sectors, from
+ *                         order 5 on; QIW_LANE_DUAL=0 / 1 overrides) the first M / 2 members of a record are summed
+ *                         for sector a and the others for sector b, the Delta operands being loaded once for both
  *   items[n_items]      : per record `order` Delta slots, then M * K segment slots, padded to a multiple of 8
  *   segdef[nSegL][seg_stride] : propagator slots of every segment product (0xFFFF = unused)
  *   seg_coef[nSegL]     : index of the coefficient folded into the product (0xFFFF = none) */
