@@ -205,7 +205,6 @@ class _PreparedStep:
             self.onehot[self.orders.index(td.order), j] = 1.0
         # the std of a single sequence is NaN (src/randomization.jl:99), of the exact order-0 entries 0 (src/inchworm.jl:155)
         self.std = {o: np.full(ctx.bsize, 0.0 if o == 0 else np.nan, dtype=complex) for o in self.orders}
-        self.N = top_data[0].N_samples
 
 
 def _step(solver: Solver, t_i, t_w, t_f, top_data):
@@ -214,11 +213,12 @@ def _step(solver: Solver, t_i, t_w, t_f, top_data):
         key = tuple(td.entry_id for td in top_data)
         ps = solver._steps.get(key)
         if ps is None:
-            assert all(td.N_samples == top_data[0].N_samples for td in top_data)
             ps = solver._steps[key] = _PreparedStep(solver.ctx, top_data)
-        solver.ctx.eval_prepared(t_i, t_w, t_f, ps.n, ps.ids_ptr, ps.N, ps.out_ptr)
+        N = top_data[0].N_samples       # (not cached: a Solver reuses compiled entries across calls with other sample counts)
+        assert all(td.N_samples == N for td in top_data)
+        solver.ctx.eval_prepared(t_i, t_w, t_f, ps.n, ps.ids_ptr, N, ps.out_ptr)
         sums = (ps.onehot @ ps.out_real).view(np.complex128)          # [n_orders, bsize], a fresh array
-        return sums.sum(axis=0), {o: sums[q] for q, o in enumerate(ps.orders)}, ps.std
+        return sums.sum(axis=0), {o: sums[q] for q, o in enumerate(ps.orders)}, {o: v.copy() for o, v in ps.std.items()}
     mean, std = solver.eval_entries(t_i, t_w, t_f, top_data)
     return _order_sums(top_data, mean, std, solver.ctx.bsize)
 

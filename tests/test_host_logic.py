@@ -350,6 +350,11 @@ def test_host_stepped_step_bookkeeping(qlib):
     total_b, contribs_b, _ = inchworm_step(solver, grid, 0, 4, 5, top)
     assert np.allclose(total_b, 2.0 * t2) and np.allclose(total, t2)
     assert len(solver._steps) == 1
+    # the same compiled entries with another sample count (a Solver is reused across calls): the count of THIS call travels
+    top2 = _bold_entries(solver, range(0, 4), 256, None, None)
+    assert [td.entry_id for td in top2] == [td.entry_id for td in top]
+    inchworm_step(solver, grid, 0, 4, 5, top2)
+    assert seen["args"][4] == 256 and len(solver._steps) == 1
     # a randomised call takes the general path (it needs the GPU): only check that the fast path is not chosen
     assert RandomizationParams().rng is None and RandomizationParams().N_seqs == 1
     # normalize_at
