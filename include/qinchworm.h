@@ -165,7 +165,7 @@ int qiw_entry_records(qiw_context* ctx, int32_t entry_id, int32_t* info, uint32_
  * with every member's coefficient folded into its first segment product.  Call with NULL arrays to get the sizes.
  *   info[8]             : n_sections, n_items, nSegL, seg_stride, K, order, first slot of the segment table, cost
  *   sections[n_sections][4] : sector code, M, number of records, first item; sector code = initial sector a |
- *                         (sector b + 1) << 8: with a second sector (records shared by two initial sectors, from
+ *                         (sector b + 1) << 16: with a second sector (records shared by two initial sectors, from
  *                         order 5 on; QIW_LANE_DUAL=0 / 1 overrides) the first M / 2 members of a record are summed
  *                         for sector a and the others for sector b, the Delta operands being loaded once for both
  *   items[n_items]      : per record `order` Delta slots, then M * K segment slots, padded to a multiple of 8

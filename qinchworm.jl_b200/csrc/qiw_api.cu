@@ -781,7 +781,7 @@ int qiw_entry_lane_program(qiw_context* ctx, int32_t id, int32_t* info, int32_t*
     if (sections)
         for (size_t k = 0; k < p.lane_sections.size(); ++k) {
             const auto& sc = p.lane_sections[k];
-            sections[4 * k] = sc.s_i | ((sc.s_b + 1) << 8); sections[4 * k + 1] = sc.M; sections[4 * k + 2] = (int32_t)sc.n_rec; sections[4 * k + 3] = (int32_t)(sc.chunk0 * 8u);
+            sections[4 * k] = sc.s_i | ((sc.s_b + 1) << 16); sections[4 * k + 1] = sc.M; sections[4 * k + 2] = (int32_t)sc.n_rec; sections[4 * k + 3] = (int32_t)(sc.chunk0 * 8u);
         }
     if (items) for (size_t k = 0; k < p.lane_items.size(); ++k) items[k] = p.lane_items[k];
     if (segdef) memcpy(segdef, p.lane_segdef.data(), (size_t)p.nSegL * p.seg_stride * sizeof(uint16_t));
@@ -886,7 +886,7 @@ static void append_entry_chunks(const EntryProgram& p, int n_chunks, std::vector
             if (!last) take = (uint32_t)std::min<int64_t>(take, std::max<int64_t>(1, (target - done + sec.cost - 1) / sec.cost));
             const int ni = lane_record_items(p.order, p.K, sec.M) / 8;
             const uint32_t mc = sec.M == 1 ? 0u : (sec.M == 2 ? 1u : 2u);
-            runs.push_back(make_uint4(sec.chunk0 + r_in * (uint32_t)ni, take, (uint32_t)sec.s_i | ((uint32_t)(sec.s_b + 1) << 8),
+            runs.push_back(make_uint4(sec.chunk0 + r_in * (uint32_t)ni, take, (uint32_t)sec.s_i | ((uint32_t)(sec.s_b + 1) << 16),
                                       (uint32_t)(p.order * 16 + (p.K - 1) * 4) + mc));
             done += (int64_t)take * sec.cost;
             r_in += take;

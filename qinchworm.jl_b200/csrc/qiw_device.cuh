@@ -65,7 +65,7 @@ struct WorkItem {
 
 // A run of consecutive records of one section (same shape, same initial sector) inside a chunk.
 //   x = first 128-bit word of the run in DevEntry::lane_items, y = number of records,
-//   z = initial sector | (second sector + 1) << 8 (0: none; else the first M / 2 members of a record belong to the
+//   z = initial sector | (second sector + 1) << 16 (0: none; else the first M / 2 members of a record belong to the
 //       initial sector, the others to the second one), w = shape code: order * 16 + (K - 1) * 4 + (0, 1, 2 for M = 1, 2, 4)
 typedef uint4 LaneRun;
 

@@ -458,7 +458,7 @@ __device__ __forceinline__ void phase_walk(const Cta<REAL>& c, int S, double2* p
             const LaneRun rn = c.runs[k];
             // s2 >= 0: records shared by two sectors (only in the DUAL instantiations of the kernels: programs without
             // such records run the kernels that do not carry the code for them)
-            const int s = (int)(rn.z & 0xFFu), s2 = DUAL ? (int)(rn.z >> 8) - 1 : -1;
+            const int s = (int)(rn.z & 0xFFFFu), s2 = DUAL ? (int)(rn.z >> 16) - 1 : -1;
             T acc, acc2 = N::zero();
             if (DUAL && s2 >= 0) {
                 const Acc2<REAL> pr = lane_dispatch2<REAL>(rn.w, c.items + rn.x, (int)rn.y, c.Tb + col, c.row_bytes);

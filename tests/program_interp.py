@@ -88,9 +88,9 @@ def run_lane_program(lp, prog, expansion, payload, mode, t_i, t_w, t_f, times):
     out = np.zeros(prog["S"], dtype=complex)
     n_members = 0
     for s_code, M, n_rec, item0 in lp["sections"]:
-        # s_code = sector a | (sector b + 1) << 8: with a second sector, the first M / 2 members of a record belong to
+        # s_code = sector a | (sector b + 1) << 16: with a second sector, the first M / 2 members of a record belong to
         # sector a and the others to sector b (the pair-interaction operands are shared)
-        s_a, s_b = int(s_code) & 0xFF, (int(s_code) >> 8) - 1
+        s_a, s_b = int(s_code) & 0xFFFF, (int(s_code) >> 16) - 1
         ni = (n + M * K + 7) // 8 * 8
         for r in range(n_rec):
             it = lp["items"][item0 + r * ni: item0 + (r + 1) * ni]

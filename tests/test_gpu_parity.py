@@ -488,7 +488,7 @@ def test_paired_records(gpu_ctx, qlib, oracle_lib, monkeypatch, arith):
         assert relerr(got, ref) < RTOL, (mode, relerr(got, ref))
     lp = gpu_ctx.entry_lane_program(ids[-1])
     assert len(lp["sections"]) > 0 and any(M == 4 for _, M, _, _ in lp["sections"])
-    assert any(int(sc) >> 8 and M == 4 for sc, M, _, _ in lp["sections"]) and any(int(sc) >> 8 and M == 2 for sc, M, _, _ in lp["sections"])
+    assert any(int(sc) >> 16 and M == 4 for sc, M, _, _ in lp["sections"]) and any(int(sc) >> 16 and M == 2 for sc, M, _, _ in lp["sections"])
 
 
 @pytest.mark.parametrize("spline", [True, False])

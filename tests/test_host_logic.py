@@ -148,8 +148,8 @@ def test_compiled_programs_replay_to_oracle(qlib, oracle_lib, model, shared, mon
                     got2 = np.array([run_records(rec, prog, ex, pl, mode, t_i, t_w, t_f, times[i]) for i in range(2)])
                     assert np.abs(got2 - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1e-300)
                     lp = ctx.entry_lane_program(eid)   # ... and the lane program the step kernel executes (lane = sample)
-                    n_shared += sum(int(n) for sc, _, n, _ in lp["sections"] if int(sc) >> 8)
-                    assert shared == "1" or all(int(sc) >> 8 == 0 for sc, _, _, _ in lp["sections"])
+                    n_shared += sum(int(n) for sc, _, n, _ in lp["sections"] if int(sc) >> 16)
+                    assert shared == "1" or all(int(sc) >> 16 == 0 for sc, _, _, _ in lp["sections"])
                     res3 = [run_lane_program(lp, prog, ex, pl, mode, t_i, t_w, t_f, times[i]) for i in range(2)]
                     assert all(nm == lv for _, nm in res3)
                     got3 = np.array([r for r, _ in res3])
