@@ -366,3 +366,32 @@ def test_host_stepped_step_bookkeeping(qlib):
     assert abs(lam - lam_ref) < 1e-14 * max(1.0, abs(lam_ref))
     assert np.allclose(ex.P, P0 * np.exp(-grid.tau * lam_ref)[:, None], rtol=1e-14, atol=0)
     assert abs(np.max(-ex.P[5, diag].imag) - 1.0) < 1e-13
+
+
+def test_order5_lane_program_shares_records_by_default(qlib, oracle_lib, monkeypatch):
+    """From order 5 on the lane program uses records shared by two initial sectors without being asked to
+    (QIW_LANE_DUAL unset); replayed on CPU against the oracle for one bold order-5 entry."""
+    monkeypatch.delenv("QIW_LANE_DUAL", raising=False)
+    rng = np.random.default_rng(5)
+    ex, grid, f = models.anderson(n_tau=30)
+    ex.P = ex.P * (1 + 0.1 * rng.random(ex.P.shape))
+    pl = ex.flatten()
+    ctx = qlib.Context(device=qlib.DEVICE_NONE)
+    ctx.set_expansion(ex)
+    o = oracle_lib.Oracle(pl, ex.P)
+    tau = grid.tau
+    for eid, (order, k) in enumerate([(4, 3), (5, 3)]):
+        pr, pa = qlib.topologies(order, k)
+        ctx.set_topologies(eid, qlib.MODE_BOLD, order, k, pr, pa)
+        o.set_topologies(eid, qlib.MODE_BOLD, order, k, pr, pa)
+        lp, prog = ctx.entry_lane_program(eid), ctx.entry_program(eid)
+        n_shared = sum(int(n) for sc, _, n, _ in lp["sections"] if int(sc) >> 16)
+        assert (n_shared > 0) == (order >= 5)
+        t_i, t_w, t_f = 0.0, tau[11], tau[12]
+        times = np.zeros((1, 2 * order))
+        times[0, :k] = np.sort(rng.uniform(t_w, t_f, k))[::-1]
+        times[0, k:] = np.sort(rng.uniform(t_i, t_w, 2 * order - k))[::-1]
+        ref = o.eval_at_times(eid, t_i, t_w, t_f, times)
+        got, n_members = run_lane_program(lp, prog, ex, pl, qlib.MODE_BOLD, t_i, t_w, t_f, times[0])
+        assert n_members == o.last_counts()[1]
+        assert np.abs(got - ref[0]).max() <= 1e-9 * np.abs(ref).max()
